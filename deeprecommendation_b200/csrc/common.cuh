@@ -1,0 +1,71 @@
+// Shared device/host helpers for libb200rec (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/b200rec.h"
+
+#define B200REC_CHECK_LAUNCH()                                   \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return b200rec_set_cuda_error(e__);  \
+  } while (0)
+
+#define B200REC_CUDA(call)                                       \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return b200rec_set_cuda_error(e__);  \
+  } while (0)
+
+int b200rec_set_cuda_error(cudaError_t e);          // api.cu: records the message, returns B200REC_ERR_CUDA
+int b200rec_fail(int code, const char* msg);        // api.cu: records msg, returns code
+
+static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// number of SMs of the current device (cached)
+int b200rec_num_sms();
+
+namespace b200rec {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// 128-bit read-only loads of 4 consecutive table elements as fp32 (tables are fp32 or bf16).
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  float4 o;
+  o.x = __uint_as_float(r.x << 16);
+  o.y = __uint_as_float(r.x & 0xffff0000u);
+  o.z = __uint_as_float(r.y << 16);
+  o.w = __uint_as_float(r.y & 0xffff0000u);
+  return o;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<unsigned*>(&a);
+  r.y = *reinterpret_cast<unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+}  // namespace b200rec

@@ -1,0 +1,235 @@
+// K3 — GraphNCF bipartite message passing as a row-owner CSR SpMM with symmetric degree normalisation and a
+// fused per-layer combine.
+//
+// Replaces PyG `propagate` + `message` + scatter-add of gnn_ncf.py:39-94 and the `stack`+`mean` of :351.
+// The reference transforms every EDGE (`W(x_j)` on an (E, d) tensor, :91-93) and scatter-adds with atomics;
+// here the Linear is applied once per NODE beforehand (K1a with row_scale = deg^-1/2 of the source), so a layer is
+//
+//   x_next[r] = dinv[r] * sum_{k in row r}  w[k] * t[col[k]]            t[s] = dinv[s] * (W_type x[s] + b_type)
+//   acc_out[r] = (acc_in[r] + x_next[r]) * acc_scale                    (running sum of hs; 1/(L+1) on the last layer)
+//
+// over the neighbour index built by K4 (edges stably sorted by destination, 8 bytes per edge: int32 source +
+// fp32 weight).  Rows are cut into chunks of <= CHUNK edges at graph-build time; one warp owns one chunk, so the
+// heavy-tailed MovieLens degrees (max ~81k) are edge-balanced.  Single-chunk rows are finished in the same
+// kernel; multi-chunk rows write per-chunk partials that a second tiny kernel adds IN CHUNK ORDER — no atomics,
+// bit-reproducible run to run (the reference's GPU scatter-add is not).  Each edge costs one coalesced 128-bit
+// load per lane of the source row (d=128 fp32: 512 B per edge; d=64: two edges per warp step).
+#include "common.cuh"
+
+namespace b200rec {
+
+constexpr int SPMM_WARPS = 8;
+
+struct SpmmParams {
+  const int* chunk_row;
+  const int* chunk_start;
+  const int* chunk_slot;     // -1: the row has a single chunk (direct epilogue); else index into `partials`
+  int n_chunks;
+  int chunk_size;
+  const int* row_ptr;
+  const int* col;
+  const float* w;            // per CSR entry, or null (binary graph: weight 1)
+  const int* perm;           // CSR entry -> position in the interactions file (for the skip bitmap)
+  const unsigned* skip_bits; // training: bit p set = interaction p is a target edge of this batch (masked out)
+  const void* t;             // (N, d) source features, fp32 or bf16
+  long long ld_t;
+  int d;
+  const float* dinv;         // per destination row, or null
+  float* partials;
+  float* x_next;             // nullable
+  long long ld_x;
+  const float* acc_in;       // nullable
+  float* acc_out;            // nullable
+  long long ld_acc;
+  float acc_scale;
+  // fix-up pass
+  const int* multi_row;
+  const int* multi_first_slot;
+  const int* multi_n_slots;
+  int n_multi;
+};
+
+template <int NV>
+__device__ __forceinline__ void row_epilogue(const SpmmParams& p, int row, int c0, int cstride, const float (&acc)[NV][4]) {
+  const float s = p.dinv ? __ldg(p.dinv + row) : 1.f;
+#pragma unroll
+  for (int nv = 0; nv < NV; ++nv) {
+    const int c = c0 + nv * cstride;
+    if (c < p.d) {
+      float4 v = make_float4(acc[nv][0] * s, acc[nv][1] * s, acc[nv][2] * s, acc[nv][3] * s);
+      if (p.x_next) st4(p.x_next + (long long)row * p.ld_x + c, v);
+      if (p.acc_out) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.acc_in) a = *reinterpret_cast<const float4*>(p.acc_in + (long long)row * p.ld_acc + c);
+        st4(p.acc_out + (long long)row * p.ld_acc + c,
+            make_float4((a.x + v.x) * p.acc_scale, (a.y + v.y) * p.acc_scale, (a.z + v.z) * p.acc_scale,
+                        (a.w + v.w) * p.acc_scale));
+      }
+    }
+  }
+}
+
+// G lanes cooperate on one edge (G*4*NV >= d); 32/G edges are in flight per warp step.
+template <int G, int NV, typename T>
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
+spmm_chunk_kernel(SpmmParams p) {
+  constexpr int EPW = 32 / G;                 // edges per warp step
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  if (chunk >= p.n_chunks) return;
+  const int g = lane / G, sl = lane % G;
+  const int row = __ldg(p.chunk_row + chunk);
+  const int s = __ldg(p.chunk_start + chunk);
+  const int e = min(s + p.chunk_size, __ldg(p.row_ptr + row + 1));
+  const T* __restrict__ t = reinterpret_cast<const T*>(p.t);
+
+  float acc[NV][4];
+#pragma unroll
+  for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[nv][q] = 0.f;
+
+  for (int k0 = s; k0 < e; k0 += 32) {
+    const int cnt = min(32, e - k0);
+    int c = -1;
+    float wv = 0.f;
+    if (lane < cnt) {
+      c = __ldg(p.col + k0 + lane);
+      wv = p.w ? __ldg(p.w + k0 + lane) : 1.f;
+      if (p.skip_bits) {
+        const int pos = __ldg(p.perm + k0 + lane);
+        if ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) { wv = 0.f; c = -1; }
+      }
+    }
+#pragma unroll
+    for (int st0 = 0; st0 < G; st0 += 8) {
+      if (st0 * EPW < cnt) {
+        float4 x[8][NV];
+        float ww[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int src_lane = (st0 + u) * EPW + g;
+          const int cc = __shfl_sync(FULL, c, src_lane);
+          ww[u] = __shfl_sync(FULL, wv, src_lane);
+#pragma unroll
+          for (int nv = 0; nv < NV; ++nv) {
+            const int cidx = sl * 4 + nv * G * 4;
+            x[u][nv] = (cc >= 0 && cidx < p.d) ? ld4(t + (long long)cc * p.ld_t + cidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int nv = 0; nv < NV; ++nv) {
+            acc[nv][0] = fmaf(ww[u], x[u][nv].x, acc[nv][0]);
+            acc[nv][1] = fmaf(ww[u], x[u][nv].y, acc[nv][1]);
+            acc[nv][2] = fmaf(ww[u], x[u][nv].z, acc[nv][2]);
+            acc[nv][3] = fmaf(ww[u], x[u][nv].w, acc[nv][3]);
+          }
+      }
+    }
+  }
+  // fold the 32/G edge lanes together (fixed order)
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[nv][q] += __shfl_xor_sync(FULL, acc[nv][q], o);
+
+  if (g == 0) {
+    const int slot = __ldg(p.chunk_slot + chunk);
+    if (slot < 0) {
+      row_epilogue<NV>(p, row, sl * 4, G * 4, acc);
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; ++nv) {
+        const int cidx = sl * 4 + nv * G * 4;
+        if (cidx < p.d) st4(p.partials + (long long)slot * p.d + cidx, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
+      }
+    }
+  }
+}
+
+// rows that were cut into several chunks: add the partials in chunk order, then the same epilogue
+template <int NV>
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
+spmm_fixup_kernel(SpmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  if (m >= p.n_multi) return;
+  const int row = __ldg(p.multi_row + m);
+  const int first = __ldg(p.multi_first_slot + m), n = __ldg(p.multi_n_slots + m);
+  float acc[NV][4];
+#pragma unroll
+  for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[nv][q] = 0.f;
+  for (int sidx = 0; sidx < n; ++sidx) {
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv) {
+      const int cidx = lane * 4 + nv * 128;
+      if (cidx < p.d) {
+        const float4 v = *reinterpret_cast<const float4*>(p.partials + (long long)(first + sidx) * p.d + cidx);
+        acc[nv][0] += v.x; acc[nv][1] += v.y; acc[nv][2] += v.z; acc[nv][3] += v.w;
+      }
+    }
+  }
+  row_epilogue<NV>(p, row, lane * 4, 128, acc);
+}
+
+template <typename T>
+static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+  const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
+  if (p.n_chunks > 0) {
+    if (p.d <= 32) spmm_chunk_kernel<8, 1, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    else if (p.d <= 64) spmm_chunk_kernel<16, 1, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    else if (p.d <= 128) spmm_chunk_kernel<32, 1, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    else if (p.d <= 256) spmm_chunk_kernel<32, 2, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    else if (p.d <= 512) spmm_chunk_kernel<32, 4, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    else return b200rec_fail(B200REC_ERR_UNSUPPORTED, "spmm: node_emb wider than 512");
+    B200REC_CHECK_LAUNCH();
+  }
+  if (p.n_multi > 0) {
+    const int g2 = ceil_div_i(p.n_multi, SPMM_WARPS);
+    if (p.d <= 128) spmm_fixup_kernel<1><<<g2, SPMM_WARPS * 32, 0, st>>>(p);
+    else if (p.d <= 256) spmm_fixup_kernel<2><<<g2, SPMM_WARPS * 32, 0, st>>>(p);
+    else spmm_fixup_kernel<4><<<g2, SPMM_WARPS * 32, 0, st>>>(p);
+    B200REC_CHECK_LAUNCH();
+  }
+  return B200REC_OK;
+}
+
+}  // namespace b200rec
+
+using namespace b200rec;
+
+extern "C" int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream) {
+  if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: null descriptor");
+  if (a->d <= 0 || (a->d % 4) || a->n_chunks < 0 || a->n_multi < 0 || a->chunk_size <= 0)
+    return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: d must be a positive multiple of 4");
+  if (a->n_chunks == 0) return B200REC_OK;
+  if (!a->chunk_row || !a->chunk_start || !a->chunk_slot || !a->row_ptr || !a->col || !a->t)
+    return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: null index / feature pointer");
+  if (a->n_multi > 0 && (!a->partials || !a->multi_row || !a->multi_first_slot || !a->multi_n_slots))
+    return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: multi-chunk rows need partials + lists");
+  if (a->skip_bits && !a->perm) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: skip bitmap needs perm");
+  const int esz = a->t_dtype == B200REC_BF16 ? 2 : 4;
+  if ((uintptr_t)a->t % (4 * esz) || (a->ld_t % 4) || (a->x_next && ((uintptr_t)a->x_next % 16 || a->ld_x % 4)) ||
+      (a->acc_out && ((uintptr_t)a->acc_out % 16 || a->ld_acc % 4)) || (a->acc_in && (uintptr_t)a->acc_in % 16) ||
+      (a->partials && (uintptr_t)a->partials % 16))
+    return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: feature pointers / leading dims must allow 128-bit access");
+  SpmmParams p;
+  p.chunk_row = a->chunk_row; p.chunk_start = a->chunk_start; p.chunk_slot = a->chunk_slot;
+  p.n_chunks = a->n_chunks; p.chunk_size = a->chunk_size;
+  p.row_ptr = a->row_ptr; p.col = a->col; p.w = a->w; p.perm = a->perm; p.skip_bits = a->skip_bits;
+  p.t = a->t; p.ld_t = a->ld_t; p.d = a->d; p.dinv = a->dinv; p.partials = a->partials;
+  p.x_next = a->x_next; p.ld_x = a->ld_x; p.acc_in = a->acc_in; p.acc_out = a->acc_out; p.ld_acc = a->ld_acc;
+  p.acc_scale = a->acc_scale;
+  p.multi_row = a->multi_row; p.multi_first_slot = a->multi_first_slot; p.multi_n_slots = a->multi_n_slots;
+  p.n_multi = a->n_multi;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->t_dtype == B200REC_F32) return launch_spmm<float>(p, st);
+  if (a->t_dtype == B200REC_BF16) return launch_spmm<__nv_bfloat16>(p, st);
+  return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: bad t_dtype");
+}

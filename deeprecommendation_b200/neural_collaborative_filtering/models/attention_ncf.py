@@ -1,0 +1,120 @@
+"""AttentionNCF on the B200 path (reference: neural_collaborative_filtering/models/attention_ncf.py:64-224)."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from ... import _lib as L
+from ... import ops
+from ..util import build_MLP_layers, run_mlp
+from .base import NCF, _named_like
+
+
+def _pad_rows(w, b, mult=4):
+    """Zero-pads the output rows of a Linear to a multiple of `mult` (the pooling kernel loads 128-bit rows)."""
+    n = w.shape[0]
+    extra = (-n) % mult
+    if extra == 0:
+        return w, b
+    w = torch.cat((w, w.new_zeros(extra, w.shape[1])), 0)
+    if b is not None:
+        b = torch.cat((b, b.new_zeros(extra)), 0)
+    return w, b
+
+
+class AttentionNCF(NCF):
+    """The user profile is built on the fly from the user's rated items with item-item attention against the candidate
+    (attention_ncf.py:136-224).  Device pipeline per call:
+
+      K1a  Ec = ItemEmb(candidate)                         (B, E)
+      K1a  [Er | Q] = rated_items · [W_I ; W_U]ᵀ           one pass over the (I, F) profiles feeds both the item
+                                                           embedding and the pooled-profile projection Q = R·W_Uᵀ
+      K1a  Pc = Ec·A1cᵀ + a1,  Pr = Er·A1rᵀ                AttentionNet.0 split into candidate / rated halves
+      K2   user_emb = Σ_i softmax_i(a2·ReLU(Pc+Pr_i)+a20)·um_bi·Q_i + b_U     ragged, one warp per candidate
+      K1b  out = MLP([Ec, user_emb])                       item first (attention_ncf.py:219)
+
+    Nothing of shape (B·I, E) or (B, I, ·) is ever materialised (the reference builds two of them, :154-155)."""
+
+    def __init__(self, item_dim, item_emb=128, user_emb=128, att_dense=None, mlp_dense_layers=None, use_cos_sim_instead=False,
+                 dropout_rate=0.2, message_dropout=None):
+        super().__init__()
+        mlp_dense_layers = [256, 128] if mlp_dense_layers is None else mlp_dense_layers
+        self.kwargs = dict(item_dim=item_dim, item_emb=item_emb, user_emb=user_emb, att_dense=att_dense,
+                           mlp_dense_layers=mlp_dense_layers, dropout_rate=dropout_rate,
+                           use_cos_sim_instead=use_cos_sim_instead, message_dropout=message_dropout)
+        self.use_cos_sim_instead, self.message_dropout = use_cos_sim_instead, message_dropout
+        self.ItemEmbeddings = nn.Sequential(nn.Linear(item_dim, item_emb))
+        self.UserEmbeddings = nn.Sequential(nn.Linear(item_dim, user_emb))
+        if not use_cos_sim_instead:
+            self.att_dense = att_dense if att_dense is not None else 0
+            if att_dense is not None:
+                self.AttentionNet = nn.Sequential(nn.Linear(2 * item_emb, att_dense), nn.ReLU(), nn.Dropout(dropout_rate),
+                                                  nn.Linear(att_dense, 1))
+            else:
+                self.AttentionNet = nn.Sequential(nn.Linear(2 * item_emb, 1))
+        self.MLP = build_MLP_layers(item_emb + user_emb, mlp_dense_layers, dropout_rate=dropout_rate)
+
+    def important_hypeparams(self) -> str:
+        return '_cosine' if self.use_cos_sim_instead else f'_attNet{self.att_dense}'
+
+    def is_dataset_compatible(self, dataset_class):
+        return _named_like(dataset_class, 'DynamicPointwiseDataset', 'DynamicRankingDataset')
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _score_tables(self, Ec, Er):
+        """(Pc, Pr, mode, a2, a20) for the three scoring variants (attention_ncf.py:162-179)."""
+        E = Ec.shape[1]
+        if self.use_cos_sim_instead:                               # <normalize(Ec_b), normalize(Er_i)>  (:163-173)
+            Pc = torch.nn.functional.normalize(Ec, p=2, dim=1)
+            Pr = torch.nn.functional.normalize(Er, p=2, dim=1)
+            pad = (-E) % 4
+            if pad:
+                Pc, Pr = torch.nn.functional.pad(Pc, (0, pad)), torch.nn.functional.pad(Pr, (0, pad))
+            return Pc, Pr.contiguous(), L.ATT_DOT, None, None
+        first = self.AttentionNet[0]
+        if len(self.AttentionNet) > 1:                             # Linear(2E,H) ReLU Dropout Linear(H,1)  (:112-117)
+            head = self.AttentionNet[3]
+            A1, a1 = _pad_rows(first.weight, first.bias)
+            a2 = head.weight.view(-1)
+            if a2.shape[0] != A1.shape[0]:
+                a2 = torch.cat((a2, a2.new_zeros(A1.shape[0] - a2.shape[0])))
+            Pc = ops.linear(Ec, A1[:, :E], a1)                     # candidate half first (:176)
+            Pr = ops.linear(Er, A1[:, E:], None)
+            return Pc, Pr, L.ATT_NET, a2, head.bias
+        # att_dense=None: a single Linear(2E, 1): s = A_c·Ec_b + A_r·Er_i + a0 = <[sc,1,0,0], [1,sr,0,0]>  (:120-122)
+        sc = ops.linear(Ec, first.weight[:, :E], first.bias)       # (B, 1)
+        sr = ops.linear(Er, first.weight[:, E:], None)             # (I, 1)
+        Pc = torch.cat((sc, torch.ones_like(sc), torch.zeros_like(sc), torch.zeros_like(sc)), 1)
+        Pr = torch.cat((torch.ones_like(sr), sr, torch.zeros_like(sr), torch.zeros_like(sr)), 1)
+        return Pc, Pr, L.ATT_DOT, None, None
+
+    def forward(self, candidate_items, rated_items, user_matrix, return_attention_weights=False):
+        item, user = self.ItemEmbeddings[0], self.UserEmbeddings[0]
+        E, U = item.weight.shape[0], user.weight.shape[0]
+        Ec = ops.linear(candidate_items, item.weight, item.bias)                        # :150
+        WU, bU = _pad_rows(user.weight, user.bias)
+        # one sweep over rated_items: item embedding (:151) and Q = rated_items·W_Uᵀ (pooling moved into embedding space:
+        # W_U(Σ α·um·R_i) = Σ α·um·(W_U R_i), :213+:216)
+        Wcat = torch.cat((item.weight, WU), 0)
+        bcat = torch.cat((item.bias, torch.zeros_like(bU)), 0)
+        ErQ = ops.linear(rated_items, Wcat, bcat)
+        Er, Q = ErQ[:, :E], ErQ[:, E:]
+        Pc, Pr, mode, a2, a20 = self._score_tables(Ec, Er)
+
+        um, scale, drop_zero, train_mask = user_matrix, 1.0, False, None
+        if self.training:
+            if self.message_dropout is not None:                                        # :185-189
+                drop_zero = True
+                if self.message_dropout > 0.0:
+                    keep = torch.rand_like(um) >= self.message_dropout
+                    um = um * keep                   # a dropped pair gets -inf, i.e. behaves like "unrated"
+                    scale = 1.0 / (1.0 - self.message_dropout)
+            train_mask = (Ec, Er, 1e-5, 1e-5)                                           # isclose(atol=1e-5) (:199)
+        res = ops.attention_pool(Pc, Pr, Q, mode=mode, a2=a2, a20=a20,
+                                 bU=bU, user_matrix=um, return_attention_weights=return_attention_weights,
+                                 train_mask=train_mask, drop_zero_scores=drop_zero, score_scale=scale)
+        user_emb, att = res if return_attention_weights else (res, None)
+        if user_emb.shape[1] != U:
+            user_emb = user_emb[:, :U]
+        out = run_mlp(self.MLP, Ec, user_emb, training=self.training)                   # :219-222
+        return (out, att.detach()) if return_attention_weights else out

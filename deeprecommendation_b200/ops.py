@@ -1,0 +1,413 @@
+"""Tensor-level wrappers over the C ABI (include/b200rec.h) + autograd glue.
+
+PyTorch is plumbing here: device memory, streams and autograd bookkeeping.  Every forward op launches
+hand-written sm_100a kernels from libb200rec.so on the caller's current CUDA stream.  There is no CPU
+path: tensors must live on a CUDA device.
+
+Backward passes (training is row (f)-1 "next" in SURVEY.md §8): the SpMM backward runs the same CUDA
+kernel on the transposed weights; Linear / MLP-tower / attention-pool backward recompute with torch
+CUDA ops for now (documented in DESIGN.md §7).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('deeprecommendation_b200 runs on CUDA (sm_100a) only; got a CPU tensor and there is no CPU fallback')
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _row_major(t: torch.Tensor):
+    """Returns (tensor, leading dimension) for a 2-D fp32 tensor usable without a copy when rows are contiguous."""
+    if t.dim() != 2:
+        raise ValueError('expected a 2-D tensor')
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    ld = t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+    return t, ld
+
+
+def _dtype_code(dt):
+    if dt == torch.float32:
+        return L.F32
+    if dt == torch.bfloat16:
+        return L.BF16
+    raise ValueError(f'unsupported dtype {dt}')
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K1a linear
+# ------------------------------------------------------------------------------------------------------------------
+def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_dtype=torch.float32):
+    """out = act((x @ weight.T + bias) * row_scale[:, None]) — b200rec_linear."""
+    _require_cuda(x, weight, bias, row_scale, out)
+    x, ldx = _row_major(x)
+    w, ldw = _row_major(weight)
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f'linear: weight is {tuple(w.shape)}, input is {tuple(x.shape)}')
+    if bias is not None:
+        bias = bias.contiguous().float()
+    if row_scale is not None:
+        row_scale = row_scale.contiguous().float()
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    elif out.shape != (M, N) or out.stride(1) != 1:
+        raise ValueError('linear: bad `out`')
+    ldy = out.stride(0) if M > 1 else max(N, out.stride(0))
+    lib = L.lib()
+    ws_bytes = lib.b200rec_linear_workspace(M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+    with torch.cuda.device(x.device):
+        L.check(lib.b200rec_linear(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
+                                   _dtype_code(out.dtype), _ptr(ws), ws_bytes, _stream()), 'linear')
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, row_scale, relu):
+        y = linear_raw(x, weight, bias, row_scale, relu)
+        ctx.save_for_backward(x, weight, row_scale, y if relu else None)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, rs, y = ctx.saved_tensors
+        g = g.contiguous()
+        if y is not None:
+            g = g * (y > 0)
+        if rs is not None:
+            g = g * rs[:, None]
+        gx = g @ w if ctx.needs_input_grad[0] else None
+        gw = g.t() @ x if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None, None
+
+
+def linear(x, weight, bias=None, row_scale=None, relu=False):
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        return _LinearFn.apply(x, weight, bias, row_scale, relu)
+    return linear_raw(x, weight, bias, row_scale, relu)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K1b MLP tower
+# ------------------------------------------------------------------------------------------------------------------
+def mlp_tower_raw(in0, in1, weights, biases, idx0=None, idx1=None):
+    _require_cuda(in0, in1, idx0, idx1, *weights)
+    n = len(weights)
+    if n < 1 or n > L.MLP_MAX_LAYERS:
+        raise NotImplementedError(f'MLP tower supports 1..{L.MLP_MAX_LAYERS} Linear layers, got {n}')
+    in0, ld0 = _row_major(in0)
+    E0 = in0.shape[1]
+    if in1 is not None:
+        in1, ld1 = _row_major(in1)
+        E1 = in1.shape[1]
+    else:
+        ld1, E1 = 0, 0
+    B = idx0.shape[0] if idx0 is not None else in0.shape[0]
+    keep = []
+    d = L.MlpDesc()
+    d.n_layers = n
+    prev = E0 + E1
+    for l, (w, b) in enumerate(zip(weights, biases)):
+        w = w.detach().contiguous().float()
+        if w.shape[1] != prev:
+            raise ValueError(f'MLP layer {l}: weight {tuple(w.shape)} does not take {prev} inputs')
+        keep.append(w)
+        d.W[l] = w.data_ptr()
+        if b is not None:
+            b = b.detach().contiguous().float()
+            keep.append(b)
+            d.b[l] = b.data_ptr()
+        else:
+            d.b[l] = None
+        d.out_dim[l] = w.shape[0]
+        prev = w.shape[0]
+    if idx0 is not None:
+        idx0 = idx0.contiguous().long()
+    if idx1 is not None:
+        idx1 = idx1.contiguous().long()
+    out = torch.empty((B, prev), dtype=torch.float32, device=in0.device)
+    with torch.cuda.device(in0.device):
+        L.check(L.lib().b200rec_mlp_tower(_ptr(in0), ld0, _ptr(idx0), E0, _ptr(in1), ld1, _ptr(idx1), E1, B, C.byref(d), _ptr(out),
+                                         prev, _stream()), 'mlp_tower')
+    return out
+
+
+def _mlp_torch(x, weights, biases):
+    for l, (w, b) in enumerate(zip(weights, biases)):
+        if l > 0:
+            x = torch.relu(x)
+        x = torch.nn.functional.linear(x, w, b)
+    return x
+
+
+class _MlpTowerFn(torch.autograd.Function):
+    """forward: fused CUDA tower.  backward: recompute with torch ops (interim)."""
+
+    @staticmethod
+    def forward(ctx, in0, in1, idx0, idx1, n_layers, *params):
+        weights, biases = params[:n_layers], params[n_layers:]
+        ctx.n_layers = n_layers
+        ctx.save_for_backward(in0, in1, idx0, idx1, *params)
+        return mlp_tower_raw(in0, in1, weights, biases, idx0, idx1)
+
+    @staticmethod
+    def backward(ctx, g):
+        in0, in1, idx0, idx1, *params = ctx.saved_tensors
+        n = ctx.n_layers
+        with torch.enable_grad():
+            a = in0.detach().requires_grad_(True)
+            b = in1.detach().requires_grad_(True) if in1 is not None else None
+            ps = [p.detach().requires_grad_(True) if p is not None else None for p in params]
+            xa = a[idx0] if idx0 is not None else a
+            if b is not None:
+                xb = b[idx1] if idx1 is not None else b
+                x = torch.cat((xa, xb), dim=1)
+            else:
+                x = xa
+            out = _mlp_torch(x, ps[:n], ps[n:])
+            wanted = [t for t in [a, b] + ps if t is not None]
+            grads = list(torch.autograd.grad(out, wanted, g, allow_unused=True))
+        it = iter(grads)
+        ga = next(it)
+        gb = next(it) if b is not None else None
+        gps = [next(it) if p is not None else None for p in ps]
+        return (ga, gb, None, None, None, *gps)
+
+
+def mlp_tower(in0, in1, weights, biases, idx0=None, idx1=None):
+    params = list(weights) + list(biases)
+    needs = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in [in0, in1] + params)
+    if needs:
+        return _MlpTowerFn.apply(in0, in1, idx0, idx1, len(weights), *params)
+    return mlp_tower_raw(in0, in1, weights, biases, idx0, idx1)
+
+
+def rowdot(in0, in1, idx0=None, idx1=None):
+    _require_cuda(in0, in1)
+    in0, ld0 = _row_major(in0)
+    in1, ld1 = _row_major(in1)
+    B = idx0.shape[0] if idx0 is not None else in0.shape[0]
+    if idx0 is not None:
+        idx0 = idx0.contiguous().long()
+    if idx1 is not None:
+        idx1 = idx1.contiguous().long()
+    out = torch.empty((B, 1), dtype=torch.float32, device=in0.device)
+    with torch.cuda.device(in0.device):
+        L.check(L.lib().b200rec_rowdot(_ptr(in0), ld0, _ptr(idx0), _ptr(in1), ld1, _ptr(idx1), in0.shape[1], B, _ptr(out), _stream()),
+                'rowdot')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K2 attention pooling
+# ------------------------------------------------------------------------------------------------------------------
+def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None, user_matrix=None, csr=None,
+                       return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0):
+    """out (B,U) [, att (B,I)] — b200rec_attention_pool.  `csr` = (row_ptr int32, col int32, val fp32)."""
+    _require_cuda(Pc, Pr, Q, user_matrix)
+    Pc = Pc.contiguous().float()
+    if Pr.dtype != Q.dtype:
+        raise ValueError('Pr and Q must share a dtype')
+    if Pr.stride(1) != 1 or Pr.stride(0) % 4 or Pr.data_ptr() % 16:
+        Pr = Pr.clone(memory_format=torch.contiguous_format)
+    if Q.stride(1) != 1 or Q.stride(0) % 4 or Q.data_ptr() % 16:
+        Q = Q.clone(memory_format=torch.contiguous_format)
+    B, H = Pc.shape
+    I, U = Q.shape
+    if Pr.shape != (I, H):
+        raise ValueError('attention_pool: table shapes disagree')
+    d = L.AttentionDesc()
+    keep = [Pc, Pr, Q]
+    d.Pc, d.Pr, d.Q = Pc.data_ptr(), Pr.data_ptr(), Q.data_ptr()
+    d.table_dtype = _dtype_code(Pr.dtype)
+    d.mode = mode
+    for name, t in (('a2', a2), ('a20', a20), ('bU', bU)):
+        if t is not None:
+            t = t.detach().contiguous().float().view(-1)
+            keep.append(t)
+            setattr(d, name, t.data_ptr())
+    if user_matrix is not None:
+        um, ld = _row_major(user_matrix)
+        if um.shape != (B, I):
+            raise ValueError('attention_pool: user_matrix must be (B, I)')
+        keep.append(um)
+        d.user_matrix, d.ld_user_matrix = um.data_ptr(), ld
+    elif csr is not None:
+        rp, col, val = csr
+        rp, col, val = rp.contiguous().int(), col.contiguous().int(), val.contiguous().float()
+        keep += [rp, col, val]
+        d.row_ptr, d.col, d.val = rp.data_ptr(), col.data_ptr(), val.data_ptr()
+    else:
+        raise ValueError('attention_pool: need user_matrix or csr')
+    d.B, d.I, d.H, d.U = B, I, H, U
+    d.ld_pr, d.ld_q = (Pr.stride(0) if I > 1 else H), (Q.stride(0) if I > 1 else U)
+    out = torch.empty((B, U), dtype=torch.float32, device=Pc.device)
+    d.out, d.ldo = out.data_ptr(), U
+    att = None
+    if return_attention_weights:
+        att = torch.zeros((B, I), dtype=torch.float32, device=Pc.device)
+        d.att_weights = att.data_ptr()
+    if train_mask is not None:
+        Ec, Er, atol, rtol = train_mask
+        Ec, Er = Ec.detach().contiguous().float(), Er.detach().contiguous().float()
+        keep += [Ec, Er]
+        d.train_cand_emb, d.train_rated_emb, d.E, d.atol, d.rtol = Ec.data_ptr(), Er.data_ptr(), Ec.shape[1], atol, rtol
+    d.drop_zero_scores = int(drop_zero_scores)
+    d.score_scale = float(score_scale)
+    with torch.cuda.device(Pc.device):
+        L.check(L.lib().b200rec_attention_pool(C.byref(d), _stream()), 'attention_pool')
+    return (out, att) if return_attention_weights else out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K3 SpMM
+# ------------------------------------------------------------------------------------------------------------------
+def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, skip_bits=None):
+    """One propagation step over a `GraphIndex` (graph.py): b200rec_spmm.  Returns nothing; writes x_next / acc_out."""
+    _require_cuda(t)
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    d = L.SpmmDesc()
+    d.chunk_row, d.chunk_start, d.chunk_slot = index.chunk_row.data_ptr(), index.chunk_start.data_ptr(), index.chunk_slot.data_ptr()
+    d.n_chunks, d.chunk_size = index.n_chunks, index.chunk_size
+    d.row_ptr, d.col = index.row_ptr.data_ptr(), index.col.data_ptr()
+    d.w = w.data_ptr() if w is not None else None
+    d.perm = index.pos.data_ptr()
+    d.skip_bits = skip_bits.data_ptr() if skip_bits is not None else None
+    d.t, d.t_dtype, d.ld_t, d.d = t.data_ptr(), _dtype_code(t.dtype), t.stride(0), t.shape[1]
+    d.dinv = dinv.data_ptr() if dinv is not None else None
+    partials = None
+    if index.n_multi > 0:
+        partials = torch.empty((index.n_slots, t.shape[1]), dtype=torch.float32, device=t.device)
+        d.partials = partials.data_ptr()
+    if x_next is not None:
+        d.x_next, d.ld_x = x_next.data_ptr(), x_next.stride(0)
+    if acc_out is not None:
+        d.acc_out, d.ld_acc = acc_out.data_ptr(), acc_out.stride(0)
+        if acc_in is not None:
+            if acc_in.stride(0) != acc_out.stride(0):
+                raise ValueError('spmm: acc_in and acc_out must share a leading dimension')
+            d.acc_in = acc_in.data_ptr()
+    d.acc_scale = acc_scale
+    if index.n_multi > 0:
+        d.multi_row, d.multi_first_slot, d.multi_n_slots = (index.multi_row.data_ptr(), index.multi_first_slot.data_ptr(),
+                                                            index.multi_n_slots.data_ptr())
+    d.n_multi = index.n_multi
+    with torch.cuda.device(t.device):
+        L.check(L.lib().b200rec_spmm(C.byref(d), _stream()), 'spmm')
+
+
+class _PropagateFn(torch.autograd.Function):
+    """x_next = dinv ∘ (A_w · t).  backward = the same kernel on the reverse-direction weights (graph.py: w_bwd)."""
+
+    @staticmethod
+    def forward(ctx, t, index, w, w_bwd, dinv, skip_bits):
+        x_next = torch.empty((index.num_nodes, t.shape[1]), dtype=torch.float32, device=t.device)
+        spmm_raw(index, t, w=w, dinv=dinv, x_next=x_next, skip_bits=skip_bits)
+        ctx.index, ctx.w_bwd, ctx.dinv, ctx.skip_bits, ctx.has_w = index, w_bwd, dinv, skip_bits, w is not None
+        return x_next
+
+    @staticmethod
+    def backward(ctx, g):
+        index = ctx.index
+        if ctx.has_w and ctx.w_bwd is None:
+            raise NotImplementedError('GraphNCF backward needs symmetric edge lists (binary=False)')
+        gs = (g * ctx.dinv[:, None]).contiguous() if ctx.dinv is not None else g.contiguous()
+        gt = torch.empty_like(gs)
+        spmm_raw(index, gs, w=ctx.w_bwd, dinv=None, x_next=gt, skip_bits=ctx.skip_bits)
+        return gt, None, None, None, None, None
+
+
+def propagate(t, index, w, w_bwd, dinv, skip_bits=None):
+    return _PropagateFn.apply(t, index, w, w_bwd, dinv, skip_bits)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K2 autograd wrapper
+# ------------------------------------------------------------------------------------------------------------------
+def _attention_pool_torch(Pc, Pr, Q, a2, a20, bU, um, mode, train_mask, drop_zero_scores, score_scale=1.0):
+    """Differentiable torch restatement on the non-zeros (used only inside backward)."""
+    b_idx, i_idx = (um != 0).nonzero(as_tuple=True)
+    if mode == L.ATT_NET:
+        s = (torch.relu(Pc[b_idx] + Pr[i_idx]) * a2.view(1, -1)).sum(1)
+        if a20 is not None:
+            s = s + a20.view(())
+    else:
+        s = (Pc[b_idx] * Pr[i_idx]).sum(1)
+    s = s * score_scale
+    keep = torch.ones_like(s, dtype=torch.bool)
+    if drop_zero_scores:
+        keep &= s.detach() != 0
+    if train_mask is not None:
+        Ec, Er, atol, rtol = train_mask
+        keep &= ~torch.isclose(Ec[b_idx], Er[i_idx], atol=atol, rtol=rtol).all(dim=1)
+    b_idx, i_idx, s = b_idx[keep], i_idx[keep], s[keep]
+    B = Pc.shape[0]
+    m = torch.full((B,), float('-inf'), device=s.device).scatter_reduce(0, b_idx, s.detach(), reduce='amax', include_self=True)
+    e = torch.exp(s - m[b_idx])
+    l = torch.zeros(B, device=s.device).index_add(0, b_idx, e)
+    alpha = e / l[b_idx]
+    wgt = alpha * um[b_idx, i_idx]
+    out = torch.zeros((B, Q.shape[1]), device=s.device).index_add(0, b_idx, wgt[:, None] * Q[i_idx])
+    return out + bU.view(1, -1) if bU is not None else out
+
+
+class _AttentionPoolFn(torch.autograd.Function):
+    """forward: fused CUDA kernel.  backward: torch recompute on the non-zeros (interim)."""
+
+    @staticmethod
+    def forward(ctx, Pc, Pr, Q, a2, a20, bU, um, mode, want_att, train_mask, drop_zero_scores, score_scale):
+        ctx.mode, ctx.train_mask, ctx.drop, ctx.scale = mode, train_mask, drop_zero_scores, score_scale
+        ctx.save_for_backward(Pc, Pr, Q, a2, a20, bU, um)
+        r = attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, user_matrix=um,
+                               return_attention_weights=want_att, train_mask=train_mask, drop_zero_scores=drop_zero_scores,
+                               score_scale=score_scale)
+        if want_att:
+            ctx.mark_non_differentiable(r[1])
+            return r
+        return r, None
+
+    @staticmethod
+    def backward(ctx, g, _g_att=None):
+        Pc, Pr, Q, a2, a20, bU, um = ctx.saved_tensors
+        with torch.enable_grad():
+            ins = [t.detach().requires_grad_(True) if t is not None else None for t in (Pc, Pr, Q, a2, a20, bU)]
+            out = _attention_pool_torch(*ins, um, ctx.mode, ctx.train_mask, ctx.drop, ctx.scale)
+            wanted = [t for t in ins if t is not None]
+            grads = iter(torch.autograd.grad(out, wanted, g, allow_unused=True))
+        res = [next(grads) if t is not None else None for t in ins]
+        return (*res, None, None, None, None, None, None)
+
+
+def attention_pool(Pc, Pr, Q, *, mode, a2, a20, bU, user_matrix, return_attention_weights=False, train_mask=None,
+                   drop_zero_scores=False, score_scale=1.0):
+    needs = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (Pc, Pr, Q, a2, a20, bU))
+    if needs:
+        out, att = _AttentionPoolFn.apply(Pc, Pr, Q, a2, a20, bU, user_matrix, mode, return_attention_weights, train_mask,
+                                          drop_zero_scores, score_scale)
+        return (out, att) if return_attention_weights else out
+    return attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, user_matrix=user_matrix,
+                              return_attention_weights=return_attention_weights, train_mask=train_mask,
+                              drop_zero_scores=drop_zero_scores, score_scale=score_scale)

@@ -1,0 +1,186 @@
+/* libb200rec — C ABI of the B200-native scoring hot path of DeepRecommendation (BasicNCF / AttentionNCF / GraphNCF).
+ *
+ * The reference (michaelbzms/DeepRecommendation) is 100 % Python: it has no FFI, operator or plugin layer, so the
+ * drop-in seam is its Python class API.  This header is the boundary BELOW that seam: the entry
+ * points a maintainer binds (ctypes stub in INTEGRATION.md; `deeprecommendation_b200/_lib.py` is that binding) to
+ * replace the device work of the reference functions cited on each declaration.  Paths are relative to
+ * /root/reference/src/neural_collaborative_filtering/ unless they start with src/.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
+ *  - the caller owns every buffer; entry points never allocate, never synchronise and launch on `stream`
+ *    (a cudaStream_t passed as void*); workspaces are sized by the matching *_workspace() query;
+ *  - matrices are row-major with an explicit leading dimension in ELEMENTS; weights keep nn.Linear's (out, in) layout;
+ *  - return value: B200REC_OK or an error code; b200rec_last_error() gives the message (thread-local);
+ *  - there is no CPU path: without a CUDA device every compute call returns B200REC_ERR_CUDA.
+ */
+#ifndef B200REC_H
+#define B200REC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REC_VERSION 100
+
+typedef void* b200rec_stream_t; /* cudaStream_t */
+
+enum { B200REC_OK = 0, B200REC_ERR_CUDA = 1, B200REC_ERR_BAD_ARG = 2, B200REC_ERR_UNSUPPORTED = 3, B200REC_ERR_WORKSPACE = 4 };
+enum { B200REC_F32 = 0, B200REC_BF16 = 1 };
+enum { B200REC_ATT_NET = 0, B200REC_ATT_DOT = 1 };
+
+const char* b200rec_last_error(void);
+int b200rec_version(void);
+int b200rec_sm_count(void);
+
+/* ---- K1a  linear layer:  Y = act((X · Wᵀ + bias) ∘ row_scale) ---------------------------------------------------
+ * Replaces nn.Linear at models/basic_ncf.py:38-39, models/attention_ncf.py:150-151,216, models/gnn_ncf.py:300-301 and
+ * (transform-before-gather) the per-edge Linear of models/gnn_ncf.py:91-93.  fp32 FFMA, fp32 accumulate.
+ * X (M,K) ld=ldx; W (N,K) ld=ldw; bias (N) or NULL; row_scale (M) or NULL; Y (M,N) ld=ldy of y_dtype. */
+size_t b200rec_linear_workspace(int64_t M, int64_t N, int64_t K);
+int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
+                   const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, void* workspace, size_t workspace_bytes,
+                   b200rec_stream_t stream);
+
+/* ---- K1b  fused MLP tower ------------------------------------------------------------------------------------
+ * Replaces torch.cat + build_MLP_layers (util.py:5-18; basic_ncf.py:40-41, attention_ncf.py:219-222, gnn_ncf.py:354-362):
+ * out = MLP([in0[idx0], in1[idx1]]).  idx0/idx1 (int64, B) are optional row gathers (GraphNCF's combined[itemIds] /
+ * combined[userIds]); NULL = identity.  Layer l: W[l] (out_dim[l], in) row-major, b[l] (out_dim[l]) or NULL; ReLU between
+ * layers, none after the last.  Activations never leave shared memory. */
+#define B200REC_MLP_MAX_LAYERS 8
+typedef struct {
+  const float* W[B200REC_MLP_MAX_LAYERS];
+  const float* b[B200REC_MLP_MAX_LAYERS];
+  int out_dim[B200REC_MLP_MAX_LAYERS];
+  int n_layers;
+} b200rec_mlp_t;
+int b200rec_mlp_tower(const float* in0, int64_t ld0, const int64_t* idx0, int E0, const float* in1, int64_t ld1, const int64_t* idx1,
+                      int E1, int64_t B, const b200rec_mlp_t* mlp, float* out, int64_t ldo, b200rec_stream_t stream);
+/* GraphNCF(use_dot_product=True), gnn_ncf.py:365: out[b] = <in0[idx0[b]], in1[idx1[b]]> */
+int b200rec_rowdot(const float* in0, int64_t ld0, const int64_t* idx0, const float* in1, int64_t ld1, const int64_t* idx1, int E,
+                   int64_t B, float* out, b200rec_stream_t stream);
+
+/* ---- K2  AttentionNCF ragged attention pooling ------------------------------------------------------------------
+ * Replaces attention_ncf.py:154-216.  With AttentionNet.0 = [A1c | A1r]:  Pc = Ec·A1cᵀ + a1 (B,H), Pr = Er·A1rᵀ (I,H),
+ * Q = rated_items·W_Uᵀ (I,U);  s_bi = a2·ReLU(Pc[b] + Pr[i]) + a20 (mode NET)  or  <Pc[b], Pr[i]> (mode DOT: cosine / att_dense=None);
+ * out[b] = Σ_i softmax_i(s_b·)·um_bi·Q[i] + bU   over the i with um_bi != 0 (exact 0.0 = "unrated", :158,192).
+ * Give either the reference's dense user_matrix (B,I) or its CSR (row_ptr int32 B+1, col int32, val fp32).
+ * att_weights (B,I), if non-NULL, must be zero-filled; it receives the softmax weights (:224).
+ * Training extras: train_cand_emb/train_rated_emb (+E, atol, rtol) reproduce the isclose() target mask (:199);
+ * drop_zero_scores reproduces `attOut[attOut == 0] = -inf` (:189).  H, U: multiples of 4, <= 512. */
+typedef struct {
+  const float* Pc;
+  const void* Pr;
+  const void* Q;
+  int table_dtype; /* dtype of Pr and Q */
+  int mode;
+  const float* a2;  /* (H), mode NET */
+  const float* a20; /* device scalar or NULL */
+  const float* bU;  /* (U) or NULL */
+  const float* user_matrix; /* (B,I) dense, or NULL when CSR is given */
+  int64_t ld_user_matrix;   /* 0 = I */
+  const int* row_ptr;
+  const int* col;
+  const float* val;
+  int64_t B, I;
+  int H, U;
+  float* out; /* (B,U) */
+  int64_t ldo;
+  float* att_weights;
+  const float* train_cand_emb;
+  const float* train_rated_emb;
+  int E;
+  float atol, rtol;
+  int drop_zero_scores;
+  float score_scale; /* 0 = 1.0; message dropout keeps scores / (1-p) (F.dropout, :187) */
+  int64_t ld_pr, ld_q; /* leading dimensions of Pr / Q in elements; 0 = H / U */
+} b200rec_attention_t;
+int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream);
+
+/* ---- K3  GraphNCF propagation: edge-balanced CSR SpMM + degree normalisation + fused combine -----------------------
+ * Replaces LightGCNConv.forward/message + PyG propagate (gnn_ncf.py:39-94) and the stack+mean of gnn_ncf.py:351:
+ *   x_next[r] = dinv[r] · Σ_{k in row r} w[k]·t[col[k]];   acc_out[r] = (acc_in[r] + x_next[r])·acc_scale
+ * t (N,d) are the per-NODE transformed features dinv[s]·(W_type x[s] + b_type) produced by b200rec_linear.
+ * chunk_* / multi_* come from b200rec_spmm_plan_*; skip_bits (+perm) is the training-time target-edge mask. */
+typedef struct {
+  const int* chunk_row;
+  const int* chunk_start;
+  const int* chunk_slot;
+  int n_chunks;
+  int chunk_size;
+  const int* row_ptr;
+  const int* col;
+  const float* w; /* NULL = 1 (binary graph) */
+  const int* perm;
+  const uint32_t* skip_bits;
+  const void* t;
+  int t_dtype;
+  int64_t ld_t;
+  int d;
+  const float* dinv;
+  float* partials; /* (n_slots, d) */
+  float* x_next;   /* may be NULL */
+  int64_t ld_x;
+  const float* acc_in; /* may be NULL */
+  float* acc_out;      /* may be NULL */
+  int64_t ld_acc;
+  float acc_scale;
+  const int* multi_row;
+  const int* multi_first_slot;
+  const int* multi_n_slots;
+  int n_multi;
+} b200rec_spmm_t;
+int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream);
+
+/* ---- K4  neighbour-index build (bit-exact vs src/content_providers/graph_providers.py:10-66,76-80) ---------------- */
+size_t b200rec_scan_workspace(int64_t n);
+int b200rec_exclusive_scan_i32(const int* in, int64_t n, int* out /* n+1 */, void* ws, size_t ws_bytes, b200rec_stream_t stream);
+size_t b200rec_sort_pairs_workspace(int64_t n);
+int b200rec_sort_pairs_i32(int* keys, int* vals, int64_t n, int key_bits, void* ws, size_t ws_bytes, b200rec_stream_t stream);
+
+/* sorted-unique raw id -> rank (graph_providers.py:76-80).  flags (id_bound), rank (id_bound+1; rank[id_bound] = #unique),
+ * sorted_ids (#unique, may be NULL); *err_flag is set to 1 if an id is outside [0, id_bound). */
+int b200rec_id_rank_table(const int64_t* ids, int64_t n, int64_t id_bound, int* flags, int* rank, int64_t* sorted_ids, int* err_flag,
+                          void* ws, size_t ws_bytes, b200rec_stream_t stream);
+int b200rec_id_lookup(const int64_t* ids, int64_t n, int64_t id_bound, const int* flags, const int* rank, int64_t offset, int64_t* out,
+                      int* err_flag, b200rec_stream_t stream);
+/* per-group rating count and fp64 sum (pandas groupby.mean, graph_providers.py:16-17); count/sum must be zeroed */
+int b200rec_group_stats(const int64_t* idx, const double* rating, int64_t n, int64_t idx_offset, int* count, double* sum,
+                        b200rec_stream_t stream);
+/* centred edge attrs (fp64 -> fp32) and the `binary` keep flags per interaction, file order (graph_providers.py:32-46) */
+int b200rec_edge_attrs(const int64_t* u_node, const int64_t* i_node, const double* rating, int64_t n, int64_t n_items, const int* cnt_u,
+                       const double* sum_u, const int* cnt_i, const double* sum_i, float* attr_u2i, float* attr_i2u, int* keep_u,
+                       int* keep_i, b200rec_stream_t stream);
+/* edge_index (2, n_out) int64 from (src, dst) per interaction; keep/pos (exclusive scan of keep) compact when binary */
+int b200rec_edge_scatter(const int64_t* src, const int64_t* dst, int64_t n, const int* keep, const int* pos, int64_t n_out,
+                         int64_t* edge_index, b200rec_stream_t stream);
+/* CSR by destination of cat(u2i, i2u): stable radix sort.  row_ptr (N+1), col/w/pos (e1+e2), deg (N), dinv (N, may be NULL);
+ * pos[k] = position of CSR entry k inside its own edge list (the pos_df value). */
+size_t b200rec_csr_workspace(int64_t n_edges_total, int64_t num_nodes);
+int b200rec_csr_build(const int64_t* u2i, int64_t e1, const int64_t* i2u, int64_t e2, const float* attr_u2i, const float* attr_i2u,
+                      int64_t num_nodes, int* row_ptr, int* col, float* w, int* pos, int* deg, float* dinv, void* ws, size_t ws_bytes,
+                      b200rec_stream_t stream);
+int b200rec_dinv(const int* deg, int64_t n, float* dinv, b200rec_stream_t stream);
+/* chunk plan for b200rec_spmm: count (offset arrays of n_rows+1 ints; totals in their last entry), then fill */
+size_t b200rec_spmm_plan_workspace(int64_t n_rows);
+int b200rec_spmm_plan_count(const int* row_ptr, int64_t n_rows, int chunk, int* chunk_off, int* multi_off, int* slot_off, void* ws,
+                            size_t ws_bytes, b200rec_stream_t stream);
+int b200rec_spmm_plan_fill(const int* row_ptr, int64_t n_rows, int chunk, const int* chunk_off, const int* multi_off, const int* slot_off,
+                           int* chunk_row, int* chunk_start, int* chunk_slot, int* multi_row, int* multi_first_slot, int* multi_n_slots,
+                           b200rec_stream_t stream);
+/* (src,dst) -> position hash = pos_df (graph_providers.py:54) and its lookup (gnn_ncf.py:370); missing pairs give -1 and bump
+ * *n_missing (the reference raises KeyError).  capacity: power of two >= 2n. */
+int b200rec_pairhash_build(const int64_t* edge_index, int64_t n, uint64_t* keys, int* vals, int64_t capacity, b200rec_stream_t stream);
+int b200rec_pairhash_lookup(const int64_t* src, const int64_t* dst, int64_t n, const uint64_t* keys, const int* vals, int64_t capacity,
+                            int64_t* out, int* n_missing, b200rec_stream_t stream);
+/* training-time target-edge mask (gnn_ncf.py:314-320,369-378): sets skip bits and decrements both endpoints' in-degree */
+int b200rec_mask_targets(const int64_t* positions, int64_t n, int64_t n_edges, const int64_t* u2i, const int64_t* i2u,
+                         uint32_t* skip_bits, int* deg, b200rec_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H */

@@ -1,0 +1,287 @@
+"""End-to-end parity of the three model classes (the drop-in seam) on a B200: CUDA path through the
+C ABI vs (1) golden outputs of the UNMODIFIED reference (tests/golden, made by oracle/make_golden.py) and (2) the CPU
+oracle restatement on larger seeded inputs.  fp32 tolerance: max-norm relative error <= 1e-5 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from oracle import synth
+from tests._golden import load, maxnorm_rel
+from tests.test_oracle import GRAPH_CASES, attention_full_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = 'cuda:0'
+
+
+def _models():
+    from deeprecommendation_b200.neural_collaborative_filtering import models
+    return models
+
+
+def _cuda(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+# ---- BasicNCF -----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['basic_small_a', 'basic_small_b', 'basic_small_c'])
+def test_basic_small_vs_reference(name):
+    d, sd, kw = load(name)
+    m = _models().BasicNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)                       # reference key names load unchanged
+    with torch.no_grad():
+        out = m(torch.from_numpy(d['X_user']).to(DEV), torch.from_numpy(d['X_item']).to(DEV))
+    assert out.shape == (37, 1) and out.device.type == 'cuda'
+    assert maxnorm_rel(out, d['out']) < TOL
+
+
+@pytest.mark.parametrize('name', ['basic_full_256', 'basic_full_256_128'])
+def test_basic_full_vs_reference(name):
+    d, _, kw = load(name)
+    sd = synth.to_torch(synth.basic_ncf_weights(seed=int(d['weight_seed']), **kw))
+    m = _models().BasicNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    B = int(d['B'])
+    xi = torch.from_numpy(synth.item_profiles(B, seed=int(d['item_seed']))).to(DEV)
+    xu = torch.from_numpy((synth.item_profiles(B, seed=int(d['user_seed'])) - 0.25) * 0.125).to(DEV)
+    with torch.no_grad():
+        out = m(xu, xi)
+    assert maxnorm_rel(out, d['out']) < TOL
+
+
+def test_basic_cfg1_batches_vs_oracle():
+    """BASELINE config 1 shape: F=2094 dense profiles, emb 128, batches of 512 (train_model.py:38-42)."""
+    kw = dict(item_dim=2094, user_dim=2094, item_emb=128, user_emb=128, mlp_dense_layers=[256], dropout_rate=0.2)
+    sd = synth.to_torch(synth.basic_ncf_weights(seed=1, **kw))
+    m = _models().BasicNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    items = synth.item_profiles(2048, seed=7)
+    users = (synth.item_profiles(2048, seed=8) - 0.3) * 0.1
+    for B in (1, 127, 512, 2048):
+        xu, xi = torch.from_numpy(users[:B]), torch.from_numpy(items[:B])
+        ref = R.basic_ncf_forward(sd, xu, xi)
+        with torch.no_grad():
+            out = m(xu.to(DEV), xi.to(DEV))
+        assert maxnorm_rel(out, ref) < TOL
+
+
+# ---- AttentionNCF ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['attention_small_net', 'attention_small_lin', 'attention_small_cos'])
+def test_attention_small_vs_reference(name):
+    d, sd, kw = load(name)
+    m = _models().AttentionNCF(**kw).to(DEV)
+    m.load_state_dict(sd)
+    t = [torch.from_numpy(d[k]).to(DEV) for k in ('candidate_items', 'rated_items', 'user_matrix')]
+    with torch.no_grad():
+        m.eval()
+        out, att = m(*t, return_attention_weights=True)
+        out_only = m(*t)
+        m.train()                 # dropout_rate=0.0, message_dropout=None: only the isclose() candidate mask differs
+        out_tr, att_tr = m(*t, return_attention_weights=True)
+    assert maxnorm_rel(out, d['out']) < TOL and maxnorm_rel(att, d['att']) < TOL
+    assert torch.equal(out_only, out)
+    assert torch.all(att[1] == 0) and torch.all(att[d['user_matrix'] == 0] == 0)
+    assert maxnorm_rel(out_tr, d['out_train']) < TOL and maxnorm_rel(att_tr, d['att_train']) < TOL
+    assert att_tr[0, 3] == 0 and att[0, 3] > 0
+
+
+def test_attention_full_vs_reference():
+    d, _, kw = load('attention_full')
+    wkw = {k: v for k, v in kw.items() if k not in ('use_cos_sim_instead', 'message_dropout')}
+    sd = synth.to_torch(synth.attention_ncf_weights(seed=int(d['weight_seed']), **wkw))
+    m = _models().AttentionNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    cand, rated, um = attention_full_inputs(d)
+    with torch.no_grad():
+        out, att = m(torch.from_numpy(cand).to(DEV), torch.from_numpy(rated).to(DEV), torch.from_numpy(um).to(DEV),
+                     return_attention_weights=True)
+    assert maxnorm_rel(out, d['out']) < TOL and maxnorm_rel(att, d['att']) < TOL
+    rows = torch.from_numpy((um != 0).any(1))
+    assert torch.allclose(att.sum(1).cpu()[rows], torch.ones(int(rows.sum())), atol=1e-5)
+
+
+def _cfg2_batch(B, n_items, seed, max_len=2698):
+    """ragged rated lists, mean ~165 / heavy tail, as a dense (B, I) user_matrix over the batch's item union"""
+    rng = np.random.default_rng(seed)
+    lens = np.clip(rng.lognormal(4.6, 1.0, size=B).astype(int), 1, min(max_len, n_items))
+    lens[0], lens[1] = min(max_len, n_items), 0          # the longest list and an empty one
+    um = np.zeros((B, n_items), dtype=np.float32)
+    for b in range(B):
+        cols = rng.choice(n_items, size=lens[b], replace=False)
+        um[b, cols] = rng.integers(1, 11, size=lens[b]) * 0.5 - 2.75
+    used = np.flatnonzero((um != 0).any(0))
+    return um[:, used], used
+
+
+def test_attention_cfg2_ragged_vs_oracle():
+    """BASELINE config 2 shape (F=2094, 128/128/128, [256,128]); ragged lists up to ~2.7k, dense and CSR front-ends"""
+    from deeprecommendation_b200 import ops
+    kw = dict(item_dim=2094, item_emb=128, user_emb=128, att_dense=128, mlp_dense_layers=[256, 128], dropout_rate=0.2)
+    sd = synth.to_torch(synth.attention_ncf_weights(seed=3, **kw))
+    m = _models().AttentionNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    B, n_items = 96, 3000
+    um, used = _cfg2_batch(B, n_items, seed=11)
+    prof = synth.item_profiles(n_items + B, seed=12)
+    rated, cand = torch.from_numpy(prof[used]), torch.from_numpy(prof[n_items:])
+    umt = torch.from_numpy(um)
+    ref_out, ref_att = R.attention_ncf_forward_blocked(sd, cand, rated, umt, block=16, return_attention_weights=True)
+    with torch.no_grad():
+        out, att = m(cand.to(DEV), rated.to(DEV), umt.to(DEV), return_attention_weights=True)
+    assert maxnorm_rel(out, ref_out) < TOL and maxnorm_rel(att, ref_att) < TOL
+    # the ragged-native (CSR) entry gives the same user embeddings as the dense drop-in entry
+    E = 128
+    with torch.no_grad():
+        Ec = ops.linear_raw(cand.to(DEV), m.ItemEmbeddings[0].weight, m.ItemEmbeddings[0].bias)
+        Er = ops.linear_raw(rated.to(DEV), m.ItemEmbeddings[0].weight, m.ItemEmbeddings[0].bias)
+        Q = ops.linear_raw(rated.to(DEV), m.UserEmbeddings[0].weight, None)
+        A1 = m.AttentionNet[0].weight
+        Pc = ops.linear_raw(Ec, A1[:, :E], m.AttentionNet[0].bias)
+        Pr = ops.linear_raw(Er, A1[:, E:], None)
+        common = dict(mode=0, a2=m.AttentionNet[3].weight, a20=m.AttentionNet[3].bias, bU=m.UserEmbeddings[0].bias)
+        dense = ops.attention_pool_raw(Pc, Pr, Q, user_matrix=umt.to(DEV), **common)
+        nz = umt != 0
+        row_ptr = torch.cat((torch.zeros(1, dtype=torch.int64), nz.sum(1).cumsum(0))).int()
+        col = nz.nonzero()[:, 1].int()
+        csr = ops.attention_pool_raw(Pc, Pr, Q, csr=(row_ptr.to(DEV), col.to(DEV), umt[nz].to(DEV)), **common)
+        assert torch.equal(dense, csr)
+        bf = ops.attention_pool_raw(Pc, Pr.bfloat16(), Q.bfloat16(), user_matrix=umt.to(DEV), **common)
+        assert maxnorm_rel(bf, dense) < 1e-2                                  # bf16 tables, fp32 accumulate
+
+
+def test_attention_webapp_pattern_vs_oracle():
+    """webapp/backend.py:78-99: one user, every candidate shares the same rated list"""
+    kw = dict(item_dim=256, item_emb=64, user_emb=64, att_dense=64, mlp_dense_layers=[128, 64], dropout_rate=0.2)
+    sd = synth.to_torch(synth.attention_ncf_weights(seed=4, **kw))
+    m = _models().AttentionNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    prof = synth.item_profiles(1200, seed=5, f_binary=128, f_dense=128)
+    rated, cand = torch.from_numpy(prof[:40]), torch.from_numpy(prof[40:])
+    row = np.random.default_rng(6).integers(1, 11, size=40) * 0.5 - 2.9
+    um = torch.from_numpy(np.repeat(row[None, :], cand.shape[0], 0).astype(np.float32))
+    ref, ref_att = R.attention_ncf_forward_blocked(sd, cand, rated, um, block=128, return_attention_weights=True)
+    with torch.no_grad():
+        out, att = m(cand.to(DEV), rated.to(DEV), um.to(DEV), return_attention_weights=True)
+    assert maxnorm_rel(out, ref) < TOL and maxnorm_rel(att, ref_att) < TOL
+
+
+# ---- GraphNCF ------------------------------------------------------------------------------------------------------------
+def _graph_from_golden(build, d):
+    from deeprecommendation_b200.graph import GraphData
+    g = GraphData(item_features=torch.from_numpy(d['item_features']), user_features=torch.from_numpy(d['user_features']),
+                  user2item_edge_index=torch.from_numpy(build['user2item_edge_index']),
+                  item2user_edge_index=torch.from_numpy(build['item2user_edge_index']),
+                  user2item_edge_attr=torch.from_numpy(build['user2item_edge_attr']) if 'user2item_edge_attr' in build else None,
+                  item2user_edge_attr=torch.from_numpy(build['item2user_edge_attr']) if 'item2user_edge_attr' in build else None)
+    return g.to(DEV)
+
+
+@pytest.mark.parametrize('name', [c for c in GRAPH_CASES if c != 'graph_ncf_gat'])
+def test_graph_ncf_vs_reference(name):
+    d, sd, kw = load(name)
+    build, _, _ = load('graph_build_binary1' if name == 'graph_ncf_binary' else 'graph_build_binary0')
+    g = _graph_from_golden(build, d)
+    m = _models().GraphNCF(**kw).to(DEV)
+    m.load_state_dict(sd)                       # aliased gnn_convs.{k}.* keys load as in the reference
+    uid, iid = torch.from_numpy(d['userIds']).to(DEV), torch.from_numpy(d['itemIds']).to(DEV)
+    with torch.no_grad():
+        m.eval()
+        out = m(g, uid, iid, DEV)
+        assert maxnorm_rel(out, d['out']) < TOL
+        if 'out_train_masked' in d:
+            m.train()             # every dropout is 0: only the target-edge masking differs (gnn_ncf.py:314-320)
+            assert maxnorm_rel(m(g, uid, iid, DEV, mask_targets=True), d['out_train_masked']) < TOL
+            assert maxnorm_rel(m(g, uid, iid, DEV, mask_targets=False), d['out_train_unmasked']) < TOL
+    if 'out_train_masked' in d:   # the autograd path runs the same kernels
+        m.train()
+        assert maxnorm_rel(m(g, uid, iid, DEV, mask_targets=True), d['out_train_masked']) < TOL
+
+
+def test_graph_ncf_gat_fails_loudly():
+    _, _, kw = load('graph_ncf_gat')
+    with pytest.raises(NotImplementedError):
+        _models().GraphNCF(**kw)
+
+
+def test_graph_ncf_missing_target_edge_raises_keyerror():
+    d, sd, kw = load('graph_ncf_hetero_mean')
+    build, _, _ = load('graph_build_binary0')
+    g = _graph_from_golden(build, d)
+    m = _models().GraphNCF(**kw).to(DEV).train()
+    m.load_state_dict(sd)
+    u2i = set(zip(build['user2item_edge_index'][0].tolist(), build['user2item_edge_index'][1].tolist()))
+    nI = d['item_features'].shape[0]
+    u, i = next((u, i) for u in range(nI, nI + 5) for i in range(nI) if (u, i) not in u2i)
+    with pytest.raises(KeyError):
+        m(g, torch.tensor([u], device=DEV), torch.tensor([i], device=DEV), DEV)
+
+
+@pytest.mark.parametrize('d_emb,L_,n_users,n_items,n', [(128, 2, 3000, 1500, 150_000), (64, 3, 2000, 4000, 120_000)])
+def test_graph_ncf_medium_vs_oracle(d_emb, L_, n_users, n_items, n):
+    """heavy-tailed degrees (rows far longer than one SpMM chunk), zero-degree items, both reference hyper-parameter sets"""
+    from deeprecommendation_b200.graph import IdTable, create_graph
+    users, items, ratings = synth.interactions_zipf(n_users, n_items, n, seed=9)
+    F = 96
+    rng = np.random.default_rng(1)
+    item_feat = rng.standard_normal((n_items, F)).astype(np.float32)
+    user_feat = rng.standard_normal((n_users, F)).astype(np.float32)
+    kw = dict(item_dim=F, user_dim=F, num_gnn_layers=L_, hetero=True, node_emb=d_emb, mlp_dense_layers=[256, 128] if d_emb == 128 else [128],
+              dropout_rate=0.2)
+    sd = synth.to_torch(synth.graph_ncf_weights(seed=2, **kw))
+    all_u, all_i = np.arange(n_users), np.arange(n_items)
+    ref_g = R.create_graph(users, items, ratings, all_u, all_i)
+    gd = {k: (torch.from_numpy(v) if v is not None else None) for k, v in ref_g.items()}
+    gd['item_features'], gd['user_features'] = torch.from_numpy(item_feat), torch.from_numpy(user_feat)
+    pick = rng.permutation(n)[:512]
+    uid = torch.from_numpy(ref_g['user2item_edge_index'][0][pick])
+    iid = torch.from_numpy(ref_g['user2item_edge_index'][1][pick])
+    ref = R.graph_ncf_forward(sd, gd, uid, iid, L_)
+    ref_masked = R.graph_ncf_forward(sd, gd, uid, iid, L_, masked_positions=torch.from_numpy(pick))
+    ut, it = IdTable(torch.from_numpy(all_u).to(DEV)), IdTable(torch.from_numpy(all_i).to(DEV))
+    g = create_graph(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), torch.from_numpy(ratings).to(DEV),
+                     torch.from_numpy(item_feat).to(DEV), torch.from_numpy(user_feat).to(DEV), ut, it)
+    m = _models().GraphNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out = m(g, uid.to(DEV), iid.to(DEV), DEV)
+        assert maxnorm_rel(out, ref) < TOL
+        assert torch.equal(out, m(g, uid.to(DEV), iid.to(DEV), DEV))            # deterministic: no atomics in K3
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        assert maxnorm_rel(m(g, uid.to(DEV), iid.to(DEV), DEV, mask_targets=True), ref_masked) < TOL
+
+
+# ---- backward (interim torch recompute + CUDA SpMM transpose) ------------------------------------------------------------------
+def test_gradients_vs_oracle_autograd():
+    d, sd, kw = load('graph_ncf_hetero_mean')
+    build, _, _ = load('graph_build_binary0')
+    g = _graph_from_golden(build, d)
+    m = _models().GraphNCF(**kw).to(DEV).train()
+    m.load_state_dict(sd)
+    uid, iid = torch.from_numpy(d['userIds']), torch.from_numpy(d['itemIds'])
+    m(g, uid.to(DEV), iid.to(DEV), DEV, mask_targets=False).square().sum().backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    # aliases of the shared conv must be ONE leaf, as in the reference (gnn_ncf.py:227)
+    for k in list(ref_sd):
+        if k.startswith('gnn_convs.1.'):
+            ref_sd[k] = ref_sd[k.replace('gnn_convs.1.', 'gnn_convs.0.')]
+    gd = {k: torch.from_numpy(build[k]) for k in ('user2item_edge_index', 'item2user_edge_index', 'user2item_edge_attr', 'item2user_edge_attr')}
+    gd['item_features'], gd['user_features'] = torch.from_numpy(d['item_features']), torch.from_numpy(d['user_features'])
+    R.graph_ncf_forward(ref_sd, gd, uid, iid, kw['num_gnn_layers']).square().sum().backward()
+    got = dict(m.named_parameters())
+    for k in ('item_embeddings.0.weight', 'user_embeddings.0.bias', 'gnn_convs.0.user2item_W.0.weight', 'gnn_convs.0.item2user_W.0.bias',
+              'MLP.0.weight', 'MLP.6.bias'):
+        assert maxnorm_rel(got[k].grad, ref_sd[k].grad) < 1e-4, k
+
+    da, sda, kwa = load('attention_small_net')
+    ma = _models().AttentionNCF(**kwa).to(DEV).train()
+    ma.load_state_dict(sda)
+    t = [torch.from_numpy(da[k]) for k in ('candidate_items', 'rated_items', 'user_matrix')]
+    ma(*[x.to(DEV) for x in t]).square().sum().backward()
+    ref_a = {k: v.clone().requires_grad_(True) for k, v in sda.items()}
+    R.attention_ncf_forward(ref_a, *t, training=True).square().sum().backward()
+    for k, p in ma.named_parameters():
+        assert maxnorm_rel(p.grad, ref_a[k].grad) < 1e-4, k
