@@ -42,6 +42,7 @@ SIGNATURES = {
     'b200rec_last_error': (C.c_char_p, []),
     'b200rec_version': (c_int, []),
     'b200rec_sm_count': (c_int, []),
+    'b200rec_launch_count': (c_i64, []),
     'b200rec_linear_workspace': (c_sz, [c_i64, c_i64, c_i64]),
     'b200rec_linear': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
     'b200rec_mlp_tower': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_i64, C.POINTER(MlpDesc), c_vp, c_i64, c_vp]),

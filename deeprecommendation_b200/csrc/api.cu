@@ -4,7 +4,12 @@
 
 #include "common.cuh"
 
+#include <atomic>
+
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void b200rec_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int b200rec_set_cuda_error(cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "CUDA error %d: %s", (int)e, cudaGetErrorString(e));
@@ -31,3 +36,4 @@ int b200rec_num_sms() {
 extern "C" const char* b200rec_last_error(void) { return g_err; }
 extern "C" int b200rec_version(void) { return B200REC_VERSION; }
 extern "C" int b200rec_sm_count(void) { return b200rec_num_sms(); }
+extern "C" int64_t b200rec_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }

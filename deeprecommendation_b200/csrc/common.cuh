@@ -6,10 +6,12 @@
 
 #include "../../include/b200rec.h"
 
+// placed after EVERY kernel launch: checks the launch and counts it (b200rec_launch_count, bench.py's gpu_launches)
 #define B200REC_CHECK_LAUNCH()                                   \
   do {                                                           \
     cudaError_t e__ = cudaGetLastError();                        \
     if (e__ != cudaSuccess) return b200rec_set_cuda_error(e__);  \
+    b200rec_count_launch();                                      \
   } while (0)
 
 #define B200REC_CUDA(call)                                       \
@@ -20,6 +22,7 @@
 
 int b200rec_set_cuda_error(cudaError_t e);          // api.cu: records the message, returns B200REC_ERR_CUDA
 int b200rec_fail(int code, const char* msg);        // api.cu: records msg, returns code
+void b200rec_count_launch();                        // api.cu
 
 static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
 

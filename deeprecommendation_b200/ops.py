@@ -17,6 +17,53 @@ import torch
 from . import _lib as L
 
 
+class OpTimer:
+    """Optional per-op CUDA-event timing on the launching stream (bench.py's roofline leg).  Off by default."""
+
+    def __init__(self):
+        self.records = []          # (name, meta, start_event, end_event)
+
+    def summary(self):
+        """{(name, meta): [ms, ...]} — call after a synchronize."""
+        out = {}
+        for name, meta, a, b in self.records:
+            out.setdefault((name, meta), []).append(a.elapsed_time(b))
+        return out
+
+
+_timer = None
+
+
+def set_timer(timer):
+    """Install (or remove with None) an OpTimer; returns the previous one."""
+    global _timer
+    prev, _timer = _timer, timer
+    return prev
+
+
+class _timed:
+    def __init__(self, name, meta=()):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if _timer is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timer is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _timer.records.append((self.name, self.meta, self.a, b))
+        return False
+
+
+def launch_count() -> int:
+    """Kernels launched by libb200rec in this process so far."""
+    return int(L.lib().b200rec_launch_count())
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -75,7 +122,7 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     lib = L.lib()
     ws_bytes = lib.b200rec_linear_workspace(M, N, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed('linear', (M, K, N)):
         L.check(lib.b200rec_linear(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                    _dtype_code(out.dtype), _ptr(ws), ws_bytes, _stream()), 'linear')
     return out
@@ -148,7 +195,7 @@ def mlp_tower_raw(in0, in1, weights, biases, idx0=None, idx1=None):
     if idx1 is not None:
         idx1 = idx1.contiguous().long()
     out = torch.empty((B, prev), dtype=torch.float32, device=in0.device)
-    with torch.cuda.device(in0.device):
+    with torch.cuda.device(in0.device), _timed('mlp_tower', (B, E0 + E1)):
         L.check(L.lib().b200rec_mlp_tower(_ptr(in0), ld0, _ptr(idx0), E0, _ptr(in1), ld1, _ptr(idx1), E1, B, C.byref(d), _ptr(out),
                                          prev, _stream()), 'mlp_tower')
     return out
@@ -276,7 +323,7 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
         d.train_cand_emb, d.train_rated_emb, d.E, d.atol, d.rtol = Ec.data_ptr(), Er.data_ptr(), Ec.shape[1], atol, rtol
     d.drop_zero_scores = int(drop_zero_scores)
     d.score_scale = float(score_scale)
-    with torch.cuda.device(Pc.device):
+    with torch.cuda.device(Pc.device), _timed('attention_pool', (B, I, H, U)):
         L.check(L.lib().b200rec_attention_pool(C.byref(d), _stream()), 'attention_pool')
     return (out, att) if return_attention_weights else out
 
@@ -315,7 +362,7 @@ def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, 
         d.multi_row, d.multi_first_slot, d.multi_n_slots = (index.multi_row.data_ptr(), index.multi_first_slot.data_ptr(),
                                                             index.multi_n_slots.data_ptr())
     d.n_multi = index.n_multi
-    with torch.cuda.device(t.device):
+    with torch.cuda.device(t.device), _timed('spmm', (index.e1 + index.e2, t.shape[1])):
         L.check(L.lib().b200rec_spmm(C.byref(d), _stream()), 'spmm')
 
 

@@ -35,6 +35,7 @@ enum { B200REC_ATT_NET = 0, B200REC_ATT_DOT = 1 };
 const char* b200rec_last_error(void);
 int b200rec_version(void);
 int b200rec_sm_count(void);
+int64_t b200rec_launch_count(void); /* kernels launched by this library in this process so far */
 
 /* ---- K1a  linear layer:  Y = act((X · Wᵀ + bias) ∘ row_scale) ---------------------------------------------------
  * Replaces nn.Linear at models/basic_ncf.py:38-39, models/attention_ncf.py:150-151,216, models/gnn_ncf.py:300-301 and

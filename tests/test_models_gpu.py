@@ -283,5 +283,7 @@ def test_gradients_vs_oracle_autograd():
     ma(*[x.to(DEV) for x in t]).square().sum().backward()
     ref_a = {k: v.clone().requires_grad_(True) for k, v in sda.items()}
     R.attention_ncf_forward(ref_a, *t, training=True).square().sum().backward()
+    scale = max(float(v.grad.abs().max()) for v in ref_a.values())
     for k, p in ma.named_parameters():
-        assert maxnorm_rel(p.grad, ref_a[k].grad) < 1e-4, k
+        # AttentionNet.3.bias shifts every score of a row equally: its true gradient is 0 (softmax shift invariance)
+        assert float((p.grad.cpu() - ref_a[k].grad).abs().max()) < 1e-4 * max(float(ref_a[k].grad.abs().max()), 1e-4 * scale), k

@@ -1,0 +1,93 @@
+"""Host-side logic that needs no GPU: the dynamic collate (a-8) against the reference's golden output, the datasets'
+collate / do_forward contract, and checkpoint round trips with the reference's key names."""
+import io
+
+import numpy as np
+import pandas as pd
+import torch
+
+from deeprecommendation_b200.content_providers import ArrayDynamicProvider, ArrayProfilesProvider
+from deeprecommendation_b200.neural_collaborative_filtering.datasets.dynamic_datasets import DynamicPointwiseDataset
+from deeprecommendation_b200.neural_collaborative_filtering.datasets.fixed_datasets import FixedPointwiseDataset
+from deeprecommendation_b200.neural_collaborative_filtering.models import AttentionNCF, BasicNCF, GraphNCF
+from deeprecommendation_b200.neural_collaborative_filtering.util import load_model
+from tests._golden import load
+
+
+def _provider(d):
+    n_items, n_users = d['profiles'].shape[0], len(d['mean_rating'])
+    return ArrayDynamicProvider(np.arange(n_items), d['profiles'], np.arange(n_users), d['row_ptr'], d['rated_idx'], d['rated_rating'])
+
+
+def test_collate_bit_exact_vs_reference():
+    d, _, _ = load('collate')
+    p = _provider(d)
+    assert np.array_equal(p.mean_rating, d['mean_rating'])
+    batch = [(int(u), int(i), 3.5) for u, i in zip(d['batch_users'], d['batch_items'])]
+    cand_ids, rated_ids, cand, rated, um, tgt = p.collate_interacted_items(batch, for_ranking=False)
+    assert np.array_equal(rated_ids, d['rated_items_idx']) and np.array_equal(cand_ids, d['batch_items'])
+    for got, key in ((cand, 'candidate_items'), (rated, 'rated_items'), (um, 'user_matrix')):
+        assert got.dtype == torch.float32
+        assert np.array_equal(got.numpy().view(np.int32), d[key].view(np.int32)), key
+    assert tgt.tolist() == [3.5] * len(batch)
+    # ranking form: the third element becomes the second candidate's profiles
+    out = p.collate_interacted_items([(0, 1, 2), (3, 4, 5)], for_ranking=True)
+    assert out[5].shape == (2, d['profiles'].shape[1])
+
+
+def test_dataset_contract_with_dataloader():
+    d, _, _ = load('collate')
+    p = _provider(d)
+    frame = pd.DataFrame({'userId': d['batch_users'], 'movieId': d['batch_items'], 'rating': np.linspace(1, 4, len(d['batch_users']))})
+    ds = DynamicPointwiseDataset(frame, p)
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, collate_fn=ds.use_collate())
+    batches = list(loader)
+    assert len(batches) == 2 and len(batches[0]) == 6 and batches[0][4].shape[0] == 4
+    calls = []
+
+    class Probe(torch.nn.Module):
+        def forward(self, cand, rated, um, return_attention_weights=False):
+            calls.append((cand.dtype, cand.shape, rated.shape, um.shape))
+            out = torch.zeros(cand.shape[0], 1)
+            return (out, torch.zeros_like(um)) if return_attention_weights else out
+    out, y = DynamicPointwiseDataset.do_forward(Probe(), batches[0], 'cpu')
+    assert out.shape == (4, 1) and y.shape == (4,) and calls[0][0] == torch.float32
+    res = DynamicPointwiseDataset.do_forward(Probe(), batches[0], 'cpu', return_attention_weights=True)
+    assert len(res) == 6
+    assert float(ds.calculate_loss(torch.ones(4, 1), torch.tensor([1., 2., 3., 4.]))) == 14.0    # MSE, reduction='sum'
+
+    fp = ArrayProfilesProvider(np.arange(30), d['profiles'], np.arange(12), np.ones((12, 5)))
+    fds = FixedPointwiseDataset(frame, fp)
+    b = next(iter(torch.utils.data.DataLoader(fds, batch_size=3, collate_fn=fds.use_collate())))
+    assert b[0].shape == (3, 5) and b[1].shape == (3, d['profiles'].shape[1]) and b[2].shape == (3,)
+
+
+def test_compatibility_checks_and_hyperparams():
+    from deeprecommendation_b200.neural_collaborative_filtering.datasets import fixed_datasets, dynamic_datasets, gnn_datasets
+    b = BasicNCF(8, 8, item_emb=4, user_emb=4, mlp_dense_layers=[8])
+    a = AttentionNCF(8, 4, 4, att_dense=4, mlp_dense_layers=[8])
+    g = GraphNCF(8, 8, 2, True, node_emb=4, mlp_dense_layers=[8])
+    assert b.is_dataset_compatible(fixed_datasets.FixedPointwiseDataset) and not b.is_dataset_compatible(dynamic_datasets.DynamicPointwiseDataset)
+    assert a.is_dataset_compatible(dynamic_datasets.DynamicRankingDataset) and not a.is_dataset_compatible(gnn_datasets.GraphPointwiseDataset)
+    assert g.is_dataset_compatible(gnn_datasets.GraphPointwiseDataset) and not g.is_dataset_compatible(fixed_datasets.FixedRankingDataset)
+    assert a.important_hypeparams() == '_attNet4' and g.important_hypeparams() == '_LightGCN'
+    assert AttentionNCF(8, 4, 4, use_cos_sim_instead=True).important_hypeparams() == '_cosine'
+    assert g.gnn_convs[0] is g.gnn_convs[1]                    # one conv aliased L times (gnn_ncf.py:227)
+    assert set(b.kwargs) == {'item_dim', 'user_dim', 'item_emb', 'user_emb', 'mlp_dense_layers', 'dropout_rate'}
+
+
+def test_checkpoint_round_trip_and_reference_keys():
+    _, sd, kw = load('attention_small_net')
+    m = AttentionNCF(**kw)
+    m.load_state_dict(sd)                                      # the reference's own key names
+    buf = io.BytesIO()
+    m.save_model(buf)
+    buf.seek(0)
+    m2 = load_model(buf, AttentionNCF, map_location='cpu')
+    assert m2.kwargs == m.kwargs
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    _, gsd, gkw = load('graph_ncf_hetero_l3')
+    g = GraphNCF(**gkw)
+    assert set(g.state_dict().keys()) == set(gsd.keys())
+    g.load_state_dict(gsd)
