@@ -142,9 +142,17 @@ def op_breakdown(step_fn, steps, start_index):
         torch.cuda.synchronize()
     finally:
         ops.set_timer(None)
-    agg = {}
+    # batches differ slightly in their row counts (I = size of the rated-item union): group by op and inner dims
+    groups = {}
     for (name, meta), ms in timer.summary().items():
-        agg[(name, meta)] = (float(np.mean(ms)), len(ms) / steps)
+        key = (name, tuple(meta[1:]) if name in ('linear', 'attention_pool') else tuple(meta))
+        g = groups.setdefault(key, {'ms': [], 'rows': []})
+        g['ms'] += ms
+        g['rows'] += [meta[0]] * len(ms)
+    agg = {}
+    for (name, inner), g in groups.items():
+        meta = (int(np.max(g['rows'])),) + inner if name in ('linear', 'attention_pool') else inner
+        agg[(name, meta)] = (float(np.median(g['ms'])), len(g['ms']) / steps)
     return agg
 
 

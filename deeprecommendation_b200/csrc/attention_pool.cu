@@ -13,11 +13,13 @@
 // (cosine variant / att_dense=None variant: s_bi = <P_c[b], P_r[i]>, MODE_DOT, with the host passing
 // normalised embeddings resp. 4-wide [sc,1,0,0]/[1,sr,0,0] rows.)
 //
-// One warp owns one candidate row b.  Non-zeros are consumed 32 at a time: for each of the 32 the warp loads the
+// One CTA owns one candidate row b and each of its 8 warps a contiguous slice of the row (round 1 used one warp per
+// row: 4.6 % warps active, 560 us at B=512 — profiles/r01).  Per warp, non-zeros are consumed 32 at a time: for each of the 32 the warp loads the
 // P_r row with one coalesced 128-bit load per lane, every lane forms its partial dot product, and a 31-shuffle
 // butterfly reduce-scatter leaves lane j with the full score of non-zero j (1 shuffle per score instead of 5).
 // The softmax is online (running max / denominator, FlashAttention-style rescale), so each segment is read once;
-// pooling re-walks the 32 non-zeros with one coalesced Q-row load each.  Nothing of size (B, I, *) exists.
+// pooling re-walks the 32 non-zeros with one coalesced Q-row load each; the per-warp (max, denominator, pooled vector)
+// states are merged through shared memory at the end.  Nothing of size (B, I, *) exists.
 // Two front-ends feed the same core: a CSR reader (ragged-native entry) and a dense-row scanner that compacts
 // the reference's dense (B, I) `user_matrix` on the fly through a per-warp shared-memory queue (drop-in entry;
 // exact 0.0 means "unrated", attention_ncf.py:158,192).
@@ -27,7 +29,7 @@
 
 namespace b200rec {
 
-constexpr int ATT_WARPS = 4;
+constexpr int ATT_WARPS = 8;      // one CTA per candidate row; the row's non-zeros are split over the warps
 enum { MODE_NET = 0, MODE_DOT = 1 };
 
 struct AttParams {
@@ -189,50 +191,74 @@ struct RowCore {
     }
   }
 
-  __device__ void write_out() {
-    const float inv = l > 0.f ? 1.f / l : 0.f;        // no valid rated item -> weights 0 -> user_emb = b_U (:208-209)
+  // ---- cross-warp merge (one CTA = one candidate row, every warp owns a slice of the row's non-zeros) ----------
+  __device__ void export_state(float* s_m, float* s_l, float* s_acc, int warp) const {
+    if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
 #pragma unroll
-    for (int uv = 0; uv < UV; ++uv) {
-      const int u = lane * 4 + uv * 128;
-      if (u < p.U) {
-        float4 bu = p.bU ? ld4(p.bU + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 o = make_float4(fmaf(acc[uv][0], inv, bu.x), fmaf(acc[uv][1], inv, bu.y), fmaf(acc[uv][2], inv, bu.z),
-                               fmaf(acc[uv][3], inv, bu.w));
-        st4(p.out + (long long)b * p.ldo + u, o);
-      }
-    }
-  }
-
-  __device__ float normalise(float s) const {
-    return (l > 0.f && s != -INFINITY) ? __expf(s - m) / l : 0.f;
+    for (int uv = 0; uv < UV; ++uv)
+      *reinterpret_cast<float4*>(s_acc + (size_t)warp * (UV * 128) + lane * 4 + uv * 128) =
+          make_float4(acc[uv][0], acc[uv][1], acc[uv][2], acc[uv][3]);
   }
 };
+
+// after __syncthreads(): global running max / denominator of the row and the pooled output
+template <int UV>
+__device__ __forceinline__ void merge_and_write(const AttParams& p, int b, const float* s_m, const float* s_l, const float* s_acc,
+                                                float& M, float& Lsum) {
+  M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < ATT_WARPS; ++w) M = fmaxf(M, s_m[w]);
+  float scale[ATT_WARPS];
+  Lsum = 0.f;
+#pragma unroll
+  for (int w = 0; w < ATT_WARPS; ++w) {
+    scale[w] = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - M);
+    Lsum += s_l[w] * scale[w];
+  }
+  const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;      // no valid rated item -> weights 0 -> user_emb = b_U (:208-209)
+  for (int u = threadIdx.x; u < p.U; u += ATT_WARPS * 32) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) a = fmaf(s_acc[(size_t)w * (UV * 128) + u], scale[w], a);
+    p.out[(long long)b * p.ldo + u] = fmaf(a, inv, p.bU ? __ldg(p.bU + u) : 0.f);
+  }
+}
+
+__device__ __forceinline__ float normalise_score(float s, float M, float Lsum) {
+  return (Lsum > 0.f && s != -INFINITY) ? __expf(s - M) / Lsum : 0.f;
+}
 
 // ---- ragged-native front-end: CSR of user_matrix ------------------------------------------------------------
 template <int HV, int UV, int MODE, typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col,
                           const float* __restrict__ val) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5);
-  if (b >= p.B) return;
+  __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];
+  __shared__ __align__(16) float s_acc[ATT_WARPS * UV * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
   RowCore<HV, UV, MODE, T> core(p, lane, b);
   const int start = __ldg(row_ptr + b), end = __ldg(row_ptr + b + 1);
-  for (int k0 = start; k0 < end; k0 += 32) {
+  const int blocks = (end - start + 31) >> 5;
+  const int bpw = (blocks + ATT_WARPS - 1) / ATT_WARPS;
+  const int my_start = start + warp * bpw * 32, my_end = min(end, my_start + bpw * 32);
+  for (int k0 = my_start; k0 < my_end; k0 += 32) {
     const int k = k0 + lane;
     int c = -1;
     float v = 0.f;
-    if (k < end) { c = __ldg(col + k); v = __ldg(val + k); }
-    const bool valid = (k < end) && (v != 0.f);        // an explicit 0.0 in the CSR is "unrated", like the dense form
-    core.batch(valid ? c : -1, valid ? v : 0.f, min(32, end - k0));
+    if (k < my_end) { c = __ldg(col + k); v = __ldg(val + k); }
+    const bool valid = (k < my_end) && (v != 0.f);     // an explicit 0.0 in the CSR is "unrated", like the dense form
+    core.batch(valid ? c : -1, valid ? v : 0.f, min(32, my_end - k0));
   }
-  core.write_out();
+  core.export_state(s_m, s_l, s_acc, warp);
+  __syncthreads();
+  float M, Lsum;
+  merge_and_write<UV>(p, b, s_m, s_l, s_acc, M, Lsum);
   if (p.att != nullptr) {
-    __syncwarp();
-    for (int k = start + lane; k < end; k += 32) {
+    for (int k = my_start + lane; k < my_end; k += 32) {
       if (__ldg(val + k) != 0.f) {
         float* a = p.att + (long long)b * p.I + __ldg(col + k);
-        *a = core.normalise(*a);
+        *a = normalise_score(*a, M, Lsum);
       }
     }
   }
@@ -244,15 +270,20 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_pool_dense_kernel(AttParams p, const float* __restrict__ um, long long ld_um) {
   __shared__ int qcol[ATT_WARPS][64];
   __shared__ float qval[ATT_WARPS][64];
+  __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];
+  __shared__ __align__(16) float s_acc[ATT_WARPS * UV * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * ATT_WARPS + warp;
-  if (b >= p.B) return;
+  const int b = blockIdx.x;
   RowCore<HV, UV, MODE, T> core(p, lane, b);
   const float* __restrict__ row = um + (long long)b * ld_um;
+  // every warp scans a contiguous slice of the row (multiples of 32 columns) and compacts its non-zeros on the fly
+  const int chunks = (p.I + 31) >> 5;
+  const int cpw = (chunks + ATT_WARPS - 1) / ATT_WARPS;
+  const int i_begin = warp * cpw * 32, i_end = min(p.I, i_begin + cpw * 32);
   int qn = 0;
-  for (int i0 = 0; i0 < p.I; i0 += 32) {
+  for (int i0 = i_begin; i0 < i_end; i0 += 32) {
     const int i = i0 + lane;
-    const float v = (i < p.I) ? __ldg(row + i) : 0.f;
+    const float v = (i < i_end) ? __ldg(row + i) : 0.f;
     const bool nz = v != 0.f;
     const unsigned mask = __ballot_sync(FULL, nz);
     if (nz) {
@@ -274,13 +305,16 @@ attention_pool_dense_kernel(AttParams p, const float* __restrict__ um, long long
     }
   }
   if (qn > 0) core.batch(lane < qn ? qcol[warp][lane] : -1, lane < qn ? qval[warp][lane] : 0.f, qn);
-  core.write_out();
+  core.export_state(s_m, s_l, s_acc, warp);
+  __syncthreads();
+  float M, Lsum;
+  merge_and_write<UV>(p, b, s_m, s_l, s_acc, M, Lsum);
   if (p.att != nullptr) {
     __syncwarp();
-    for (int i = lane; i < p.I; i += 32) {
+    for (int i = i_begin + lane; i < i_end; i += 32) {
       if (__ldg(row + i) != 0.f) {
         float* a = p.att + (long long)b * p.I + i;
-        *a = core.normalise(*a);
+        *a = normalise_score(*a, M, Lsum);
       }
     }
   }
@@ -289,7 +323,7 @@ attention_pool_dense_kernel(AttParams p, const float* __restrict__ um, long long
 template <int HV, int UV, int MODE, typename T>
 static int launch_att(const AttParams& p, const float* um, long long ld_um, const int* row_ptr, const int* col,
                       const float* val, cudaStream_t st) {
-  const int grid = ceil_div_i(p.B, ATT_WARPS);
+  const int grid = p.B;
   if (um)
     attention_pool_dense_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, um, ld_um);
   else

@@ -13,12 +13,16 @@
 // heavy-tailed MovieLens degrees (max ~81k) are edge-balanced.  Single-chunk rows are finished in the same
 // kernel; multi-chunk rows write per-chunk partials that a second tiny kernel adds IN CHUNK ORDER — no atomics,
 // bit-reproducible run to run (the reference's GPU scatter-add is not).  Each edge costs one coalesced 128-bit
-// load per lane of the source row (d=128 fp32: 512 B per edge; d=64: two edges per warp step).
+// load per lane of the source row (d=128 fp32: 512 B per edge; d=64: two edges per warp step), staged through a
+// per-warp cp.async ring in shared memory so that 12 row gathers are always in flight per warp (round-1 ncu of the
+// register-staged version: long_scoreboard 6.2 per issue, 37 % warps active, 2.1 ms per layer — profiles/r01).
 #include "common.cuh"
 
 namespace b200rec {
 
-constexpr int SPMM_WARPS = 8;
+constexpr int SPMM_WARPS = 16;     // 512 threads; 2 CTAs per SM (96 KB of shared memory each)
+constexpr int SPMM_NST = 3;        // cp.async stages in flight per warp
+constexpr int FIX_WARPS = 8;
 
 struct SpmmParams {
   const int* chunk_row;
@@ -49,103 +53,169 @@ struct SpmmParams {
   int n_multi;
 };
 
-template <int NV>
-__device__ __forceinline__ void row_epilogue(const SpmmParams& p, int row, int c0, int cstride, const float (&acc)[NV][4]) {
-  const float s = p.dinv ? __ldg(p.dinv + row) : 1.f;
-#pragma unroll
-  for (int nv = 0; nv < NV; ++nv) {
-    const int c = c0 + nv * cstride;
-    if (c < p.d) {
-      float4 v = make_float4(acc[nv][0] * s, acc[nv][1] * s, acc[nv][2] * s, acc[nv][3] * s);
-      if (p.x_next) st4(p.x_next + (long long)row * p.ld_x + c, v);
-      if (p.acc_out) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.acc_in) a = *reinterpret_cast<const float4*>(p.acc_in + (long long)row * p.ld_acc + c);
-        st4(p.acc_out + (long long)row * p.ld_acc + c,
-            make_float4((a.x + v.x) * p.acc_scale, (a.y + v.y) * p.acc_scale, (a.z + v.z) * p.acc_scale,
-                        (a.w + v.w) * p.acc_scale));
-      }
-    }
+// writes 4 consecutive columns [c, c+4) of one finished row
+__device__ __forceinline__ void row_epilogue4(const SpmmParams& p, int row, int c, float s, float4 v) {
+  if (c >= p.d) return;
+  v = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+  if (p.x_next) st4(p.x_next + (long long)row * p.ld_x + c, v);
+  if (p.acc_out) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.acc_in) a = *reinterpret_cast<const float4*>(p.acc_in + (long long)row * p.ld_acc + c);
+    st4(p.acc_out + (long long)row * p.ld_acc + c,
+        make_float4((a.x + v.x) * p.acc_scale, (a.y + v.y) * p.acc_scale, (a.z + v.z) * p.acc_scale, (a.w + v.w) * p.acc_scale));
   }
 }
 
-// G lanes cooperate on one edge (G*4*NV >= d); 32/G edges are in flight per warp step.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <typename T> struct Lane16;
+template <> struct Lane16<float> {
+  static constexpr int VPL = 4;
+  static __device__ __forceinline__ void fma(float (&acc)[4], float w, const float4& raw) {
+    acc[0] = fmaf(w, raw.x, acc[0]); acc[1] = fmaf(w, raw.y, acc[1]); acc[2] = fmaf(w, raw.z, acc[2]); acc[3] = fmaf(w, raw.w, acc[3]);
+  }
+};
+template <> struct Lane16<__nv_bfloat16> {
+  static constexpr int VPL = 8;
+  static __device__ __forceinline__ void fma(float (&acc)[8], float w, const float4& raw) {
+    const unsigned r[4] = {__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fmaf(w, __uint_as_float(r[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(w, __uint_as_float(r[i] & 0xffff0000u), acc[2 * i + 1]);
+    }
+  }
+};
+
+// G lanes cooperate on one edge (each lane owns 16 bytes of the source row; G*16*NV >= row bytes), so 32/G edges
+// advance per warp step.  Source rows are staged global -> shared with cp.async (LDGSTS, no register staging):
+// SPMM_NST stages of SPS steps are always in flight per warp, and every lane reads back exactly the 16 bytes it
+// copied itself, so the pipeline needs no barrier at all — only cp.async.wait_group.
 template <int G, int NV, typename T>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+__global__ void __launch_bounds__(SPMM_WARPS * 32, 2)
 spmm_chunk_kernel(SpmmParams p) {
-  constexpr int EPW = 32 / G;                 // edges per warp step
-  const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  constexpr int EPW = 32 / G;                       // edges per warp step
+  constexpr int SPS = (G == 8) ? 2 : 4;             // steps per stage; NST*SPS*EPW <= 32 keeps issue <= one meta block ahead
+  constexpr int VPL = Lane16<T>::VPL;
+  constexpr int STEP_BYTES = NV * 512;
+  constexpr int WARP_BYTES = SPMM_NST * SPS * STEP_BYTES;
+  static_assert(SPMM_NST * SPS * EPW <= 32, "issue pointer would run more than one 32-edge block ahead");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * SPMM_WARPS + warp;
   if (chunk >= p.n_chunks) return;
   const int g = lane / G, sl = lane % G;
+  unsigned char* wbuf = smem_raw + (size_t)warp * WARP_BYTES + lane * 16;
   const int row = __ldg(p.chunk_row + chunk);
   const int s = __ldg(p.chunk_start + chunk);
   const int e = min(s + p.chunk_size, __ldg(p.row_ptr + row + 1));
+  const int n = e - s;
+  const int nsteps = (n + EPW - 1) / EPW;
+  const int nstages = (nsteps + SPS - 1) / SPS;
   const T* __restrict__ t = reinterpret_cast<const T*>(p.t);
+  bool active[NV];
+  long long coff[NV];
+#pragma unroll
+  for (int nv = 0; nv < NV; ++nv) {
+    const int cidx = (sl + nv * G) * VPL;
+    active[nv] = cidx < p.d;
+    coff[nv] = cidx;
+  }
 
-  float acc[NV][4];
+  float acc[NV][VPL];
 #pragma unroll
   for (int nv = 0; nv < NV; ++nv)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[nv][q] = 0.f;
+    for (int q = 0; q < VPL; ++q) acc[nv][q] = 0.f;
 
-  for (int k0 = s; k0 < e; k0 += 32) {
-    const int cnt = min(32, e - k0);
-    int c = -1;
-    float wv = 0.f;
-    if (lane < cnt) {
-      c = __ldg(p.col + k0 + lane);
-      wv = p.w ? __ldg(p.w + k0 + lane) : 1.f;
+  // edge metadata: lane j of set A/B holds edge (blk*32 + j) of the chunk; invalid / masked edges carry (c=-1, w=0)
+  auto load_meta = [&](int blk, int& c, float& wv) {
+    const int k = s + blk * 32 + lane;
+    c = -1; wv = 0.f;
+    if (k < e) {
+      c = __ldcs(p.col + k);
+      wv = p.w ? __ldcs(p.w + k) : 1.f;
       if (p.skip_bits) {
-        const int pos = __ldg(p.perm + k0 + lane);
+        const int pos = __ldcs(p.perm + k);
         if ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) { wv = 0.f; c = -1; }
       }
     }
+  };
+  int cA, cB, blkA = 0;
+  float wA, wB;
+  load_meta(0, cA, wA);
+  load_meta(1, cB, wB);
+
+  auto issue = [&](int q) {
+    if (q < nstages) {
 #pragma unroll
-    for (int st0 = 0; st0 < G; st0 += 8) {
-      if (st0 * EPW < cnt) {
-        float4 x[8][NV];
-        float ww[8];
+      for (int u = 0; u < SPS; ++u) {
+        const int step = q * SPS + u;
+        const int erel = step * EPW + g;
+        const int blk = (step * EPW) >> 5;                       // warp-uniform
+        const int cc = __shfl_sync(FULL, blk == blkA ? cA : cB, erel & 31);
+        if (cc >= 0) {                                          // also false beyond the chunk (meta lanes hold -1)
+          unsigned char* dst = wbuf + (size_t)((q % SPMM_NST) * SPS + u) * STEP_BYTES;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int src_lane = (st0 + u) * EPW + g;
-          const int cc = __shfl_sync(FULL, c, src_lane);
-          ww[u] = __shfl_sync(FULL, wv, src_lane);
-#pragma unroll
-          for (int nv = 0; nv < NV; ++nv) {
-            const int cidx = sl * 4 + nv * G * 4;
-            x[u][nv] = (cc >= 0 && cidx < p.d) ? ld4(t + (long long)cc * p.ld_t + cidx) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int nv = 0; nv < NV; ++nv)
+            if (active[nv]) cp_async16(dst + nv * 512, t + (long long)cc * p.ld_t + coff[nv]);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-#pragma unroll
-          for (int nv = 0; nv < NV; ++nv) {
-            acc[nv][0] = fmaf(ww[u], x[u][nv].x, acc[nv][0]);
-            acc[nv][1] = fmaf(ww[u], x[u][nv].y, acc[nv][1]);
-            acc[nv][2] = fmaf(ww[u], x[u][nv].z, acc[nv][2]);
-            acc[nv][3] = fmaf(ww[u], x[u][nv].w, acc[nv][3]);
-          }
       }
     }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int q = 0; q < SPMM_NST; ++q) issue(q);
+
+  for (int q = 0; q < nstages; ++q) {
+    const int blk = (q * SPS * EPW) >> 5;
+    if (blk != blkA) {                                           // the consume pointer entered the next 32-edge block
+      cA = cB; wA = wB; blkA = blk;
+      load_meta(blk + 1, cB, wB);
+    }
+    cp_async_wait<SPMM_NST - 1>();
+#pragma unroll
+    for (int u = 0; u < SPS; ++u) {
+      const int step = q * SPS + u;
+      const int erel = step * EPW + g;
+      const float wv = __shfl_sync(FULL, wA, erel & 31);         // consume never leaves block A
+      if (wv != 0.f) {                                           // w == 0: masked, out of range, or a true zero weight
+        const unsigned char* src = wbuf + (size_t)((q % SPMM_NST) * SPS + u) * STEP_BYTES;
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv)
+          if (active[nv]) Lane16<T>::fma(acc[nv], wv, *reinterpret_cast<const float4*>(src + nv * 512));
+      }
+    }
+    issue(q + SPMM_NST);
   }
+  cp_async_wait<0>();
+
   // fold the 32/G edge lanes together (fixed order)
 #pragma unroll
   for (int o = G; o < 32; o <<= 1)
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[nv][q] += __shfl_xor_sync(FULL, acc[nv][q], o);
+      for (int q = 0; q < VPL; ++q) acc[nv][q] += __shfl_xor_sync(FULL, acc[nv][q], o);
 
   if (g == 0) {
     const int slot = __ldg(p.chunk_slot + chunk);
-    if (slot < 0) {
-      row_epilogue<NV>(p, row, sl * 4, G * 4, acc);
-    } else {
+    const float sc = (slot < 0 && p.dinv) ? __ldg(p.dinv + row) : 1.f;
 #pragma unroll
-      for (int nv = 0; nv < NV; ++nv) {
-        const int cidx = sl * 4 + nv * G * 4;
-        if (cidx < p.d) st4(p.partials + (long long)slot * p.d + cidx, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
+    for (int nv = 0; nv < NV; ++nv) {
+#pragma unroll
+      for (int h = 0; h < VPL / 4; ++h) {
+        const int c = (int)coff[nv] + 4 * h;
+        const float4 v = make_float4(acc[nv][4 * h], acc[nv][4 * h + 1], acc[nv][4 * h + 2], acc[nv][4 * h + 3]);
+        if (slot < 0) row_epilogue4(p, row, c, sc, v);
+        else if (c < p.d) st4(p.partials + (long long)slot * p.d + c, v);
       }
     }
   }
@@ -153,10 +223,10 @@ spmm_chunk_kernel(SpmmParams p) {
 
 // rows that were cut into several chunks: add the partials in chunk order, then the same epilogue
 template <int NV>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+__global__ void __launch_bounds__(FIX_WARPS * 32)
 spmm_fixup_kernel(SpmmParams p) {
   const int lane = threadIdx.x & 31;
-  const int m = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  const int m = blockIdx.x * FIX_WARPS + (threadIdx.x >> 5);
   if (m >= p.n_multi) return;
   const int row = __ldg(p.multi_row + m);
   const int first = __ldg(p.multi_first_slot + m), n = __ldg(p.multi_n_slots + m);
@@ -175,26 +245,45 @@ spmm_fixup_kernel(SpmmParams p) {
       }
     }
   }
-  row_epilogue<NV>(p, row, lane * 4, 128, acc);
+  const float sc = p.dinv ? __ldg(p.dinv + row) : 1.f;
+#pragma unroll
+  for (int nv = 0; nv < NV; ++nv)
+    row_epilogue4(p, row, lane * 4 + nv * 128, sc, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
+}
+
+template <int G, int NV, typename T>
+static int launch_chunks(const SpmmParams& p, cudaStream_t st) {
+  constexpr int SPS = (G == 8) ? 2 : 4;
+  const size_t smem = (size_t)SPMM_WARPS * SPMM_NST * SPS * NV * 512;
+  static bool configured = false;          // per instantiation
+  if (!configured) {
+    B200REC_CUDA(cudaFuncSetAttribute(spmm_chunk_kernel<G, NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
+  spmm_chunk_kernel<G, NV, T><<<grid, SPMM_WARPS * 32, smem, st>>>(p);
+  B200REC_CHECK_LAUNCH();
+  return B200REC_OK;
 }
 
 template <typename T>
 static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
-  const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
+  const int row_bytes = p.d * (int)sizeof(T);
   if (p.n_chunks > 0) {
-    if (p.d <= 32) spmm_chunk_kernel<8, 1, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
-    else if (p.d <= 64) spmm_chunk_kernel<16, 1, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
-    else if (p.d <= 128) spmm_chunk_kernel<32, 1, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
-    else if (p.d <= 256) spmm_chunk_kernel<32, 2, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
-    else if (p.d <= 512) spmm_chunk_kernel<32, 4, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    int rc;
+    if (row_bytes <= 128) rc = launch_chunks<8, 1, T>(p, st);
+    else if (row_bytes <= 256) rc = launch_chunks<16, 1, T>(p, st);
+    else if (row_bytes <= 512) rc = launch_chunks<32, 1, T>(p, st);
+    else if (row_bytes <= 1024) rc = launch_chunks<32, 2, T>(p, st);
+    else if (row_bytes <= 2048 && sizeof(T) == 4) rc = launch_chunks<32, 4, T>(p, st);
     else return b200rec_fail(B200REC_ERR_UNSUPPORTED, "spmm: node_emb wider than 512");
-    B200REC_CHECK_LAUNCH();
+    if (rc) return rc;
   }
   if (p.n_multi > 0) {
-    const int g2 = ceil_div_i(p.n_multi, SPMM_WARPS);
-    if (p.d <= 128) spmm_fixup_kernel<1><<<g2, SPMM_WARPS * 32, 0, st>>>(p);
-    else if (p.d <= 256) spmm_fixup_kernel<2><<<g2, SPMM_WARPS * 32, 0, st>>>(p);
-    else spmm_fixup_kernel<4><<<g2, SPMM_WARPS * 32, 0, st>>>(p);
+    const int g2 = ceil_div_i(p.n_multi, FIX_WARPS);
+    if (p.d <= 128) spmm_fixup_kernel<1><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+    else if (p.d <= 256) spmm_fixup_kernel<2><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+    else spmm_fixup_kernel<4><<<g2, FIX_WARPS * 32, 0, st>>>(p);
     B200REC_CHECK_LAUNCH();
   }
   return B200REC_OK;
@@ -206,8 +295,8 @@ using namespace b200rec;
 
 extern "C" int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream) {
   if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: null descriptor");
-  if (a->d <= 0 || (a->d % 4) || a->n_chunks < 0 || a->n_multi < 0 || a->chunk_size <= 0)
-    return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: d must be a positive multiple of 4");
+  if (a->d <= 0 || (a->d % 4) || a->n_chunks < 0 || a->n_multi < 0 || a->chunk_size <= 0 || (a->t_dtype == B200REC_BF16 && (a->d % 8)))
+    return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: d must be a positive multiple of 4 (fp32) / 8 (bf16)");
   if (a->n_chunks == 0) return B200REC_OK;
   if (!a->chunk_row || !a->chunk_start || !a->chunk_slot || !a->row_ptr || !a->col || !a->t)
     return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: null index / feature pointer");
@@ -215,7 +304,7 @@ extern "C" int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream) {
     return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: multi-chunk rows need partials + lists");
   if (a->skip_bits && !a->perm) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: skip bitmap needs perm");
   const int esz = a->t_dtype == B200REC_BF16 ? 2 : 4;
-  if ((uintptr_t)a->t % (4 * esz) || (a->ld_t % 4) || (a->x_next && ((uintptr_t)a->x_next % 16 || a->ld_x % 4)) ||
+  if ((uintptr_t)a->t % 16 || ((a->ld_t * esz) % 16) || (a->ld_t % 4) || (a->x_next && ((uintptr_t)a->x_next % 16 || a->ld_x % 4)) ||
       (a->acc_out && ((uintptr_t)a->acc_out % 16 || a->ld_acc % 4)) || (a->acc_in && (uintptr_t)a->acc_in % 16) ||
       (a->partials && (uintptr_t)a->partials % 16))
     return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: feature pointers / leading dims must allow 128-bit access");
