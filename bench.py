@@ -145,13 +145,23 @@ def op_breakdown(step_fn, steps, start_index):
     # batches differ slightly in their row counts (I = size of the rated-item union): group by op and inner dims
     groups = {}
     for (name, meta), ms in timer.summary().items():
-        key = (name, tuple(meta[1:]) if name in ('linear', 'attention_pool') else tuple(meta))
-        g = groups.setdefault(key, {'ms': [], 'rows': []})
+        if name == 'linear':                       # (M, K, N): M varies with I
+            key, var = (name, tuple(meta[1:])), meta[0]
+        elif name == 'attention_pool':             # (B, I, H, U): I varies
+            key, var = (name, (meta[0],) + tuple(meta[2:])), meta[1]
+        else:
+            key, var = (name, tuple(meta)), None
+        g = groups.setdefault(key, {'ms': [], 'var': []})
         g['ms'] += ms
-        g['rows'] += [meta[0]] * len(ms)
+        g['var'] += [var] * len(ms)
     agg = {}
     for (name, inner), g in groups.items():
-        meta = (int(np.max(g['rows'])),) + inner if name in ('linear', 'attention_pool') else inner
+        if name == 'linear':
+            meta = (int(np.max(g['var'])),) + inner
+        elif name == 'attention_pool':
+            meta = (inner[0], int(np.max(g['var']))) + inner[1:]
+        else:
+            meta = inner
         agg[(name, meta)] = (float(np.median(g['ms'])), len(g['ms']) / steps)
     return agg
 

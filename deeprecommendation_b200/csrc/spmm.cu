@@ -13,15 +13,14 @@
 // heavy-tailed MovieLens degrees (max ~81k) are edge-balanced.  Single-chunk rows are finished in the same
 // kernel; multi-chunk rows write per-chunk partials that a second tiny kernel adds IN CHUNK ORDER — no atomics,
 // bit-reproducible run to run (the reference's GPU scatter-add is not).  Each edge costs one coalesced 128-bit
-// load per lane of the source row (d=128 fp32: 512 B per edge; d=64: two edges per warp step), staged through a
-// per-warp cp.async ring in shared memory so that 12 row gathers are always in flight per warp (round-1 ncu of the
-// register-staged version: long_scoreboard 6.2 per issue, 37 % warps active, 2.1 ms per layer — profiles/r01).
+// load per lane of the source row (d=128 fp32: 512 B per edge; d=64: two edges per warp step), 8 row gathers in
+// flight per warp.  (A cp.async/LDGSTS shared-memory ring was tried and measured 1.5x SLOWER — 3.4 vs 2.25 ms per
+// layer on the MovieLens-25M shape — and was dropped)
 #include "common.cuh"
 
 namespace b200rec {
 
-constexpr int SPMM_WARPS = 16;     // 512 threads; 2 CTAs per SM (96 KB of shared memory each)
-constexpr int SPMM_NST = 3;        // cp.async stages in flight per warp
+constexpr int SPMM_WARPS = 8;
 constexpr int FIX_WARPS = 8;
 
 struct SpmmParams {
@@ -66,25 +65,18 @@ __device__ __forceinline__ void row_epilogue4(const SpmmParams& p, int row, int 
   }
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 template <typename T> struct Lane16;
 template <> struct Lane16<float> {
   static constexpr int VPL = 4;
-  static __device__ __forceinline__ void fma(float (&acc)[4], float w, const float4& raw) {
-    acc[0] = fmaf(w, raw.x, acc[0]); acc[1] = fmaf(w, raw.y, acc[1]); acc[2] = fmaf(w, raw.z, acc[2]); acc[3] = fmaf(w, raw.w, acc[3]);
+  static __device__ __forceinline__ void fma(float (&acc)[4], float w, const uint4& raw) {
+    acc[0] = fmaf(w, __uint_as_float(raw.x), acc[0]); acc[1] = fmaf(w, __uint_as_float(raw.y), acc[1]);
+    acc[2] = fmaf(w, __uint_as_float(raw.z), acc[2]); acc[3] = fmaf(w, __uint_as_float(raw.w), acc[3]);
   }
 };
 template <> struct Lane16<__nv_bfloat16> {
   static constexpr int VPL = 8;
-  static __device__ __forceinline__ void fma(float (&acc)[8], float w, const float4& raw) {
-    const unsigned r[4] = {__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+  static __device__ __forceinline__ void fma(float (&acc)[8], float w, const uint4& raw) {
+    const unsigned r[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       acc[2 * i] = fmaf(w, __uint_as_float(r[i] << 16), acc[2 * i]);
@@ -93,39 +85,34 @@ template <> struct Lane16<__nv_bfloat16> {
   }
 };
 
+__device__ __forceinline__ uint4 ldg16(const unsigned char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
 // G lanes cooperate on one edge (each lane owns 16 bytes of the source row; G*16*NV >= row bytes), so 32/G edges
-// advance per warp step.  Source rows are staged global -> shared with cp.async (LDGSTS, no register staging):
-// SPMM_NST stages of SPS steps are always in flight per warp, and every lane reads back exactly the 16 bytes it
-// copied itself, so the pipeline needs no barrier at all — only cp.async.wait_group.
+// advance per warp step.  The inner loop is branch- and predicate-free: padding / masked edges carry (source 0,
+// weight 0) and lanes beyond the row width read column 0, so every load is valid and the per-edge cost is
+// 2 SHFL + 1 IMAD.WIDE.U32 + 1 LDG.128 + 4 FFMA (the first version spent ~26 instructions per edge on predicated
+// 64-bit address arithmetic and zero-fill moves — profiles/r01).
 template <int G, int NV, typename T>
-__global__ void __launch_bounds__(SPMM_WARPS * 32, 2)
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_chunk_kernel(SpmmParams p) {
   constexpr int EPW = 32 / G;                       // edges per warp step
-  constexpr int SPS = (G == 8) ? 2 : 4;             // steps per stage; NST*SPS*EPW <= 32 keeps issue <= one meta block ahead
   constexpr int VPL = Lane16<T>::VPL;
-  constexpr int STEP_BYTES = NV * 512;
-  constexpr int WARP_BYTES = SPMM_NST * SPS * STEP_BYTES;
-  static_assert(SPMM_NST * SPS * EPW <= 32, "issue pointer would run more than one 32-edge block ahead");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * SPMM_WARPS + warp;
+  constexpr int STEPS = 32 / EPW;                   // warp steps per 32-edge block (= G)
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
   if (chunk >= p.n_chunks) return;
   const int g = lane / G, sl = lane % G;
-  unsigned char* wbuf = smem_raw + (size_t)warp * WARP_BYTES + lane * 16;
   const int row = __ldg(p.chunk_row + chunk);
   const int s = __ldg(p.chunk_start + chunk);
   const int e = min(s + p.chunk_size, __ldg(p.row_ptr + row + 1));
-  const int n = e - s;
-  const int nsteps = (n + EPW - 1) / EPW;
-  const int nstages = (nsteps + SPS - 1) / SPS;
-  const T* __restrict__ t = reinterpret_cast<const T*>(p.t);
+  const unsigned stride_bytes = (unsigned)(p.ld_t * (long long)sizeof(T));
+  const unsigned char* base[NV];
   bool active[NV];
-  long long coff[NV];
 #pragma unroll
   for (int nv = 0; nv < NV; ++nv) {
     const int cidx = (sl + nv * G) * VPL;
     active[nv] = cidx < p.d;
-    coff[nv] = cidx;
+    base[nv] = reinterpret_cast<const unsigned char*>(p.t) + (size_t)(active[nv] ? cidx : 0) * sizeof(T);
   }
 
   float acc[NV][VPL];
@@ -134,69 +121,38 @@ spmm_chunk_kernel(SpmmParams p) {
 #pragma unroll
     for (int q = 0; q < VPL; ++q) acc[nv][q] = 0.f;
 
-  // edge metadata: lane j of set A/B holds edge (blk*32 + j) of the chunk; invalid / masked edges carry (c=-1, w=0)
-  auto load_meta = [&](int blk, int& c, float& wv) {
-    const int k = s + blk * 32 + lane;
-    c = -1; wv = 0.f;
-    if (k < e) {
-      c = __ldcs(p.col + k);
-      wv = p.w ? __ldcs(p.w + k) : 1.f;
+  for (int k0 = s; k0 < e; k0 += 32) {
+    const int cnt = min(32, e - k0);
+    unsigned c = 0u;
+    float wv = 0.f;
+    if (lane < cnt) {
+      c = (unsigned)__ldcs(p.col + k0 + lane);
+      wv = p.w ? __ldcs(p.w + k0 + lane) : 1.f;
       if (p.skip_bits) {
-        const int pos = __ldcs(p.perm + k);
-        if ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) { wv = 0.f; c = -1; }
+        const int pos = __ldcs(p.perm + k0 + lane);
+        if ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) { wv = 0.f; c = 0u; }
       }
     }
-  };
-  int cA, cB, blkA = 0;
-  float wA, wB;
-  load_meta(0, cA, wA);
-  load_meta(1, cB, wB);
-
-  auto issue = [&](int q) {
-    if (q < nstages) {
 #pragma unroll
-      for (int u = 0; u < SPS; ++u) {
-        const int step = q * SPS + u;
-        const int erel = step * EPW + g;
-        const int blk = (step * EPW) >> 5;                       // warp-uniform
-        const int cc = __shfl_sync(FULL, blk == blkA ? cA : cB, erel & 31);
-        if (cc >= 0) {                                          // also false beyond the chunk (meta lanes hold -1)
-          unsigned char* dst = wbuf + (size_t)((q % SPMM_NST) * SPS + u) * STEP_BYTES;
+    for (int st0 = 0; st0 < STEPS; st0 += 8) {
+      if (st0 * EPW < cnt) {                                       // warp-uniform: at most 8 steps of padding per chunk
+        uint4 x[8][NV];
+        float ww[8];
 #pragma unroll
-          for (int nv = 0; nv < NV; ++nv)
-            if (active[nv]) cp_async16(dst + nv * 512, t + (long long)cc * p.ld_t + coff[nv]);
+        for (int u = 0; u < 8; ++u) {
+          const int src_lane = (st0 + u) * EPW + g;
+          const unsigned cc = __shfl_sync(FULL, c, src_lane);
+          ww[u] = __shfl_sync(FULL, wv, src_lane);
+#pragma unroll
+          for (int nv = 0; nv < NV; ++nv) x[u][nv] = ldg16(base[nv] + (unsigned long long)cc * stride_bytes);
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int nv = 0; nv < NV; ++nv) Lane16<T>::fma(acc[nv], ww[u], x[u][nv]);
       }
     }
-    cp_async_commit();
-  };
-
-#pragma unroll
-  for (int q = 0; q < SPMM_NST; ++q) issue(q);
-
-  for (int q = 0; q < nstages; ++q) {
-    const int blk = (q * SPS * EPW) >> 5;
-    if (blk != blkA) {                                           // the consume pointer entered the next 32-edge block
-      cA = cB; wA = wB; blkA = blk;
-      load_meta(blk + 1, cB, wB);
-    }
-    cp_async_wait<SPMM_NST - 1>();
-#pragma unroll
-    for (int u = 0; u < SPS; ++u) {
-      const int step = q * SPS + u;
-      const int erel = step * EPW + g;
-      const float wv = __shfl_sync(FULL, wA, erel & 31);         // consume never leaves block A
-      if (wv != 0.f) {                                           // w == 0: masked, out of range, or a true zero weight
-        const unsigned char* src = wbuf + (size_t)((q % SPMM_NST) * SPS + u) * STEP_BYTES;
-#pragma unroll
-        for (int nv = 0; nv < NV; ++nv)
-          if (active[nv]) Lane16<T>::fma(acc[nv], wv, *reinterpret_cast<const float4*>(src + nv * 512));
-      }
-    }
-    issue(q + SPMM_NST);
   }
-  cp_async_wait<0>();
-
   // fold the 32/G edge lanes together (fixed order)
 #pragma unroll
   for (int o = G; o < 32; o <<= 1)
@@ -210,12 +166,13 @@ spmm_chunk_kernel(SpmmParams p) {
     const float sc = (slot < 0 && p.dinv) ? __ldg(p.dinv + row) : 1.f;
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv) {
+      if (!active[nv]) continue;
 #pragma unroll
       for (int h = 0; h < VPL / 4; ++h) {
-        const int c = (int)coff[nv] + 4 * h;
+        const int c4 = (sl + nv * G) * VPL + 4 * h;
         const float4 v = make_float4(acc[nv][4 * h], acc[nv][4 * h + 1], acc[nv][4 * h + 2], acc[nv][4 * h + 3]);
-        if (slot < 0) row_epilogue4(p, row, c, sc, v);
-        else if (c < p.d) st4(p.partials + (long long)slot * p.d + c, v);
+        if (slot < 0) row_epilogue4(p, row, c4, sc, v);
+        else if (c4 < p.d) st4(p.partials + (long long)slot * p.d + c4, v);
       }
     }
   }
@@ -253,15 +210,8 @@ spmm_fixup_kernel(SpmmParams p) {
 
 template <int G, int NV, typename T>
 static int launch_chunks(const SpmmParams& p, cudaStream_t st) {
-  constexpr int SPS = (G == 8) ? 2 : 4;
-  const size_t smem = (size_t)SPMM_WARPS * SPMM_NST * SPS * NV * 512;
-  static bool configured = false;          // per instantiation
-  if (!configured) {
-    B200REC_CUDA(cudaFuncSetAttribute(spmm_chunk_kernel<G, NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
-  spmm_chunk_kernel<G, NV, T><<<grid, SPMM_WARPS * 32, smem, st>>>(p);
+  spmm_chunk_kernel<G, NV, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }

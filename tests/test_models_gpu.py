@@ -145,7 +145,7 @@ def test_attention_cfg2_ragged_vs_oracle():
         row_ptr = torch.cat((torch.zeros(1, dtype=torch.int64), nz.sum(1).cumsum(0))).int()
         col = nz.nonzero()[:, 1].int()
         csr = ops.attention_pool_raw(Pc, Pr, Q, csr=(row_ptr.to(DEV), col.to(DEV), umt[nz].to(DEV)), **common)
-        assert torch.equal(dense, csr)
+        assert maxnorm_rel(csr, dense) < 1e-6      # same core; the warps slice the row by column (dense) vs by non-zero count (CSR)
         bf = ops.attention_pool_raw(Pc, Pr.bfloat16(), Q.bfloat16(), user_matrix=umt.to(DEV), **common)
         assert maxnorm_rel(bf, dense) < 1e-2                                  # bf16 tables, fp32 accumulate
 
