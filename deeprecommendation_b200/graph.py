@@ -187,19 +187,7 @@ class GraphIndex:
                                           _ptr(attr_i2u) if has_w else None, num_nodes, _ptr(self.row_ptr), _ptr(self.col),
                                           _ptr(self.w), _ptr(self.pos), _ptr(self.deg), _ptr(self.dinv), _ptr(ws), ws.numel(), st),
                     'csr_build')
-            # chunk plan
-            chunk_off, multi_off, slot_off = (_i32(num_nodes + 1, dev) for _ in range(3))
-            pws = _ws(lib.b200rec_spmm_plan_workspace(num_nodes), dev)
-            L.check(lib.b200rec_spmm_plan_count(_ptr(self.row_ptr), num_nodes, chunk, _ptr(chunk_off), _ptr(multi_off), _ptr(slot_off),
-                                                _ptr(pws), pws.numel(), st), 'spmm_plan_count')
-            totals = torch.stack([chunk_off[-1], multi_off[-1], slot_off[-1]]).tolist()     # one D2H sync per graph build
-            self.n_chunks, self.n_multi, self.n_slots = (int(x) for x in totals)
-            self.chunk_row, self.chunk_start, self.chunk_slot = (_i32(self.n_chunks, dev) for _ in range(3))
-            self.multi_row, self.multi_first_slot, self.multi_n_slots = (_i32(max(self.n_multi, 1), dev) for _ in range(3))
-            L.check(lib.b200rec_spmm_plan_fill(_ptr(self.row_ptr), num_nodes, chunk, _ptr(chunk_off), _ptr(multi_off), _ptr(slot_off),
-                                               _ptr(self.chunk_row), _ptr(self.chunk_start), _ptr(self.chunk_slot),
-                                               _ptr(self.multi_row), _ptr(self.multi_first_slot), _ptr(self.multi_n_slots), st),
-                    'spmm_plan_fill')
+        self._build_plan()
         # the two lists mirror each other position by position when nothing was filtered (binary=False)
         self.symmetric = has_w and e1 == e2
         if self.symmetric:
@@ -208,6 +196,26 @@ class GraphIndex:
         else:
             self.w_bwd = None
         self._hash = None
+
+    def _build_plan(self):
+        """SpMM chunk plan (chunk_row / chunk_start / chunk_slot + the multi-chunk row lists) for self.row_ptr."""
+        lib = L.lib()
+        dev = self.row_ptr.device
+        n_rows, chunk = int(self.row_ptr.numel() - 1), self.chunk_size
+        with torch.cuda.device(dev):
+            st = _stream()
+            chunk_off, multi_off, slot_off = (_i32(n_rows + 1, dev) for _ in range(3))
+            pws = _ws(lib.b200rec_spmm_plan_workspace(n_rows), dev)
+            L.check(lib.b200rec_spmm_plan_count(_ptr(self.row_ptr), n_rows, chunk, _ptr(chunk_off), _ptr(multi_off), _ptr(slot_off),
+                                                _ptr(pws), pws.numel(), st), 'spmm_plan_count')
+            totals = torch.stack([chunk_off[-1], multi_off[-1], slot_off[-1]]).tolist()     # one D2H sync per graph build
+            self.n_chunks, self.n_multi, self.n_slots = (int(x) for x in totals)
+            self.chunk_row, self.chunk_start, self.chunk_slot = (_i32(self.n_chunks, dev) for _ in range(3))
+            self.multi_row, self.multi_first_slot, self.multi_n_slots = (_i32(max(self.n_multi, 1), dev) for _ in range(3))
+            L.check(lib.b200rec_spmm_plan_fill(_ptr(self.row_ptr), n_rows, chunk, _ptr(chunk_off), _ptr(multi_off), _ptr(slot_off),
+                                               _ptr(self.chunk_row), _ptr(self.chunk_start), _ptr(self.chunk_slot),
+                                               _ptr(self.multi_row), _ptr(self.multi_first_slot), _ptr(self.multi_n_slots), st),
+                    'spmm_plan_fill')
 
     # (src,dst) -> position in the user2item list: the reference's `pos_df` (graph_providers.py:54)
     def positions(self, user_nodes: torch.Tensor, item_nodes: torch.Tensor) -> torch.Tensor:

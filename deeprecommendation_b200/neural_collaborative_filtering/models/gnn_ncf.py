@@ -154,6 +154,10 @@ class GraphNCF(GNN_NCF):
         return torch.cat(hs, dim=1) if self.concat else torch.mean(torch.stack(hs, dim=0), dim=0)     # :348-351
 
     def forward(self, graph, userIds, itemIds, device=None, mask_targets=True):
+        pg = getattr(graph, '_b200rec_partition', None)
+        if pg is not None and not self.training:      # 1-D row-partitioned multi-GPU propagation (parallel.py)
+            from ...parallel import forward_partitioned
+            return forward_partitioned(self, pg, userIds, itemIds)
         index = get_index(graph)
         skip, dinv = None, index.dinv
         if self.training:

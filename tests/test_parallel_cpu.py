@@ -1,0 +1,96 @@
+"""Host-side logic of the multi-GPU GraphNCF path on CPU: nnz-balanced row partition, slot addressing of the gathered
+feature buffer and the all-gather layout, with world_size-2 (and 3) gloo process groups.  The SpMM arithmetic is emulated
+with torch index_add_ here (the CUDA kernel is covered by the -m gpu tests and tests/mp_graph_check.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from deeprecommendation_b200 import synth
+from deeprecommendation_b200.parallel import RowPartition, split_rows
+from oracle import restatement as R
+
+
+def _graph(seed=5, n_users=300, n_items=200, n=9000):
+    users, items, ratings = synth.interactions_zipf(n_users, n_items, n, seed=seed)
+    g = R.create_graph(users, items, ratings, np.arange(n_users), np.arange(n_items))
+    total = np.concatenate([g['user2item_edge_index'], g['item2user_edge_index']], axis=1)
+    N = n_users + n_items
+    row_ptr, col, perm = R.csr_by_destination(total, N)
+    w = np.concatenate([g['user2item_edge_attr'], g['item2user_edge_attr']])[perm]
+    return torch.from_numpy(row_ptr), torch.from_numpy(col), torch.from_numpy(w), N
+
+
+def _spmm(row_ptr, col, w, feats, n_rows):
+    dst = torch.repeat_interleave(torch.arange(n_rows), row_ptr[1:] - row_ptr[:-1])
+    return torch.zeros(n_rows, feats.shape[1], dtype=torch.float64).index_add_(0, dst, w.double()[:, None] * feats.double()[col])
+
+
+def test_split_rows_balances_edges():
+    row_ptr, col, w, N = _graph()
+    nnz = int(row_ptr[-1])
+    for P in (1, 2, 3, 4, 8):
+        s = split_rows(row_ptr, P)
+        assert s[0] == 0 and s[-1] == N and all(a <= b for a, b in zip(s[:-1], s[1:]))
+        per = [int(row_ptr[b] - row_ptr[a]) for a, b in zip(s[:-1], s[1:])]
+        assert sum(per) == nnz
+        max_deg = int((row_ptr[1:] - row_ptr[:-1]).max())
+        assert max(per) <= nnz / P + max_deg          # no part exceeds its share by more than one row
+    # degenerate: more parts than rows with edges
+    tiny = torch.tensor([0, 0, 5, 5])
+    assert split_rows(tiny, 4)[-1] == 3
+
+
+def test_slot_index_round_trip():
+    part = RowPartition([0, 7, 7, 20, 31], rank=2)
+    ids = torch.arange(31)
+    slots = part.slot_index(ids)
+    assert part.max_rows == 16 and len(torch.unique(slots)) == 31
+    owner = slots // part.max_rows
+    assert owner.tolist() == [0] * 7 + [2] * 13 + [3] * 11
+    assert (slots - owner * part.max_rows).tolist() == list(range(7)) + list(range(13)) + list(range(11))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        row_ptr, col, w, N = _graph()
+        d = 8
+        feats = torch.from_numpy(np.random.default_rng(1).standard_normal((N, d)).astype(np.float32))
+        part = RowPartition(split_rows(row_ptr, world), rank)
+        lrp, lcol, lw = part.local_csr(row_ptr, col, w)
+        # every rank contributes only ITS rows of the features; all-gather into padded slots
+        mine = torch.zeros(part.max_rows, d)
+        mine[:part.rows] = feats[part.r0:part.r1]
+        slots = [torch.zeros(part.max_rows, d) for _ in range(world)]
+        dist.all_gather(slots, mine)
+        gathered = torch.cat(slots)
+        out_own = _spmm(lrp, lcol, lw, gathered, part.rows)
+        # reassemble on every rank and compare with the single-process product
+        pad = torch.zeros(part.max_rows, d, dtype=torch.float64)
+        pad[:part.rows] = out_own
+        outs = [torch.zeros(part.max_rows, d, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(outs, pad)
+        full = torch.cat([o[:b - a] for o, a, b in zip(outs, part.splits[:-1], part.splits[1:])])
+        ref = _spmm(row_ptr, col, w, feats, N)
+        ret[rank] = bool(torch.equal(full, ref)) and int(lcol.numel()) > 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_partitioned_propagation_matches_single_process(world):
+    ret = mp.get_context('spawn').Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world and all(ret.values()), dict(ret)
