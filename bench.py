@@ -145,7 +145,7 @@ def op_breakdown(step_fn, steps, start_index):
     # batches differ slightly in their row counts (I = size of the rated-item union): group by op and inner dims
     groups = {}
     for (name, meta), ms in timer.summary().items():
-        if name == 'linear':                       # (M, K, N): M varies with I
+        if name in ('linear', 'linear_tc'):        # (M, K, N): M varies with I
             key, var = (name, tuple(meta[1:])), meta[0]
         elif name == 'attention_pool':             # (B, I, H, U): I varies
             key, var = (name, (meta[0],) + tuple(meta[2:])), meta[1]
@@ -156,7 +156,7 @@ def op_breakdown(step_fn, steps, start_index):
         g['var'] += [var] * len(ms)
     agg = {}
     for (name, inner), g in groups.items():
-        if name == 'linear':
+        if name in ('linear', 'linear_tc'):
             meta = (int(np.max(g['var'])),) + inner
         elif name == 'attention_pool':
             meta = (inner[0], int(np.max(g['var']))) + inner[1:]
@@ -226,14 +226,15 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     ops_ms = op_breakdown(step, min(steps, nb), 0)
     (name, meta), (kms, per_step) = max(ops_ms.items(), key=lambda kv: kv[1][0] * kv[1][1])
     I_mean = float(np.mean([b[1].shape[0] for b in host]))
-    if name == 'linear':
+    if name in ('linear', 'linear_tc'):
         M, K, N = meta
         alg_bytes = 4.0 * (M * K + N * K + M * N)          # read X and W once, write Y once
-        kname = f'gemm_tn_kernel (K1a linear {M}x{K}->{N}, fp32 FFMA)'
+        kname = (f'gemm_tc_kernel (K1a linear {M}x{K}->{N}, tcgen05 {w.get("gemm", "tf32x3")})' if name == 'linear_tc'
+                 else f'gemm_tn_kernel (K1a linear {M}x{K}->{N}, fp32 FFMA)')
     elif name == 'attention_pool':
         nnz_mean = float(np.mean(w['nnz']))
         alg_bytes = nnz_mean * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)
-        kname = 'attention_pool_dense_kernel (K2)'
+        kname = 'um_compact_kernel + attention_pool_csr_kernel (K2)'
     else:
         alg_bytes, kname = 0.0, name
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
@@ -318,17 +319,39 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
     ids = [(u2i[0][pick[k]].contiguous(), u2i[1][pick[k]].contiguous()) for k in range(pick.shape[0])]
     ids_host = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in ids]
 
-    def step(i):
+    def step_eager(i):
         with torch.no_grad():
             a, b = ids[i % len(ids)]
             return model(graph, a, b, dev)
 
+    # the whole forward (~25 launches + collectives) is captured once and replayed: deeprecommendation_b200/graphed.py
+    from deeprecommendation_b200.graphed import GraphedForward
+    graphed = None
+    if not w.get('eager'):
+        try:
+            graphed = GraphedForward(lambda a, b: model(graph, a, b, dev), *ids[0])
+        except Exception as e:                               # keep the measurement, say what happened
+            w['graph_capture_error'] = repr(e)[:300]
+            graphed = None
+
+    def step(i):
+        if graphed is None:
+            return step_eager(i)
+        return graphed(*ids[i % len(ids)])
+
     ms, launches = timed_steps(step, steps, warmup, dist, dev)
+    if graphed is not None:                                  # replays do not pass through the launch counter
+        l0 = __import__('deeprecommendation_b200.ops', fromlist=['x']).launch_count()
+        step_eager(0)
+        launches = (__import__('deeprecommendation_b200.ops', fromlist=['x']).launch_count() - l0) * steps
 
     def step_e2e(i):
-        with torch.no_grad():
-            a, b = ids_host[i % len(ids)]
-            return model(graph, a.to(dev, non_blocking=True), b.to(dev, non_blocking=True), dev).cpu()
+        a, b = ids_host[i % len(ids)]
+        a, b = a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)
+        if graphed is None:
+            with torch.no_grad():
+                return model(graph, a, b, dev).cpu()
+        return graphed(a, b).cpu()
 
     for i in range(min(warmup, 3)):
         step_e2e(i)
@@ -339,7 +362,7 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
     torch.cuda.synchronize()
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
 
-    ops_ms = op_breakdown(step, min(steps, 4), 0)
+    ops_ms = op_breakdown(step_eager, min(steps, 4), 0)
     spmm = [(k, v) for k, v in ops_ms.items() if k[0] == 'spmm']
     kms = spmm[0][1][0] if spmm else 0.0
     N, d, E2 = index.num_nodes, w['d'], index.e1 + index.e2
@@ -355,7 +378,8 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes), 'features_fit_l2': bool(feat <= l2),
             'gather_inclusive_gbs': round((E2 * 8 + E2 * d * 4) / (kms * 1e-3) / 1e9, 1) if kms > 0 else 0.0,
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
-    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof)
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof,
+                launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
 def cpu_graph(w, sample_frac=0.04, repeats=2):
@@ -511,6 +535,9 @@ def main():
     ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic'])
     ap.add_argument('--graph-scale', type=float, default=1.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
+                    help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
+    ap.add_argument('--eager', action='store_true', help='do not capture the GraphNCF step into a CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -532,10 +559,13 @@ def main():
         dist = dist_mod
     peaks = _peaks()
     result, also = None, []
+    from deeprecommendation_b200 import ops as _ops
+    _ops.set_gemm_engine(args.gemm)
 
     with ClockSampler(local) as clocks:
         if args.workload in ('all', 'attention'):
             w = build_attention(dev, rank)
+            w['gemm'] = args.gemm
             r = run_attention(w, args.steps, args.warmup, dist, dev, peaks)
             pairs = BATCH * args.steps * world
             result = {'metric': 'scored user-item pairs/sec (NCF fwd)', 'value': pairs / (r['ms'] * 1e-3), 'unit': 'pairs/s',
@@ -575,15 +605,17 @@ def main():
             torch.cuda.empty_cache()
         if args.workload in ('all', 'graph'):
             w = build_graph(dev, args.graph_scale, world)
+            w['eager'] = args.eager
             r = run_graph(w, args.steps, args.warmup, dist, dev, peaks)
             msgs = 2.0 * w['E'] * w['L'] * args.steps          # the graph is fixed: strong scaling
             entry = {'metric': 'GNN propagation directed-edge messages/sec (GraphNCF fwd)', 'value': msgs / (r['ms'] * 1e-3),
                      'unit': 'edges/s', 'ms_per_step': r['ms'] / args.steps,
-                     'scaling': 'strong', 'parallelism': f'rows 1-D nnz-partitioned over {world} GPU(s), NCCL all-gather per layer' if world > 1 else 'single GPU',
+                     'scaling': 'strong', 'parallelism': f'item and user rows each 1-D nnz-partitioned over {world} GPUs; two NCCL all-gathers per layer, the larger one hidden behind the first SpMM; batch rows by all-reduce' if world > 1 else 'single GPU',
                      'dtype': 'f32',
                      'config': {'workload': f'configs[2]: GraphNCF L=2 d=128 hetero, synthetic MovieLens-25M shape (nU={w["nU"]}, nI={w["nI"]}, '
                                 f'E={w["E"]}), pre-embedded (N,128) node features, whole-graph propagation + MLP on a batch of 512 per step',
-                                'l2': 'CSR (400 MB) + features (115 MB) > L2', 'index_build_s': round(w['build_s'], 3)},
+                                'l2': 'CSR (400 MB) + features (115 MB) > L2', 'index_build_s': round(w['build_s'], 3),
+                                'launch_mode': r['launch_mode']},
                      'roofline': r['roofline'],
                      'e2e': {'value': msgs / (r['e2e_ms'] * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
                      'gpu_launches': r['launches']}
@@ -594,6 +626,7 @@ def main():
                 result = entry
             else:
                 also.append(entry)
+    result.setdefault('config', {})['gemm_engine'] = args.gemm
     for k, v in (('n_gpus', world), ('steps', args.steps), ('warmup', args.warmup), ('higher_is_better', True), ('vs_baseline', None),
                  ('data', 'synthetic')):
         result.setdefault(k, v)

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libb200rec.so')
 OK, ERR_CUDA, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 F32, BF16 = 0, 1
 ATT_NET, ATT_DOT = 0, 1
+TC_TF32X3, TC_BF16 = 0, 1
 MLP_MAX_LAYERS = 8
 
 c_i64, c_int, c_sz, c_vp, c_f = C.c_int64, C.c_int, C.c_size_t, C.c_void_p, C.c_float
@@ -26,7 +27,7 @@ class AttentionDesc(C.Structure):
                 ('bU', c_vp), ('user_matrix', c_vp), ('ld_user_matrix', c_i64), ('row_ptr', c_vp), ('col', c_vp), ('val', c_vp),
                 ('B', c_i64), ('I', c_i64), ('H', c_int), ('U', c_int), ('out', c_vp), ('ldo', c_i64), ('att_weights', c_vp),
                 ('train_cand_emb', c_vp), ('train_rated_emb', c_vp), ('E', c_int), ('atol', c_f), ('rtol', c_f),
-                ('drop_zero_scores', c_int), ('score_scale', c_f), ('ld_pr', c_i64), ('ld_q', c_i64)]
+                ('drop_zero_scores', c_int), ('score_scale', c_f), ('ld_pr', c_i64), ('ld_q', c_i64), ('workspace', c_vp), ('workspace_bytes', c_sz)]
 
 
 class SpmmDesc(C.Structure):
@@ -45,8 +46,10 @@ SIGNATURES = {
     'b200rec_launch_count': (c_i64, []),
     'b200rec_linear_workspace': (c_sz, [c_i64, c_i64, c_i64]),
     'b200rec_linear': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
+    'b200rec_linear_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
     'b200rec_mlp_tower': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_i64, C.POINTER(MlpDesc), c_vp, c_i64, c_vp]),
     'b200rec_rowdot': (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp]),
+    'b200rec_attention_pool_workspace': (c_sz, [c_i64, c_i64]),
     'b200rec_attention_pool': (c_int, [C.POINTER(AttentionDesc), c_vp]),
     'b200rec_spmm': (c_int, [C.POINTER(SpmmDesc), c_vp]),
     'b200rec_scan_workspace': (c_sz, [c_i64]),

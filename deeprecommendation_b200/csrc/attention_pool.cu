@@ -232,34 +232,92 @@ __device__ __forceinline__ float normalise_score(float s, float M, float Lsum) {
 template <int HV, int UV, int MODE, typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col,
-                          const float* __restrict__ val) {
+                          const float* __restrict__ val, const int* __restrict__ row_nnz, long long padded_stride) {
   __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];
   __shared__ __align__(16) float s_acc[ATT_WARPS * UV * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x;
   RowCore<HV, UV, MODE, T> core(p, lane, b);
-  const int start = __ldg(row_ptr + b), end = __ldg(row_ptr + b + 1);
-  const int blocks = (end - start + 31) >> 5;
+  // either a true CSR (row_ptr) or the row-padded form written by um_compact_kernel (row b starts at b*stride)
+  const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
+  const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
+  const int blocks = (int)((end - start + 31) >> 5);
   const int bpw = (blocks + ATT_WARPS - 1) / ATT_WARPS;
-  const int my_start = start + warp * bpw * 32, my_end = min(end, my_start + bpw * 32);
-  for (int k0 = my_start; k0 < my_end; k0 += 32) {
-    const int k = k0 + lane;
+  const long long my_start = start + (long long)warp * bpw * 32, my_end = min(end, my_start + (long long)bpw * 32);
+  for (long long k0 = my_start; k0 < my_end; k0 += 32) {
+    const long long k = k0 + lane;
     int c = -1;
     float v = 0.f;
     if (k < my_end) { c = __ldg(col + k); v = __ldg(val + k); }
     const bool valid = (k < my_end) && (v != 0.f);     // an explicit 0.0 in the CSR is "unrated", like the dense form
-    core.batch(valid ? c : -1, valid ? v : 0.f, min(32, my_end - k0));
+    core.batch(valid ? c : -1, valid ? v : 0.f, (int)min(32LL, my_end - k0));
   }
   core.export_state(s_m, s_l, s_acc, warp);
   __syncthreads();
   float M, Lsum;
   merge_and_write<UV>(p, b, s_m, s_l, s_acc, M, Lsum);
   if (p.att != nullptr) {
-    for (int k = my_start + lane; k < my_end; k += 32) {
+    for (long long k = my_start + lane; k < my_end; k += 32) {
       if (__ldg(val + k) != 0.f) {
         float* a = p.att + (long long)b * p.I + __ldg(col + k);
         *a = normalise_score(*a, M, Lsum);
       }
+    }
+  }
+}
+
+// ---- dense (B, I) user_matrix -> row-padded (col, val) lists + per-row counts ---------------------------------
+// One CTA per row; pure streaming (four independent coalesced loads per thread and iteration, no dependent work), so
+// the dense scan costs a few microseconds instead of sitting on the critical path of the pooling kernel, and the
+// pooling kernel can split every row's non-zeros EVENLY over its warps.
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __restrict__ col, float* __restrict__ val,
+                  int* __restrict__ row_nnz) {
+  __shared__ int s_cnt[ATT_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const float* __restrict__ row = um + (long long)b * ld_um;
+  const int chunks = (I + 31) >> 5;
+  const int cpw = (chunks + ATT_WARPS - 1) / ATT_WARPS;
+  const int i_begin = warp * cpw * 32, i_end = min(I, i_begin + cpw * 32);
+  int cnt = 0;
+  for (int i0 = i_begin; i0 < i_end; i0 += 128) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 + lane;
+      v[u] = (i < i_end) ? __ldg(row + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cnt += __popc(__ballot_sync(FULL, v[u] != 0.f));
+  }
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < ATT_WARPS; ++w) {
+    if (w < warp) base += s_cnt[w];
+    total += s_cnt[w];
+  }
+  if (threadIdx.x == 0) row_nnz[b] = total;
+  long long out = (long long)b * I + base;
+  for (int i0 = i_begin; i0 < i_end; i0 += 128) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 + lane;
+      v[u] = (i < i_end) ? __ldg(row + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool nz = v[u] != 0.f;
+      const unsigned mask = __ballot_sync(FULL, nz);
+      if (nz) {
+        const long long pos = out + __popc(mask & ((1u << lane) - 1u));
+        col[pos] = i0 + u * 32 + lane;
+        val[pos] = v[u];
+      }
+      out += __popc(mask);
     }
   }
 }
@@ -320,31 +378,50 @@ attention_pool_dense_kernel(AttParams p, const float* __restrict__ um, long long
   }
 }
 
+struct AttInputs {
+  const float* um; long long ld_um;
+  const int* row_ptr; const int* col; const float* val;
+  void* ws; size_t ws_bytes;
+};
+
+static size_t att_workspace_bytes(long long B, long long I) {
+  return (size_t)(B * I) * (sizeof(int) + sizeof(float)) + (size_t)B * sizeof(int) + 64;
+}
+
 template <int HV, int UV, int MODE, typename T>
-static int launch_att(const AttParams& p, const float* um, long long ld_um, const int* row_ptr, const int* col,
-                      const float* val, cudaStream_t st) {
+static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) {
   const int grid = p.B;
-  if (um)
-    attention_pool_dense_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, um, ld_um);
-  else
-    attention_pool_csr_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, row_ptr, col, val);
+  if (in.um && in.ws && in.ws_bytes >= att_workspace_bytes(p.B, p.I)) {
+    // two kernels: streaming compaction of the dense matrix, then the balanced ragged kernel
+    int* ccol = reinterpret_cast<int*>(in.ws);
+    float* cval = reinterpret_cast<float*>(ccol + (size_t)p.B * p.I);
+    int* cnnz = reinterpret_cast<int*>(cval + (size_t)p.B * p.I);
+    um_compact_kernel<<<grid, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, ccol, cval, cnnz);
+    B200REC_CHECK_LAUNCH();
+    attention_pool_csr_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, nullptr, ccol, cval, cnnz, p.I);
+  } else if (in.um) {
+    attention_pool_dense_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, in.um, in.ld_um);
+  } else {
+    attention_pool_csr_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, in.row_ptr, in.col, in.val, nullptr, 0);
+  }
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
 template <int MODE, typename T>
-static int dispatch_att(const AttParams& p, const float* um, long long ld_um, const int* row_ptr, const int* col,
-                        const float* val, cudaStream_t st) {
+static int dispatch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) {
   const int w = p.H > p.U ? p.H : p.U;
-  if (w <= 128) return launch_att<1, 1, MODE, T>(p, um, ld_um, row_ptr, col, val, st);
-  if (w <= 256) return launch_att<2, 2, MODE, T>(p, um, ld_um, row_ptr, col, val, st);
-  if (w <= 512) return launch_att<4, 4, MODE, T>(p, um, ld_um, row_ptr, col, val, st);
+  if (w <= 128) return launch_att<1, 1, MODE, T>(p, in, st);
+  if (w <= 256) return launch_att<2, 2, MODE, T>(p, in, st);
+  if (w <= 512) return launch_att<4, 4, MODE, T>(p, in, st);
   return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: att_dense / user_emb wider than 512");
 }
 
 }  // namespace b200rec
 
 using namespace b200rec;
+
+extern "C" size_t b200rec_attention_pool_workspace(int64_t B, int64_t I) { return (B > 0 && I > 0) ? att_workspace_bytes(B, I) : 0; }
 
 extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream) {
   if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: null descriptor");
@@ -373,12 +450,13 @@ extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stre
   if (p.Ec && (!p.Er || p.E <= 0)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: training mask needs both embeddings");
   cudaStream_t st = (cudaStream_t)stream;
   const long long ld_um = a->user_matrix ? (a->ld_user_matrix ? a->ld_user_matrix : a->I) : 0;
+  AttInputs in{a->user_matrix, ld_um, a->row_ptr, a->col, a->val, a->workspace, a->workspace_bytes};
   if (a->table_dtype == B200REC_F32) {
-    if (a->mode == MODE_NET) return dispatch_att<MODE_NET, float>(p, a->user_matrix, ld_um, a->row_ptr, a->col, a->val, st);
-    if (a->mode == MODE_DOT) return dispatch_att<MODE_DOT, float>(p, a->user_matrix, ld_um, a->row_ptr, a->col, a->val, st);
+    if (a->mode == MODE_NET) return dispatch_att<MODE_NET, float>(p, in, st);
+    if (a->mode == MODE_DOT) return dispatch_att<MODE_DOT, float>(p, in, st);
   } else if (a->table_dtype == B200REC_BF16) {
-    if (a->mode == MODE_NET) return dispatch_att<MODE_NET, __nv_bfloat16>(p, a->user_matrix, ld_um, a->row_ptr, a->col, a->val, st);
-    if (a->mode == MODE_DOT) return dispatch_att<MODE_DOT, __nv_bfloat16>(p, a->user_matrix, ld_um, a->row_ptr, a->col, a->val, st);
+    if (a->mode == MODE_NET) return dispatch_att<MODE_NET, __nv_bfloat16>(p, in, st);
+    if (a->mode == MODE_DOT) return dispatch_att<MODE_DOT, __nv_bfloat16>(p, in, st);
   }
   return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: bad mode / table_dtype");
 }

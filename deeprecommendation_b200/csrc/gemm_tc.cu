@@ -1,0 +1,453 @@
+// K1a on the 5th-generation tensor cores:  Y = act((X · Wᵀ + bias) ∘ row_scale)  with tcgen05.mma + TMEM accumulators.
+//
+// Why the operands are NOT moved by TMA: the reference's profile width F = 2094 makes row pitches of 8376 bytes — not a
+// multiple of 16, which cuTensorMapEncodeTiled requires — and the inputs arrive as fp32 while the MMA wants bf16 or a
+// TF32 hi/lo split.  So eight producer warps read X and W with 64-bit loads, convert in registers and write the tiles
+// straight into the canonical K-major SWIZZLE_128B shared-memory layout (16-byte chunk c of row r lives at chunk c^(r&7)
+// of its 128-byte row; 8-row groups are 1024 B apart), publish them to the async proxy with fence.proxy.async and an
+// mbarrier, and one elected thread of a ninth warp issues the MMAs.  HBM traffic is the compulsory one: every input
+// byte is read once as fp32, nothing is staged through a converted copy.
+//
+// Two arithmetic modes on the same skeleton:
+//   TC_TF32X3 (fp32 parity, default): x = hi + lo with hi = round-to-TF32(x); D += A_hi·B_hi + A_hi·B_lo + A_lo·B_hi
+//             (kind::tf32, fp32 accumulate in TMEM).  The dropped lo·lo term and the truncation of lo are ~2^-21
+//             relative, i.e. inside the reference tolerance rel <= 1e-5.
+//   TC_BF16   (bf16 mode, rel <= 1e-2): one kind::f16 MMA per k-step on bf16-rounded operands.
+//
+// CTA = 128 (M) x 128 (N) output tile, accumulator = 128 TMEM columns x 128 lanes (fp32), NSTAGE-deep smem ring.
+// Warp roles: warps 0-7 producers, then epilogue (tcgen05.ld 32x32b: warp w reads TMEM lanes 32*(w%4).., columns
+// 64*(w/4)..); warp 8 allocates TMEM and issues tcgen05.mma / tcgen05.commit.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace b200rec {
+
+enum { TC_TF32X3 = 0, TC_BF16 = 1 };
+
+constexpr int TC_BM = 128, TC_BN = 128;
+constexpr int TC_PRODUCERS = 256;                 // 8 warps
+constexpr int TC_THREADS = TC_PRODUCERS + 32;     // + MMA warp
+constexpr int TILE_BYTES = 128 * 128;             // one operand tile: 128 rows x 128 bytes
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "LAB_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int MODE>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (MODE == TC_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B >> 4 in [32,46), version = 1 in [46,48),
+// layout_type = 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffff) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format at [7,10)/[10,13)
+// (BF16 = 1, TF32 = 2), both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+template <int MODE>
+__device__ __forceinline__ uint32_t make_idesc() {
+  const uint32_t fmt = (MODE == TC_BF16) ? 1u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_round(float x) {
+  // round-to-nearest (ties away) on the 13 dropped mantissa bits; inf/nan pass through unchanged enough for our inputs
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+struct TcParams {
+  const float* X; long long ldx;
+  const float* W; long long ldw;
+  int M, N, K;
+  void* Y; long long ldy; int y_bf16;
+  const float* bias; const float* row_scale; int relu;
+  int dbg;     // experiments only (B200REC_TC_DBG): 1 = no MMA, 2 = no prefetch loads, 4 = no proxy fence
+};
+
+// One operand tile (128 rows x KB fp32 source elements) -> smem by the 256 producer threads, COALESCED: a warp owns 16
+// consecutive rows; in one load instruction its lanes cover 32/LPR rows x KB contiguous floats (EPL = 2 or 4 floats per
+// lane, LPR = KB/EPL lanes per row).  Everything that does not depend on the k-block — clamped global row offsets, the
+// swizzled shared-memory offsets, the row-validity bits — is computed ONCE per thread (TileAddr); per k-block a load costs
+// IADD + IMAD.WIDE + LDG and a store LOP/FADD + STS.  History (profiles/r01/gemm_tc_notes.md): half-row-per-thread loads
+// sat on the L1 tag stage; per-load bounds branches made ptxas wrap every LDG in BSSY/BSYNC; recomputing addresses in the
+// loop cost ~1200 instructions per thread and k-block.
+template <int MODE, int EPL>
+struct TileAddr {
+  static constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
+  static constexpr int LPR = KB / EPL, RPI = 32 / LPR, ITER = 16 / RPI;
+  unsigned goff[ITER];        // element offset of (clamped row, this lane's first column at k = 0)
+  unsigned soff[ITER];        // byte offset inside a 128x128-byte swizzled tile
+  unsigned row_ok;            // bit it: the row exists
+  int kcol;                   // this lane's first column inside a k-block
+
+  __device__ __forceinline__ void init(long long ld, int row0, int rows_total, int warp, int lane) {
+    kcol = (lane % LPR) * EPL;
+    row_ok = 0u;
+    const unsigned byte = (unsigned)kcol * ((MODE == TC_BF16) ? 2u : 4u);
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int r = warp * 16 + it * RPI + lane / LPR;
+      const int grow = row0 + r;
+      row_ok |= (grow < rows_total ? 1u : 0u) << it;
+      goff[it] = (unsigned)((long long)min(grow, rows_total - 1) * ld) + (unsigned)kcol;
+      soff[it] = (unsigned)(r >> 3) * 1024u + (unsigned)(r & 7) * 128u + (((byte >> 4) ^ (unsigned)(r & 7)) << 4) + (byte & 15u);
+    }
+  }
+};
+
+template <int MODE, int EPL>
+struct TileRegs {
+  using Addr = TileAddr<MODE, EPL>;
+  static constexpr int ITER = Addr::ITER;
+  float v[ITER][EPL];
+  bool k_ok;
+
+  // vector path: K % EPL == 0 (launcher), so a vector is entirely inside or outside [0, K)
+  template <bool VEC>
+  __device__ __forceinline__ void load(const float* __restrict__ src, const Addr& a, int k0, int K) {
+    const int k = k0 + a.kcol;
+    k_ok = k < K;
+    if constexpr (VEC) {
+      const unsigned kc = k_ok ? (unsigned)k0 : 0u;      // out-of-range columns re-read k-block 0 and are zeroed at store time
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const float* p = src + (a.goff[it] + kc);
+        if constexpr (EPL == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+          v[it][0] = t.x; v[it][1] = t.y; v[it][2] = t.z; v[it][3] = t.w;
+        } else {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+          v[it][0] = t.x; v[it][1] = t.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const bool ok = k + e < K;
+          const float t = __ldg(src + (a.goff[it] + (ok ? (unsigned)(k0 + e) : 0u)));
+          v[it][e] = ok ? t : 0.f;
+        }
+      }
+      k_ok = true;
+    }
+  }
+
+  __device__ __forceinline__ void store(unsigned char* tile_hi, unsigned char* tile_lo, const Addr& a) const {
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const bool ok = k_ok && ((a.row_ok >> it) & 1u);
+      float x[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) x[e] = ok ? v[it][e] : 0.f;
+      if constexpr (MODE == TC_BF16) {
+        unsigned char* dst = tile_hi + a.soff[it];
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]);
+        if constexpr (EPL == 4) {
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(x[2], x[3]);
+          *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+        } else {
+          *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(&b0);
+        }
+      } else {
+        float hi[EPL], lo[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          hi[e] = tf32_round(x[e]);
+          lo[e] = x[e] - hi[e];
+        }
+        if constexpr (EPL == 4) {
+          *reinterpret_cast<float4*>(tile_hi + a.soff[it]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(tile_lo + a.soff[it]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        } else {
+          *reinterpret_cast<float2*>(tile_hi + a.soff[it]) = make_float2(hi[0], hi[1]);
+          *reinterpret_cast<float2*>(tile_lo + a.soff[it]) = make_float2(lo[0], lo[1]);
+        }
+      }
+    }
+  }
+};
+
+template <int MODE, int NSTAGE, int EPL, bool VEC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(TcParams p) {
+  constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
+  constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
+  constexpr int STAGE_BYTES = 2 * PLANES * TILE_BYTES;          // A (hi[,lo]) + B (hi[,lo])
+  constexpr int UMMA_K_BYTES = 32;                              // 16 bf16 or 8 tf32 per MMA
+  // The tensor core adds into the fp32 accumulator with truncation; over K = 2094 (786 accumulate steps in TF32x3) that
+  // alone costs 1.3e-5 (measured).  TF32x3 therefore spreads the work over FOUR TMEM accumulators — hi·hi alternates
+  // between two per k-block, the small cross terms go to two more — and the epilogue adds them in registers.
+  constexpr int NACC = (MODE == TC_BF16) ? 1 : 4;
+  constexpr int TMEM_COLS = 128 * NACC;
+  extern __shared__ unsigned char smem_dyn[];
+  // SWIZZLE_128B needs 1024-byte aligned tiles
+  unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int num_kb = (p.K + KB - 1) / KB;
+  const int kb_shift = (int)((blockIdx.y * 7u + blockIdx.x * 3u) % (unsigned)num_kb);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_bar[s], TC_PRODUCERS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {   // TMEM: 128 columns per fp32 accumulator (128 lanes x 128 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 8) {
+    // ===================== producers =====================
+    // k-blocks are walked from a per-CTA offset (wrapping around): all CTAs of a wave would otherwise ask L2 for the
+    // SAME W tile at the same moment.  The set of products accumulated is unchanged.
+    constexpr int PF = (MODE == TC_BF16) ? 1 : 2;             // k-blocks of global loads in flight ahead of the store
+    TileAddr<MODE, EPL> aa, ab;
+    aa.init(p.ldx, m0, p.M, warp, lane);
+    ab.init(p.ldw, n0, p.N, warp, lane);
+    TileRegs<MODE, EPL> xa[PF + 1], xb[PF + 1];
+    int kload = kb_shift;                                     // k-block index of the next load
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+      if (d < num_kb) {
+        xa[d].template load<VEC>(p.X, aa, kload * KB, p.K);
+        xb[d].template load<VEC>(p.W, ab, kload * KB, p.K);
+        kload = (kload + 1 == num_kb) ? 0 : kload + 1;
+      }
+    }
+    // The k-loop is unrolled by PF+1 so that the register buffers rotate by NAME: copying them (xa[d] = xa[d+1]) would
+    // make every iteration wait for the loads it has just issued.
+    for (int kb0 = 0; kb0 < num_kb; kb0 += PF + 1) {
+#pragma unroll
+      for (int j = 0; j <= PF; ++j) {
+        const int kb = kb0 + j;
+        if (kb < num_kb) {
+          const int s = kb % NSTAGE;
+          const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
+          if (kb + PF < num_kb && !(p.dbg & 2)) {              // loads of k-block kb+PF fly while kb is converted
+            xa[(j + PF) % (PF + 1)].template load<VEC>(p.X, aa, kload * KB, p.K);
+            xb[(j + PF) % (PF + 1)].template load<VEC>(p.W, ab, kload * KB, p.K);
+            kload = (kload + 1 == num_kb) ? 0 : kload + 1;
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1u);                  // first pass through the ring: returns immediately
+          unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+          xa[j].store(st, st + TILE_BYTES, aa);
+          xb[j].store(st + PLANES * TILE_BYTES, st + (PLANES + 1) * TILE_BYTES, ab);
+          if (!(p.dbg & 4)) fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core
+          mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
+    // ===================== epilogue =====================
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3, chalf = warp >> 2;
+    const int row = m0 + quad * 32 + lane;
+    const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col0 = chalf * 64 + cc * 32;
+      float acc[32];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * 128 + col0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        const bool written = (a & 1) == 0 || num_kb > 1;      // with a single k-block the odd accumulators stay untouched
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = written ? __uint_as_float(r[j]) : 0.f;
+          acc[j] = (a == 0) ? x : acc[j] + x;
+        }
+      }
+      if (row < p.M) {
+        const int gcol0 = n0 + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int gc = gcol0 + j + e;
+            float x = acc[j + e];
+            if (gc < p.N) {
+              if (p.bias) x += __ldg(p.bias + gc);
+              x *= rs;
+              if (p.relu) x = fmaxf(x, 0.f);
+            }
+            o[e] = x;
+          }
+          const int gc = gcol0 + j;
+          if (p.y_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.Y) + (long long)row * p.ldy + gc;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gc + e < p.N) dst[e] = __float2bfloat16_rn(o[e]);
+          } else {
+            float* dst = reinterpret_cast<float*>(p.Y) + (long long)row * p.ldy + gc;
+            if (gc + 3 < p.N && ((((uintptr_t)dst) & 15) == 0)) {
+              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (gc + e < p.N) dst[e] = o[e];
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ===================== MMA issuer (one elected lane) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc<MODE>();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % NSTAGE;
+        const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+        const uint32_t b_hi = a_hi + PLANES * TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 128 / UMMA_K_BYTES; ++ks) {
+          if (p.dbg & 1) break;
+          const uint32_t off = (uint32_t)ks * UMMA_K_BYTES;
+          if constexpr (MODE == TC_BF16) {
+            umma<MODE>(tmem_base, make_desc(a_hi + off), make_desc(b_hi + off), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          } else {
+            const uint32_t a_lo = a_hi + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+            const uint32_t d_main = tmem_base + (uint32_t)((kb & 1) * 128);          // accumulators 0 / 1
+            const uint32_t d_cross = tmem_base + (uint32_t)(256 + (kb & 1) * 128);   // accumulators 2 / 3
+            const uint32_t first = (kb > 1 || ks > 0) ? 1u : 0u;                     // k-blocks 0 and 1 start their accumulators
+            umma<MODE>(d_main, make_desc(a_hi + off), make_desc(b_hi + off), idesc, first);    // hi·hi
+            umma<MODE>(d_cross, make_desc(a_hi + off), make_desc(b_lo + off), idesc, first);   // hi·lo
+            umma<MODE>(d_cross, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);      // lo·hi
+          }
+        }
+        umma_commit(&empty_bar[s]);          // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(&accum_bar);               // accumulator complete
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int MODE, int EPL, bool VEC>
+static int launch_tc_epl(const TcParams& p, cudaStream_t st) {
+  constexpr int NSTAGE = (MODE == TC_BF16) ? 4 : 3;
+  constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
+  const size_t smem = (size_t)NSTAGE * 2 * PLANES * TILE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200REC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, NSTAGE, EPL, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div_i(p.N, TC_BN), ceil_div_i(p.M, TC_BM));
+  gemm_tc_kernel<MODE, NSTAGE, EPL, VEC><<<grid, TC_THREADS, smem, st>>>(p);
+  B200REC_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+template <int MODE>
+static int launch_tc(const TcParams& p, cudaStream_t st) {
+  auto aligned = [&](int n) {
+    return (p.K % n) == 0 && (p.ldx % n) == 0 && (p.ldw % n) == 0 && ((uintptr_t)p.X % (4 * n)) == 0 && ((uintptr_t)p.W % (4 * n)) == 0;
+  };
+  if (aligned(4)) return launch_tc_epl<MODE, 4, true>(p, st);        // 128-bit loads (e.g. K = 128 transforms)
+  if (aligned(2)) return launch_tc_epl<MODE, 2, true>(p, st);        // 64-bit loads (F = 2094)
+  return launch_tc_epl<MODE, 2, false>(p, st);                       // odd K / pitch: scalar loads
+}
+
+}  // namespace b200rec
+
+using namespace b200rec;
+
+extern "C" int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
+                                 const float* bias, const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode,
+                                 b200rec_stream_t stream) {
+  if (M < 0 || N <= 0 || K <= 0 || !W || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad argument");
+  if (M == 0) return B200REC_OK;
+  if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: dim > int32");
+  if (ldx < K || ldw < K || ldy < N) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: leading dimension too small");
+  if (M * ldx >= (1LL << 32) || N * ldw >= (1LL << 32)) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: operand larger than 2^32 elements");
+  if (y_dtype != B200REC_F32 && y_dtype != B200REC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad y_dtype");
+  TcParams p;
+  p.X = X; p.ldx = ldx; p.W = W; p.ldw = ldw; p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.Y = Y; p.ldy = ldy; p.y_bf16 = y_dtype == B200REC_BF16; p.bias = bias; p.row_scale = row_scale; p.relu = relu;
+  {
+    const char* e = getenv("B200REC_TC_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == B200REC_TC_TF32X3) return launch_tc<TC_TF32X3>(p, st);
+  if (mode == B200REC_TC_BF16) return launch_tc<TC_BF16>(p, st);
+  return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad mode");
+}

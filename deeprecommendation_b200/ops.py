@@ -101,8 +101,23 @@ def _dtype_code(dt):
 # ------------------------------------------------------------------------------------------------------------------
 # K1a linear
 # ------------------------------------------------------------------------------------------------------------------
-def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_dtype=torch.float32):
-    """out = act((x @ weight.T + bias) * row_scale[:, None]) — b200rec_linear."""
+# GEMM engine for K1a: 'simt' = fp32 FFMA everywhere; 'tf32x3' / 'bf16' = tcgen05 tensor-core kernel (csrc/gemm_tc.cu) for
+# large M, FFMA for the small ones (a 128-row tile per CTA cannot fill 148 SMs below ~2k rows).
+_gemm_engine = 'simt'
+TC_MIN_ROWS = 2048
+TC_MIN_K = 512          # short-K GEMMs (the d x d GraphNCF transforms) are epilogue/latency-bound: FFMA is as fast there
+
+
+def set_gemm_engine(name: str):
+    global _gemm_engine
+    if name not in ('simt', 'tf32x3', 'bf16'):
+        raise ValueError(name)
+    prev, _gemm_engine = _gemm_engine, name
+    return prev
+
+
+def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_dtype=torch.float32, engine=None):
+    """out = act((x @ weight.T + bias) * row_scale[:, None]) — b200rec_linear / b200rec_linear_tc."""
     _require_cuda(x, weight, bias, row_scale, out)
     x, ldx = _row_major(x)
     w, ldw = _row_major(weight)
@@ -120,6 +135,13 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
         raise ValueError('linear: bad `out`')
     ldy = out.stride(0) if M > 1 else max(N, out.stride(0))
     lib = L.lib()
+    engine = engine or _gemm_engine
+    if engine != 'simt' and ((M >= TC_MIN_ROWS and K >= TC_MIN_K) or engine.endswith('!')) and M * ldx < 2 ** 32:
+        mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+        with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
+            L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
+                                          _dtype_code(out.dtype), mode, _stream()), 'linear_tc')
+        return out
     ws_bytes = lib.b200rec_linear_workspace(M, N, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device), _timed('linear', (M, K, N)):
@@ -301,6 +323,11 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
             raise ValueError('attention_pool: user_matrix must be (B, I)')
         keep.append(um)
         d.user_matrix, d.ld_user_matrix = um.data_ptr(), ld
+        wsb = L.lib().b200rec_attention_pool_workspace(B, I)
+        if wsb:
+            ws = torch.empty(wsb, dtype=torch.uint8, device=Pc.device)
+            keep.append(ws)
+            d.workspace, d.workspace_bytes = ws.data_ptr(), wsb
     elif csr is not None:
         rp, col, val = csr
         rp, col, val = rp.contiguous().int(), col.contiguous().int(), val.contiguous().float()

@@ -5,7 +5,7 @@ into P contiguous ranges with (nearly) equal numbers of EDGES — degrees are he
 balance.  Rank r owns rows [splits[r], splits[r+1]) of x, of the CSR and of every output.  Per layer:
 
     t_own   = dinv ∘ (W_type x_own + b_type)          K1a, written straight into rank r's slot of the gather buffer
-    T       = all_gather(t_own)                        (P, max_rows, d) padded slots; NCCL, in place
+    T       = all_gather(t_own)                        (P, max_rows, d) padded slots; NCCL, in place, one per node type
     x'_own  = dinv ∘ (A_own · T)                       K3 over the local rows; `col` was remapped once to slot addressing
 
 BasicNCF / AttentionNCF need no collective: pairs are sharded across ranks (bench.py).
@@ -59,7 +59,7 @@ class RowPartition:
 
 
 class _LocalIndex(GraphIndex):
-    """GraphIndex over the owned rows only (no edge lists / hash: inference-side object)."""
+    """GraphIndex over a set of owned rows only (no edge lists / hash: inference-side object)."""
 
     def __init__(self, row_ptr, col, w, pos, dinv_own, chunk):
         self.row_ptr, self.col, self.w, self.pos = row_ptr, col, w, pos
@@ -72,34 +72,59 @@ class _LocalIndex(GraphIndex):
 
 
 class PartitionedGraph:
-    """What rank `rank` keeps of a graph: its rows of the index and the slot map.  Build with `partition_graph`."""
+    """What rank `rank` keeps of a graph.  Build with `partition_graph`.
+
+    Ownership is per node TYPE: rank r owns an nnz-balanced range of the item rows AND an nnz-balanced range of the user
+    rows.  Item rows only gather user features and vice versa (the graph is bipartite), so a layer needs two all-gathers
+    — T_items (consumed by the user rows) and T_users (consumed by the item rows) — and the second one is hidden behind
+    the first SpMM (see `encode_partitioned`)."""
 
     def __init__(self, graph, group=None, rank=None, world=None):
         import torch.distributed as dist
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
-        full = get_index(graph)                      # every rank builds the (cheap, ~10 ms at 50M edges) full index, keeps a slice
-        self.nI = int(graph.item_features.shape[0])
-        self.N = full.num_nodes
-        self.part = RowPartition(split_rows(full.row_ptr, self.world), self.rank)
-        lrp, lcol, lw, lpos = self.part.local_csr(full.row_ptr, full.col, full.w, full.pos)
-        self.dinv_own = full.dinv[self.part.r0:self.part.r1].contiguous()
-        self.index = _LocalIndex(lrp, lcol, lw, lpos, self.dinv_own, full.chunk_size)
+        full = get_index(graph)                      # every rank builds the (cheap, ~10 ms at 50M edges) full index, keeps slices
+        nI, N = int(graph.item_features.shape[0]), full.num_nodes
+        self.nI, self.N = nI, N
+        rp = full.row_ptr
+        k_items = int(rp[nI])                        # CSR entries of the item rows come first
+        self.items = RowPartition(split_rows(rp[:nI + 1], self.world), self.rank)
+        self.users = RowPartition(split_rows(rp[nI:] - k_items, self.world), self.rank)
+        it, us = self.items, self.users
+        # item rows [it.r0, it.r1): sources are USERS -> slot addressing of T_users (ids shifted by nI)
+        k0, k1 = int(rp[it.r0]), int(rp[it.r1])
+        cut = lambda a: None if a is None else a[k0:k1].contiguous()
+        col_i = us.slot_index(full.col[k0:k1].long() - nI).to(full.col.dtype).contiguous()
+        self.dinv_items = full.dinv[it.r0:it.r1].contiguous()
+        self.index_items = _LocalIndex((rp[it.r0:it.r1 + 1] - k0).contiguous(), col_i, cut(full.w), cut(full.pos), self.dinv_items,
+                                       full.chunk_size)
+        # user rows [nI + us.r0, nI + us.r1): sources are ITEMS -> slot addressing of T_items
+        k0, k1 = int(rp[nI + us.r0]), int(rp[nI + us.r1])
+        col_u = it.slot_index(full.col[k0:k1].long()).to(full.col.dtype).contiguous()
+        self.dinv_users = full.dinv[nI + us.r0: nI + us.r1].contiguous()
+        self.index_users = _LocalIndex((rp[nI + us.r0: nI + us.r1 + 1] - k0).contiguous(), col_u, cut(full.w), cut(full.pos),
+                                       self.dinv_users, full.chunk_size)
         self.edges_total = full.e1 + full.e2
-        self.edges_own = int(lcol.numel())
-        p = self.part
-        # own rows split by node type: items are global rows [0, nI), users [nI, N)
-        self.items_own = (p.r0, min(p.r1, self.nI)) if p.r0 < self.nI else (p.r0, p.r0)
-        self.users_own = (max(p.r0, self.nI), p.r1) if p.r1 > self.nI else (p.r1, p.r1)
-        self.item_features = graph.item_features[self.items_own[0]:self.items_own[1]]
-        self.user_features = graph.user_features[self.users_own[0] - self.nI:self.users_own[1] - self.nI]
-        self._tg = None
+        self.edges_own = int(col_i.numel() + col_u.numel())
+        self.item_features = graph.item_features[it.r0:it.r1]
+        self.user_features = graph.user_features[us.r0:us.r1]
+        self._bufs = None
 
-    def gather_buffer(self, d, device):
-        if self._tg is None or self._tg.shape[1] != d:
-            self._tg = torch.zeros((self.world * self.part.max_rows, d), dtype=torch.float32, device=device)
-        return self._tg
+    def gather_buffers(self, d, device):
+        if self._bufs is None or self._bufs[0].shape[1] != d:
+            self._bufs = (torch.zeros((self.world * self.items.max_rows, d), dtype=torch.float32, device=device),
+                          torch.zeros((self.world * self.users.max_rows, d), dtype=torch.float32, device=device))
+        return self._bufs
+
+    def locate(self, ids: torch.Tensor):
+        """(owned-by-me mask, local row in my [items | users] block) for global node ids"""
+        is_item = ids < self.nI
+        it, us = self.items, self.users
+        local_item = ids - it.r0
+        local_user = ids - self.nI - us.r0
+        mine = torch.where(is_item, (local_item >= 0) & (local_item < it.rows), (local_user >= 0) & (local_user < us.rows))
+        return mine, torch.where(is_item, local_item, local_user + it.rows)
 
 
 def partition_graph(graph, group=None) -> PartitionedGraph:
@@ -112,71 +137,80 @@ def partition_graph(graph, group=None) -> PartitionedGraph:
 
 
 def encode_partitioned(model, pg: PartitionedGraph):
-    """Propagated + combined embeddings of ALL nodes in slot addressing, (P*max_rows, width), identical on every rank.
-    Inference only (the training path of GraphNCF is single-GPU for now)."""
+    """Propagated + combined embeddings of the OWNED rows, ([items_own | users_own], d).  Inference only.
+
+    Per layer (main stream; NCCL runs the gathers on its own stream, `async_op=True`):
+        GEMM t_items_own -> T_items slot,  GEMM t_users_own -> T_users slot
+        all_gather(T_items) | all_gather(T_users)          issued back to back
+        wait(T_items);  SpMM(user rows <- T_items)          overlaps the (larger) T_users gather
+        wait(T_users);  SpMM(item rows <- T_users)
+    """
     import torch.distributed as dist
     if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
         raise NotImplementedError('partitioned GraphNCF propagation is inference-only; wrap the call in torch.no_grad()')
     if model.concat:
         raise NotImplementedError('concat=True is not supported by the partitioned path yet')
-    p, idx = pg.part, pg.index
-    dev = pg.dinv_own.device
+    it, us = pg.items, pg.users
+    dev = pg.dinv_items.device
     L_ = len(model.gnn_convs)
     d = model.item_embeddings[0].weight.shape[0]
     ie, ue = model.item_embeddings[0], model.user_embeddings[0]
-    ni = pg.items_own[1] - pg.items_own[0]              # owned rows = [items | users], items first
-    x0 = torch.empty((p.rows, d), dtype=torch.float32, device=dev)
+    ni, nu = it.rows, us.rows
+    x0 = torch.empty((ni + nu, d), dtype=torch.float32, device=dev)
     if ni:
         ops.linear_raw(pg.item_features, ie.weight, ie.bias, out=x0[:ni])
-    if p.rows - ni:
+    if nu:
         ops.linear_raw(pg.user_features, ue.weight, ue.bias, out=x0[ni:])
-    tg = pg.gather_buffer(d, dev)
-    mine = tg[p.rank * p.max_rows: p.rank * p.max_rows + p.rows]
-    slot = tg[p.rank * p.max_rows: (p.rank + 1) * p.max_rows]
-    acc = torch.empty((p.rows, d), dtype=torch.float32, device=dev)
-    x, spare = x0, (torch.empty((p.rows, d), dtype=torch.float32, device=dev) if L_ > 1 else None)
-    if L_:
-        lin_u, lin_i, _ = model.gnn_convs[0].typed()
+    if L_ == 0:
+        return x0
+    TI, TU = pg.gather_buffers(d, dev)
+    slot_i = TI[it.rank * it.max_rows: (it.rank + 1) * it.max_rows]
+    slot_u = TU[us.rank * us.max_rows: (us.rank + 1) * us.max_rows]
+    acc = torch.empty((ni + nu, d), dtype=torch.float32, device=dev)
+    spare = torch.empty((ni + nu, d), dtype=torch.float32, device=dev) if L_ > 1 else None
+    lin_u, lin_i, _ = model.gnn_convs[0].typed()
+    x = x0
     for l in range(L_):
         if ni:
-            ops.linear_raw(x[:ni], lin_i.weight, lin_i.bias, row_scale=pg.dinv_own[:ni], out=mine[:ni])
-        if p.rows - ni:
-            ops.linear_raw(x[ni:], lin_u.weight, lin_u.bias, row_scale=pg.dinv_own[ni:], out=mine[ni:])
-        if pg.world > 1:
-            dist.all_gather_into_tensor(tg, slot, group=pg.group)         # in place: rank r's slot is already in position
+            ops.linear_raw(x[:ni], lin_i.weight, lin_i.bias, row_scale=pg.dinv_items, out=slot_i[:ni])
+        if nu:
+            ops.linear_raw(x[ni:], lin_u.weight, lin_u.bias, row_scale=pg.dinv_users, out=slot_u[:nu])
+        w_i = w_u = None
+        if pg.world > 1:                              # in place: this rank's slot already sits at its position
+            w_i = dist.all_gather_into_tensor(TI, slot_i, group=pg.group, async_op=True)
+            w_u = dist.all_gather_into_tensor(TU, slot_u, group=pg.group, async_op=True)
         last = l == L_ - 1
+        scale = 1.0 / (L_ + 1) if last else 1.0
+        src = x0 if l == 0 else acc
         xn = None if last else spare
-        ops.spmm_raw(idx, tg, w=idx.w, dinv=pg.dinv_own, x_next=xn, acc_in=x0 if l == 0 else acc, acc_out=acc,
-                     acc_scale=1.0 / (L_ + 1) if last else 1.0)
+        if w_i is not None:
+            w_i.wait()
+        if nu:
+            ops.spmm_raw(pg.index_users, TI, w=pg.index_users.w, dinv=pg.dinv_users, x_next=None if xn is None else xn[ni:],
+                         acc_in=src[ni:], acc_out=acc[ni:], acc_scale=scale)
+        if w_u is not None:
+            w_u.wait()
+        if ni:
+            ops.spmm_raw(pg.index_items, TU, w=pg.index_items.w, dinv=pg.dinv_items, x_next=None if xn is None else xn[:ni],
+                         acc_in=src[:ni], acc_out=acc[:ni], acc_scale=scale)
         x = xn
-    if L_ == 0:
-        acc = x0
-    # combined embeddings of every node, for the batch gather
-    out = torch.zeros((pg.world * p.max_rows, d), dtype=torch.float32, device=dev)
-    out[p.rank * p.max_rows: p.rank * p.max_rows + p.rows] = acc
-    if pg.world > 1:
-        dist.all_gather_into_tensor(out, out[p.rank * p.max_rows: (p.rank + 1) * p.max_rows], group=pg.group)
-    return out
+    return acc
 
 
 def forward_partitioned(model, pg: PartitionedGraph, userIds, itemIds):
-    """GraphNCF.forward on a partitioned graph: every rank propagates its rows, then scores its shard of the batch and
-    the (B, 1) scores are all-gathered (NCF batches are data-parallel)."""
+    """GraphNCF.forward on a partitioned graph.  After the propagation only the 2B batch rows are exchanged: every rank
+    drops the rows it owns into a zero (2B, d) buffer and one all-reduce (exactly one non-zero contributor per row, so
+    the sum is exact) gives every rank the batch embeddings; the MLP on B pairs is then computed on every rank."""
     import torch.distributed as dist
+    from .neural_collaborative_filtering.util import run_mlp
     comb = encode_partitioned(model, pg)
     B = userIds.shape[0]
-    W = pg.world
-    per = (B + W - 1) // W
-    lo, hi = min(B, pg.rank * per), min(B, (pg.rank + 1) * per)
-    u_slot, i_slot = pg.part.slot_index(userIds.long()), pg.part.slot_index(itemIds.long())
-    from .neural_collaborative_filtering.util import run_mlp
+    ids = torch.cat((itemIds.long(), userIds.long()))
+    mine, local = pg.locate(ids)
+    # no boolean-mask indexing here: it would force a device->host sync in the middle of every step
+    rows = comb[local.clamp(0, comb.shape[0] - 1)] * mine[:, None].to(comb.dtype)
+    if pg.world > 1:
+        dist.all_reduce(rows, group=pg.group)
     if model.MLP is None:
-        mine = ops.rowdot(comb, comb, u_slot[lo:hi], i_slot[lo:hi])
-    else:
-        mine = run_mlp(model.MLP, comb, comb, idx0=i_slot[lo:hi], idx1=u_slot[lo:hi], training=False)
-    if W == 1:
-        return mine
-    buf = torch.zeros((W * per, 1), dtype=torch.float32, device=comb.device)
-    buf[pg.rank * per: pg.rank * per + (hi - lo)] = mine
-    dist.all_gather_into_tensor(buf, buf[pg.rank * per:(pg.rank + 1) * per], group=pg.group)
-    return buf[:B]
+        return ops.rowdot(rows[B:], rows[:B])
+    return run_mlp(model.MLP, rows[:B], rows[B:], training=False)              # item first (gnn_ncf.py:361)

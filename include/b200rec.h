@@ -31,6 +31,7 @@ typedef void* b200rec_stream_t; /* cudaStream_t */
 enum { B200REC_OK = 0, B200REC_ERR_CUDA = 1, B200REC_ERR_BAD_ARG = 2, B200REC_ERR_UNSUPPORTED = 3, B200REC_ERR_WORKSPACE = 4 };
 enum { B200REC_F32 = 0, B200REC_BF16 = 1 };
 enum { B200REC_ATT_NET = 0, B200REC_ATT_DOT = 1 };
+enum { B200REC_TC_TF32X3 = 0, B200REC_TC_BF16 = 1 };
 
 const char* b200rec_last_error(void);
 int b200rec_version(void);
@@ -45,6 +46,11 @@ size_t b200rec_linear_workspace(int64_t M, int64_t N, int64_t K);
 int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
                    const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, void* workspace, size_t workspace_bytes,
                    b200rec_stream_t stream);
+
+/* Same contract on the tensor cores (tcgen05.mma, TMEM accumulators; csrc/gemm_tc.cu).  mode B200REC_TC_TF32X3: fp32-parity
+ * 3xTF32 split (rel <= 1e-5); B200REC_TC_BF16: bf16 operands (rel <= 1e-2).  Needs no workspace; meant for M >= ~1024. */
+int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
+                      const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, b200rec_stream_t stream);
 
 /* ---- K1b  fused MLP tower ------------------------------------------------------------------------------------
  * Replaces torch.cat + build_MLP_layers (util.py:5-18; basic_ncf.py:40-41, attention_ncf.py:219-222, gnn_ncf.py:354-362):
@@ -98,7 +104,10 @@ typedef struct {
   int drop_zero_scores;
   float score_scale; /* 0 = 1.0; message dropout keeps scores / (1-p) (F.dropout, :187) */
   int64_t ld_pr, ld_q; /* leading dimensions of Pr / Q in elements; 0 = H / U */
+  void* workspace;     /* dense form only: b200rec_attention_pool_workspace(B, I) bytes enable the two-kernel path */
+  size_t workspace_bytes; /* (streaming compaction + evenly split ragged kernel); NULL = single fused kernel */
 } b200rec_attention_t;
+size_t b200rec_attention_pool_workspace(int64_t B, int64_t I);
 int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream);
 
 /* ---- K3  GraphNCF propagation: edge-balanced CSR SpMM + degree normalisation + fused combine -----------------------

@@ -44,7 +44,7 @@ def main():
         out = m(g, uid, iid, dev)
     err = float((out - ref).abs().max() / ref.abs().max())
     errs = [None] * world
-    dist.all_gather_object(errs, (err, pg.edges_own, pg.part.rows))
+    dist.all_gather_object(errs, (err, pg.edges_own, pg.items.rows + pg.users.rows))
     if rank == 0:
         print(json.dumps({'world': world, 'max_rel_err_per_rank': [e[0] for e in errs], 'edges_per_rank': [e[1] for e in errs],
                           'rows_per_rank': [e[2] for e in errs], 'ok': all(e[0] < 1e-5 for e in errs)}), flush=True)

@@ -1,0 +1,58 @@
+"""K1a on tcgen05 (csrc/gemm_tc.cu): hand-written tensor-core GEMM vs an fp64 reference.
+TF32x3 mode must stay inside the fp32 parity tolerance (max-norm rel <= 1e-5); bf16 mode inside 1e-2."""
+import pytest
+import torch
+
+from tests._golden import maxnorm_rel
+
+pytestmark = pytest.mark.gpu
+SHAPES = [(128, 64, 128), (128, 32, 128), (300, 2094, 256), (9447, 2094, 256), (1000, 128, 128), (129, 70, 17), (4096, 2093, 130),
+          (50000, 128, 128)]
+
+
+def _case(M, K, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    s = torch.rand(M, generator=g) + 0.5
+    return x, w, b, s
+
+
+@pytest.mark.parametrize('M,K,N', SHAPES)
+def test_linear_tc_tf32x3_fp32_parity(M, K, N):
+    from deeprecommendation_b200 import ops
+    x, w, b, s = _case(M, K, N, M + K)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    y = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='tf32x3!')
+    assert maxnorm_rel(y, ref) < 1e-5
+    # epilogue: row scale + relu, strided output
+    out = torch.full((M, N + 8), 3.0, device='cuda')
+    ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), s.cuda(), True, out=out[:, 4:4 + N], engine='tf32x3!')
+    ref2 = (ref * s.double()[:, None]).relu()
+    assert maxnorm_rel(out[:, 4:4 + N], ref2) < 1e-5
+    assert torch.all(out[:, :4] == 3.0) and torch.all(out[:, 4 + N:] == 3.0)
+
+
+@pytest.mark.parametrize('M,K,N', SHAPES[:5])
+def test_linear_tc_bf16(M, K, N):
+    from deeprecommendation_b200 import ops
+    x, w, b, s = _case(M, K, N, M + K + 1)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    y = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='bf16!')
+    assert maxnorm_rel(y, ref) < 1e-2
+    yb = ops.linear_raw(x.cuda(), w.cuda(), None, out_dtype=torch.bfloat16, engine='bf16!')
+    assert yb.dtype == torch.bfloat16 and maxnorm_rel(yb.float(), x.double() @ w.double().T) < 1e-2
+
+
+def test_linear_tc_real_profiles():
+    """the reference's own input statistics: sparse binary block + dense [0,1) block, F = 2094 (8-byte aligned rows)"""
+    from deeprecommendation_b200 import ops, synth
+    x = torch.from_numpy(synth.item_profiles(3000, seed=3))
+    sd = synth.to_torch(synth.attention_ncf_weights(2094, seed=2))
+    w = torch.cat((sd['ItemEmbeddings.0.weight'], sd['UserEmbeddings.0.weight']))
+    b = torch.cat((sd['ItemEmbeddings.0.bias'], sd['UserEmbeddings.0.bias']))
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    y = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='tf32x3!')
+    simt = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='simt')
+    assert maxnorm_rel(y, ref) < 1e-5 and maxnorm_rel(simt, ref) < 1e-5

@@ -318,8 +318,8 @@ def test_partitioned_world1_equals_single():
 
 @pytest.mark.parametrize('P', [2, 3, 8])
 def test_partition_emulated_ranks_on_one_gpu(P):
-    """P emulated ranks share one GPU and one gather buffer (so the all-gather is the identity): checks the nnz-balanced
-    split, the slot addressing of `col`, the per-rank chunk plans and the item/user row split with the real kernels."""
+    """P emulated ranks share one GPU and one pair of gather buffers (so the all-gathers are the identity): checks the
+    per-type nnz-balanced split, the slot addressing of `col`, the per-rank chunk plans and `locate` with the real kernels."""
     from deeprecommendation_b200 import ops
     from deeprecommendation_b200.graph import get_index
     from deeprecommendation_b200.parallel import PartitionedGraph
@@ -328,38 +328,52 @@ def test_partition_emulated_ranks_on_one_gpu(P):
     L_, d = len(m.gnn_convs), 64
     ranks = [PartitionedGraph(g, rank=r, world=P) for r in range(P)]
     assert sum(pg.edges_own for pg in ranks) == full.e1 + full.e2
-    assert max(pg.edges_own for pg in ranks) <= (full.e1 + full.e2) / P + int(full.deg.max())
+    assert max(pg.edges_own for pg in ranks) <= (full.e1 + full.e2) / P + 2 * int(full.deg.max())
     ie, ue = m.item_embeddings[0], m.user_embeddings[0]
     lin_u, lin_i, _ = m.gnn_convs[0].typed()
-    mr = ranks[0].part.max_rows
-    tg = torch.zeros((P * mr, d), device=DEV)
+    TI, TU = ranks[0].gather_buffers(d, DEV)
+    mi, mu = ranks[0].items.max_rows, ranks[0].users.max_rows
     with torch.no_grad():
         xs, accs = [], []
         for pg in ranks:
-            ni = pg.items_own[1] - pg.items_own[0]
-            x0 = torch.empty((pg.part.rows, d), device=DEV)
+            ni, nu = pg.items.rows, pg.users.rows
+            x0 = torch.empty((ni + nu, d), device=DEV)
             if ni:
                 ops.linear_raw(pg.item_features, ie.weight, ie.bias, out=x0[:ni])
-            if pg.part.rows - ni:
+            if nu:
                 ops.linear_raw(pg.user_features, ue.weight, ue.bias, out=x0[ni:])
             xs.append(x0)
             accs.append(torch.empty_like(x0))
         x0s = list(xs)
         for l in range(L_):
             for pg, x in zip(ranks, xs):
-                ni = pg.items_own[1] - pg.items_own[0]
-                mine = tg[pg.rank * mr: pg.rank * mr + pg.part.rows]
+                ni, nu = pg.items.rows, pg.users.rows
                 if ni:
-                    ops.linear_raw(x[:ni], lin_i.weight, lin_i.bias, row_scale=pg.dinv_own[:ni], out=mine[:ni])
-                if pg.part.rows - ni:
-                    ops.linear_raw(x[ni:], lin_u.weight, lin_u.bias, row_scale=pg.dinv_own[ni:], out=mine[ni:])
+                    ops.linear_raw(x[:ni], lin_i.weight, lin_i.bias, row_scale=pg.dinv_items, out=TI[pg.rank * mi: pg.rank * mi + ni])
+                if nu:
+                    ops.linear_raw(x[ni:], lin_u.weight, lin_u.bias, row_scale=pg.dinv_users, out=TU[pg.rank * mu: pg.rank * mu + nu])
             nxt = []
             for k, pg in enumerate(ranks):
+                ni, nu = pg.items.rows, pg.users.rows
                 xn = torch.empty_like(xs[k])
-                ops.spmm_raw(pg.index, tg, w=pg.index.w, dinv=pg.dinv_own, x_next=xn, acc_in=x0s[k] if l == 0 else accs[k],
-                             acc_out=accs[k], acc_scale=1.0 / (L_ + 1) if l == L_ - 1 else 1.0)
+                src = x0s[k] if l == 0 else accs[k]
+                scale = 1.0 / (L_ + 1) if l == L_ - 1 else 1.0
+                if nu:
+                    ops.spmm_raw(pg.index_users, TI, w=pg.index_users.w, dinv=pg.dinv_users, x_next=xn[ni:], acc_in=src[ni:],
+                                 acc_out=accs[k][ni:], acc_scale=scale)
+                if ni:
+                    ops.spmm_raw(pg.index_items, TU, w=pg.index_items.w, dinv=pg.dinv_items, x_next=xn[:ni], acc_in=src[:ni],
+                                 acc_out=accs[k][:ni], acc_scale=scale)
                 nxt.append(xn)
             xs = nxt
-        comb = torch.cat(accs)
         ref = m._encode(g, full, None, full.dinv, False)
+        nI = ranks[0].nI
+        comb = torch.empty_like(ref)
+        ids = torch.arange(ref.shape[0], device=DEV)
+        seen = torch.zeros(ref.shape[0], dtype=torch.int32, device=DEV)
+        for k, pg in enumerate(ranks):
+            mine, local = pg.locate(ids)
+            comb[mine] = accs[k][local[mine]]
+            seen += mine.int()
+        assert torch.all(seen == 1)                     # every node has exactly one owner
     assert maxnorm_rel(comb, ref) < 1e-6
