@@ -58,9 +58,11 @@ class ClockSampler:
         self.gpu, self.f, self.p = gpu_index, None, None
 
     def __enter__(self):
+        if int(os.environ.get('RANK', '0')) != 0:      # NVML queries take driver locks: one sampler per job, not per rank
+            return self
         try:
             self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i',
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i',
                                        str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -405,6 +407,43 @@ def cpu_graph(w, sample_frac=0.04, repeats=2):
         f'first {n} of {len(w["edges"][0])} interactions ({sample_frac:.0%} edge sample, same node set), median of {repeats} forwards, oracle/restatement.py'
 
 
+def run_k3_hbm_regime(dev, peaks, n_users=8_000_000, n_items=1_000_000, n_edges=100_000_000, d=64, reps=5):
+    """K3 where the roofline formula is meaningful: node features (2.3 GB) >> L2, so every gathered row comes from HBM.
+    Shape = one GPU's share of BASELINE configs[4] (10M users x 1M items x 1B edges, d=64, 8 GPUs), propagation only."""
+    from deeprecommendation_b200 import ops
+    from deeprecommendation_b200.graph import IdTable, create_graph, get_index
+    users, items, ratings = zipf_edges_gpu(n_users, n_items, n_edges, dev, seed=11, a_user=0.5, a_item=0.9)
+    graph = create_graph(users, items, ratings, torch.empty(n_items, 1, device=dev), torch.empty(n_users, 1, device=dev),
+                         IdTable(torch.arange(n_users, device=dev)), IdTable(torch.arange(n_items, device=dev)))
+    del users, items, ratings
+    index = get_index(graph)
+    N, E2 = index.num_nodes, index.e1 + index.e2
+    t = torch.randn(N, d, device=dev)
+    x_next, acc = torch.empty(N, d, device=dev), torch.zeros(N, d, device=dev)
+    ts = []
+    for r in range(reps + 2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.spmm_raw(index, t, w=index.w, dinv=index.dinv, x_next=x_next, acc_in=acc, acc_out=acc, acc_scale=1.0)
+        b.record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    alg = E2 * 8 + E2 * d * 4 + N * d * 4                   # SURVEY.md §8d K3, features larger than L2
+    achieved = alg / (ms * 1e-3) / 1e9
+    out = {'metric': 'K3 SpMM directed-edge messages/sec, HBM regime (features >> L2)', 'value': E2 / (ms * 1e-3), 'unit': 'edges/s',
+           'ms_per_step': ms, 'dtype': 'f32',
+           'config': {'workload': f'one layer of K3 on nU={n_users}, nI={n_items}, E={n_edges} (2E={E2} directed), d={d}: one GPU share of '
+                      f'configs[4]; features {N * d * 4 / 1e9:.2f} GB, CSR {E2 * 8 / 1e9:.2f} GB', 'l2': 'working set >> L2'},
+           'roofline': {'bound': 'hbm', 'kernel': 'spmm_chunk_kernel (K3)', 'achieved': round(achieved, 1), 'peak': peaks['hbm_gbs'],
+                        'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('k3_hbm'),
+                        'peak_source': peaks['src'], 'kernel_ms': round(ms, 4), 'algorithmic_bytes': int(alg)}}
+    del graph, index, t, x_next, acc
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # workload C — BasicNCF, BASELINE configs[0] shape
 # ----------------------------------------------------------------------------------------------------------------------
@@ -537,6 +576,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
                     help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
+    ap.add_argument('--skip-hbm-regime', action='store_true')
     ap.add_argument('--eager', action='store_true', help='do not capture the GraphNCF step into a CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -626,6 +666,11 @@ def main():
                 result = entry
             else:
                 also.append(entry)
+    if args.workload == 'all' and world == 1 and not args.skip_hbm_regime:
+        try:
+            also.append(run_k3_hbm_regime(dev, peaks))
+        except Exception as e:
+            also.append({'metric': 'K3 HBM regime', 'error': repr(e)[:300]})
     result.setdefault('config', {})['gemm_engine'] = args.gemm
     for k, v in (('n_gpus', world), ('steps', args.steps), ('warmup', args.warmup), ('higher_is_better', True), ('vs_baseline', None),
                  ('data', 'synthetic')):

@@ -35,7 +35,7 @@ class SpmmDesc(C.Structure):
                 ('row_ptr', c_vp), ('col', c_vp), ('w', c_vp), ('perm', c_vp), ('skip_bits', c_vp), ('t', c_vp), ('t_dtype', c_int),
                 ('ld_t', c_i64), ('d', c_int), ('dinv', c_vp), ('partials', c_vp), ('x_next', c_vp), ('ld_x', c_i64),
                 ('acc_in', c_vp), ('acc_out', c_vp), ('ld_acc', c_i64), ('acc_scale', c_f), ('multi_row', c_vp),
-                ('multi_first_slot', c_vp), ('multi_n_slots', c_vp), ('n_multi', c_int)]
+                ('multi_first_slot', c_vp), ('multi_n_slots', c_vp), ('n_multi', c_int), ('att_src', c_vp), ('partials_ml', c_vp)]
 
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/b200rec.h

@@ -16,6 +16,8 @@
 // load per lane of the source row (d=128 fp32: 512 B per edge; d=64: two edges per warp step), 8 row gathers in
 // flight per warp.  (A cp.async/LDGSTS shared-memory ring was tried and measured 1.5x SLOWER — 3.4 vs 2.25 ms per
 // layer on the MovieLens-25M shape — and was dropped)
+#include <math.h>
+
 #include "common.cuh"
 
 namespace b200rec {
@@ -50,6 +52,9 @@ struct SpmmParams {
   const int* multi_first_slot;
   const int* multi_n_slots;
   int n_multi;
+  // LightGAT (gnn_ncf.py:97-177): edge weight = w * softmax over the row of att_src[col]; no degree normalisation
+  const float* att_src;      // per SOURCE node score A[:, :d]·x[s]; null = LightGCN
+  float* partials_ml;        // (n_slots, 2): running max and denominator of multi-chunk rows
 };
 
 // writes 4 consecutive columns [c, c+4) of one finished row
@@ -92,7 +97,7 @@ __device__ __forceinline__ uint4 ldg16(const unsigned char* p) { return __ldg(re
 // weight 0) and lanes beyond the row width read column 0, so every load is valid and the per-edge cost is
 // 2 SHFL + 1 IMAD.WIDE.U32 + 1 LDG.128 + 4 FFMA (the first version spent ~26 instructions per edge on predicated
 // 64-bit address arithmetic and zero-fill moves — profiles/r01).
-template <int G, int NV, typename T>
+template <int G, int NV, typename T, bool GAT>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_chunk_kernel(SpmmParams p) {
   constexpr int EPW = 32 / G;                       // edges per warp step
@@ -120,6 +125,7 @@ spmm_chunk_kernel(SpmmParams p) {
   for (int nv = 0; nv < NV; ++nv)
 #pragma unroll
     for (int q = 0; q < VPL; ++q) acc[nv][q] = 0.f;
+  float gat_m = -INFINITY, gat_l = 0.f;             // GAT: online softmax state of this chunk (warp-uniform)
 
   for (int k0 = s; k0 < e; k0 += 32) {
     const int cnt = min(32, e - k0);
@@ -132,6 +138,32 @@ spmm_chunk_kernel(SpmmParams p) {
         const int pos = __ldcs(p.perm + k0 + lane);
         if ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) { wv = 0.f; c = 0u; }
       }
+    }
+    if constexpr (GAT) {
+      // softmax over the incoming edges of the row of the source scores (the destination half of the reference's
+      // Linear(2d -> 1) is constant within a row and cancels in the softmax).  Masked edges (training) do not take part.
+          float sc = -INFINITY;
+      if (lane < cnt) {
+        bool masked = false;
+        if (p.skip_bits) {
+          const int pos = __ldcs(p.perm + k0 + lane);
+          masked = ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) != 0u;
+        }
+        if (!masked) sc = __ldg(p.att_src + __ldcs(p.col + k0 + lane));
+      }
+      const float m_new = fmaxf(gat_m, warp_max(sc));
+      float ex = 0.f;
+      if (m_new != -INFINITY) {
+        const float rescale = __expf(gat_m - m_new);           // gat_m == -inf -> 0
+        ex = (sc == -INFINITY) ? 0.f : __expf(sc - m_new);
+        gat_l = gat_l * rescale + warp_sum(ex);
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+          for (int q = 0; q < VPL; ++q) acc[nv][q] *= rescale;
+        gat_m = m_new;
+      }
+      wv *= ex;
     }
 #pragma unroll
     for (int st0 = 0; st0 < STEPS; st0 += 8) {
@@ -163,7 +195,11 @@ spmm_chunk_kernel(SpmmParams p) {
 
   if (g == 0) {
     const int slot = __ldg(p.chunk_slot + chunk);
-    const float sc = (slot < 0 && p.dinv) ? __ldg(p.dinv + row) : 1.f;
+    float sc = (slot < 0 && p.dinv) ? __ldg(p.dinv + row) : 1.f;
+    if constexpr (GAT) {
+      if (slot < 0) sc = 1.f / (gat_l + 1e-16f);               // PyG softmax: exp(s - max) / (sum + 1e-16)
+      else if (sl == 0) { p.partials_ml[2 * slot] = gat_m; p.partials_ml[2 * slot + 1] = gat_l; }
+    }
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv) {
       if (!active[nv]) continue;
@@ -179,7 +215,7 @@ spmm_chunk_kernel(SpmmParams p) {
 }
 
 // rows that were cut into several chunks: add the partials in chunk order, then the same epilogue
-template <int NV>
+template <int NV, bool GAT>
 __global__ void __launch_bounds__(FIX_WARPS * 32)
 spmm_fixup_kernel(SpmmParams p) {
   const int lane = threadIdx.x & 31;
@@ -192,17 +228,28 @@ spmm_fixup_kernel(SpmmParams p) {
   for (int nv = 0; nv < NV; ++nv)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[nv][q] = 0.f;
+  float M = -INFINITY, Lsum = 0.f;
+  if constexpr (GAT) {
+    for (int sidx = 0; sidx < n; ++sidx) M = fmaxf(M, p.partials_ml[2 * (first + sidx)]);
+  }
   for (int sidx = 0; sidx < n; ++sidx) {
+    float f = 1.f;
+    if constexpr (GAT) {
+      const float ms = p.partials_ml[2 * (first + sidx)];
+      f = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+      Lsum += p.partials_ml[2 * (first + sidx) + 1] * f;
+    }
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv) {
       const int cidx = lane * 4 + nv * 128;
       if (cidx < p.d) {
         const float4 v = *reinterpret_cast<const float4*>(p.partials + (long long)(first + sidx) * p.d + cidx);
-        acc[nv][0] += v.x; acc[nv][1] += v.y; acc[nv][2] += v.z; acc[nv][3] += v.w;
+        acc[nv][0] = fmaf(v.x, f, acc[nv][0]); acc[nv][1] = fmaf(v.y, f, acc[nv][1]);
+        acc[nv][2] = fmaf(v.z, f, acc[nv][2]); acc[nv][3] = fmaf(v.w, f, acc[nv][3]);
       }
     }
   }
-  const float sc = p.dinv ? __ldg(p.dinv + row) : 1.f;
+  const float sc = GAT ? 1.f / (Lsum + 1e-16f) : (p.dinv ? __ldg(p.dinv + row) : 1.f);
 #pragma unroll
   for (int nv = 0; nv < NV; ++nv)
     row_epilogue4(p, row, lane * 4 + nv * 128, sc, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
@@ -211,7 +258,8 @@ spmm_fixup_kernel(SpmmParams p) {
 template <int G, int NV, typename T>
 static int launch_chunks(const SpmmParams& p, cudaStream_t st) {
   const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
-  spmm_chunk_kernel<G, NV, T><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  if (p.att_src) spmm_chunk_kernel<G, NV, T, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  else spmm_chunk_kernel<G, NV, T, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -231,9 +279,15 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   }
   if (p.n_multi > 0) {
     const int g2 = ceil_div_i(p.n_multi, FIX_WARPS);
-    if (p.d <= 128) spmm_fixup_kernel<1><<<g2, FIX_WARPS * 32, 0, st>>>(p);
-    else if (p.d <= 256) spmm_fixup_kernel<2><<<g2, FIX_WARPS * 32, 0, st>>>(p);
-    else spmm_fixup_kernel<4><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+    if (p.att_src) {
+      if (p.d <= 128) spmm_fixup_kernel<1, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+      else if (p.d <= 256) spmm_fixup_kernel<2, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+      else spmm_fixup_kernel<4, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+    } else {
+      if (p.d <= 128) spmm_fixup_kernel<1, false><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+      else if (p.d <= 256) spmm_fixup_kernel<2, false><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+      else spmm_fixup_kernel<4, false><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+    }
     B200REC_CHECK_LAUNCH();
   }
   return B200REC_OK;
@@ -267,6 +321,8 @@ extern "C" int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream) {
   p.acc_scale = a->acc_scale;
   p.multi_row = a->multi_row; p.multi_first_slot = a->multi_first_slot; p.multi_n_slots = a->multi_n_slots;
   p.n_multi = a->n_multi;
+  p.att_src = a->att_src; p.partials_ml = a->partials_ml;
+  if (p.att_src && p.n_multi > 0 && !p.partials_ml) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: LightGAT needs partials_ml for multi-chunk rows");
   cudaStream_t st = (cudaStream_t)stream;
   if (a->t_dtype == B200REC_F32) return launch_spmm<float>(p, st);
   if (a->t_dtype == B200REC_BF16) return launch_spmm<__nv_bfloat16>(p, st);

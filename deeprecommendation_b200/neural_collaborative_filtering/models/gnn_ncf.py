@@ -40,6 +40,36 @@ class LightGCNConv(nn.Module):
         return self.W[0], self.W[0], self.W[1].p
 
 
+class LightGATConv(nn.Module):
+    """Parameter holder for the GAT-style layer (gnn_ncf.py:97-177): per edge type a Linear(d, d) and an attention
+    Linear(2d, 1) over [x_source, x_destination].  Executed by K3 with an edge softmax: the destination half of the
+    attention Linear is constant over the incoming edges of a node, so it cancels in the softmax (PyG's `+1e-16`
+    denominator included) and only the source half is evaluated — one scalar per NODE instead of one 2d-dot per EDGE."""
+
+    def __init__(self, in_channels, out_channels, hetero, dropout=0.1):
+        super().__init__()
+        self.hetero = hetero
+        if hetero:
+            self.user2item_W = _TypedLinear(in_channels, out_channels, dropout)
+            self.item2user_W = _TypedLinear(in_channels, out_channels, dropout)
+            self.user2item_AttNet = nn.Sequential(nn.Linear(in_channels * 2, 1))
+            self.item2user_AttNet = nn.Sequential(nn.Linear(in_channels * 2, 1))
+        else:
+            self.W = _TypedLinear(in_channels, out_channels, dropout)
+            self.AttNet = nn.Sequential(nn.Linear(in_channels * 2, 1))
+
+    def typed(self):
+        if self.hetero:
+            return self.user2item_W[0], self.item2user_W[0], self.user2item_W[1].p
+        return self.W[0], self.W[0], self.W[1].p
+
+    def attention(self):
+        """(attention Linear for user sources, for item sources)"""
+        if self.hetero:
+            return self.user2item_AttNet[0], self.item2user_AttNet[0]
+        return self.AttNet[0], self.AttNet[0]
+
+
 class GraphNCF(GNN_NCF):
     """Node embed -> L shared-weight propagation layers over the whole bipartite graph -> mean (or concat) of the L+1
     embeddings -> gather the batch rows -> MLP (item first) or dot product  (gnn_ncf.py:298-367).
@@ -67,7 +97,7 @@ class GraphNCF(GNN_NCF):
         if convType == 'LightGCN':
             conv = LightGCNConv(node_emb, node_emb, hetero=hetero, dropout=dropout_rate / 2)
         elif convType == 'LightGAT':
-            raise NotImplementedError('LightGATConv is queued (SURVEY.md §8f-3); no shipped script of the reference reaches it')
+            conv = LightGATConv(node_emb, node_emb, hetero=hetero, dropout=dropout_rate / 2)
         else:
             raise ValueError('Invalid convType.')
         self.gnn_convs = nn.ModuleList([conv] * num_gnn_layers)        # ONE module aliased L times (gnn_ncf.py:227)
@@ -124,21 +154,33 @@ class GraphNCF(GNN_NCF):
                 return x0
             x, t = x0, torch.empty((N, d), dtype=torch.float32, device=dev)
             spare = torch.empty((N, d), dtype=torch.float32, device=dev) if (L_ > 1 and not self.concat) else None
+            gat = self.convType == 'LightGAT'
+            if gat:
+                att_u, att_i = self.gnn_convs[0].attention()
+                ps = torch.empty((N, 1), dtype=torch.float32, device=dev)
             for l in range(L_):
-                ops.linear_raw(x[:nI], lin_i.weight, lin_i.bias, row_scale=dinv[:nI], out=t[:nI])     # item sources: item2user_W
-                ops.linear_raw(x[nI:], lin_u.weight, lin_u.bias, row_scale=dinv[nI:], out=t[nI:])     # user sources: user2item_W
+                if gat:      # no degree normalisation; per-source attention score from the source half of Linear(2d, 1)
+                    ops.linear_raw(x[:nI], lin_i.weight, lin_i.bias, out=t[:nI])
+                    ops.linear_raw(x[nI:], lin_u.weight, lin_u.bias, out=t[nI:])
+                    ops.linear_raw(x[:nI], att_i.weight[:, :d], None, out=ps[:nI], engine='simt')
+                    ops.linear_raw(x[nI:], att_u.weight[:, :d], None, out=ps[nI:], engine='simt')
+                else:
+                    ops.linear_raw(x[:nI], lin_i.weight, lin_i.bias, row_scale=dinv[:nI], out=t[:nI])     # item sources: item2user_W
+                    ops.linear_raw(x[nI:], lin_u.weight, lin_u.bias, row_scale=dinv[nI:], out=t[nI:])     # user sources: user2item_W
                 last = l == L_ - 1
                 if self.concat:
                     xn = comb[:, d * (l + 1): d * (l + 2)]
-                    ops.spmm_raw(index, t, w=index.w, dinv=dinv, x_next=xn, skip_bits=skip)
+                    ops.spmm_raw(index, t, w=index.w, dinv=None if gat else dinv, x_next=xn, skip_bits=skip, att_src=ps if gat else None)
                 else:
                     # x is dead once t has been formed (same stream), so one spare buffer serves every layer; it must not
                     # alias x0, which layer 0 still reads as acc_in
                     xn = None if last else spare
-                    ops.spmm_raw(index, t, w=index.w, dinv=dinv, x_next=xn, acc_in=x0 if l == 0 else comb, acc_out=comb,
-                                 acc_scale=1.0 / (L_ + 1) if last else 1.0, skip_bits=skip)
+                    ops.spmm_raw(index, t, w=index.w, dinv=None if gat else dinv, x_next=xn, acc_in=x0 if l == 0 else comb, acc_out=comb,
+                                 acc_scale=1.0 / (L_ + 1) if last else 1.0, skip_bits=skip, att_src=ps if gat else None)
                 x = xn
             return comb
+        if self.convType == 'LightGAT':
+            raise NotImplementedError('LightGAT backward is not implemented: run it under torch.no_grad() (SURVEY.md §8f-1/3)')
         # training path: same kernels through autograd Functions (backward of K3 = K3 on the reverse weights)
         x = torch.cat((ops.linear(graph.item_features, ie.weight, ie.bias), ops.linear(graph.user_features, ue.weight, ue.bias)), 0)
         hs = [x]

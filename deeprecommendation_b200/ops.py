@@ -358,7 +358,7 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
 # ------------------------------------------------------------------------------------------------------------------
 # K3 SpMM
 # ------------------------------------------------------------------------------------------------------------------
-def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, skip_bits=None):
+def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, skip_bits=None, att_src=None):
     """One propagation step over a `GraphIndex` (graph.py): b200rec_spmm.  Returns nothing; writes x_next / acc_out."""
     _require_cuda(t)
     if t.stride(1) != 1:
@@ -389,6 +389,13 @@ def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, 
         d.multi_row, d.multi_first_slot, d.multi_n_slots = (index.multi_row.data_ptr(), index.multi_first_slot.data_ptr(),
                                                             index.multi_n_slots.data_ptr())
     d.n_multi = index.n_multi
+    ml = None
+    if att_src is not None:
+        att_src = att_src.contiguous().float().view(-1)
+        d.att_src = att_src.data_ptr()
+        if index.n_multi > 0:
+            ml = torch.empty((index.n_slots, 2), dtype=torch.float32, device=t.device)
+            d.partials_ml = ml.data_ptr()
     with torch.cuda.device(t.device), _timed('spmm', (index.e1 + index.e2, t.shape[1])):
         L.check(L.lib().b200rec_spmm(C.byref(d), _stream()), 'spmm')
 

@@ -148,8 +148,8 @@ def encode_partitioned(model, pg: PartitionedGraph):
     import torch.distributed as dist
     if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
         raise NotImplementedError('partitioned GraphNCF propagation is inference-only; wrap the call in torch.no_grad()')
-    if model.concat:
-        raise NotImplementedError('concat=True is not supported by the partitioned path yet')
+    if model.concat or model.convType != 'LightGCN':
+        raise NotImplementedError('the partitioned path covers LightGCN with mean combine (concat / LightGAT: single GPU)')
     it, us = pg.items, pg.users
     dev = pg.dinv_items.device
     L_ = len(model.gnn_convs)

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gemm_tc_gpu.py -m gpu -q -x 2>&1 | tail -3
-for d in 0 7; do echo "== DBG $d"; B200REC_TC_DBG=$d python tools/gemm_bench.py 2>&1 | grep -E "tf32x3|bf16"; done
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+python bench.py > gpurun_out/bench4.json 2> gpurun_out/bench4.err; echo "rc=$?"; tail -3 gpurun_out/bench4.err

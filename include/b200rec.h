@@ -142,6 +142,8 @@ typedef struct {
   const int* multi_first_slot;
   const int* multi_n_slots;
   int n_multi;
+  const float* att_src; /* LightGAT (gnn_ncf.py:97-177): per-source score; edge weight = w * softmax_row(att_src[col]); NULL = LightGCN */
+  float* partials_ml;   /* (n_slots, 2) scratch for the softmax state of multi-chunk rows */
 } b200rec_spmm_t;
 int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream);
 
