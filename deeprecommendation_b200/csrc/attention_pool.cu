@@ -230,7 +230,7 @@ __device__ __forceinline__ float normalise_score(float s, float M, float Lsum) {
 
 // ---- ragged-native front-end: CSR of user_matrix ------------------------------------------------------------
 template <int HV, int UV, int MODE, typename T>
-__global__ void __launch_bounds__(ATT_WARPS * 32)
+__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 3 : 1)
 attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col,
                           const float* __restrict__ val, const int* __restrict__ row_nnz, long long padded_stride) {
   __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];
@@ -258,6 +258,94 @@ attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const in
   merge_and_write<UV>(p, b, s_m, s_l, s_acc, M, Lsum);
   if (p.att != nullptr) {
     for (long long k = my_start + lane; k < my_end; k += 32) {
+      if (__ldg(val + k) != 0.f) {
+        float* a = p.att + (long long)b * p.I + __ldg(col + k);
+        *a = normalise_score(*a, M, Lsum);
+      }
+    }
+  }
+}
+
+// ---- segment-parallel ragged kernel -------------------------------------------------------------------------
+// Rows are heavy-tailed (mean ~550 non-zeros per candidate at config 2, max ~2.7k): with one CTA per row the kernel
+// lasts as long as its longest row.  Here a CTA owns ONE SEGMENT of at most ATT_SEG non-zeros of one row (grid =
+// B x ceil(I / ATT_SEG), CTAs beyond a row's length exit at once), writes its (max, denominator, pooled vector) to a
+// partial slot, and a small second kernel merges a row's partials, adds b_U and normalises the attention weights.
+constexpr int ATT_SEG = 512;
+
+template <int HV, int UV, int MODE, typename T>
+__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 3 : 1)
+attention_seg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
+                     const int* __restrict__ row_nnz, long long padded_stride, float* __restrict__ partials, int nseg_max) {
+  __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];
+  __shared__ __align__(16) float s_acc[ATT_WARPS * UV * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x, seg = blockIdx.y;
+  const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
+  const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
+  const long long seg_start = start + (long long)seg * ATT_SEG;
+  if (seg_start >= end) return;                                    // (whole CTA) this row has fewer segments
+  const long long seg_end = min(end, seg_start + ATT_SEG);
+  RowCore<HV, UV, MODE, T> core(p, lane, b);
+  const int blocks = (int)((seg_end - seg_start + 31) >> 5);
+  const int bpw = (blocks + ATT_WARPS - 1) / ATT_WARPS;
+  const long long my_start = seg_start + (long long)warp * bpw * 32, my_end = min(seg_end, my_start + (long long)bpw * 32);
+  for (long long k0 = my_start; k0 < my_end; k0 += 32) {
+    const long long k = k0 + lane;
+    int c = -1;
+    float v = 0.f;
+    if (k < my_end) { c = __ldg(col + k); v = __ldg(val + k); }
+    const bool valid = (k < my_end) && (v != 0.f);
+    core.batch(valid ? c : -1, valid ? v : 0.f, (int)min(32LL, my_end - k0));
+  }
+  core.export_state(s_m, s_l, s_acc, warp);
+  __syncthreads();
+  // merge the 8 warps -> one partial (m, l, acc[U]) for this segment
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < ATT_WARPS; ++w) M = fmaxf(M, s_m[w]);
+  float scale[ATT_WARPS], Lsum = 0.f;
+#pragma unroll
+  for (int w = 0; w < ATT_WARPS; ++w) {
+    scale[w] = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - M);
+    Lsum += s_l[w] * scale[w];
+  }
+  float* slot = partials + ((long long)b * nseg_max + seg) * (p.U + 2);
+  if (threadIdx.x == 0) { slot[0] = M; slot[1] = Lsum; }
+  for (int u = threadIdx.x; u < p.U; u += ATT_WARPS * 32) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATT_WARPS; ++w) a = fmaf(s_acc[(size_t)w * (UV * 128) + u], scale[w], a);
+    slot[2 + u] = a;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
+                       const int* __restrict__ row_nnz, long long padded_stride, const float* __restrict__ partials, int nseg_max) {
+  const int b = blockIdx.x;
+  const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
+  const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
+  const int nseg = (int)((end - start + ATT_SEG - 1) / ATT_SEG);
+  const float* base = partials + (long long)b * nseg_max * (p.U + 2);
+  float M = -INFINITY;
+  for (int sgi = 0; sgi < nseg; ++sgi) M = fmaxf(M, base[(long long)sgi * (p.U + 2)]);
+  float Lsum = 0.f;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const float ms = base[(long long)sgi * (p.U + 2)];
+    Lsum += base[(long long)sgi * (p.U + 2) + 1] * ((ms == -INFINITY) ? 0.f : __expf(ms - M));
+  }
+  const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;      // no valid rated item -> weights 0 -> user_emb = b_U (:208-209)
+  for (int u = threadIdx.x; u < p.U; u += blockDim.x) {
+    float a = 0.f;
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const float ms = base[(long long)sgi * (p.U + 2)];
+      a = fmaf(base[(long long)sgi * (p.U + 2) + 2 + u], (ms == -INFINITY) ? 0.f : __expf(ms - M), a);
+    }
+    p.out[(long long)b * p.ldo + u] = fmaf(a, inv, p.bU ? __ldg(p.bU + u) : 0.f);
+  }
+  if (p.att != nullptr) {
+    for (long long k = start + threadIdx.x; k < end; k += blockDim.x) {
       if (__ldg(val + k) != 0.f) {
         float* a = p.att + (long long)b * p.I + __ldg(col + k);
         *a = normalise_score(*a, M, Lsum);
@@ -384,26 +472,46 @@ struct AttInputs {
   void* ws; size_t ws_bytes;
 };
 
-static size_t att_workspace_bytes(long long B, long long I) {
+static size_t att_partials_bytes(long long B, long long I, int U) {
+  const long long nseg = (I + ATT_SEG - 1) / ATT_SEG;
+  return (size_t)(B * (nseg > 0 ? nseg : 1)) * (size_t)(U + 2) * sizeof(float);
+}
+static size_t att_compact_bytes(long long B, long long I) {
   return (size_t)(B * I) * (sizeof(int) + sizeof(float)) + (size_t)B * sizeof(int) + 64;
+}
+// dense form: compaction lists + partial slots; CSR form: partial slots only
+static size_t att_workspace_bytes(long long B, long long I, int U, bool dense) {
+  return att_partials_bytes(B, I, U) + 256 + (dense ? att_compact_bytes(B, I) : 0);
 }
 
 template <int HV, int UV, int MODE, typename T>
 static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) {
-  const int grid = p.B;
-  if (in.um && in.ws && in.ws_bytes >= att_workspace_bytes(p.B, p.I)) {
-    // two kernels: streaming compaction of the dense matrix, then the balanced ragged kernel
-    int* ccol = reinterpret_cast<int*>(in.ws);
-    float* cval = reinterpret_cast<float*>(ccol + (size_t)p.B * p.I);
-    int* cnnz = reinterpret_cast<int*>(cval + (size_t)p.B * p.I);
-    um_compact_kernel<<<grid, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, ccol, cval, cnnz);
+  const bool dense = in.um != nullptr;
+  const bool have_ws = in.ws && in.ws_bytes >= att_workspace_bytes(p.B, p.I, p.U, dense);
+  if (!have_ws) {                      // no workspace: single fused kernel, one CTA per row
+    if (dense) attention_pool_dense_kernel<HV, UV, MODE, T><<<p.B, ATT_WARPS * 32, 0, st>>>(p, in.um, in.ld_um);
+    else attention_pool_csr_kernel<HV, UV, MODE, T><<<p.B, ATT_WARPS * 32, 0, st>>>(p, in.row_ptr, in.col, in.val, nullptr, 0);
     B200REC_CHECK_LAUNCH();
-    attention_pool_csr_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, nullptr, ccol, cval, cnnz, p.I);
-  } else if (in.um) {
-    attention_pool_dense_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, in.um, in.ld_um);
-  } else {
-    attention_pool_csr_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, in.row_ptr, in.col, in.val, nullptr, 0);
+    return B200REC_OK;
   }
+  float* partials = reinterpret_cast<float*>(in.ws);
+  const int* ccol = in.col; const float* cval = in.val; const int* cnnz = nullptr; const int* rp = in.row_ptr;
+  long long stride = 0;
+  if (dense) {                         // streaming compaction of the dense matrix into row-padded lists
+    unsigned char* q = reinterpret_cast<unsigned char*>(in.ws) + ((att_partials_bytes(p.B, p.I, p.U) + 255) & ~(size_t)255);
+    int* wcol = reinterpret_cast<int*>(q);
+    float* wval = reinterpret_cast<float*>(wcol + (size_t)p.B * p.I);
+    int* wnnz = reinterpret_cast<int*>(wval + (size_t)p.B * p.I);
+    um_compact_kernel<<<p.B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz);
+    B200REC_CHECK_LAUNCH();
+    ccol = wcol; cval = wval; cnnz = wnnz; rp = nullptr; stride = p.I;
+  }
+  const int nseg_max = p.I > 0 ? (p.I + ATT_SEG - 1) / ATT_SEG : 1;
+  dim3 grid(p.B, nseg_max);
+  if (nseg_max > 65535) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: more than 65535 segments per row");
+  attention_seg_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, rp, ccol, cval, cnnz, stride, partials, nseg_max);
+  B200REC_CHECK_LAUNCH();
+  attention_merge_kernel<<<p.B, 128, 0, st>>>(p, rp, ccol, cval, cnnz, stride, partials, nseg_max);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -421,7 +529,9 @@ static int dispatch_att(const AttParams& p, const AttInputs& in, cudaStream_t st
 
 using namespace b200rec;
 
-extern "C" size_t b200rec_attention_pool_workspace(int64_t B, int64_t I) { return (B > 0 && I > 0) ? att_workspace_bytes(B, I) : 0; }
+extern "C" size_t b200rec_attention_pool_workspace(int64_t B, int64_t I, int U, int dense) {
+  return (B > 0 && I > 0 && U > 0) ? att_workspace_bytes(B, I, U, dense != 0) : 0;
+}
 
 extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream) {
   if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: null descriptor");

@@ -11,6 +11,8 @@
 namespace b200rec {
 
 constexpr int MLP_THREADS = 256;
+constexpr int MLP_KC = 32;             // k extent of a staged W tile
+constexpr int MLP_WS = MLP_KC + 4;     // padded row stride (floats) of the tile
 
 template <int TM>
 __global__ void __launch_bounds__(MLP_THREADS)
@@ -20,6 +22,7 @@ mlp_tower_kernel(const float* __restrict__ in0, long long ld0, const int64_t* __
   extern __shared__ __align__(16) float smem[];
   float* buf0 = smem;
   float* buf1 = smem + (size_t)TM * stride;
+  float* wtile = smem + (size_t)2 * TM * stride;      // 2 x [256 x 36] floats
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row0 = (long long)blockIdx.x * TM;
 
@@ -51,33 +54,84 @@ mlp_tower_kernel(const float* __restrict__ in0, long long ld0, const int64_t* __
     const float* __restrict__ W = d.W[l];
     const float* __restrict__ bias = d.b[l];
     const bool last = (l == d.n_layers - 1);
-    if (H >= 32) {
-      // thread-per-output-column, all TM rows in registers; activations are shared-memory broadcasts
-      for (int c = tid; c < H; c += MLP_THREADS) {
+    if (H >= 32 && w_vec_ok && (Kd % 4 == 0)) {
+      // Wide layer.  Thread c owns output column c for all TM rows.  W is streamed through shared memory in
+      // [256 columns x 32 k] tiles with cp.async (coalesced 128-byte row segments, double buffered, rows padded to 36
+      // floats so that the per-thread float4 reads are conflict-free); activations are shared-memory broadcasts.
+      // (v1 let every thread walk its own W row in global memory: 32 different sectors per load, 34 us at B = 512.)
+      const int n_kc = (Kd + MLP_KC - 1) / MLP_KC;
+      for (int c0 = 0; c0 < H; c0 += MLP_THREADS) {
+        const int c = c0 + tid;
         float acc[TM];
-        const float b0 = bias ? __ldg(bias + c) : 0.f;
+        const float b0 = (bias && c < H) ? __ldg(bias + c) : 0.f;
 #pragma unroll
         for (int r = 0; r < TM; ++r) acc[r] = b0;
-        const float* wrow = W + (size_t)c * Kd;
-        int k = 0;
-        if (w_vec_ok && (Kd % 4 == 0)) {
-          for (; k < Kd; k += 4) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + k));
+        auto stage = [&](int kc, int buf) {
+          float* dst = wtile + (size_t)buf * MLP_THREADS * MLP_WS;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int idx = tid + j * MLP_THREADS;
+            const int rr = idx >> 3, ch = idx & 7;              // 8 x 16-byte chunks per 128-byte row segment
+            const int col = c0 + rr, k = kc * MLP_KC + ch * 4;
+            float* d = dst + (size_t)rr * MLP_WS + ch * 4;
+            if (col < H && k < Kd) {
+              const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(W + (size_t)col * Kd + k) : "memory");
+            } else {
+              *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          asm volatile("cp.async.commit_group;\n" ::: "memory");
+        };
+        stage(0, 0);
+        for (int kc = 0; kc < n_kc; ++kc) {
+          if (kc + 1 < n_kc) {
+            stage(kc + 1, (kc + 1) & 1);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+          } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+          }
+          __syncthreads();
+          const float* wt = wtile + (size_t)(kc & 1) * MLP_THREADS * MLP_WS + (size_t)tid * MLP_WS;
+          const int kbase = kc * MLP_KC;
+          const int kn = min(MLP_KC, Kd - kbase);
+#pragma unroll 4
+          for (int k = 0; k < kn; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wt + k);
 #pragma unroll
             for (int r = 0; r < TM; ++r) {
-              const float4 a = *reinterpret_cast<const float4*>(cur + (size_t)r * stride + k);
+              const float4 a = *reinterpret_cast<const float4*>(cur + (size_t)r * stride + kbase + k);
               acc[r] = fmaf(a.x, w.x, acc[r]);
               acc[r] = fmaf(a.y, w.y, acc[r]);
               acc[r] = fmaf(a.z, w.z, acc[r]);
               acc[r] = fmaf(a.w, w.w, acc[r]);
             }
           }
-        } else {
-          for (; k < Kd; ++k) {
-            const float w = __ldg(wrow + k);
+          __syncthreads();                                      // the tile is free for the stage after next
+        }
+        if (c < H) {
 #pragma unroll
-            for (int r = 0; r < TM; ++r) acc[r] = fmaf(cur[(size_t)r * stride + k], w, acc[r]);
+          for (int r = 0; r < TM; ++r) {
+            if (last) {
+              if (row0 + r < B) out[(row0 + r) * ldo + c] = acc[r];
+            } else {
+              nxt[(size_t)r * stride + c] = fmaxf(acc[r], 0.f);
+            }
           }
+        }
+      }
+    } else if (H >= 32) {
+      // wide layer, unaligned weights: thread-per-output-column straight from global memory
+      for (int c = tid; c < H; c += MLP_THREADS) {
+        float acc[TM];
+        const float b0 = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+        for (int r = 0; r < TM; ++r) acc[r] = b0;
+        const float* wrow = W + (size_t)c * Kd;
+        for (int k = 0; k < Kd; ++k) {
+          const float w = __ldg(wrow + k);
+#pragma unroll
+          for (int r = 0; r < TM; ++r) acc[r] = fmaf(cur[(size_t)r * stride + k], w, acc[r]);
         }
 #pragma unroll
         for (int r = 0; r < TM; ++r) {
@@ -153,7 +207,7 @@ extern "C" int b200rec_mlp_tower(const float* in0, int64_t ld0, const int64_t* i
   // small batches: fewer rows per CTA so that more SMs take part
   const bool small = B < (long long)16 * sms * 2;
   const int TM = small ? 8 : 16;
-  size_t smem = (size_t)2 * TM * stride * sizeof(float);
+  size_t smem = ((size_t)2 * TM * stride + (size_t)2 * MLP_THREADS * MLP_WS) * sizeof(float);
   if (smem > 200 * 1024) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "mlp_tower: layer too wide for shared memory");
   long long grid = (B + TM - 1) / TM;
   if (grid > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "mlp_tower: batch too large");

@@ -88,15 +88,27 @@ class AttentionNCF(NCF):
         Pr = torch.cat((torch.ones_like(sr), sr, torch.zeros_like(sr), torch.zeros_like(sr)), 1)
         return Pc, Pr, L.ATT_DOT, None, None
 
+    def _stacked_projection(self):
+        """[W_I ; W_U] and [b_I ; 0] for the single sweep over rated_items.  Under no_grad the stacked copies are cached
+        until a parameter changes (its `_version` moves with every optimizer step / load_state_dict)."""
+        item, user = self.ItemEmbeddings[0], self.UserEmbeddings[0]
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in (item.weight, user.weight))
+        key = None if grad else tuple((p.data_ptr(), p._version) for p in (item.weight, item.bias, user.weight, user.bias))
+        cached = getattr(self, '_proj_cache', None)
+        if key is not None and cached is not None and cached[0] == key:
+            return cached[1]
+        WU, bU = _pad_rows(user.weight, user.bias)
+        out = (torch.cat((item.weight, WU), 0), torch.cat((item.bias, torch.zeros_like(bU)), 0), bU)
+        self._proj_cache = (key, tuple(t.detach() for t in out)) if key is not None else None
+        return out
+
     def forward(self, candidate_items, rated_items, user_matrix, return_attention_weights=False):
         item, user = self.ItemEmbeddings[0], self.UserEmbeddings[0]
         E, U = item.weight.shape[0], user.weight.shape[0]
         Ec = ops.linear(candidate_items, item.weight, item.bias)                        # :150
-        WU, bU = _pad_rows(user.weight, user.bias)
         # one sweep over rated_items: item embedding (:151) and Q = rated_items·W_Uᵀ (pooling moved into embedding space:
         # W_U(Σ α·um·R_i) = Σ α·um·(W_U R_i), :213+:216)
-        Wcat = torch.cat((item.weight, WU), 0)
-        bcat = torch.cat((item.bias, torch.zeros_like(bU)), 0)
+        Wcat, bcat, bU = self._stacked_projection()
         ErQ = ops.linear(rated_items, Wcat, bcat)
         Er, Q = ErQ[:, :E], ErQ[:, E:]
         Pc, Pr, mode, a2, a20 = self._score_tables(Ec, Er)

@@ -125,9 +125,9 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f'linear: weight is {tuple(w.shape)}, input is {tuple(x.shape)}')
-    if bias is not None:
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
         bias = bias.contiguous().float()
-    if row_scale is not None:
+    if row_scale is not None and (row_scale.dtype != torch.float32 or not row_scale.is_contiguous()):
         row_scale = row_scale.contiguous().float()
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=x.device)
@@ -199,13 +199,15 @@ def mlp_tower_raw(in0, in1, weights, biases, idx0=None, idx1=None):
     d.n_layers = n
     prev = E0 + E1
     for l, (w, b) in enumerate(zip(weights, biases)):
-        w = w.detach().contiguous().float()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.detach().contiguous().float()
         if w.shape[1] != prev:
             raise ValueError(f'MLP layer {l}: weight {tuple(w.shape)} does not take {prev} inputs')
         keep.append(w)
         d.W[l] = w.data_ptr()
         if b is not None:
-            b = b.detach().contiguous().float()
+            if b.dtype != torch.float32 or not b.is_contiguous():
+                b = b.detach().contiguous().float()
             keep.append(b)
             d.b[l] = b.data_ptr()
         else:
@@ -293,7 +295,7 @@ def rowdot(in0, in1, idx0=None, idx1=None):
 # K2 attention pooling
 # ------------------------------------------------------------------------------------------------------------------
 def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None, user_matrix=None, csr=None,
-                       return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0):
+                       return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0, use_workspace=True):
     """out (B,U) [, att (B,I)] — b200rec_attention_pool.  `csr` = (row_ptr int32, col int32, val fp32)."""
     _require_cuda(Pc, Pr, Q, user_matrix)
     Pc = Pc.contiguous().float()
@@ -323,11 +325,6 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
             raise ValueError('attention_pool: user_matrix must be (B, I)')
         keep.append(um)
         d.user_matrix, d.ld_user_matrix = um.data_ptr(), ld
-        wsb = L.lib().b200rec_attention_pool_workspace(B, I)
-        if wsb:
-            ws = torch.empty(wsb, dtype=torch.uint8, device=Pc.device)
-            keep.append(ws)
-            d.workspace, d.workspace_bytes = ws.data_ptr(), wsb
     elif csr is not None:
         rp, col, val = csr
         rp, col, val = rp.contiguous().int(), col.contiguous().int(), val.contiguous().float()
@@ -336,6 +333,11 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
     else:
         raise ValueError('attention_pool: need user_matrix or csr')
     d.B, d.I, d.H, d.U = B, I, H, U
+    wsb = L.lib().b200rec_attention_pool_workspace(B, I, U, int(user_matrix is not None)) if use_workspace else 0
+    if wsb:
+        ws = torch.empty(wsb, dtype=torch.uint8, device=Pc.device)
+        keep.append(ws)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), wsb
     d.ld_pr, d.ld_q = (Pr.stride(0) if I > 1 else H), (Q.stride(0) if I > 1 else U)
     out = torch.empty((B, U), dtype=torch.float32, device=Pc.device)
     d.out, d.ldo = out.data_ptr(), U

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-python bench.py > gpurun_out/bench4.json 2> gpurun_out/bench4.err; echo "rc=$?"; tail -3 gpurun_out/bench4.err
+timeout 400 python -m pytest tests/test_models_gpu.py tests/test_kernels_gpu.py -m gpu -q -x 2>&1 | tail -3
+python bench.py --no-cpu-baseline --skip-hbm-regime > gpurun_out/b6.json 2> gpurun_out/b6.err; echo rc=$?; tail -2 gpurun_out/b6.err

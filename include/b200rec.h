@@ -104,10 +104,10 @@ typedef struct {
   int drop_zero_scores;
   float score_scale; /* 0 = 1.0; message dropout keeps scores / (1-p) (F.dropout, :187) */
   int64_t ld_pr, ld_q; /* leading dimensions of Pr / Q in elements; 0 = H / U */
-  void* workspace;     /* dense form only: b200rec_attention_pool_workspace(B, I) bytes enable the two-kernel path */
-  size_t workspace_bytes; /* (streaming compaction + evenly split ragged kernel); NULL = single fused kernel */
+  void* workspace;     /* b200rec_attention_pool_workspace(B, I, U, dense) bytes enable the segment-parallel path (streaming */
+  size_t workspace_bytes; /* compaction of a dense matrix, one CTA per <=512 non-zeros, merge kernel); NULL = one fused kernel */
 } b200rec_attention_t;
-size_t b200rec_attention_pool_workspace(int64_t B, int64_t I);
+size_t b200rec_attention_pool_workspace(int64_t B, int64_t I, int U, int dense);
 int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream);
 
 /* ---- K3  GraphNCF propagation: edge-balanced CSR SpMM + degree normalisation + fused combine -----------------------

@@ -146,6 +146,13 @@ def test_attention_cfg2_ragged_vs_oracle():
         col = nz.nonzero()[:, 1].int()
         csr = ops.attention_pool_raw(Pc, Pr, Q, csr=(row_ptr.to(DEV), col.to(DEV), umt[nz].to(DEV)), **common)
         assert maxnorm_rel(csr, dense) < 1e-6      # same core; the warps slice the row by column (dense) vs by non-zero count (CSR)
+        # single fused kernel (no workspace) vs segment-parallel path (compaction + one CTA per 512 non-zeros + merge)
+        fused_d = ops.attention_pool_raw(Pc, Pr, Q, user_matrix=umt.to(DEV), use_workspace=False, **common)
+        fused_c = ops.attention_pool_raw(Pc, Pr, Q, csr=(row_ptr.to(DEV), col.to(DEV), umt[nz].to(DEV)), use_workspace=False, **common)
+        assert maxnorm_rel(fused_d, dense) < 1e-6 and maxnorm_rel(fused_c, dense) < 1e-6
+        o1, a1 = ops.attention_pool_raw(Pc, Pr, Q, user_matrix=umt.to(DEV), return_attention_weights=True, use_workspace=False, **common)
+        o2, a2 = ops.attention_pool_raw(Pc, Pr, Q, csr=(row_ptr.to(DEV), col.to(DEV), umt[nz].to(DEV)), return_attention_weights=True, **common)
+        assert maxnorm_rel(a1, att) < 1e-5 and maxnorm_rel(a2, att) < 1e-5
         bf = ops.attention_pool_raw(Pc, Pr.bfloat16(), Q.bfloat16(), user_matrix=umt.to(DEV), **common)
         assert maxnorm_rel(bf, dense) < 1e-2                                  # bf16 tables, fp32 accumulate
 
