@@ -46,9 +46,12 @@ SIGNATURES = {
     'b200rec_launch_count': (c_i64, []),
     'b200rec_linear_workspace': (c_sz, [c_i64, c_i64, c_i64]),
     'b200rec_linear': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
-    'b200rec_linear_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
+    'b200rec_linear_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    'b200rec_packed_weight_bytes': (c_sz, [c_i64, c_i64, c_int]),
+    'b200rec_pack_weights_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
     'b200rec_mlp_tower': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_i64, C.POINTER(MlpDesc), c_vp, c_i64, c_vp]),
     'b200rec_rowdot': (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp]),
+    'b200rec_topk_rows': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),
     'b200rec_attention_pool_workspace': (c_sz, [c_i64, c_i64, c_int, c_int]),
     'b200rec_attention_pool': (c_int, [C.POINTER(AttentionDesc), c_vp]),
     'b200rec_spmm': (c_int, [C.POINTER(SpmmDesc), c_vp]),

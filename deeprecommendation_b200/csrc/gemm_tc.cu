@@ -51,6 +51,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, UBLKCP); completion is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -100,6 +109,7 @@ struct TcParams {
   int M, N, K;
   void* Y; long long ldy; int y_bf16;
   const float* bias; const float* row_scale; int relu;
+  const unsigned char* Wp;   // optional: W pre-packed by pack_weights_kernel (swizzled tiles), moved by TMA bulk copies
   int dbg;     // experiments only (B200REC_TC_DBG): 1 = no MMA, 2 = no prefetch loads, 4 = no proxy fence
 };
 
@@ -208,7 +218,7 @@ struct TileRegs {
   }
 };
 
-template <int MODE, int NSTAGE, int EPL, bool VEC>
+template <int MODE, int NSTAGE, int EPL, bool VEC, bool WPACK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(TcParams p) {
   constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
@@ -234,7 +244,7 @@ gemm_tc_kernel(TcParams p) {
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full_bar[s], TC_PRODUCERS);
+      mbar_init(&full_bar[s], TC_PRODUCERS + (WPACK ? 1 : 0));     // + the expect_tx arrive of the W bulk copy
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
@@ -256,14 +266,17 @@ gemm_tc_kernel(TcParams p) {
     constexpr int PF = (MODE == TC_BF16) ? 1 : 2;             // k-blocks of global loads in flight ahead of the store
     TileAddr<MODE, EPL> aa, ab;
     aa.init(p.ldx, m0, p.M, warp, lane);
-    ab.init(p.ldw, n0, p.N, warp, lane);
+    if constexpr (!WPACK) ab.init(p.ldw, n0, p.N, warp, lane);
+    // packed W: tile (n-tile, k-block) = PLANES x 16 KB, already converted and swizzled (pack_weights_kernel)
+    const unsigned char* wp_tiles = WPACK ? p.Wp + (size_t)blockIdx.x * num_kb * (PLANES * TILE_BYTES) : nullptr;
+    int kstore = kb_shift;                                    // k-block index of the stage being stored
     TileRegs<MODE, EPL> xa[PF + 1], xb[PF + 1];
     int kload = kb_shift;                                     // k-block index of the next load
 #pragma unroll
     for (int d = 0; d < PF; ++d) {
       if (d < num_kb) {
         xa[d].template load<VEC>(p.X, aa, kload * KB, p.K);
-        xb[d].template load<VEC>(p.W, ab, kload * KB, p.K);
+        if constexpr (!WPACK) xb[d].template load<VEC>(p.W, ab, kload * KB, p.K);
         kload = (kload + 1 == num_kb) ? 0 : kload + 1;
       }
     }
@@ -278,13 +291,20 @@ gemm_tc_kernel(TcParams p) {
           const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
           if (kb + PF < num_kb && !(p.dbg & 2)) {              // loads of k-block kb+PF fly while kb is converted
             xa[(j + PF) % (PF + 1)].template load<VEC>(p.X, aa, kload * KB, p.K);
-            xb[(j + PF) % (PF + 1)].template load<VEC>(p.W, ab, kload * KB, p.K);
+            if constexpr (!WPACK) xb[(j + PF) % (PF + 1)].template load<VEC>(p.W, ab, kload * KB, p.K);
             kload = (kload + 1 == num_kb) ? 0 : kload + 1;
           }
           mbar_wait(&empty_bar[s], ph ^ 1u);                  // first pass through the ring: returns immediately
           unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+          if constexpr (WPACK) {
+            if (tid == 0) {                                   // W tile: one TMA bulk copy, no thread touches the data
+              mbar_arrive_expect_tx(&full_bar[s], PLANES * TILE_BYTES);
+              tma_bulk_g2s(st + PLANES * TILE_BYTES, wp_tiles + (size_t)kstore * (PLANES * TILE_BYTES), PLANES * TILE_BYTES, &full_bar[s]);
+            }
+            kstore = (kstore + 1 == num_kb) ? 0 : kstore + 1;
+          }
           xa[j].store(st, st + TILE_BYTES, aa);
-          xb[j].store(st + PLANES * TILE_BYTES, st + (PLANES + 1) * TILE_BYTES, ab);
+          if constexpr (!WPACK) xb[j].store(st + PLANES * TILE_BYTES, st + (PLANES + 1) * TILE_BYTES, ab);
           if (!(p.dbg & 4)) fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core
           mbar_arrive(&full_bar[s]);
         }
@@ -400,18 +420,61 @@ gemm_tc_kernel(TcParams p) {
   }
 }
 
-template <int MODE, int EPL, bool VEC>
+// W (N, K) fp32 -> tiles [n-tile][k-block][plane][128 rows x 128 B], converted (bf16 / TF32 hi,lo) and laid out exactly as
+// the MMA wants them (K-major SWIZZLE_128B), zero-padded in N and K.  One thread per (row, 16-byte chunk).
+template <int MODE>
+__global__ void pack_weights_kernel(const float* __restrict__ W, long long ldw, int N, int K, unsigned char* __restrict__ out) {
+  constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
+  constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
+  constexpr int EPC = (MODE == TC_BF16) ? 8 : 4;                  // source elements per 16-byte chunk
+  const int num_kb = (K + KB - 1) / KB;
+  const int n_tiles = (N + 127) / 128;
+  const long long total = (long long)n_tiles * num_kb * 128 * 8;  // 8 chunks per 128-byte row
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx & 7);
+  const int r = (int)((idx >> 3) & 127);
+  const long long tile = idx >> 10;
+  const int kb = (int)(tile % num_kb), nt = (int)(tile / num_kb);
+  const int row = nt * 128 + r, k0 = kb * KB + ch * EPC;
+  float v[EPC];
+#pragma unroll
+  for (int e = 0; e < EPC; ++e) v[e] = (row < N && k0 + e < K) ? __ldg(W + (long long)row * ldw + k0 + e) : 0.f;
+  unsigned char* base = out + (size_t)tile * (PLANES * TILE_BYTES);
+  const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+  if constexpr (MODE == TC_BF16) {
+    uint4 q;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+    q.x = *reinterpret_cast<uint32_t*>(&b0); q.y = *reinterpret_cast<uint32_t*>(&b1);
+    q.z = *reinterpret_cast<uint32_t*>(&b2); q.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(base + off) = q;
+  } else {
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { hi[e] = tf32_round(v[e]); lo[e] = v[e] - hi[e]; }
+    *reinterpret_cast<float4*>(base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(base + TILE_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+static size_t packed_weight_bytes(long long N, long long K, int mode) {
+  const int KB = (mode == TC_BF16) ? 64 : 32, PL = (mode == TC_BF16) ? 1 : 2;
+  return (size_t)((N + 127) / 128) * (size_t)((K + KB - 1) / KB) * PL * TILE_BYTES;
+}
+
+template <int MODE, int EPL, bool VEC, bool WPACK>
 static int launch_tc_epl(const TcParams& p, cudaStream_t st) {
   constexpr int NSTAGE = (MODE == TC_BF16) ? 4 : 3;
   constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
   const size_t smem = (size_t)NSTAGE * 2 * PLANES * TILE_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    B200REC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, NSTAGE, EPL, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200REC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   dim3 grid(ceil_div_i(p.N, TC_BN), ceil_div_i(p.M, TC_BM));
-  gemm_tc_kernel<MODE, NSTAGE, EPL, VEC><<<grid, TC_THREADS, smem, st>>>(p);
+  gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK><<<grid, TC_THREADS, smem, st>>>(p);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -419,28 +482,54 @@ static int launch_tc_epl(const TcParams& p, cudaStream_t st) {
 template <int MODE>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   auto aligned = [&](int n) {
-    return (p.K % n) == 0 && (p.ldx % n) == 0 && (p.ldw % n) == 0 && ((uintptr_t)p.X % (4 * n)) == 0 && ((uintptr_t)p.W % (4 * n)) == 0;
+    return (p.K % n) == 0 && (p.ldx % n) == 0 && ((uintptr_t)p.X % (4 * n)) == 0 &&
+           (p.Wp != nullptr || ((p.ldw % n) == 0 && ((uintptr_t)p.W % (4 * n)) == 0));
   };
-  if (aligned(4)) return launch_tc_epl<MODE, 4, true>(p, st);        // 128-bit loads (e.g. K = 128 transforms)
-  if (aligned(2)) return launch_tc_epl<MODE, 2, true>(p, st);        // 64-bit loads (F = 2094)
-  return launch_tc_epl<MODE, 2, false>(p, st);                       // odd K / pitch: scalar loads
+  if (p.Wp) {
+    if (aligned(4)) return launch_tc_epl<MODE, 4, true, true>(p, st);
+    if (aligned(2)) return launch_tc_epl<MODE, 2, true, true>(p, st);
+    return launch_tc_epl<MODE, 2, false, true>(p, st);
+  }
+  if (aligned(4)) return launch_tc_epl<MODE, 4, true, false>(p, st);        // 128-bit loads (e.g. K = 128 transforms)
+  if (aligned(2)) return launch_tc_epl<MODE, 2, true, false>(p, st);        // 64-bit loads (F = 2094)
+  return launch_tc_epl<MODE, 2, false, false>(p, st);                       // odd K / pitch: scalar loads
 }
 
 }  // namespace b200rec
 
 using namespace b200rec;
 
+extern "C" size_t b200rec_packed_weight_bytes(int64_t N, int64_t K, int mode) {
+  return (N > 0 && K > 0) ? packed_weight_bytes(N, K, mode) : 0;
+}
+
+extern "C" int b200rec_pack_weights_tc(const float* W, int64_t N, int64_t K, int64_t ldw, int mode, void* packed, size_t packed_bytes,
+                                       b200rec_stream_t stream) {
+  if (!W || !packed || N <= 0 || K <= 0 || ldw < K) return b200rec_fail(B200REC_ERR_BAD_ARG, "pack_weights_tc: bad argument");
+  if (packed_bytes < packed_weight_bytes(N, K, mode) || ((uintptr_t)packed % 128))
+    return b200rec_fail(B200REC_ERR_WORKSPACE, "pack_weights_tc: buffer too small or not 128-byte aligned");
+  const int KB = (mode == TC_BF16) ? 64 : 32;
+  const long long total = ((N + 127) / 128) * ((K + KB - 1) / KB) * 128LL * 8;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (mode == TC_BF16) pack_weights_kernel<TC_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)N, (int)K, (unsigned char*)packed);
+  else if (mode == TC_TF32X3) pack_weights_kernel<TC_TF32X3><<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)N, (int)K, (unsigned char*)packed);
+  else return b200rec_fail(B200REC_ERR_BAD_ARG, "pack_weights_tc: bad mode");
+  B200REC_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 extern "C" int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
                                  const float* bias, const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode,
-                                 b200rec_stream_t stream) {
-  if (M < 0 || N <= 0 || K <= 0 || !W || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad argument");
+                                 const void* packed_w, b200rec_stream_t stream) {
+  if (M < 0 || N <= 0 || K <= 0 || (!W && !packed_w) || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad argument");
   if (M == 0) return B200REC_OK;
   if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: dim > int32");
   if (ldx < K || ldw < K || ldy < N) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: leading dimension too small");
-  if (M * ldx >= (1LL << 32) || N * ldw >= (1LL << 32)) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: operand larger than 2^32 elements");
+  if (M * ldx >= (1LL << 32) || (!packed_w && N * ldw >= (1LL << 32))) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: operand larger than 2^32 elements");
   if (y_dtype != B200REC_F32 && y_dtype != B200REC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad y_dtype");
   TcParams p;
   p.X = X; p.ldx = ldx; p.W = W; p.ldw = ldw; p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.Wp = (const unsigned char*)packed_w;
   p.Y = Y; p.ldy = ldy; p.y_bf16 = y_dtype == B200REC_BF16; p.bias = bias; p.row_scale = row_scale; p.relu = relu;
   {
     const char* e = getenv("B200REC_TC_DBG");

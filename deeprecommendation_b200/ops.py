@@ -11,6 +11,7 @@ CUDA ops for now (documented in DESIGN.md §7).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -108,6 +109,29 @@ TC_MIN_ROWS = 2048
 TC_MIN_K = 512          # short-K GEMMs (the d x d GraphNCF transforms) are epilogue/latency-bound: FFMA is as fast there
 
 
+_pack_weights = True          # move the W operand of the tensor-core GEMM by TMA from a pre-swizzled copy
+_pack_cache = {}              # (data_ptr, version, shape, ld, mode) -> packed buffer; a handful of weight matrices at most
+
+
+def _packed_weight(w, ldw, mode):
+    """MMA-ready copy of a weight matrix (b200rec_pack_weights_tc), cached until the tensor changes (`_version`)."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), ldw, mode, w.device.index)
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0]() is w:          # same live tensor object, unchanged since it was packed
+        return hit[1]
+    lib = L.lib()
+    N, K = w.shape
+    nbytes = lib.b200rec_packed_weight_bytes(N, K, mode)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        L.check(lib.b200rec_pack_weights_tc(_ptr(w), N, K, ldw, mode, _ptr(buf), nbytes, _stream()), 'pack_weights_tc')
+    if len(_pack_cache) > 64:
+        _pack_cache.clear()
+    if not (torch.is_grad_enabled() and w.requires_grad):
+        _pack_cache[key] = (weakref.ref(w), buf)
+    return buf
+
+
 def set_gemm_engine(name: str):
     global _gemm_engine
     if name not in ('simt', 'tf32x3', 'bf16'):
@@ -138,9 +162,10 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     engine = engine or _gemm_engine
     if engine != 'simt' and ((M >= TC_MIN_ROWS and K >= TC_MIN_K) or engine.endswith('!')) and M * ldx < 2 ** 32:
         mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+        packed = _packed_weight(w, ldw, mode) if _pack_weights else None
         with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
             L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
-                                          _dtype_code(out.dtype), mode, _stream()), 'linear_tc')
+                                          _dtype_code(out.dtype), mode, _ptr(packed), _stream()), 'linear_tc')
         return out
     ws_bytes = lib.b200rec_linear_workspace(M, N, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
@@ -494,3 +519,20 @@ def attention_pool(Pc, Pr, Q, *, mode, a2, a20, bU, user_matrix, return_attentio
     return attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, user_matrix=user_matrix,
                               return_attention_weights=return_attention_weights, train_mask=train_mask,
                               drop_zero_scores=drop_zero_scores, score_scale=score_scale)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# top-k
+# ------------------------------------------------------------------------------------------------------------------
+def topk_rows(scores, k):
+    """(values (R,k), indices (R,k) int64) of the k largest entries of every row, descending — b200rec_topk_rows."""
+    _require_cuda(scores)
+    squeeze = scores.dim() == 1
+    s2 = scores.view(1, -1) if squeeze else scores
+    s2, ld = _row_major(s2)
+    R, Cc = s2.shape
+    val = torch.empty((R, k), dtype=torch.float32, device=s2.device)
+    idx = torch.empty((R, k), dtype=torch.int64, device=s2.device)
+    with torch.cuda.device(s2.device), _timed('topk', (R, Cc, k)):
+        L.check(L.lib().b200rec_topk_rows(_ptr(s2), R, Cc, ld, k, _ptr(val), _ptr(idx), _stream()), 'topk_rows')
+    return (val[0], idx[0]) if squeeze else (val, idx)

@@ -50,7 +50,13 @@ int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const floa
 /* Same contract on the tensor cores (tcgen05.mma, TMEM accumulators; csrc/gemm_tc.cu).  mode B200REC_TC_TF32X3: fp32-parity
  * 3xTF32 split (rel <= 1e-5); B200REC_TC_BF16: bf16 operands (rel <= 1e-2).  Needs no workspace; meant for M >= ~1024. */
 int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
-                      const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, b200rec_stream_t stream);
+                      const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w,
+                      b200rec_stream_t stream);
+/* Optional: W converted once into MMA-ready swizzled tiles (bf16 or TF32 hi/lo, zero-padded).  With `packed_w` the GEMM moves
+ * the W operand by TMA bulk copies (cp.async.bulk) and only X is converted by the producer warps.  128-byte aligned buffer. */
+size_t b200rec_packed_weight_bytes(int64_t N, int64_t K, int mode);
+int b200rec_pack_weights_tc(const float* W, int64_t N, int64_t K, int64_t ldw, int mode, void* packed, size_t packed_bytes,
+                            b200rec_stream_t stream);
 
 /* ---- K1b  fused MLP tower ------------------------------------------------------------------------------------
  * Replaces torch.cat + build_MLP_layers (util.py:5-18; basic_ncf.py:40-41, attention_ncf.py:219-222, gnn_ncf.py:354-362):
@@ -69,6 +75,12 @@ int b200rec_mlp_tower(const float* in0, int64_t ld0, const int64_t* idx0, int E0
 /* GraphNCF(use_dot_product=True), gnn_ncf.py:365: out[b] = <in0[idx0[b]], in1[idx1[b]]> */
 int b200rec_rowdot(const float* in0, int64_t ld0, const int64_t* idx0, const float* in1, int64_t ld1, const int64_t* idx1, int E,
                    int64_t B, float* out, b200rec_stream_t stream);
+
+/* ---- row-wise top-k (k <= 64), descending, ties towards the lower column, NaN never selected; rows with fewer than k valid
+ * scores are padded with (-inf, -1).  Replaces `sort_values(by='score', ascending=False).iloc[:k]` of src/webapp/backend.py:113-121
+ * and the per-user top-K of BASELINE config 4.  scores (rows, cols) ld; out_val (rows, k) fp32; out_idx (rows, k) int64. */
+int b200rec_topk_rows(const float* scores, int64_t rows, int64_t cols, int64_t ld, int k, float* out_val, int64_t* out_idx,
+                      b200rec_stream_t stream);
 
 /* ---- K2  AttentionNCF ragged attention pooling ------------------------------------------------------------------
  * Replaces attention_ncf.py:154-216.  With AttentionNet.0 = [A1c | A1r]:  Pc = Ec·A1cᵀ + a1 (B,H), Pr = Er·A1rᵀ (I,H),

@@ -130,3 +130,29 @@ def test_stable_sort_pairs(dev, n, bits):
     order = np.argsort(k, kind='stable')
     assert np.array_equal(kt.cpu().numpy(), k[order])
     assert np.array_equal(vt.cpu().numpy(), v[order])          # bit-exact permutation == numpy's stable argsort
+
+
+# ---- row-wise top-k (serving path: webapp/backend.py:113-121, BASELINE configs[3]) -----------------------------------
+@pytest.mark.parametrize('R,C,k', [(1, 9724, 10), (37, 1000, 5), (8, 100_000, 20), (3, 7, 10), (5, 300, 64), (2, 1, 1)])
+def test_topk_rows_matches_stable_sort(dev, R, C, k):
+    """indices bit-exact against a stable descending sort (ties -> lower column, as pandas' mergesort-free
+    `sort_values(ascending=False)` would only guarantee for distinct scores; we pin the stable order)"""
+    from deeprecommendation_b200 import ops
+    g = torch.Generator().manual_seed(R * 131 + C)
+    s = torch.randn(R, C, generator=g)
+    s[:, ::7] = s[:, :1]                                  # many exact ties
+    if C > 3:
+        s[0, 2] = float('nan')                            # never selected
+    val, idx = ops.topk_rows(s.to(dev), k)
+    sn = s.numpy().copy()
+    sn[np.isnan(sn)] = -np.inf
+    order = np.argsort(-sn, axis=1, kind='stable')[:, :k]
+    kk = min(k, C)
+    ref_idx = np.full((R, k), -1, dtype=np.int64)
+    ref_val = np.full((R, k), -np.inf, dtype=np.float32)
+    ref_idx[:, :kk] = order[:, :kk]
+    ref_val[:, :kk] = np.take_along_axis(sn, order[:, :kk], 1)
+    nanpos = np.isinf(ref_val) & (ref_idx >= 0) & np.isnan(np.take_along_axis(s.numpy(), np.maximum(ref_idx, 0), 1))
+    ref_idx[nanpos] = -1                                  # a NaN column is reported as "no entry"
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert np.array_equal(val.cpu().numpy(), ref_val)
