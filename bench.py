@@ -140,6 +140,9 @@ def op_breakdown(step_fn, steps, start_index):
     ops.set_timer(timer)
     try:
         for i in range(steps):
+            # keep the device busy for ~1 ms first, so that the whole step is queued behind it and the events bracket
+            # device time only (not the CPU's launch latency, which is what an idle GPU would make them measure)
+            torch.cuda._sleep(2_000_000)
             step_fn(start_index + i)
         torch.cuda.synchronize()
     finally:
@@ -199,18 +202,45 @@ def build_attention(dev, rank, n_batches=8):
 
 
 def run_attention(w, steps, warmup, dist, dev, peaks):
+    from deeprecommendation_b200 import ops
+    from deeprecommendation_b200.graphed import GraphedForward
     model, host = w['model'], w['host']
     resident = [tuple(t.to(dev) for t in b) for b in host]
     nb = len(resident)
 
-    def step(i):
+    def step_eager(i):
         with torch.no_grad():
             return model(*resident[i % nb])
 
-    ms, launches = timed_steps(step, steps, warmup, dist, dev)
+    # one CUDA graph per rotating batch (their rated-item unions differ in size, i.e. in shape): the ~12 launches of a
+    # forward are replayed without Python / launch overhead.  The captured inputs are the graphs' own resident copies.
+    graphs = None
+    if not w.get('eager'):
+        try:
+            graphs = [GraphedForward(lambda c, r, um: model(c, r, um), *b) for b in resident]
+            resident = None                                  # the graphs own the device copies now
+        except Exception as e:
+            w['graph_capture_error'] = repr(e)[:300]
+            graphs = None
+    if graphs is None and resident is None:
+        resident = [tuple(t.to(dev) for t in b) for b in host]
 
-    # end to end: pinned host buffers in, scores out, every step
+    def step(i):
+        if graphs is None:
+            return step_eager(i)
+        return graphs[i % nb].replay()
+
+    ms, launches = timed_steps(step, steps, warmup, dist, dev)
+    if graphs is not None:                                   # replays do not pass through the launch counter
+        resident = [tuple(g.static_in) for g in graphs]
+        l0 = ops.launch_count()
+        step_eager(0)
+        launches = (ops.launch_count() - l0) * steps
+
+    # end to end: pinned host buffers in, scores out, every step (H2D straight into the captured input buffers)
     def step_e2e(i):
+        if graphs is not None:
+            return graphs[i % nb](*host[i % nb]).cpu()
         with torch.no_grad():
             c, r, um = (t.to(dev, non_blocking=True) for t in host[i % nb])
             return model(c, r, um).cpu()
@@ -225,6 +255,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
     h2d = int(np.mean([sum(t.numel() * 4 for t in b) for b in host]))
 
+    step = step_eager
     ops_ms = op_breakdown(step, min(steps, nb), 0)
     (name, meta), (kms, per_step) = max(ops_ms.items(), key=lambda kv: kv[1][0] * kv[1][1])
     I_mean = float(np.mean([b[1].shape[0] for b in host]))
@@ -245,7 +276,8 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4, roofline=roof, I_mean=I_mean,
-                nnz_mean=float(np.mean(w['nnz'])))
+                nnz_mean=float(np.mean(w['nnz'])),
+                launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
 def cpu_attention(w, sample_pairs=64, repeats=3):
@@ -577,7 +609,7 @@ def main():
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
                     help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
     ap.add_argument('--skip-hbm-regime', action='store_true')
-    ap.add_argument('--eager', action='store_true', help='do not capture the GraphNCF step into a CUDA graph')
+    ap.add_argument('--eager', action='store_true', help='do not capture the steps into CUDA graphs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -606,6 +638,7 @@ def main():
         if args.workload in ('all', 'attention'):
             w = build_attention(dev, rank)
             w['gemm'] = args.gemm
+            w['eager'] = args.eager
             r = run_attention(w, args.steps, args.warmup, dist, dev, peaks)
             pairs = BATCH * args.steps * world
             result = {'metric': 'scored user-item pairs/sec (NCF fwd)', 'value': pairs / (r['ms'] * 1e-3), 'unit': 'pairs/s',
@@ -613,7 +646,8 @@ def main():
                       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                       'config': {'workload': ATT_WORKLOAD, 'batch': BATCH, 'parallelism': f'dp{world} (pairs sharded, no collective)',
                                  'mean_rated_union_I': r['I_mean'], 'mean_nnz_per_batch': r['nnz_mean'],
-                                 'l2': f'{len(w["host"])} rotating batches (~105 MB each) resident in HBM, > 126 MB L2 between reuses'},
+                                 'l2': f'{len(w["host"])} rotating batches (~105 MB each) resident in HBM, > 126 MB L2 between reuses',
+                                 'launch_mode': r['launch_mode']},
                       'roofline': r['roofline'],
                       'e2e': {'value': pairs / (r['e2e_ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': r['h2d'],
                               'd2h_bytes_per_step': r['d2h'], 'ms_per_step': r['e2e_ms'] / args.steps},

@@ -12,6 +12,7 @@ OK, ERR_CUDA, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 F32, BF16 = 0, 1
 ATT_NET, ATT_DOT = 0, 1
 TC_TF32X3, TC_BF16 = 0, 1
+AP_BF16, AP_BF16X2 = 0, 1
 MLP_MAX_LAYERS = 8
 
 c_i64, c_int, c_sz, c_vp, c_f = C.c_int64, C.c_int, C.c_size_t, C.c_void_p, C.c_float
@@ -51,6 +52,11 @@ SIGNATURES = {
     'b200rec_pack_weights_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
     'b200rec_mlp_tower': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_i64, C.POINTER(MlpDesc), c_vp, c_i64, c_vp]),
     'b200rec_rowdot': (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp]),
+    'b200rec_allpairs_packed_bytes': (c_sz, [c_int, c_int]),
+    'b200rec_allpairs_pack': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    'b200rec_allpairs_splits': (c_int, [c_i64, c_i64, c_int]),
+    'b200rec_allpairs_workspace': (c_sz, [c_i64, c_int, c_int]),
+    'b200rec_allpairs_topk': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'b200rec_topk_rows': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),
     'b200rec_attention_pool_workspace': (c_sz, [c_i64, c_i64, c_int, c_int]),
     'b200rec_attention_pool': (c_int, [C.POINTER(AttentionDesc), c_vp]),

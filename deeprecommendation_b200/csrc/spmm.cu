@@ -17,6 +17,7 @@
 // flight per warp.  (A cp.async/LDGSTS shared-memory ring was tried and measured 1.5x SLOWER — 3.4 vs 2.25 ms per
 // layer on the MovieLens-25M shape — and was dropped)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -91,13 +92,26 @@ template <> struct Lane16<__nv_bfloat16> {
 };
 
 __device__ __forceinline__ uint4 ldg16(const unsigned char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// Feature rows are the only data of a layer that is re-read (2E gathers over N rows); the CSR streams (`__ldcs`) and the
+// outputs pass through once.  KEEP = load the rows with an L2 evict_last policy so that the streams do not push them out
+// (profiles/r01: 2.2 GB of DRAM reads per layer against 0.63 GB compulsory with the default policy).
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg16_keep(const unsigned char* p, uint64_t pol) {
+  uint4 r;
+  asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
 
 // G lanes cooperate on one edge (each lane owns 16 bytes of the source row; G*16*NV >= row bytes), so 32/G edges
 // advance per warp step.  The inner loop is branch- and predicate-free: padding / masked edges carry (source 0,
 // weight 0) and lanes beyond the row width read column 0, so every load is valid and the per-edge cost is
 // 2 SHFL + 1 IMAD.WIDE.U32 + 1 LDG.128 + 4 FFMA (the first version spent ~26 instructions per edge on predicated
 // 64-bit address arithmetic and zero-fill moves — profiles/r01).
-template <int G, int NV, typename T, bool GAT>
+template <int G, int NV, typename T, bool GAT, bool KEEP>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 spmm_chunk_kernel(SpmmParams p) {
   constexpr int EPW = 32 / G;                       // edges per warp step
@@ -111,6 +125,7 @@ spmm_chunk_kernel(SpmmParams p) {
   const int s = __ldg(p.chunk_start + chunk);
   const int e = min(s + p.chunk_size, __ldg(p.row_ptr + row + 1));
   const unsigned stride_bytes = (unsigned)(p.ld_t * (long long)sizeof(T));
+  const uint64_t keep = KEEP ? l2_keep_policy() : 0ull;
   const unsigned char* base[NV];
   bool active[NV];
 #pragma unroll
@@ -176,7 +191,10 @@ spmm_chunk_kernel(SpmmParams p) {
           const unsigned cc = __shfl_sync(FULL, c, src_lane);
           ww[u] = __shfl_sync(FULL, wv, src_lane);
 #pragma unroll
-          for (int nv = 0; nv < NV; ++nv) x[u][nv] = ldg16(base[nv] + (unsigned long long)cc * stride_bytes);
+          for (int nv = 0; nv < NV; ++nv) {
+            const unsigned char* src = base[nv] + (unsigned long long)cc * stride_bytes;
+            x[u][nv] = KEEP ? ldg16_keep(src, keep) : ldg16(src);
+          }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -258,8 +276,10 @@ spmm_fixup_kernel(SpmmParams p) {
 template <int G, int NV, typename T>
 static int launch_chunks(const SpmmParams& p, cudaStream_t st) {
   const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
-  if (p.att_src) spmm_chunk_kernel<G, NV, T, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
-  else spmm_chunk_kernel<G, NV, T, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  static const bool keep = []() { const char* e = getenv("B200REC_SPMM_L2_KEEP"); return e == nullptr || atoi(e) != 0; }();
+  if (p.att_src) spmm_chunk_kernel<G, NV, T, true, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  else if (keep) spmm_chunk_kernel<G, NV, T, false, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  else spmm_chunk_kernel<G, NV, T, false, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }

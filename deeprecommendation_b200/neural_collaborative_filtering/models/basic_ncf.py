@@ -4,7 +4,7 @@ from __future__ import annotations
 from torch import nn
 
 from ... import ops
-from ..util import build_MLP_layers, run_mlp
+from ..util import build_MLP_layers, mlp_parameters, run_mlp
 from .base import NCF, _named_like
 
 
@@ -27,6 +27,24 @@ class BasicNCF(NCF):
         user_emb = ops.linear(X_user, ue.weight, ue.bias)
         item_emb = ops.linear(X_item, ie.weight, ie.bias)
         return run_mlp(self.MLP, user_emb, item_emb, training=self.training)
+
+    def recommend(self, X_users, X_items, k=10, precision='fp32', seen=None, return_scores=False):
+        """Top-k items for every user over ALL (user, item) pairs — BASELINE configs[3]; the batched form of the reference's
+        serving loop (src/webapp/backend.py:78-121: score every candidate for a user, sort, keep k).  X_users (nU, user_dim),
+        X_items (nI, item_dim).  Returns (scores (nU, k), item positions (nU, k) int64[, all scores (nU, nI)]).
+        Same arithmetic as `forward` on every pair, with the first MLP Linear split per side (exact) and the rest in the fused
+        tcgen05 kernel (csrc/allpairs.cu); `seen` = CSR (ptr, idx) of pairs to leave out (`ignore_seen`, backend.py:85)."""
+        if self.training:
+            raise RuntimeError('recommend() is an inference call: model.eval() first')
+        import torch
+        ue, ie = self.user_embeddings[0], self.item_embeddings[0]
+        with torch.no_grad():
+            user_emb = ops.linear_raw(X_users, ue.weight, ue.bias)
+            item_emb = ops.linear_raw(X_items, ie.weight, ie.bias)
+            weights, biases, _ = mlp_parameters(self.MLP)
+            val, idx, scores = ops.mlp_allpairs_topk(user_emb, item_emb, weights, biases, k, rows_first=True, precision=precision,
+                                                     seen=seen, return_scores=return_scores)
+        return (val, idx, scores) if return_scores else (val, idx)
 
     def is_dataset_compatible(self, dataset_class):
         return _named_like(dataset_class, 'FixedPointwiseDataset', 'FixedRankingDataset')

@@ -536,3 +536,108 @@ def topk_rows(scores, k):
     with torch.cuda.device(s2.device), _timed('topk', (R, Cc, k)):
         L.check(L.lib().b200rec_topk_rows(_ptr(s2), R, Cc, ld, k, _ptr(val), _ptr(idx), _stream()), 'topk_rows')
     return (val[0], idx[0]) if squeeze else (val, idx)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K5 all-pairs scoring + top-k (tcgen05)
+# ------------------------------------------------------------------------------------------------------------------
+_ap_cache = {}
+
+
+def allpairs_pack(W2, b2, w3, b3, H1p, mode):
+    """MMA-ready copy of the second MLP layer (+ b2, w3, b3) for `allpairs_topk_raw`; cached until a tensor changes."""
+    _require_cuda(W2, b2, w3, b3)
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (W2, b2, w3, b3) if t is not None) + (H1p, mode, W2.device.index)
+    hit = _ap_cache.get(key)
+    if hit is not None:
+        return hit
+    lib = L.lib()
+    H2, H1 = W2.shape
+    w2p = W2.detach().float()
+    if H1 != H1p or not w2p.is_contiguous():                 # zero-pad K to a multiple of 64
+        w2p = torch.nn.functional.pad(w2p, (0, H1p - H1)).contiguous()
+    b2c, w3c = b2.detach().float().contiguous(), w3.detach().float().contiguous().view(-1)
+    b3c = b3.detach().float().contiguous().view(-1) if b3 is not None else None
+    nbytes = lib.b200rec_allpairs_packed_bytes(H1p, mode)
+    if nbytes == 0:
+        raise NotImplementedError(f'all-pairs kernel: first hidden width {H1} > 256')
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=W2.device)
+    with torch.cuda.device(W2.device):
+        L.check(lib.b200rec_allpairs_pack(_ptr(w2p), H1p, H2, H1p, _ptr(b2c), _ptr(w3c), _ptr(b3c), mode, _ptr(buf), nbytes, _stream()),
+                'allpairs_pack')
+    if len(_ap_cache) > 32:
+        _ap_cache.clear()
+    if not torch.is_grad_enabled() or not any(t is not None and t.requires_grad for t in (W2, b2, w3, b3)):
+        _ap_cache[key] = buf
+    return buf
+
+
+def allpairs_topk_raw(A, B, packed, mode, k, *, return_scores=False, seen=None, n_splits=0):
+    """A (nU, H1p), B (nI, H1p) contiguous fp32 with H1p % 64 == 0.  Returns (top_val (nU,k), top_idx (nU,k) int64, scores|None)
+    — b200rec_allpairs_topk.  `seen` = (ptr int32 (nU+1), idx int32 sorted per user): pairs never recommended."""
+    _require_cuda(A, B, packed)
+    if A.dtype != torch.float32 or B.dtype != torch.float32 or not A.is_contiguous() or not B.is_contiguous():
+        raise ValueError('allpairs: A and B must be contiguous fp32')
+    nU, H1p = A.shape
+    nI = B.shape[0]
+    if B.shape[1] != H1p:
+        raise ValueError('allpairs: A and B disagree on the hidden width')
+    lib = L.lib()
+    dev = A.device
+    if n_splits <= 0:
+        n_splits = lib.b200rec_allpairs_splits(nU, nI, mode)
+    val = torch.empty((nU, k), dtype=torch.float32, device=dev) if k > 0 else None
+    idx = torch.empty((nU, k), dtype=torch.int64, device=dev) if k > 0 else None
+    scores = torch.empty((nU, nI), dtype=torch.float32, device=dev) if return_scores else None
+    wsb = lib.b200rec_allpairs_workspace(nU, k, n_splits) if k > 0 else 0
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+    sp = si = None
+    if seen is not None:
+        sp, si = seen[0].contiguous().int(), seen[1].contiguous().int()
+        if sp.numel() != nU + 1:
+            raise ValueError('allpairs: seen_ptr must have nU + 1 entries')
+    with torch.cuda.device(dev), _timed('allpairs', (nU, nI, H1p, k, mode)):
+        L.check(lib.b200rec_allpairs_topk(_ptr(A), _ptr(B), nU, nI, H1p, _ptr(packed), mode, k, n_splits, _ptr(sp), _ptr(si),
+                                          _ptr(scores), nI, _ptr(val), _ptr(idx), _ptr(ws), wsb, _stream()), 'allpairs_topk')
+    return val, idx, scores
+
+
+def mlp_allpairs_topk(row_emb, col_emb, weights, biases, k, *, rows_first=True, precision='fp32', seen=None, return_scores=False,
+                      n_splits=0):
+    """Scores `MLP(cat(row_emb[u], col_emb[i]))` (rows_first) or `MLP(cat(col_emb[i], row_emb[u]))` for EVERY (u, i) and keeps
+    the k best columns per row.  The first Linear is split into its two halves (two K1a GEMMs over nU resp. nI rows), the rest
+    runs in the fused tensor-core kernel.  precision 'fp32' = bf16 hi/lo split operands (rel <= 1e-5), 'bf16' = plain bf16."""
+    n = len(weights)
+    if n not in (2, 3):
+        raise NotImplementedError(f'all-pairs scoring supports MLPs with 1 or 2 hidden layers (the reference uses [256], [128], '
+                                  f'[256,128]); got {n - 1}')
+    mode = {'fp32': L.AP_BF16X2, 'bf16': L.AP_BF16}[precision]
+    W1, b1 = weights[0], biases[0]
+    Er, Ec = row_emb.shape[1], col_emb.shape[1]
+    H1 = W1.shape[0]
+    if W1.shape[1] != Er + Ec:
+        raise ValueError('all-pairs: first MLP layer does not take cat(row_emb, col_emb)')
+    H1p = (H1 + 63) // 64 * 64
+    if H1p > 256:
+        raise NotImplementedError(f'all-pairs kernel: first hidden width {H1} > 256')
+    W1r, W1c = (W1[:, :Er], W1[:, Er:]) if rows_first else (W1[:, Ec:], W1[:, :Ec])
+    dev = row_emb.device
+    A = torch.zeros((row_emb.shape[0], H1p), dtype=torch.float32, device=dev) if H1p != H1 else \
+        torch.empty((row_emb.shape[0], H1p), dtype=torch.float32, device=dev)
+    Bm = torch.zeros((col_emb.shape[0], H1p), dtype=torch.float32, device=dev) if H1p != H1 else \
+        torch.empty((col_emb.shape[0], H1p), dtype=torch.float32, device=dev)
+    linear_raw(row_emb, W1r, b1, out=A[:, :H1])
+    linear_raw(col_emb, W1c, None, out=Bm[:, :H1])
+    if n == 3:
+        W2, b2, w3, b3 = weights[1], biases[1], weights[2], biases[2]
+        if W2.shape[0] > 128:
+            raise NotImplementedError(f'all-pairs kernel: second hidden width {W2.shape[0]} > 128')
+    else:
+        # one hidden layer: score = w2·h1 + b2 = ReLU(w2·h1) - ReLU(-w2·h1) + b2 — two rows of the generic second layer
+        w2 = weights[1].detach().view(1, -1)
+        W2 = torch.cat((w2, -w2), 0)
+        b2 = torch.zeros(2, dtype=torch.float32, device=dev)
+        w3 = torch.tensor([1.0, -1.0], dtype=torch.float32, device=dev)
+        b3 = biases[1]
+    packed = allpairs_pack(W2, b2, w3, b3, H1p, mode)
+    return allpairs_topk_raw(A, Bm, packed, mode, k, return_scores=return_scores, seen=seen, n_splits=n_splits)

@@ -82,6 +82,28 @@ int b200rec_rowdot(const float* in0, int64_t ld0, const int64_t* idx0, const flo
 int b200rec_topk_rows(const float* scores, int64_t rows, int64_t cols, int64_t ld, int k, float* out_val, int64_t* out_idx,
                       b200rec_stream_t stream);
 
+/* ---- K5  all-pairs scoring + per-user top-k (tcgen05 tensor cores; csrc/allpairs.cu) --------------------------------
+ * Replaces, for every (user, item) pair of a user set x item set, `MLP(cat(user_emb, item_emb))` of models/basic_ncf.py:40-41
+ * (util.py:5-18; item-first for models/gnn_ncf.py:361) followed by the `sort_values(by='score', ascending=False).iloc[:k]` of
+ * src/webapp/backend.py:113-121 — BASELINE configs[3].  The first Linear of the MLP is split by the caller:
+ *   A = user_emb · W1[:, :Eu]^T + b1  (nU, H1),   B = item_emb · W1[:, Eu:]^T  (nI, H1)      (K1a; contiguous rows, H1 % 64 == 0,
+ *   H1 <= 256 — zero-pad the columns);  score(u, i) = w3 · ReLU(W2 · ReLU(A[u] + B[i]) + b2) + b3,  W2 (H2 <= 128, H1).
+ * b200rec_allpairs_pack converts W2 once into MMA-ready bf16 tiles (+ b2, w3, b3).  mode B200REC_AP_BF16: bf16 operands
+ * (rel <= 1e-2); B200REC_AP_BF16X2: operands split into bf16 hi + lo, 3 MMAs per k-step (fp32 tolerance, rel <= 1e-5).
+ * Outputs: top_val (nU, k) fp32 / top_idx (nU, k) int64 item positions, descending, ties towards the lower item, fewer than k
+ * valid items padded with (-inf, -1), NaN never selected; optional `scores` (nU, nI) ld = lds (NULL = never materialised);
+ * optional CSR `seen_ptr` (nU+1) / `seen_idx` (sorted item positions per user): those pairs are not recommended
+ * (`ignore_seen`, backend.py:85).  n_splits <= 0 = automatic (b200rec_allpairs_splits). */
+enum { B200REC_AP_BF16 = 0, B200REC_AP_BF16X2 = 1 };
+size_t b200rec_allpairs_packed_bytes(int H1, int mode);
+int b200rec_allpairs_pack(const float* W2, int64_t ldw2, int H2, int H1, const float* b2, const float* w3, const float* b3, int mode,
+                          void* packed, size_t packed_bytes, b200rec_stream_t stream);
+int b200rec_allpairs_splits(int64_t nU, int64_t nI, int mode);
+size_t b200rec_allpairs_workspace(int64_t nU, int k, int n_splits);
+int b200rec_allpairs_topk(const float* A, const float* B, int64_t nU, int64_t nI, int H1, const void* packed, int mode, int k,
+                          int n_splits, const int32_t* seen_ptr, const int32_t* seen_idx, float* scores, int64_t lds, float* top_val,
+                          int64_t* top_idx, void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
+
 /* ---- K2  AttentionNCF ragged attention pooling ------------------------------------------------------------------
  * Replaces attention_ncf.py:154-216.  With AttentionNet.0 = [A1c | A1r]:  Pc = Ec·A1cᵀ + a1 (B,H), Pr = Er·A1rᵀ (I,H),
  * Q = rated_items·W_Uᵀ (I,U);  s_bi = a2·ReLU(Pc[b] + Pr[i]) + a20 (mode NET)  or  <Pc[b], Pr[i]> (mode DOT: cosine / att_dense=None);

@@ -45,6 +45,35 @@ def basic_ncf_forward(sd, X_user: torch.Tensor, X_item: torch.Tensor) -> torch.T
     return mlp_forward(combined, sd)                                                            # :41
 
 
+def basic_ncf_all_pairs(sd, X_users: torch.Tensor, X_items: torch.Tensor) -> torch.Tensor:
+    """(nU, nI) scores: the reference forward on every (user, item) pair, users major — what BASELINE configs[3] and the
+    webapp's score-every-candidate loop (webapp/backend.py:96-99) evaluate."""
+    nU, nI = X_users.shape[0], X_items.shape[0]
+    out = torch.empty((nU, nI), dtype=torch.float32)
+    for u in range(nU):
+        out[u] = basic_ncf_forward(sd, X_users[u:u + 1].expand(nI, -1), X_items).view(-1)
+    return out
+
+
+def topk_stable(scores: torch.Tensor, k: int, seen=None):
+    """k best columns per row, descending, ties towards the lower column (`sort_values(by='score', ascending=False).iloc[:k]`,
+    webapp/backend.py:113-121, pinned to a stable order); `seen[u]` = columns left out (`ignore_seen`, :85).
+    Returns (values (nU, k) fp32, indices (nU, k) int64); rows with fewer than k candidates are padded with (-inf, -1)."""
+    s = scores.detach().cpu().numpy().astype(np.float32).copy()
+    nU, nI = s.shape
+    val = np.full((nU, k), -np.inf, dtype=np.float32)
+    idx = np.full((nU, k), -1, dtype=np.int64)
+    for u in range(nU):
+        cols = np.arange(nI)
+        if seen is not None:
+            cols = np.setdiff1d(cols, np.asarray(seen[u], dtype=np.int64))
+        cols = cols[~np.isnan(s[u, cols])]
+        order = cols[np.argsort(-s[u, cols], kind='stable')][:k]
+        val[u, :len(order)] = s[u, order]
+        idx[u, :len(order)] = order
+    return torch.from_numpy(val), torch.from_numpy(idx)
+
+
 # --------------------------------------------------------------------------------------------------
 # a-3  AttentionNCF.forward — models/attention_ncf.py:136-224
 # --------------------------------------------------------------------------------------------------

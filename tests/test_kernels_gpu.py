@@ -140,7 +140,7 @@ def test_topk_rows_matches_stable_sort(dev, R, C, k):
     from deeprecommendation_b200 import ops
     g = torch.Generator().manual_seed(R * 131 + C)
     s = torch.randn(R, C, generator=g)
-    s[:, ::7] = s[:, :1]                                  # many exact ties
+    s[:, ::7] = s[:, :1].clone()                          # many exact ties
     if C > 3:
         s[0, 2] = float('nan')                            # never selected
     val, idx = ops.topk_rows(s.to(dev), k)
