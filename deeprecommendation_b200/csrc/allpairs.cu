@@ -99,6 +99,13 @@ __device__ __forceinline__ uint32_t ap_pack(float x0, float x1) {
   return d;
 }
 
+// relu(a * 1 + b) on two packed bf16 pairs (HFMA2.BF16 with the ReLU folded in)
+__device__ __forceinline__ uint32_t ap_add_relu_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x3F803F80u), "r"(b));
+  return d;
+}
+
 struct AllPairsParams {
   const float* A;             // (nU, H1) contiguous
   const float* B;             // (nI, H1) contiguous
@@ -124,7 +131,8 @@ struct ApLayout {
   __host__ __device__ static constexpr int w2(int) { return 0; }
   __host__ __device__ static constexpr int ring(int nkb) { return nkb * PLANES * AP_TILE; }
   __host__ __device__ static constexpr int users(int nkb) { return ring(nkb) + NS * STAGE; }
-  __host__ __device__ static constexpr int tail(int nkb) { return users(nkb) + UT * nkb * 64 * 4; }      // b2, w3, b3
+  static constexpr int UBYTES = MODE == AP_BF16 ? 2 : 4;      // user rows: bf16 (AP_BF16) or permuted fp32 (AP_BF16X2)
+  __host__ __device__ static constexpr int tail(int nkb) { return users(nkb) + UT * nkb * 64 * UBYTES; }   // b2, w3, b3
   __host__ __device__ static constexpr int list_val(int nkb) { return tail(nkb) + 2 * AP_NPAD * 4 + 16; }
   __host__ __device__ static constexpr int list_idx(int nkb) { return list_val(nkb) + UT * AP_KMAX * 4; }
   __host__ __device__ static constexpr int thr(int nkb) { return list_idx(nkb) + UT * AP_KMAX * 4; }
@@ -199,49 +207,127 @@ allpairs_topk_kernel(AllPairsParams p) {
     for (int t = 0; t < NKB * PLANES; ++t) ap_bulk_g2s(sm_w2 + t * AP_TILE, p.Wp + (size_t)t * AP_TILE, AP_TILE, &w_bar);
     const uint32_t ub = (uint32_t)users_here * H1 * 4u, tb = 2 * AP_NPAD * 4 + 16;
     ap_mbar_expect_tx(&u_bar, ub + tb);
-    ap_bulk_g2s(sm_users, p.A + (size_t)u0 * H1, ub, &u_bar);
+    ap_bulk_g2s(sm_ring, p.A + (size_t)u0 * H1, ub, &u_bar);       // raw fp32 rows, re-laid out by the producers below
     ap_bulk_g2s(sm_b2, p.Wp + W2_BYTES, tb, &u_bar);
   }
 
   if (warp < 8) {
     // ===================== producers: A-operand tiles ReLU(a_u + b_i) =====================
-    const int c = tid & 7, il = tid >> 3;                       // 16-byte chunk (8 k values) of item row `il` of the tile
-    const uint32_t soff = (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u + (uint32_t)((c ^ (il & 7)) << 4);
-    float breg[NKB][8], bnext[NKB][8];
-    auto load_items = [&](float (&dst)[NKB][8], int it) {
-      const int item = min(i_begin + it * AP_IT + il, p.nI - 1);
-      const float* src = p.B + (size_t)item * H1 + c * 8;
-#pragma unroll
-      for (int kb = 0; kb < NKB; ++kb) {
-        const float4 lo = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
-        const float4 hi = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
-        dst[kb][0] = lo.x; dst[kb][1] = lo.y; dst[kb][2] = lo.z; dst[kb][3] = lo.w;
-        dst[kb][4] = hi.x; dst[kb][5] = hi.y; dst[kb][6] = hi.z; dst[kb][7] = hi.w;
-      }
-    };
-    if (n_it > 0) load_items(breg, 0);
+    // (0) user rows: raw fp32 (TMA, parked in the ring) -> the layout the inner loop reads without bank conflicts
     ap_mbar_wait(&u_bar, 0);
+    {
+      const float4* raw = reinterpret_cast<const float4*>(sm_ring);
+      if constexpr (MODE == AP_BF16) {                           // bf16 rows: one 16-byte chunk = 8 consecutive k
+        uint4* dst = reinterpret_cast<uint4*>(sm_users);
+        for (int idx = tid; idx < UT * H1 / 8; idx += AP_PRODUCERS) {
+          uint4 q = make_uint4(0u, 0u, 0u, 0u);
+          if (idx / (H1 / 8) < users_here) {
+            const float4 x = raw[2 * idx], y = raw[2 * idx + 1];
+            q = make_uint4(ap_pack(x.x, x.y), ap_pack(x.z, x.w), ap_pack(y.x, y.y), ap_pack(y.z, y.w));
+          }
+          dst[idx] = q;
+        }
+      } else {                                                   // fp32 rows, 16-byte pieces of a k-block stored as [half][chunk]
+        float4* dst = reinterpret_cast<float4*>(sm_users);
+        for (int idx = tid; idx < UT * H1 / 4; idx += AP_PRODUCERS) {
+          const int row = idx / (H1 / 4), pq = idx % (H1 / 4), kb = pq >> 4, cc = (pq & 15) >> 1, half = pq & 1;
+          dst[row * (H1 / 4) + kb * 16 + half * 8 + cc] = row < users_here ? raw[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(AP_PRODUCERS) : "memory");   // the ring is free for operand tiles from here on
     uint32_t cnt = 0;
-    for (int it = 0; it < n_it; ++it) {
-      if (it + 1 < n_it) load_items(bnext, it + 1);             // in flight while this item tile is expanded
-      for (int uq = 0; uq < uq_count; ++uq) {
+    if constexpr (MODE == AP_BF16) {
+      // thread = (16-byte chunk c, item pair ip / ip+16, user half uh): 2 items x 2 users = 4 rows of every tile.  Item rows
+      // live in registers as packed bf16 (prefetched one item tile ahead), user rows come from shared memory as bf16; one
+      // HFMA2.BF16 with ReLU per two elements.  Shared-memory cost per tile: 256 wavefronts of loads + 512 of stores.
+      const int c = tid & 7, ip = (tid >> 3) & 15, uh = tid >> 7;
+      const uint32_t soff = (uint32_t)(ip >> 3) * 1024u + (uint32_t)(ip & 7) * 128u + (uint32_t)((c ^ (ip & 7)) << 4);
+      uint4 bq[2][NKB], bnext[2][NKB];
+      auto load_items = [&](uint4 (&dst)[2][NKB], int it) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const int item = min(i_begin + it * AP_IT + ip + 16 * m, p.nI - 1);
+          const float* src = p.B + (size_t)item * H1 + c * 8;
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
+            const float4 y = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+            dst[m][kb] = make_uint4(ap_pack(x.x, x.y), ap_pack(x.z, x.w), ap_pack(y.x, y.y), ap_pack(y.z, y.w));
+          }
+        }
+      };
+      if (n_it > 0) load_items(bq, 0);
+      const uint4* ua = reinterpret_cast<const uint4*>(sm_users);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) load_items(bnext, it + 1);
+        for (int uq = 0; uq < uq_count; ++uq) {
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint32_t s = cnt % NS, ph = (cnt / NS) & 1u;
+            ap_mbar_wait(&a_empty[s], ph ^ 1u);
+            unsigned char* st = sm_ring + (size_t)s * STAGE;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = 2 * uh + jj;
+              const uint4 av = ua[(size_t)(uq * 4 + j) * (H1 / 8) + kb * 8 + c];
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                uint4 q;
+                q.x = ap_add_relu_bf16x2(av.x, bq[m][kb].x); q.y = ap_add_relu_bf16x2(av.y, bq[m][kb].y);
+                q.z = ap_add_relu_bf16x2(av.z, bq[m][kb].z); q.w = ap_add_relu_bf16x2(av.w, bq[m][kb].w);
+                *reinterpret_cast<uint4*>(st + soff + m * 2048 + j * 4096) = q;
+              }
+            }
+            ap_fence_async();
+            ap_mbar_arrive(&a_full[s]);
+            ++cnt;
+          }
+        }
+        if (it + 1 < n_it) {
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) bq[m][kb] = bnext[m][kb];
+        }
+      }
+    } else {
+      // thread = (chunk c, item il): the 4 users of the quad x 1 item; fp32 sum, hi/lo bf16 split
+      const int c = tid & 7, il = tid >> 3;
+      const uint32_t soff = (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u + (uint32_t)((c ^ (il & 7)) << 4);
+      float breg[NKB][8], bnext[NKB][8];
+      auto load_items = [&](float (&dst)[NKB][8], int it) {
+        const int item = min(i_begin + it * AP_IT + il, p.nI - 1);
+        const float* src = p.B + (size_t)item * H1 + c * 8;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb) {
-          const uint32_t s = cnt % NS, ph = (cnt / NS) & 1u;
-          ap_mbar_wait(&a_empty[s], ph ^ 1u);
-          unsigned char* st = sm_ring + (size_t)s * STAGE;
+          const float4 lo = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
+          const float4 hi = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+          dst[kb][0] = lo.x; dst[kb][1] = lo.y; dst[kb][2] = lo.z; dst[kb][3] = lo.w;
+          dst[kb][4] = hi.x; dst[kb][5] = hi.y; dst[kb][6] = hi.z; dst[kb][7] = hi.w;
+        }
+      };
+      if (n_it > 0) load_items(breg, 0);
+      const float4* ua = reinterpret_cast<const float4*>(sm_users);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) load_items(bnext, it + 1);             // in flight while this item tile is expanded
+        for (int uq = 0; uq < uq_count; ++uq) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                          // the 4 users of the quad: rows 32 j + il
-            const float* a = sm_users + (size_t)(uq * 4 + j) * H1 + kb * 64 + c * 8;
-            const float4 a0 = *reinterpret_cast<const float4*>(a), a1 = *reinterpret_cast<const float4*>(a + 4);
-            const float h[8] = {a0.x + breg[kb][0], a0.y + breg[kb][1], a0.z + breg[kb][2], a0.w + breg[kb][3],
-                                a1.x + breg[kb][4], a1.y + breg[kb][5], a1.z + breg[kb][6], a1.w + breg[kb][7]};
-            uint4 q;
-            q.x = ap_pack_relu(h[0], h[1]); q.y = ap_pack_relu(h[2], h[3]);
-            q.z = ap_pack_relu(h[4], h[5]); q.w = ap_pack_relu(h[6], h[7]);
-            *reinterpret_cast<uint4*>(st + soff + j * 4096) = q;
-            if constexpr (MODE == AP_BF16X2) {                   // lo plane: bf16(relu(h) - hi)
-              const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint32_t s = cnt % NS, ph = (cnt / NS) & 1u;
+            ap_mbar_wait(&a_empty[s], ph ^ 1u);
+            unsigned char* st = sm_ring + (size_t)s * STAGE;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                          // the 4 users of the quad: rows 32 j + il
+              const float4* a = ua + (size_t)(uq * 4 + j) * (H1 / 4) + kb * 16 + c;
+              const float4 a0 = a[0], a1 = a[8];
+              const float h[8] = {a0.x + breg[kb][0], a0.y + breg[kb][1], a0.z + breg[kb][2], a0.w + breg[kb][3],
+                                  a1.x + breg[kb][4], a1.y + breg[kb][5], a1.z + breg[kb][6], a1.w + breg[kb][7]};
+              uint4 q;
+              q.x = ap_pack_relu(h[0], h[1]); q.y = ap_pack_relu(h[2], h[3]);
+              q.z = ap_pack_relu(h[4], h[5]); q.w = ap_pack_relu(h[6], h[7]);
+              *reinterpret_cast<uint4*>(st + soff + j * 4096) = q;
+              const uint32_t qq[4] = {q.x, q.y, q.z, q.w};         // lo plane: bf16(relu(h) - hi)
               uint32_t r[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -251,17 +337,17 @@ allpairs_topk_kernel(AllPairsParams p) {
               }
               *reinterpret_cast<uint4*>(st + AP_TILE + soff + j * 4096) = make_uint4(r[0], r[1], r[2], r[3]);
             }
+            ap_fence_async();
+            ap_mbar_arrive(&a_full[s]);
+            ++cnt;
           }
-          ap_fence_async();
-          ap_mbar_arrive(&a_full[s]);
-          ++cnt;
         }
-      }
-      if (it + 1 < n_it) {
+        if (it + 1 < n_it) {
 #pragma unroll
-        for (int kb = 0; kb < NKB; ++kb)
+          for (int kb = 0; kb < NKB; ++kb)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) breg[kb][e] = bnext[kb][e];
+            for (int e = 0; e < 8; ++e) breg[kb][e] = bnext[kb][e];
+        }
       }
     }
   } else if (warp < 12) {
@@ -282,7 +368,7 @@ allpairs_topk_kernel(AllPairsParams p) {
         const uint32_t acc = t & 1u;
         ap_mbar_wait(&acc_full[acc], (t >> 1) & 1u);
         ap_tc_after();
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int cg = 0; cg < AP_NPAD / 32; ++cg) {
           uint32_t r[32];
@@ -306,13 +392,13 @@ allpairs_topk_kernel(AllPairsParams p) {
           for (int j = 0; j < 32; j += 4) {
             const float4 bb = *reinterpret_cast<const float4*>(sm_b2 + cg * 32 + j);
             const float4 ww = *reinterpret_cast<const float4*>(sm_w3 + cg * 32 + j);
-            s = fmaf(fmaxf(__uint_as_float(r[j]) + bb.x, 0.f), ww.x, s);
-            s = fmaf(fmaxf(__uint_as_float(r[j + 1]) + bb.y, 0.f), ww.y, s);
-            s = fmaf(fmaxf(__uint_as_float(r[j + 2]) + bb.z, 0.f), ww.z, s);
-            s = fmaf(fmaxf(__uint_as_float(r[j + 3]) + bb.w, 0.f), ww.w, s);
+            s0 = fmaf(fmaxf(__uint_as_float(r[j]) + bb.x, 0.f), ww.x, s0);
+            s1 = fmaf(fmaxf(__uint_as_float(r[j + 1]) + bb.y, 0.f), ww.y, s1);
+            s2 = fmaf(fmaxf(__uint_as_float(r[j + 2]) + bb.z, 0.f), ww.z, s2);
+            s3 = fmaf(fmaxf(__uint_as_float(r[j + 3]) + bb.w, 0.f), ww.w, s3);
           }
         }
-        s += b3;
+        const float s = ((s0 + s1) + (s2 + s3)) + b3;
         const int ul = uq * 4 + e, u = u0 + ul;
         const bool valid = ul < users_here && item < i_end;
         if (p.scores != nullptr && valid) p.scores[(long long)u * p.lds + item] = s;
@@ -498,15 +584,24 @@ constexpr int AP_UQ_BF16 = 8, AP_UQ_X2 = 4;
 
 static int ap_users_per_cta(int mode) { return 4 * (mode == AP_BF16 ? AP_UQ_BF16 : AP_UQ_X2); }
 
-// item splits: enough CTAs to fill the device twice over, never fewer than 256 items per split, at most 128 splits
+// item splits: at least one CTA per SM where the items allow it (>= 256 items per split, <= 128 splits), and among the
+// candidates up to four waves the count that leaves the smallest idle tail in the last wave
 static int ap_auto_splits(int64_t nU, int64_t nI, int mode) {
   const int64_t ublocks = (nU + ap_users_per_cta(mode) - 1) / ap_users_per_cta(mode);
-  int64_t s = (2LL * b200rec_num_sms() + ublocks - 1) / ublocks;
-  const int64_t max_by_items = (nI + 255) / 256;
-  if (s > max_by_items) s = max_by_items;
-  if (s > 128) s = 128;
-  if (s < 1) s = 1;
-  return (int)s;
+  const int64_t sms = b200rec_num_sms();
+  int64_t smax = (nI + 255) / 256;
+  if (smax > 128) smax = 128;
+  if (smax < 1) smax = 1;
+  if (ublocks >= 8 * sms) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int64_t s = 1; s <= smax; ++s) {
+    const int64_t ctas = ublocks * s, waves = (ctas + sms - 1) / sms;
+    const double eff = (double)ctas / (double)(waves * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = (int)s; }
+    if (waves > 4) break;
+  }
+  return best;
 }
 
 }  // namespace b200rec

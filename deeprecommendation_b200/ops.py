@@ -547,10 +547,12 @@ _ap_cache = {}
 def allpairs_pack(W2, b2, w3, b3, H1p, mode):
     """MMA-ready copy of the second MLP layer (+ b2, w3, b3) for `allpairs_topk_raw`; cached until a tensor changes."""
     _require_cuda(W2, b2, w3, b3)
-    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (W2, b2, w3, b3) if t is not None) + (H1p, mode, W2.device.index)
+    # keyed on the tensor OBJECTS (weak references), not on addresses: a freed temporary's address is reused by the allocator
+    ts = tuple(t for t in (W2, b2, w3, b3) if t is not None)
+    key = tuple((id(t), t._version) for t in ts) + (H1p, mode)
     hit = _ap_cache.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and all(r() is t for r, t in zip(hit[0], ts)):
+        return hit[1]
     lib = L.lib()
     H2, H1 = W2.shape
     w2p = W2.detach().float()
@@ -567,8 +569,8 @@ def allpairs_pack(W2, b2, w3, b3, H1p, mode):
                 'allpairs_pack')
     if len(_ap_cache) > 32:
         _ap_cache.clear()
-    if not torch.is_grad_enabled() or not any(t is not None and t.requires_grad for t in (W2, b2, w3, b3)):
-        _ap_cache[key] = buf
+    if not torch.is_grad_enabled() or not any(t.requires_grad for t in ts):
+        _ap_cache[key] = (tuple(weakref.ref(t) for t in ts), buf)
     return buf
 
 
