@@ -36,8 +36,9 @@ def _peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return {'hbm_gbs': d['hbm_gbs'], 'src': 'measured (MEASURED_PEAKS.json)'}
-    return {'hbm_gbs': 6650.0, 'src': 'fallback (B200_PROFILING.md)'}
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d.get('bf16_tflops', 1590.0), 'bf16_tflops_sustained': d.get('bf16_tflops_sustained', 1400.0),
+                'src': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'src': 'fallback (B200_PROFILING.md)'}
 
 
 def _traffic(name):
@@ -550,6 +551,86 @@ def cpu_basic(w, repeats=10):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# workload D — BasicNCF all-pairs top-K, BASELINE configs[3] (one slab of users per GPU against the whole catalogue)
+# ----------------------------------------------------------------------------------------------------------------------
+AP_USERS, AP_ITEMS, AP_K = 4736, 100_000, 10          # 148 CTAs x 32 users; configs[3] has 10^6 users x 10^5 items = 211 such slabs
+
+
+def build_allpairs(dev, rank):
+    from deeprecommendation_b200 import synth
+    from deeprecommendation_b200.neural_collaborative_filtering.models import BasicNCF
+    kw = dict(item_dim=F, user_dim=F, item_emb=128, user_emb=128, mlp_dense_layers=[256, 128], dropout_rate=0.2)
+    sd = synth.to_torch(synth.basic_ncf_weights(seed=1, **kw))
+    model = BasicNCF(**kw).to(dev).eval()
+    model.load_state_dict(sd)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    # dense F=2094 profiles like synth.item_profiles (966 Bernoulli(0.01) columns + 1128 U[0,1) columns), generated on the device
+    def profiles(n):
+        x = torch.rand(n, F, device=dev, generator=g)
+        x[:, :966] = (x[:, :966] < 0.01).float()
+        return x
+    items = profiles(AP_ITEMS)
+    users = [((profiles(AP_USERS) - 0.3) * 0.1) for _ in range(2)]          # two rotating slabs (40 MB each)
+    users_host = [u.cpu().pin_memory() for u in users]
+    return dict(model=model, sd=sd, items=items, users=users, users_host=users_host)
+
+
+def run_allpairs(w, steps, warmup, dist, dev, peaks, precision='fp32'):
+    from deeprecommendation_b200 import ops
+    model, items, users = w['model'], w['items'], w['users']
+
+    def step(i):
+        return model.recommend(users[i % 2], items, k=AP_K, precision=precision)
+
+    ms, launches = timed_steps(step, steps, warmup, dist, dev)
+
+    def step_e2e(i):
+        xu = w['users_host'][i % 2].to(dev, non_blocking=True)
+        val, idx = model.recommend(xu, items, k=AP_K, precision=precision)
+        return val.cpu(), idx.cpu()
+
+    for i in range(2):
+        step_e2e(i)
+    _barrier(dist)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
+    ops_ms = op_breakdown(step, min(steps, 3), 0)
+    ap = [(k, v) for k, v in ops_ms.items() if k[0] == 'allpairs']
+    kms = ap[0][1][0] if ap else 0.0
+    pairs = AP_USERS * AP_ITEMS
+    flop = pairs * (2.0 * 256 * 128 + 2 * 128)                     # 65,792 per pair in all-pairs mode
+    issued = flop * (3 if precision == 'fp32' else 1)
+    peak = peaks.get('bf16_tflops', 1590.0)
+    ach = flop / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+    roof = {'bound': 'tensor', 'kernel': f'allpairs_topk_kernel (K5, tcgen05 kind::f16, {"bf16 hi/lo split: 3 MMAs per k-step" if precision == "fp32" else "bf16"})',
+            'achieved': round(ach, 1), 'peak': peak, 'unit': 'TFLOP/s', 'frac': round(ach / peak, 4),
+            'issued_tflops': round(issued / (kms * 1e-3) / 1e12, 1) if kms > 0 else 0.0,
+            'issued_frac': round(issued / (kms * 1e-3) / 1e12 / peak, 4) if kms > 0 else 0.0,
+            'traffic': _traffic('allpairs'), 'peak_source': peaks['src'] + ' bf16_tflops (burst: kernel timed alone)', 'kernel_ms': round(kms, 4),
+            'algorithmic_flops': int(flop),
+            'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=AP_USERS * F * 4, d2h=AP_USERS * AP_K * 12, roofline=roof, pairs=pairs)
+
+
+def cpu_allpairs(w, n_users=16, n_items=2000):
+    """reference forward on every pair of a sub-grid (oracle port), host cores"""
+    from oracle import restatement as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    xu, xi = w['users_host'][0][:n_users].clone(), w['items'][:n_items].cpu()
+    with torch.no_grad():
+        R.basic_ncf_all_pairs(w['sd'], xu[:2], xi)
+        t0 = time.perf_counter()
+        sc = R.basic_ncf_all_pairs(w['sd'], xu, xi)
+        R.topk_stable(sc, AP_K)
+        dt = time.perf_counter() - t0
+    return n_users * n_items / dt, torch.get_num_threads(), \
+        f'{n_users} users x {n_items} items sub-grid of the same inputs (reference forward per pair + stable top-{AP_K}), oracle/restatement.py'
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def reference_arm(args):
     """--impl reference: the reference's own CPU algorithm (the reference is pure Python/PyTorch and absent on the GPU box,
     so the oracle port — the same torch op sequence — stands in), all host threads, bounded samples of the same configs."""
@@ -603,7 +684,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic'])
+    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs'])
     ap.add_argument('--graph-scale', type=float, default=1.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
@@ -700,6 +781,36 @@ def main():
                 result = entry
             else:
                 also.append(entry)
+        if args.workload in ('all', 'allpairs'):
+            w = build_allpairs(dev, rank)
+            entry = None
+            for precision in ('fp32', 'bf16'):
+                r = run_allpairs(w, max(3, args.steps // 4), 3, dist, dev, peaks, precision)
+                n_steps = max(3, args.steps // 4)
+                e = {'metric': f'scored user-item pairs/sec (BasicNCF all-pairs + top-{AP_K})', 'value': r['pairs'] * n_steps * world / (r['ms'] * 1e-3),
+                     'unit': 'pairs/s', 'ms_per_step': r['ms'] / n_steps, 'steps': n_steps, 'scaling': 'weak',
+                     'parallelism': f'dp{world}: users sharded, catalogue replicated, no collective', 'dtype': 'f32' if precision == 'fp32' else 'bf16',
+                     'config': {'workload': f'configs[3] slab: BasicNCF(2094, 2094, 128, 128, [256,128]).recommend — {AP_USERS} users x {AP_ITEMS} items '
+                                            f'per GPU and step (configs[3] = 211 such slabs per 10^6 users), F=2094 profiles in, top-{AP_K} per user out; '
+                                            'embeddings + layer-1 halves by K1a, the rest fused in K5',
+                                'precision': 'fp32 tolerance (bf16 hi/lo split operands, rel <= 1e-5)' if precision == 'fp32' else 'bf16 operands (rel <= 1e-2)',
+                                'l2': 'item tables 100k x 1 KB = 102 MB streamed once per 32 users; profiles 838 MB > L2'},
+                     'roofline': r['roofline'],
+                     'e2e': {'value': r['pairs'] * n_steps * world / (r['e2e_ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
+                     'gpu_launches': r['launches']}
+                if entry is None:
+                    entry = e
+                else:
+                    entry['bf16_mode'] = {k: e[k] for k in ('value', 'ms_per_step', 'roofline', 'e2e', 'dtype')}
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                v, cores, sample = cpu_allpairs(w)
+                entry['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+            if result is None:
+                result = entry
+            else:
+                also.append(entry)
+            del w
+            torch.cuda.empty_cache()
     if args.workload == 'all' and world == 1 and not args.skip_hbm_regime:
         try:
             also.append(run_k3_hbm_regime(dev, peaks))

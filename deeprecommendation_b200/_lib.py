@@ -53,10 +53,10 @@ SIGNATURES = {
     'b200rec_mlp_tower': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_i64, C.POINTER(MlpDesc), c_vp, c_i64, c_vp]),
     'b200rec_rowdot': (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp]),
     'b200rec_allpairs_packed_bytes': (c_sz, [c_int, c_int]),
-    'b200rec_allpairs_pack': (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    'b200rec_allpairs_pack': (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     'b200rec_allpairs_splits': (c_int, [c_i64, c_i64, c_int]),
     'b200rec_allpairs_workspace': (c_sz, [c_i64, c_int, c_int]),
-    'b200rec_allpairs_topk': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'b200rec_allpairs_topk': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'b200rec_topk_rows': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),
     'b200rec_attention_pool_workspace': (c_sz, [c_i64, c_i64, c_int, c_int]),
     'b200rec_attention_pool': (c_int, [C.POINTER(AttentionDesc), c_vp]),

@@ -110,7 +110,7 @@ struct AllPairsParams {
   const float* A;             // (nU, H1) contiguous
   const float* B;             // (nI, H1) contiguous
   int nU, nI, H1;             // H1 in {64, 128, 192, 256}
-  const unsigned char* Wp;    // packed by allpairs_pack_kernel: [kb][plane][128 x 128 B] tiles, then b2[128], w3[128], b3
+  const unsigned char* Wp;    // packed by allpairs_pack_kernel: [kb][plane][128 x 128 B] tiles
   int k;                      // 0 = no top-k
   int n_splits, items_per_split;
   float* part_val;            // (nU, n_splits, k)
@@ -119,6 +119,10 @@ struct AllPairsParams {
   long long lds;
   const int* seen_ptr;        // optional CSR (nU+1) / sorted item ids: pairs the user has already interacted with are skipped
   const int* seen_idx;
+  // epilogue constants travel in the kernel parameter block (constant bank): FADD / FFMA read them as c[0][..] operands.
+  // As shared-memory broadcasts they cost one wavefront per quarter-warp and instruction — 1,024 wavefronts per tile, more
+  // than the MMA's own operand fetch (profiles/r01/ncu_allpairs_v2.txt).
+  float b2[AP_NPAD], w3[AP_NPAD], b3;
 };
 
 // shared-memory layout (byte offsets from the 1024-aligned base); NKB = H1 / 64
@@ -132,8 +136,7 @@ struct ApLayout {
   __host__ __device__ static constexpr int ring(int nkb) { return nkb * PLANES * AP_TILE; }
   __host__ __device__ static constexpr int users(int nkb) { return ring(nkb) + NS * STAGE; }
   static constexpr int UBYTES = MODE == AP_BF16 ? 2 : 4;      // user rows: bf16 (AP_BF16) or permuted fp32 (AP_BF16X2)
-  __host__ __device__ static constexpr int tail(int nkb) { return users(nkb) + UT * nkb * 64 * UBYTES; }   // b2, w3, b3
-  __host__ __device__ static constexpr int list_val(int nkb) { return tail(nkb) + 2 * AP_NPAD * 4 + 16; }
+  __host__ __device__ static constexpr int list_val(int nkb) { return users(nkb) + UT * nkb * 64 * UBYTES; }
   __host__ __device__ static constexpr int list_idx(int nkb) { return list_val(nkb) + UT * AP_KMAX * 4; }
   __host__ __device__ static constexpr int thr(int nkb) { return list_idx(nkb) + UT * AP_KMAX * 4; }
   __host__ __device__ static constexpr int total(int nkb) { return thr(nkb) + UT * 4 + 1024; }           // + alignment slack
@@ -166,8 +169,6 @@ allpairs_topk_kernel(AllPairsParams p) {
   unsigned char* sm_w2 = sm + LY::w2(NKB);
   unsigned char* sm_ring = sm + LY::ring(NKB);
   float* sm_users = reinterpret_cast<float*>(sm + LY::users(NKB));
-  float* sm_b2 = reinterpret_cast<float*>(sm + LY::tail(NKB));
-  float* sm_w3 = sm_b2 + AP_NPAD;
   float* sm_lv = reinterpret_cast<float*>(sm + LY::list_val(NKB));
   int* sm_li = reinterpret_cast<int*>(sm + LY::list_idx(NKB));
   float* sm_thr = reinterpret_cast<float*>(sm + LY::thr(NKB));
@@ -205,10 +206,9 @@ allpairs_topk_kernel(AllPairsParams p) {
     ap_mbar_expect_tx(&w_bar, W2_BYTES);
 #pragma unroll
     for (int t = 0; t < NKB * PLANES; ++t) ap_bulk_g2s(sm_w2 + t * AP_TILE, p.Wp + (size_t)t * AP_TILE, AP_TILE, &w_bar);
-    const uint32_t ub = (uint32_t)users_here * H1 * 4u, tb = 2 * AP_NPAD * 4 + 16;
-    ap_mbar_expect_tx(&u_bar, ub + tb);
+    const uint32_t ub = (uint32_t)users_here * H1 * 4u;
+    ap_mbar_expect_tx(&u_bar, ub);
     ap_bulk_g2s(sm_ring, p.A + (size_t)u0 * H1, ub, &u_bar);       // raw fp32 rows, re-laid out by the producers below
-    ap_bulk_g2s(sm_b2, p.Wp + W2_BYTES, tb, &u_bar);
   }
 
   if (warp < 8) {
@@ -359,8 +359,6 @@ allpairs_topk_kernel(AllPairsParams p) {
       if (lane == 0) sm_thr[ul] = -INFINITY;
     }
     __syncwarp();
-    ap_mbar_wait(&u_bar, 0);
-    const float b3 = sm_w3[AP_NPAD];
     uint32_t t = 0;
     for (int it = 0; it < n_it; ++it) {
       const int item = i_begin + it * AP_IT + lane;
@@ -390,15 +388,14 @@ allpairs_topk_kernel(AllPairsParams p) {
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(sm_b2 + cg * 32 + j);
-            const float4 ww = *reinterpret_cast<const float4*>(sm_w3 + cg * 32 + j);
-            s0 = fmaf(fmaxf(__uint_as_float(r[j]) + bb.x, 0.f), ww.x, s0);
-            s1 = fmaf(fmaxf(__uint_as_float(r[j + 1]) + bb.y, 0.f), ww.y, s1);
-            s2 = fmaf(fmaxf(__uint_as_float(r[j + 2]) + bb.z, 0.f), ww.z, s2);
-            s3 = fmaf(fmaxf(__uint_as_float(r[j + 3]) + bb.w, 0.f), ww.w, s3);
+            const int n = cg * 32 + j;
+            s0 = fmaf(fmaxf(__uint_as_float(r[j]) + p.b2[n], 0.f), p.w3[n], s0);
+            s1 = fmaf(fmaxf(__uint_as_float(r[j + 1]) + p.b2[n + 1], 0.f), p.w3[n + 1], s1);
+            s2 = fmaf(fmaxf(__uint_as_float(r[j + 2]) + p.b2[n + 2], 0.f), p.w3[n + 2], s2);
+            s3 = fmaf(fmaxf(__uint_as_float(r[j + 3]) + p.b2[n + 3], 0.f), p.w3[n + 3], s3);
           }
         }
-        const float s = ((s0 + s1) + (s2 + s3)) + b3;
+        const float s = ((s0 + s1) + (s2 + s3)) + p.b3;
         const int ul = uq * 4 + e, u = u0 + ul;
         const bool valid = ul < users_here && item < i_end;
         if (p.scores != nullptr && valid) p.scores[(long long)u * p.lds + item] = s;
@@ -475,10 +472,9 @@ allpairs_topk_kernel(AllPairsParams p) {
   }
 }
 
-// W2 (H2, H1) fp32 -> [kb][plane] swizzled bf16 tiles (rows >= H2 zero), then b2[128] | w3[128] | b3 | pad
+// W2 (H2, H1) fp32 -> [kb][plane] swizzled bf16 tiles (rows >= H2 zero)
 template <int MODE>
-__global__ void allpairs_pack_kernel(const float* __restrict__ W2, long long ldw, int H2, int H1, const float* __restrict__ b2,
-                                     const float* __restrict__ w3, const float* __restrict__ b3, unsigned char* __restrict__ out) {
+__global__ void allpairs_pack_kernel(const float* __restrict__ W2, long long ldw, int H2, int H1, unsigned char* __restrict__ out) {
   constexpr int PLANES = MODE == AP_BF16 ? 1 : 2;
   const int nkb = H1 / 64;
   const int total = nkb * 128 * 8;                               // (k-block, row, 16-byte chunk)
@@ -501,13 +497,6 @@ __global__ void allpairs_pack_kernel(const float* __restrict__ W2, long long ldw
         lo[e] = ap_pack(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
       *reinterpret_cast<uint4*>(base + AP_TILE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-  }
-  if (blockIdx.x == 0 && threadIdx.x < AP_NPAD) {
-    float* tail = reinterpret_cast<float*>(out + (size_t)nkb * PLANES * AP_TILE);
-    const int n = threadIdx.x;
-    tail[n] = n < H2 ? __ldg(b2 + n) : 0.f;
-    tail[AP_NPAD + n] = n < H2 ? __ldg(w3 + n) : 0.f;
-    if (n < 4) tail[2 * AP_NPAD + n] = (n == 0 && b3) ? __ldg(b3) : 0.f;
   }
 }
 
@@ -553,7 +542,7 @@ allpairs_merge_kernel(const float* __restrict__ part_val, const int* __restrict_
 }
 
 static size_t ap_packed_bytes(int H1, int mode) {
-  return (size_t)(H1 / 64) * (mode == AP_BF16 ? 1 : 2) * AP_TILE + 2 * AP_NPAD * 4 + 16;
+  return (size_t)(H1 / 64) * (mode == AP_BF16 ? 1 : 2) * AP_TILE;
 }
 
 template <int MODE, int UQ, int NKB>
@@ -613,9 +602,9 @@ extern "C" size_t b200rec_allpairs_packed_bytes(int H1, int mode) {
   return ap_packed_bytes(H1, mode);
 }
 
-extern "C" int b200rec_allpairs_pack(const float* W2, int64_t ldw2, int H2, int H1, const float* b2, const float* w3, const float* b3,
-                                     int mode, void* packed, size_t packed_bytes, b200rec_stream_t stream) {
-  if (!W2 || !b2 || !w3 || !packed || H2 <= 0 || H2 > AP_NPAD || H1 <= 0 || H1 > 256 || (H1 % 64) || ldw2 < H1)
+extern "C" int b200rec_allpairs_pack(const float* W2, int64_t ldw2, int H2, int H1, int mode, void* packed, size_t packed_bytes,
+                                     b200rec_stream_t stream) {
+  if (!W2 || !packed || H2 <= 0 || H2 > AP_NPAD || H1 <= 0 || H1 > 256 || (H1 % 64) || ldw2 < H1)
     return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_pack: need H2 <= 128, H1 in {64,128,192,256} (zero-pad the inputs), ldw2 >= H1");
   if (mode != AP_BF16 && mode != AP_BF16X2) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_pack: bad mode");
   if (packed_bytes < ap_packed_bytes(H1, mode) || ((uintptr_t)packed % 128))
@@ -623,8 +612,8 @@ extern "C" int b200rec_allpairs_pack(const float* W2, int64_t ldw2, int H2, int 
   const int total = (H1 / 64) * 128 * 8;
   const int grid = (total + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == AP_BF16) allpairs_pack_kernel<AP_BF16><<<grid, 256, 0, st>>>(W2, ldw2, H2, H1, b2, w3, b3, (unsigned char*)packed);
-  else allpairs_pack_kernel<AP_BF16X2><<<grid, 256, 0, st>>>(W2, ldw2, H2, H1, b2, w3, b3, (unsigned char*)packed);
+  if (mode == AP_BF16) allpairs_pack_kernel<AP_BF16><<<grid, 256, 0, st>>>(W2, ldw2, H2, H1, (unsigned char*)packed);
+  else allpairs_pack_kernel<AP_BF16X2><<<grid, 256, 0, st>>>(W2, ldw2, H2, H1, (unsigned char*)packed);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -639,11 +628,12 @@ extern "C" size_t b200rec_allpairs_workspace(int64_t nU, int k, int n_splits) {
   return (size_t)nU * n_splits * k * (sizeof(float) + sizeof(int)) + 256;
 }
 
-extern "C" int b200rec_allpairs_topk(const float* A, const float* B, int64_t nU, int64_t nI, int H1, const void* packed, int mode, int k,
-                                     int n_splits, const int32_t* seen_ptr, const int32_t* seen_idx, float* scores, int64_t lds,
+extern "C" int b200rec_allpairs_topk(const float* A, const float* B, int64_t nU, int64_t nI, int H1, const void* packed,
+                                     const float* epilogue_host, int H2, int mode, int k, int n_splits, const int32_t* seen_ptr, const int32_t* seen_idx, float* scores, int64_t lds,
                                      float* top_val, int64_t* top_idx, void* workspace, size_t workspace_bytes,
                                      b200rec_stream_t stream) {
-  if (nU < 0 || nI < 0 || !packed || (nU > 0 && nI > 0 && (!A || !B))) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_topk: null operand");
+  if (nU < 0 || nI < 0 || !packed || !epilogue_host || (nU > 0 && nI > 0 && (!A || !B))) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_topk: null operand");
+  if (H2 <= 0 || H2 > AP_NPAD) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "allpairs_topk: H2 must be in 1..128");
   if (H1 <= 0 || H1 > 256 || (H1 % 64)) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "allpairs_topk: H1 must be 64, 128, 192 or 256 (zero-pad)");
   if (mode != AP_BF16 && mode != AP_BF16X2) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_topk: bad mode");
   if (k < 0 || k > AP_KMAX) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_topk: need 0 <= k <= 64");
@@ -667,6 +657,11 @@ extern "C" int b200rec_allpairs_topk(const float* A, const float* B, int64_t nU,
   p.part_val = reinterpret_cast<float*>(workspace);
   p.part_idx = k > 0 ? reinterpret_cast<int*>(p.part_val + (size_t)nU * n_splits * k) : nullptr;
   p.scores = scores; p.lds = lds; p.seen_ptr = seen_ptr; p.seen_idx = seen_idx;
+  for (int n = 0; n < AP_NPAD; ++n) {            // host block: b2[H2] | w3[H2] | b3; padded columns contribute ReLU(0 + 0) * 0
+    p.b2[n] = n < H2 ? epilogue_host[n] : 0.f;
+    p.w3[n] = n < H2 ? epilogue_host[H2 + n] : 0.f;
+  }
+  p.b3 = epilogue_host[2 * H2];
   const int ut = ap_users_per_cta(mode);
   dim3 grid((unsigned)((nU + ut - 1) / ut), (unsigned)n_splits);
   if (nI > 0) {

@@ -257,6 +257,23 @@ class GraphIndex:
             L.check(lib.b200rec_dinv(_ptr(deg), self.num_nodes, _ptr(dinv), st), 'dinv')
         return skip, dinv
 
+    def seen_items(self, user_nodes: torch.Tensor):
+        """CSR (ptr int32 (n+1), idx int32 sorted ascending) of the item nodes each given user node is connected to — the
+        `ignore_seen` set of the serving path (src/webapp/backend.py:85).  Rows of the neighbour index are ordered by
+        interaction position, so the sources of a user row are sorted here once per call."""
+        users = user_nodes.contiguous().long()
+        dev = users.device
+        start, end = self.row_ptr[users].long(), self.row_ptr[users + 1].long()
+        cnt = end - start
+        ptr = torch.zeros(users.numel() + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(cnt, 0)
+        total = int(ptr[-1])
+        rows = torch.repeat_interleave(torch.arange(users.numel(), device=dev), cnt)
+        within = torch.arange(total, device=dev) - ptr[:-1][rows]
+        items = self.col[start[rows] + within].long()
+        key = torch.sort(rows * self.num_nodes + items).values
+        return ptr.int(), (key % self.num_nodes).int()
+
 
 def get_index(graph) -> GraphIndex:
     """GraphIndex of a graph object (ours or the reference's PyG `Data`), built once and cached on it."""

@@ -130,3 +130,37 @@ class AttentionNCF(NCF):
             user_emb = user_emb[:, :U]
         out = run_mlp(self.MLP, Ec, user_emb, training=self.training)                   # :219-222
         return (out, att.detach()) if return_attention_weights else out
+
+    def recommend_for_user(self, item_profiles, rated_positions, rated_ratings, k=10, ignore_seen=True, explain_factor=1.5,
+                           explain_constant=0.025):
+        """The reference's serving call (src/webapp/backend.py:78-121 `recommend_for_user`) on the device: every item of the
+        catalogue is a candidate for ONE user described by the items they rated.
+
+        item_profiles (nI, F) CUDA fp32; rated_positions (R,) int64 rows of `item_profiles` the user rated (any order, unique);
+        rated_ratings (R,) raw ratings.  Returns a dict: `items` (k,) catalogue rows sorted by score, `scores` (k,), and per
+        recommended item the rated items whose attention weight exceeds `explain_factor / R + explain_constant` (:105-110):
+        `because` (list of k int64 tensors of catalogue rows) and `attention` (their weights)."""
+        if self.training:
+            raise RuntimeError('recommend_for_user() is an inference call: model.eval() first')
+        dev = item_profiles.device
+        rated_positions = rated_positions.to(dev).long()
+        order = torch.argsort(rated_positions)                                          # np.sort(np.unique(...)) (:89)
+        rated_sorted = rated_positions[order]
+        ratings = rated_ratings.to(dev).double()[order]
+        centred = (ratings - (ratings.mean() + 2.5) / 2).float()                        # (:93)
+        if ignore_seen:                                                                 # item_features.drop(...) (:85)
+            keep = torch.ones(item_profiles.shape[0], dtype=torch.bool, device=dev)
+            keep[rated_sorted] = False
+            cand_rows = keep.nonzero().view(-1)
+        else:
+            cand_rows = torch.arange(item_profiles.shape[0], device=dev)
+        with torch.no_grad():
+            um = centred.view(1, -1).expand(cand_rows.numel(), -1).contiguous()        # the same row B times (:93)
+            y, att = self.forward(item_profiles[cand_rows], item_profiles[rated_sorted], um, return_attention_weights=True)
+            val, top = ops.topk_rows(y.view(1, -1), min(k, cand_rows.numel()))
+        top = top.view(-1)
+        thr = explain_factor * (1.0 / max(rated_sorted.numel(), 1)) + explain_constant  # (:102)
+        att_top = att[top]
+        mask = att_top > thr
+        return {'items': cand_rows[top], 'scores': val.view(-1),
+                'because': [rated_sorted[m] for m in mask], 'attention': [a[m] for a, m in zip(att_top, mask)]}

@@ -7,7 +7,7 @@ from torch import nn
 
 from ... import ops
 from ...graph import get_index
-from ..util import build_MLP_layers, run_mlp
+from ..util import build_MLP_layers, mlp_parameters, run_mlp
 from .base import GNN_NCF, _named_like
 
 
@@ -194,6 +194,33 @@ class GraphNCF(GNN_NCF):
             x = ops.propagate(t, index, index.w, index.w_bwd, dinv, skip)
             hs.append(x)
         return torch.cat(hs, dim=1) if self.concat else torch.mean(torch.stack(hs, dim=0), dim=0)     # :348-351
+
+    def recommend(self, graph, k=10, user_nodes=None, precision='fp32', ignore_seen=True, return_scores=False):
+        """Top-k item NODE ids for the given user nodes (default: every user) over ALL items — the whole-catalogue form of
+        `forward` (gnn_ncf.py:298-367: propagate, gather the pair's rows, MLP item-first or dot product), with the selection of
+        the reference's serving loop (src/webapp/backend.py:85,113-121).  One propagation (K1a + K3), then the fused all-pairs
+        kernel K5 over (users x items); `ignore_seen` leaves out the items a user is connected to in the graph."""
+        if self.training:
+            raise RuntimeError('recommend() is an inference call: model.eval() first')
+        index = get_index(graph)
+        nI = graph.item_features.shape[0]
+        with torch.no_grad():
+            comb = self._encode(graph, index, None, index.dinv, False)
+            users = torch.arange(nI, index.num_nodes, device=comb.device) if user_nodes is None else user_nodes.long()
+            user_emb, item_emb = comb[users].contiguous(), comb[:nI]
+            seen = index.seen_items(users) if ignore_seen else None
+            if self.MLP is None:                                      # dot product (:365): one GEMM + row-wise top-k
+                scores = ops.linear_raw(user_emb, item_emb, None)
+                if seen is not None:
+                    ptr, idx = seen
+                    rows = torch.repeat_interleave(torch.arange(users.numel(), device=comb.device), (ptr[1:] - ptr[:-1]).long())
+                    scores[rows, idx.long()] = float('nan')           # never selected by the top-k kernel
+                val, idx = ops.topk_rows(scores, k)
+                return (val, idx, scores) if return_scores else (val, idx)
+            weights, biases, _ = mlp_parameters(self.MLP)
+            val, idx, scores = ops.mlp_allpairs_topk(user_emb, item_emb, weights, biases, k, rows_first=False, precision=precision,
+                                                     seen=seen, return_scores=return_scores)
+        return (val, idx, scores) if return_scores else (val, idx)
 
     def forward(self, graph, userIds, itemIds, device=None, mask_targets=True):
         pg = getattr(graph, '_b200rec_partition', None)

@@ -544,8 +544,17 @@ def topk_rows(scores, k):
 _ap_cache = {}
 
 
+class AllPairsWeights:
+    """second MLP layer in MMA-ready form (device) + the epilogue constants b2 | w3 | b3 as a HOST array (they travel in
+    the kernel's parameter block)"""
+
+    def __init__(self, buf, epi, H2):
+        self.buf, self.epi, self.H2 = buf, epi, H2
+
+
 def allpairs_pack(W2, b2, w3, b3, H1p, mode):
-    """MMA-ready copy of the second MLP layer (+ b2, w3, b3) for `allpairs_topk_raw`; cached until a tensor changes."""
+    """`AllPairsWeights` for `allpairs_topk_raw`; cached until a tensor changes (one device->host read of 2*H2+1 floats
+    per weight version)."""
     _require_cuda(W2, b2, w3, b3)
     # keyed on the tensor OBJECTS (weak references), not on addresses: a freed temporary's address is reused by the allocator
     ts = tuple(t for t in (W2, b2, w3, b3) if t is not None)
@@ -558,15 +567,15 @@ def allpairs_pack(W2, b2, w3, b3, H1p, mode):
     w2p = W2.detach().float()
     if H1 != H1p or not w2p.is_contiguous():                 # zero-pad K to a multiple of 64
         w2p = torch.nn.functional.pad(w2p, (0, H1p - H1)).contiguous()
-    b2c, w3c = b2.detach().float().contiguous(), w3.detach().float().contiguous().view(-1)
-    b3c = b3.detach().float().contiguous().view(-1) if b3 is not None else None
+    b3c = b3.detach().float().view(-1)[:1] if b3 is not None else torch.zeros(1, device=W2.device)
+    epi = torch.cat((b2.detach().float().view(-1), w3.detach().float().view(-1), b3c)).cpu().contiguous()
     nbytes = lib.b200rec_allpairs_packed_bytes(H1p, mode)
     if nbytes == 0:
         raise NotImplementedError(f'all-pairs kernel: first hidden width {H1} > 256')
     buf = torch.empty(nbytes, dtype=torch.uint8, device=W2.device)
     with torch.cuda.device(W2.device):
-        L.check(lib.b200rec_allpairs_pack(_ptr(w2p), H1p, H2, H1p, _ptr(b2c), _ptr(w3c), _ptr(b3c), mode, _ptr(buf), nbytes, _stream()),
-                'allpairs_pack')
+        L.check(lib.b200rec_allpairs_pack(_ptr(w2p), H1p, H2, H1p, mode, _ptr(buf), nbytes, _stream()), 'allpairs_pack')
+    buf = AllPairsWeights(buf, epi, H2)
     if len(_ap_cache) > 32:
         _ap_cache.clear()
     if not torch.is_grad_enabled() or not any(t.requires_grad for t in ts):
@@ -577,7 +586,7 @@ def allpairs_pack(W2, b2, w3, b3, H1p, mode):
 def allpairs_topk_raw(A, B, packed, mode, k, *, return_scores=False, seen=None, n_splits=0):
     """A (nU, H1p), B (nI, H1p) contiguous fp32 with H1p % 64 == 0.  Returns (top_val (nU,k), top_idx (nU,k) int64, scores|None)
     — b200rec_allpairs_topk.  `seen` = (ptr int32 (nU+1), idx int32 sorted per user): pairs never recommended."""
-    _require_cuda(A, B, packed)
+    _require_cuda(A, B, packed.buf)
     if A.dtype != torch.float32 or B.dtype != torch.float32 or not A.is_contiguous() or not B.is_contiguous():
         raise ValueError('allpairs: A and B must be contiguous fp32')
     nU, H1p = A.shape
@@ -599,7 +608,7 @@ def allpairs_topk_raw(A, B, packed, mode, k, *, return_scores=False, seen=None, 
         if sp.numel() != nU + 1:
             raise ValueError('allpairs: seen_ptr must have nU + 1 entries')
     with torch.cuda.device(dev), _timed('allpairs', (nU, nI, H1p, k, mode)):
-        L.check(lib.b200rec_allpairs_topk(_ptr(A), _ptr(B), nU, nI, H1p, _ptr(packed), mode, k, n_splits, _ptr(sp), _ptr(si),
+        L.check(lib.b200rec_allpairs_topk(_ptr(A), _ptr(B), nU, nI, H1p, _ptr(packed.buf), _ptr(packed.epi), packed.H2, mode, k, n_splits, _ptr(sp), _ptr(si),
                                           _ptr(scores), nI, _ptr(val), _ptr(idx), _ptr(ws), wsb, _stream()), 'allpairs_topk')
     return val, idx, scores
 

@@ -88,7 +88,8 @@ int b200rec_topk_rows(const float* scores, int64_t rows, int64_t cols, int64_t l
  * src/webapp/backend.py:113-121 — BASELINE configs[3].  The first Linear of the MLP is split by the caller:
  *   A = user_emb · W1[:, :Eu]^T + b1  (nU, H1),   B = item_emb · W1[:, Eu:]^T  (nI, H1)      (K1a; contiguous rows, H1 % 64 == 0,
  *   H1 <= 256 — zero-pad the columns);  score(u, i) = w3 · ReLU(W2 · ReLU(A[u] + B[i]) + b2) + b3,  W2 (H2 <= 128, H1).
- * b200rec_allpairs_pack converts W2 once into MMA-ready bf16 tiles (+ b2, w3, b3).  mode B200REC_AP_BF16: bf16 operands
+ * b200rec_allpairs_pack converts W2 once into MMA-ready bf16 tiles; `epilogue_host` is a HOST array b2[H2] | w3[H2] | b3
+ * (2*H2+1 floats) that travels in the kernel's parameter block (constant bank).  mode B200REC_AP_BF16: bf16 operands
  * (rel <= 1e-2); B200REC_AP_BF16X2: operands split into bf16 hi + lo, 3 MMAs per k-step (fp32 tolerance, rel <= 1e-5).
  * Outputs: top_val (nU, k) fp32 / top_idx (nU, k) int64 item positions, descending, ties towards the lower item, fewer than k
  * valid items padded with (-inf, -1), NaN never selected; optional `scores` (nU, nI) ld = lds (NULL = never materialised);
@@ -96,12 +97,12 @@ int b200rec_topk_rows(const float* scores, int64_t rows, int64_t cols, int64_t l
  * (`ignore_seen`, backend.py:85).  n_splits <= 0 = automatic (b200rec_allpairs_splits). */
 enum { B200REC_AP_BF16 = 0, B200REC_AP_BF16X2 = 1 };
 size_t b200rec_allpairs_packed_bytes(int H1, int mode);
-int b200rec_allpairs_pack(const float* W2, int64_t ldw2, int H2, int H1, const float* b2, const float* w3, const float* b3, int mode,
-                          void* packed, size_t packed_bytes, b200rec_stream_t stream);
+int b200rec_allpairs_pack(const float* W2, int64_t ldw2, int H2, int H1, int mode, void* packed, size_t packed_bytes,
+                          b200rec_stream_t stream);
 int b200rec_allpairs_splits(int64_t nU, int64_t nI, int mode);
 size_t b200rec_allpairs_workspace(int64_t nU, int k, int n_splits);
-int b200rec_allpairs_topk(const float* A, const float* B, int64_t nU, int64_t nI, int H1, const void* packed, int mode, int k,
-                          int n_splits, const int32_t* seen_ptr, const int32_t* seen_idx, float* scores, int64_t lds, float* top_val,
+int b200rec_allpairs_topk(const float* A, const float* B, int64_t nU, int64_t nI, int H1, const void* packed,
+                          const float* epilogue_host, int H2, int mode, int k, int n_splits, const int32_t* seen_ptr, const int32_t* seen_idx, float* scores, int64_t lds, float* top_val,
                           int64_t* top_idx, void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
 
 /* ---- K2  AttentionNCF ragged attention pooling ------------------------------------------------------------------

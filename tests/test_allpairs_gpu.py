@@ -114,3 +114,69 @@ def test_recommend_matches_forward_on_pairs(dev):
     with torch.no_grad():
         fwd = m(xu.repeat_interleave(90, 0), xi.repeat(40, 1)).view(40, 90)
     assert maxnorm_rel(scores, fwd) < 1e-5
+
+
+def test_graph_ncf_recommend_vs_oracle(dev):
+    """GraphNCF.recommend == oracle forward on every (user, item) pair + stable top-k, connected items left out"""
+    from deeprecommendation_b200 import synth
+    from deeprecommendation_b200.graph import IdTable, create_graph
+    from deeprecommendation_b200.neural_collaborative_filtering.models import GraphNCF
+    from oracle import restatement as R
+    users, items, ratings = synth.interactions_zipf(120, 90, 2500, seed=7)
+    nU, nI, F_ = 120, 90, 32
+    kw = dict(item_dim=F_, user_dim=F_, num_gnn_layers=2, hetero=True, node_emb=64, mlp_dense_layers=[128, 64], dropout_rate=0.2)
+    sd = synth.to_torch(synth.graph_ncf_weights(seed=8, **kw))
+    rng = np.random.default_rng(3)
+    fi, fu = rng.standard_normal((nI, F_)).astype(np.float32), rng.standard_normal((nU, F_)).astype(np.float32)
+    g = R.create_graph(users, items, ratings, np.arange(nU), np.arange(nI))
+    gd = {k: (torch.from_numpy(v) if v is not None else None) for k, v in g.items()}
+    gd['item_features'], gd['user_features'] = torch.from_numpy(fi), torch.from_numpy(fu)
+    uu = torch.arange(nI, nI + nU).repeat_interleave(nI)
+    ii = torch.arange(nI).repeat(nU)
+    with torch.no_grad():
+        ref = R.graph_ncf_forward(sd, gd, uu, ii, 2).view(nU, nI)
+    graph = create_graph(torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev), torch.from_numpy(ratings).to(dev),
+                         torch.from_numpy(fi).to(dev), torch.from_numpy(fu).to(dev),
+                         IdTable(torch.arange(nU, device=dev)), IdTable(torch.arange(nI, device=dev)))
+    m = GraphNCF(**kw).to(dev).eval()
+    m.load_state_dict(sd)
+    val, idx, scores = m.recommend(graph, k=5, return_scores=True)
+    assert maxnorm_rel(scores, ref) < 1e-5
+    e = g['user2item_edge_index']
+    seen = [np.unique(e[1][e[0] == nI + u]) for u in range(nU)]
+    sv, si = R.topk_stable(scores.cpu(), 5, seen=seen)
+    assert torch.equal(idx.cpu(), si) and torch.equal(val.cpu(), sv)
+    rv, _ = R.topk_stable(ref, 5, seen=seen)
+    assert float((val.cpu() - rv).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_attention_recommend_for_user_vs_oracle(dev):
+    """AttentionNCF.recommend_for_user reproduces webapp/backend.py:78-121 computed with the oracle forward"""
+    from deeprecommendation_b200 import synth
+    from deeprecommendation_b200.neural_collaborative_filtering.models import AttentionNCF
+    from oracle import restatement as R
+    kw = dict(item_dim=256, item_emb=128, user_emb=128, att_dense=128, mlp_dense_layers=[256, 128], dropout_rate=0.2)
+    sd = synth.to_torch(synth.attention_ncf_weights(seed=4, **kw))
+    m = AttentionNCF(**kw).to(dev).eval()
+    m.load_state_dict(sd)
+    prof = torch.from_numpy(synth.item_profiles(700, seed=5, f_binary=128, f_dense=128))
+    rng = np.random.default_rng(1)
+    rated = rng.choice(700, size=23, replace=False)
+    ratings = rng.integers(1, 11, size=23) * 0.5
+    out = m.recommend_for_user(prof.to(dev), torch.from_numpy(rated), torch.from_numpy(ratings), k=10)
+    # oracle: the reference's own steps
+    rs = np.sort(rated)
+    r_sorted = ratings[np.argsort(rated)]
+    cand = np.setdiff1d(np.arange(700), rs)
+    um = np.repeat((r_sorted - (r_sorted.mean() + 2.5) / 2)[None, :], len(cand), 0).astype(np.float32)
+    with torch.no_grad():
+        y, att = R.attention_ncf_forward(sd, prof[cand], prof[rs], torch.from_numpy(um), return_attention_weights=True)
+    y = y.view(-1)
+    order = np.argsort(-y.numpy(), kind='stable')[:10]
+    assert np.array_equal(out['items'].cpu().numpy(), cand[order])
+    assert maxnorm_rel(out['scores'], y[order]) < 1e-5
+    thr = 1.5 / 23 + 0.025
+    for j, o in enumerate(order):
+        mask = att[o].numpy() > thr
+        assert np.array_equal(out['because'][j].cpu().numpy(), rs[mask])
+        assert np.allclose(out['attention'][j].cpu().numpy(), att[o].numpy()[mask], rtol=1e-4, atol=1e-6)
