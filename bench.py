@@ -151,7 +151,7 @@ def op_breakdown(step_fn, steps, start_index):
     # batches differ slightly in their row counts (I = size of the rated-item union): group by op and inner dims
     groups = {}
     for (name, meta), ms in timer.summary().items():
-        if name in ('linear', 'linear_tc'):        # (M, K, N): M varies with I
+        if name in ('linear', 'linear_tc', 'linear_tc_batch'):        # (M, K, N): M varies with I
             key, var = (name, tuple(meta[1:])), meta[0]
         elif name == 'attention_pool':             # (B, I, H, U): I varies
             key, var = (name, (meta[0],) + tuple(meta[2:])), meta[1]
@@ -162,7 +162,7 @@ def op_breakdown(step_fn, steps, start_index):
         g['var'] += [var] * len(ms)
     agg = {}
     for (name, inner), g in groups.items():
-        if name in ('linear', 'linear_tc'):
+        if name in ('linear', 'linear_tc', 'linear_tc_batch'):
             meta = (int(np.max(g['var'])),) + inner
         elif name == 'attention_pool':
             meta = (inner[0], int(np.max(g['var']))) + inner[1:]
@@ -260,10 +260,10 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     ops_ms = op_breakdown(step, min(steps, nb), 0)
     (name, meta), (kms, per_step) = max(ops_ms.items(), key=lambda kv: kv[1][0] * kv[1][1])
     I_mean = float(np.mean([b[1].shape[0] for b in host]))
-    if name in ('linear', 'linear_tc'):
+    if name in ('linear', 'linear_tc', 'linear_tc_batch'):
         M, K, N = meta
         alg_bytes = 4.0 * (M * K + N * K + M * N)          # read X and W once, write Y once
-        kname = (f'gemm_tc_kernel (K1a linear {M}x{K}->{N}, tcgen05 {w.get("gemm", "tf32x3")})' if name == 'linear_tc'
+        kname = (f'gemm_tc_kernel (K1a linear {M}x{K}->{N}{" = rated + candidate rows in one launch" if name == "linear_tc_batch" else ""}, tcgen05 {w.get("gemm", "tf32x3")})' if name != 'linear'
                  else f'gemm_tn_kernel (K1a linear {M}x{K}->{N}, fp32 FFMA)')
     elif name == 'attention_pool':
         nnz_mean = float(np.mean(w['nnz']))
@@ -273,7 +273,8 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
         alg_bytes, kname = 0.0, name
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     roof = {'bound': 'hbm', 'kernel': kname, 'achieved': round(achieved, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-            'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention'), 'peak_source': peaks['src'],
+            'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention' if name.startswith('linear') else 'attention_pool'),
+            'peak_source': peaks['src'],
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4, roofline=roof, I_mean=I_mean,
@@ -321,7 +322,7 @@ def zipf_edges_gpu(n_users, n_items, n_edges, dev, seed=42, a_user=0.55, a_item=
     return keys // n_items, keys % n_items, ratings
 
 
-def build_graph(dev, scale=1.0, world=1):
+def build_graph(dev, scale=1.0, world=1, scheme='reduce'):
     from deeprecommendation_b200 import synth
     from deeprecommendation_b200.graph import IdTable, create_graph, get_index
     from deeprecommendation_b200.neural_collaborative_filtering.models import GraphNCF
@@ -343,7 +344,7 @@ def build_graph(dev, scale=1.0, world=1):
     pick = torch.randint(0, E, (64, BATCH), device=dev, generator=g)
     if world > 1:                       # 1-D nnz-balanced row partition + per-layer all-gather (parallel.py)
         from deeprecommendation_b200.parallel import partition_graph
-        partition_graph(graph)
+        partition_graph(graph, scheme=scheme)
     return dict(model=model, sd=sd, graph=graph, index=index, E=E, nU=nU, nI=nI, d=d, L=L_, pick=pick, build_s=build_s, kw=kw,
                 edges=(users, items, ratings))
 
@@ -690,6 +691,9 @@ def main():
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
                     help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
     ap.add_argument('--skip-hbm-regime', action='store_true')
+    ap.add_argument('--graph-scheme', default='reduce', choices=['reduce', 'gather'],
+                    help="multi-GPU GraphNCF: 'reduce' = users partitioned, items replicated, one all-reduce of the item partials per "
+                         "layer; 'gather' = both sides partitioned, per-layer all-gathers (deeprecommendation_b200/parallel.py)")
     ap.add_argument('--eager', action='store_true', help='do not capture the steps into CUDA graphs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -759,13 +763,13 @@ def main():
             del w
             torch.cuda.empty_cache()
         if args.workload in ('all', 'graph'):
-            w = build_graph(dev, args.graph_scale, world)
+            w = build_graph(dev, args.graph_scale, world, args.graph_scheme)
             w['eager'] = args.eager
             r = run_graph(w, args.steps, args.warmup, dist, dev, peaks)
             msgs = 2.0 * w['E'] * w['L'] * args.steps          # the graph is fixed: strong scaling
             entry = {'metric': 'GNN propagation directed-edge messages/sec (GraphNCF fwd)', 'value': msgs / (r['ms'] * 1e-3),
                      'unit': 'edges/s', 'ms_per_step': r['ms'] / args.steps,
-                     'scaling': 'strong', 'parallelism': f'item and user rows each 1-D nnz-partitioned over {world} GPUs; two NCCL all-gathers per layer, the larger one hidden behind the first SpMM; batch rows by all-reduce' if world > 1 else 'single GPU',
+                     'scaling': 'strong', 'parallelism': ((f'users 1-D nnz-partitioned over {world} GPUs, items replicated; one NCCL all-reduce of the (nI, d) item partials per non-final layer, hidden behind the user-row SpMM; batch rows by all-reduce' if args.graph_scheme == 'reduce' else f'item and user rows each 1-D nnz-partitioned over {world} GPUs; two NCCL all-gathers per layer, the larger one hidden behind the first SpMM; batch rows by all-reduce') if world > 1 else 'single GPU'),
                      'dtype': 'f32',
                      'config': {'workload': f'configs[2]: GraphNCF L=2 d=128 hetero, synthetic MovieLens-25M shape (nU={w["nU"]}, nI={w["nI"]}, '
                                 f'E={w["E"]}), pre-embedded (N,128) node features, whole-graph propagation + MLP on a batch of 512 per step',

@@ -31,6 +31,11 @@ class AttentionDesc(C.Structure):
                 ('drop_zero_scores', c_int), ('score_scale', c_f), ('ld_pr', c_i64), ('ld_q', c_i64), ('workspace', c_vp), ('workspace_bytes', c_sz)]
 
 
+class LinearProblem(C.Structure):
+    _fields_ = [('X', c_vp), ('M', c_i64), ('ldx', c_i64), ('W', c_vp), ('N', c_i64), ('ldw', c_i64), ('packed_w', c_vp), ('bias', c_vp),
+                ('row_scale', c_vp), ('relu', c_int), ('Y', c_vp), ('ldy', c_i64), ('y_dtype', c_int)]
+
+
 class SpmmDesc(C.Structure):
     _fields_ = [('chunk_row', c_vp), ('chunk_start', c_vp), ('chunk_slot', c_vp), ('n_chunks', c_int), ('chunk_size', c_int),
                 ('row_ptr', c_vp), ('col', c_vp), ('w', c_vp), ('perm', c_vp), ('skip_bits', c_vp), ('t', c_vp), ('t_dtype', c_int),
@@ -48,6 +53,7 @@ SIGNATURES = {
     'b200rec_linear_workspace': (c_sz, [c_i64, c_i64, c_i64]),
     'b200rec_linear': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
     'b200rec_linear_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    'b200rec_linear_tc_batch': (c_int, [C.POINTER(LinearProblem), c_int, c_i64, c_int, c_vp]),
     'b200rec_packed_weight_bytes': (c_sz, [c_i64, c_i64, c_int]),
     'b200rec_pack_weights_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
     'b200rec_mlp_tower': (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_i64, c_vp, c_int, c_i64, C.POINTER(MlpDesc), c_vp, c_i64, c_vp]),

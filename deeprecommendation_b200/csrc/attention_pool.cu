@@ -89,11 +89,13 @@ struct RowCore {
     const T* __restrict__ Q = reinterpret_cast<const T*>(p.Q);
     float v[32];
 #pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 8) {
-      if (j0 < count) {
-        float4 pr[8][HV];
+    constexpr int LB = (HV == 1 && UV == 1) ? 16 : 8;     // row gathers in flight per warp
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+    for (int j0 = 0; j0 < 32; j0 += LB) {
+      if (j0 < count) {
+        float4 pr[LB][HV];
+#pragma unroll
+        for (int jj = 0; jj < LB; ++jj) {
           const int c = __shfl_sync(FULL, my_col, j0 + jj);
 #pragma unroll
           for (int hv = 0; hv < HV; ++hv) {
@@ -102,7 +104,7 @@ struct RowCore {
           }
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < LB; ++jj) {
           float s = 0.f;
 #pragma unroll
           for (int hv = 0; hv < HV; ++hv) {
@@ -117,7 +119,7 @@ struct RowCore {
         }
       } else {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) v[j0 + jj] = 0.f;
+        for (int jj = 0; jj < LB; ++jj) v[j0 + jj] = 0.f;
       }
     }
     // butterfly reduce-scatter: after the last step lane j holds sum over lanes of v[j]
@@ -164,12 +166,13 @@ struct RowCore {
     }
     const float wgt = pj * my_val;                    // attention x centred rating (:212)
 #pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 8) {
-      if (j0 < count) {
-        float4 q[8][UV];
-        float w[8];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+    for (int j0 = 0; j0 < 32; j0 += LB) {
+      if (j0 < count) {
+        float4 q[LB][UV];
+        float w[LB];
+#pragma unroll
+        for (int jj = 0; jj < LB; ++jj) {
           const int c = __shfl_sync(FULL, my_col, j0 + jj);
           w[jj] = __shfl_sync(FULL, wgt, j0 + jj);
 #pragma unroll
@@ -179,7 +182,7 @@ struct RowCore {
           }
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
+        for (int jj = 0; jj < LB; ++jj)
 #pragma unroll
           for (int uv = 0; uv < UV; ++uv) {
             acc[uv][0] = fmaf(w[jj], q[jj][uv].x, acc[uv][0]);
@@ -230,7 +233,7 @@ __device__ __forceinline__ float normalise_score(float s, float M, float Lsum) {
 
 // ---- ragged-native front-end: CSR of user_matrix ------------------------------------------------------------
 template <int HV, int UV, int MODE, typename T>
-__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 3 : 1)
+__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 2 : 1)
 attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col,
                           const float* __restrict__ val, const int* __restrict__ row_nnz, long long padded_stride) {
   __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];
@@ -274,7 +277,7 @@ attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const in
 constexpr int ATT_SEG = 512;
 
 template <int HV, int UV, int MODE, typename T>
-__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 3 : 1)
+__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 2 : 1)
 attention_seg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
                      const int* __restrict__ row_nnz, long long padded_stride, float* __restrict__ partials, int nseg_max) {
   __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];

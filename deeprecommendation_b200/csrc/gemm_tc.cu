@@ -113,6 +113,16 @@ struct TcParams {
   int dbg;     // experiments only (B200REC_TC_DBG): 1 = no MMA, 2 = no prefetch loads, 4 = no proxy fence
 };
 
+// Several GEMMs of the same K and mode in ONE launch (b200rec_linear_tc_batch): problem q owns the m-tiles
+// [tile_start[q], tile_start[q+1]) of grid.y.  The scoring path is a chain of short GEMMs (candidate and rated-item
+// projections share their weights; the two halves of AttentionNet.0 share their shape): one launch instead of four.
+constexpr int TC_MAX_BATCH = 4;
+struct TcBatch {
+  TcParams prob[TC_MAX_BATCH];
+  int tile_start[TC_MAX_BATCH + 1];
+  int n;
+};
+
 // One operand tile (128 rows x KB fp32 source elements) -> smem by the 256 producer threads, COALESCED: a warp owns 16
 // consecutive rows; in one load instruction its lanes cover 32/LPR rows x KB contiguous floats (EPL = 2 or 4 floats per
 // lane, LPR = KB/EPL lanes per row).  Everything that does not depend on the k-block — clamped global row offsets, the
@@ -220,7 +230,13 @@ struct TileRegs {
 
 template <int MODE, int NSTAGE, int EPL, bool VEC, bool WPACK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(TcParams p) {
+gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
+  int q = 0;
+#pragma unroll
+  for (int t = 1; t < TC_MAX_BATCH; ++t)
+    if (t < batch.n && (int)blockIdx.y >= batch.tile_start[t]) q = t;
+  const TcParams& p = batch.prob[q];
+  if ((int)blockIdx.x * TC_BN >= p.N) return;                   // this problem has fewer n-tiles than the widest of the batch
   constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
   constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
   constexpr int STAGE_BYTES = 2 * PLANES * TILE_BYTES;          // A (hi[,lo]) + B (hi[,lo])
@@ -237,7 +253,7 @@ gemm_tc_kernel(TcParams p) {
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int m0 = ((int)blockIdx.y - batch.tile_start[q]) * TC_BM, n0 = blockIdx.x * TC_BN;
   const int num_kb = (p.K + KB - 1) / KB;
   const int kb_shift = (int)((blockIdx.y * 7u + blockIdx.x * 3u) % (unsigned)num_kb);
 
@@ -464,7 +480,7 @@ static size_t packed_weight_bytes(long long N, long long K, int mode) {
 }
 
 template <int MODE, int EPL, bool VEC, bool WPACK>
-static int launch_tc_epl(const TcParams& p, cudaStream_t st) {
+static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   constexpr int NSTAGE = (MODE == TC_BF16) ? 4 : 3;
   constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
   const size_t smem = (size_t)NSTAGE * 2 * PLANES * TILE_BYTES + 1024;
@@ -473,26 +489,37 @@ static int launch_tc_epl(const TcParams& p, cudaStream_t st) {
     B200REC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid(ceil_div_i(p.N, TC_BN), ceil_div_i(p.M, TC_BM));
-  gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK><<<grid, TC_THREADS, smem, st>>>(p);
+  int nmax = 0;
+  for (int q = 0; q < b.n; ++q) nmax = b.prob[q].N > nmax ? b.prob[q].N : nmax;
+  dim3 grid(ceil_div_i(nmax, TC_BN), b.tile_start[b.n]);
+  gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK><<<grid, TC_THREADS, smem, st>>>(b);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
 template <int MODE>
-static int launch_tc(const TcParams& p, cudaStream_t st) {
+static int launch_tc(const TcBatch& b, cudaStream_t st) {
   auto aligned = [&](int n) {
-    return (p.K % n) == 0 && (p.ldx % n) == 0 && ((uintptr_t)p.X % (4 * n)) == 0 &&
-           (p.Wp != nullptr || ((p.ldw % n) == 0 && ((uintptr_t)p.W % (4 * n)) == 0));
+    for (int q = 0; q < b.n; ++q) {
+      const TcParams& p = b.prob[q];
+      if (!((p.K % n) == 0 && (p.ldx % n) == 0 && ((uintptr_t)p.X % (4 * n)) == 0 &&
+            (p.Wp != nullptr || ((p.ldw % n) == 0 && ((uintptr_t)p.W % (4 * n)) == 0))))
+        return false;
+    }
+    return true;
   };
-  if (p.Wp) {
-    if (aligned(4)) return launch_tc_epl<MODE, 4, true, true>(p, st);
-    if (aligned(2)) return launch_tc_epl<MODE, 2, true, true>(p, st);
-    return launch_tc_epl<MODE, 2, false, true>(p, st);
+  bool packed = true;
+  for (int q = 0; q < b.n; ++q) packed = packed && b.prob[q].Wp != nullptr;
+  if (packed) {
+    if (aligned(4)) return launch_tc_epl<MODE, 4, true, true>(b, st);
+    if (aligned(2)) return launch_tc_epl<MODE, 2, true, true>(b, st);
+    return launch_tc_epl<MODE, 2, false, true>(b, st);
   }
-  if (aligned(4)) return launch_tc_epl<MODE, 4, true, false>(p, st);        // 128-bit loads (e.g. K = 128 transforms)
-  if (aligned(2)) return launch_tc_epl<MODE, 2, true, false>(p, st);        // 64-bit loads (F = 2094)
-  return launch_tc_epl<MODE, 2, false, false>(p, st);                       // odd K / pitch: scalar loads
+  for (int q = 0; q < b.n; ++q)
+    if (b.prob[q].Wp != nullptr && b.prob[q].W == nullptr) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: a batch mixes packed-only and plain weights");
+  if (aligned(4)) return launch_tc_epl<MODE, 4, true, false>(b, st);        // 128-bit loads (e.g. K = 128 transforms)
+  if (aligned(2)) return launch_tc_epl<MODE, 2, true, false>(b, st);        // 64-bit loads (F = 2094)
+  return launch_tc_epl<MODE, 2, false, false>(b, st);                       // odd K / pitch: scalar loads
 }
 
 }  // namespace b200rec
@@ -518,25 +545,55 @@ extern "C" int b200rec_pack_weights_tc(const float* W, int64_t N, int64_t K, int
   return B200REC_OK;
 }
 
-extern "C" int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
-                                 const float* bias, const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode,
-                                 const void* packed_w, b200rec_stream_t stream) {
+static int tc_fill(TcParams& p, const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
+                   const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, const void* packed_w) {
   if (M < 0 || N <= 0 || K <= 0 || (!W && !packed_w) || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad argument");
-  if (M == 0) return B200REC_OK;
   if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: dim > int32");
   if (ldx < K || ldw < K || ldy < N) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: leading dimension too small");
   if (M * ldx >= (1LL << 32) || (!packed_w && N * ldw >= (1LL << 32))) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: operand larger than 2^32 elements");
   if (y_dtype != B200REC_F32 && y_dtype != B200REC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad y_dtype");
-  TcParams p;
   p.X = X; p.ldx = ldx; p.W = W; p.ldw = ldw; p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.Wp = (const unsigned char*)packed_w;
   p.Y = Y; p.ldy = ldy; p.y_bf16 = y_dtype == B200REC_BF16; p.bias = bias; p.row_scale = row_scale; p.relu = relu;
-  {
-    const char* e = getenv("B200REC_TC_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  const char* e = getenv("B200REC_TC_DBG");
+  p.dbg = e ? atoi(e) : 0;
+  return B200REC_OK;
+}
+
+extern "C" int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
+                                 const float* bias, const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode,
+                                 const void* packed_w, b200rec_stream_t stream) {
+  TcBatch b;
+  b.n = 1;
+  const int rc = tc_fill(b.prob[0], X, M, K, ldx, W, N, ldw, bias, row_scale, relu, Y, ldy, y_dtype, packed_w);
+  if (rc) return rc;
+  if (M == 0) return B200REC_OK;
+  b.tile_start[0] = 0;
+  b.tile_start[1] = ceil_div_i(M, TC_BM);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == B200REC_TC_TF32X3) return launch_tc<TC_TF32X3>(p, st);
-  if (mode == B200REC_TC_BF16) return launch_tc<TC_BF16>(p, st);
+  if (mode == B200REC_TC_TF32X3) return launch_tc<TC_TF32X3>(b, st);
+  if (mode == B200REC_TC_BF16) return launch_tc<TC_BF16>(b, st);
   return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad mode");
+}
+
+extern "C" int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode,
+                                       b200rec_stream_t stream) {
+  if (!problems || n_problems < 1 || n_problems > TC_MAX_BATCH) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_batch: 1..4 problems");
+  TcBatch b;
+  b.n = 0;
+  b.tile_start[0] = 0;
+  for (int q = 0; q < n_problems; ++q) {
+    const b200rec_linear_problem_t& r = problems[q];
+    if (r.M == 0) continue;
+    const int rc = tc_fill(b.prob[b.n], r.X, r.M, K, r.ldx, r.W, r.N, r.ldw, r.bias, r.row_scale, r.relu, r.Y, r.ldy, r.y_dtype, r.packed_w);
+    if (rc) return rc;
+    b.tile_start[b.n + 1] = b.tile_start[b.n] + ceil_div_i(r.M, TC_BM);
+    ++b.n;
+  }
+  if (b.n == 0) return B200REC_OK;
+  for (int q = b.n; q < TC_MAX_BATCH; ++q) b.tile_start[q + 1] = b.tile_start[b.n];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == B200REC_TC_TF32X3) return launch_tc<TC_TF32X3>(b, st);
+  if (mode == B200REC_TC_BF16) return launch_tc<TC_BF16>(b, st);
+  return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_batch: bad mode");
 }

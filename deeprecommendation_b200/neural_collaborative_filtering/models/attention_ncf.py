@@ -102,16 +102,45 @@ class AttentionNCF(NCF):
         self._proj_cache = (key, tuple(t.detach() for t in out)) if key is not None else None
         return out
 
+    def _attention_halves(self):
+        """(A1c, A1r, a1, a2, head bias) of AttentionNet as STABLE view objects (so their MMA-ready packed copies stay cached)
+        — only for the Linear-ReLU-Linear variant with att_dense % 4 == 0; None otherwise."""
+        if self.use_cos_sim_instead or len(self.AttentionNet) == 1 or self.AttentionNet[0].weight.shape[0] % 4:
+            return None
+        first, head = self.AttentionNet[0], self.AttentionNet[3]
+        key = (first.weight.data_ptr(), first.weight._version, head.weight.data_ptr(), head.weight._version)
+        cached = getattr(self, '_att_cache', None)
+        if cached is None or cached[0] != key:
+            E = first.weight.shape[1] // 2
+            w = first.weight.detach()
+            cached = (key, (w[:, :E], w[:, E:], first.bias.detach(), head.weight.detach().view(-1), head.bias.detach()))
+            self._att_cache = cached
+        return cached[1]
+
     def forward(self, candidate_items, rated_items, user_matrix, return_attention_weights=False):
         item, user = self.ItemEmbeddings[0], self.UserEmbeddings[0]
         E, U = item.weight.shape[0], user.weight.shape[0]
-        Ec = ops.linear(candidate_items, item.weight, item.bias)                        # :150
-        # one sweep over rated_items: item embedding (:151) and Q = rated_items·W_Uᵀ (pooling moved into embedding space:
-        # W_U(Σ α·um·R_i) = Σ α·um·(W_U R_i), :213+:216)
         Wcat, bcat, bU = self._stacked_projection()
-        ErQ = ops.linear(rated_items, Wcat, bcat)
-        Er, Q = ErQ[:, :E], ErQ[:, E:]
-        Pc, Pr, mode, a2, a20 = self._score_tables(Ec, Er)
+        halves = self._attention_halves()
+        no_grad = not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
+        if (no_grad and halves is not None and ops.tc_batch_available() and rated_items.shape[0] >= ops.TC_MIN_ROWS
+                and rated_items.shape[1] >= ops.TC_MIN_K):
+            # inference on the tensor-core engine: the rated-item sweep fills the device exactly (74 x 2 tiles on 148 SMs at
+            # config 2 — adding the candidates' 4 row tiles to that launch costs a second wave, measured 132 vs 71 us), so
+            # the candidates keep their own split-K GEMM; both halves of AttentionNet.0 share ONE tensor-core launch.
+            A1c, A1r, a1, a2, a20 = halves
+            Ec = ops.linear_raw(candidate_items, item.weight, item.bias)                # :150
+            ErQ = ops.linear_raw(rated_items, Wcat, bcat)                               # :151 + Q = R·W_Uᵀ
+            Er, Q = ErQ[:, :E], ErQ[:, E:]
+            Pr, Pc = ops.linear_tc_batch([(Er, A1r, None, None), (Ec, A1c, a1, None)])
+            mode = L.ATT_NET
+        else:
+            Ec = ops.linear(candidate_items, item.weight, item.bias)                    # :150
+            # one sweep over rated_items: item embedding (:151) and Q = rated_items·W_Uᵀ (pooling moved into embedding
+            # space: W_U(Σ α·um·R_i) = Σ α·um·(W_U R_i), :213+:216)
+            ErQ = ops.linear(rated_items, Wcat, bcat)
+            Er, Q = ErQ[:, :E], ErQ[:, E:]
+            Pc, Pr, mode, a2, a20 = self._score_tables(Ec, Er)
 
         um, scale, drop_zero, train_mask = user_matrix, 1.0, False, None
         if self.training:

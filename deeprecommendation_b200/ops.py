@@ -175,6 +175,52 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     return out
 
 
+def tc_batch_available(engine=None):
+    return (engine or _gemm_engine) != 'simt'
+
+
+def linear_tc_batch(problems, engine=None):
+    """Up to four `out = x @ weight.T + bias` GEMMs of the same K in ONE tensor-core launch (b200rec_linear_tc_batch).
+    problems: list of (x, weight, bias | None, out | None); returns the outputs.  Inference only."""
+    engine = engine or _gemm_engine
+    if engine == 'simt':
+        raise RuntimeError('linear_tc_batch needs a tensor-core engine (set_gemm_engine)')
+    mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+    arr = (L.LinearProblem * len(problems))()
+    keep, outs, K, dev, meta = [], [], None, None, []
+    for q, (x, weight, bias, out) in enumerate(problems):
+        _require_cuda(x, weight, bias, out)
+        x, ldx = _row_major(x)
+        w, ldw = _row_major(weight)
+        M, Kq = x.shape
+        N = w.shape[0]
+        if w.shape[1] != Kq or (K is not None and Kq != K):
+            raise ValueError('linear_tc_batch: the problems must share K')
+        K, dev = Kq, x.device
+        if M * ldx >= 2 ** 32:
+            raise NotImplementedError('linear_tc_batch: operand larger than 2^32 elements')
+        if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+            bias = bias.contiguous().float()
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=dev)
+        elif out.shape != (M, N) or out.stride(1) != 1:
+            raise ValueError('linear_tc_batch: bad `out`')
+        packed = _packed_weight(weight if weight is w else w, ldw, mode) if _pack_weights else None
+        p = arr[q]
+        p.X, p.M, p.ldx = x.data_ptr(), M, ldx
+        p.W, p.N, p.ldw = w.data_ptr(), N, ldw
+        p.packed_w = packed.data_ptr() if packed is not None else None
+        p.bias = bias.data_ptr() if bias is not None else None
+        p.row_scale, p.relu = None, 0
+        p.Y, p.ldy, p.y_dtype = out.data_ptr(), (out.stride(0) if M > 1 else max(N, out.stride(0))), _dtype_code(out.dtype)
+        keep += [x, w, bias, packed, out]
+        outs.append(out)
+        meta.append((M, N))
+    with torch.cuda.device(dev), _timed('linear_tc_batch', (sum(m for m, _ in meta), K, max(n for _, n in meta))):
+        L.check(L.lib().b200rec_linear_tc_batch(arr, len(problems), K, mode, _stream()), 'linear_tc_batch')
+    return outs
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, row_scale, relu):

@@ -52,6 +52,15 @@ int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const floa
 int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
                       const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w,
                       b200rec_stream_t stream);
+/* Up to four such GEMMs sharing K and mode in ONE launch (candidate + rated-item projections, the two halves of
+ * AttentionNet.0 — attention_ncf.py:150-151,176): problem q covers its own rows; fields as in b200rec_linear_tc. */
+typedef struct {
+  const float* X; int64_t M; int64_t ldx;
+  const float* W; int64_t N; int64_t ldw; const void* packed_w;
+  const float* bias; const float* row_scale; int relu;
+  void* Y; int64_t ldy; int y_dtype;
+} b200rec_linear_problem_t;
+int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode, b200rec_stream_t stream);
 /* Optional: W converted once into MMA-ready swizzled tiles (bf16 or TF32 hi/lo, zero-padded).  With `packed_w` the GEMM moves
  * the W operand by TMA bulk copies (cp.async.bulk) and only X is converted by the producer warps.  128-byte aligned buffer. */
 size_t b200rec_packed_weight_bytes(int64_t N, int64_t K, int mode);

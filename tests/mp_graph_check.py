@@ -38,16 +38,20 @@ def main():
     m.load_state_dict(sd)
     pick = rng.permutation(n)[:1000]
     uid, iid = g.user2item_edge_index[0][pick].contiguous(), g.user2item_edge_index[1][pick].contiguous()
+    err, info = 0.0, {}
     with torch.no_grad():
         ref = m(g, uid, iid, dev)
-        pg = partition_graph(g)
-        out = m(g, uid, iid, dev)
-    err = float((out - ref).abs().max() / ref.abs().max())
+        for scheme in ('gather', 'reduce'):
+            pg = partition_graph(g, scheme=scheme)
+            out = m(g, uid, iid, dev)
+            e = float((out - ref).abs().max() / ref.abs().max())
+            info[scheme] = e
+            err = max(err, e)
     errs = [None] * world
-    dist.all_gather_object(errs, (err, pg.edges_own, pg.items.rows + pg.users.rows))
+    dist.all_gather_object(errs, (err, pg.edges_own, pg.users.rows, info))
     if rank == 0:
         print(json.dumps({'world': world, 'max_rel_err_per_rank': [e[0] for e in errs], 'edges_per_rank': [e[1] for e in errs],
-                          'rows_per_rank': [e[2] for e in errs], 'ok': all(e[0] < 1e-5 for e in errs)}), flush=True)
+                          'user_rows_per_rank': [e[2] for e in errs], 'per_scheme': errs[0][3], 'ok': all(e[0] < 1e-5 for e in errs)}), flush=True)
     dist.destroy_process_group()
     if err >= 1e-5:
         sys.exit(1)

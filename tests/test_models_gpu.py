@@ -338,13 +338,13 @@ def _medium_graph(n_users=1500, n_items=900, n=60_000, F=48, d_emb=64, L_=2):
 
 
 def test_partitioned_world1_equals_single():
-    from deeprecommendation_b200.parallel import PartitionedGraph, forward_partitioned
+    from deeprecommendation_b200.parallel import PartitionedGraph, UserPartitionedGraph, forward_partitioned
     m, g, uid, iid = _medium_graph()
     with torch.no_grad():
         ref = m(g, uid, iid, DEV)
-        pg = PartitionedGraph(g, rank=0, world=1)
-        out = forward_partitioned(m, pg, uid, iid)
-    assert maxnorm_rel(out, ref) < 1e-6
+        for cls in (PartitionedGraph, UserPartitionedGraph):
+            out = forward_partitioned(m, cls(g, rank=0, world=1), uid, iid)
+            assert maxnorm_rel(out, ref) < 1e-6
 
 
 @pytest.mark.parametrize('P', [2, 3, 8])
@@ -407,4 +407,47 @@ def test_partition_emulated_ranks_on_one_gpu(P):
             comb[mine] = accs[k][local[mine]]
             seen += mine.int()
         assert torch.all(seen == 1)                     # every node has exactly one owner
+    assert maxnorm_rel(comb, ref) < 1e-6
+
+
+@pytest.mark.parametrize('P', [2, 3, 8])
+def test_user_partition_reduce_scheme_emulated_ranks(P):
+    """scheme 'reduce' with P emulated ranks on one GPU: the all-reduce of the item partials is a sum over the ranks'
+    buffers.  Checks the column-sliced item CSRs, the owned user-row CSRs and their chunk plans with the real kernels."""
+    from deeprecommendation_b200 import ops
+    from deeprecommendation_b200.graph import get_index
+    from deeprecommendation_b200.parallel import UserPartitionedGraph
+    m, g, uid, iid = _medium_graph()
+    full = get_index(g)
+    L_, d = len(m.gnn_convs), 64
+    ranks = [UserPartitionedGraph(g, rank=r, world=P) for r in range(P)]
+    nI = ranks[0].nI
+    assert sum(pg.edges_own for pg in ranks) == full.e1 + full.e2
+    assert sum(pg.users.rows for pg in ranks) == full.num_nodes - nI
+    ie, ue = m.item_embeddings[0], m.user_embeddings[0]
+    lin_u, lin_i, _ = m.gnn_convs[0].typed()
+    with torch.no_grad():
+        ref = m._encode(g, full, None, full.dinv, False)
+        x_items = ops.linear_raw(g.item_features, ie.weight, ie.bias)
+        x_users = [ops.linear_raw(pg.user_features, ue.weight, ue.bias) for pg in ranks]
+        acc_items = x_items.clone()
+        acc_users = [x.clone() for x in x_users]
+        for l in range(L_):
+            t_items = ops.linear_raw(x_items, lin_i.weight, lin_i.bias, row_scale=ranks[0].dinv_items)
+            total = torch.zeros((nI, d), device=DEV)
+            nxt = []
+            for k, pg in enumerate(ranks):
+                nu = pg.users.rows
+                part = torch.zeros((nI, d), device=DEV)
+                xn = torch.empty((nu, d), device=DEV)
+                if nu:
+                    t_users = ops.linear_raw(x_users[k], lin_u.weight, lin_u.bias, row_scale=pg.dinv_users)
+                    ops.spmm_raw(pg.index_items, t_users, w=pg.index_items.w, dinv=pg.dinv_items, x_next=part)
+                    ops.spmm_raw(pg.index_users, t_items, w=pg.index_users.w, dinv=pg.dinv_users, x_next=xn)
+                total += part                                        # the all-reduce
+                nxt.append(xn)
+                acc_users[k] = acc_users[k] + xn
+            x_items, x_users = total, nxt
+            acc_items = acc_items + x_items
+        comb = torch.cat([acc_items] + acc_users) / (L_ + 1)
     assert maxnorm_rel(comb, ref) < 1e-6

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from deeprecommendation_b200 import synth
-from deeprecommendation_b200.parallel import RowPartition, split_rows
+from deeprecommendation_b200.parallel import RowPartition, column_slice_csr, split_rows
 from oracle import restatement as R
 
 
@@ -93,4 +93,50 @@ def _worker(rank, world, port, ret):
 def test_partitioned_propagation_matches_single_process(world):
     ret = mp.get_context('spawn').Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world and all(ret.values()), dict(ret)
+
+
+# ---- scheme 'reduce': users partitioned, items replicated, one all-reduce of the item partials per layer ---------------------
+def test_column_slice_csr_keeps_order_and_counts():
+    row_ptr = torch.tensor([0, 3, 3, 7, 8])
+    col = torch.tensor([5, 1, 9, 2, 6, 7, 3, 6])
+    w = torch.arange(8.0)
+    rp, c, ww = column_slice_csr(row_ptr, col, 5, 8, w)
+    assert rp.tolist() == [0, 1, 1, 3, 4] and c.tolist() == [0, 1, 2, 1] and ww.tolist() == [0.0, 4.0, 5.0, 7.0]
+    rp, c, none = column_slice_csr(row_ptr, col, 100, 200, None)
+    assert rp.tolist() == [0, 0, 0, 0, 0] and c.numel() == 0 and none is None
+
+
+def _worker_reduce(rank, world, port, ret):
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        n_users, n_items = 300, 200
+        row_ptr, col, w, N = _graph(n_users=n_users, n_items=n_items)
+        nI, d = n_items, 8
+        feats = torch.from_numpy(np.random.default_rng(1).standard_normal((N, d)).astype(np.float32))
+        k_items = int(row_ptr[nI])
+        part = RowPartition(split_rows(row_ptr[nI:] - k_items, world), rank)        # users by their own-row nnz
+        # (a) partial item rows from the owned users' edges, completed by an all-reduce
+        lrp, lcol, lw = column_slice_csr(row_ptr[:nI + 1], col[:k_items], nI + part.r0, nI + part.r1, w[:k_items])
+        own_user_feats = feats[nI + part.r0: nI + part.r1]
+        partial = _spmm(lrp, lcol, lw, own_user_feats, nI)
+        dist.all_reduce(partial)
+        # (b) owned user rows from the replicated item table
+        k0, k1 = int(row_ptr[nI + part.r0]), int(row_ptr[nI + part.r1])
+        urp = row_ptr[nI + part.r0: nI + part.r1 + 1] - k0
+        own_users = _spmm(urp, col[k0:k1], w[k0:k1], feats[:nI], part.rows)
+        ref = _spmm(row_ptr, col, w, feats, N)
+        counts = torch.tensor([int(lcol.numel())])
+        dist.all_reduce(counts)
+        ok = torch.allclose(partial, ref[:nI], rtol=1e-12, atol=1e-12) and torch.equal(own_users, ref[nI + part.r0: nI + part.r1])
+        ret[rank] = bool(ok) and int(counts) == k_items
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_user_partitioned_reduce_scheme_matches_single_process(world):
+    ret = mp.get_context('spawn').Manager().dict()
+    mp.spawn(_worker_reduce, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world and all(ret.values()), dict(ret)
