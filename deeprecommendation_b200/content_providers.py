@@ -95,6 +95,92 @@ class ArrayDynamicProvider(DynamicContentProvider):
         return np.array(cands), self.item_ids[rated_idx], candidate_items, rated_items, torch.from_numpy(um), third
 
 
+class ResidentRows:
+    """Rows of a profile table that lives in HBM: what the dense `(n, F)` tensor of the collate contract becomes when the
+    provider is device-resident.  `pos` = int64 row numbers (host, pinned when CUDA is present)."""
+
+    def __init__(self, table: torch.Tensor, pos: np.ndarray):
+        self.table = table
+        t = torch.from_numpy(np.ascontiguousarray(pos, dtype=np.int64))
+        self.pos = t.pin_memory() if torch.cuda.is_available() else t
+
+    def __len__(self):
+        return int(self.pos.numel())
+
+    def dense(self, device=None):
+        """the reference's tensor, materialised (tests / training fallback)"""
+        dev = self.table.device if device is None else device
+        return self.table.index_select(0, self.pos.to(self.table.device, non_blocking=True)).to(dev)
+
+
+class SparseUserMatrix:
+    """CSR of the `(B, I)` user_matrix of the collate contract (exact zeros = "unrated" are simply absent)."""
+
+    def __init__(self, row_ptr, col, val, shape):
+        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+        self.row_ptr = pin(torch.from_numpy(np.ascontiguousarray(row_ptr, dtype=np.int32)))
+        self.col = pin(torch.from_numpy(np.ascontiguousarray(col, dtype=np.int32)))
+        self.val = pin(torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)))
+        self.shape = tuple(shape)
+
+    def to_dense(self) -> torch.Tensor:
+        um = torch.zeros(self.shape, dtype=torch.float32)
+        rows = torch.repeat_interleave(torch.arange(self.shape[0]), (self.row_ptr[1:] - self.row_ptr[:-1]).long())
+        um[rows, self.col.long()] = self.val
+        return um
+
+    def nbytes(self) -> int:
+        return int(self.row_ptr.numel() * 4 + self.col.numel() * 8)
+
+
+class ResidentDynamicProvider(ArrayDynamicProvider):
+    """`ArrayDynamicProvider` with the item-profile table resident in HBM (row f-4 of SURVEY.md §8: device-side data path).
+
+    The reference's collate copies `item_profiles[rated_items_ids]` — 79 MB per batch at config 2 — to the host tensor that
+    `do_forward` then ships over PCIe (dynamic_profiles_provider.py:70, dynamic_datasets.py:25-40).  Here the 6-tuple keeps
+    its shape but carries row numbers (`ResidentRows`) and the user matrix as CSR (`SparseUserMatrix`): ~2.4 MB per batch.
+    `DynamicPointwiseDataset.do_forward` recognises them and calls `AttentionNCF.forward_resident`; results are identical
+    to the dense path (tests/test_providers.py, tests/test_models_gpu.py)."""
+
+    def __init__(self, item_ids, item_profiles, user_ids, row_ptr, rated_item_idx, rated_rating, device='cuda'):
+        super().__init__(item_ids, item_profiles, user_ids, row_ptr, rated_item_idx, rated_rating)
+        self.table = torch.as_tensor(self.item_profiles, dtype=torch.float32).to(device)
+
+    def collate_csr(self, user_idx, ignore_ratings=False):
+        """(rated item indices (I,), CSR of user_matrix) — same arithmetic as `collate_indices`, without the dense matrix"""
+        user_idx = np.asarray(user_idx, dtype=np.int64)
+        starts, ends = self.row_ptr[user_idx], self.row_ptr[user_idx + 1]
+        lens = ends - starts
+        ptr = np.zeros(len(user_idx) + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        flat = np.repeat(starts - ptr[:-1], lens) + np.arange(ptr[-1])
+        items = self.rated_item_idx[flat]
+        rated = np.unique(items)
+        cols = np.searchsorted(rated, items)
+        if ignore_ratings:
+            vals = np.ones(len(flat), dtype=np.float32)
+        else:
+            vals = (self.rated_rating[flat] - np.repeat((self.mean_rating[user_idx] + 2.5) / 2, lens)).astype(np.float32)
+        keep = vals != 0.0                      # an exactly-zero centred rating is "unrated" in the dense form too
+        if not keep.all():
+            rows = np.repeat(np.arange(len(user_idx)), lens)[keep]
+            cols, vals = cols[keep], vals[keep]
+            ptr = np.zeros(len(user_idx) + 1, dtype=np.int64)
+            np.cumsum(np.bincount(rows, minlength=len(user_idx)), out=ptr[1:])
+        return rated, SparseUserMatrix(ptr, cols, vals, (len(user_idx), len(rated)))
+
+    def collate_interacted_items(self, batch, for_ranking: bool, ignore_ratings=False):
+        users, cands, third = zip(*batch)
+        u_idx = np.searchsorted(self.user_ids, np.asarray(users))
+        candidate_items = ResidentRows(self.table, np.searchsorted(self.item_ids, np.asarray(cands)))
+        if for_ranking:
+            third = ResidentRows(self.table, np.searchsorted(self.item_ids, np.asarray(third)))
+        else:
+            third = torch.FloatTensor(np.asarray(third, dtype=np.float64))
+        rated_idx, um = self.collate_csr(u_idx, ignore_ratings)
+        return np.array(cands), self.item_ids[rated_idx], candidate_items, ResidentRows(self.table, rated_idx), um, third
+
+
 class ArrayGraphProvider(GraphContentProvider):
     """Bipartite graph of an interaction list, built ON THE DEVICE by K4 (graph.create_graph), node ids assigned like
     src/content_providers/graph_providers.py:76-80 from ALL known ids (not just the graph's interactions)."""

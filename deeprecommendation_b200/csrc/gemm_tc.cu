@@ -110,6 +110,7 @@ struct TcParams {
   void* Y; long long ldy; int y_bf16;
   const float* bias; const float* row_scale; int relu;
   const unsigned char* Wp;   // optional: W pre-packed by pack_weights_kernel (swizzled tiles), moved by TMA bulk copies
+  const long long* row_index;   // optional: row m of the GEMM is row row_index[m] of X (resident profile table + ids)
   int dbg;     // experiments only (B200REC_TC_DBG): 1 = no MMA, 2 = no prefetch loads, 4 = no proxy fence
 };
 
@@ -139,7 +140,7 @@ struct TileAddr {
   unsigned row_ok;            // bit it: the row exists
   int kcol;                   // this lane's first column inside a k-block
 
-  __device__ __forceinline__ void init(long long ld, int row0, int rows_total, int warp, int lane) {
+  __device__ __forceinline__ void init(long long ld, int row0, int rows_total, int warp, int lane, const long long* row_index = nullptr) {
     kcol = (lane % LPR) * EPL;
     row_ok = 0u;
     const unsigned byte = (unsigned)kcol * ((MODE == TC_BF16) ? 2u : 4u);
@@ -148,7 +149,9 @@ struct TileAddr {
       const int r = warp * 16 + it * RPI + lane / LPR;
       const int grow = row0 + r;
       row_ok |= (grow < rows_total ? 1u : 0u) << it;
-      goff[it] = (unsigned)((long long)min(grow, rows_total - 1) * ld) + (unsigned)kcol;
+      const int crow = min(grow, rows_total - 1);
+      const long long srow = row_index ? __ldg(row_index + crow) : (long long)crow;
+      goff[it] = (unsigned)(srow * ld) + (unsigned)kcol;
       soff[it] = (unsigned)(r >> 3) * 1024u + (unsigned)(r & 7) * 128u + (((byte >> 4) ^ (unsigned)(r & 7)) << 4) + (byte & 15u);
     }
   }
@@ -281,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     // SAME W tile at the same moment.  The set of products accumulated is unchanged.
     constexpr int PF = (MODE == TC_BF16) ? 1 : 2;             // k-blocks of global loads in flight ahead of the store
     TileAddr<MODE, EPL> aa, ab;
-    aa.init(p.ldx, m0, p.M, warp, lane);
+    aa.init(p.ldx, m0, p.M, warp, lane, p.row_index);
     if constexpr (!WPACK) ab.init(p.ldw, n0, p.N, warp, lane);
     // packed W: tile (n-tile, k-block) = PLANES x 16 KB, already converted and swizzled (pack_weights_kernel)
     const unsigned char* wp_tiles = WPACK ? p.Wp + (size_t)blockIdx.x * num_kb * (PLANES * TILE_BYTES) : nullptr;
@@ -546,12 +549,15 @@ extern "C" int b200rec_pack_weights_tc(const float* W, int64_t N, int64_t K, int
 }
 
 static int tc_fill(TcParams& p, const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
-                   const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, const void* packed_w) {
+                   const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, const void* packed_w,
+                   const int64_t* row_index = nullptr, int64_t x_rows = 0) {
   if (M < 0 || N <= 0 || K <= 0 || (!W && !packed_w) || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad argument");
   if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: dim > int32");
   if (ldx < K || ldw < K || ldy < N) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: leading dimension too small");
-  if (M * ldx >= (1LL << 32) || (!packed_w && N * ldw >= (1LL << 32))) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: operand larger than 2^32 elements");
+  if ((row_index ? x_rows : M) * ldx >= (1LL << 32) || (!packed_w && N * ldw >= (1LL << 32))) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: operand larger than 2^32 elements");
+  if (row_index && x_rows <= 0) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: row_index needs the row count of X");
   if (y_dtype != B200REC_F32 && y_dtype != B200REC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad y_dtype");
+  p.row_index = reinterpret_cast<const long long*>(row_index);
   p.X = X; p.ldx = ldx; p.W = W; p.ldw = ldw; p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.Wp = (const unsigned char*)packed_w;
   p.Y = Y; p.ldy = ldy; p.y_bf16 = y_dtype == B200REC_BF16; p.bias = bias; p.row_scale = row_scale; p.relu = relu;
@@ -562,10 +568,10 @@ static int tc_fill(TcParams& p, const float* X, int64_t M, int64_t K, int64_t ld
 
 extern "C" int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
                                  const float* bias, const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode,
-                                 const void* packed_w, b200rec_stream_t stream) {
+                                 const void* packed_w, const int64_t* row_index, int64_t x_rows, b200rec_stream_t stream) {
   TcBatch b;
   b.n = 1;
-  const int rc = tc_fill(b.prob[0], X, M, K, ldx, W, N, ldw, bias, row_scale, relu, Y, ldy, y_dtype, packed_w);
+  const int rc = tc_fill(b.prob[0], X, M, K, ldx, W, N, ldw, bias, row_scale, relu, Y, ldy, y_dtype, packed_w, row_index, x_rows);
   if (rc) return rc;
   if (M == 0) return B200REC_OK;
   b.tile_start[0] = 0;

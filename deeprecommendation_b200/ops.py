@@ -140,12 +140,20 @@ def set_gemm_engine(name: str):
     return prev
 
 
-def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_dtype=torch.float32, engine=None):
-    """out = act((x @ weight.T + bias) * row_scale[:, None]) — b200rec_linear / b200rec_linear_tc."""
-    _require_cuda(x, weight, bias, row_scale, out)
+def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_dtype=torch.float32, engine=None, row_index=None):
+    """out = act((x @ weight.T + bias) * row_scale[:, None]) — b200rec_linear / b200rec_linear_tc.
+    `row_index` (int64, M): use rows x[row_index] without materialising them (tensor-core engine; gathered first otherwise)."""
+    _require_cuda(x, weight, bias, row_scale, out, row_index)
     x, ldx = _row_major(x)
     w, ldw = _row_major(weight)
-    M, K = x.shape
+    x_rows = x.shape[0]
+    if row_index is not None:
+        row_index = row_index.contiguous().long()
+        eng = engine or _gemm_engine
+        if eng == 'simt' or not ((row_index.numel() >= TC_MIN_ROWS and x.shape[1] >= TC_MIN_K) or eng.endswith('!')) or x_rows * ldx >= 2 ** 32:
+            x, row_index = x.index_select(0, row_index), None
+            x, ldx = _row_major(x)
+    M, K = (x.shape if row_index is None else (row_index.numel(), x.shape[1]))
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f'linear: weight is {tuple(w.shape)}, input is {tuple(x.shape)}')
@@ -160,12 +168,12 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     ldy = out.stride(0) if M > 1 else max(N, out.stride(0))
     lib = L.lib()
     engine = engine or _gemm_engine
-    if engine != 'simt' and ((M >= TC_MIN_ROWS and K >= TC_MIN_K) or engine.endswith('!')) and M * ldx < 2 ** 32:
+    if engine != 'simt' and ((M >= TC_MIN_ROWS and K >= TC_MIN_K) or engine.endswith('!')) and (x_rows if row_index is not None else M) * ldx < 2 ** 32:
         mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
         packed = _packed_weight(w, ldw, mode) if _pack_weights else None
         with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
             L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
-                                          _dtype_code(out.dtype), mode, _ptr(packed), _stream()), 'linear_tc')
+                                          _dtype_code(out.dtype), mode, _ptr(packed), _ptr(row_index), x_rows, _stream()), 'linear_tc')
         return out
     ws_bytes = lib.b200rec_linear_workspace(M, N, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None

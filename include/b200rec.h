@@ -48,10 +48,12 @@ int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const floa
                    b200rec_stream_t stream);
 
 /* Same contract on the tensor cores (tcgen05.mma, TMEM accumulators; csrc/gemm_tc.cu).  mode B200REC_TC_TF32X3: fp32-parity
- * 3xTF32 split (rel <= 1e-5); B200REC_TC_BF16: bf16 operands (rel <= 1e-2).  Needs no workspace; meant for M >= ~1024. */
+ * 3xTF32 split (rel <= 1e-5); B200REC_TC_BF16: bf16 operands (rel <= 1e-2).  Needs no workspace; meant for M >= ~1024.
+ * `row_index` (M int64, or NULL): GEMM row m reads row row_index[m] of an X table of `x_rows` rows — the gather of
+ * `item_profiles[rated_items_ids]` (src/content_providers/dynamic_profiles_provider.py:70) fused into the projection. */
 int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
                       const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w,
-                      b200rec_stream_t stream);
+                      const int64_t* row_index, int64_t x_rows, b200rec_stream_t stream);
 /* Up to four such GEMMs sharing K and mode in ONE launch (candidate + rated-item projections, the two halves of
  * AttentionNet.0 — attention_ncf.py:150-151,176): problem q covers its own rows; fields as in b200rec_linear_tc. */
 typedef struct {

@@ -451,3 +451,33 @@ def test_user_partition_reduce_scheme_emulated_ranks(P):
             acc_items = acc_items + x_items
         comb = torch.cat([acc_items] + acc_users) / (L_ + 1)
     assert maxnorm_rel(comb, ref) < 1e-6
+
+
+def test_attention_forward_resident_equals_dense_forward():
+    """ResidentDynamicProvider + forward_resident (ids + CSR in, gather fused into the GEMM) == the dense contract, bit for bit"""
+    from deeprecommendation_b200 import ops
+    from deeprecommendation_b200.content_providers import ArrayDynamicProvider, ResidentDynamicProvider
+    from deeprecommendation_b200.neural_collaborative_filtering.datasets.dynamic_datasets import DynamicPointwiseDataset
+    users_raw, items_raw, ratings = synth.interactions_small(200, 3000, 60_000, seed=3)
+    _, u = synth.dense_ids(users_raw)
+    item_ids, it = synth.dense_ids(items_raw)
+    n_items = len(item_ids)
+    profiles = synth.item_profiles(n_items, seed=4, f_binary=300, f_dense=300)
+    row_ptr, idx, rr, _ = synth.user_rating_lists(u, it, ratings, 200)
+    args = (np.arange(n_items), profiles, np.arange(200), row_ptr, idx, rr)
+    dense, res = ArrayDynamicProvider(*args), ResidentDynamicProvider(*args, device=DEV)
+    kw = dict(item_dim=600, item_emb=128, user_emb=128, att_dense=128, mlp_dense_layers=[256, 128], dropout_rate=0.2)
+    m = _models().AttentionNCF(**kw).to(DEV).eval()
+    m.load_state_dict(synth.to_torch(synth.attention_ncf_weights(seed=9, **kw)))
+    pick = np.random.default_rng(0).permutation(len(u))[:256]
+    batch = [(int(a), int(b), 3.0) for a, b in zip(u[pick], it[pick])]
+    for engine in ('simt', 'tf32x3'):
+        prev = ops.set_gemm_engine(engine)
+        try:
+            with torch.no_grad():
+                out_d, _, _, _, att_d, _ = DynamicPointwiseDataset.do_forward(m, dense.collate_interacted_items(batch, False), DEV, True)
+                out_r, _, _, _, att_r, _ = DynamicPointwiseDataset.do_forward(m, res.collate_interacted_items(batch, False), DEV, True)
+        finally:
+            ops.set_gemm_engine(prev)
+        assert torch.equal(out_d, out_r), engine
+        assert torch.equal(att_d, att_r), engine

@@ -91,3 +91,28 @@ def test_checkpoint_round_trip_and_reference_keys():
     g = GraphNCF(**gkw)
     assert set(g.state_dict().keys()) == set(gsd.keys())
     g.load_state_dict(gsd)
+
+
+def test_resident_provider_collate_equals_dense_collate():
+    """device-resident form of the collate (row numbers + CSR) carries exactly the dense 6-tuple's information"""
+    from deeprecommendation_b200.content_providers import ResidentDynamicProvider
+    d, _, _ = load('collate')
+    n_items, n_users = d['profiles'].shape[0], len(d['mean_rating'])
+    args = (np.arange(n_items), d['profiles'], np.arange(n_users), d['row_ptr'], d['rated_idx'], d['rated_rating'])
+    dense, res = ArrayDynamicProvider(*args), ResidentDynamicProvider(*args, device='cpu')
+    batch = [(int(u), int(i), 3.5) for u, i in zip(d['batch_users'], d['batch_items'])]
+    a = dense.collate_interacted_items(batch, for_ranking=False)
+    b = res.collate_interacted_items(batch, for_ranking=False)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and torch.equal(a[5], b[5])
+    assert torch.equal(b[2].dense(), a[2]) and torch.equal(b[3].dense(), a[3])
+    assert torch.equal(b[4].to_dense(), a[4])
+    assert int((a[4] != 0).sum()) == b[4].col.numel()                     # exact zeros are absent from the CSR
+    # the dataset hands the resident form to model.forward_resident
+    seen = {}
+
+    class Probe(torch.nn.Module):
+        def forward_resident(self, cand, rated, um, return_attention_weights=False):
+            seen['shapes'] = (len(cand), len(rated), um.shape)
+            return torch.zeros(len(cand), 1)
+    out, y = DynamicPointwiseDataset.do_forward(Probe(), b, 'cpu')
+    assert out.shape == (len(batch), 1) and seen['shapes'] == (len(batch), a[3].shape[0], tuple(a[4].shape))
