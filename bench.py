@@ -530,13 +530,33 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
     resident = [tuple(t.to(dev) for t in b) for b in host]
     nb = len(resident)
 
-    def step(i):
+    def step_eager(i):
         with torch.no_grad():
             return model(*resident[i % nb])
 
+    from deeprecommendation_b200 import ops
+    from deeprecommendation_b200.graphed import GraphedForward
+    graphed = None
+    if not w.get('eager'):
+        try:                                   # all batches share one shape: one captured forward, inputs copied in
+            graphed = GraphedForward(lambda a, b: model(a, b), *resident[0])
+        except Exception as e:
+            w['graph_capture_error'] = repr(e)[:300]
+
+    def step(i):
+        if graphed is None:
+            return step_eager(i)
+        return graphed(*resident[i % nb])
+
     ms, launches = timed_steps(step, steps, warmup, dist, dev)
+    if graphed is not None:
+        l0 = ops.launch_count()
+        step_eager(0)
+        launches = (ops.launch_count() - l0) * steps
 
     def step_e2e(i):
+        if graphed is not None:
+            return graphed(*host[i % nb]).cpu()
         with torch.no_grad():
             xu, xi = (t.to(dev, non_blocking=True) for t in host[i % nb])
             return model(xu, xi).cpu()
@@ -549,7 +569,53 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
         step_e2e(i)
     torch.cuda.synchronize()
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
-    ops_ms = op_breakdown(step, min(steps, nb), 0)
+    # configs[0] names a TRAIN step: forward (dropout 0.2 active) + sum-MSE backward + Adam, gradients of every GEMM on K1a
+    train_ms, train_mode = None, 'eager'
+    try:
+        model.train()
+        ys = [torch.rand(BATCH, 1, device=dev) * 4.5 + 0.5 for _ in range(nb)]
+        sx = [t.clone() for t in resident[0]] + [ys[0].clone()]           # static inputs of the captured step
+
+        def one_step(opt):
+            opt.zero_grad(set_to_none=True)
+            loss = (model(sx[0], sx[1]) - sx[2]).square().sum()
+            loss.backward()
+            opt.step()
+
+        graph = None
+        if not w.get('eager'):
+            try:                                                          # whole train step (fwd + bwd + Adam) as ONE CUDA graph
+                opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        one_step(opt)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    one_step(opt)
+                train_mode = 'cuda_graph'
+            except Exception as e:
+                graph, train_mode = None, 'eager: ' + repr(e)[:200]
+                torch.cuda.synchronize()
+        if graph is None:
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+        def train_step(i):
+            for dst, src in zip(sx, resident[i % nb] + (ys[i % nb],)):
+                dst.copy_(src, non_blocking=True)
+            if graph is not None:
+                graph.replay()
+            else:
+                one_step(opt)
+
+        train_ms, _ = timed_steps(train_step, steps, warmup, dist, dev)
+    finally:
+        model.eval()
+        model.load_state_dict(w['sd'])
+    ops_ms = op_breakdown(step_eager, min(steps, nb), 0)
     lin = [(k, v) for k, v in ops_ms.items() if k[0] == 'linear']
     kms = float(np.mean([v[0] for _, v in lin])) if lin else 0.0
     alg_bytes = 4.0 * (BATCH * F + 128 * F + BATCH * 128)
@@ -558,7 +624,8 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
             'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('basic'),
             'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
-    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * F * 4, d2h=BATCH * 4, roofline=roof)
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * F * 4, d2h=BATCH * 4, roofline=roof, train_ms=train_ms, train_mode=train_mode,
+                launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
 def cpu_basic(w, repeats=10):
@@ -573,6 +640,24 @@ def cpu_basic(w, repeats=10):
             R.basic_ncf_forward(w['sd'], xu, xi)
             ts.append(time.perf_counter() - t0)
     return BATCH / float(np.median(ts)), torch.get_num_threads(), f'batch 0 ({BATCH} pairs, F={F}), median of {repeats} forwards, oracle/restatement.py'
+
+
+def cpu_basic_train(w, repeats=10):
+    """the reference's train step on host cores: forward (oracle port) + sum-MSE backward + Adam (NCF/train.py:99-105)"""
+    from oracle import restatement as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    xu, xi = (t.clone() for t in w['host'][0])
+    sd = {k: v.clone().requires_grad_(True) for k, v in w['sd'].items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-4)
+    y = torch.rand(BATCH, 1) * 4.5 + 0.5
+    ts = []
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        (R.basic_ncf_forward(sd, xu, xi) - y).square().sum().backward()
+        opt.step()
+        ts.append(time.perf_counter() - t0)
+    return BATCH / float(np.median(ts[1:]))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -774,18 +859,25 @@ def main():
             torch.cuda.empty_cache()
         if args.workload in ('all', 'basic'):
             w = build_basic(dev, rank)
+            w['eager'] = args.eager
             r = run_basic(w, args.steps, args.warmup, dist, dev, peaks)
             pairs = BATCH * args.steps * world
             entry = {'metric': 'scored user-item pairs/sec (BasicNCF fwd)', 'value': pairs / (r['ms'] * 1e-3), 'unit': 'pairs/s',
                      'ms_per_step': r['ms'] / args.steps, 'scaling': 'weak', 'dtype': 'f32',
                      'config': {'workload': 'configs[0] shape: BasicNCF(2094, 2094, 128, 128, [256]) forward, batches of 512 (user, item) '
-                                'profile pairs', 'l2': f'{len(w["host"])} rotating batches (275 MB) > L2'},
+                                'profile pairs', 'l2': f'{len(w["host"])} rotating batches (275 MB) > L2', 'launch_mode': r.get('launch_mode')},
                      'roofline': r['roofline'],
                      'e2e': {'value': pairs / (r['e2e_ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
                      'gpu_launches': r['launches']}
+            if r.get('train_ms'):
+                entry['train_step'] = {'value': pairs / (r['train_ms'] * 1e-3), 'unit': 'pairs/s', 'ms_per_step': r['train_ms'] / args.steps,
+                                       'launch_mode': r.get('train_mode'),
+                                       'what': 'forward (dropout 0.2) + sum-MSE backward + Adam on the same batches; forward and gradient GEMMs on K1a, '
+                                               'torch elementwise ops for masks / bias sums / the optimizer'}
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 v, cores, sample = cpu_basic(w)
                 entry['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+                entry['cpu_baseline']['train_step_value'] = cpu_basic_train(w)
             if result is None:
                 result = entry
             else:

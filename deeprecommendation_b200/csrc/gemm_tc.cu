@@ -282,7 +282,9 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     // ===================== producers =====================
     // k-blocks are walked from a per-CTA offset (wrapping around): all CTAs of a wave would otherwise ask L2 for the
     // SAME W tile at the same moment.  The set of products accumulated is unchanged.
-    constexpr int PF = (MODE == TC_BF16) ? 1 : 2;             // k-blocks of global loads in flight ahead of the store
+    // k-blocks of global loads in flight ahead of the store.  ncu (profiles/r01/ncu_full_gemm_tc_v3.txt, source page): 27 % of the
+    // stall samples sat on the first use of the loaded registers (long scoreboard) with 2 k-blocks ahead.
+    constexpr int PF = (MODE == TC_BF16) ? 1 : 2;    // (3 and 4 were measured: register spills, 5-100 % slower)
     TileAddr<MODE, EPL> aa, ab;
     aa.init(p.ldx, m0, p.M, warp, lane, p.row_index);
     if constexpr (!WPACK) ab.init(p.ldw, n0, p.N, warp, lane);

@@ -245,8 +245,9 @@ class _LinearFn(torch.autograd.Function):
             g = g * (y > 0)
         if rs is not None:
             g = g * rs[:, None]
-        gx = g @ w if ctx.needs_input_grad[0] else None
-        gw = g.t() @ x if ctx.needs_input_grad[1] else None
+        # both gradient GEMMs on the library's own kernels (K1a): gx = g·W, gW = gᵀ·x
+        gx = linear_raw(g, w.t()) if ctx.needs_input_grad[0] else None
+        gw = linear_raw(g.t(), x.t()) if ctx.needs_input_grad[1] else None
         gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb, None, None
 
@@ -304,16 +305,9 @@ def mlp_tower_raw(in0, in1, weights, biases, idx0=None, idx1=None):
     return out
 
 
-def _mlp_torch(x, weights, biases):
-    for l, (w, b) in enumerate(zip(weights, biases)):
-        if l > 0:
-            x = torch.relu(x)
-        x = torch.nn.functional.linear(x, w, b)
-    return x
-
-
 class _MlpTowerFn(torch.autograd.Function):
-    """forward: fused CUDA tower.  backward: recompute with torch ops (interim)."""
+    """forward: fused CUDA tower (K1b).  backward: the layer activations are recomputed with K1a (bias + ReLU fused) and
+    every gradient GEMM (g·W, gᵀ·h) runs on K1a too; only masks, bias sums and the row scatter are torch elementwise ops."""
 
     @staticmethod
     def forward(ctx, in0, in1, idx0, idx1, n_layers, *params):
@@ -326,24 +320,31 @@ class _MlpTowerFn(torch.autograd.Function):
     def backward(ctx, g):
         in0, in1, idx0, idx1, *params = ctx.saved_tensors
         n = ctx.n_layers
-        with torch.enable_grad():
-            a = in0.detach().requires_grad_(True)
-            b = in1.detach().requires_grad_(True) if in1 is not None else None
-            ps = [p.detach().requires_grad_(True) if p is not None else None for p in params]
-            xa = a[idx0] if idx0 is not None else a
-            if b is not None:
-                xb = b[idx1] if idx1 is not None else b
-                x = torch.cat((xa, xb), dim=1)
-            else:
-                x = xa
-            out = _mlp_torch(x, ps[:n], ps[n:])
-            wanted = [t for t in [a, b] + ps if t is not None]
-            grads = list(torch.autograd.grad(out, wanted, g, allow_unused=True))
-        it = iter(grads)
-        ga = next(it)
-        gb = next(it) if b is not None else None
-        gps = [next(it) if p is not None else None for p in ps]
-        return (ga, gb, None, None, None, *gps)
+        weights, biases = params[:n], params[n:]
+        xa = in0[idx0] if idx0 is not None else in0
+        if in1 is not None:
+            x = torch.cat((xa, in1[idx1] if idx1 is not None else in1), dim=1)
+        else:
+            x = xa
+        acts = [x.float().contiguous()]
+        for l in range(n - 1):                                         # the last layer's output is not needed
+            acts.append(linear_raw(acts[-1], weights[l], biases[l], relu=True))
+        g = g.contiguous().float()
+        gws, gbs = [None] * n, [None] * n
+        for l in range(n - 1, -1, -1):
+            if l < n - 1:
+                g = g * (acts[l + 1] > 0)
+            gws[l] = linear_raw(g.t(), acts[l].t())
+            if biases[l] is not None:
+                gbs[l] = g.sum(0)
+            g = linear_raw(g, weights[l].t())
+        E0 = in0.shape[1]
+        ga_rows, gb_rows = g[:, :E0], (g[:, E0:] if in1 is not None else None)
+        ga = torch.zeros_like(in0, dtype=torch.float32).index_add_(0, idx0, ga_rows) if idx0 is not None else ga_rows
+        gb = None
+        if in1 is not None:
+            gb = torch.zeros_like(in1, dtype=torch.float32).index_add_(0, idx1, gb_rows) if idx1 is not None else gb_rows
+        return (ga, gb, None, None, None, *gws, *gbs)
 
 
 def mlp_tower(in0, in1, weights, biases, idx0=None, idx1=None):
