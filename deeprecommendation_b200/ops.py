@@ -106,6 +106,7 @@ def _dtype_code(dt):
 # large M, FFMA for the small ones (a 128-row tile per CTA cannot fill 148 SMs below ~2k rows).
 _gemm_engine = 'simt'
 TC_MIN_ROWS = 2048
+SHORTK_MIN_ROWS = 4096  # below this a handful of 64x64 FFMA tiles is as fast as the persistent kernel's set-up
 TC_MIN_K = 512          # short-K GEMMs (the d x d GraphNCF transforms) are epilogue/latency-bound: FFMA is as fast there
 
 
@@ -168,6 +169,16 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     ldy = out.stride(0) if M > 1 else max(N, out.stride(0))
     lib = L.lib()
     engine = engine or _gemm_engine
+    if (engine in ('tf32x3', 'shortk!') and row_index is None and K <= 128 and K % 32 == 0 and N <= 128 and (M >= SHORTK_MIN_ROWS or engine == 'shortk!')
+            and ldx % 4 == 0 and x.data_ptr() % 16 == 0 and out.dtype == torch.float32):
+        # per-node d x d transforms (GraphNCF): persistent streaming kernel, W resident in shared memory
+        packed = _packed_weight(w, ldw, L.TC_TF32X3)
+        with torch.cuda.device(x.device), _timed('linear_shortk', (M, K, N)):
+            L.check(lib.b200rec_linear_shortk(_ptr(x), M, K, ldx, _ptr(packed), N, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
+                                              _stream()), 'linear_shortk')
+        return out
+    if engine == 'shortk!':
+        raise ValueError('linear: shape not supported by the short-K kernel')
     if engine != 'simt' and ((M >= TC_MIN_ROWS and K >= TC_MIN_K) or engine.endswith('!')) and (x_rows if row_index is not None else M) * ldx < 2 ** 32:
         mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
         packed = _packed_weight(w, ldw, mode) if _pack_weights else None

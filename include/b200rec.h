@@ -54,6 +54,11 @@ int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const floa
 int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
                       const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w,
                       const int64_t* row_index, int64_t x_rows, b200rec_stream_t stream);
+/* Persistent short-K variant for the per-node transforms of GraphNCF (K in {32,64,96,128}, N <= 128; csrc/node_gemm.cu):
+ * W stays in shared memory (`packed_w` = b200rec_pack_weights_tc(..., B200REC_TC_TF32X3)), row tiles are streamed, fp32 parity
+ * by the 3xTF32 split.  X rows 16-byte aligned (ldx % 4 == 0); Y fp32. */
+int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
+                          const float* row_scale, int relu, float* Y, int64_t ldy, b200rec_stream_t stream);
 /* Up to four such GEMMs sharing K and mode in ONE launch (candidate + rated-item projections, the two halves of
  * AttentionNet.0 — attention_ncf.py:150-151,176): problem q covers its own rows; fields as in b200rec_linear_tc. */
 typedef struct {

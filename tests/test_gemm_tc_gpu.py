@@ -56,3 +56,26 @@ def test_linear_tc_real_profiles():
     y = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='tf32x3!')
     simt = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='simt')
     assert maxnorm_rel(y, ref) < 1e-5 and maxnorm_rel(simt, ref) < 1e-5
+
+
+@pytest.mark.parametrize('M,K,N', [(5000, 128, 128), (130, 64, 64), (100_000, 128, 128), (777, 96, 100), (20_000, 32, 8), (1, 128, 128),
+                                   (162_541, 128, 128)])
+def test_linear_shortk_persistent_fp32_parity(M, K, N):
+    """K1c (csrc/node_gemm.cu): persistent short-K tcgen05 GEMM of the per-node transforms, 3xTF32 -> fp32 tolerance"""
+    from deeprecommendation_b200 import ops
+    x, w, b, s = _case(M, K, N, M + K + 7)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    y = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='shortk!')
+    assert y.shape == (M, N) and maxnorm_rel(y, ref) < 1e-5
+    # row scale + relu, strided input (column slice of a wider buffer) and strided output
+    xw = torch.zeros(M, K + 32, device='cuda')
+    xw[:, 16:16 + K] = x.cuda()
+    out = torch.full((M, N + 8), 3.0, device='cuda')
+    ops.linear_raw(xw[:, 16:16 + K], w.cuda(), None, s.cuda(), True, out=out[:, 4:4 + N], engine='shortk!')
+    ref2 = (torch.nn.functional.linear(x.double(), w.double()) * s.double()[:, None]).relu()
+    assert maxnorm_rel(out[:, 4:4 + N], ref2) < 1e-5
+    assert torch.all(out[:, :4] == 3.0) and torch.all(out[:, 4 + N:] == 3.0)
+    # the automatic dispatch of the default tensor-core engine picks it for large M and gives the same bits
+    if M >= ops.SHORTK_MIN_ROWS:
+        y2 = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='tf32x3')
+        assert torch.equal(y, y2)

@@ -9,7 +9,7 @@ flush = torch.empty(256 * 1024 * 1024 // 4, device='cuda')
 out = {}
 for M, K, N in SHAPES:
     x = torch.randn(M, K, device='cuda'); w = torch.randn(N, K, device='cuda') / K ** 0.5; b = torch.randn(N, device='cuda')
-    for eng in ('simt', 'tf32x3!', 'bf16!'):
+    for eng in ('simt', 'tf32x3!', 'bf16!') + (('shortk!',) if K <= 128 else ()):
         ts = []
         for r in range(7):
             flush.zero_()
