@@ -8,6 +8,8 @@
 // through mbarriers: 8 producer warps (global fp32 -> TF32 hi/lo -> swizzled smem ring), one MMA warp (3xTF32: hi·hi into a
 // main accumulator, hi·lo + lo·hi into a second one), 4 epilogue warps draining the previous tile's accumulators from TMEM
 // (two accumulator pairs = all 512 columns) while the next tile is produced.  fp32 parity: the same split as gemm_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200rec {
@@ -16,6 +18,7 @@ constexpr int NT_PRODUCERS = 256, NT_EPI = 128, NT_THREADS = NT_PRODUCERS + NT_E
 constexpr int NT_TILE = 128 * 128;          // 128 rows x 128 bytes (32 TF32 of K)
 constexpr int NT_STAGE = 2 * NT_TILE;       // hi + lo planes
 constexpr int NT_NS = 2;                    // ring stages
+constexpr int NT_STG_LD = 36;               // staging row pitch in floats (144 B: conflict-free 128-bit accesses)
 
 __device__ __forceinline__ uint32_t nt_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void nt_mbar_init(uint64_t* bar, uint32_t count) {
@@ -72,6 +75,7 @@ struct NodeGemmParams {
   const unsigned char* Wp;             // b200rec_pack_weights_tc(TF32X3) of W (N, K): [k-block][hi | lo] tiles of 16 KB
   const float* bias; const float* row_scale; int relu;
   float* Y; long long ldy;
+  int dbg;                             // experiments (B200REC_NT_DBG): 1 = no stores, 2 = no MMA, 4 = no TMEM loads
 };
 
 template <int NKB>
@@ -82,6 +86,7 @@ node_gemm_kernel(NodeGemmParams p) {
   unsigned char* sm_w = sm;                                   // NKB * 32 KB
   unsigned char* sm_ring = sm + NKB * NT_STAGE;               // NT_NS * 32 KB
   float* sm_bias = reinterpret_cast<float*>(sm_ring + NT_NS * NT_STAGE);   // 128 floats
+  float* sm_stage = sm_bias + 128;                                         // 4 warps x 32 rows x NT_STG_LD floats
   __shared__ __align__(8) uint64_t w_bar, a_full[NT_NS], a_empty[NT_NS], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
@@ -168,7 +173,6 @@ node_gemm_kernel(NodeGemmParams p) {
       nt_tc_after();
       const int row = tile * 128 + e * 32 + lane;
       const float rs = (p.row_scale != nullptr && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
-      float* dst = p.Y + (long long)row * p.ldy;
 #pragma unroll
       for (int cg = 0; cg < 4; ++cg) {
         uint32_t a[32], b[32];
@@ -198,23 +202,38 @@ node_gemm_kernel(NodeGemmParams p) {
           nt_tc_before();
           nt_mbar_arrive(&acc_empty[acc]);
         }
-        if (row < p.M) {
+        // through a per-warp staging tile so that the global stores are full 128-byte lines: a warp instruction writes
+        // 4 rows x 32 columns instead of 32 rows x 4 columns (measured: 58 -> 36 us without the 16-byte-per-row stores)
+        float* stg = sm_stage + e * (32 * NT_STG_LD);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = cg * 32 + j;
-            if (n < p.N) {
-              float o[4];
+        for (int j = 0; j < 32; j += 4) {
+          const int n = cg * 32 + j;
+          float o[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float v = (__uint_as_float(a[j + q]) + __uint_as_float(b[j + q]) + sm_bias[n + q]) * rs;
-                o[q] = p.relu ? fmaxf(v, 0.f) : v;
+          for (int q = 0; q < 4; ++q) {
+            const float v = (__uint_as_float(a[j + q]) + __uint_as_float(b[j + q]) + sm_bias[n + q]) * rs;
+            o[q] = p.relu ? fmaxf(v, 0.f) : v;
+          }
+          *reinterpret_cast<float4*>(stg + lane * NT_STG_LD + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        if (!(p.dbg & 1)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3), cc = (lane & 7) * 4;
+            const int grow = tile * 128 + e * 32 + r, n = cg * 32 + cc;
+            if (grow < p.M && n < p.N) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + r * NT_STG_LD + cc);
+              float* d = p.Y + (long long)grow * p.ldy + n;
+              if (n + 3 < p.N && (((uintptr_t)d & 15) == 0)) *reinterpret_cast<float4*>(d) = v;
+              else {
+                const float o[4] = {v.x, v.y, v.z, v.w};
+                for (int q = 0; q < 4 && n + q < p.N; ++q) d[q] = o[q];
               }
-              if (n + 3 < p.N) *reinterpret_cast<float4*>(dst + n) = make_float4(o[0], o[1], o[2], o[3]);
-              else
-                for (int q = 0; q < 4 && n + q < p.N; ++q) dst[n + q] = o[q];
             }
           }
         }
+        __syncwarp();
       }
     }
   } else {
@@ -239,6 +258,7 @@ node_gemm_kernel(NodeGemmParams p) {
           for (int ks = 0; ks < 4; ++ks) {                       // 8 TF32 (32 bytes) of K per MMA
             const uint32_t off = (uint32_t)ks * 32u;
             const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
+            if (p.dbg & 2) continue;
             nt_umma_tf32(d_main, nt_desc(a_hi + off), nt_desc(w_hi + off), idesc, first);     // hi · hi
             nt_umma_tf32(d_cross, nt_desc(a_hi + off), nt_desc(w_lo + off), idesc, first);    // hi · lo
             nt_umma_tf32(d_cross, nt_desc(a_lo + off), nt_desc(w_hi + off), idesc, 1u);       // lo · hi
@@ -261,7 +281,7 @@ node_gemm_kernel(NodeGemmParams p) {
 
 template <int NKB>
 static int nt_launch(const NodeGemmParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)NKB * NT_STAGE + NT_NS * NT_STAGE + 512 + 1024;
+  const size_t smem = (size_t)NKB * NT_STAGE + NT_NS * NT_STAGE + 512 + 4 * 32 * NT_STG_LD * 4 + 1024;
   static bool configured = false;
   if (!configured) {
     B200REC_CUDA(cudaFuncSetAttribute(node_gemm_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -292,6 +312,10 @@ extern "C" int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64
   NodeGemmParams p;
   p.X = X; p.ldx = ldx; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.Wp = (const unsigned char*)packed_w;
   p.bias = bias; p.row_scale = row_scale; p.relu = relu; p.Y = Y; p.ldy = ldy;
+  {
+    const char* e = getenv("B200REC_NT_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (K / 32) {
     case 1: return nt_launch<1>(p, st);

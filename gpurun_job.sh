@@ -1,8 +1,2 @@
-mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_models_gpu.py -m gpu -q -x 2>&1 | tail -2
-timeout 300 python bench.py --workload graph --no-cpu-baseline > gpurun_out/b14_graph.json 2> gpurun_out/b14_graph.err; echo rc=$?; tail -2 gpurun_out/b14_graph.err
-python - <<'P'
-import json
-d=json.loads(open('gpurun_out/b14_graph.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['roofline']['op_ms_per_step'])
-P
+C="python tools/gemm_bench.py"
+$C > gpurun_out/plain_gb.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:node_gemm_kernel -s 2 -c 1 -f -o gpurun_out/prof_nodegemm_v1 $C > gpurun_out/ncu_ng.log 2>&1; echo "ncu rc=$?"
