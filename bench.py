@@ -292,7 +292,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     elif name == 'attention_pool':
         nnz_mean = float(np.mean(w['nnz']))
         alg_bytes = nnz_mean * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)
-        kname = 'um_compact_kernel + attention_pool_csr_kernel (K2)'
+        kname = 'um_compact_kernel + attention_wseg_tma_kernel + attention_merge_kernel (K2)'
     else:
         alg_bytes, kname = 0.0, name
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
@@ -301,6 +301,23 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
             'peak_source': peaks['src'],
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
+    # the second roofline kernel of this workload, whichever of K1a / K2 is not the dominant one (same formulas)
+    other = []
+    for (n2, m2), (k2, _) in ops_ms.items():
+        if n2 == name:
+            continue
+        if n2 == 'attention_pool':
+            ab = float(np.mean(w['nnz'])) * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)
+            other.append({'kernel': 'um_compact_kernel + attention_wseg_tma_kernel + attention_merge_kernel (K2; tables L2-resident at this size)',
+                          'kernel_ms': round(k2, 4), 'algorithmic_bytes': int(ab), 'achieved': round(ab / (k2 * 1e-3) / 1e9, 1), 'unit': 'GB/s',
+                          'frac': round(ab / (k2 * 1e-3) / 1e9 / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention_pool')})
+        elif n2 in ('linear_tc', 'linear_tc_batch') and m2[1] >= 512:
+            ab = 4.0 * (m2[0] * m2[1] + m2[2] * m2[1] + m2[0] * m2[2])
+            other.append({'kernel': f'gemm_tc_kernel (K1a {m2[0]}x{m2[1]}->{m2[2]})', 'kernel_ms': round(k2, 4), 'algorithmic_bytes': int(ab),
+                          'achieved': round(ab / (k2 * 1e-3) / 1e9, 1), 'unit': 'GB/s', 'frac': round(ab / (k2 * 1e-3) / 1e9 / peaks['hbm_gbs'], 4),
+                          'traffic': _traffic('attention')})
+    if other:
+        roof['other_kernels'] = other
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4, roofline=roof, I_mean=I_mean,
                 nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res,
                 launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
@@ -478,26 +495,107 @@ def run_k3_hbm_regime(dev, peaks, n_users=8_000_000, n_items=1_000_000, n_edges=
     N, E2 = index.num_nodes, index.e1 + index.e2
     t = torch.randn(N, d, device=dev)
     x_next, acc = torch.empty(N, d, device=dev), torch.zeros(N, d, device=dev)
-    ts = []
-    for r in range(reps + 2):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.spmm_raw(index, t, w=index.w, dinv=index.dinv, x_next=x_next, acc_in=acc, acc_out=acc, acc_scale=1.0)
-        b.record()
-        torch.cuda.synchronize()
-        if r >= 2:
-            ts.append(a.elapsed_time(b))
-    ms = float(np.median(ts))
+
+    def timed(**kw):
+        ts = []
+        for r in range(reps + 2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.spmm_raw(index, t, w=index.w, dinv=index.dinv, **kw)
+            b.record()
+            torch.cuda.synchronize()
+            if r >= 2:
+                ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    ms = timed(x_next=x_next)                                               # the layer as SURVEY.md §8d counts it: one (N, d) output
+    ms_fused = timed(x_next=x_next, acc_in=acc, acc_out=acc, acc_scale=1.0)     # + the fused running mean (reads and writes one more (N, d))
     alg = E2 * 8 + E2 * d * 4 + N * d * 4                   # SURVEY.md §8d K3, features larger than L2
     achieved = alg / (ms * 1e-3) / 1e9
+    alg_fused = alg + 2 * N * d * 4
+    probe = _gather_probe()
+    roof = {'bound': 'hbm', 'kernel': 'spmm_chunk_kernel + spmm_fixup_kernel (K3)', 'achieved': round(achieved, 1), 'peak': peaks['hbm_gbs'],
+            'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('k3_hbm'),
+            'peak_source': peaks['src'], 'kernel_ms': round(ms, 4), 'algorithmic_bytes': int(alg),
+            'with_fused_combine': {'kernel_ms': round(ms_fused, 4), 'algorithmic_bytes': int(alg_fused),
+                                   'achieved': round(alg_fused / (ms_fused * 1e-3) / 1e9, 1), 'frac': round(alg_fused / (ms_fused * 1e-3) / 1e9 / peaks['hbm_gbs'], 4)}}
+    if probe and probe.get(f'gather_{d * 4}B_GBs'):
+        roof['random_gather_ceiling'] = {'GB/s': probe[f'gather_{d * 4}B_GBs'], 'frac_of_it': round(achieved / probe[f'gather_{d * 4}B_GBs'], 4),
+                                         'what': f'tools/gather_probe.cu: independent random {d * 4}-byte rows of a 4 GiB table, no arithmetic, same GPU, same run'}
     out = {'metric': 'K3 SpMM directed-edge messages/sec, HBM regime (features >> L2)', 'value': E2 / (ms * 1e-3), 'unit': 'edges/s',
            'ms_per_step': ms, 'dtype': 'f32',
            'config': {'workload': f'one layer of K3 on nU={n_users}, nI={n_items}, E={n_edges} (2E={E2} directed), d={d}: one GPU share of '
                       f'configs[4]; features {N * d * 4 / 1e9:.2f} GB, CSR {E2 * 8 / 1e9:.2f} GB', 'l2': 'working set >> L2'},
-           'roofline': {'bound': 'hbm', 'kernel': 'spmm_chunk_kernel (K3)', 'achieved': round(achieved, 1), 'peak': peaks['hbm_gbs'],
-                        'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('k3_hbm'),
-                        'peak_source': peaks['src'], 'kernel_ms': round(ms, 4), 'algorithmic_bytes': int(alg)}}
+           'roofline': roof}
     del graph, index, t, x_next, acc
+    torch.cuda.empty_cache()
+    return out
+
+
+_PROBE = None
+
+
+def _gather_probe():
+    """tools/gather_probe.cu (prebuilt by __graft_entry__.build()): the random-row gather bandwidth of this GPU, run once per bench"""
+    global _PROBE
+    if _PROBE is None:
+        exe = os.path.join(ROOT, 'tools', 'build', 'gather_probe')
+        _PROBE = {}
+        if os.path.exists(exe):
+            try:
+                r = subprocess.run([exe, '4', '48'], capture_output=True, text=True, timeout=120)
+                _PROBE = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:
+                _PROBE = {'error': repr(e)[:200]}
+    return _PROBE
+
+
+def run_k2_hbm_regime(dev, peaks, n_items=4_000_000, n_rows=8192, H=128, reps=5, seed=5):
+    """K2 where its roofline formula measures HBM (SURVEY.md §8d asks for it): the Pr / Q tables (2 x 2 GB) >> L2, ragged rated lists
+    with the config-2 length law (log-normal, mean ~165, clipped to [20, 2698]) over a 4 M-item catalogue, CSR front-end."""
+    from deeprecommendation_b200 import ops
+    from deeprecommendation_b200 import _lib as L
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lens = torch.exp(torch.randn(n_rows, device=dev, generator=g) * 1.0 + 4.6).clamp_(20, 2698).long()
+    row_ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(lens, 0)
+    nnz = int(row_ptr[-1])
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), lens)
+    col = torch.randint(0, n_items, (nnz,), device=dev, generator=g)
+    col = torch.sort(rows * n_items + col).values % n_items                  # ascending inside a row, like the reference's collate
+    val = (torch.randint(1, 11, (nnz,), device=dev, generator=g).float() * 0.5 - 2.75)
+    csr = (row_ptr.int(), col.int(), val)
+    Pr, Q = torch.randn(n_items, H, device=dev), torch.randn(n_items, H, device=dev)
+    Pc, a2 = torch.randn(n_rows, H, device=dev), torch.randn(H, device=dev)
+    a20, bU = torch.zeros(1, device=dev), torch.zeros(H, device=dev)
+    mx = int(lens.max())
+    ts = []
+    inner = 8                      # calls per timed region, queued back to back: the ~50 us of host-side launch work per call hides behind the GPU
+    for r in range(reps + 2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(inner):
+            ops.attention_pool_raw(Pc, Pr, Q, mode=L.ATT_NET, a2=a2, a20=a20, bU=bU, csr=csr, max_row_nnz=mx)
+        b.record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            ts.append(a.elapsed_time(b) / inner)
+    ms = float(np.median(ts))
+    alg = nnz * (2 * H * 4 + 8) + n_rows * (H * 4 + 4)                       # SURVEY.md §8d, K2
+    achieved = alg / (ms * 1e-3) / 1e9
+    probe = _gather_probe()
+    roof = {'bound': 'hbm', 'kernel': 'att_worklist_kernel + attention_wseg_tma_kernel + attention_merge_kernel (K2, CSR front-end)', 'achieved': round(achieved, 1),
+            'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('k2_hbm'),
+            'peak_source': peaks['src'], 'kernel_ms': round(ms, 4), 'algorithmic_bytes': int(alg)}
+    if probe and probe.get(f'gather_{H * 4}B_GBs'):
+        roof['random_gather_ceiling'] = {'GB/s': probe[f'gather_{H * 4}B_GBs'], 'frac_of_it': round(achieved / probe[f'gather_{H * 4}B_GBs'], 4),
+                                         'what': f'tools/gather_probe.cu: independent random {H * 4}-byte rows of a 4 GiB table, no arithmetic, same GPU, same run'}
+    out = {'metric': 'K2 attention pooling (candidate, rated-item) interactions/sec, HBM regime (tables >> L2)', 'value': nnz / (ms * 1e-3),
+           'unit': 'interactions/s', 'ms_per_step': ms, 'dtype': 'f32',
+           'config': {'workload': f'K2 on {n_rows} candidate rows x {n_items} catalogue items, {nnz} non-zeros (mean {nnz / n_rows:.0f}, max {mx} per row), '
+                      f'H=U={H}: Pr and Q tables {2 * n_items * H * 4 / 1e9:.1f} GB', 'l2': 'tables >> L2, random rows'},
+           'roofline': roof}
+    del Pr, Q, Pc, csr, col, val, rows
     torch.cuda.empty_cache()
     return out
 
@@ -794,7 +892,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs'])
+    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs', 'k3hbm', 'k2hbm'])
     ap.add_argument('--graph-scale', type=float, default=1.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
@@ -937,11 +1035,18 @@ def main():
                 also.append(entry)
             del w
             torch.cuda.empty_cache()
-    if args.workload == 'all' and world == 1 and not args.skip_hbm_regime:
+    if args.workload in ('all', 'k3hbm') and world == 1 and not args.skip_hbm_regime:
         try:
             also.append(run_k3_hbm_regime(dev, peaks))
         except Exception as e:
             also.append({'metric': 'K3 HBM regime', 'error': repr(e)[:300]})
+    if args.workload in ('all', 'k2hbm') and world == 1 and not args.skip_hbm_regime:
+        try:
+            also.append(run_k2_hbm_regime(dev, peaks))
+        except Exception as e:
+            also.append({'metric': 'K2 HBM regime', 'error': repr(e)[:300]})
+    if result is None:
+        result, also = also[0], also[1:]
     result.setdefault('config', {})['gemm_engine'] = args.gemm
     for k, v in (('n_gpus', world), ('steps', args.steps), ('warmup', args.warmup), ('higher_is_better', True), ('vs_baseline', None),
                  ('data', 'synthetic')):

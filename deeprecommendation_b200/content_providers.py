@@ -122,6 +122,7 @@ class SparseUserMatrix:
         self.col = pin(torch.from_numpy(np.ascontiguousarray(col, dtype=np.int32)))
         self.val = pin(torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)))
         self.shape = tuple(shape)
+        self.max_row_nnz = int(np.max(np.diff(np.asarray(row_ptr)))) if len(row_ptr) > 1 else 0     # known on the host: sizes K2's segment grid
 
     def to_dense(self) -> torch.Tensor:
         um = torch.zeros(self.shape, dtype=torch.float32)

@@ -33,6 +33,18 @@ int b200rec_num_sms() {
   return cached[dev];
 }
 
+long long b200rec_l2_bytes() {
+  static long long cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 126ll << 20;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrL2CacheSize, dev) != cudaSuccess || n <= 0) n = 126 << 20;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 extern "C" const char* b200rec_last_error(void) { return g_err; }
 extern "C" int b200rec_version(void) { return B200REC_VERSION; }
 extern "C" int b200rec_sm_count(void) { return b200rec_num_sms(); }

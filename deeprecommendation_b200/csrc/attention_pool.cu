@@ -24,11 +24,15 @@
 // the reference's dense (B, I) `user_matrix` on the fly through a per-warp shared-memory queue (drop-in entry;
 // exact 0.0 means "unrated", attention_ncf.py:158,192).
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
 namespace b200rec {
 
+static int g_att_path = 0;       // b200rec_attention_pool_set_path: 0 auto, 1 register-staged gathers, 2 TMA-staged gathers
 constexpr int ATT_WARPS = 8;      // one CTA per candidate row; the row's non-zeros are split over the warps
 enum { MODE_NET = 0, MODE_DOT = 1 };
 
@@ -52,6 +56,37 @@ struct AttParams {
   float score_scale;      // message dropout: kept scores are scaled by 1/(1-p) (:187)
   long long ldPr, ldQ;
 };
+
+
+// ---- TMA / mbarrier helpers (bulk-copy row gathers of the warp-segment kernel) -----------------------------------
+__device__ __forceinline__ uint32_t att_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void att_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(att_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void att_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(att_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void att_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "ATT_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra ATT_DONE_%=;\n\t"
+      "bra ATT_WAIT_%=;\n\t"
+      "ATT_DONE_%=:\n\t}" ::"r"(att_smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared; completion = transaction bytes on the mbarrier.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void att_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(att_smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(att_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void att_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 4 consecutive table elements from SHARED memory as fp32
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 lds4(const __nv_bfloat16* p) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+}
 
 template <int HV, int UV, int MODE, typename T>
 struct RowCore {
@@ -83,45 +118,9 @@ struct RowCore {
     a20 = (MODE == MODE_NET && p.a20) ? __ldg(p.a20) : 0.f;
   }
 
-  // lane j holds non-zero j of this batch (col < 0 beyond `count`)
-  __device__ void batch(int my_col, float my_val, int count) {
-    const T* __restrict__ Pr = reinterpret_cast<const T*>(p.Pr);
-    const T* __restrict__ Q = reinterpret_cast<const T*>(p.Q);
-    float v[32];
-#pragma unroll
-    constexpr int LB = (HV == 1 && UV == 1) ? 16 : 8;     // row gathers in flight per warp
-#pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += LB) {
-      if (j0 < count) {
-        float4 pr[LB][HV];
-#pragma unroll
-        for (int jj = 0; jj < LB; ++jj) {
-          const int c = __shfl_sync(FULL, my_col, j0 + jj);
-#pragma unroll
-          for (int hv = 0; hv < HV; ++hv) {
-            const int h = lane * 4 + hv * 128;
-            pr[jj][hv] = (c >= 0 && h < p.H) ? ld4(Pr + (long long)c * p.ldPr + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int jj = 0; jj < LB; ++jj) {
-          float s = 0.f;
-#pragma unroll
-          for (int hv = 0; hv < HV; ++hv) {
-            const float r[4] = {pr[jj][hv].x, pr[jj][hv].y, pr[jj][hv].z, pr[jj][hv].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (MODE == MODE_NET) s = fmaf(a2[hv][e], fmaxf(pc[hv][e] + r[e], 0.f), s);
-              else s = fmaf(pc[hv][e], r[e], s);
-            }
-          }
-          v[j0 + jj] = s;
-        }
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < LB; ++jj) v[j0 + jj] = 0.f;
-      }
-    }
+  // scores of one batch (lane-partial dot products in v[0..31]) -> online-softmax state update; returns this lane's
+  // pooling weight = attention numerator x centred rating (:212)
+  __device__ __forceinline__ float softmax_update(float (&v)[32], int my_col, float my_val, int count) {
     // butterfly reduce-scatter: after the last step lane j holds sum over lanes of v[j]
 #pragma unroll
     for (int k = 16; k >= 1; k >>= 1) {
@@ -164,7 +163,49 @@ struct RowCore {
         for (int e = 0; e < 4; ++e) acc[uv][e] *= scale;
       m = m_new;
     }
-    const float wgt = pj * my_val;                    // attention x centred rating (:212)
+    return pj * my_val;
+  }
+
+  // lane j holds non-zero j of this batch (col < 0 beyond `count`)
+  __device__ void batch(int my_col, float my_val, int count) {
+    const T* __restrict__ Pr = reinterpret_cast<const T*>(p.Pr);
+    const T* __restrict__ Q = reinterpret_cast<const T*>(p.Q);
+    float v[32];
+#pragma unroll
+    constexpr int LB = (HV == 1 && UV == 1) ? 16 : 8;     // row gathers in flight per warp
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += LB) {
+      if (j0 < count) {
+        float4 pr[LB][HV];
+#pragma unroll
+        for (int jj = 0; jj < LB; ++jj) {
+          const int c = __shfl_sync(FULL, my_col, j0 + jj);
+#pragma unroll
+          for (int hv = 0; hv < HV; ++hv) {
+            const int h = lane * 4 + hv * 128;
+            pr[jj][hv] = (c >= 0 && h < p.H) ? ld4(Pr + (long long)c * p.ldPr + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < LB; ++jj) {
+          float s = 0.f;
+#pragma unroll
+          for (int hv = 0; hv < HV; ++hv) {
+            const float r[4] = {pr[jj][hv].x, pr[jj][hv].y, pr[jj][hv].z, pr[jj][hv].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (MODE == MODE_NET) s = fmaf(a2[hv][e], fmaxf(pc[hv][e] + r[e], 0.f), s);
+              else s = fmaf(pc[hv][e], r[e], s);
+            }
+          }
+          v[j0 + jj] = s;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < LB; ++jj) v[j0 + jj] = 0.f;
+      }
+    }
+    const float wgt = softmax_update(v, my_col, my_val, count);
 #pragma unroll
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += LB) {
@@ -190,6 +231,40 @@ struct RowCore {
             acc[uv][2] = fmaf(w[jj], q[jj][uv].z, acc[uv][2]);
             acc[uv][3] = fmaf(w[jj], q[jj][uv].w, acc[uv][3]);
           }
+      }
+    }
+  }
+
+  // The same batch with the 32 Pr rows and 32 Q rows already in shared memory (landed there by TMA bulk copies: one
+  // memory latency per batch instead of four register-staged gather rounds).  HV == UV == 1 only; sPr / sQ rows are 128
+  // elements apart; `valid` = ballot of (my_col >= 0): rows of invalid lanes were not copied and are never read.
+  __device__ void batch_smem(int my_col, float my_val, int count, const T* sPr, const T* sQ, unsigned valid) {
+    static_assert(HV == 1 && UV == 1, "shared-memory batches are for H, U <= 128");
+    float v[32];
+    const int h = lane * 4;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float s = 0.f;
+      if (((valid >> j) & 1u) && h < p.H) {
+        const float4 r4 = lds4(sPr + j * 128 + h);
+        const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (MODE == MODE_NET) s = fmaf(a2[0][e], fmaxf(pc[0][e] + r[e], 0.f), s);
+          else s = fmaf(pc[0][e], r[e], s);
+        }
+      }
+      v[j] = s;
+    }
+    const float wgt = softmax_update(v, my_col, my_val, count);
+    const int u = lane * 4;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float wj = __shfl_sync(FULL, wgt, j);
+      if (((valid >> j) & 1u) && u < p.U) {
+        const float4 q = lds4(sQ + j * 128 + u);
+        acc[0][0] = fmaf(wj, q.x, acc[0][0]); acc[0][1] = fmaf(wj, q.y, acc[0][1]);
+        acc[0][2] = fmaf(wj, q.z, acc[0][2]); acc[0][3] = fmaf(wj, q.w, acc[0][3]);
       }
     }
   }
@@ -270,85 +345,204 @@ attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const in
 }
 
 // ---- segment-parallel ragged kernel -------------------------------------------------------------------------
-// Rows are heavy-tailed (mean ~550 non-zeros per candidate at config 2, max ~2.7k): with one CTA per row the kernel
-// lasts as long as its longest row.  Here a CTA owns ONE SEGMENT of at most ATT_SEG non-zeros of one row (grid =
-// B x ceil(I / ATT_SEG), CTAs beyond a row's length exit at once), writes its (max, denominator, pooled vector) to a
-// partial slot, and a small second kernel merges a row's partials, adds b_U and normalises the attention weights.
-constexpr int ATT_SEG = 512;
+// Rows are heavy-tailed (config 2: mean ~550 non-zeros per candidate, max ~2.7k; a big catalogue: mean ~160), so neither a CTA
+// per row (lasts as long as its longest row) nor a CTA per 512-non-zero segment (v3: 5 of 8 warps idle at a barrier on the typical
+// short row — ncu on the HBM-regime shape: 15 resident warps per SM of which ~6 live, 0.375 of the HBM roofline) keeps the
+// memory system busy.  Here the unit is ONE WARP per segment of <= ATT_WSEG non-zeros: a tiny kernel (or the tail of the
+// compaction kernel) writes a dense work list of (row, segment) items — list positions come from an atomic counter, which only
+// orders the list, never a value — and a persistent grid of warps strides over it.  Every resident warp is live, there is no
+// block-level barrier and no shared memory; each item leaves a (max, denominator, pooled vector) partial, and the merge kernel
+// combines a row's partials in segment order (bit-reproducible), adds b_U and normalises the attention weights.
+constexpr int ATT_WSEG = 64;
 
-template <int HV, int UV, int MODE, typename T>
-__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 2 : 1)
-attention_seg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
-                     const int* __restrict__ row_nnz, long long padded_stride, float* __restrict__ partials, int nseg_max) {
-  __shared__ float s_m[ATT_WARPS], s_l[ATT_WARPS];
-  __shared__ __align__(16) float s_acc[ATT_WARPS * UV * 128];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x, seg = blockIdx.y;
-  const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
-  const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
-  const long long seg_start = start + (long long)seg * ATT_SEG;
-  if (seg_start >= end) return;                                    // (whole CTA) this row has fewer segments
-  const long long seg_end = min(end, seg_start + ATT_SEG);
-  RowCore<HV, UV, MODE, T> core(p, lane, b);
-  const int blocks = (int)((seg_end - seg_start + 31) >> 5);
-  const int bpw = (blocks + ATT_WARPS - 1) / ATT_WARPS;
-  const long long my_start = seg_start + (long long)warp * bpw * 32, my_end = min(seg_end, my_start + (long long)bpw * 32);
-  for (long long k0 = my_start; k0 < my_end; k0 += 32) {
-    const long long k = k0 + lane;
-    int c = -1;
-    float v = 0.f;
-    if (k < my_end) { c = __ldg(col + k); v = __ldg(val + k); }
-    const bool valid = (k < my_end) && (v != 0.f);
-    core.batch(valid ? c : -1, valid ? v : 0.f, (int)min(32LL, my_end - k0));
+struct AttWork {
+  int* counter;        // [0] = number of items
+  int* seg_base;       // (B): first partial slot of the row
+  int2* items;         // (row, segment)
+  float* partials;     // (n_items, U + 4): m, l, -, -, acc[U]
+  int max_items;       // capacity of items / partials (a max_row_nnz hint that is not a true bound must not overrun them)
+};
+
+__device__ __forceinline__ void att_emit_items(const AttWork& w, int b, int len, int tid, int nthreads, int* s_base) {
+  const int n = (len + ATT_WSEG - 1) / ATT_WSEG;
+  if (tid == 0) {
+    const int base = n > 0 ? atomicAdd(w.counter, n) : 0;
+    w.seg_base[b] = base;
+    *s_base = base;
   }
-  core.export_state(s_m, s_l, s_acc, warp);
   __syncthreads();
-  // merge the 8 warps -> one partial (m, l, acc[U]) for this segment
-  float M = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < ATT_WARPS; ++w) M = fmaxf(M, s_m[w]);
-  float scale[ATT_WARPS], Lsum = 0.f;
-#pragma unroll
-  for (int w = 0; w < ATT_WARPS; ++w) {
-    scale[w] = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - M);
-    Lsum += s_l[w] * scale[w];
-  }
-  float* slot = partials + ((long long)b * nseg_max + seg) * (p.U + 2);
-  if (threadIdx.x == 0) { slot[0] = M; slot[1] = Lsum; }
-  for (int u = threadIdx.x; u < p.U; u += ATT_WARPS * 32) {
-    float a = 0.f;
-#pragma unroll
-    for (int w = 0; w < ATT_WARPS; ++w) a = fmaf(s_acc[(size_t)w * (UV * 128) + u], scale[w], a);
-    slot[2 + u] = a;
-  }
+  const int base = *s_base;
+  for (int j = tid; j < n; j += nthreads)
+    if (base + j < w.max_items) w.items[base + j] = make_int2(b, j);
 }
 
 __global__ void __launch_bounds__(128)
+att_worklist_kernel(const int* __restrict__ row_ptr, int B, AttWork w) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int len = __ldg(row_ptr + b + 1) - __ldg(row_ptr + b);
+  const int n = (len + ATT_WSEG - 1) / ATT_WSEG;
+  const int base = n > 0 ? atomicAdd(w.counter, n) : 0;
+  w.seg_base[b] = base;
+  for (int j = 0; j < n; ++j)
+    if (base + j < w.max_items) w.items[base + j] = make_int2(b, j);
+}
+
+template <int HV, int UV, int MODE, typename T>
+__global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 2 : 1)
+attention_wseg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
+                      const int* __restrict__ row_nnz, long long padded_stride, AttWork w) {
+  const int lane = threadIdx.x & 31;
+  const int n_warps = gridDim.x * ATT_WARPS;
+  const int total = min(__ldg(w.counter), w.max_items);
+  for (int it = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5); it < total; it += n_warps) {
+    const int2 item = __ldg(w.items + it);
+    const int b = item.x, seg = item.y;
+    const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
+    const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
+    const long long seg_start = start + (long long)seg * ATT_WSEG;
+    const long long seg_end = min(end, seg_start + ATT_WSEG);
+    // index stream of the whole segment (<= 64 entries = two batches) is fetched up front: one latency instead of one per batch
+    int c0 = -1, c1 = -1;
+    float v0 = 0.f, v1 = 0.f;
+    if (seg_start + lane < seg_end) { c0 = __ldg(col + seg_start + lane); v0 = __ldg(val + seg_start + lane); }
+    if (seg_start + 32 + lane < seg_end) { c1 = __ldg(col + seg_start + 32 + lane); v1 = __ldg(val + seg_start + 32 + lane); }
+    const int slot_idx = __ldg(w.seg_base + b) + seg;
+    RowCore<HV, UV, MODE, T> core(p, lane, b);
+    const int n0 = (int)min(32LL, seg_end - seg_start);
+    core.batch(v0 != 0.f ? c0 : -1, v0, n0);                      // an explicit 0.0 is "unrated", like the dense form
+    if (seg_start + 32 < seg_end) core.batch(v1 != 0.f ? c1 : -1, v1, (int)(seg_end - seg_start - 32));
+    float* slot = w.partials + (long long)slot_idx * (p.U + 4);
+    if (lane == 0) { slot[0] = core.m; slot[1] = core.l; }
+#pragma unroll
+    for (int uv = 0; uv < UV; ++uv) {
+      const int u = lane * 4 + uv * 128;
+      if (u < p.U) st4(slot + 4 + u, make_float4(core.acc[uv][0], core.acc[uv][1], core.acc[uv][2], core.acc[uv][3]));
+    }
+  }
+}
+
+// The same persistent warp-per-segment loop with the row gathers done by the TMA engine: every lane issues ONE 1-D bulk copy
+// for "its" Pr row and one for its Q row (2 x 32 rows x 512 B = 32 KB per warp in flight, no registers held), the warp waits on
+// its own mbarrier and then reads the rows from shared memory.  Bytes in flight per SM are bounded by shared memory (6 warps x
+// 32 KB fp32, 12 x 16 KB bf16) instead of by registers (v4: 16 warps x 8 KB, and four dependent gather rounds per batch).
+template <int MODE, typename T>
+__global__ void __launch_bounds__(512, 1)
+attention_wseg_tma_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
+                          const int* __restrict__ row_nnz, long long padded_stride, AttWork w) {
+  extern __shared__ __align__(128) unsigned char att_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  constexpr int ROW = 128 * (int)sizeof(T);                     // shared-memory pitch of one staged row
+  T* sPr = reinterpret_cast<T*>(att_smem + (size_t)warp * 64 * ROW);
+  T* sQ = sPr + 32 * 128;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(att_smem + (size_t)warps * 64 * ROW) + warp;
+  if (lane == 0) {
+    att_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  unsigned phase = 0;
+  const uint32_t pr_bytes = (uint32_t)p.H * sizeof(T), q_bytes = (uint32_t)p.U * sizeof(T);
+  const T* __restrict__ Pr = reinterpret_cast<const T*>(p.Pr);
+  const T* __restrict__ Q = reinterpret_cast<const T*>(p.Q);
+  const int n_warps = gridDim.x * warps;
+  const int total = min(__ldg(w.counter), w.max_items);
+  for (int it = blockIdx.x * warps + warp; it < total; it += n_warps) {
+    const int2 item = __ldg(w.items + it);
+    const int b = item.x, seg = item.y;
+    const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
+    const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
+    const long long seg_start = start + (long long)seg * ATT_WSEG;
+    const long long seg_end = min(end, seg_start + ATT_WSEG);
+    int cc[ATT_WSEG / 32];
+    float vv[ATT_WSEG / 32];
+#pragma unroll
+    for (int t = 0; t < ATT_WSEG / 32; ++t) {
+      cc[t] = -1; vv[t] = 0.f;
+      const long long k = seg_start + 32 * t + lane;
+      if (k < seg_end) { cc[t] = __ldg(col + k); vv[t] = __ldg(val + k); }
+      if (vv[t] == 0.f) cc[t] = -1;                               // an explicit 0.0 is "unrated", like the dense form
+    }
+    const int slot_idx = __ldg(w.seg_base + b) + seg;
+    RowCore<1, 1, MODE, T> core(p, lane, b);
+#pragma unroll
+    for (int t = 0; t < ATT_WSEG / 32; ++t) {
+      const int cnt = (int)min(32LL, seg_end - seg_start - 32 * t);
+      if (cnt <= 0) break;
+      const unsigned valid = __ballot_sync(FULL, cc[t] >= 0);
+      if (valid) {
+        att_fence_async();                                         // this warp's earlier shared-memory reads before the async writes
+        __syncwarp();
+        if (lane == 0) att_mbar_expect_tx(bar, (uint32_t)__popc(valid) * (pr_bytes + q_bytes));
+        __syncwarp();
+        if (cc[t] >= 0) {
+          att_bulk_g2s(sPr + lane * 128, Pr + (long long)cc[t] * p.ldPr, pr_bytes, bar);
+          att_bulk_g2s(sQ + lane * 128, Q + (long long)cc[t] * p.ldQ, q_bytes, bar);
+        }
+        att_mbar_wait(bar, phase);
+        phase ^= 1u;
+      }
+      core.batch_smem(cc[t], vv[t], cnt, sPr, sQ, valid);
+    }
+    float* slot = w.partials + (long long)slot_idx * (p.U + 4);
+    if (lane == 0) { slot[0] = core.m; slot[1] = core.l; }
+    if (lane * 4 < p.U) st4(slot + 4 + lane * 4, make_float4(core.acc[0][0], core.acc[0][1], core.acc[0][2], core.acc[0][3]));
+  }
+}
+
+// One WARP per candidate row: lanes take the segments' (max, denominator) pairs in parallel, then every lane owns 4 output columns
+// and adds the partial vectors in segment order with independent 128-bit loads (v4 used a CTA per row whose threads walked the
+// segments with three dependent scalar loops: 35 us at 8192 rows, 10 % of the K2 call).
+constexpr int MERGE_WARPS = 8;
+__global__ void __launch_bounds__(MERGE_WARPS * 32)
 attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
-                       const int* __restrict__ row_nnz, long long padded_stride, const float* __restrict__ partials, int nseg_max) {
-  const int b = blockIdx.x;
+                       const int* __restrict__ row_nnz, long long padded_stride, AttWork w) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5);
+  if (b >= p.B) return;
   const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
   const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
-  const int nseg = (int)((end - start + ATT_SEG - 1) / ATT_SEG);
-  const float* base = partials + (long long)b * nseg_max * (p.U + 2);
+  const int first = __ldg(w.seg_base + b);
+  const int nseg = max(0, min((int)((end - start + ATT_WSEG - 1) / ATT_WSEG), w.max_items - first));
+  const long long stride = p.U + 4;
+  const float* base = w.partials + (long long)first * stride;
   float M = -INFINITY;
-  for (int sgi = 0; sgi < nseg; ++sgi) M = fmaxf(M, base[(long long)sgi * (p.U + 2)]);
+  for (int s0 = 0; s0 < nseg; s0 += 32) M = fmaxf(M, (s0 + lane < nseg) ? base[(long long)(s0 + lane) * stride] : -INFINITY);
+  M = warp_max(M);
   float Lsum = 0.f;
-  for (int sgi = 0; sgi < nseg; ++sgi) {
-    const float ms = base[(long long)sgi * (p.U + 2)];
-    Lsum += base[(long long)sgi * (p.U + 2) + 1] * ((ms == -INFINITY) ? 0.f : __expf(ms - M));
-  }
-  const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;      // no valid rated item -> weights 0 -> user_emb = b_U (:208-209)
-  for (int u = threadIdx.x; u < p.U; u += blockDim.x) {
-    float a = 0.f;
-    for (int sgi = 0; sgi < nseg; ++sgi) {
-      const float ms = base[(long long)sgi * (p.U + 2)];
-      a = fmaf(base[(long long)sgi * (p.U + 2) + 2 + u], (ms == -INFINITY) ? 0.f : __expf(ms - M), a);
+  for (int s0 = 0; s0 < nseg; s0 += 32) {
+    if (s0 + lane < nseg) {
+      const float2 ml = *reinterpret_cast<const float2*>(base + (long long)(s0 + lane) * stride);
+      Lsum += ml.y * ((ml.x == -INFINITY) ? 0.f : __expf(ml.x - M));
     }
-    p.out[(long long)b * p.ldo + u] = fmaf(a, inv, p.bU ? __ldg(p.bU + u) : 0.f);
+  }
+  Lsum = warp_sum(Lsum);          // (the summation order over segments is fixed by the lane layout -> reproducible)
+  const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;      // no valid rated item -> weights 0 -> user_emb = b_U (:208-209)
+  for (int u = lane * 4; u < p.U; u += 128) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < nseg; s0 += 4) {
+      float4 v[4];
+      float f[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        f[k] = 0.f;
+        if (s0 + k < nseg) {
+          const float ms = base[(long long)(s0 + k) * stride];
+          f[k] = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+          v[k] = *reinterpret_cast<const float4*>(base + (long long)(s0 + k) * stride + 4 + u);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a.x = fmaf(v[k].x, f[k], a.x); a.y = fmaf(v[k].y, f[k], a.y); a.z = fmaf(v[k].z, f[k], a.z); a.w = fmaf(v[k].w, f[k], a.w);
+      }
+    }
+    const float4 bu = p.bU ? ld4(p.bU + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    st4(p.out + (long long)b * p.ldo + u, make_float4(fmaf(a.x, inv, bu.x), fmaf(a.y, inv, bu.y), fmaf(a.z, inv, bu.z), fmaf(a.w, inv, bu.w)));
   }
   if (p.att != nullptr) {
-    for (long long k = start + threadIdx.x; k < end; k += blockDim.x) {
+    for (long long k = start + lane; k < end; k += 32) {
       if (__ldg(val + k) != 0.f) {
         float* a = p.att + (long long)b * p.I + __ldg(col + k);
         *a = normalise_score(*a, M, Lsum);
@@ -363,8 +557,9 @@ attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* 
 // pooling kernel can split every row's non-zeros EVENLY over its warps.
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __restrict__ col, float* __restrict__ val,
-                  int* __restrict__ row_nnz) {
+                  int* __restrict__ row_nnz, AttWork w) {
   __shared__ int s_cnt[ATT_WARPS];
+  __shared__ int s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x;
   const float* __restrict__ row = um + (long long)b * ld_um;
@@ -391,6 +586,7 @@ um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __r
     total += s_cnt[w];
   }
   if (threadIdx.x == 0) row_nnz[b] = total;
+  att_emit_items(w, b, total, threadIdx.x, ATT_WARPS * 32, &s_base);      // this row's (row, segment) work items
   long long out = (long long)b * I + base;
   for (int i0 = i_begin; i0 < i_end; i0 += 128) {
     float v[4];
@@ -473,48 +669,94 @@ struct AttInputs {
   const float* um; long long ld_um;
   const int* row_ptr; const int* col; const float* val;
   void* ws; size_t ws_bytes;
+  long long max_row_nnz;     // CSR form: upper bound of a row's length (0 = unknown -> I); sizes the work list and the partial slots
+  long long nnz;             // CSR form: number of stored entries (0 = unknown); tightens the same bound
 };
 
-static size_t att_partials_bytes(long long B, long long I, int U) {
-  const long long nseg = (I + ATT_SEG - 1) / ATT_SEG;
-  return (size_t)(B * (nseg > 0 ? nseg : 1)) * (size_t)(U + 2) * sizeof(float);
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+// upper bound of the number of (row, segment) work items: every row ends with at most one partial segment
+static long long att_max_items(long long B, long long I, long long max_row_nnz, long long nnz) {
+  const long long full = B * std::max(1LL, (I + ATT_WSEG - 1) / ATT_WSEG);
+  if (nnz > 0) return std::min(full, nnz / ATT_WSEG + B);                 // exact knowledge wins over the hint
+  if (max_row_nnz > 0) return std::min(full, B * ((max_row_nnz + ATT_WSEG - 1) / ATT_WSEG));
+  return full;
 }
-static size_t att_compact_bytes(long long B, long long I) {
-  return (size_t)(B * I) * (sizeof(int) + sizeof(float)) + (size_t)B * sizeof(int) + 64;
-}
-// dense form: compaction lists + partial slots; CSR form: partial slots only
-static size_t att_workspace_bytes(long long B, long long I, int U, bool dense) {
-  return att_partials_bytes(B, I, U) + 256 + (dense ? att_compact_bytes(B, I) : 0);
+struct AttLayout { size_t counter, seg_base, items, partials, compact, total; };
+// workspace = counter | seg_base (B) | items | partials | [dense: col, val, row_nnz lists]
+static AttLayout att_layout(long long B, long long I, int U, bool dense, long long max_row_nnz, long long nnz) {
+  const long long items = att_max_items(B, I, dense ? 0 : max_row_nnz, dense ? 0 : nnz);
+  AttLayout l;
+  l.counter = 0;
+  l.seg_base = 256;
+  l.items = l.seg_base + align256((size_t)B * sizeof(int));
+  l.partials = l.items + align256((size_t)items * sizeof(int2));
+  l.compact = l.partials + align256((size_t)items * (size_t)(U + 4) * sizeof(float));
+  l.total = l.compact + (dense ? (size_t)(B * I) * (sizeof(int) + sizeof(float)) + (size_t)B * sizeof(int) + 64 : 0);
+  return l;
 }
 
 template <int HV, int UV, int MODE, typename T>
 static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) {
   const bool dense = in.um != nullptr;
-  const bool have_ws = in.ws && in.ws_bytes >= att_workspace_bytes(p.B, p.I, p.U, dense);
+  const AttLayout lay = att_layout(p.B, p.I, p.U, dense, in.max_row_nnz, in.nnz);
+  const bool have_ws = in.ws && in.ws_bytes >= lay.total;
   if (!have_ws) {                      // no workspace: single fused kernel, one CTA per row
     if (dense) attention_pool_dense_kernel<HV, UV, MODE, T><<<p.B, ATT_WARPS * 32, 0, st>>>(p, in.um, in.ld_um);
     else attention_pool_csr_kernel<HV, UV, MODE, T><<<p.B, ATT_WARPS * 32, 0, st>>>(p, in.row_ptr, in.col, in.val, nullptr, 0);
     B200REC_CHECK_LAUNCH();
     return B200REC_OK;
   }
-  float* partials = reinterpret_cast<float*>(in.ws);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(in.ws);
+  AttWork w;
+  w.counter = reinterpret_cast<int*>(ws + lay.counter);
+  w.seg_base = reinterpret_cast<int*>(ws + lay.seg_base);
+  w.items = reinterpret_cast<int2*>(ws + lay.items);
+  w.partials = reinterpret_cast<float*>(ws + lay.partials);
+  const long long max_items = att_max_items(p.B, p.I, dense ? 0 : in.max_row_nnz, dense ? 0 : in.nnz);
+  if (max_items > 0x7fffffffLL) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: more than 2^31 segments");
+  w.max_items = (int)max_items;
+  B200REC_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), st));
   const int* ccol = in.col; const float* cval = in.val; const int* cnnz = nullptr; const int* rp = in.row_ptr;
   long long stride = 0;
-  if (dense) {                         // streaming compaction of the dense matrix into row-padded lists
-    unsigned char* q = reinterpret_cast<unsigned char*>(in.ws) + ((att_partials_bytes(p.B, p.I, p.U) + 255) & ~(size_t)255);
-    int* wcol = reinterpret_cast<int*>(q);
+  if (dense) {                         // streaming compaction of the dense matrix into row-padded lists (+ the work list)
+    int* wcol = reinterpret_cast<int*>(ws + lay.compact);
     float* wval = reinterpret_cast<float*>(wcol + (size_t)p.B * p.I);
     int* wnnz = reinterpret_cast<int*>(wval + (size_t)p.B * p.I);
-    um_compact_kernel<<<p.B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz);
+    um_compact_kernel<<<p.B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz, w);
     B200REC_CHECK_LAUNCH();
     ccol = wcol; cval = wval; cnnz = wnnz; rp = nullptr; stride = p.I;
+  } else {
+    att_worklist_kernel<<<ceil_div_i(p.B, 128), 128, 0, st>>>(rp, p.B, w);
+    B200REC_CHECK_LAUNCH();
   }
-  const int nseg_max = p.I > 0 ? (p.I + ATT_SEG - 1) / ATT_SEG : 1;
-  dim3 grid(p.B, nseg_max);
-  if (nseg_max > 65535) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: more than 65535 segments per row");
-  attention_seg_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, rp, ccol, cval, cnnz, stride, partials, nseg_max);
-  B200REC_CHECK_LAUNCH();
-  attention_merge_kernel<<<p.B, 128, 0, st>>>(p, rp, ccol, cval, cnnz, stride, partials, nseg_max);
+  // rows as TMA bulk copies need 16-byte aligned rows whose length is a multiple of 16 bytes
+  const bool no_tma = g_att_path == 1, force_tma = g_att_path == 2;
+  // tables that stay in L2 (config 2: 10 MB) are served faster by the register-staged gathers with 16 warps per SM (72 vs 98 us);
+  // the TMA staging pays when the rows come from HBM
+  const bool big_tables = (double)p.I * (p.H + p.U) * sizeof(T) > 0.5 * b200rec_l2_bytes();
+  const bool tma_ok = HV == 1 && UV == 1 && !no_tma && (big_tables || force_tma) && (p.H * sizeof(T)) % 16 == 0 && (p.U * sizeof(T)) % 16 == 0 &&
+                      (p.ldPr * sizeof(T)) % 16 == 0 && (p.ldQ * sizeof(T)) % 16 == 0 && (uintptr_t)p.Pr % 16 == 0 && (uintptr_t)p.Q % 16 == 0;
+  if constexpr (HV == 1 && UV == 1) {
+    if (tma_ok) {
+      const int warps = sizeof(T) == 4 ? 6 : 12;
+      const size_t smem = (size_t)warps * 64 * 128 * sizeof(T) + (size_t)warps * sizeof(uint64_t);
+      static bool attr_set = false;       // per template instantiation
+      if (!attr_set) {
+        B200REC_CUDA(cudaFuncSetAttribute(attention_wseg_tma_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      const int grid = (int)std::max(1LL, std::min((max_items + warps - 1) / warps, (long long)b200rec_num_sms()));
+      attention_wseg_tma_kernel<MODE, T><<<grid, warps * 32, smem, st>>>(p, rp, ccol, cval, cnnz, stride, w);
+      B200REC_CHECK_LAUNCH();
+    }
+  }
+  if (!tma_ok) {
+    const int ctas_per_sm = (HV == 1 && UV == 1) ? 2 : 1;
+    const int grid = (int)std::max(1LL, std::min((max_items + ATT_WARPS - 1) / ATT_WARPS, (long long)b200rec_num_sms() * ctas_per_sm));
+    attention_wseg_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, rp, ccol, cval, cnnz, stride, w);
+    B200REC_CHECK_LAUNCH();
+  }
+  attention_merge_kernel<<<ceil_div_i(p.B, MERGE_WARPS), MERGE_WARPS * 32, 0, st>>>(p, rp, ccol, cval, cnnz, stride, w);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -532,8 +774,16 @@ static int dispatch_att(const AttParams& p, const AttInputs& in, cudaStream_t st
 
 using namespace b200rec;
 
+extern "C" int b200rec_attention_pool_set_path(int path) {
+  if (path < 0 || path > 2) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_set_path: 0 auto, 1 registers, 2 TMA");
+  g_att_path = path;
+  return B200REC_OK;
+}
 extern "C" size_t b200rec_attention_pool_workspace(int64_t B, int64_t I, int U, int dense) {
-  return (B > 0 && I > 0 && U > 0) ? att_workspace_bytes(B, I, U, dense != 0) : 0;
+  return (B > 0 && I > 0 && U > 0) ? att_layout(B, I, U, dense != 0, 0, 0).total : 0;
+}
+extern "C" size_t b200rec_attention_pool_workspace_csr(int64_t B, int64_t I, int U, int64_t max_row_nnz, int64_t nnz) {
+  return (B > 0 && I > 0 && U > 0) ? att_layout(B, I, U, false, max_row_nnz, nnz).total : 0;
 }
 
 extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream) {
@@ -563,7 +813,7 @@ extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stre
   if (p.Ec && (!p.Er || p.E <= 0)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: training mask needs both embeddings");
   cudaStream_t st = (cudaStream_t)stream;
   const long long ld_um = a->user_matrix ? (a->ld_user_matrix ? a->ld_user_matrix : a->I) : 0;
-  AttInputs in{a->user_matrix, ld_um, a->row_ptr, a->col, a->val, a->workspace, a->workspace_bytes};
+  AttInputs in{a->user_matrix, ld_um, a->row_ptr, a->col, a->val, a->workspace, a->workspace_bytes, a->max_row_nnz, a->nnz};
   if (a->table_dtype == B200REC_F32) {
     if (a->mode == MODE_NET) return dispatch_att<MODE_NET, float>(p, in, st);
     if (a->mode == MODE_DOT) return dispatch_att<MODE_DOT, float>(p, in, st);

@@ -28,6 +28,8 @@ static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1
 
 // number of SMs of the current device (cached)
 int b200rec_num_sms();
+// L2 cache size of the current device in bytes (cached)
+long long b200rec_l2_bytes();
 
 namespace b200rec {
 

@@ -111,8 +111,8 @@ __device__ __forceinline__ uint4 ldg16_keep(const unsigned char* p, uint64_t pol
 // weight 0) and lanes beyond the row width read column 0, so every load is valid and the per-edge cost is
 // 2 SHFL + 1 IMAD.WIDE.U32 + 1 LDG.128 + 4 FFMA (the first version spent ~26 instructions per edge on predicated
 // 64-bit address arithmetic and zero-fill moves — profiles/r01).
-template <int G, int NV, typename T, bool GAT, bool KEEP>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+template <int G, int NV, typename T, bool GAT, bool KEEP, int UN = 8>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, (NV == 1 && UN == 8 && !GAT) ? 4 : 1)
 spmm_chunk_kernel(SpmmParams p) {
   constexpr int EPW = 32 / G;                       // edges per warp step
   constexpr int VPL = Lane16<T>::VPL;
@@ -142,30 +142,36 @@ spmm_chunk_kernel(SpmmParams p) {
     for (int q = 0; q < VPL; ++q) acc[nv][q] = 0.f;
   float gat_m = -INFINITY, gat_l = 0.f;             // GAT: online softmax state of this chunk (warp-uniform)
 
+  // the index stream of the NEXT 32-edge block is fetched while the rows of the current one are gathered, so the
+  // (col -> row address) dependency costs one memory latency per chunk instead of one per block
+  unsigned c_nx = 0u;
+  float w_nx = 0.f;
+  int pos_nx = 0;
+  if (s + lane < e) {
+    c_nx = (unsigned)__ldcs(p.col + s + lane);
+    w_nx = p.w ? __ldcs(p.w + s + lane) : 1.f;
+    if (p.skip_bits) pos_nx = __ldcs(p.perm + s + lane);
+  }
   for (int k0 = s; k0 < e; k0 += 32) {
     const int cnt = min(32, e - k0);
-    unsigned c = 0u;
-    float wv = 0.f;
-    if (lane < cnt) {
-      c = (unsigned)__ldcs(p.col + k0 + lane);
-      wv = p.w ? __ldcs(p.w + k0 + lane) : 1.f;
-      if (p.skip_bits) {
-        const int pos = __ldcs(p.perm + k0 + lane);
-        if ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) { wv = 0.f; c = 0u; }
-      }
+    unsigned c = c_nx;
+    float wv = w_nx;
+    const int pos = pos_nx;
+    c_nx = 0u; w_nx = 0.f;
+    if (k0 + 32 + lane < e) {
+      c_nx = (unsigned)__ldcs(p.col + k0 + 32 + lane);
+      w_nx = p.w ? __ldcs(p.w + k0 + 32 + lane) : 1.f;
+      if (p.skip_bits) pos_nx = __ldcs(p.perm + k0 + 32 + lane);
     }
+    bool masked = false;
+    if (p.skip_bits != nullptr && lane < cnt) masked = ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) != 0u;
+    const unsigned c_raw = c;
+    if (masked) { wv = 0.f; c = 0u; }
     if constexpr (GAT) {
       // softmax over the incoming edges of the row of the source scores (the destination half of the reference's
       // Linear(2d -> 1) is constant within a row and cancels in the softmax).  Masked edges (training) do not take part.
-          float sc = -INFINITY;
-      if (lane < cnt) {
-        bool masked = false;
-        if (p.skip_bits) {
-          const int pos = __ldcs(p.perm + k0 + lane);
-          masked = ((__ldg(p.skip_bits + (pos >> 5)) >> (pos & 31)) & 1u) != 0u;
-        }
-        if (!masked) sc = __ldg(p.att_src + __ldcs(p.col + k0 + lane));
-      }
+      float sc = -INFINITY;
+      if (lane < cnt && !masked) sc = __ldg(p.att_src + c_raw);
       const float m_new = fmaxf(gat_m, warp_max(sc));
       float ex = 0.f;
       if (m_new != -INFINITY) {
@@ -181,12 +187,12 @@ spmm_chunk_kernel(SpmmParams p) {
       wv *= ex;
     }
 #pragma unroll
-    for (int st0 = 0; st0 < STEPS; st0 += 8) {
-      if (st0 * EPW < cnt) {                                       // warp-uniform: at most 8 steps of padding per chunk
-        uint4 x[8][NV];
-        float ww[8];
+    for (int st0 = 0; st0 < STEPS; st0 += UN) {
+      if (st0 * EPW < cnt) {                                       // warp-uniform: at most UN steps of padding per chunk
+        uint4 x[UN][NV];
+        float ww[UN];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < UN; ++u) {
           const int src_lane = (st0 + u) * EPW + g;
           const unsigned cc = __shfl_sync(FULL, c, src_lane);
           ww[u] = __shfl_sync(FULL, wv, src_lane);
@@ -197,7 +203,7 @@ spmm_chunk_kernel(SpmmParams p) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < UN; ++u)
 #pragma unroll
           for (int nv = 0; nv < NV; ++nv) Lane16<T>::fma(acc[nv], ww[u], x[u][nv]);
       }
@@ -277,8 +283,10 @@ template <int G, int NV, typename T>
 static int launch_chunks(const SpmmParams& p, cudaStream_t st) {
   const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
   static const bool keep = []() { const char* e = getenv("B200REC_SPMM_L2_KEEP"); return e != nullptr && atoi(e) != 0; }();   // off by default: measured 3.21 vs 3.16 ms per config-3 step with the hint
+  static const bool unroll16 = []() { const char* e = getenv("B200REC_SPMM_UNROLL"); return e != nullptr && atoi(e) == 16; }();
   if (p.att_src) spmm_chunk_kernel<G, NV, T, true, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   else if (keep) spmm_chunk_kernel<G, NV, T, false, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  else if (NV == 1 && G >= 16 && unroll16) spmm_chunk_kernel<G, NV, T, false, false, (NV == 1 && G >= 16) ? 16 : 8><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   else spmm_chunk_kernel<G, NV, T, false, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;

@@ -188,7 +188,7 @@ class AttentionNCF(NCF):
         else:
             Pc, Pr, mode, a2, a20 = self._score_tables(Ec, Er)
         res = ops.attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, csr=csr,
-                                     return_attention_weights=return_attention_weights)
+                                     return_attention_weights=return_attention_weights, max_row_nnz=getattr(user_matrix, 'max_row_nnz', 0))
         user_emb, att = res if return_attention_weights else (res, None)
         if user_emb.shape[1] != U:
             user_emb = user_emb[:, :U]

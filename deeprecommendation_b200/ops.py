@@ -385,9 +385,15 @@ def rowdot(in0, in1, idx0=None, idx1=None):
 # ------------------------------------------------------------------------------------------------------------------
 # K2 attention pooling
 # ------------------------------------------------------------------------------------------------------------------
+def set_attention_path(path: str):
+    """'auto' | 'registers' | 'tma' — how K2's segment-parallel path gathers table rows (b200rec_attention_pool_set_path)"""
+    L.check(L.lib().b200rec_attention_pool_set_path({'auto': 0, 'registers': 1, 'tma': 2}[path]), 'attention_pool_set_path')
+
+
 def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None, user_matrix=None, csr=None,
-                       return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0, use_workspace=True):
-    """out (B,U) [, att (B,I)] — b200rec_attention_pool.  `csr` = (row_ptr int32, col int32, val fp32)."""
+                       return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0, use_workspace=True, max_row_nnz=0):
+    """out (B,U) [, att (B,I)] — b200rec_attention_pool.  `csr` = (row_ptr int32, col int32, val fp32); `max_row_nnz` (CSR only,
+    optional) = a host-known bound of the row lengths, so that the segment grid is not sized by I."""
     _require_cuda(Pc, Pr, Q, user_matrix)
     Pc = Pc.contiguous().float()
     if Pr.dtype != Q.dtype:
@@ -424,7 +430,11 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
     else:
         raise ValueError('attention_pool: need user_matrix or csr')
     d.B, d.I, d.H, d.U = B, I, H, U
-    wsb = L.lib().b200rec_attention_pool_workspace(B, I, U, int(user_matrix is not None)) if use_workspace else 0
+    if user_matrix is None:
+        d.max_row_nnz, d.nnz = max(0, int(max_row_nnz)), int(csr[1].numel())
+        wsb = L.lib().b200rec_attention_pool_workspace_csr(B, I, U, d.max_row_nnz, d.nnz) if use_workspace else 0
+    else:
+        wsb = L.lib().b200rec_attention_pool_workspace(B, I, U, 1) if use_workspace else 0
     if wsb:
         ws = torch.empty(wsb, dtype=torch.uint8, device=Pc.device)
         keep.append(ws)

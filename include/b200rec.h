@@ -155,11 +155,17 @@ typedef struct {
   int drop_zero_scores;
   float score_scale; /* 0 = 1.0; message dropout keeps scores / (1-p) (F.dropout, :187) */
   int64_t ld_pr, ld_q; /* leading dimensions of Pr / Q in elements; 0 = H / U */
-  void* workspace;     /* b200rec_attention_pool_workspace(B, I, U, dense) bytes enable the segment-parallel path (streaming */
-  size_t workspace_bytes; /* compaction of a dense matrix, one CTA per <=512 non-zeros, merge kernel); NULL = one fused kernel */
+  void* workspace;     /* b200rec_attention_pool_workspace(B, I, U, dense) bytes enable the segment-parallel path (streaming compaction */
+  size_t workspace_bytes; /* of a dense matrix, work list of <=64-non-zero segments, one warp each, merge kernel); NULL = one fused kernel */
+  int64_t max_row_nnz;    /* CSR form, optional: upper bound of a row's length (0 = unknown, I is used) and the number of stored entries */
+  int64_t nnz;            /* (0 = unknown).  They only size the work list / partial slots: b200rec_attention_pool_workspace_csr(). */
 } b200rec_attention_t;
 size_t b200rec_attention_pool_workspace(int64_t B, int64_t I, int U, int dense);
+size_t b200rec_attention_pool_workspace_csr(int64_t B, int64_t I, int U, int64_t max_row_nnz, int64_t nnz);
 int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream);
+/* How the segment-parallel path gathers table rows: 0 = auto (TMA bulk copies into shared memory when the tables exceed half of L2,
+ * register-staged 128-bit loads otherwise), 1 = always registers, 2 = TMA whenever the layout allows (H, U <= 128, 16-byte rows). */
+int b200rec_attention_pool_set_path(int path);
 
 /* ---- K3  GraphNCF propagation: edge-balanced CSR SpMM + degree normalisation + fused combine -----------------------
  * Replaces LightGCNConv.forward/message + PyG propagate (gnn_ncf.py:39-94) and the stack+mean of gnn_ncf.py:351:

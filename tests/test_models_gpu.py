@@ -155,6 +155,19 @@ def test_attention_cfg2_ragged_vs_oracle():
         assert maxnorm_rel(a1, att) < 1e-5 and maxnorm_rel(a2, att) < 1e-5
         bf = ops.attention_pool_raw(Pc, Pr.bfloat16(), Q.bfloat16(), user_matrix=umt.to(DEV), **common)
         assert maxnorm_rel(bf, dense) < 1e-2                                  # bf16 tables, fp32 accumulate
+        # the same segments with the rows staged by TMA bulk copies (the path big tables take): same arithmetic, same order
+        csr_args = (row_ptr.to(DEV), col.to(DEV), umt[nz].to(DEV))
+        ops.set_attention_path('tma')
+        try:
+            t_dense = ops.attention_pool_raw(Pc, Pr, Q, user_matrix=umt.to(DEV), **common)
+            t_csr, t_att = ops.attention_pool_raw(Pc, Pr, Q, csr=csr_args, return_attention_weights=True,
+                                                  max_row_nnz=int(nz.sum(1).max()), **common)
+            t_bf = ops.attention_pool_raw(Pc, Pr.bfloat16(), Q.bfloat16(), csr=csr_args, **common)
+            t_hint = ops.attention_pool_raw(Pc, Pr, Q, csr=csr_args, max_row_nnz=7, **common)          # nnz is known from the CSR: a wrong hint is ignored
+        finally:
+            ops.set_attention_path('auto')
+        assert torch.equal(t_dense, dense) and torch.equal(t_csr, csr) and torch.equal(t_hint, csr)
+        assert maxnorm_rel(t_att, att) < 1e-5 and maxnorm_rel(t_bf, dense) < 1e-2
 
 
 def test_attention_webapp_pattern_vs_oracle():
