@@ -555,14 +555,37 @@ attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* 
 // One CTA per row; pure streaming (four independent coalesced loads per thread and iteration, no dependent work), so
 // the dense scan costs a few microseconds instead of sitting on the critical path of the pooling kernel, and the
 // pooling kernel can split every row's non-zeros EVENLY over its warps.
+// STAGED: the row is first copied to shared memory with 16 independent loads per thread in flight (one memory latency per 4096
+// columns instead of one per 128 — the two scans then run out of shared memory); rows wider than the shared memory take the
+// streaming form.
+template <bool STAGED>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __restrict__ col, float* __restrict__ val,
                   int* __restrict__ row_nnz, AttWork w) {
+  extern __shared__ float um_row_smem[];
   __shared__ int s_cnt[ATT_WARPS];
   __shared__ int s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x;
-  const float* __restrict__ row = um + (long long)b * ld_um;
+  const float* __restrict__ grow = um + (long long)b * ld_um;
+  if constexpr (STAGED) {
+    for (int i0 = 0; i0 < I; i0 += ATT_WARPS * 32 * 16) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = i0 + u * (ATT_WARPS * 32) + (int)threadIdx.x;
+        v[u] = (i < I) ? __ldcs(grow + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = i0 + u * (ATT_WARPS * 32) + (int)threadIdx.x;
+        if (i < I) um_row_smem[i] = v[u];
+      }
+    }
+    __syncthreads();
+  }
+  const float* row = STAGED ? um_row_smem : grow;
+  auto ldv = [](const float* q) { if constexpr (STAGED) return *q; else return __ldg(q); };
   const int chunks = (I + 31) >> 5;
   const int cpw = (chunks + ATT_WARPS - 1) / ATT_WARPS;
   const int i_begin = warp * cpw * 32, i_end = min(I, i_begin + cpw * 32);
@@ -572,7 +595,7 @@ um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __r
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * 32 + lane;
-      v[u] = (i < i_end) ? __ldg(row + i) : 0.f;
+      v[u] = (i < i_end) ? ldv(row + i) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) cnt += __popc(__ballot_sync(FULL, v[u] != 0.f));
@@ -593,7 +616,7 @@ um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __r
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * 32 + lane;
-      v[u] = (i < i_end) ? __ldg(row + i) : 0.f;
+      v[u] = (i < i_end) ? ldv(row + i) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -722,7 +745,17 @@ static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) 
     int* wcol = reinterpret_cast<int*>(ws + lay.compact);
     float* wval = reinterpret_cast<float*>(wcol + (size_t)p.B * p.I);
     int* wnnz = reinterpret_cast<int*>(wval + (size_t)p.B * p.I);
-    um_compact_kernel<<<p.B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz, w);
+    const size_t row_bytes = (size_t)p.I * sizeof(float);
+    if (row_bytes <= 96 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        B200REC_CUDA(cudaFuncSetAttribute(um_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+      }
+      um_compact_kernel<true><<<p.B, ATT_WARPS * 32, row_bytes, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz, w);
+    } else {
+      um_compact_kernel<false><<<p.B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz, w);
+    }
     B200REC_CHECK_LAUNCH();
     ccol = wcol; cval = wval; cnnz = wnnz; rp = nullptr; stride = p.I;
   } else {

@@ -30,6 +30,7 @@ class AttentionNCF(NCF):
       K1a  [Er | Q] = rated_items · [W_I ; W_U]ᵀ           one pass over the (I, F) profiles feeds both the item
                                                            embedding and the pooled-profile projection Q = R·W_Uᵀ
       K1a  Pc = Ec·A1cᵀ + a1,  Pr = Er·A1rᵀ                AttentionNet.0 split into candidate / rated halves
+           (inference: the last two lines collapse into [Ec | Pc] and [Pr | Q] straight from the profiles, `_composite_projection`)
       K2   user_emb = Σ_i softmax_i(a2·ReLU(Pc+Pr_i)+a20)·um_bi·Q_i + b_U     ragged, one warp per candidate
       K1b  out = MLP([Ec, user_emb])                       item first (attention_ncf.py:219)
 
@@ -102,6 +103,37 @@ class AttentionNCF(NCF):
         self._proj_cache = (key, tuple(t.detach() for t in out)) if key is not None else None
         return out
 
+    def _composite_projection(self):
+        """Inference-only algebra: AttentionNet.0's halves are folded into the profile projections, so that the attention
+        pre-activations come straight out of the two sweeps over the F-wide profiles and the (I, E) x (E, H) GEMMs disappear:
+
+            Pr = (R·W_Iᵀ + b_I)·A1rᵀ       = R·(A1r·W_I)ᵀ + A1r·b_I              rated side:      [Pr | Q]  = R·[A1r·W_I ; W_U]ᵀ + [A1r·b_I ; 0]
+            Pc = (C·W_Iᵀ + b_I)·A1cᵀ + a1  = C·(A1c·W_I)ᵀ + (A1c·b_I + a1)        candidate side:  [Ec | Pc] = C·[W_I ; A1c·W_I]ᵀ + [b_I ; A1c·b_I + a1]
+
+        (Er itself is only needed by the training-mode isclose() mask, attention_ncf.py:199.)  The composites are formed in
+        float64 and rounded once; the results differ from the two-step order by ~1e-7 relative, inside the fp32 tolerance.
+        Returns (Wr, br, Wc, bc, bU, a2, a20, H) or None when the variant does not apply; cached per parameter version."""
+        halves = self._attention_halves()
+        if halves is None:
+            return None
+        item, user, first = self.ItemEmbeddings[0], self.UserEmbeddings[0], self.AttentionNet[0]
+        params = (item.weight, item.bias, user.weight, user.bias, first.weight, first.bias, self.AttentionNet[3].weight)
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        cached = getattr(self, '_comp_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        with torch.no_grad():
+            A1c, A1r, a1, a2, a20 = halves
+            WI, bI = item.weight.double(), item.bias.double()
+            WU, bU = _pad_rows(user.weight.detach(), user.bias.detach())
+            Wr = torch.cat(((A1r.double() @ WI).float(), WU), 0).contiguous()
+            br = torch.cat(((A1r.double() @ bI).float(), torch.zeros_like(bU)), 0).contiguous()
+            Wc = torch.cat((item.weight.detach(), (A1c.double() @ WI).float()), 0).contiguous()
+            bc = torch.cat((item.bias.detach(), (A1c.double() @ bI + a1.double()).float()), 0).contiguous()
+        out = (Wr, br, Wc, bc, bU, a2, a20, A1r.shape[0])
+        self._comp_cache = (key, out)
+        return out
+
     def _attention_halves(self):
         """(A1c, A1r, a1, a2, head bias) of AttentionNet as STABLE view objects (so their MMA-ready packed copies stay cached)
         — only for the Linear-ReLU-Linear variant with att_dense % 4 == 0; None otherwise."""
@@ -120,21 +152,20 @@ class AttentionNCF(NCF):
     def forward(self, candidate_items, rated_items, user_matrix, return_attention_weights=False):
         item, user = self.ItemEmbeddings[0], self.UserEmbeddings[0]
         E, U = item.weight.shape[0], user.weight.shape[0]
-        Wcat, bcat, bU = self._stacked_projection()
-        halves = self._attention_halves()
         no_grad = not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
-        if (no_grad and halves is not None and ops.tc_batch_available() and rated_items.shape[0] >= ops.TC_MIN_ROWS
-                and rated_items.shape[1] >= ops.TC_MIN_K):
-            # inference on the tensor-core engine: the rated-item sweep fills the device exactly (74 x 2 tiles on 148 SMs at
-            # config 2 — adding the candidates' 4 row tiles to that launch costs a second wave, measured 132 vs 71 us), so
-            # the candidates keep their own split-K GEMM; both halves of AttentionNet.0 share ONE tensor-core launch.
-            A1c, A1r, a1, a2, a20 = halves
-            Ec = ops.linear_raw(candidate_items, item.weight, item.bias)                # :150
-            ErQ = ops.linear_raw(rated_items, Wcat, bcat)                               # :151 + Q = R·W_Uᵀ
-            Er, Q = ErQ[:, :E], ErQ[:, E:]
-            Pr, Pc = ops.linear_tc_batch([(Er, A1r, None, None), (Ec, A1c, a1, None)])
+        comp = self._composite_projection() if (no_grad and not self.training) else None
+        if comp is not None:
+            # inference: two sweeps over the F-wide profiles give everything K2 and the MLP need (see _composite_projection).
+            # The rated-item sweep fills the device exactly at config 2 (74 x 2 tiles on 148 SMs — adding the candidates' 4
+            # row tiles to that launch costs a second wave, measured 132 vs 71 us), so the candidates keep their own GEMM.
+            Wr, br, Wc, bc, bU, a2, a20, H = comp
+            EcPc = ops.linear_raw(candidate_items, Wc, bc)                              # :150 (+ candidate half of :176)
+            PrQ = ops.linear_raw(rated_items, Wr, br)                                   # :151 folded with :176, + Q = R·W_Uᵀ
+            Ec, Pc = EcPc[:, :E], EcPc[:, E:]
+            Pr, Q = PrQ[:, :H], PrQ[:, H:]
             mode = L.ATT_NET
         else:
+            Wcat, bcat, bU = self._stacked_projection()
             Ec = ops.linear(candidate_items, item.weight, item.bias)                    # :150
             # one sweep over rated_items: item embedding (:151) and Q = rated_items·W_Uᵀ (pooling moved into embedding
             # space: W_U(Σ α·um·R_i) = Σ α·um·(W_U R_i), :213+:216)
@@ -176,16 +207,19 @@ class AttentionNCF(NCF):
         cand_pos = candidate_items.pos.to(dev, non_blocking=True)
         rated_pos = rated_items.pos.to(dev, non_blocking=True)
         csr = tuple(t.to(dev, non_blocking=True) for t in (user_matrix.row_ptr, user_matrix.col, user_matrix.val))
-        Wcat, bcat, bU = self._stacked_projection()
-        Ec = ops.linear_raw(table.index_select(0, cand_pos), item.weight, item.bias)
-        ErQ = ops.linear_raw(table, Wcat, bcat, row_index=rated_pos)
-        Er, Q = ErQ[:, :E], ErQ[:, E:]
-        halves = self._attention_halves()
-        if halves is not None and ops.tc_batch_available() and rated_pos.numel() >= ops.TC_MIN_ROWS:
-            A1c, A1r, a1, a2, a20 = halves
-            Pr, Pc = ops.linear_tc_batch([(Er, A1r, None, None), (Ec, A1c, a1, None)])
+        comp = self._composite_projection()
+        if comp is not None:
+            Wr, br, Wc, bc, bU, a2, a20, H = comp
+            EcPc = ops.linear_raw(table.index_select(0, cand_pos), Wc, bc)
+            PrQ = ops.linear_raw(table, Wr, br, row_index=rated_pos)
+            Ec, Pc = EcPc[:, :E], EcPc[:, E:]
+            Pr, Q = PrQ[:, :H], PrQ[:, H:]
             mode = L.ATT_NET
         else:
+            Wcat, bcat, bU = self._stacked_projection()
+            Ec = ops.linear_raw(table.index_select(0, cand_pos), item.weight, item.bias)
+            ErQ = ops.linear_raw(table, Wcat, bcat, row_index=rated_pos)
+            Er, Q = ErQ[:, :E], ErQ[:, E:]
             Pc, Pr, mode, a2, a20 = self._score_tables(Ec, Er)
         res = ops.attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, csr=csr,
                                      return_attention_weights=return_attention_weights, max_row_nnz=getattr(user_matrix, 'max_row_nnz', 0))
