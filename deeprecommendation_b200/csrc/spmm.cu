@@ -238,45 +238,119 @@ spmm_chunk_kernel(SpmmParams p) {
   }
 }
 
-// rows that were cut into several chunks: add the partials in chunk order, then the same epilogue
+// rows that were cut into several chunks: add the partials in a fixed order, then the same epilogue.
+// One warp per row while the row has <= FIX_LONG partial slots (slots added in chunk order, 8 independent loads at a time).
+// Longer rows — the few hottest items of a Zipf catalogue own thousands of chunks; one warp walking 9,800 slots was 2.0 ms of a
+// 12.4 ms layer in the HBM regime — are handled by the whole CTA afterwards: warp w adds slots w, w+8, ..., the eight sums are
+// combined in warp order.  Either way the order depends only on the index structure: bit-reproducible run to run.
+constexpr int FIX_LONG = 64;
+
+template <int NV, bool GAT>
+__device__ __forceinline__ void fixup_accumulate(const SpmmParams& p, int first, int begin, int step, int n, int lane, float M,
+                                                 float (&acc)[NV][4], float& Lsum) {
+  for (int s0 = begin; s0 < n; s0 += 8 * step) {
+    float4 v[8][NV];
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int sidx = s0 + k * step;
+      const bool ok = sidx < n;
+      f[k] = ok ? 1.f : 0.f;
+      if constexpr (GAT) {
+        if (ok) {
+          const float ms = p.partials_ml[2 * (first + sidx)];
+          const float e = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+          Lsum += p.partials_ml[2 * (first + sidx) + 1] * e;
+          f[k] = e;
+        }
+      }
+#pragma unroll
+      for (int nv = 0; nv < NV; ++nv) {
+        const int cidx = lane * 4 + nv * 128;
+        v[k][nv] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cidx < p.d && ok) v[k][nv] = *reinterpret_cast<const float4*>(p.partials + (long long)(first + sidx) * p.d + cidx);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int nv = 0; nv < NV; ++nv) {
+        acc[nv][0] = fmaf(v[k][nv].x, f[k], acc[nv][0]); acc[nv][1] = fmaf(v[k][nv].y, f[k], acc[nv][1]);
+        acc[nv][2] = fmaf(v[k][nv].z, f[k], acc[nv][2]); acc[nv][3] = fmaf(v[k][nv].w, f[k], acc[nv][3]);
+      }
+  }
+}
+
 template <int NV, bool GAT>
 __global__ void __launch_bounds__(FIX_WARPS * 32)
 spmm_fixup_kernel(SpmmParams p) {
-  const int lane = threadIdx.x & 31;
-  const int m = blockIdx.x * FIX_WARPS + (threadIdx.x >> 5);
-  if (m >= p.n_multi) return;
-  const int row = __ldg(p.multi_row + m);
-  const int first = __ldg(p.multi_first_slot + m), n = __ldg(p.multi_n_slots + m);
-  float acc[NV][4];
-#pragma unroll
-  for (int nv = 0; nv < NV; ++nv)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[nv][q] = 0.f;
-  float M = -INFINITY, Lsum = 0.f;
-  if constexpr (GAT) {
-    for (int sidx = 0; sidx < n; ++sidx) M = fmaxf(M, p.partials_ml[2 * (first + sidx)]);
-  }
-  for (int sidx = 0; sidx < n; ++sidx) {
-    float f = 1.f;
-    if constexpr (GAT) {
-      const float ms = p.partials_ml[2 * (first + sidx)];
-      f = (ms == -INFINITY) ? 0.f : __expf(ms - M);
-      Lsum += p.partials_ml[2 * (first + sidx) + 1] * f;
-    }
-#pragma unroll
-    for (int nv = 0; nv < NV; ++nv) {
-      const int cidx = lane * 4 + nv * 128;
-      if (cidx < p.d) {
-        const float4 v = *reinterpret_cast<const float4*>(p.partials + (long long)(first + sidx) * p.d + cidx);
-        acc[nv][0] = fmaf(v.x, f, acc[nv][0]); acc[nv][1] = fmaf(v.y, f, acc[nv][1]);
-        acc[nv][2] = fmaf(v.z, f, acc[nv][2]); acc[nv][3] = fmaf(v.w, f, acc[nv][3]);
+  __shared__ __align__(16) float s_acc[FIX_WARPS][NV * 128];
+  __shared__ float s_red[FIX_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- phase 1: one warp per short row ----
+  {
+    const int m = blockIdx.x * FIX_WARPS + warp;
+    const int n = m < p.n_multi ? __ldg(p.multi_n_slots + m) : 0;
+    if (n > 0 && n <= FIX_LONG) {
+      const int row = __ldg(p.multi_row + m), first = __ldg(p.multi_first_slot + m);
+      float acc[NV][4] = {};
+      float M = -INFINITY, Lsum = 0.f;
+      if constexpr (GAT) {
+        for (int sidx = 0; sidx < n; ++sidx) M = fmaxf(M, p.partials_ml[2 * (first + sidx)]);
       }
+      fixup_accumulate<NV, GAT>(p, first, 0, 1, n, lane, M, acc, Lsum);
+      const float sc = GAT ? 1.f / (Lsum + 1e-16f) : (p.dinv ? __ldg(p.dinv + row) : 1.f);
+#pragma unroll
+      for (int nv = 0; nv < NV; ++nv)
+        row_epilogue4(p, row, lane * 4 + nv * 128, sc, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
     }
   }
-  const float sc = GAT ? 1.f / (Lsum + 1e-16f) : (p.dinv ? __ldg(p.dinv + row) : 1.f);
+  // ---- phase 2: the CTA's long rows, one after the other, all warps on each (CTA-uniform control flow) ----
+  for (int r = 0; r < FIX_WARPS; ++r) {
+    const int m = blockIdx.x * FIX_WARPS + r;
+    if (m >= p.n_multi) break;
+    const int n = __ldg(p.multi_n_slots + m);
+    if (n <= FIX_LONG) continue;
+    const int row = __ldg(p.multi_row + m), first = __ldg(p.multi_first_slot + m);
+    float M = -INFINITY;
+    if constexpr (GAT) {
+      for (int sidx = threadIdx.x; sidx < n; sidx += FIX_WARPS * 32) M = fmaxf(M, p.partials_ml[2 * (first + sidx)]);
+      M = warp_max(M);
+      if (lane == 0) s_red[warp] = M;
+      __syncthreads();
+      M = s_red[0];
 #pragma unroll
-  for (int nv = 0; nv < NV; ++nv)
-    row_epilogue4(p, row, lane * 4 + nv * 128, sc, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
+      for (int w = 1; w < FIX_WARPS; ++w) M = fmaxf(M, s_red[w]);
+      __syncthreads();
+    }
+    float acc[NV][4] = {};
+    float Lsum = 0.f;
+    fixup_accumulate<NV, GAT>(p, first, warp, FIX_WARPS, n, lane, M, acc, Lsum);
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv)
+      *reinterpret_cast<float4*>(&s_acc[warp][nv * 128 + lane * 4]) = make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]);
+    if (GAT && lane == 0) s_red[warp] = Lsum;
+    __syncthreads();
+    if (warp == 0) {
+      float L = 0.f;
+      float4 t[NV];
+#pragma unroll
+      for (int nv = 0; nv < NV; ++nv) t[nv] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < FIX_WARPS; ++w) {
+        if (GAT) L += s_red[w];
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv) {
+          const float4 x = *reinterpret_cast<const float4*>(&s_acc[w][nv * 128 + lane * 4]);
+          t[nv].x += x.x; t[nv].y += x.y; t[nv].z += x.z; t[nv].w += x.w;
+        }
+      }
+      const float sc = GAT ? 1.f / (L + 1e-16f) : (p.dinv ? __ldg(p.dinv + row) : 1.f);
+#pragma unroll
+      for (int nv = 0; nv < NV; ++nv) row_epilogue4(p, row, lane * 4 + nv * 128, sc, t[nv]);
+    }
+    __syncthreads();
+  }
 }
 
 template <int G, int NV, typename T>

@@ -1,2 +1,5 @@
 set -x
-for d in 8 9 10 11 15; do echo "== dbg $d"; B200REC_TC_DBG=$d python tools/gemm_bench.py 2>&1 | grep "9447x2094->256 \(tf32\|bf16\)"; done > gpurun_out/gb25_dbg.log 2>&1
+python -m pytest tests/test_kernels_gpu.py tests/test_models_gpu.py tests/test_graph_build_gpu.py -m gpu -x -q > gpurun_out/t27.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/t27.log
+python bench.py --workload k3hbm --no-cpu-baseline > gpurun_out/b27_k3hbm.json 2> gpurun_out/b27_k3hbm.err
+python bench.py --workload graph --no-cpu-baseline --skip-hbm-regime > gpurun_out/b27_graph.json 2> gpurun_out/b27_graph.err

@@ -248,6 +248,37 @@ def test_graph_ncf_gat_medium_vs_oracle():
         assert maxnorm_rel(m(g, uid.to(DEV), iid.to(DEV), DEV, mask_targets=True), ref_masked) < TOL
 
 
+@pytest.mark.parametrize('conv', ['LightGCN', 'LightGAT'])
+def test_graph_ncf_long_rows_cta_fixup_vs_oracle(conv):
+    """rows cut into MORE than 64 chunks (the CTA-cooperative branch of spmm_fixup_kernel): index built with 16-edge chunks, so
+    that the hot items of a small Zipf graph own hundreds of partial slots"""
+    from deeprecommendation_b200.graph import GraphIndex, IdTable, create_graph
+    n_users, n_items, n, F, d_emb = 2500, 120, 60_000, 24, 64
+    users, items, ratings = synth.interactions_zipf(n_users, n_items, n, seed=15)
+    rng = np.random.default_rng(8)
+    fi, fu = rng.standard_normal((n_items, F)).astype(np.float32), rng.standard_normal((n_users, F)).astype(np.float32)
+    kw = dict(item_dim=F, user_dim=F, num_gnn_layers=2, hetero=True, node_emb=d_emb, mlp_dense_layers=[64], dropout_rate=0.2, convType=conv)
+    sd = synth.to_torch(synth.graph_ncf_weights(seed=14, **kw))
+    ref_g = R.create_graph(users, items, ratings, np.arange(n_users), np.arange(n_items))
+    gd = {k: (torch.from_numpy(v) if v is not None else None) for k, v in ref_g.items()}
+    gd['item_features'], gd['user_features'] = torch.from_numpy(fi), torch.from_numpy(fu)
+    pick = rng.permutation(n)[:128]
+    uid, iid = torch.from_numpy(ref_g['user2item_edge_index'][0][pick]), torch.from_numpy(ref_g['user2item_edge_index'][1][pick])
+    ref = R.graph_ncf_forward(sd, gd, uid, iid, 2, convType=conv)
+    g = create_graph(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), torch.from_numpy(ratings).to(DEV),
+                     torch.from_numpy(fi).to(DEV), torch.from_numpy(fu).to(DEV),
+                     IdTable(torch.arange(n_users, device=DEV)), IdTable(torch.arange(n_items, device=DEV)))
+    idx = GraphIndex(g.user2item_edge_index, g.item2user_edge_index, g.user2item_edge_attr, g.item2user_edge_attr, n_users + n_items, chunk=16)
+    assert int(idx.row_ptr.diff().max()) > 64 * 16                      # some row really takes the long-row branch
+    object.__setattr__(g, '_b200rec_index', idx)
+    m = _models().GraphNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out = m(g, uid.to(DEV), iid.to(DEV), DEV)
+        assert maxnorm_rel(out, ref) < TOL
+        assert torch.equal(out, m(g, uid.to(DEV), iid.to(DEV), DEV))
+
+
 def test_graph_ncf_missing_target_edge_raises_keyerror():
     d, sd, kw = load('graph_ncf_hetero_mean')
     build, _, _ = load('graph_build_binary0')
