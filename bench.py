@@ -292,7 +292,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     elif name == 'attention_pool':
         nnz_mean = float(np.mean(w['nnz']))
         alg_bytes = nnz_mean * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)
-        kname = 'um_compact_kernel + attention_wseg_tma_kernel + attention_merge_kernel (K2)'
+        kname = 'um_compact_kernel + attention_wseg_kernel + attention_merge_kernel (K2)'
     else:
         alg_bytes, kname = 0.0, name
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
@@ -301,6 +301,22 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
             'peak_source': peaks['src'],
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
+    if name in ('linear_tc', 'linear_tc_batch'):
+        # roofline_time = max(bytes / HBM_peak, flops / pipe_peak).  In fp32-parity mode every product is issued as three
+        # TF32 MMAs (hi·hi + hi·lo + lo·hi), so the pipe peak of THIS arithmetic is TF32_peak / 3; MEASURED_PEAKS.json has no TF32 figure,
+        # the dense TF32 rate is half the bf16 one (same tcgen05 pipe, 32-bit operands).  The larger of the two times names the bound.
+        M, K, N = meta
+        flops = 2.0 * M * K * N
+        issue = 3.0 if w.get('gemm', 'tf32x3') == 'tf32x3' else 1.0
+        pipe = (peaks['bf16_tflops'] / 2.0 if issue == 3.0 else peaks['bf16_tflops']) / issue
+        t_hbm, t_pipe = alg_bytes / (peaks['hbm_gbs'] * 1e9), flops / (pipe * 1e12)
+        hbm_view = {'achieved': roof['achieved'], 'peak': roof['peak'], 'unit': 'GB/s', 'frac': roof['frac']}
+        if t_pipe > t_hbm:
+            ach = flops / (kms * 1e-3) / 1e12
+            roof.update({'bound': 'tensor', 'achieved': round(ach, 1), 'peak': round(pipe, 1), 'unit': 'TFLOP/s', 'frac': round(ach / pipe, 4),
+                         'algorithmic_flops': int(flops), 'issued_tflops': round(ach * issue, 1),
+                         'peak_source': peaks['src'] + ': bf16 burst %.0f TFLOP/s -> TF32 = half -> / 3 MMAs per product (fp32 parity)' % peaks['bf16_tflops']
+                         if issue == 3.0 else peaks['src'], 'hbm_view': hbm_view})
     # the second roofline kernel of this workload, whichever of K1a / K2 is not the dominant one (same formulas)
     other = []
     for (n2, m2), (k2, _) in ops_ms.items():
@@ -308,7 +324,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
             continue
         if n2 == 'attention_pool':
             ab = float(np.mean(w['nnz'])) * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)
-            other.append({'kernel': 'um_compact_kernel + attention_wseg_tma_kernel + attention_merge_kernel (K2; tables L2-resident at this size)',
+            other.append({'kernel': 'um_compact_kernel + attention_wseg_kernel + attention_merge_kernel (K2; tables L2-resident at this size)',
                           'kernel_ms': round(k2, 4), 'algorithmic_bytes': int(ab), 'achieved': round(ab / (k2 * 1e-3) / 1e9, 1), 'unit': 'GB/s',
                           'frac': round(ab / (k2 * 1e-3) / 1e9 / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention_pool')})
         elif n2 in ('linear_tc', 'linear_tc_batch') and m2[1] >= 512:

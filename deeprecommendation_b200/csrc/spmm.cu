@@ -24,6 +24,10 @@
 namespace b200rec {
 
 constexpr int SPMM_WARPS = 8;
+#ifndef SPMM_MIN_CTAS
+#define SPMM_MIN_CTAS 4      // 4 CTAs x 8 warps at 64 registers (a few spilled index registers) beat 3 CTAs without spills: 10.7 vs 12.1 ms
+#endif                      // per HBM-regime layer — resident warps, not per-warp latency, carry the gathers
+
 constexpr int FIX_WARPS = 8;
 
 struct SpmmParams {
@@ -112,7 +116,7 @@ __device__ __forceinline__ uint4 ldg16_keep(const unsigned char* p, uint64_t pol
 // 2 SHFL + 1 IMAD.WIDE.U32 + 1 LDG.128 + 4 FFMA (the first version spent ~26 instructions per edge on predicated
 // 64-bit address arithmetic and zero-fill moves — profiles/r01).
 template <int G, int NV, typename T, bool GAT, bool KEEP, int UN = 8>
-__global__ void __launch_bounds__(SPMM_WARPS * 32, (NV == 1 && UN == 8 && !GAT) ? 4 : 1)
+__global__ void __launch_bounds__(SPMM_WARPS * 32, (NV == 1 && UN == 8 && !GAT) ? SPMM_MIN_CTAS : 1)
 spmm_chunk_kernel(SpmmParams p) {
   constexpr int EPW = 32 / G;                       // edges per warp step
   constexpr int VPL = Lane16<T>::VPL;
@@ -123,6 +127,8 @@ spmm_chunk_kernel(SpmmParams p) {
   const int g = lane / G, sl = lane % G;
   const int row = __ldg(p.chunk_row + chunk);
   const int s = __ldg(p.chunk_start + chunk);
+  const int slot = __ldg(p.chunk_slot + chunk);                  // (epilogue operands are fetched up front, off the critical path:
+  const float dinv_row = p.dinv ? __ldg(p.dinv + row) : 1.f;     //  ncu showed the final FMUL waiting on dinv[row])
   const int e = min(s + p.chunk_size, __ldg(p.row_ptr + row + 1));
   const unsigned stride_bytes = (unsigned)(p.ld_t * (long long)sizeof(T));
   const uint64_t keep = KEEP ? l2_keep_policy() : 0ull;
@@ -218,8 +224,7 @@ spmm_chunk_kernel(SpmmParams p) {
       for (int q = 0; q < VPL; ++q) acc[nv][q] += __shfl_xor_sync(FULL, acc[nv][q], o);
 
   if (g == 0) {
-    const int slot = __ldg(p.chunk_slot + chunk);
-    float sc = (slot < 0 && p.dinv) ? __ldg(p.dinv + row) : 1.f;
+    float sc = (slot < 0 && p.dinv) ? dinv_row : 1.f;
     if constexpr (GAT) {
       if (slot < 0) sc = 1.f / (gat_l + 1e-16f);               // PyG softmax: exp(s - max) / (sum + 1e-16)
       else if (sl == 0) { p.partials_ml[2 * slot] = gat_m; p.partials_ml[2 * slot + 1] = gat_l; }

@@ -11,6 +11,8 @@ REPORTS = {                      # bench workload key -> report (the command lin
     'attention_pool': 'gpurun_out/prof_attseg_v3.ncu-rep',
     'graph': 'gpurun_out/prof_spmm_v4.ncu-rep',
     'allpairs': 'gpurun_out/prof_allpairs_v2.ncu-rep',
+    'k2_hbm': 'gpurun_out/prof_k2hbm_v2.ncu-rep',        # attention_wseg_tma_kernel, bench.py --workload k2hbm
+    'k3_hbm': 'gpurun_out/prof_k3hbm_v1.ncu-rep',        # spmm_chunk_kernel, bench.py --workload k3hbm
 }
 UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
 
@@ -30,14 +32,15 @@ def dram_bytes(path):
 
 
 def main():
-    res = {}
+    out = os.path.join(ROOT, 'profiles', 'traffic.json')
+    res = json.load(open(out)) if os.path.exists(out) else {}       # reports of earlier sessions may be gone: keep their numbers
     for key, rel in REPORTS.items():
         p = os.path.join(ROOT, rel)
         if os.path.exists(p):
             b, k = dram_bytes(p)
             res[key] = int(b)
             print(f'{key}: {b / 1e6:.1f} MB per launch  ({k[:60]})')
-    json.dump(res, open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w'), indent=1)
+    json.dump(res, open(out, 'w'), indent=1)
 
 
 if __name__ == '__main__':
