@@ -935,6 +935,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # stdout carries exactly one JSON line, whatever NCCL_DEBUG says
         dist_mod.init_process_group('nccl', device_id=dev)
         dist = dist_mod
     peaks = _peaks()

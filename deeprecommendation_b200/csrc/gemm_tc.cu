@@ -112,6 +112,10 @@ struct TcParams {
   const unsigned char* Wp;   // optional: W pre-packed by pack_weights_kernel (swizzled tiles), moved by TMA bulk copies
   const long long* row_index;   // optional: row m of the GEMM is row row_index[m] of X (resident profile table + ids)
   int dbg;     // experiments only (B200REC_TC_DBG): 1 = no MMA, 2 = no prefetch loads, 4 = no proxy fence
+  // split-K (b200rec_linear_tc_splitk): CTA z = blockIdx.z owns k-blocks [z*kb_per_split, ...) and writes its raw fp32 tile to
+  // partial[z] (M x N, ld N); bias / scale / activation are applied by tc_splitk_reduce_kernel.  0 = the whole K in one CTA.
+  int kb_per_split;
+  float* partial;
 };
 
 // Several GEMMs of the same K and mode in ONE launch (b200rec_linear_tc_batch): problem q owns the m-tiles
@@ -257,8 +261,10 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = ((int)blockIdx.y - batch.tile_start[q]) * TC_BM, n0 = blockIdx.x * TC_BN;
-  const int num_kb = (p.K + KB - 1) / KB;
-  const int kb_shift = (int)((blockIdx.y * 7u + blockIdx.x * 3u) % (unsigned)num_kb);
+  const int num_kb_total = (p.K + KB - 1) / KB;
+  const int kb_base = p.kb_per_split ? (int)blockIdx.z * p.kb_per_split : 0;
+  const int num_kb = p.kb_per_split ? min(p.kb_per_split, num_kb_total - kb_base) : num_kb_total;
+  const int kb_shift = (int)((blockIdx.y * 7u + blockIdx.x * 3u + blockIdx.z) % (unsigned)num_kb);
 
   if (tid == 0) {
 #pragma unroll
@@ -289,15 +295,15 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     aa.init(p.ldx, m0, p.M, warp, lane, p.row_index);
     if constexpr (!WPACK) ab.init(p.ldw, n0, p.N, warp, lane);
     // packed W: tile (n-tile, k-block) = PLANES x 16 KB, already converted and swizzled (pack_weights_kernel)
-    const unsigned char* wp_tiles = WPACK ? p.Wp + (size_t)blockIdx.x * num_kb * (PLANES * TILE_BYTES) : nullptr;
+    const unsigned char* wp_tiles = WPACK ? p.Wp + ((size_t)blockIdx.x * num_kb_total + kb_base) * (PLANES * TILE_BYTES) : nullptr;
     int kstore = kb_shift;                                    // k-block index of the stage being stored
     TileRegs<MODE, EPL> xa[PF + 1], xb[PF + 1];
     int kload = kb_shift;                                     // k-block index of the next load
 #pragma unroll
     for (int d = 0; d < PF; ++d) {
       if (d < num_kb) {
-        xa[d].template load<VEC>(p.X, aa, kload * KB, p.K);
-        if constexpr (!WPACK) xb[d].template load<VEC>(p.W, ab, kload * KB, p.K);
+        xa[d].template load<VEC>(p.X, aa, (kb_base + kload) * KB, p.K);
+        if constexpr (!WPACK) xb[d].template load<VEC>(p.W, ab, (kb_base + kload) * KB, p.K);
         kload = (kload + 1 == num_kb) ? 0 : kload + 1;
       }
     }
@@ -311,8 +317,8 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
           const int s = kb % NSTAGE;
           const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
           if (kb + PF < num_kb && !(p.dbg & 2)) {              // loads of k-block kb+PF fly while kb is converted
-            xa[(j + PF) % (PF + 1)].template load<VEC>(p.X, aa, kload * KB, p.K);
-            if constexpr (!WPACK) xb[(j + PF) % (PF + 1)].template load<VEC>(p.W, ab, kload * KB, p.K);
+            xa[(j + PF) % (PF + 1)].template load<VEC>(p.X, aa, (kb_base + kload) * KB, p.K);
+            if constexpr (!WPACK) xb[(j + PF) % (PF + 1)].template load<VEC>(p.W, ab, (kb_base + kload) * KB, p.K);
             kload = (kload + 1 == num_kb) ? 0 : kload + 1;
           }
           mbar_wait(&empty_bar[s], ph ^ 1u);                  // first pass through the ring: returns immediately
@@ -336,7 +342,13 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     tc_fence_after();
     const int quad = warp & 3, chalf = warp >> 2;
     const int row = m0 + quad * 32 + lane;
-    const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
+    // split-K: the raw tile goes to this split's slab of the workspace; the epilogue arithmetic happens after the reduction
+    const bool split = p.kb_per_split > 0;
+    const float* e_bias = split ? nullptr : p.bias;
+    const int e_relu = split ? 0 : p.relu, e_bf16 = split ? 0 : p.y_bf16;
+    void* e_Y = split ? (void*)(p.partial + (size_t)blockIdx.z * (size_t)p.M * (size_t)p.N) : p.Y;
+    const long long e_ldy = split ? (long long)p.N : p.ldy;
+    const float rs = (!split && p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int col0 = chalf * 64 + cc * 32;
@@ -374,20 +386,20 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
             const int gc = gcol0 + j + e;
             float x = acc[j + e];
             if (gc < p.N) {
-              if (p.bias) x += __ldg(p.bias + gc);
+              if (e_bias) x += __ldg(e_bias + gc);
               x *= rs;
-              if (p.relu) x = fmaxf(x, 0.f);
+              if (e_relu) x = fmaxf(x, 0.f);
             }
             o[e] = x;
           }
           const int gc = gcol0 + j;
-          if (p.y_bf16) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.Y) + (long long)row * p.ldy + gc;
+          if (e_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e_Y) + (long long)row * e_ldy + gc;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (gc + e < p.N) dst[e] = __float2bfloat16_rn(o[e]);
           } else {
-            float* dst = reinterpret_cast<float*>(p.Y) + (long long)row * p.ldy + gc;
+            float* dst = reinterpret_cast<float*>(e_Y) + (long long)row * e_ldy + gc;
             if (gc + 3 < p.N && ((((uintptr_t)dst) & 15) == 0)) {
               *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
@@ -484,6 +496,59 @@ static size_t packed_weight_bytes(long long N, long long K, int mode) {
   return (size_t)((N + 127) / 128) * (size_t)((K + KB - 1) / KB) * PL * TILE_BYTES;
 }
 
+// split-K: partial[z] (M x N) summed in split order (deterministic), then bias, row scale, activation
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, void* __restrict__ Y, long long ldy, int y_bf16,
+                        const float* __restrict__ bias, const float* __restrict__ row_scale, int relu) {
+  const long long total4 = (long long)M * N / 4;               // N % 4 == 0 (launcher)
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const long long idx = i4 * 4;
+  const int row = (int)(idx / N), col = (int)(idx % N);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z0 = 0; z0 < splits; z0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = (z0 + k < splits) ? __ldcs(reinterpret_cast<const float4*>(partial + (long long)(z0 + k) * M * N + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+  }
+  float o[4] = {s.x, s.y, s.z, s.w};
+  const float rs = row_scale ? __ldg(row_scale + row) : 1.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (bias) o[e] += __ldg(bias + col + e);
+    o[e] *= rs;
+    if (relu) o[e] = fmaxf(o[e], 0.f);
+  }
+  if (y_bf16) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Y) + (long long)row * ldy + col;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[e] = __float2bfloat16_rn(o[e]);
+  } else {
+    float* dst = reinterpret_cast<float*>(Y) + (long long)row * ldy + col;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[e] = o[e];
+  }
+}
+
+// number of K splits for a GEMM whose output tiles alone leave most SMs idle (0 = do not split)
+static int tc_splits(long long M, long long N, long long K, int mode, int* kb_per_split) {
+  const int KB = (mode == TC_BF16) ? 64 : 32;
+  const long long tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int num_kb = (int)((K + KB - 1) / KB);
+  const int sms = b200rec_num_sms();
+  *kb_per_split = 0;
+  if (tiles * 2 > sms || num_kb < 8 || (N % 4) != 0) return 0;
+  int want = (int)(sms / tiles);
+  if (want > num_kb / 3) want = num_kb / 3;                    // at least 3 k-blocks per CTA
+  if (want < 2) return 0;
+  const int kbps = (num_kb + want - 1) / want;
+  *kb_per_split = kbps;
+  return (num_kb + kbps - 1) / kbps;
+}
+
 template <int MODE, int EPL, bool VEC, bool WPACK>
 static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   constexpr int NSTAGE = (MODE == TC_BF16) ? 4 : 3;
@@ -496,9 +561,17 @@ static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   }
   int nmax = 0;
   for (int q = 0; q < b.n; ++q) nmax = b.prob[q].N > nmax ? b.prob[q].N : nmax;
-  dim3 grid(ceil_div_i(nmax, TC_BN), b.tile_start[b.n]);
+  const TcParams& p0 = b.prob[0];
+  const int nsplit = p0.kb_per_split ? ceil_div_i(ceil_div_i(p0.K, (MODE == TC_BF16) ? 64 : 32), p0.kb_per_split) : 1;
+  dim3 grid(ceil_div_i(nmax, TC_BN), b.tile_start[b.n], nsplit);
   gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK><<<grid, TC_THREADS, smem, st>>>(b);
   B200REC_CHECK_LAUNCH();
+  if (p0.kb_per_split) {
+    const long long total4 = (long long)p0.M * p0.N / 4;
+    tc_splitk_reduce_kernel<<<ceil_div_i(total4, 256), 256, 0, st>>>(p0.partial, nsplit, p0.M, p0.N, p0.Y, p0.ldy, p0.y_bf16, p0.bias,
+                                                                     p0.row_scale, p0.relu);
+    B200REC_CHECK_LAUNCH();
+  }
   return B200REC_OK;
 }
 
@@ -565,6 +638,8 @@ static int tc_fill(TcParams& p, const float* X, int64_t M, int64_t K, int64_t ld
   p.Y = Y; p.ldy = ldy; p.y_bf16 = y_dtype == B200REC_BF16; p.bias = bias; p.row_scale = row_scale; p.relu = relu;
   const char* e = getenv("B200REC_TC_DBG");
   p.dbg = e ? atoi(e) : 0;
+  p.kb_per_split = 0;
+  p.partial = nullptr;
   return B200REC_OK;
 }
 
@@ -582,6 +657,37 @@ extern "C" int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t l
   if (mode == B200REC_TC_TF32X3) return launch_tc<TC_TF32X3>(b, st);
   if (mode == B200REC_TC_BF16) return launch_tc<TC_BF16>(b, st);
   return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad mode");
+}
+
+extern "C" size_t b200rec_linear_tc_splitk_workspace(int64_t M, int64_t N, int64_t K, int mode) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int kbps = 0;
+  const int splits = tc_splits(M, N, K, mode == B200REC_TC_BF16 ? TC_BF16 : TC_TF32X3, &kbps);
+  return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+}
+
+extern "C" int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
+                                        const float* bias, const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode,
+                                        const void* packed_w, void* workspace, size_t workspace_bytes, b200rec_stream_t stream) {
+  TcBatch b;
+  b.n = 1;
+  const int rc = tc_fill(b.prob[0], X, M, K, ldx, W, N, ldw, bias, row_scale, relu, Y, ldy, y_dtype, packed_w, nullptr, 0);
+  if (rc) return rc;
+  if (M == 0) return B200REC_OK;
+  if (mode != B200REC_TC_TF32X3 && mode != B200REC_TC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_splitk: bad mode");
+  int kbps = 0;
+  const int splits = tc_splits(M, N, K, mode == B200REC_TC_BF16 ? TC_BF16 : TC_TF32X3, &kbps);
+  if (splits > 1) {
+    const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace % 16)) return b200rec_fail(B200REC_ERR_WORKSPACE, "linear_tc_splitk: workspace too small");
+    b.prob[0].kb_per_split = kbps;
+    b.prob[0].partial = (float*)workspace;
+  }
+  b.tile_start[0] = 0;
+  b.tile_start[1] = ceil_div_i(M, TC_BM);
+  for (int q = 1; q < TC_MAX_BATCH; ++q) b.tile_start[q + 1] = b.tile_start[1];
+  cudaStream_t st = (cudaStream_t)stream;
+  return mode == B200REC_TC_TF32X3 ? launch_tc<TC_TF32X3>(b, st) : launch_tc<TC_BF16>(b, st);
 }
 
 extern "C" int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode,

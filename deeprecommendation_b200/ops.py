@@ -106,6 +106,7 @@ def _dtype_code(dt):
 # large M, FFMA for the small ones (a 128-row tile per CTA cannot fill 148 SMs below ~2k rows).
 _gemm_engine = 'simt'
 TC_MIN_ROWS = 2048
+TC_SPLITK_MIN_ROWS = 128      # below TC_MIN_ROWS the tensor-core GEMM runs split-K (if K is long enough to be dealt out)
 SHORTK_MIN_ROWS = 4096  # below this a handful of 64x64 FFMA tiles is as fast as the persistent kernel's set-up
 TC_MIN_K = 512          # short-K GEMMs (the d x d GraphNCF transforms) are epilogue/latency-bound: FFMA is as fast there
 
@@ -186,6 +187,17 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
             L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                           _dtype_code(out.dtype), mode, _ptr(packed), _ptr(row_index), x_rows, _stream()), 'linear_tc')
         return out
+    if engine != 'simt' and row_index is None and TC_SPLITK_MIN_ROWS <= M < TC_MIN_ROWS and K >= TC_MIN_K and M * ldx < 2 ** 32:
+        # short-M, long-K (a batch of pairs against the F-wide profiles): split-K on the tensor cores
+        mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+        ws_bytes = lib.b200rec_linear_tc_splitk_workspace(M, N, K, mode)
+        if ws_bytes:
+            packed = _packed_weight(w, ldw, mode) if _pack_weights else None
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            with torch.cuda.device(x.device), _timed('linear_tc_splitk', (M, K, N)):
+                L.check(lib.b200rec_linear_tc_splitk(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
+                                                     _dtype_code(out.dtype), mode, _ptr(packed), _ptr(ws), ws_bytes, _stream()), 'linear_tc_splitk')
+            return out
     ws_bytes = lib.b200rec_linear_workspace(M, N, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     with torch.cuda.device(x.device), _timed('linear', (M, K, N)):

@@ -54,6 +54,14 @@ int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const floa
 int b200rec_linear_tc(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
                       const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w,
                       const int64_t* row_index, int64_t x_rows, b200rec_stream_t stream);
+/* Split-K form for SHORT-M, long-K GEMMs (a 512-pair batch against the F = 2094 profiles: 4 x 2 output tiles would occupy 8 of 148
+ * SMs): the k-blocks are dealt out over ~SMs / tiles CTAs per output tile, every CTA leaves a raw fp32 tile in `workspace`
+ * (b200rec_linear_tc_splitk_workspace bytes; 0 = the shape is not split and none is needed) and a second kernel adds the slabs in
+ * split order (deterministic) and applies bias / row_scale / ReLU.  N % 4 == 0 to be split. */
+size_t b200rec_linear_tc_splitk_workspace(int64_t M, int64_t N, int64_t K, int mode);
+int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
+                             const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w,
+                             void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
 /* Persistent short-K variant for the per-node transforms of GraphNCF (K in {32,64,96,128}, N <= 128; csrc/node_gemm.cu):
  * W stays in shared memory (`packed_w` = b200rec_pack_weights_tc(..., B200REC_TC_TF32X3)), row tiles are streamed, fp32 parity
  * by the 3xTF32 split.  X rows 16-byte aligned (ldx % 4 == 0); Y fp32. */

@@ -34,6 +34,33 @@ def test_linear_tc_tf32x3_fp32_parity(M, K, N):
     assert torch.all(out[:, :4] == 3.0) and torch.all(out[:, 4 + N:] == 3.0)
 
 
+@pytest.mark.parametrize('M,K,N', [(512, 2094, 256), (512, 2094, 128), (128, 2094, 128), (1000, 2093, 132), (257, 1024, 64), (2000, 4096, 256)])
+def test_linear_tc_splitk_fp32_parity(M, K, N):
+    """short-M, long-K shapes (a batch of pairs against the F-wide profiles) take the split-K tensor-core route of `linear_raw`:
+    same tolerance, bit-reproducible (the slabs are added in split order), epilogue applied after the reduction"""
+    from deeprecommendation_b200 import _lib as L
+    from deeprecommendation_b200 import ops
+    x, w, b, s = _case(M, K, N, M + K + 7)
+    assert L.lib().b200rec_linear_tc_splitk_workspace(M, N, K, L.TC_TF32X3) > 0
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    timer = ops.OpTimer()
+    ops.set_timer(timer)
+    try:
+        y = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='tf32x3')
+    finally:
+        ops.set_timer(None)
+    torch.cuda.synchronize()
+    assert any(name == 'linear_tc_splitk' for name, _ in timer.summary())
+    assert maxnorm_rel(y, ref) < 1e-5
+    assert torch.equal(y, ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='tf32x3'))
+    out = torch.full((M, N + 8), 3.0, device='cuda')
+    ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), s.cuda(), True, out=out[:, 4:4 + N], engine='tf32x3')
+    assert maxnorm_rel(out[:, 4:4 + N], (ref * s.double()[:, None]).relu()) < 1e-5
+    assert torch.all(out[:, :4] == 3.0) and torch.all(out[:, 4 + N:] == 3.0)
+    yb = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), out_dtype=torch.bfloat16, engine='tf32x3')
+    assert yb.dtype == torch.bfloat16 and maxnorm_rel(yb.float(), ref) < 1e-2
+
+
 @pytest.mark.parametrize('M,K,N', SHAPES[:5])
 def test_linear_tc_bf16(M, K, N):
     from deeprecommendation_b200 import ops
