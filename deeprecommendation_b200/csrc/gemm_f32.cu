@@ -276,8 +276,8 @@ extern "C" size_t b200rec_linear_workspace(int64_t M, int64_t N, int64_t K) {
 extern "C" int b200rec_linear(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
                               const float* bias, const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype,
                               void* workspace, size_t workspace_bytes, b200rec_stream_t stream) {
-  if (M < 0 || N <= 0 || K <= 0 || !W || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear: bad argument");
-  if (M == 0) return B200REC_OK;
+  if (M == 0) return B200REC_OK;                     // an empty batch is not an error (its buffers may be null)
+  if (M < 0 || N <= 0 || K <= 0 || !W || !Y || !X) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear: bad argument");
   if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear: dim > int32");
   if (ldx < K || ldw < K || ldy < N) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear: leading dimension too small");
   if (y_dtype != B200REC_F32 && y_dtype != B200REC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear: bad y_dtype");

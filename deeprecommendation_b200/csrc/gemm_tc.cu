@@ -626,7 +626,7 @@ extern "C" int b200rec_pack_weights_tc(const float* W, int64_t N, int64_t K, int
 static int tc_fill(TcParams& p, const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
                    const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, const void* packed_w,
                    const int64_t* row_index = nullptr, int64_t x_rows = 0) {
-  if (M < 0 || N <= 0 || K <= 0 || (!W && !packed_w) || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad argument");
+  if (M < 0 || N <= 0 || K <= 0 || (!W && !packed_w) || (M > 0 && (!X || !Y))) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: bad argument");
   if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: dim > int32");
   if (ldx < K || ldw < K || ldy < N) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: leading dimension too small");
   if ((row_index ? x_rows : M) * ldx >= (1LL << 32) || (!packed_w && N * ldw >= (1LL << 32))) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc: operand larger than 2^32 elements");

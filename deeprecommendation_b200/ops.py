@@ -168,6 +168,8 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     elif out.shape != (M, N) or out.stride(1) != 1:
         raise ValueError('linear: bad `out`')
     ldy = out.stride(0) if M > 1 else max(N, out.stride(0))
+    if M == 0:
+        return out                                   # empty batch: nothing to launch (nn.Linear returns an empty (0, N) too)
     lib = L.lib()
     engine = engine or _gemm_engine
     if (engine in ('tf32x3', 'shortk!') and row_index is None and K <= 128 and K % 32 == 0 and N <= 128 and (M >= SHORTK_MIN_ROWS or engine == 'shortk!')
@@ -322,6 +324,8 @@ def mlp_tower_raw(in0, in1, weights, biases, idx0=None, idx1=None):
     if idx1 is not None:
         idx1 = idx1.contiguous().long()
     out = torch.empty((B, prev), dtype=torch.float32, device=in0.device)
+    if B == 0:
+        return out
     with torch.cuda.device(in0.device), _timed('mlp_tower', (B, E0 + E1)):
         L.check(L.lib().b200rec_mlp_tower(_ptr(in0), ld0, _ptr(idx0), E0, _ptr(in1), ld1, _ptr(idx1), E1, B, C.byref(d), _ptr(out),
                                          prev, _stream()), 'mlp_tower')
@@ -465,6 +469,8 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
         d.train_cand_emb, d.train_rated_emb, d.E, d.atol, d.rtol = Ec.data_ptr(), Er.data_ptr(), Ec.shape[1], atol, rtol
     d.drop_zero_scores = int(drop_zero_scores)
     d.score_scale = float(score_scale)
+    if B == 0:
+        return (out, att) if return_attention_weights else out
     with torch.cuda.device(Pc.device), _timed('attention_pool', (B, I, H, U)):
         L.check(L.lib().b200rec_attention_pool(C.byref(d), _stream()), 'attention_pool')
     return (out, att) if return_attention_weights else out

@@ -1,0 +1,162 @@
+"""Edge cases of the hot path on a B200, each against the CPU oracle (oracle/restatement.py) on the same inputs:
+degenerate batch sizes, users with nothing rated, exact-zero centred ratings, odd layer widths, isolated graph nodes,
+repeated targets, binary graphs, k larger than the catalogue.  SURVEY.md §8a lists the semantics these must reproduce."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from oracle import synth
+from tests._golden import maxnorm_rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = 'cuda:0'
+
+
+def _models():
+    from deeprecommendation_b200.neural_collaborative_filtering import models
+    return models
+
+
+def _attention(kw, seed):
+    sd = synth.to_torch(synth.attention_ncf_weights(seed=seed, **kw))
+    m = _models().AttentionNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    return m, sd
+
+
+@pytest.mark.parametrize('engine', ['simt', 'tf32x3'])
+@pytest.mark.parametrize('B,I', [(1, 1), (1, 37), (3, 1), (2, 600)])
+def test_attention_tiny_batches(B, I, engine):
+    """a single candidate / a single rated item; both GEMM engines"""
+    from deeprecommendation_b200 import ops
+    kw = dict(item_dim=96, item_emb=32, user_emb=32, att_dense=16, mlp_dense_layers=[32], dropout_rate=0.2)
+    m, sd = _attention(kw, seed=21)
+    prof = synth.item_profiles(I + B, seed=22, f_binary=48, f_dense=48)
+    rng = np.random.default_rng(23)
+    um = (rng.integers(1, 11, (B, I)) * 0.5 - 2.75).astype(np.float32)
+    cand, rated, umt = torch.from_numpy(prof[I:]), torch.from_numpy(prof[:I]), torch.from_numpy(um)
+    ref, ref_att = R.attention_ncf_forward(sd, cand, rated, umt, return_attention_weights=True)
+    prev = ops.set_gemm_engine(engine)
+    try:
+        with torch.no_grad():
+            out, att = m(cand.to(DEV), rated.to(DEV), umt.to(DEV), return_attention_weights=True)
+    finally:
+        ops.set_gemm_engine(prev)
+    assert out.shape == (B, 1) and att.shape == (B, I)
+    assert maxnorm_rel(out, ref) < TOL and maxnorm_rel(att, ref_att) < TOL
+
+
+def test_attention_nothing_rated_and_exact_zero_ratings():
+    """row 0: all zeros (softmax over nothing -> NaN -> 0, user_emb = b_U, attention_ncf.py:208-209); row 1: one rated item;
+    row 2: several entries whose centred rating is EXACTLY 0.0 and therefore count as unrated (:158,192)"""
+    kw = dict(item_dim=128, item_emb=64, user_emb=64, att_dense=32, mlp_dense_layers=[64, 32], dropout_rate=0.2)
+    m, sd = _attention(kw, seed=31)
+    I, B = 50, 4
+    prof = synth.item_profiles(I + B, seed=32, f_binary=64, f_dense=64)
+    um = np.zeros((B, I), dtype=np.float32)
+    um[1, 7] = 1.25
+    um[2, :20] = np.where(np.arange(20) % 3 == 0, 0.0, 0.75).astype(np.float32)      # a 3.5-star rating of a user whose mean is 4.5: exactly 0
+    um[3] = (np.random.default_rng(33).integers(1, 11, I) * 0.5 - 2.75)
+    cand, rated, umt = torch.from_numpy(prof[I:]), torch.from_numpy(prof[:I]), torch.from_numpy(um)
+    ref, ref_att = R.attention_ncf_forward(sd, cand, rated, umt, return_attention_weights=True)
+    with torch.no_grad():
+        out, att = m(cand.to(DEV), rated.to(DEV), umt.to(DEV), return_attention_weights=True)
+    assert torch.isfinite(out).all()
+    assert maxnorm_rel(out, ref) < TOL and maxnorm_rel(att, ref_att) < TOL
+    assert torch.all(att[0] == 0) and torch.all(att[2, :20:3] == 0) and float(att[1, 7]) == 1.0
+
+
+@pytest.mark.parametrize('att_dense,user_emb', [(30, 50), (None, 64), (20, 34)])
+def test_attention_odd_widths(att_dense, user_emb):
+    """widths that are not multiples of 4 (padded internally) and the att_dense=None variant (a single Linear(2E, 1))"""
+    kw = dict(item_dim=80, item_emb=36, user_emb=user_emb, att_dense=att_dense, mlp_dense_layers=[48], dropout_rate=0.2)
+    m, sd = _attention(kw, seed=41)
+    I, B = 90, 17
+    prof = synth.item_profiles(I + B, seed=42, f_binary=40, f_dense=40)
+    rng = np.random.default_rng(43)
+    um = ((rng.integers(1, 11, (B, I)) * 0.5 - 2.75) * (rng.random((B, I)) < 0.4)).astype(np.float32)
+    cand, rated, umt = torch.from_numpy(prof[I:]), torch.from_numpy(prof[:I]), torch.from_numpy(um)
+    ref = R.attention_ncf_forward(sd, cand, rated, umt)
+    with torch.no_grad():
+        out = m(cand.to(DEV), rated.to(DEV), umt.to(DEV))
+    assert maxnorm_rel(out, ref) < TOL
+
+
+def test_basic_ncf_degenerate_batches():
+    kw = dict(item_dim=200, user_dim=120, item_emb=64, user_emb=32, mlp_dense_layers=[48, 16], dropout_rate=0.2)
+    sd = synth.to_torch(synth.basic_ncf_weights(seed=51, **kw))
+    m = _models().BasicNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    rng = np.random.default_rng(52)
+    for B in (1, 2, 129):
+        xu, xi = torch.from_numpy(rng.standard_normal((B, 120)).astype(np.float32)), torch.from_numpy(rng.random((B, 200)).astype(np.float32))
+        with torch.no_grad():
+            out = m(xu.to(DEV), xi.to(DEV))
+        assert out.shape == (B, 1) and maxnorm_rel(out, R.basic_ncf_forward(sd, xu, xi)) < TOL
+    with torch.no_grad():                                    # an empty batch gives an empty (0, 1) result, like nn.Linear does
+        out = m(torch.empty(0, 120, device=DEV), torch.empty(0, 200, device=DEV))
+    assert out.shape == (0, 1)
+
+
+def test_attention_empty_batch():
+    kw = dict(item_dim=96, item_emb=32, user_emb=32, att_dense=16, mlp_dense_layers=[32], dropout_rate=0.2)
+    m, _ = _attention(kw, seed=81)
+    rated = torch.from_numpy(synth.item_profiles(12, seed=82, f_binary=48, f_dense=48)).to(DEV)
+    with torch.no_grad():
+        out, att = m(torch.empty(0, 96, device=DEV), rated, torch.empty(0, 12, device=DEV), return_attention_weights=True)
+    assert out.shape == (0, 1) and att.shape == (0, 12)
+
+
+@pytest.mark.parametrize('binary', [False, True])
+def test_graph_isolated_nodes_repeated_targets_binary(binary):
+    """users / items that exist in the id tables but have no interaction (zero rows, deg^-1/2 = inf -> 0, gnn_ncf.py:49-50),
+    the same (user, item) pair several times in one batch, and the binary graph (r >= centre kept, no edge weights)"""
+    from deeprecommendation_b200.graph import IdTable, create_graph
+    n_users, n_items, n, F, d = 300, 200, 4000, 16, 32
+    users, items, ratings = synth.interactions_zipf(n_users - 40, n_items - 30, n, seed=61)      # the last 40 users / 30 items never interact
+    rng = np.random.default_rng(62)
+    fi, fu = rng.standard_normal((n_items, F)).astype(np.float32), rng.standard_normal((n_users, F)).astype(np.float32)
+    kw = dict(item_dim=F, user_dim=F, num_gnn_layers=2, hetero=True, node_emb=d, mlp_dense_layers=[32], dropout_rate=0.2)
+    sd = synth.to_torch(synth.graph_ncf_weights(seed=63, **kw))
+    ref_g = R.create_graph(users, items, ratings, np.arange(n_users), np.arange(n_items), binary=binary)
+    gd = {k: (torch.from_numpy(v) if v is not None else None) for k, v in ref_g.items()}
+    gd['item_features'], gd['user_features'] = torch.from_numpy(fi), torch.from_numpy(fu)
+    e = ref_g['user2item_edge_index']
+    pick = np.array([0, 0, 0, 5, 5, e.shape[1] - 1, 17])
+    uid = torch.cat((torch.from_numpy(e[0][pick]), torch.tensor([n_items + n_users - 1, n_items + n_users - 2])))     # + two isolated users
+    iid = torch.cat((torch.from_numpy(e[1][pick]), torch.tensor([n_items - 1, 3])))                                   # + an isolated item
+    ref = R.graph_ncf_forward(sd, gd, uid, iid, 2)
+    g = create_graph(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), torch.from_numpy(ratings).to(DEV),
+                     torch.from_numpy(fi).to(DEV), torch.from_numpy(fu).to(DEV),
+                     IdTable(torch.arange(n_users, device=DEV)), IdTable(torch.arange(n_items, device=DEV)), binary=binary)
+    assert np.array_equal(g.user2item_edge_index.cpu().numpy(), e)
+    m = _models().GraphNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out = m(g, uid.to(DEV), iid.to(DEV), DEV)
+    assert torch.isfinite(out).all() and maxnorm_rel(out, ref) < TOL
+    with torch.no_grad():                                    # an empty batch of targets
+        none = m(g, torch.empty(0, dtype=torch.int64, device=DEV), torch.empty(0, dtype=torch.int64, device=DEV), DEV)
+    assert none.shape == (0, 1)
+
+
+def test_topk_k_larger_than_catalogue():
+    """recommend(k) with fewer items than k: short rows are padded with (-inf, -1), ties go to the lower item index"""
+    kw = dict(item_dim=64, user_dim=64, item_emb=32, user_emb=32, mlp_dense_layers=[64, 32], dropout_rate=0.2)
+    sd = synth.to_torch(synth.basic_ncf_weights(seed=71, **kw))
+    m = _models().BasicNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    rng = np.random.default_rng(72)
+    xu, xi = torch.from_numpy(rng.standard_normal((9, 64)).astype(np.float32)), torch.from_numpy(rng.random((6, 64)).astype(np.float32))
+    xi[4] = xi[2]                                              # two identical items -> a tie
+    with torch.no_grad():
+        val, idx = m.recommend(xu.to(DEV), xi.to(DEV), k=10)
+    assert val.shape == (9, 10) and idx.shape == (9, 10)
+    assert torch.all(idx[:, 6:] == -1) and torch.all(torch.isinf(val[:, 6:]) & (val[:, 6:] < 0))
+    scores = R.basic_ncf_all_pairs(sd, xu, xi)
+    ref_val, ref_idx = R.topk_stable(scores, 6)
+    assert torch.equal(idx[:, :6].cpu(), ref_idx) and maxnorm_rel(val[:, :6], ref_val) < TOL
+    pos2, pos4 = (idx[:, :6] == 2).nonzero()[:, 1], (idx[:, :6] == 4).nonzero()[:, 1]
+    assert torch.all(pos2 < pos4)
