@@ -13,8 +13,10 @@ namespace b200rec {
 constexpr int MLP_THREADS = 256;
 constexpr int MLP_KC = 32;             // k extent of a staged W tile
 constexpr int MLP_WS = MLP_KC + 4;     // padded row stride (floats) of the tile
+// W tiles in flight = template parameter MLP_NSTG: 4 for small batches (a CTA of a 512-pair batch is a chain of ~20 dependent
+// 36 KB tile loads out of L2 — 64 CTAs, each streaming all the weights), 2 when there are CTAs enough to overlap each other.
 
-template <int TM>
+template <int TM, int MLP_NSTG>
 __global__ void __launch_bounds__(MLP_THREADS)
 mlp_tower_kernel(const float* __restrict__ in0, long long ld0, const int64_t* __restrict__ idx0, int E0,
                  const float* __restrict__ in1, long long ld1, const int64_t* __restrict__ idx1, int E1, long long B,
@@ -22,7 +24,7 @@ mlp_tower_kernel(const float* __restrict__ in0, long long ld0, const int64_t* __
   extern __shared__ __align__(16) float smem[];
   float* buf0 = smem;
   float* buf1 = smem + (size_t)TM * stride;
-  float* wtile = smem + (size_t)2 * TM * stride;      // 2 x [256 x 36] floats
+  float* wtile = smem + (size_t)2 * TM * stride;      // MLP_NSTG x [256 x 36] floats
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row0 = (long long)blockIdx.x * TM;
 
@@ -83,16 +85,17 @@ mlp_tower_kernel(const float* __restrict__ in0, long long ld0, const int64_t* __
           }
           asm volatile("cp.async.commit_group;\n" ::: "memory");
         };
-        stage(0, 0);
+#pragma unroll
+        for (int s0 = 0; s0 < MLP_NSTG - 1; ++s0) {
+          if (s0 < n_kc) stage(s0, s0);
+          else asm volatile("cp.async.commit_group;\n" ::: "memory");      // empty group: keeps the count uniform
+        }
         for (int kc = 0; kc < n_kc; ++kc) {
-          if (kc + 1 < n_kc) {
-            stage(kc + 1, (kc + 1) & 1);
-            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-          } else {
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-          }
+          if (kc + MLP_NSTG - 1 < n_kc) stage(kc + MLP_NSTG - 1, (kc + MLP_NSTG - 1) % MLP_NSTG);
+          else asm volatile("cp.async.commit_group;\n" ::: "memory");
+          asm volatile("cp.async.wait_group %0;\n" ::"n"(MLP_NSTG - 1) : "memory");      // tile kc has landed
           __syncthreads();
-          const float* wt = wtile + (size_t)(kc & 1) * MLP_THREADS * MLP_WS + (size_t)tid * MLP_WS;
+          const float* wt = wtile + (size_t)(kc % MLP_NSTG) * MLP_THREADS * MLP_WS + (size_t)tid * MLP_WS;
           const int kbase = kc * MLP_KC;
           const int kn = min(MLP_KC, Kd - kbase);
 #pragma unroll 4
@@ -207,17 +210,17 @@ extern "C" int b200rec_mlp_tower(const float* in0, int64_t ld0, const int64_t* i
   // small batches: fewer rows per CTA so that more SMs take part
   const bool small = B < (long long)16 * sms * 2;
   const int TM = small ? 8 : 16;
-  size_t smem = ((size_t)2 * TM * stride + (size_t)2 * MLP_THREADS * MLP_WS) * sizeof(float);
+  size_t smem = ((size_t)2 * TM * stride + (size_t)(small ? 4 : 2) * MLP_THREADS * MLP_WS) * sizeof(float);
   if (smem > 200 * 1024) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "mlp_tower: layer too wide for shared memory");
   long long grid = (B + TM - 1) / TM;
   if (grid > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "mlp_tower: batch too large");
   if (small) {
-    B200REC_CUDA(cudaFuncSetAttribute(mlp_tower_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tower_kernel<8><<<(unsigned)grid, MLP_THREADS, smem, st>>>(in0, ld0, idx0, E0, in1, ld1, idx1, E1, B, *mlp, out, ldo,
+    B200REC_CUDA(cudaFuncSetAttribute(mlp_tower_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_tower_kernel<8, 4><<<(unsigned)grid, MLP_THREADS, smem, st>>>(in0, ld0, idx0, E0, in1, ld1, idx1, E1, B, *mlp, out, ldo,
                                                                   stride, vec_ok);
   } else {
-    B200REC_CUDA(cudaFuncSetAttribute(mlp_tower_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tower_kernel<16><<<(unsigned)grid, MLP_THREADS, smem, st>>>(in0, ld0, idx0, E0, in1, ld1, idx1, E1, B, *mlp, out, ldo,
+    B200REC_CUDA(cudaFuncSetAttribute(mlp_tower_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_tower_kernel<16, 2><<<(unsigned)grid, MLP_THREADS, smem, st>>>(in0, ld0, idx0, E0, in1, ld1, idx1, E1, B, *mlp, out, ldo,
                                                                    stride, vec_ok);
   }
   B200REC_CHECK_LAUNCH();
