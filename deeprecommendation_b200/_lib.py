@@ -29,7 +29,7 @@ class AttentionDesc(C.Structure):
                 ('B', c_i64), ('I', c_i64), ('H', c_int), ('U', c_int), ('out', c_vp), ('ldo', c_i64), ('att_weights', c_vp),
                 ('train_cand_emb', c_vp), ('train_rated_emb', c_vp), ('E', c_int), ('atol', c_f), ('rtol', c_f),
                 ('drop_zero_scores', c_int), ('score_scale', c_f), ('ld_pr', c_i64), ('ld_q', c_i64), ('workspace', c_vp), ('workspace_bytes', c_sz),
-                ('max_row_nnz', c_i64), ('nnz', c_i64)]
+                ('max_row_nnz', c_i64), ('nnz', c_i64), ('prepared', c_int), ('ld_pc', c_i64)]
 
 
 class LinearProblem(C.Structure):
@@ -72,6 +72,7 @@ SIGNATURES = {
     'b200rec_attention_pool_workspace_csr': (c_sz, [c_i64, c_i64, c_int, c_i64, c_i64]),
     'b200rec_attention_pool': (c_int, [C.POINTER(AttentionDesc), c_vp]),
     'b200rec_attention_pool_set_path': (c_int, [c_int]),
+    'b200rec_attention_pool_prepare': (c_int, [C.POINTER(AttentionDesc), c_vp]),
     'b200rec_spmm': (c_int, [C.POINTER(SpmmDesc), c_vp]),
     'b200rec_scan_workspace': (c_sz, [c_i64]),
     'b200rec_exclusive_scan_i32': (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

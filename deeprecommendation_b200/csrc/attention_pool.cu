@@ -54,7 +54,7 @@ struct AttParams {
   float atol, rtol;
   int drop_zero_scores;   // message_dropout is not None: scores == 0.0 -> -inf (:189)
   float score_scale;      // message dropout: kept scores are scaled by 1/(1-p) (:187)
-  long long ldPr, ldQ;
+  long long ldPr, ldQ, ldPc;
 };
 
 
@@ -103,7 +103,7 @@ struct RowCore {
       const int h = lane * 4 + hv * 128;
       float4 c = make_float4(0.f, 0.f, 0.f, 0.f), w = c;
       if (h < p.H) {
-        c = ld4(p.Pc + (long long)b * p.H + h);
+        c = ld4(p.Pc + (long long)b * p.ldPc + h);
         if (MODE == MODE_NET) w = ld4(p.a2 + h);
       }
       pc[hv][0] = c.x; pc[hv][1] = c.y; pc[hv][2] = c.z; pc[hv][3] = c.w;
@@ -694,6 +694,8 @@ struct AttInputs {
   void* ws; size_t ws_bytes;
   long long max_row_nnz;     // CSR form: upper bound of a row's length (0 = unknown -> I); sizes the work list and the partial slots
   long long nnz;             // CSR form: number of stored entries (0 = unknown); tightens the same bound
+  int prepare_light;         // prepare on a side stream: the compaction kernel without dynamic shared memory (co-resident with the GEMM CTAs)
+  int prepared;              // the work list (and the compaction of a dense matrix) is already in the workspace (b200rec_attention_pool_prepare)
 };
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -718,6 +720,50 @@ static AttLayout att_layout(long long B, long long I, int U, bool dense, long lo
   return l;
 }
 
+struct AttLists { const int* col; const float* val; const int* row_nnz; const int* row_ptr; long long stride; };
+
+// First phase of the segment-parallel path: zero the counter, compact a dense matrix (or read the CSR's row lengths) and write
+// the work list.  It depends on `user_matrix` only — not on the projections — so the host may run it on a second stream next
+// to the GEMMs (b200rec_attention_pool_prepare; `launch` = false just recomputes the pointers into an already prepared workspace).
+static int att_prepare(int B, int I, int U, const AttInputs& in, cudaStream_t st, bool launch, AttWork& w, AttLists& lists) {
+  const bool dense = in.um != nullptr;
+  const AttLayout lay = att_layout(B, I, U, dense, in.max_row_nnz, in.nnz);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(in.ws);
+  w.counter = reinterpret_cast<int*>(ws + lay.counter);
+  w.seg_base = reinterpret_cast<int*>(ws + lay.seg_base);
+  w.items = reinterpret_cast<int2*>(ws + lay.items);
+  w.partials = reinterpret_cast<float*>(ws + lay.partials);
+  const long long max_items = att_max_items(B, I, dense ? 0 : in.max_row_nnz, dense ? 0 : in.nnz);
+  if (max_items > 0x7fffffffLL) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: more than 2^31 segments");
+  w.max_items = (int)max_items;
+  if (launch) B200REC_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), st));
+  lists.col = in.col; lists.val = in.val; lists.row_nnz = nullptr; lists.row_ptr = in.row_ptr; lists.stride = 0;
+  if (dense) {                         // streaming compaction of the dense matrix into row-padded lists (+ the work list)
+    int* wcol = reinterpret_cast<int*>(ws + lay.compact);
+    float* wval = reinterpret_cast<float*>(wcol + (size_t)B * I);
+    int* wnnz = reinterpret_cast<int*>(wval + (size_t)B * I);
+    if (launch) {
+      const size_t row_bytes = (size_t)I * sizeof(float);
+      if (row_bytes <= 96 * 1024 && !in.prepare_light) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          B200REC_CUDA(cudaFuncSetAttribute(um_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+          attr_set = true;
+        }
+        um_compact_kernel<true><<<B, ATT_WARPS * 32, row_bytes, st>>>(in.um, in.ld_um, I, wcol, wval, wnnz, w);
+      } else {
+        um_compact_kernel<false><<<B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, I, wcol, wval, wnnz, w);
+      }
+      B200REC_CHECK_LAUNCH();
+    }
+    lists.col = wcol; lists.val = wval; lists.row_nnz = wnnz; lists.row_ptr = nullptr; lists.stride = I;
+  } else if (launch) {
+    att_worklist_kernel<<<ceil_div_i(B, 128), 128, 0, st>>>(in.row_ptr, B, w);
+    B200REC_CHECK_LAUNCH();
+  }
+  return B200REC_OK;
+}
+
 template <int HV, int UV, int MODE, typename T>
 static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) {
   const bool dense = in.um != nullptr;
@@ -729,39 +775,15 @@ static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) 
     B200REC_CHECK_LAUNCH();
     return B200REC_OK;
   }
-  unsigned char* ws = reinterpret_cast<unsigned char*>(in.ws);
   AttWork w;
-  w.counter = reinterpret_cast<int*>(ws + lay.counter);
-  w.seg_base = reinterpret_cast<int*>(ws + lay.seg_base);
-  w.items = reinterpret_cast<int2*>(ws + lay.items);
-  w.partials = reinterpret_cast<float*>(ws + lay.partials);
-  const long long max_items = att_max_items(p.B, p.I, dense ? 0 : in.max_row_nnz, dense ? 0 : in.nnz);
-  if (max_items > 0x7fffffffLL) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: more than 2^31 segments");
-  w.max_items = (int)max_items;
-  B200REC_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), st));
-  const int* ccol = in.col; const float* cval = in.val; const int* cnnz = nullptr; const int* rp = in.row_ptr;
-  long long stride = 0;
-  if (dense) {                         // streaming compaction of the dense matrix into row-padded lists (+ the work list)
-    int* wcol = reinterpret_cast<int*>(ws + lay.compact);
-    float* wval = reinterpret_cast<float*>(wcol + (size_t)p.B * p.I);
-    int* wnnz = reinterpret_cast<int*>(wval + (size_t)p.B * p.I);
-    const size_t row_bytes = (size_t)p.I * sizeof(float);
-    if (row_bytes <= 96 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        B200REC_CUDA(cudaFuncSetAttribute(um_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-      }
-      um_compact_kernel<true><<<p.B, ATT_WARPS * 32, row_bytes, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz, w);
-    } else {
-      um_compact_kernel<false><<<p.B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, p.I, wcol, wval, wnnz, w);
-    }
-    B200REC_CHECK_LAUNCH();
-    ccol = wcol; cval = wval; cnnz = wnnz; rp = nullptr; stride = p.I;
-  } else {
-    att_worklist_kernel<<<ceil_div_i(p.B, 128), 128, 0, st>>>(rp, p.B, w);
-    B200REC_CHECK_LAUNCH();
+  AttLists lists;
+  {
+    const int rc = att_prepare(p.B, p.I, p.U, in, st, !in.prepared, w, lists);
+    if (rc) return rc;
   }
+  const int* ccol = lists.col; const float* cval = lists.val; const int* cnnz = lists.row_nnz; const int* rp = lists.row_ptr;
+  const long long stride = lists.stride;
+  const long long max_items = w.max_items;
   // rows as TMA bulk copies need 16-byte aligned rows whose length is a multiple of 16 bytes
   const bool no_tma = g_att_path == 1, force_tma = g_att_path == 2;
   // tables that stay in L2 (config 2: 10 MB) are served faster by the register-staged gathers with 16 warps per SM (72 vs 98 us);
@@ -807,6 +829,21 @@ static int dispatch_att(const AttParams& p, const AttInputs& in, cudaStream_t st
 
 using namespace b200rec;
 
+extern "C" int b200rec_attention_pool_prepare(const b200rec_attention_t* a, b200rec_stream_t stream) {
+  if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_prepare: null descriptor");
+  if (a->B < 0 || a->I < 0 || a->U <= 0 || (a->U % 4)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_prepare: bad shape");
+  if (a->B == 0) return B200REC_OK;
+  if (!a->user_matrix && !(a->row_ptr && (a->col || a->I == 0))) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_prepare: need user_matrix or CSR");
+  const bool dense = a->user_matrix != nullptr;
+  if (!a->workspace || a->workspace_bytes < att_layout(a->B, a->I, a->U, dense, a->max_row_nnz, a->nnz).total)
+    return b200rec_fail(B200REC_ERR_WORKSPACE, "attention_pool_prepare: workspace too small");
+  const long long ld_um = dense ? (a->ld_user_matrix ? a->ld_user_matrix : a->I) : 0;
+  AttInputs in{a->user_matrix, ld_um, a->row_ptr, a->col, a->val, a->workspace, a->workspace_bytes, a->max_row_nnz, a->nnz, 1, 0};
+  AttWork w;
+  AttLists lists;
+  return att_prepare((int)a->B, (int)a->I, a->U, in, (cudaStream_t)stream, true, w, lists);
+}
+
 extern "C" int b200rec_attention_pool_set_path(int path) {
   if (path < 0 || path > 2) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_set_path: 0 auto, 1 registers, 2 TMA");
   g_att_path = path;
@@ -842,11 +879,13 @@ extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stre
   p.score_scale = a->score_scale == 0.f ? 1.f : a->score_scale;
   p.ldPr = a->ld_pr ? a->ld_pr : a->H;
   p.ldQ = a->ld_q ? a->ld_q : a->U;
+  p.ldPc = a->ld_pc ? a->ld_pc : a->H;
+  if (p.ldPc < a->H || (p.ldPc % 4)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: bad Pc leading dimension");
   if (p.ldPr < a->H || p.ldQ < a->U || (p.ldPr % 4) || (p.ldQ % 4)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: bad table leading dimension");
   if (p.Ec && (!p.Er || p.E <= 0)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: training mask needs both embeddings");
   cudaStream_t st = (cudaStream_t)stream;
   const long long ld_um = a->user_matrix ? (a->ld_user_matrix ? a->ld_user_matrix : a->I) : 0;
-  AttInputs in{a->user_matrix, ld_um, a->row_ptr, a->col, a->val, a->workspace, a->workspace_bytes, a->max_row_nnz, a->nnz};
+  AttInputs in{a->user_matrix, ld_um, a->row_ptr, a->col, a->val, a->workspace, a->workspace_bytes, a->max_row_nnz, a->nnz, 0, a->prepared};
   if (a->table_dtype == B200REC_F32) {
     if (a->mode == MODE_NET) return dispatch_att<MODE_NET, float>(p, in, st);
     if (a->mode == MODE_DOT) return dispatch_att<MODE_DOT, float>(p, in, st);

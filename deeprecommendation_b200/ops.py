@@ -406,12 +406,41 @@ def set_attention_path(path: str):
     L.check(L.lib().b200rec_attention_pool_set_path({'auto': 0, 'registers': 1, 'tma': 2}[path]), 'attention_pool_set_path')
 
 
+class AttentionPrepared:
+    """Workspace of `attention_pool_raw` with its first phase (compaction of the dense user_matrix + work list) already
+    launched — see `attention_prepare`."""
+
+    def __init__(self, ws, um, shape, U):
+        self.ws, self.um, self.shape, self.U = ws, um, shape, U
+
+
+def attention_prepare(user_matrix, U):
+    """Launches K2's first phase for a dense `(B, I)` user_matrix on the CURRENT stream (b200rec_attention_pool_prepare).  It reads
+    nothing but the matrix, so AttentionNCF runs it on a side stream next to the projection GEMMs and joins before
+    `attention_pool_raw(..., prepared=...)`."""
+    _require_cuda(user_matrix)
+    um, ld = _row_major(user_matrix)
+    B, I = um.shape
+    d = L.AttentionDesc()
+    d.user_matrix, d.ld_user_matrix = um.data_ptr(), ld
+    d.B, d.I, d.U = B, I, U
+    wsb = L.lib().b200rec_attention_pool_workspace(B, I, U, 1)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=um.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), wsb
+    if B > 0 and I > 0:
+        with torch.cuda.device(um.device), _timed('attention_prepare', (B, I)):
+            L.check(L.lib().b200rec_attention_pool_prepare(C.byref(d), _stream()), 'attention_pool_prepare')
+    return AttentionPrepared(ws, um, (B, I), U)
+
+
 def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None, user_matrix=None, csr=None,
-                       return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0, use_workspace=True, max_row_nnz=0):
+                       return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0, use_workspace=True, max_row_nnz=0,
+                       prepared=None):
     """out (B,U) [, att (B,I)] — b200rec_attention_pool.  `csr` = (row_ptr int32, col int32, val fp32); `max_row_nnz` (CSR only,
     optional) = a host-known bound of the row lengths, so that the segment grid is not sized by I."""
     _require_cuda(Pc, Pr, Q, user_matrix)
-    Pc = Pc.contiguous().float()
+    if Pc.dtype != torch.float32 or Pc.stride(1) != 1 or Pc.stride(0) % 4 or Pc.data_ptr() % 16:
+        Pc = Pc.contiguous().float()
     if Pr.dtype != Q.dtype:
         raise ValueError('Pr and Q must share a dtype')
     if Pr.stride(1) != 1 or Pr.stride(0) % 4 or Pr.data_ptr() % 16:
@@ -432,6 +461,10 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
             t = t.detach().contiguous().float().view(-1)
             keep.append(t)
             setattr(d, name, t.data_ptr())
+    if prepared is not None and (prepared.shape != (B, I) or prepared.U != U or B == 0 or I == 0):
+        prepared = None
+    if prepared is not None:
+        user_matrix = prepared.um
     if user_matrix is not None:
         um, ld = _row_major(user_matrix)
         if um.shape != (B, I):
@@ -451,11 +484,15 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
         wsb = L.lib().b200rec_attention_pool_workspace_csr(B, I, U, d.max_row_nnz, d.nnz) if use_workspace else 0
     else:
         wsb = L.lib().b200rec_attention_pool_workspace(B, I, U, 1) if use_workspace else 0
-    if wsb:
+    if prepared is not None:
+        keep.append(prepared.ws)
+        d.workspace, d.workspace_bytes, d.prepared = prepared.ws.data_ptr(), prepared.ws.numel(), 1
+    elif wsb:
         ws = torch.empty(wsb, dtype=torch.uint8, device=Pc.device)
         keep.append(ws)
         d.workspace, d.workspace_bytes = ws.data_ptr(), wsb
     d.ld_pr, d.ld_q = (Pr.stride(0) if I > 1 else H), (Q.stride(0) if I > 1 else U)
+    d.ld_pc = Pc.stride(0) if B > 1 else H
     out = torch.empty((B, U), dtype=torch.float32, device=Pc.device)
     d.out, d.ldo = out.data_ptr(), U
     att = None

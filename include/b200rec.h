@@ -167,10 +167,16 @@ typedef struct {
   size_t workspace_bytes; /* of a dense matrix, work list of <=64-non-zero segments, one warp each, merge kernel); NULL = one fused kernel */
   int64_t max_row_nnz;    /* CSR form, optional: upper bound of a row's length (0 = unknown, I is used) and the number of stored entries */
   int64_t nnz;            /* (0 = unknown).  They only size the work list / partial slots: b200rec_attention_pool_workspace_csr(). */
+  int prepared;           /* 1 = b200rec_attention_pool_prepare already ran on this workspace for this user_matrix / CSR */
+  int64_t ld_pc;          /* leading dimension of Pc in elements (a column slice of the [Ec | Pc] projection is used in place); 0 = H */
 } b200rec_attention_t;
 size_t b200rec_attention_pool_workspace(int64_t B, int64_t I, int U, int dense);
 size_t b200rec_attention_pool_workspace_csr(int64_t B, int64_t I, int U, int64_t max_row_nnz, int64_t nnz);
 int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream);
+/* First phase of the segment-parallel path on its own: compaction of the dense matrix / work list into `workspace`.  It reads only
+ * user_matrix (or the CSR) — B, I, U, the matrix fields and the workspace of `a` must be set, the tables may be NULL — so a host can
+ * launch it on a second stream while the projection GEMMs run, then call b200rec_attention_pool with the same workspace and prepared = 1. */
+int b200rec_attention_pool_prepare(const b200rec_attention_t* a, b200rec_stream_t stream);
 /* How the segment-parallel path gathers table rows: 0 = auto (TMA bulk copies into shared memory when the tables exceed half of L2,
  * register-staged 128-bit loads otherwise), 1 = always registers, 2 = TMA whenever the layout allows (H, U <= 128, 16-byte rows). */
 int b200rec_attention_pool_set_path(int path);

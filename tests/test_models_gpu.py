@@ -525,3 +525,25 @@ def test_attention_forward_resident_equals_dense_forward():
             ops.set_gemm_engine(prev)
         assert torch.equal(out_d, out_r), engine
         assert torch.equal(att_d, att_r), engine
+
+
+def test_attention_overlap_prepare_equals_default():
+    """AttentionNCF.overlap_prepare (K2's first phase through b200rec_attention_pool_prepare on a side stream, `prepared = 1`)
+    gives the same bits as the single-stream path, eagerly and replayed from a captured CUDA graph."""
+    d, _, kw = load('attention_full')
+    wkw = {k: v for k, v in kw.items() if k not in ('use_cos_sim_instead', 'message_dropout')}
+    m = _models().AttentionNCF(**kw).to(DEV).eval()
+    m.load_state_dict(synth.to_torch(synth.attention_ncf_weights(seed=int(d['weight_seed']), **wkw)))
+    cand, rated, um = (torch.from_numpy(a).to(DEV) for a in attention_full_inputs(d))
+    with torch.no_grad():
+        ref_out, ref_att = m(cand, rated, um, return_attention_weights=True)
+        m.overlap_prepare = True
+        out, att = m(cand, rated, um, return_attention_weights=True)
+        assert torch.equal(out, ref_out) and torch.equal(att, ref_att)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gout = m(cand, rated, um)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(gout, ref_out)
