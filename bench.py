@@ -463,13 +463,14 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
     if pg is not None:                  # rank 0's share of the rows
         E2 = pg.edges_own
     l2 = torch.cuda.get_device_properties(dev).L2_cache_size
-    feat = N * d * 4
-    alg_bytes = E2 * 8 + (E2 * d * 4 + feat if feat > l2 else 2 * feat)
+    ts = 2 if getattr(model, 'message_dtype', 'fp32') == 'bf16' else 4        # bytes per gathered feature (t); outputs stay fp32
+    feat = N * d * ts
+    alg_bytes = E2 * 8 + (E2 * d * ts + N * d * 4 if feat > l2 else feat + N * d * 4)
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
     roof = {'bound': 'hbm', 'kernel': 'spmm_chunk_kernel (K3, per layer)', 'achieved': round(achieved, 1), 'peak': peaks['hbm_gbs'],
             'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('graph'), 'peak_source': peaks['src'],
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes), 'features_fit_l2': bool(feat <= l2),
-            'gather_inclusive_gbs': round((E2 * 8 + E2 * d * 4) / (kms * 1e-3) / 1e9, 1) if kms > 0 else 0.0,
+            'gather_inclusive_gbs': round((E2 * 8 + E2 * d * ts) / (kms * 1e-3) / 1e9, 1) if kms > 0 else 0.0,
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof,
                 launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
@@ -1015,6 +1016,19 @@ def main():
                      'roofline': r['roofline'],
                      'e2e': {'value': msgs / (r['e2e_ms'] * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
                      'gpu_launches': r['launches']}
+            if world == 1:
+                # bf16 message mode (north_star: rel <= 1e-2): the transform GEMM rounds t once to bf16, K3 gathers 2-byte features
+                w['model'].message_dtype = 'bf16'
+                try:
+                    n_steps = max(3, args.steps // 2)
+                    rb = run_graph(w, n_steps, 3, dist, dev, peaks)
+                    entry['bf16_mode'] = {'value': 2.0 * w['E'] * w['L'] * n_steps / (rb['ms'] * 1e-3), 'ms_per_step': rb['ms'] / n_steps, 'steps': n_steps,
+                                          'dtype': 'bf16 messages, fp32 accumulate', 'roofline': rb['roofline'],
+                                          'e2e': {'value': 2.0 * w['E'] * w['L'] * n_steps / (rb['e2e_ms'] * 1e-3), 'unit': 'edges/s',
+                                                  'h2d_bytes_per_step': rb['h2d'], 'd2h_bytes_per_step': rb['d2h']}}
+                except Exception as e:
+                    entry['bf16_mode'] = {'error': repr(e)[:300]}
+                w['model'].message_dtype = 'fp32'
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 v, cores, sample = cpu_graph(w)
                 entry['cpu_baseline'] = {'value': v, 'unit': 'edges/s', 'cores': cores, 'kind': 'port', 'sample': sample}

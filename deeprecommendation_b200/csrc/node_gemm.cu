@@ -74,7 +74,7 @@ struct NodeGemmParams {
   int M, N, K;                         // K in {32, 64, 96, 128}, N <= 128
   const unsigned char* Wp;             // b200rec_pack_weights_tc(TF32X3) of W (N, K): [k-block][hi | lo] tiles of 16 KB
   const float* bias; const float* row_scale; int relu;
-  float* Y; long long ldy;
+  void* Y; long long ldy; int y_bf16;   // Y: fp32, or bf16 (GraphNCF's bf16 message mode: K3 gathers half the bytes)
   int dbg;                             // experiments (B200REC_NT_DBG): 1 = no stores, 2 = no MMA, 4 = no TMEM loads
 };
 
@@ -224,7 +224,18 @@ node_gemm_kernel(NodeGemmParams p) {
             const int grow = tile * 128 + e * 32 + r, n = cg * 32 + cc;
             if (grow < p.M && n < p.N) {
               const float4 v = *reinterpret_cast<const float4*>(stg + r * NT_STG_LD + cc);
-              float* d = p.Y + (long long)grow * p.ldy + n;
+              if (p.y_bf16) {                                      // 4 rows x 64 bytes per warp instruction
+                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.Y) + (long long)grow * p.ldy + n;
+                if (n + 3 < p.N && (((uintptr_t)d & 7) == 0)) {
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                  *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+                } else {
+                  const float o[4] = {v.x, v.y, v.z, v.w};
+                  for (int q = 0; q < 4 && n + q < p.N; ++q) d[q] = __float2bfloat16_rn(o[q]);
+                }
+                continue;
+              }
+              float* d = reinterpret_cast<float*>(p.Y) + (long long)grow * p.ldy + n;
               if (n + 3 < p.N && (((uintptr_t)d & 15) == 0)) *reinterpret_cast<float4*>(d) = v;
               else {
                 const float o[4] = {v.x, v.y, v.z, v.w};
@@ -302,16 +313,17 @@ static int nt_launch(const NodeGemmParams& p, cudaStream_t st) {
 using namespace b200rec;
 
 extern "C" int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
-                                     const float* row_scale, int relu, float* Y, int64_t ldy, b200rec_stream_t stream) {
+                                     const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, b200rec_stream_t stream) {
   if (M < 0 || !packed_w || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_shortk: null operand");
   if (K <= 0 || K > 128 || (K % 32) || N <= 0 || N > 128) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_shortk: needs K in {32,64,96,128}, N <= 128");
   if (ldx < K || ldy < N || (ldx % 4) || ((uintptr_t)X % 16) || ((uintptr_t)packed_w % 128))
     return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_shortk: X rows must be 16-byte aligned (ldx % 4 == 0), packed W 128-byte aligned");
   if (M > INT32_MAX) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_shortk: M > int32");
+  if (y_dtype != B200REC_F32 && y_dtype != B200REC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_shortk: bad y_dtype");
   if (M == 0) return B200REC_OK;
   NodeGemmParams p;
   p.X = X; p.ldx = ldx; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.Wp = (const unsigned char*)packed_w;
-  p.bias = bias; p.row_scale = row_scale; p.relu = relu; p.Y = Y; p.ldy = ldy;
+  p.bias = bias; p.row_scale = row_scale; p.relu = relu; p.Y = Y; p.ldy = ldy; p.y_bf16 = y_dtype == B200REC_BF16;
   {
     const char* e = getenv("B200REC_NT_DBG");
     p.dbg = e ? atoi(e) : 0;

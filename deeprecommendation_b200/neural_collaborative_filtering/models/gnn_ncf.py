@@ -78,7 +78,13 @@ class GraphNCF(GNN_NCF):
                 x'[r] = deg[r]^-1/2 · Σ_{s->r} w_sr · t[s]     deterministic edge-balanced CSR SpMM, running mean fused in
 
     `cache_eval_embeddings=True` (new, default off) keeps the propagated embeddings between eval-mode calls while neither
-    the graph nor the parameters change; the reference recomputes them for every mini-batch (:298-351)."""
+    the graph nor the parameters change; the reference recomputes them for every mini-batch (:298-351).
+
+    `message_dtype = 'bf16'` (attribute, default 'fp32'; inference only): the per-node messages `t` are rounded ONCE to bf16 by
+    the transform GEMM's epilogue and K3 gathers 2-byte features (half the bytes through L1 / L2 / HBM); accumulation, the
+    running mean and everything else stay fp32.  Tolerance of this mode: max-norm relative error <= 1e-2 (north_star)."""
+
+    message_dtype = 'fp32'
 
     def __init__(self, item_dim, user_dim, num_gnn_layers: int, hetero, node_emb=64, mlp_dense_layers=None, dropout_rate=0.2,
                  use_dot_product=False, concat=False, message_dropout=None, node_dropout=None, convType='LightGCN',
@@ -152,7 +158,10 @@ class GraphNCF(GNN_NCF):
             ops.linear_raw(graph.user_features, ue.weight, ue.bias, out=x0[nI:])          # :301, items first (:304)
             if L_ == 0:
                 return x0
-            x, t = x0, torch.empty((N, d), dtype=torch.float32, device=dev)
+            if self.message_dtype not in ('fp32', 'bf16'):
+                raise ValueError("message_dtype must be 'fp32' or 'bf16'")
+            t_dtype = torch.bfloat16 if (self.message_dtype == 'bf16' and d % 8 == 0) else torch.float32
+            x, t = x0, torch.empty((N, d), dtype=t_dtype, device=dev)
             spare = torch.empty((N, d), dtype=torch.float32, device=dev) if (L_ > 1 and not self.concat) else None
             gat = self.convType == 'LightGAT'
             if gat:
@@ -234,7 +243,7 @@ class GraphNCF(GNN_NCF):
             if removed is not None:
                 skip, dinv = index.masked(removed)
         use_cache = self.cache_eval_embeddings and not self.training and not torch.is_grad_enabled()
-        key = (id(index), tuple(p._version for p in self.parameters())) if use_cache else None
+        key = (id(index), self.message_dtype, tuple(p._version for p in self.parameters())) if use_cache else None
         if use_cache and self._cache is not None and self._cache[0] == key:
             comb = self._cache[1]
         else:

@@ -173,12 +173,12 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     lib = L.lib()
     engine = engine or _gemm_engine
     if (engine in ('tf32x3', 'shortk!') and row_index is None and K <= 128 and K % 32 == 0 and N <= 128 and (M >= SHORTK_MIN_ROWS or engine == 'shortk!')
-            and ldx % 4 == 0 and x.data_ptr() % 16 == 0 and out.dtype == torch.float32):
+            and ldx % 4 == 0 and x.data_ptr() % 16 == 0 and out.dtype in (torch.float32, torch.bfloat16)):
         # per-node d x d transforms (GraphNCF): persistent streaming kernel, W resident in shared memory
         packed = _packed_weight(w, ldw, L.TC_TF32X3)
         with torch.cuda.device(x.device), _timed('linear_shortk', (M, K, N)):
             L.check(lib.b200rec_linear_shortk(_ptr(x), M, K, ldx, _ptr(packed), N, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
-                                              _stream()), 'linear_shortk')
+                                              _dtype_code(out.dtype), _stream()), 'linear_shortk')
         return out
     if engine == 'shortk!':
         raise ValueError('linear: shape not supported by the short-K kernel')

@@ -64,9 +64,10 @@ int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, int64_t ldx, 
                              void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
 /* Persistent short-K variant for the per-node transforms of GraphNCF (K in {32,64,96,128}, N <= 128; csrc/node_gemm.cu):
  * W stays in shared memory (`packed_w` = b200rec_pack_weights_tc(..., B200REC_TC_TF32X3)), row tiles are streamed, fp32 parity
- * by the 3xTF32 split.  X rows 16-byte aligned (ldx % 4 == 0); Y fp32. */
+ * by the 3xTF32 split.  X rows 16-byte aligned (ldx % 4 == 0); Y fp32 or bf16 (`y_dtype`; bf16 = the message table of GraphNCF's
+ * bf16 mode, rounded once from the fp32 accumulator). */
 int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
-                          const float* row_scale, int relu, float* Y, int64_t ldy, b200rec_stream_t stream);
+                          const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, b200rec_stream_t stream);
 /* Up to four such GEMMs sharing K and mode in ONE launch (candidate + rated-item projections, the two halves of
  * AttentionNet.0 — attention_ncf.py:150-151,176): problem q covers its own rows; fields as in b200rec_linear_tc. */
 typedef struct {

@@ -106,3 +106,17 @@ def test_linear_shortk_persistent_fp32_parity(M, K, N):
     if M >= ops.SHORTK_MIN_ROWS:
         y2 = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), engine='tf32x3')
         assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize('M,K,N', [(5000, 128, 128), (777, 96, 100), (20_000, 32, 8), (1, 128, 128)])
+def test_linear_shortk_bf16_output(M, K, N):
+    """K1c with a bf16 epilogue (GraphNCF.message_dtype = 'bf16'): the fp32 result rounded once, bit-identical to rounding the
+    fp32-output run; strided output leaves its neighbours alone"""
+    from deeprecommendation_b200 import ops
+    x, w, b, s = _case(M, K, N, M + K + 11)
+    y32 = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), s.cuda(), engine='shortk!')
+    y16 = ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), s.cuda(), out_dtype=torch.bfloat16, engine='shortk!')
+    assert y16.dtype == torch.bfloat16 and torch.equal(y16, y32.bfloat16())
+    out = torch.full((M, N + 12), 3.0, device='cuda', dtype=torch.bfloat16)
+    ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), s.cuda(), out=out[:, 6:6 + N], engine='shortk!')       # rows only 4-byte aligned
+    assert torch.equal(out[:, 6:6 + N], y16) and torch.all(out[:, :6] == 3.0) and torch.all(out[:, 6 + N:] == 3.0)

@@ -322,6 +322,10 @@ def test_graph_ncf_medium_vs_oracle(d_emb, L_, n_users, n_items, n):
         out = m(g, uid.to(DEV), iid.to(DEV), DEV)
         assert maxnorm_rel(out, ref) < TOL
         assert torch.equal(out, m(g, uid.to(DEV), iid.to(DEV), DEV))            # deterministic: no atomics in K3
+        m.message_dtype = 'bf16'                                                # bf16 message table, fp32 accumulate: rel <= 1e-2
+        out_bf = m(g, uid.to(DEV), iid.to(DEV), DEV)
+        assert maxnorm_rel(out_bf, ref) < 1e-2 and not torch.equal(out_bf, out)
+        m.message_dtype = 'fp32'
         m.train()
         for mod in m.modules():
             if isinstance(mod, torch.nn.Dropout):
