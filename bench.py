@@ -282,6 +282,31 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
 
     step = step_eager
     ops_ms = op_breakdown(step, min(steps, nb), 0)
+
+    # training step of the same batches (NCF/train.py:99-105): forward in train mode (dropout 0.2, isclose target mask), sum-MSE loss,
+    # backward (K2's own backward kernel, gradient GEMMs on K1a) and Adam; eager launches — the rated-item union differs per batch
+    train = None
+    if not w.get('no_train'):
+        try:
+            model.train()
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+            ys = [torch.rand(BATCH, 1, device=dev) * 4.5 + 0.5 for _ in range(nb)]
+
+            def train_step(i):
+                opt.zero_grad(set_to_none=True)
+                (model(*resident[i % nb]) - ys[i % nb]).square().sum().backward()
+                opt.step()
+
+            n_train = max(3, steps // 2)
+            train_ms, _ = timed_steps(train_step, n_train, 3, dist, dev)
+            t_ops = op_breakdown(train_step, min(n_train, nb), 0)
+            train = {'ms': train_ms / n_train, 'steps': n_train,
+                     'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(t_ops.items(), key=lambda kv: -kv[1][0] * kv[1][1])[:8]}}
+        except Exception as e:
+            train = {'error': repr(e)[:300]}
+        finally:
+            model.eval()
+            model.load_state_dict(w['sd'])
     (name, meta), (kms, per_step) = max(ops_ms.items(), key=lambda kv: kv[1][0] * kv[1][1])
     I_mean = float(np.mean([b[1].shape[0] for b in host]))
     if name in ('linear', 'linear_tc', 'linear_tc_batch'):
@@ -335,7 +360,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     if other:
         roof['other_kernels'] = other
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4, roofline=roof, I_mean=I_mean,
-                nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res,
+                nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res, train=train,
                 launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
@@ -948,6 +973,7 @@ def main():
         if args.workload in ('all', 'attention'):
             w = build_attention(dev, rank)
             w['gemm'] = args.gemm
+            w['no_train'] = world > 1              # the train-step leg is single-GPU (no gradient all-reduce: out of scope)
             w['eager'] = args.eager
             r = run_attention(w, args.steps, args.warmup, dist, dev, peaks)
             pairs = BATCH * args.steps * world
@@ -968,6 +994,13 @@ def main():
                                           'note': 'same batches through content_providers.ResidentDynamicProvider + AttentionNCF.forward_resident: '
                                                   'profile table resident in HBM, per step only row numbers + the CSR of user_matrix are copied '
                                                   '(pinned host -> device) and the scores read back; `e2e` above is the dense 6-tuple contract'}
+            if r.get('train'):
+                t = r['train']
+                result['train_step'] = ({'value': BATCH * world / (t['ms'] * 1e-3), 'unit': 'pairs/s', 'ms_per_step': t['ms'], 'steps': t['steps'],
+                                         'launch_mode': 'eager', 'op_ms_per_step': t['op_ms_per_step'],
+                                         'what': 'forward in train mode (dropout 0.2, isclose target mask) + sum-MSE backward + Adam on the same batches: '
+                                                 'K2 backward = attention_pool_bwd_kernel, forward and gradient GEMMs on K1a, torch elementwise ops '
+                                                 'for dropout masks / bias sums / the optimizer'} if 'ms' in t else t)
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 v, cores, sample = cpu_attention(w)
                 result['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}

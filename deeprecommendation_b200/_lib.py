@@ -32,6 +32,13 @@ class AttentionDesc(C.Structure):
                 ('max_row_nnz', c_i64), ('nnz', c_i64), ('prepared', c_int), ('ld_pc', c_i64)]
 
 
+class AttentionBwdDesc(C.Structure):
+    _fields_ = [('Pc', c_vp), ('Pr', c_vp), ('Q', c_vp), ('mode', c_int), ('a2', c_vp), ('bU', c_vp), ('user_matrix', c_vp), ('ld_user_matrix', c_i64),
+                ('att_weights', c_vp), ('out', c_vp), ('ldo', c_i64), ('grad_out', c_vp), ('ld_grad_out', c_i64), ('B', c_i64), ('I', c_i64),
+                ('H', c_int), ('U', c_int), ('score_scale', c_f), ('ld_pc', c_i64), ('ld_pr', c_i64), ('ld_q', c_i64),
+                ('dPc', c_vp), ('dPr', c_vp), ('dQ', c_vp), ('da2_rows', c_vp), ('da20_rows', c_vp)]
+
+
 class LinearProblem(C.Structure):
     _fields_ = [('X', c_vp), ('M', c_i64), ('ldx', c_i64), ('W', c_vp), ('N', c_i64), ('ldw', c_i64), ('packed_w', c_vp), ('bias', c_vp),
                 ('row_scale', c_vp), ('relu', c_int), ('Y', c_vp), ('ldy', c_i64), ('y_dtype', c_int)]
@@ -73,6 +80,7 @@ SIGNATURES = {
     'b200rec_attention_pool': (c_int, [C.POINTER(AttentionDesc), c_vp]),
     'b200rec_attention_pool_set_path': (c_int, [c_int]),
     'b200rec_attention_pool_prepare': (c_int, [C.POINTER(AttentionDesc), c_vp]),
+    'b200rec_attention_pool_backward': (c_int, [C.POINTER(AttentionBwdDesc), c_vp]),
     'b200rec_spmm': (c_int, [C.POINTER(SpmmDesc), c_vp]),
     'b200rec_scan_workspace': (c_sz, [c_i64]),
     'b200rec_exclusive_scan_i32': (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

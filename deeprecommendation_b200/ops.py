@@ -586,58 +586,79 @@ def propagate(t, index, w, w_bwd, dinv, skip_bits=None):
 # ------------------------------------------------------------------------------------------------------------------
 # K2 autograd wrapper
 # ------------------------------------------------------------------------------------------------------------------
-def _attention_pool_torch(Pc, Pr, Q, a2, a20, bU, um, mode, train_mask, drop_zero_scores, score_scale=1.0):
-    """Differentiable torch restatement on the non-zeros (used only inside backward)."""
-    b_idx, i_idx = (um != 0).nonzero(as_tuple=True)
-    if mode == L.ATT_NET:
-        s = (torch.relu(Pc[b_idx] + Pr[i_idx]) * a2.view(1, -1)).sum(1)
-        if a20 is not None:
-            s = s + a20.view(())
-    else:
-        s = (Pc[b_idx] * Pr[i_idx]).sum(1)
-    s = s * score_scale
-    keep = torch.ones_like(s, dtype=torch.bool)
-    if drop_zero_scores:
-        keep &= s.detach() != 0
-    if train_mask is not None:
-        Ec, Er, atol, rtol = train_mask
-        keep &= ~torch.isclose(Ec[b_idx], Er[i_idx], atol=atol, rtol=rtol).all(dim=1)
-    b_idx, i_idx, s = b_idx[keep], i_idx[keep], s[keep]
-    B = Pc.shape[0]
-    m = torch.full((B,), float('-inf'), device=s.device).scatter_reduce(0, b_idx, s.detach(), reduce='amax', include_self=True)
-    e = torch.exp(s - m[b_idx])
-    l = torch.zeros(B, device=s.device).index_add(0, b_idx, e)
-    alpha = e / l[b_idx]
-    wgt = alpha * um[b_idx, i_idx]
-    out = torch.zeros((B, Q.shape[1]), device=s.device).index_add(0, b_idx, wgt[:, None] * Q[i_idx])
-    return out + bU.view(1, -1) if bU is not None else out
+def _f32_rows(t):
+    """fp32, unit column stride, 16-byte aligned rows (what the 128-bit loads of K2 need); copies only when it must"""
+    if t.dtype != torch.float32 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
+        t = t.contiguous().float()
+    return t
+
+
+def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode, score_scale=1.0):
+    """(dPc, dPr, dQ, da2, da20) — b200rec_attention_pool_backward (csrc/attention_pool_bwd.cu).  `att` / `out` are the forward's
+    attention weights and output; da2 / da20 are None in mode DOT."""
+    _require_cuda(Pc, Pr, Q, um, att, out, grad_out)
+    Pc, Pr, Q, out, grad_out = (_f32_rows(t.detach()) for t in (Pc, Pr, Q, out, grad_out))
+    um, ld_um = _row_major(um.detach())
+    att = att.detach().contiguous().float()
+    B, H = Pc.shape
+    I, U = Q.shape
+    dev = Pc.device
+    dPc = torch.empty((B, H), dtype=torch.float32, device=dev)
+    dPr = torch.zeros((I, H), dtype=torch.float32, device=dev)
+    dQ = torch.zeros((I, U), dtype=torch.float32, device=dev)
+    net = mode == L.ATT_NET
+    da2_rows = torch.empty((B, H), dtype=torch.float32, device=dev) if net else None
+    da20_rows = torch.empty((B,), dtype=torch.float32, device=dev) if net else None
+    if B == 0 or I == 0:
+        dPc.zero_()
+        return dPc, dPr, dQ, (torch.zeros(H, device=dev) if net else None), (torch.zeros((), device=dev) if net else None)
+    d = L.AttentionBwdDesc()
+    d.Pc, d.Pr, d.Q, d.mode = Pc.data_ptr(), Pr.data_ptr(), Q.data_ptr(), mode
+    keep = []
+    if net:
+        a2c = a2.detach().contiguous().float().view(-1)
+        keep.append(a2c)
+        d.a2 = a2c.data_ptr()
+    if bU is not None:
+        buc = bU.detach().contiguous().float().view(-1)
+        keep.append(buc)
+        d.bU = buc.data_ptr()
+    d.user_matrix, d.ld_user_matrix = um.data_ptr(), ld_um
+    d.att_weights, d.out, d.ldo = att.data_ptr(), out.data_ptr(), (out.stride(0) if B > 1 else U)
+    d.grad_out, d.ld_grad_out = grad_out.data_ptr(), (grad_out.stride(0) if B > 1 else U)
+    d.B, d.I, d.H, d.U, d.score_scale = B, I, H, U, float(score_scale)
+    d.ld_pc, d.ld_pr, d.ld_q = (Pc.stride(0) if B > 1 else H), (Pr.stride(0) if I > 1 else H), (Q.stride(0) if I > 1 else U)
+    d.dPc, d.dPr, d.dQ = dPc.data_ptr(), dPr.data_ptr(), dQ.data_ptr()
+    if net:
+        d.da2_rows, d.da20_rows = da2_rows.data_ptr(), da20_rows.data_ptr()
+    with torch.cuda.device(dev), _timed('attention_pool_backward', (B, I, H, U)):
+        L.check(L.lib().b200rec_attention_pool_backward(C.byref(d), _stream()), 'attention_pool_backward')
+    return dPc, dPr, dQ, (da2_rows.sum(0) if net else None), (da20_rows.sum() if net else None)
 
 
 class _AttentionPoolFn(torch.autograd.Function):
-    """forward: fused CUDA kernel.  backward: torch recompute on the non-zeros (interim)."""
+    """forward: K2 (always with the attention weights, which the backward kernel consumes).  backward: csrc/attention_pool_bwd.cu;
+    only the column sums of the per-row a2 / a20 parts and of grad_out (dbU) are torch reductions."""
 
     @staticmethod
     def forward(ctx, Pc, Pr, Q, a2, a20, bU, um, mode, want_att, train_mask, drop_zero_scores, score_scale):
-        ctx.mode, ctx.train_mask, ctx.drop, ctx.scale = mode, train_mask, drop_zero_scores, score_scale
-        ctx.save_for_backward(Pc, Pr, Q, a2, a20, bU, um)
-        r = attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, user_matrix=um,
-                               return_attention_weights=want_att, train_mask=train_mask, drop_zero_scores=drop_zero_scores,
-                               score_scale=score_scale)
-        if want_att:
-            ctx.mark_non_differentiable(r[1])
-            return r
-        return r, None
+        out, att = attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, user_matrix=um, return_attention_weights=True,
+                                      train_mask=train_mask, drop_zero_scores=drop_zero_scores, score_scale=score_scale)
+        ctx.mode, ctx.scale = mode, score_scale
+        ctx.shapes = (None if a2 is None else a2.shape, None if a20 is None else a20.shape, None if bU is None else bU.shape)
+        ctx.save_for_backward(Pc, Pr, Q, a2, bU, um, att, out)
+        ctx.mark_non_differentiable(att)
+        return out, att
 
     @staticmethod
     def backward(ctx, g, _g_att=None):
-        Pc, Pr, Q, a2, a20, bU, um = ctx.saved_tensors
-        with torch.enable_grad():
-            ins = [t.detach().requires_grad_(True) if t is not None else None for t in (Pc, Pr, Q, a2, a20, bU)]
-            out = _attention_pool_torch(*ins, um, ctx.mode, ctx.train_mask, ctx.drop, ctx.scale)
-            wanted = [t for t in ins if t is not None]
-            grads = iter(torch.autograd.grad(out, wanted, g, allow_unused=True))
-        res = [next(grads) if t is not None else None for t in ins]
-        return (*res, None, None, None, None, None, None)
+        Pc, Pr, Q, a2, bU, um, att, out = ctx.saved_tensors
+        dPc, dPr, dQ, da2, da20 = attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, g, ctx.mode, ctx.scale)
+        s_a2, s_a20, s_bU = ctx.shapes
+        d_a2 = da2.view(s_a2) if (s_a2 is not None and da2 is not None) else None
+        d_a20 = da20.view(s_a20) if (s_a20 is not None and da20 is not None) else None
+        d_bU = g.sum(0).view(s_bU) if s_bU is not None else None
+        return (dPc, dPr, dQ, d_a2, d_a20, d_bU, None, None, None, None, None, None)
 
 
 def attention_pool(Pc, Pr, Q, *, mode, a2, a20, bU, user_matrix, return_attention_weights=False, train_mask=None,

@@ -182,6 +182,38 @@ int b200rec_attention_pool_prepare(const b200rec_attention_t* a, b200rec_stream_
  * register-staged 128-bit loads otherwise), 1 = always registers, 2 = TMA whenever the layout allows (H, U <= 128, 16-byte rows). */
 int b200rec_attention_pool_set_path(int path);
 
+/* Gradient of b200rec_attention_pool for the training step (NCF/train.py:99-105 through attention_ncf.py:154-216), dense user_matrix form,
+ * fp32 tables.  Inputs: the forward's operands, its `out`, its `att_weights` (the softmax weights: every pair the forward masked out —
+ * unrated, isclose() target mask :199, zero score under message dropout :189 — has weight 0 and receives no gradient) and grad_out =
+ * dL/dout (B,U).  Writes dPc (B,H); ADDS into dPr (I,H) and dQ (I,U) (contiguous, zero-filled by the caller: many rows share an item,
+ * 128-bit vector reductions); mode NET also writes per-row parts da2_rows (B,H) and da20_rows (B) whose column sums are the gradients
+ * of a2 / a20 (dbU is the column sum of grad_out).  H, U: multiples of 4, <= 512. */
+typedef struct {
+  const float* Pc;
+  const float* Pr;
+  const float* Q;
+  int mode;          /* as b200rec_attention_t */
+  const float* a2;   /* (H), mode NET */
+  const float* bU;   /* (U) or NULL */
+  const float* user_matrix; /* (B,I) */
+  int64_t ld_user_matrix;   /* 0 = I */
+  const float* att_weights; /* (B,I) contiguous, from the forward */
+  const float* out;         /* (B,U) forward output */
+  int64_t ldo;              /* 0 = U */
+  const float* grad_out;    /* (B,U) */
+  int64_t ld_grad_out;      /* 0 = U */
+  int64_t B, I;
+  int H, U;
+  float score_scale;        /* 0 = 1.0 */
+  int64_t ld_pc, ld_pr, ld_q; /* 0 = H / H / U */
+  float* dPc;
+  float* dPr;
+  float* dQ;
+  float* da2_rows;
+  float* da20_rows;
+} b200rec_attention_bwd_t;
+int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a, b200rec_stream_t stream);
+
 /* ---- K3  GraphNCF propagation: edge-balanced CSR SpMM + degree normalisation + fused combine -----------------------
  * Replaces LightGCNConv.forward/message + PyG propagate (gnn_ncf.py:39-94) and the stack+mean of gnn_ncf.py:351:
  *   x_next[r] = dinv[r] · Σ_{k in row r} w[k]·t[col[k]];   acc_out[r] = (acc_in[r] + x_next[r])·acc_scale

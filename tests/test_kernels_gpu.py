@@ -156,3 +156,50 @@ def test_topk_rows_matches_stable_sort(dev, R, C, k):
     ref_idx[nanpos] = -1                                  # a NaN column is reported as "no entry"
     assert np.array_equal(idx.cpu().numpy(), ref_idx)
     assert np.array_equal(val.cpu().numpy(), ref_val)
+
+
+# ---- K2 backward ------------------------------------------------------------------------------------------------------
+def _att_dense_reference(Pc, Pr, Q, a2, a20, bU, um, mode, scale, keep):
+    """float64 restatement of the factorised forward on dense (B, I, .) tensors; `keep` (B, I) bool = pairs that take part"""
+    if mode == 0:
+        s = (torch.relu(Pc[:, None, :] + Pr[None, :, :]) * a2).sum(-1) + a20
+    else:
+        s = Pc @ Pr.T
+    s = (s * scale).masked_fill(~keep, float('-inf'))
+    alpha = torch.nan_to_num(torch.softmax(s, dim=1), nan=0.0)
+    return (alpha * um) @ Q + bU
+
+
+@pytest.mark.parametrize('mode,B,I,H,U', [(0, 70, 900, 128, 128), (0, 9, 300, 132, 64), (1, 40, 500, 128, 128), (0, 5, 64, 8, 260), (1, 3, 50, 4, 12)])
+def test_attention_pool_backward_vs_float64_autograd(dev, mode, B, I, H, U):
+    """csrc/attention_pool_bwd.cu against autograd of a float64 dense restatement: ragged rows (one empty, one full), exact-zero
+    ratings, score_scale != 1.  Tolerance 1e-4 of each gradient's max norm (fp32 kernel, hardware-ordered vector reductions)."""
+    from deeprecommendation_b200 import _lib as L
+    from deeprecommendation_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + I + H)
+    Pc, Pr, Q = torch.randn(B, H, generator=g) * 0.5, torch.randn(I, H, generator=g) * 0.5, torch.randn(I, U, generator=g)
+    a2, a20, bU = torch.randn(H, generator=g) * 0.3, torch.randn(1, generator=g), torch.randn(U, generator=g)
+    dens = torch.rand(B, 1, generator=g) * 0.4
+    um = (torch.randint(1, 11, (B, I), generator=g).float() * 0.5 - 2.75) * (torch.rand(B, I, generator=g) < dens)
+    um[0] = 0.0                                             # nothing rated
+    um[1] = torch.randint(1, 11, (I,), generator=g).float() * 0.5 - 2.75    # everything rated
+    gout = torch.randn(B, U, generator=g)
+    scale = 1.25
+    leaves = [t.double().requires_grad_(True) for t in (Pc, Pr, Q, a2, a20, bU)]
+    ref = _att_dense_reference(*leaves, um.double(), mode, scale, um != 0)
+    ref_grads = torch.autograd.grad(ref, leaves, gout.double(), allow_unused=True)
+    d = [t.to(dev).requires_grad_(True) for t in (Pc, Pr, Q, a2, a20, bU)]
+    out = ops.attention_pool(d[0], d[1], d[2], mode=L.ATT_NET if mode == 0 else L.ATT_DOT, a2=d[3] if mode == 0 else None,
+                             a20=d[4] if mode == 0 else None, bU=d[5], user_matrix=um.to(dev), score_scale=scale)
+    assert maxnorm_rel(out.detach(), ref.detach()) < FP32_TOL
+    out.backward(gout.to(dev))
+    names = ['Pc', 'Pr', 'Q', 'a2', 'a20', 'bU']
+    for k, (t, rg) in enumerate(zip(d, ref_grads)):
+        if mode == 1 and names[k] in ('a2', 'a20'):
+            assert t.grad is None
+            continue
+        if names[k] == 'a20':                               # shifts every score of a row: true gradient 0 (softmax shift invariance)
+            assert float(t.grad.abs().max()) < 1e-4 * float(ref_grads[3].abs().max())
+            continue
+        assert t.grad.shape == rg.shape
+        assert maxnorm_rel(t.grad, rg) < 1e-4, names[k]
