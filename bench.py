@@ -298,7 +298,8 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
                 opt.step()
 
             n_train = max(3, steps // 2)
-            train_ms, _ = timed_steps(train_step, n_train, 3, dist, dev)
+            # warm-up walks every batch shape once: the caching allocator otherwise answers first-seen sizes with cudaMalloc (3 ms each)
+            train_ms, _ = timed_steps(train_step, n_train, nb + 2, dist, dev)
             t_ops = op_breakdown(train_step, min(n_train, nb), 0)
             train = {'ms': train_ms / n_train, 'steps': n_train,
                      'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(t_ops.items(), key=lambda kv: -kv[1][0] * kv[1][1])[:8]}}
