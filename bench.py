@@ -365,7 +365,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
                 launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
-def cpu_attention(w, sample_pairs=64, repeats=3):
+def cpu_attention(w, sample_pairs=BATCH, repeats=3):
     """the reference's own algorithm (oracle port, literal op order incl. the (B*I, E) materialisation) on host cores"""
     from oracle import restatement as R
     torch.set_num_threads(os.cpu_count() or 1)
@@ -757,11 +757,11 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
         model.eval()
         model.load_state_dict(w['sd'])
     ops_ms = op_breakdown(step_eager, min(steps, nb), 0)
-    lin = [(k, v) for k, v in ops_ms.items() if k[0] == 'linear']
+    lin = [(k, v) for k, v in ops_ms.items() if k[0] in ('linear', 'linear_tc_splitk')]
     kms = float(np.mean([v[0] for _, v in lin])) if lin else 0.0
     alg_bytes = 4.0 * (BATCH * F + 128 * F + BATCH * 128)
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-    roof = {'bound': 'hbm', 'kernel': f'gemm_tn_kernel (K1a linear {BATCH}x{F}->128, fp32 FFMA, split-K)', 'achieved': round(achieved, 1),
+    roof = {'bound': 'hbm', 'kernel': (f'gemm_tc_kernel + tc_splitk_reduce_kernel (K1a linear {BATCH}x{F}->128, tcgen05 split-K)' if any(k[0] == 'linear_tc_splitk' for k, _ in lin) else f'gemm_tn_kernel (K1a linear {BATCH}x{F}->128, fp32 FFMA, split-K)'), 'achieved': round(achieved, 1),
             'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('basic'),
             'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
@@ -902,7 +902,7 @@ def reference_arm(args):
     finally:
         torch.Tensor.pin_memory = orig
     from oracle import restatement as R
-    sample = 64
+    sample = int(os.environ.get("B200REC_REF_SAMPLE", "512"))
     times = []
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
@@ -916,8 +916,8 @@ def reference_arm(args):
     line = {'impl': 'reference', 'metric': 'scored user-item pairs/sec (NCF fwd)', 'value': value, 'unit': 'pairs/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': ATT_WORKLOAD, 'batch': BATCH, 'note': f'each step = the first {sample} pairs of a batch of {BATCH} '
-                       f'(the reference materialises two (B*I,128) fp32 tensors, attention_ncf.py:154-155)'},
+            'config': {'workload': ATT_WORKLOAD, 'batch': BATCH, 'note': (f'each step = one whole batch of {BATCH} pairs' if sample >= BATCH else f'each step = the first {sample} pairs of a batch of {BATCH}') +
+                       ' (the reference materialises two (B*I,128) fp32 tensors, attention_ncf.py:154-155: ~12 GB of host memory per batch)'},
             'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                              'sample': f'{sample} pairs per step x {args.steps} steps, oracle/restatement.py::attention_ncf_forward'},
             'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
