@@ -941,6 +941,7 @@ def main():
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
                     help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
     ap.add_argument('--skip-hbm-regime', action='store_true')
+    ap.add_argument('--no-train-step', action='store_true', help='skip the train-step legs (AttentionNCF)')
     ap.add_argument('--graph-scheme', default='reduce', choices=['reduce', 'gather'],
                     help="multi-GPU GraphNCF: 'reduce' = users partitioned, items replicated, one all-reduce of the item partials per "
                          "layer; 'gather' = both sides partitioned, per-layer all-gathers (deeprecommendation_b200/parallel.py)")
@@ -974,7 +975,7 @@ def main():
         if args.workload in ('all', 'attention'):
             w = build_attention(dev, rank)
             w['gemm'] = args.gemm
-            w['no_train'] = world > 1              # the train-step leg is single-GPU (no gradient all-reduce: out of scope)
+            w['no_train'] = world > 1 or args.no_train_step              # the train-step leg is single-GPU (no gradient all-reduce: out of scope)
             w['eager'] = args.eager
             r = run_attention(w, args.steps, args.warmup, dist, dev, peaks)
             pairs = BATCH * args.steps * world

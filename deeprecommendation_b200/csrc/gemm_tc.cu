@@ -534,19 +534,21 @@ tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, in
 }
 
 // number of K splits for a GEMM whose output tiles alone leave most SMs idle (0 = do not split)
-static int tc_splits(long long M, long long N, long long K, int mode, int* kb_per_split) {
+static int tc_splits_tiles(long long tiles, bool n_ok, long long K, int mode, int* kb_per_split) {
   const int KB = (mode == TC_BF16) ? 64 : 32;
-  const long long tiles = ((M + 127) / 128) * ((N + 127) / 128);
   const int num_kb = (int)((K + KB - 1) / KB);
   const int sms = b200rec_num_sms();
   *kb_per_split = 0;
-  if (tiles * 2 > sms || num_kb < 8 || (N % 4) != 0) return 0;
+  if (tiles * 2 > sms || num_kb < 8 || !n_ok) return 0;
   int want = (int)(sms / tiles);
   if (want > num_kb / 3) want = num_kb / 3;                    // at least 3 k-blocks per CTA
   if (want < 2) return 0;
   const int kbps = (num_kb + want - 1) / want;
   *kb_per_split = kbps;
   return (num_kb + kbps - 1) / kbps;
+}
+static int tc_splits(long long M, long long N, long long K, int mode, int* kb_per_split) {
+  return tc_splits_tiles(((M + 127) / 128) * ((N + 127) / 128), (N % 4) == 0, K, mode, kb_per_split);
 }
 
 template <int MODE, int EPL, bool VEC, bool WPACK>
@@ -567,10 +569,13 @@ static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK><<<grid, TC_THREADS, smem, st>>>(b);
   B200REC_CHECK_LAUNCH();
   if (p0.kb_per_split) {
-    const long long total4 = (long long)p0.M * p0.N / 4;
-    tc_splitk_reduce_kernel<<<ceil_div_i(total4, 256), 256, 0, st>>>(p0.partial, nsplit, p0.M, p0.N, p0.Y, p0.ldy, p0.y_bf16, p0.bias,
-                                                                     p0.row_scale, p0.relu);
-    B200REC_CHECK_LAUNCH();
+    for (int q = 0; q < b.n; ++q) {                  // (a batch shares K and kb_per_split: b200rec_linear_tc_splitk_batch)
+      const TcParams& pq = b.prob[q];
+      const long long total4 = (long long)pq.M * pq.N / 4;
+      tc_splitk_reduce_kernel<<<ceil_div_i(total4, 256), 256, 0, st>>>(pq.partial, nsplit, pq.M, pq.N, pq.Y, pq.ldy, pq.y_bf16, pq.bias,
+                                                                       pq.row_scale, pq.relu);
+      B200REC_CHECK_LAUNCH();
+    }
   }
   return B200REC_OK;
 }
@@ -710,4 +715,60 @@ extern "C" int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems,
   if (mode == B200REC_TC_TF32X3) return launch_tc<TC_TF32X3>(b, st);
   if (mode == B200REC_TC_BF16) return launch_tc<TC_BF16>(b, st);
   return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_batch: bad mode");
+}
+
+// Several short-M / long-K GEMMs of one K in ONE split-K launch (BasicNCF's user and item projections: 2 x 4 row tiles dealt out over
+// ~17 k-splits each fill the device in a single wave instead of two 88-CTA launches).  Workspace = splits x sum(M_q x N_q) floats.
+static int tc_batch_splits(const b200rec_linear_problem_t* problems, int n, int64_t K, int mode, int* kbps, size_t* floats) {
+  long long tiles = 0, total = 0;
+  bool n_ok = true;
+  for (int q = 0; q < n; ++q) {
+    if (problems[q].M <= 0) continue;
+    tiles += ((problems[q].M + 127) / 128) * ((problems[q].N + 127) / 128);
+    total += problems[q].M * problems[q].N;
+    n_ok = n_ok && (problems[q].N % 4) == 0;
+  }
+  *floats = (size_t)total;
+  if (tiles == 0) return 0;
+  return tc_splits_tiles(tiles, n_ok, K, mode == B200REC_TC_BF16 ? TC_BF16 : TC_TF32X3, kbps);
+}
+
+extern "C" size_t b200rec_linear_tc_splitk_batch_workspace(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode) {
+  if (!problems || n_problems < 1 || n_problems > TC_MAX_BATCH || K <= 0) return 0;
+  int kbps = 0;
+  size_t floats = 0;
+  const int splits = tc_batch_splits(problems, n_problems, K, mode, &kbps, &floats);
+  return splits > 1 ? (size_t)splits * floats * sizeof(float) : 0;
+}
+
+extern "C" int b200rec_linear_tc_splitk_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode, void* workspace,
+                                              size_t workspace_bytes, b200rec_stream_t stream) {
+  if (!problems || n_problems < 1 || n_problems > TC_MAX_BATCH) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_splitk_batch: 1..4 problems");
+  if (mode != B200REC_TC_TF32X3 && mode != B200REC_TC_BF16) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_splitk_batch: bad mode");
+  int kbps = 0;
+  size_t floats = 0;
+  const int splits = tc_batch_splits(problems, n_problems, K, mode, &kbps, &floats);
+  if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * floats * sizeof(float) || ((uintptr_t)workspace % 16)))
+    return b200rec_fail(B200REC_ERR_WORKSPACE, "linear_tc_splitk_batch: workspace too small");
+  TcBatch b;
+  b.n = 0;
+  b.tile_start[0] = 0;
+  float* part = (float*)workspace;
+  for (int q = 0; q < n_problems; ++q) {
+    const b200rec_linear_problem_t& r = problems[q];
+    if (r.M == 0) continue;
+    const int rc = tc_fill(b.prob[b.n], r.X, r.M, K, r.ldx, r.W, r.N, r.ldw, r.bias, r.row_scale, r.relu, r.Y, r.ldy, r.y_dtype, r.packed_w);
+    if (rc) return rc;
+    if (splits > 1) {
+      b.prob[b.n].kb_per_split = kbps;
+      b.prob[b.n].partial = part;
+      part += (size_t)splits * (size_t)r.M * (size_t)r.N;        // 16-byte aligned: N % 4 == 0
+    }
+    b.tile_start[b.n + 1] = b.tile_start[b.n] + ceil_div_i(r.M, TC_BM);
+    ++b.n;
+  }
+  if (b.n == 0) return B200REC_OK;
+  for (int q = b.n; q < TC_MAX_BATCH; ++q) b.tile_start[q + 1] = b.tile_start[b.n];
+  cudaStream_t st = (cudaStream_t)stream;
+  return mode == B200REC_TC_TF32X3 ? launch_tc<TC_TF32X3>(b, st) : launch_tc<TC_BF16>(b, st);
 }

@@ -1,6 +1,7 @@
 """BasicNCF on the B200 path (reference: neural_collaborative_filtering/models/basic_ncf.py:9-48)."""
 from __future__ import annotations
 
+import torch
 from torch import nn
 
 from ... import ops
@@ -24,8 +25,12 @@ class BasicNCF(NCF):
 
     def forward(self, X_user, X_item):
         ue, ie = self.user_embeddings[0], self.item_embeddings[0]
-        user_emb = ops.linear(X_user, ue.weight, ue.bias)
-        item_emb = ops.linear(X_item, ie.weight, ie.bias)
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            # inference: both projections of the batch in one launch when they are short-M / long-K (split-K over one wave)
+            user_emb, item_emb = ops.linear_pair(X_user, ue.weight, ue.bias, X_item, ie.weight, ie.bias)
+        else:
+            user_emb = ops.linear(X_user, ue.weight, ue.bias)
+            item_emb = ops.linear(X_item, ie.weight, ie.bias)
         return run_mlp(self.MLP, user_emb, item_emb, training=self.training)
 
     def recommend(self, X_users, X_items, k=10, precision='fp32', seen=None, return_scores=False):
@@ -36,7 +41,6 @@ class BasicNCF(NCF):
         tcgen05 kernel (csrc/allpairs.cu); `seen` = CSR (ptr, idx) of pairs to leave out (`ignore_seen`, backend.py:85)."""
         if self.training:
             raise RuntimeError('recommend() is an inference call: model.eval() first')
-        import torch
         ue, ie = self.user_embeddings[0], self.item_embeddings[0]
         with torch.no_grad():
             user_emb = ops.linear_raw(X_users, ue.weight, ue.bias)

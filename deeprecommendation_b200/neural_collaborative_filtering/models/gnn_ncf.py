@@ -1,6 +1,8 @@
 """GraphNCF on the B200 path (reference: neural_collaborative_filtering/models/gnn_ncf.py:13-94,180-378)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -84,7 +86,7 @@ class GraphNCF(GNN_NCF):
     the transform GEMM's epilogue and K3 gathers 2-byte features (half the bytes through L1 / L2 / HBM); accumulation, the
     running mean and everything else stay fp32.  Tolerance of this mode: max-norm relative error <= 1e-2 (north_star)."""
 
-    message_dtype = 'fp32'
+    message_dtype = os.environ.get('B200REC_GRAPH_MESSAGE_DTYPE', 'fp32')
 
     def __init__(self, item_dim, user_dim, num_gnn_layers: int, hetero, node_emb=64, mlp_dense_layers=None, dropout_rate=0.2,
                  use_dot_product=False, concat=False, message_dropout=None, node_dropout=None, convType='LightGCN',

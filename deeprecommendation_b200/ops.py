@@ -11,6 +11,7 @@ CUDA ops for now (documented in DESIGN.md §7).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -104,7 +105,7 @@ def _dtype_code(dt):
 # ------------------------------------------------------------------------------------------------------------------
 # GEMM engine for K1a: 'simt' = fp32 FFMA everywhere; 'tf32x3' / 'bf16' = tcgen05 tensor-core kernel (csrc/gemm_tc.cu) for
 # large M, FFMA for the small ones (a 128-row tile per CTA cannot fill 148 SMs below ~2k rows).
-_gemm_engine = 'simt'
+_gemm_engine = os.environ.get('B200REC_GEMM_ENGINE', 'simt')   # bench.py and the serving paths select 'tf32x3' (set_gemm_engine)
 TC_MIN_ROWS = 2048
 TC_SPLITK_MIN_ROWS = 128      # below TC_MIN_ROWS the tensor-core GEMM runs split-K (if K is long enough to be dealt out)
 SHORTK_MIN_ROWS = 4096  # below this a handful of 64x64 FFMA tiles is as fast as the persistent kernel's set-up
@@ -252,6 +253,49 @@ def linear_tc_batch(problems, engine=None):
     with torch.cuda.device(dev), _timed('linear_tc_batch', (sum(m for m, _ in meta), K, max(n for _, n in meta))):
         L.check(L.lib().b200rec_linear_tc_batch(arr, len(problems), K, mode, _stream()), 'linear_tc_batch')
     return outs
+
+
+def linear_pair(xa, wa, ba, xb, wb, bb):
+    """(xa @ wa.T + ba, xb @ wb.T + bb) — the two projections of one NCF batch (basic_ncf.py:38-39).  When both are short-M / long-K
+    problems of the same K on a tensor-core engine they share ONE split-K launch (b200rec_linear_tc_splitk_batch); otherwise two
+    `linear_raw` calls.  Inference only."""
+    engine = _gemm_engine
+    Ma, Mb, K = xa.shape[0], xb.shape[0], xa.shape[1]
+    ok = (engine != 'simt' and xb.shape[1] == K and K >= TC_MIN_K and TC_SPLITK_MIN_ROWS <= Ma < TC_MIN_ROWS and
+          TC_SPLITK_MIN_ROWS <= Mb < TC_MIN_ROWS and wa.shape[0] % 4 == 0 and wb.shape[0] % 4 == 0)
+    if not ok:
+        return linear_raw(xa, wa, ba), linear_raw(xb, wb, bb)
+    _require_cuda(xa, wa, ba, xb, wb, bb)
+    mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+    arr = (L.LinearProblem * 2)()
+    keep, outs = [], []
+    for q, (x, weight, bias) in enumerate(((xa, wa, ba), (xb, wb, bb))):
+        x, ldx = _row_major(x)
+        w, ldw = _row_major(weight)
+        M, N = x.shape[0], w.shape[0]
+        if w.shape[1] != K:
+            raise ValueError(f'linear_pair: weight is {tuple(w.shape)}, input is {tuple(x.shape)}')
+        if M * ldx >= 2 ** 32:
+            return linear_raw(xa, wa, ba), linear_raw(xb, wb, bb)
+        if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+            bias = bias.contiguous().float()
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        packed = _packed_weight(weight if weight is w else w, ldw, mode) if _pack_weights else None
+        pr = arr[q]
+        pr.X, pr.M, pr.ldx = x.data_ptr(), M, ldx
+        pr.W, pr.N, pr.ldw = w.data_ptr(), N, ldw
+        pr.packed_w = packed.data_ptr() if packed is not None else None
+        pr.bias = bias.data_ptr() if bias is not None else None
+        pr.row_scale, pr.relu = None, 0
+        pr.Y, pr.ldy, pr.y_dtype = out.data_ptr(), N, L.F32
+        keep += [x, w, bias, packed]
+        outs.append(out)
+    lib = L.lib()
+    ws_bytes = lib.b200rec_linear_tc_splitk_batch_workspace(arr, 2, K, mode)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=outs[0].device)
+    with torch.cuda.device(outs[0].device), _timed('linear_tc_splitk_batch', (Ma + Mb, K, max(wa.shape[0], wb.shape[0]))):
+        L.check(lib.b200rec_linear_tc_splitk_batch(arr, 2, K, mode, _ptr(ws), ws_bytes, _stream()), 'linear_tc_splitk_batch')
+    return outs[0], outs[1]
 
 
 class _LinearFn(torch.autograd.Function):

@@ -77,6 +77,11 @@ typedef struct {
   void* Y; int64_t ldy; int y_dtype;
 } b200rec_linear_problem_t;
 int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode, b200rec_stream_t stream);
+/* The same batch as split-K (short M, long K — BasicNCF's user and item projections, basic_ncf.py:38-39, in one wave): workspace from
+ * b200rec_linear_tc_splitk_batch_workspace (0 = no split pays: the call then behaves like b200rec_linear_tc_batch). */
+size_t b200rec_linear_tc_splitk_batch_workspace(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode);
+int b200rec_linear_tc_splitk_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode, void* workspace,
+                                   size_t workspace_bytes, b200rec_stream_t stream);
 /* Optional: W converted once into MMA-ready swizzled tiles (bf16 or TF32 hi/lo, zero-padded).  With `packed_w` the GEMM moves
  * the W operand by TMA bulk copies (cp.async.bulk) and only X is converted by the producer warps.  128-byte aligned buffer. */
 size_t b200rec_packed_weight_bytes(int64_t N, int64_t K, int mode);

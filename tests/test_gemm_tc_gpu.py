@@ -120,3 +120,19 @@ def test_linear_shortk_bf16_output(M, K, N):
     out = torch.full((M, N + 12), 3.0, device='cuda', dtype=torch.bfloat16)
     ops.linear_raw(x.cuda(), w.cuda(), b.cuda(), s.cuda(), out=out[:, 6:6 + N], engine='shortk!')       # rows only 4-byte aligned
     assert torch.equal(out[:, 6:6 + N], y16) and torch.all(out[:, :6] == 3.0) and torch.all(out[:, 6 + N:] == 3.0)
+
+
+@pytest.mark.parametrize('Ma,Mb,K,Na,Nb', [(512, 512, 2094, 128, 128), (300, 129, 2094, 256, 64), (512, 512, 700, 128, 128), (100, 512, 2094, 128, 128)])
+def test_linear_pair_batched_splitk(Ma, Mb, K, Na, Nb):
+    """BasicNCF's two projections in one split-K launch (b200rec_linear_tc_splitk_batch): fp32 parity for both outputs; shapes the batch
+    does not cover (M below the split-K window) fall through to two single launches with the same results"""
+    from deeprecommendation_b200 import ops
+    xa, wa, ba, _ = _case(Ma, K, Na, 3)
+    xb, wb, bb, _ = _case(Mb, K, Nb, 4)
+    prev = ops.set_gemm_engine('tf32x3')
+    try:
+        ya, yb = ops.linear_pair(xa.cuda(), wa.cuda(), ba.cuda(), xb.cuda(), wb.cuda(), bb.cuda())
+    finally:
+        ops.set_gemm_engine(prev)
+    assert maxnorm_rel(ya, torch.nn.functional.linear(xa.double(), wa.double(), ba.double())) < 1e-5
+    assert maxnorm_rel(yb, torch.nn.functional.linear(xb.double(), wb.double(), bb.double())) < 1e-5
