@@ -36,7 +36,7 @@ class AttentionBwdDesc(C.Structure):
     _fields_ = [('Pc', c_vp), ('Pr', c_vp), ('Q', c_vp), ('mode', c_int), ('a2', c_vp), ('bU', c_vp), ('user_matrix', c_vp), ('ld_user_matrix', c_i64),
                 ('att_weights', c_vp), ('out', c_vp), ('ldo', c_i64), ('grad_out', c_vp), ('ld_grad_out', c_i64), ('B', c_i64), ('I', c_i64),
                 ('H', c_int), ('U', c_int), ('score_scale', c_f), ('ld_pc', c_i64), ('ld_pr', c_i64), ('ld_q', c_i64),
-                ('dPc', c_vp), ('dPr', c_vp), ('dQ', c_vp), ('da2_rows', c_vp), ('da20_rows', c_vp)]
+                ('dPc', c_vp), ('dPr', c_vp), ('dQ', c_vp), ('da2_rows', c_vp), ('da20_rows', c_vp), ('n_slices', c_int)]
 
 
 class LinearProblem(C.Structure):

@@ -13,7 +13,9 @@
 //   DOT:  dPc[b] += ds_bi·Pr[i];  dPr[i] += ds_bi·Pc[b]
 //
 // Everything the forward masked out (unrated items, the isclose() target mask :199, zero scores under message dropout :189) has
-// α = 0 and contributes nothing, so the masks are not re-evaluated here.  One CTA per candidate row: its 8 warps scan the row's
+// α = 0 and contributes nothing, so the masks are not re-evaluated here.  One CTA per (candidate row, column slice) — `n_slices` deals
+// a row's non-zeros out over several CTAs, because a CTA-per-row grid ran 43 % busy behind its 2.7 k-non-zero rows (ncu, profiles/r01);
+// the per-row outputs then come as one part per slice and the caller adds the parts.  The CTA's 8 warps scan their slice of the row's
 // α (coalesced, 19 MB per 512 x 9.4k batch), and every non-zero is handled by a whole warp — one 128-bit load of the Q row and of
 // the Pr row per lane, a 5-shuffle dot product, register accumulation of the per-row gradients (dPc, da2, da20: summed over the
 // warps in warp order, bit-reproducible) and 128-bit vector reductions (`red.global.add.v4.f32`) into the per-item gradients
@@ -29,6 +31,7 @@ struct AttBwdParams {
   const float *Pc, *Pr, *Q, *a2, *um, *att, *out, *bU, *g;
   long long ldPc, ldPr, ldQ, ld_um, ldo, ldg;
   int B, I, H, U;
+  int n_slices, slice_cols;  // grid.y and the columns per slice (multiple of 32); a row's non-zeros are dealt out over gridDim.y CTAs
   float score_scale;
   float *dPc, *dPr, *dQ, *da2_rows, *da20_rows;     // dPc (B,H) and the per-row parts are written; dPr (I,H), dQ (I,U) are added to
 };
@@ -142,10 +145,12 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) attention_pool_bwd_kernel(AttB
   BwdRow<HV, UV, MODE> row(p, lane, b);
   const float* arow = p.att + (long long)b * p.I;
   const float* urow = p.um + (long long)b * p.ld_um;
-  for (int base = warp * 32; base < p.I; base += BWD_WARPS * 32) {
+  const int c_begin = (int)blockIdx.y * p.slice_cols, c_end = min(p.I, c_begin + p.slice_cols);
+  const long long orow = (long long)blockIdx.y * p.B + b;        // row of the per-slice outputs (dPc, da2_rows, da20_rows)
+  for (int base = c_begin + warp * 32; base < c_end; base += BWD_WARPS * 32) {
     const int i = base + lane;
     float a = 0.f, u = 0.f;
-    if (i < p.I) { a = __ldcs(arow + i); u = __ldcs(urow + i); }
+    if (i < c_end) { a = __ldcs(arow + i); u = __ldcs(urow + i); }
     unsigned mask = __ballot_sync(FULL, a != 0.f);
     while (mask) {
       const int j0 = __ffs(mask) - 1;
@@ -172,23 +177,24 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) attention_pool_bwd_kernel(AttB
       s += s_dpc[w][h];
       if (MODE == BWD_NET) s2 += s_da2[w][h];
     }
-    p.dPc[(long long)b * p.H + h] = s;
-    if (MODE == BWD_NET) p.da2_rows[(long long)b * p.H + h] = s2;
+    p.dPc[orow * p.H + h] = s;
+    if (MODE == BWD_NET) p.da2_rows[orow * p.H + h] = s2;
   }
   if (MODE == BWD_NET && threadIdx.x == 0) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < BWD_WARPS; ++w) s += s_da20[w];
-    p.da20_rows[b] = s;
+    p.da20_rows[orow] = s;
   }
 }
 
 template <int MODE>
 static int launch_bwd(const AttBwdParams& p, cudaStream_t st) {
   const int w = p.H > p.U ? p.H : p.U;
-  if (w <= 128) attention_pool_bwd_kernel<1, 1, MODE><<<p.B, BWD_WARPS * 32, 0, st>>>(p);
-  else if (w <= 256) attention_pool_bwd_kernel<2, 2, MODE><<<p.B, BWD_WARPS * 32, 0, st>>>(p);
-  else if (w <= 512) attention_pool_bwd_kernel<4, 4, MODE><<<p.B, BWD_WARPS * 32, 0, st>>>(p);
+  const dim3 grid(p.B, p.n_slices);               // every part is written, also one whose slice starts beyond I (zeros)
+  if (w <= 128) attention_pool_bwd_kernel<1, 1, MODE><<<grid, BWD_WARPS * 32, 0, st>>>(p);
+  else if (w <= 256) attention_pool_bwd_kernel<2, 2, MODE><<<grid, BWD_WARPS * 32, 0, st>>>(p);
+  else if (w <= 512) attention_pool_bwd_kernel<4, 4, MODE><<<grid, BWD_WARPS * 32, 0, st>>>(p);
   else return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool_backward: att_dense / user_emb wider than 512");
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
@@ -215,6 +221,12 @@ extern "C" int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a,
   p.ld_um = a->ld_user_matrix ? a->ld_user_matrix : a->I; p.ldo = a->ldo ? a->ldo : a->U; p.ldg = a->ld_grad_out ? a->ld_grad_out : a->U;
   p.B = (int)a->B; p.I = (int)a->I; p.H = a->H; p.U = a->U;
   p.score_scale = a->score_scale == 0.f ? 1.f : a->score_scale;
+  {
+    const int n_slices = a->n_slices > 1 ? a->n_slices : 1;
+    if (n_slices > 65535) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_backward: too many slices");
+    p.n_slices = n_slices;
+    p.slice_cols = (int)(((a->I + n_slices - 1) / n_slices + 31) / 32 * 32);
+  }
   p.dPc = a->dPc; p.dPr = a->dPr; p.dQ = a->dQ; p.da2_rows = a->da2_rows; p.da20_rows = a->da20_rows;
   if (p.ldPc < p.H || p.ldPr < p.H || p.ldQ < p.U || p.ldo < p.U || p.ldg < p.U || p.ld_um < p.I || (p.ldPc % 4) || (p.ldPr % 4) || (p.ldQ % 4) ||
       (p.ldo % 4) || (p.ldg % 4))

@@ -105,7 +105,7 @@ def _dtype_code(dt):
 # ------------------------------------------------------------------------------------------------------------------
 # GEMM engine for K1a: 'simt' = fp32 FFMA everywhere; 'tf32x3' / 'bf16' = tcgen05 tensor-core kernel (csrc/gemm_tc.cu) for
 # large M, FFMA for the small ones (a 128-row tile per CTA cannot fill 148 SMs below ~2k rows).
-_gemm_engine = os.environ.get('B200REC_GEMM_ENGINE', 'simt')   # bench.py and the serving paths select 'tf32x3' (set_gemm_engine)
+_gemm_engine = os.environ.get('B200REC_GEMM_ENGINE', 'tf32x3')   # fp32-parity tensor-core engine by default (the whole GPU suite passes under it)
 TC_MIN_ROWS = 2048
 TC_SPLITK_MIN_ROWS = 128      # below TC_MIN_ROWS the tensor-core GEMM runs split-K (if K is long enough to be dealt out)
 SHORTK_MIN_ROWS = 4096  # below this a handful of 64x64 FFMA tiles is as fast as the persistent kernel's set-up
@@ -630,6 +630,9 @@ def propagate(t, index, w, w_bwd, dinv, skip_bits=None):
 # ------------------------------------------------------------------------------------------------------------------
 # K2 autograd wrapper
 # ------------------------------------------------------------------------------------------------------------------
+ATT_BWD_SLICES = 4
+
+
 def _f32_rows(t):
     """fp32, unit column stride, 16-byte aligned rows (what the 128-bit loads of K2 need); copies only when it must"""
     if t.dtype != torch.float32 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
@@ -647,12 +650,13 @@ def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode,
     B, H = Pc.shape
     I, U = Q.shape
     dev = Pc.device
-    dPc = torch.empty((B, H), dtype=torch.float32, device=dev)
+    S = ATT_BWD_SLICES if I >= 1024 else 1              # CTAs per candidate row (long rows would otherwise set the tail)
+    dPc = torch.empty((S * B, H), dtype=torch.float32, device=dev)
     dPr = torch.zeros((I, H), dtype=torch.float32, device=dev)
     dQ = torch.zeros((I, U), dtype=torch.float32, device=dev)
     net = mode == L.ATT_NET
-    da2_rows = torch.empty((B, H), dtype=torch.float32, device=dev) if net else None
-    da20_rows = torch.empty((B,), dtype=torch.float32, device=dev) if net else None
+    da2_rows = torch.empty((S * B, H), dtype=torch.float32, device=dev) if net else None
+    da20_rows = torch.empty((S * B,), dtype=torch.float32, device=dev) if net else None
     if B == 0 or I == 0:
         dPc.zero_()
         return dPc, dPr, dQ, (torch.zeros(H, device=dev) if net else None), (torch.zeros((), device=dev) if net else None)
@@ -670,13 +674,15 @@ def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode,
     d.user_matrix, d.ld_user_matrix = um.data_ptr(), ld_um
     d.att_weights, d.out, d.ldo = att.data_ptr(), out.data_ptr(), (out.stride(0) if B > 1 else U)
     d.grad_out, d.ld_grad_out = grad_out.data_ptr(), (grad_out.stride(0) if B > 1 else U)
-    d.B, d.I, d.H, d.U, d.score_scale = B, I, H, U, float(score_scale)
+    d.B, d.I, d.H, d.U, d.score_scale, d.n_slices = B, I, H, U, float(score_scale), S
     d.ld_pc, d.ld_pr, d.ld_q = (Pc.stride(0) if B > 1 else H), (Pr.stride(0) if I > 1 else H), (Q.stride(0) if I > 1 else U)
     d.dPc, d.dPr, d.dQ = dPc.data_ptr(), dPr.data_ptr(), dQ.data_ptr()
     if net:
         d.da2_rows, d.da20_rows = da2_rows.data_ptr(), da20_rows.data_ptr()
     with torch.cuda.device(dev), _timed('attention_pool_backward', (B, I, H, U)):
         L.check(L.lib().b200rec_attention_pool_backward(C.byref(d), _stream()), 'attention_pool_backward')
+    if S > 1:
+        dPc = dPc.view(S, B, H).sum(0)
     return dPc, dPr, dQ, (da2_rows.sum(0) if net else None), (da20_rows.sum() if net else None)
 
 

@@ -216,6 +216,8 @@ typedef struct {
   float* dQ;
   float* da2_rows;
   float* da20_rows;
+  int n_slices;             /* 0 / 1 = one CTA per row; n > 1 = the columns are dealt out over n CTAs per row and dPc, da2_rows, da20_rows
+                             * hold n parts of B rows each (part-major), which the caller adds */
 } b200rec_attention_bwd_t;
 int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a, b200rec_stream_t stream);
 
