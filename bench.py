@@ -382,6 +382,26 @@ def cpu_attention(w, sample_pairs=BATCH, repeats=3):
         f'{sample_pairs} pairs of batch 0 (I={rated.shape[0]} rated items, F={F}), median of {repeats} forwards, oracle/restatement.py'
 
 
+def cpu_attention_train(w, sample_pairs=64, repeats=3):
+    """the reference's train step on host cores: forward in train mode (oracle port, dropouts 0) + sum-MSE backward + Adam
+    (NCF/train.py:99-105) on the first `sample_pairs` pairs of batch 0 — a whole batch would hold ~40 GB of autograd state"""
+    from oracle import restatement as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    cand, rated, um = (t.clone() for t in w['host'][0])
+    cand, um = cand[:sample_pairs], um[:sample_pairs]
+    sd = {k: v.clone().requires_grad_(True) for k, v in w['sd'].items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-4)
+    y = torch.rand(sample_pairs, 1) * 4.5 + 0.5
+    ts = []
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        (R.attention_ncf_forward(sd, cand, rated, um, training=True) - y).square().sum().backward()
+        opt.step()
+        ts.append(time.perf_counter() - t0)
+    return sample_pairs / float(np.median(ts[1:])), f'{sample_pairs} pairs of batch 0, median of {repeats} steps'
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # workload B — GraphNCF propagation, BASELINE configs[2]
 # ----------------------------------------------------------------------------------------------------------------------
@@ -1006,6 +1026,13 @@ def main():
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 v, cores, sample = cpu_attention(w)
                 result['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+                if r.get('train') and 'ms' in r['train']:
+                    try:
+                        tv, tsample = cpu_attention_train(w)
+                        result['cpu_baseline']['train_step_value'] = tv
+                        result['cpu_baseline']['train_step_sample'] = tsample
+                    except Exception as e:
+                        result['cpu_baseline']['train_step_error'] = repr(e)[:200]
             del w
             torch.cuda.empty_cache()
         if args.workload in ('all', 'basic'):

@@ -744,7 +744,8 @@ static int att_prepare(int B, int I, int U, const AttInputs& in, cudaStream_t st
     int* wnnz = reinterpret_cast<int*>(wval + (size_t)B * I);
     if (launch) {
       const size_t row_bytes = (size_t)I * sizeof(float);
-      if (row_bytes <= 96 * 1024 && !in.prepare_light) {
+      static const bool streaming = []() { const char* e = getenv("B200REC_ATT_COMPACT_STREAMING"); return e != nullptr && atoi(e) != 0; }();
+      if (row_bytes <= 96 * 1024 && !in.prepare_light && !streaming) {
         static bool attr_set = false;
         if (!attr_set) {
           B200REC_CUDA(cudaFuncSetAttribute(um_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
