@@ -136,6 +136,38 @@ def attention_ncf_forward_blocked(sd, candidate_items, rated_items, user_matrix,
 
 
 # --------------------------------------------------------------------------------------------------
+# f-1  gradient of the attention pooling (attention_ncf.py:154-216 under NCF/train.py:99-105), in the factorised form
+#      the CUDA path computes (csrc/attention_pool.cu): s = scale·(a2·ReLU(Pc[b]+Pr[i]) + a20) or scale·<Pc[b],Pr[i]>,
+#      alpha = softmax over the kept pairs, out = (alpha∘um)·Q + bU
+# --------------------------------------------------------------------------------------------------
+def attention_pool_factorised(Pc, Pr, Q, a2, a20, bU, um, keep, *, net=True, scale=1.0):
+    """Dense restatement of the factorised forward; `keep` (B, I) bool = pairs that take part.  Returns (out, alpha)."""
+    if net:
+        s = (torch.relu(Pc[:, None, :] + Pr[None, :, :]) * a2).sum(-1) + a20
+    else:
+        s = Pc @ Pr.T
+    s = (s * scale).masked_fill(~keep, float('-inf'))
+    alpha = torch.nan_to_num(torch.softmax(s, dim=1), nan=0.0)          # rows with nothing kept -> 0 (:208-209)
+    return (alpha * um) @ Q + bU, alpha
+
+
+def attention_pool_backward(Pc, Pr, Q, a2, bU, um, alpha, out, g, *, net=True, scale=1.0):
+    """Closed-form gradients of `attention_pool_factorised` from its outputs (what csrc/attention_pool_bwd.cu evaluates per
+    non-zero): ds = scale·alpha·(um·<g[b],Q[i]> − <g[b], out[b]−bU>).  Returns dict(Pc, Pr, Q, a2, a20, bU)."""
+    gq = g @ Q.T                                                         # (B, I): <g[b], Q[i]>
+    gdot = (g * (out - bU)).sum(1, keepdim=True)                         # softmax row sum Σ_j alpha_bj·dalpha_bj
+    ds = scale * alpha * (um * gq - gdot)
+    grads = {'Q': (alpha * um).T @ g, 'bU': g.sum(0)}
+    if net:
+        z = Pc[:, None, :] + Pr[None, :, :]                              # (B, I, H)
+        t = ds[:, :, None] * a2 * (z > 0)
+        grads.update(Pc=t.sum(1), Pr=t.sum(0), a2=(ds[:, :, None] * torch.relu(z)).sum((0, 1)), a20=ds.sum())
+    else:
+        grads.update(Pc=ds @ Pr, Pr=ds.T @ Pc, a2=None, a20=None)
+    return grads
+
+
+# --------------------------------------------------------------------------------------------------
 # a-4  LightGCNConv.forward / message — models/gnn_ncf.py:39-94 (+ PyG propagate/degree, pyg_shim)
 # --------------------------------------------------------------------------------------------------
 def _propagate_add(x, edge_index, norm, weight, W, b):

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import restatement as R
 from tests._golden import maxnorm_rel
 
 pytestmark = pytest.mark.gpu
@@ -159,17 +160,6 @@ def test_topk_rows_matches_stable_sort(dev, R, C, k):
 
 
 # ---- K2 backward ------------------------------------------------------------------------------------------------------
-def _att_dense_reference(Pc, Pr, Q, a2, a20, bU, um, mode, scale, keep):
-    """float64 restatement of the factorised forward on dense (B, I, .) tensors; `keep` (B, I) bool = pairs that take part"""
-    if mode == 0:
-        s = (torch.relu(Pc[:, None, :] + Pr[None, :, :]) * a2).sum(-1) + a20
-    else:
-        s = Pc @ Pr.T
-    s = (s * scale).masked_fill(~keep, float('-inf'))
-    alpha = torch.nan_to_num(torch.softmax(s, dim=1), nan=0.0)
-    return (alpha * um) @ Q + bU
-
-
 @pytest.mark.parametrize('mode,B,I,H,U', [(0, 70, 900, 128, 128), (0, 9, 300, 132, 64), (1, 40, 500, 128, 128), (0, 5, 64, 8, 260), (1, 3, 50, 4, 12)])
 def test_attention_pool_backward_vs_float64_autograd(dev, mode, B, I, H, U):
     """csrc/attention_pool_bwd.cu against autograd of a float64 dense restatement: ragged rows (one empty, one full), exact-zero
@@ -186,7 +176,7 @@ def test_attention_pool_backward_vs_float64_autograd(dev, mode, B, I, H, U):
     gout = torch.randn(B, U, generator=g)
     scale = 1.25
     leaves = [t.double().requires_grad_(True) for t in (Pc, Pr, Q, a2, a20, bU)]
-    ref = _att_dense_reference(*leaves, um.double(), mode, scale, um != 0)
+    ref, _ = R.attention_pool_factorised(*leaves, um.double(), um != 0, net=mode == 0, scale=scale)     # oracle/restatement.py
     ref_grads = torch.autograd.grad(ref, leaves, gout.double(), allow_unused=True)
     d = [t.to(dev).requires_grad_(True) for t in (Pc, Pr, Q, a2, a20, bU)]
     out = ops.attention_pool(d[0], d[1], d[2], mode=L.ATT_NET if mode == 0 else L.ATT_DOT, a2=d[3] if mode == 0 else None,

@@ -167,3 +167,27 @@ def test_restatement_vs_live_reference_shipped_checkpoint():
         out, att = m(cand, rated, um, return_attention_weights=True)
     o2, a2 = R.attention_ncf_forward(state, cand, rated, um, return_attention_weights=True)
     assert maxnorm_rel(o2, out) < TOL and maxnorm_rel(a2, att) < TOL
+
+
+@pytest.mark.parametrize('net', [True, False])
+def test_attention_pool_backward_closed_form_vs_autograd(net):
+    """the per-non-zero gradient formulas the K2 backward kernel evaluates (oracle.attention_pool_backward) == autograd of the
+    factorised forward, in float64: empty rows, a full row, masked pairs, score_scale != 1"""
+    g = torch.Generator().manual_seed(5)
+    B, I, H, U = 9, 40, 12, 8
+    Pc, Pr, Q = (torch.randn(n, w, generator=g, dtype=torch.float64) for n, w in ((B, H), (I, H), (I, U)))
+    a2, a20, bU = (torch.randn(n, generator=g, dtype=torch.float64) for n in (H, 1, U))
+    um = (torch.randint(1, 11, (B, I), generator=g).double() * 0.5 - 2.75) * (torch.rand(B, I, generator=g) < 0.3)
+    um[0] = 0.0
+    um[1] = torch.randint(1, 11, (I,), generator=g).double() * 0.5 - 2.75
+    keep = (um != 0) & (torch.rand(B, I, generator=g) < 0.9)            # some rated pairs masked out (target mask / dropped scores)
+    gout = torch.randn(B, U, generator=g, dtype=torch.float64)
+    leaves = [t.clone().requires_grad_(True) for t in (Pc, Pr, Q, a2, a20, bU)]
+    out, alpha = R.attention_pool_factorised(*leaves, um, keep, net=net, scale=1.25)
+    auto = torch.autograd.grad(out, leaves, gout, allow_unused=True)
+    got = R.attention_pool_backward(Pc, Pr, Q, a2, bU, um, alpha.detach(), out.detach(), gout, net=net, scale=1.25)
+    for name, ref in zip(('Pc', 'Pr', 'Q', 'a2', 'a20', 'bU'), auto):
+        if not net and name in ('a2', 'a20'):
+            assert got[name] is None
+            continue
+        assert torch.allclose(got[name].reshape(ref.shape), ref, rtol=1e-10, atol=1e-12), name
