@@ -502,6 +502,32 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
 
     ops_ms = op_breakdown(step_eager, min(steps, 4), 0)
+
+    # training step on the same graph (NCF/train.py:99-105 through gnn_ncf.py:298-367): target edges of the batch masked out of the
+    # propagation (pair hash + skip bitmap), conv / MLP dropout, sum-MSE backward (K3 on the reverse-edge weights, gradient GEMMs on
+    # K1a) and Adam; eager launches
+    train = None
+    if w.get('train_leg') and getattr(graph, '_b200rec_partition', None) is None:
+        try:
+            model.train()
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+            ys = torch.rand(BATCH, 1, device=dev) * 4.5 + 0.5
+
+            def train_step(i):
+                a, b = ids[i % len(ids)]
+                opt.zero_grad(set_to_none=True)
+                (model(graph, a, b, dev) - ys).square().sum().backward()
+                opt.step()
+
+            n_train = max(3, steps // 4)
+            train_ms, _ = timed_steps(train_step, n_train, 3, dist, dev)
+            train = {'ms': train_ms / n_train, 'steps': n_train}
+        except Exception as e:
+            train = {'error': repr(e)[:300]}
+        finally:
+            model.eval()
+            model.load_state_dict(w['sd'])
+            torch.cuda.empty_cache()
     spmm = [(k, v) for k, v in ops_ms.items() if k[0] == 'spmm']
     kms = spmm[0][1][0] if spmm else 0.0
     N, d, E2 = index.num_nodes, w['d'], index.e1 + index.e2
@@ -518,7 +544,7 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes), 'features_fit_l2': bool(feat <= l2),
             'gather_inclusive_gbs': round((E2 * 8 + E2 * d * ts) / (kms * 1e-3) / 1e9, 1) if kms > 0 else 0.0,
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
-    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof,
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof, train=train,
                 launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
@@ -961,7 +987,7 @@ def main():
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
                     help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
     ap.add_argument('--skip-hbm-regime', action='store_true')
-    ap.add_argument('--no-train-step', action='store_true', help='skip the train-step legs (AttentionNCF)')
+    ap.add_argument('--no-train-step', action='store_true', help='skip the eager train-step legs (AttentionNCF, GraphNCF)')
     ap.add_argument('--graph-scheme', default='reduce', choices=['reduce', 'gather'],
                     help="multi-GPU GraphNCF: 'reduce' = users partitioned, items replicated, one all-reduce of the item partials per "
                          "layer; 'gather' = both sides partitioned, per-layer all-gathers (deeprecommendation_b200/parallel.py)")
@@ -1065,6 +1091,7 @@ def main():
         if args.workload in ('all', 'graph'):
             w = build_graph(dev, args.graph_scale, world, args.graph_scheme)
             w['eager'] = args.eager
+            w['train_leg'] = world == 1 and not args.no_train_step
             r = run_graph(w, args.steps, args.warmup, dist, dev, peaks)
             msgs = 2.0 * w['E'] * w['L'] * args.steps          # the graph is fixed: strong scaling
             entry = {'metric': 'GNN propagation directed-edge messages/sec (GraphNCF fwd)', 'value': msgs / (r['ms'] * 1e-3),
@@ -1078,7 +1105,15 @@ def main():
                      'roofline': r['roofline'],
                      'e2e': {'value': msgs / (r['e2e_ms'] * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
                      'gpu_launches': r['launches']}
+            if r.get('train'):
+                t = r['train']
+                entry['train_step'] = ({'value': 2.0 * w['E'] * w['L'] / (t['ms'] * 1e-3), 'unit': 'edges/s', 'ms_per_step': t['ms'], 'steps': t['steps'],
+                                        'launch_mode': 'eager',
+                                        'what': 'whole-graph forward in train mode with the 512 target edges masked out (pair hash + skip bitmap), conv and '
+                                                'MLP dropout, sum-MSE backward (K3 on the reverse-edge weights, gradient GEMMs on K1a) and Adam; value counts '
+                                                'the forward messages only (2E*L per step), like the inference line'} if 'ms' in t else t)
             if world == 1:
+                w['train_leg'] = False
                 # bf16 message mode (north_star: rel <= 1e-2): the transform GEMM rounds t once to bf16, K3 gathers 2-byte features
                 w['model'].message_dtype = 'bf16'
                 try:

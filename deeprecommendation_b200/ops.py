@@ -630,7 +630,7 @@ def propagate(t, index, w, w_bwd, dinv, skip_bits=None):
 # ------------------------------------------------------------------------------------------------------------------
 # K2 autograd wrapper
 # ------------------------------------------------------------------------------------------------------------------
-ATT_BWD_SLICES = 4
+ATT_BWD_SLICES = int(os.environ.get('B200REC_ATT_BWD_SLICES', '1'))   # CTAs per candidate row in K2's backward (4 once measured)
 
 
 def _f32_rows(t):
