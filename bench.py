@@ -205,7 +205,12 @@ def build_attention(dev, rank, n_batches=8):
         rated = torch.from_numpy(profiles[rated_idx]).pin_memory()
         host.append((cand, rated, torch.from_numpy(um).pin_memory()))
         nnz.append(int((um != 0).sum()))
-    return dict(model=model, sd=sd, host=host, nnz=nnz, kw=kw, resident_form=resident_form)
+    # the reference's serving call (src/webapp/backend.py:78-121): ONE user, every unseen item of the catalogue a candidate
+    counts = np.diff(row_ptr)
+    su = int(np.argsort(counts)[len(counts) // 2])                       # the user with the median number of rated items
+    serving = dict(profiles=profiles, positions=idx[row_ptr[su]:row_ptr[su + 1]].astype(np.int64), ratings=rr[row_ptr[su]:row_ptr[su + 1]].astype(np.float64),
+                   table=(rprov.table if rprov is not None else None))
+    return dict(model=model, sd=sd, host=host, nnz=nnz, kw=kw, resident_form=resident_form, serving=serving)
 
 
 def run_attention(w, steps, warmup, dist, dev, peaks):
@@ -308,6 +313,28 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
         finally:
             model.eval()
             model.load_state_dict(w['sd'])
+    # serving pattern: recommend_for_user = one user x the whole catalogue (+ top-10 + attention-threshold explanations), eager call
+    serving = None
+    sv = w.get('serving')
+    if sv is not None and sv.get('table') is not None:
+        try:
+            pos, rat = torch.from_numpy(sv['positions']).to(dev), torch.from_numpy(sv['ratings']).to(dev)
+            for _ in range(3):
+                model.recommend_for_user(sv['table'], pos, rat, k=10)
+            torch.cuda.synchronize()
+            n_req = 10
+            t0 = time.perf_counter()
+            for _ in range(n_req):
+                rec = model.recommend_for_user(sv['table'], pos, rat, k=10)
+                rec['scores'].cpu()
+            torch.cuda.synchronize()
+            req_ms = (time.perf_counter() - t0) * 1e3 / n_req
+            n_cand = sv['table'].shape[0] - len(sv['positions'])
+            serving = {'ms_per_request': req_ms, 'candidates': int(n_cand), 'rated_items': int(len(sv['positions'])), 'value': n_cand / (req_ms * 1e-3),
+                       'unit': 'pairs/s', 'what': 'AttentionNCF.recommend_for_user (src/webapp/backend.py:78-121): every unseen catalogue item scored for one '
+                                                  'user, top-10, explanations by attention threshold; wall clock per request incl. the D2H of the result'}
+        except Exception as e:
+            serving = {'error': repr(e)[:300]}
     (name, meta), (kms, per_step) = max(ops_ms.items(), key=lambda kv: kv[1][0] * kv[1][1])
     I_mean = float(np.mean([b[1].shape[0] for b in host]))
     if name in ('linear', 'linear_tc', 'linear_tc_batch'):
@@ -361,7 +388,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     if other:
         roof['other_kernels'] = other
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4, roofline=roof, I_mean=I_mean,
-                nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res, train=train,
+                nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res, train=train, serving=serving,
                 launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
@@ -380,6 +407,29 @@ def cpu_attention(w, sample_pairs=BATCH, repeats=3):
             ts.append(time.perf_counter() - t0)
     return sample_pairs / float(np.median(ts)), torch.get_num_threads(), \
         f'{sample_pairs} pairs of batch 0 (I={rated.shape[0]} rated items, F={F}), median of {repeats} forwards, oracle/restatement.py'
+
+
+def cpu_serving(w, repeats=2):
+    """the reference's per-user serving forward on host cores (backend.py:96-99: one forward over every unseen candidate)"""
+    from oracle import restatement as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    sv = w['serving']
+    pos = np.sort(sv['positions'])
+    order = np.argsort(sv['positions'])
+    ratings = sv['ratings'][order]
+    centred = (ratings - (ratings.mean() + 2.5) / 2).astype(np.float32)
+    keep = np.ones(sv['profiles'].shape[0], dtype=bool)
+    keep[pos] = False
+    cand = torch.from_numpy(sv['profiles'][keep])
+    rated = torch.from_numpy(sv['profiles'][pos])
+    um = torch.from_numpy(np.tile(centred, (cand.shape[0], 1)))
+    ts = []
+    with torch.no_grad():
+        for _ in range(repeats + 1):
+            t0 = time.perf_counter()
+            R.attention_ncf_forward(w['sd'], cand, rated, um)
+            ts.append(time.perf_counter() - t0)
+    return float(np.median(ts[1:])) * 1e3
 
 
 def cpu_attention_train(w, sample_pairs=64, repeats=3):
@@ -1042,6 +1092,8 @@ def main():
                                           'note': 'same batches through content_providers.ResidentDynamicProvider + AttentionNCF.forward_resident: '
                                                   'profile table resident in HBM, per step only row numbers + the CSR of user_matrix are copied '
                                                   '(pinned host -> device) and the scores read back; `e2e` above is the dense 6-tuple contract'}
+            if r.get('serving'):
+                result['serving'] = r['serving']
             if r.get('train'):
                 t = r['train']
                 result['train_step'] = ({'value': BATCH * world / (t['ms'] * 1e-3), 'unit': 'pairs/s', 'ms_per_step': t['ms'], 'steps': t['steps'],
@@ -1052,6 +1104,11 @@ def main():
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
                 v, cores, sample = cpu_attention(w)
                 result['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+                if r.get('serving') and 'ms_per_request' in r['serving']:
+                    try:
+                        result['serving']['cpu_ms_per_request'] = cpu_serving(w)
+                    except Exception as e:
+                        result['serving']['cpu_error'] = repr(e)[:200]
                 if r.get('train') and 'ms' in r['train']:
                     try:
                         tv, tsample = cpu_attention_train(w)
