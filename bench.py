@@ -294,7 +294,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     if not w.get('no_train'):
         try:
             model.train()
-            opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
             ys = [torch.rand(BATCH, 1, device=dev) * 4.5 + 0.5 for _ in range(nb)]
 
             def train_step(i):
@@ -560,7 +560,7 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
     if w.get('train_leg') and getattr(graph, '_b200rec_partition', None) is None:
         try:
             model.train()
-            opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
             ys = torch.rand(BATCH, 1, device=dev) * 4.5 + 0.5
 
             def train_step(i):
