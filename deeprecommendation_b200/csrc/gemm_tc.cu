@@ -346,8 +346,9 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     const bool split = p.kb_per_split > 0;
     const float* e_bias = split ? nullptr : p.bias;
     const int e_relu = split ? 0 : p.relu, e_bf16 = split ? 0 : p.y_bf16;
-    void* e_Y = split ? (void*)(p.partial + (size_t)blockIdx.z * (size_t)p.M * (size_t)p.N) : p.Y;
-    const long long e_ldy = split ? (long long)p.N : p.ldy;
+    const long long e_np = ((long long)p.N + 3) & ~3LL;          // slab rows are padded to 4 floats: the reduction reads 128-bit vectors for any N
+    void* e_Y = split ? (void*)(p.partial + (size_t)blockIdx.z * (size_t)p.M * (size_t)e_np) : p.Y;
+    const long long e_ldy = split ? e_np : p.ldy;
     const float rs = (!split && p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
@@ -496,21 +497,23 @@ static size_t packed_weight_bytes(long long N, long long K, int mode) {
   return (size_t)((N + 127) / 128) * (size_t)((K + KB - 1) / KB) * PL * TILE_BYTES;
 }
 
-// split-K: partial[z] (M x N) summed in split order (deterministic), then bias, row scale, activation
+// split-K: partial[z] (M x Np, Np = N rounded up to 4; the pad columns are never written nor used) summed in split order
+// (deterministic), then bias, row scale, activation
 __global__ void __launch_bounds__(256)
 tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, void* __restrict__ Y, long long ldy, int y_bf16,
                         const float* __restrict__ bias, const float* __restrict__ row_scale, int relu) {
-  const long long total4 = (long long)M * N / 4;               // N % 4 == 0 (launcher)
+  const int Np = (N + 3) & ~3;
+  const long long slab = (long long)M * Np;
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
+  if (i4 >= slab / 4) return;
   const long long idx = i4 * 4;
-  const int row = (int)(idx / N), col = (int)(idx % N);
+  const int row = (int)(idx / Np), col = (int)(idx % Np);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int z0 = 0; z0 < splits; z0 += 8) {
     float4 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      v[k] = (z0 + k < splits) ? __ldcs(reinterpret_cast<const float4*>(partial + (long long)(z0 + k) * M * N + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[k] = (z0 + k < splits) ? __ldcs(reinterpret_cast<const float4*>(partial + (long long)(z0 + k) * slab + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
   }
@@ -518,18 +521,20 @@ tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, in
   const float rs = row_scale ? __ldg(row_scale + row) : 1.f;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    if (bias) o[e] += __ldg(bias + col + e);
+    if (bias && col + e < N) o[e] += __ldg(bias + col + e);
     o[e] *= rs;
     if (relu) o[e] = fmaxf(o[e], 0.f);
   }
   if (y_bf16) {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Y) + (long long)row * ldy + col;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) dst[e] = __float2bfloat16_rn(o[e]);
+    for (int e = 0; e < 4; ++e)
+      if (col + e < N) dst[e] = __float2bfloat16_rn(o[e]);
   } else {
     float* dst = reinterpret_cast<float*>(Y) + (long long)row * ldy + col;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) dst[e] = o[e];
+    for (int e = 0; e < 4; ++e)
+      if (col + e < N) dst[e] = o[e];
   }
 }
 
@@ -539,7 +544,8 @@ static int tc_splits_tiles(long long tiles, bool n_ok, long long K, int mode, in
   const int num_kb = (int)((K + KB - 1) / KB);
   const int sms = b200rec_num_sms();
   *kb_per_split = 0;
-  if (tiles * 2 > sms || num_kb < 8 || !n_ok) return 0;
+  (void)n_ok;                                                  // (slab rows are padded: any N splits)
+  if (tiles * 2 > sms || num_kb < 8) return 0;
   int want = (int)(sms / tiles);
   if (want > num_kb / 3) want = num_kb / 3;                    // at least 3 k-blocks per CTA
   if (want < 2) return 0;
@@ -571,7 +577,7 @@ static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   if (p0.kb_per_split) {
     for (int q = 0; q < b.n; ++q) {                  // (a batch shares K and kb_per_split: b200rec_linear_tc_splitk_batch)
       const TcParams& pq = b.prob[q];
-      const long long total4 = (long long)pq.M * pq.N / 4;
+      const long long total4 = (long long)pq.M * (((long long)pq.N + 3) / 4);
       tc_splitk_reduce_kernel<<<ceil_div_i(total4, 256), 256, 0, st>>>(pq.partial, nsplit, pq.M, pq.N, pq.Y, pq.ldy, pq.y_bf16, pq.bias,
                                                                        pq.row_scale, pq.relu);
       B200REC_CHECK_LAUNCH();
@@ -668,7 +674,7 @@ extern "C" size_t b200rec_linear_tc_splitk_workspace(int64_t M, int64_t N, int64
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   int kbps = 0;
   const int splits = tc_splits(M, N, K, mode == B200REC_TC_BF16 ? TC_BF16 : TC_TF32X3, &kbps);
-  return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+  return splits > 1 ? (size_t)splits * (size_t)M * (size_t)((N + 3) & ~3LL) * sizeof(float) : 0;
 }
 
 extern "C" int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw,
@@ -683,7 +689,7 @@ extern "C" int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, in
   int kbps = 0;
   const int splits = tc_splits(M, N, K, mode == B200REC_TC_BF16 ? TC_BF16 : TC_TF32X3, &kbps);
   if (splits > 1) {
-    const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
+    const size_t need = (size_t)splits * (size_t)M * (size_t)((N + 3) & ~3LL) * sizeof(float);
     if (!workspace || workspace_bytes < need || ((uintptr_t)workspace % 16)) return b200rec_fail(B200REC_ERR_WORKSPACE, "linear_tc_splitk: workspace too small");
     b.prob[0].kb_per_split = kbps;
     b.prob[0].partial = (float*)workspace;
@@ -725,7 +731,7 @@ static int tc_batch_splits(const b200rec_linear_problem_t* problems, int n, int6
   for (int q = 0; q < n; ++q) {
     if (problems[q].M <= 0) continue;
     tiles += ((problems[q].M + 127) / 128) * ((problems[q].N + 127) / 128);
-    total += problems[q].M * problems[q].N;
+    total += problems[q].M * ((problems[q].N + 3) & ~3LL);
     n_ok = n_ok && (problems[q].N % 4) == 0;
   }
   *floats = (size_t)total;
@@ -762,7 +768,7 @@ extern "C" int b200rec_linear_tc_splitk_batch(const b200rec_linear_problem_t* pr
     if (splits > 1) {
       b.prob[b.n].kb_per_split = kbps;
       b.prob[b.n].partial = part;
-      part += (size_t)splits * (size_t)r.M * (size_t)r.N;        // 16-byte aligned: N % 4 == 0
+      part += (size_t)splits * (size_t)r.M * (size_t)((r.N + 3) & ~3LL);        // 16-byte aligned: padded rows
     }
     b.tile_start[b.n + 1] = b.tile_start[b.n] + ceil_div_i(r.M, TC_BM);
     ++b.n;

@@ -262,7 +262,7 @@ def linear_pair(xa, wa, ba, xb, wb, bb):
     engine = _gemm_engine
     Ma, Mb, K = xa.shape[0], xb.shape[0], xa.shape[1]
     ok = (engine != 'simt' and xb.shape[1] == K and K >= TC_MIN_K and TC_SPLITK_MIN_ROWS <= Ma < TC_MIN_ROWS and
-          TC_SPLITK_MIN_ROWS <= Mb < TC_MIN_ROWS and wa.shape[0] % 4 == 0 and wb.shape[0] % 4 == 0)
+          TC_SPLITK_MIN_ROWS <= Mb < TC_MIN_ROWS)
     if not ok:
         return linear_raw(xa, wa, ba), linear_raw(xb, wb, bb)
     _require_cuda(xa, wa, ba, xb, wb, bb)

@@ -34,7 +34,8 @@ def test_linear_tc_tf32x3_fp32_parity(M, K, N):
     assert torch.all(out[:, :4] == 3.0) and torch.all(out[:, 4 + N:] == 3.0)
 
 
-@pytest.mark.parametrize('M,K,N', [(512, 2094, 256), (512, 2094, 128), (128, 2094, 128), (1000, 2093, 132), (257, 1024, 64), (2000, 4096, 256)])
+@pytest.mark.parametrize('M,K,N', [(512, 2094, 256), (512, 2094, 128), (128, 2094, 128), (1000, 2093, 132), (257, 1024, 64), (2000, 4096, 256),
+                                   (256, 4731, 2094), (512, 2094, 130), (300, 1000, 17), (128, 640, 1)])
 def test_linear_tc_splitk_fp32_parity(M, K, N):
     """short-M, long-K shapes (a batch of pairs against the F-wide profiles) take the split-K tensor-core route of `linear_raw`:
     same tolerance, bit-reproducible (the slabs are added in split order), epilogue applied after the reduction"""
