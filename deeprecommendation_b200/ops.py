@@ -109,6 +109,7 @@ _gemm_engine = os.environ.get('B200REC_GEMM_ENGINE', 'tf32x3')   # fp32-parity t
 TC_MIN_ROWS = 2048
 TC_SPLITK_MIN_ROWS = 128      # below TC_MIN_ROWS the tensor-core GEMM runs split-K (if K is long enough to be dealt out)
 SHORTK_MIN_ROWS = 4096  # below this a handful of 64x64 FFMA tiles is as fast as the persistent kernel's set-up
+SPLITK_ANY_N = os.environ.get('B200REC_SPLITK_ANY_N', '1') == '1'   # split-K also when N % 4 != 0 (padded slabs)
 TC_MIN_K = 512          # short-K GEMMs (the d x d GraphNCF transforms) are epilogue/latency-bound: FFMA is as fast there
 
 
@@ -190,7 +191,8 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
             L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                           _dtype_code(out.dtype), mode, _ptr(packed), _ptr(row_index), x_rows, _stream()), 'linear_tc')
         return out
-    if engine != 'simt' and row_index is None and TC_SPLITK_MIN_ROWS <= M < TC_MIN_ROWS and K >= TC_MIN_K and M * ldx < 2 ** 32:
+    if (engine != 'simt' and row_index is None and TC_SPLITK_MIN_ROWS <= M < TC_MIN_ROWS and K >= TC_MIN_K and M * ldx < 2 ** 32
+            and (N % 4 == 0 or SPLITK_ANY_N)):
         # short-M, long-K (a batch of pairs against the F-wide profiles): split-K on the tensor cores
         mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
         ws_bytes = lib.b200rec_linear_tc_splitk_workspace(M, N, K, mode)
@@ -630,7 +632,7 @@ def propagate(t, index, w, w_bwd, dinv, skip_bits=None):
 # ------------------------------------------------------------------------------------------------------------------
 # K2 autograd wrapper
 # ------------------------------------------------------------------------------------------------------------------
-ATT_BWD_SLICES = int(os.environ.get('B200REC_ATT_BWD_SLICES', '1'))   # CTAs per candidate row in K2's backward (4 once measured)
+ATT_BWD_SLICES = int(os.environ.get('B200REC_ATT_BWD_SLICES', '4'))   # CTAs per candidate row in K2's backward: 0.170 ms (1) / 0.116 (4) / 0.114 (8) at config 2
 
 
 def _f32_rows(t):
