@@ -853,11 +853,12 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
         model.eval()
         model.load_state_dict(w['sd'])
     ops_ms = op_breakdown(step_eager, min(steps, nb), 0)
-    lin = [(k, v) for k, v in ops_ms.items() if k[0] in ('linear', 'linear_tc_splitk')]
+    lin = [(k, v) for k, v in ops_ms.items() if k[0] in ('linear', 'linear_tc_splitk', 'linear_tc_splitk_batch')]
     kms = float(np.mean([v[0] for _, v in lin])) if lin else 0.0
-    alg_bytes = 4.0 * (BATCH * F + 128 * F + BATCH * 128)
+    batched = any(k[0] == 'linear_tc_splitk_batch' for k, _ in lin)           # both projections of the batch in one launch
+    alg_bytes = 4.0 * (BATCH * F + 128 * F + BATCH * 128) * (2 if batched else 1)
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-    roof = {'bound': 'hbm', 'kernel': (f'gemm_tc_kernel + tc_splitk_reduce_kernel (K1a linear {BATCH}x{F}->128, tcgen05 split-K)' if any(k[0] == 'linear_tc_splitk' for k, _ in lin) else f'gemm_tn_kernel (K1a linear {BATCH}x{F}->128, fp32 FFMA, split-K)'), 'achieved': round(achieved, 1),
+    roof = {'bound': 'hbm', 'kernel': (f'gemm_tc_kernel + 2 x tc_splitk_reduce_kernel (K1a: user and item projections {BATCH}x{F}->128 in one split-K launch, tcgen05)' if batched else f'gemm_tc_kernel + tc_splitk_reduce_kernel (K1a linear {BATCH}x{F}->128, tcgen05 split-K)' if any(k[0] == 'linear_tc_splitk' for k, _ in lin) else f'gemm_tn_kernel (K1a linear {BATCH}x{F}->128, fp32 FFMA, split-K)'), 'achieved': round(achieved, 1),
             'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('basic'),
             'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}

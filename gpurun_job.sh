@@ -1,4 +1,6 @@
 set -x
-python tools/train_profile.py > gpurun_out/train_profile_v2.txt 2>&1; grep "ms/step" gpurun_out/train_profile_v2.txt
-B200REC_SPLITK_ANY_N=0 python tools/train_profile.py > gpurun_out/train_profile_v2_n4only.txt 2>&1; grep "ms/step" gpurun_out/train_profile_v2_n4only.txt
-python -m pytest tests/test_kernels_gpu.py tests/test_models_gpu.py -m gpu -x -q -k "backward or gradients" > gpurun_out/t44.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/t44.log
+python -m pytest tests -m gpu -x -q > gpurun_out/t45.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/t45.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke45.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke45.log
+( time python bench.py > gpurun_out/b45_full.json 2> gpurun_out/b45_full.err ) 2> gpurun_out/b45_time.txt; echo "bench rc=$?"; tail -3 gpurun_out/b45_full.err; cat gpurun_out/b45_time.txt
+( time python bench.py --impl reference > gpurun_out/b45_ref.json 2> gpurun_out/b45_ref.err ) 2> gpurun_out/b45_ref_time.txt; echo "ref rc=$?"; cat gpurun_out/b45_ref_time.txt
