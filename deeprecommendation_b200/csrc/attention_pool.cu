@@ -361,8 +361,7 @@ struct AttWork {
   int2* items;         // (row, segment)
   float* partials;     // (n_items, U + 4): m, l, -, -, acc[U]
   int max_items;       // capacity of items / partials (a max_row_nnz hint that is not a true bound must not overrun them)
-  int* row_done;       // (B) zeroed counters of finished segments, or null: the warp that finishes a row's LAST segment merges the row
-};                     // inside the pooling kernel (no separate merge launch); null = attention_merge_kernel does it
+};
 
 __device__ __forceinline__ void att_emit_items(const AttWork& w, int b, int len, int tid, int nthreads, int* s_base) {
   const int n = (len + ATT_WSEG - 1) / ATT_WSEG;
@@ -389,11 +388,6 @@ att_worklist_kernel(const int* __restrict__ row_ptr, int B, AttWork w) {
     if (base + j < w.max_items) w.items[base + j] = make_int2(b, j);
 }
 
-__device__ __forceinline__ void att_segment_done(const AttParams& p, int b, int lane, long long start, long long end,
-                                                 const int* __restrict__ col, const float* __restrict__ val, const AttWork& w);
-__device__ __forceinline__ void att_empty_rows(const AttParams& p, int lane, int gwarp, int n_warps, const int* __restrict__ row_ptr,
-                                               const int* __restrict__ row_nnz);
-
 template <int HV, int UV, int MODE, typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32, (HV == 1 && UV == 1) ? 2 : 1)
 attention_wseg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
@@ -401,7 +395,6 @@ attention_wseg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* _
   const int lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * ATT_WARPS;
   const int total = min(__ldg(w.counter), w.max_items);
-  if (w.row_done) att_empty_rows(p, lane, blockIdx.x * ATT_WARPS + (threadIdx.x >> 5), n_warps, row_ptr, row_nnz);
   for (int it = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5); it < total; it += n_warps) {
     const int2 item = __ldg(w.items + it);
     const int b = item.x, seg = item.y;
@@ -426,7 +419,6 @@ attention_wseg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* _
       const int u = lane * 4 + uv * 128;
       if (u < p.U) st4(slot + 4 + u, make_float4(core.acc[uv][0], core.acc[uv][1], core.acc[uv][2], core.acc[uv][3]));
     }
-    if (w.row_done) att_segment_done(p, b, lane, start, end, col, val, w);
   }
 }
 
@@ -455,7 +447,6 @@ attention_wseg_tma_kernel(AttParams p, const int* __restrict__ row_ptr, const in
   const T* __restrict__ Q = reinterpret_cast<const T*>(p.Q);
   const int n_warps = gridDim.x * warps;
   const int total = min(__ldg(w.counter), w.max_items);
-  if (w.row_done) att_empty_rows(p, lane, blockIdx.x * warps + warp, n_warps, row_ptr, row_nnz);
   for (int it = blockIdx.x * warps + warp; it < total; it += n_warps) {
     const int2 item = __ldg(w.items + it);
     const int b = item.x, seg = item.y;
@@ -496,7 +487,6 @@ attention_wseg_tma_kernel(AttParams p, const int* __restrict__ row_ptr, const in
     float* slot = w.partials + (long long)slot_idx * (p.U + 4);
     if (lane == 0) { slot[0] = core.m; slot[1] = core.l; }
     if (lane * 4 < p.U) st4(slot + 4 + lane * 4, make_float4(core.acc[0][0], core.acc[0][1], core.acc[0][2], core.acc[0][3]));
-    if (w.row_done) att_segment_done(p, b, lane, start, end, col, val, w);
   }
 }
 
@@ -504,21 +494,25 @@ attention_wseg_tma_kernel(AttParams p, const int* __restrict__ row_ptr, const in
 // and adds the partial vectors in segment order with independent 128-bit loads (v4 used a CTA per row whose threads walked the
 // segments with three dependent scalar loops: 35 us at 8192 rows, 10 % of the K2 call).
 constexpr int MERGE_WARPS = 8;
-// (partials and raw scores may have been written by other SMs of the SAME launch when the pooling kernel merges in place: every read
-//  of them goes to L2 — `__ldcg` — because a neighbouring row's merge on this SM may have left a stale L1 line of a shared 128-byte line)
-__device__ __forceinline__ void att_merge_row(const AttParams& p, int b, int lane, long long start, long long end,
-                                              const int* __restrict__ col, const float* __restrict__ val, const AttWork& w) {
+__global__ void __launch_bounds__(MERGE_WARPS * 32)
+attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
+                       const int* __restrict__ row_nnz, long long padded_stride, AttWork w) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5);
+  if (b >= p.B) return;
+  const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
+  const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
   const int first = __ldg(w.seg_base + b);
   const int nseg = max(0, min((int)((end - start + ATT_WSEG - 1) / ATT_WSEG), w.max_items - first));
   const long long stride = p.U + 4;
   const float* base = w.partials + (long long)first * stride;
   float M = -INFINITY;
-  for (int s0 = 0; s0 < nseg; s0 += 32) M = fmaxf(M, (s0 + lane < nseg) ? __ldcg(base + (long long)(s0 + lane) * stride) : -INFINITY);
+  for (int s0 = 0; s0 < nseg; s0 += 32) M = fmaxf(M, (s0 + lane < nseg) ? base[(long long)(s0 + lane) * stride] : -INFINITY);
   M = warp_max(M);
   float Lsum = 0.f;
   for (int s0 = 0; s0 < nseg; s0 += 32) {
     if (s0 + lane < nseg) {
-      const float2 ml = __ldcg(reinterpret_cast<const float2*>(base + (long long)(s0 + lane) * stride));
+      const float2 ml = *reinterpret_cast<const float2*>(base + (long long)(s0 + lane) * stride);
       Lsum += ml.y * ((ml.x == -INFINITY) ? 0.f : __expf(ml.x - M));
     }
   }
@@ -534,9 +528,9 @@ __device__ __forceinline__ void att_merge_row(const AttParams& p, int b, int lan
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         f[k] = 0.f;
         if (s0 + k < nseg) {
-          const float ms = __ldcg(base + (long long)(s0 + k) * stride);
+          const float ms = base[(long long)(s0 + k) * stride];
           f[k] = (ms == -INFINITY) ? 0.f : __expf(ms - M);
-          v[k] = __ldcg(reinterpret_cast<const float4*>(base + (long long)(s0 + k) * stride + 4 + u));
+          v[k] = *reinterpret_cast<const float4*>(base + (long long)(s0 + k) * stride + 4 + u);
         }
       }
 #pragma unroll
@@ -551,46 +545,9 @@ __device__ __forceinline__ void att_merge_row(const AttParams& p, int b, int lan
     for (long long k = start + lane; k < end; k += 32) {
       if (__ldg(val + k) != 0.f) {
         float* a = p.att + (long long)b * p.I + __ldg(col + k);
-        *a = normalise_score(__ldcg(a), M, Lsum);
+        *a = normalise_score(*a, M, Lsum);
       }
     }
-  }
-}
-
-__global__ void __launch_bounds__(MERGE_WARPS * 32)
-attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
-                       const int* __restrict__ row_nnz, long long padded_stride, AttWork w) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5);
-  if (b >= p.B) return;
-  const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
-  const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
-  att_merge_row(p, b, lane, start, end, col, val, w);
-}
-
-// In-kernel merge of the segment-parallel kernels (w.row_done != null).  Called by every warp after it has stored a segment's partial:
-// publish, count, and the warp that counted the row's last segment merges it.  The merge order is the segment order whoever does it.
-__device__ __forceinline__ void att_segment_done(const AttParams& p, int b, int lane, long long start, long long end,
-                                                 const int* __restrict__ col, const float* __restrict__ val, const AttWork& w) {
-  __threadfence();
-  __syncwarp();
-  int prev = 0;
-  if (lane == 0) prev = atomicAdd(w.row_done + b, 1);
-  prev = __shfl_sync(FULL, prev, 0);
-  const int first = __ldg(w.seg_base + b);
-  const int nseg = max(0, min((int)((end - start + ATT_WSEG - 1) / ATT_WSEG), w.max_items - first));
-  if (prev == nseg - 1) {
-    __threadfence();
-    att_merge_row(p, b, lane, start, end, col, val, w);
-  }
-}
-// rows without any segment never reach att_segment_done: user_emb = b_U (their attention weights stay 0)
-__device__ __forceinline__ void att_empty_rows(const AttParams& p, int lane, int gwarp, int n_warps, const int* __restrict__ row_ptr,
-                                               const int* __restrict__ row_nnz) {
-  for (int b = gwarp; b < p.B; b += n_warps) {
-    const int len = row_nnz ? __ldg(row_nnz + b) : __ldg(row_ptr + b + 1) - __ldg(row_ptr + b);
-    if (len > 0) continue;
-    for (int u = lane * 4; u < p.U; u += 128) st4(p.out + (long long)b * p.ldo + u, p.bU ? ld4(p.bU + u) : make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 
@@ -749,14 +706,13 @@ static long long att_max_items(long long B, long long I, long long max_row_nnz, 
   if (max_row_nnz > 0) return std::min(full, B * ((max_row_nnz + ATT_WSEG - 1) / ATT_WSEG));
   return full;
 }
-struct AttLayout { size_t counter, row_done, seg_base, items, partials, compact, total; };
-// workspace = counter | row_done (B, zeroed together with the counter) | seg_base (B) | items | partials | [dense: col, val, row_nnz lists]
+struct AttLayout { size_t counter, seg_base, items, partials, compact, total; };
+// workspace = counter | seg_base (B) | items | partials | [dense: col, val, row_nnz lists]
 static AttLayout att_layout(long long B, long long I, int U, bool dense, long long max_row_nnz, long long nnz) {
   const long long items = att_max_items(B, I, dense ? 0 : max_row_nnz, dense ? 0 : nnz);
   AttLayout l;
   l.counter = 0;
-  l.row_done = 256;
-  l.seg_base = l.row_done + align256((size_t)B * sizeof(int));
+  l.seg_base = 256;
   l.items = l.seg_base + align256((size_t)B * sizeof(int));
   l.partials = l.items + align256((size_t)items * sizeof(int2));
   l.compact = l.partials + align256((size_t)items * (size_t)(U + 4) * sizeof(float));
@@ -775,14 +731,12 @@ static int att_prepare(int B, int I, int U, const AttInputs& in, cudaStream_t st
   unsigned char* ws = reinterpret_cast<unsigned char*>(in.ws);
   w.counter = reinterpret_cast<int*>(ws + lay.counter);
   w.seg_base = reinterpret_cast<int*>(ws + lay.seg_base);
-  static const bool fused_merge = []() { const char* e = getenv("B200REC_ATT_FUSED_MERGE"); return e != nullptr && atoi(e) != 0; }();
-  w.row_done = fused_merge ? reinterpret_cast<int*>(ws + lay.row_done) : nullptr;
   w.items = reinterpret_cast<int2*>(ws + lay.items);
   w.partials = reinterpret_cast<float*>(ws + lay.partials);
   const long long max_items = att_max_items(B, I, dense ? 0 : in.max_row_nnz, dense ? 0 : in.nnz);
   if (max_items > 0x7fffffffLL) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: more than 2^31 segments");
   w.max_items = (int)max_items;
-  if (launch) B200REC_CUDA(cudaMemsetAsync(w.counter, 0, w.row_done ? lay.seg_base : sizeof(int), st));      // counter (+ the rows' segment counters)
+  if (launch) B200REC_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), st));
   lists.col = in.col; lists.val = in.val; lists.row_nnz = nullptr; lists.row_ptr = in.row_ptr; lists.stride = 0;
   if (dense) {                         // streaming compaction of the dense matrix into row-padded lists (+ the work list)
     int* wcol = reinterpret_cast<int*>(ws + lay.compact);
@@ -858,10 +812,8 @@ static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) 
     attention_wseg_kernel<HV, UV, MODE, T><<<grid, ATT_WARPS * 32, 0, st>>>(p, rp, ccol, cval, cnnz, stride, w);
     B200REC_CHECK_LAUNCH();
   }
-  if (w.row_done == nullptr) {         // (otherwise the pooling kernel merged every row as its last segment finished)
-    attention_merge_kernel<<<ceil_div_i(p.B, MERGE_WARPS), MERGE_WARPS * 32, 0, st>>>(p, rp, ccol, cval, cnnz, stride, w);
-    B200REC_CHECK_LAUNCH();
-  }
+  attention_merge_kernel<<<ceil_div_i(p.B, MERGE_WARPS), MERGE_WARPS * 32, 0, st>>>(p, rp, ccol, cval, cnnz, stride, w);
+  B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
 
