@@ -370,6 +370,13 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
                          'algorithmic_flops': int(flops), 'issued_tflops': round(ach * issue, 1),
                          'peak_source': peaks['src'] + ': bf16 burst %.0f TFLOP/s -> TF32 = half -> / 3 MMAs per product (fp32 parity)' % peaks['bf16_tflops']
                          if issue == 3.0 else peaks['src'], 'hbm_view': hbm_view})
+            tf = os.path.join(ROOT, 'profiles', 'tf32_peak.json')      # tools/tf32_peak.py: cuBLAS TF32 / bf16 rates measured on this pool's B200
+            if issue == 3.0 and os.path.exists(tf):
+                tfp = json.load(open(tf)).get('tf32_tflops')
+                if tfp:
+                    roof['vs_measured_tf32'] = {'peak': round(tfp / 3.0, 1), 'frac': round(ach / (tfp / 3.0), 4),
+                                                'what': f'cuBLAS TF32 {tfp} TFLOP/s sustained (profiles/tf32_peak.json) / 3 MMAs per product; `frac` above keeps the '
+                                                        'more conservative half-of-bf16-burst denominator'}
     # the second roofline kernel of this workload, whichever of K1a / K2 is not the dominant one (same formulas)
     other = []
     for (n2, m2), (k2, _) in ops_ms.items():
