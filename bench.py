@@ -601,6 +601,16 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes), 'features_fit_l2': bool(feat <= l2),
             'gather_inclusive_gbs': round((E2 * 8 + E2 * d * ts) / (kms * 1e-3) / 1e9, 1) if kms > 0 else 0.0,
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
+    tf = os.path.join(ROOT, 'profiles', 'tf32_peak.json')
+    if kms > 0 and os.path.exists(tf):
+        # roofline_time = max(bytes / HBM, flops / FP32 peak); at config 3 (features ~ L2) the FP32 side is the larger one
+        fp32 = json.load(open(tf)).get('fp32_simt_tflops')
+        if fp32:
+            flops = 2.0 * E2 * d
+            t_fp32 = flops / (fp32 * 1e12) * 1e3
+            roof['fp32_view'] = {'algorithmic_flops': int(flops), 'peak': fp32, 'unit': 'TFLOP/s', 'roofline_ms': round(t_fp32, 4),
+                                 'frac': round(t_fp32 / kms, 4), 'what': 'cuBLAS fp32 SIMT rate of this GPU (profiles/tf32_peak.json); the kernel itself '
+                                 'is bound by the L1 data path (ncu l1tex 81 %), see DESIGN.md'}
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof, train=train,
                 launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
