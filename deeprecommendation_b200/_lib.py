@@ -14,6 +14,7 @@ ATT_NET, ATT_DOT = 0, 1
 TC_TF32X3, TC_BF16 = 0, 1
 AP_BF16, AP_BF16X2 = 0, 1
 MLP_MAX_LAYERS = 8
+PEER_MAX, PEER_CHANNELS, PEER_HANDLE_BYTES = 16, 16, 64
 
 c_i64, c_int, c_sz, c_vp, c_f = C.c_int64, C.c_int, C.c_size_t, C.c_void_p, C.c_float
 
@@ -49,7 +50,8 @@ class SpmmDesc(C.Structure):
                 ('row_ptr', c_vp), ('col', c_vp), ('w', c_vp), ('perm', c_vp), ('skip_bits', c_vp), ('t', c_vp), ('t_dtype', c_int),
                 ('ld_t', c_i64), ('d', c_int), ('dinv', c_vp), ('partials', c_vp), ('x_next', c_vp), ('ld_x', c_i64),
                 ('acc_in', c_vp), ('acc_out', c_vp), ('ld_acc', c_i64), ('acc_scale', c_f), ('multi_row', c_vp),
-                ('multi_first_slot', c_vp), ('multi_n_slots', c_vp), ('n_multi', c_int), ('att_src', c_vp), ('partials_ml', c_vp)]
+                ('multi_first_slot', c_vp), ('multi_n_slots', c_vp), ('n_multi', c_int), ('att_src', c_vp), ('partials_ml', c_vp),
+                ('push_dst', c_vp * PEER_MAX), ('push_parts', c_int), ('push_rows_per_part', c_int), ('push_offset', c_i64), ('push_ld', c_i64)]
 
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/b200rec.h
@@ -64,6 +66,7 @@ SIGNATURES = {
     'b200rec_linear_tc_splitk': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     'b200rec_linear_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),
     'b200rec_linear_shortk': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp]),
+    'b200rec_linear_shortk_push': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, C.POINTER(c_vp), c_int, c_i64, c_i64, c_int, c_vp]),
     'b200rec_linear_tc_batch': (c_int, [C.POINTER(LinearProblem), c_int, c_i64, c_int, c_vp]),
     'b200rec_linear_tc_splitk_batch_workspace': (c_sz, [C.POINTER(LinearProblem), c_int, c_i64, c_int]),
     'b200rec_linear_tc_splitk_batch': (c_int, [C.POINTER(LinearProblem), c_int, c_i64, c_int, c_vp, c_sz, c_vp]),
@@ -102,6 +105,15 @@ SIGNATURES = {
     'b200rec_pairhash_build': (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     'b200rec_pairhash_lookup': (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     'b200rec_mask_targets': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'b200rec_peer_alloc': (c_int, [c_sz, C.POINTER(c_vp), C.c_char_p]),
+    'b200rec_peer_open': (c_int, [C.c_char_p, C.POINTER(c_vp)]),
+    'b200rec_peer_close': (c_int, [c_vp]),
+    'b200rec_peer_free': (c_int, [c_vp]),
+    'b200rec_peer_signal': (c_int, [C.POINTER(c_vp), c_int, c_int, c_int, c_vp, c_vp]),
+    'b200rec_peer_wait': (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
+    'b200rec_peer_reduce': (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_f, c_vp]),
+    'b200rec_peer_push_rows': (c_int, [c_vp, c_i64, c_i64, c_int, C.POINTER(c_vp), c_int, c_i64, c_i64, c_vp]),
+    'b200rec_peer_gather_rows': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_int, c_f, C.POINTER(c_vp), c_int, c_i64, c_i64, c_vp]),
 }
 
 _lib = None

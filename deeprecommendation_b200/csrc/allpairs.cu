@@ -548,11 +548,8 @@ static size_t ap_packed_bytes(int H1, int mode) {
 template <int MODE, int UQ, int NKB>
 static int ap_launch(const AllPairsParams& p, dim3 grid, cudaStream_t st) {
   const size_t smem = ApLayout<MODE, UQ>::total(NKB);
-  static bool configured = false;
-  if (!configured) {
-    B200REC_CUDA(cudaFuncSetAttribute(allpairs_topk_kernel<MODE, UQ, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static B200recSmemOptIn opted;
+  B200REC_CUDA(b200rec_opt_in_smem(opted, allpairs_topk_kernel<MODE, UQ, NKB>, (int)smem));
   allpairs_topk_kernel<MODE, UQ, NKB><<<grid, AP_THREADS, smem, st>>>(p);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;

@@ -746,11 +746,8 @@ static int att_prepare(int B, int I, int U, const AttInputs& in, cudaStream_t st
       const size_t row_bytes = (size_t)I * sizeof(float);
       static const bool streaming = []() { const char* e = getenv("B200REC_ATT_COMPACT_STREAMING"); return e != nullptr && atoi(e) != 0; }();
       if (row_bytes <= 96 * 1024 && !in.prepare_light && !streaming) {
-        static bool attr_set = false;
-        if (!attr_set) {
-          B200REC_CUDA(cudaFuncSetAttribute(um_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-          attr_set = true;
-        }
+        static B200recSmemOptIn opted;
+        B200REC_CUDA(b200rec_opt_in_smem(opted, um_compact_kernel<true>, 96 * 1024));
         um_compact_kernel<true><<<B, ATT_WARPS * 32, row_bytes, st>>>(in.um, in.ld_um, I, wcol, wval, wnnz, w);
       } else {
         um_compact_kernel<false><<<B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, I, wcol, wval, wnnz, w);
@@ -796,11 +793,8 @@ static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) 
     if (tma_ok) {
       const int warps = sizeof(T) == 4 ? 6 : 12;
       const size_t smem = (size_t)warps * 64 * 128 * sizeof(T) + (size_t)warps * sizeof(uint64_t);
-      static bool attr_set = false;       // per template instantiation
-      if (!attr_set) {
-        B200REC_CUDA(cudaFuncSetAttribute(attention_wseg_tma_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-      }
+      static B200recSmemOptIn opted;       // per template instantiation, one bit per device
+      B200REC_CUDA(b200rec_opt_in_smem(opted, attention_wseg_tma_kernel<MODE, T>, (int)smem));
       const int grid = (int)std::max(1LL, std::min((max_items + warps - 1) / warps, (long long)b200rec_num_sms()));
       attention_wseg_tma_kernel<MODE, T><<<grid, warps * 32, smem, st>>>(p, rp, ccol, cval, cnnz, stride, w);
       B200REC_CHECK_LAUNCH();

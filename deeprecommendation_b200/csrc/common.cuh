@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/b200rec.h"
 
 // placed after EVERY kernel launch: checks the launch and counts it (b200rec_launch_count, bench.py's gpu_launches)
@@ -25,6 +27,23 @@ int b200rec_fail(int code, const char* msg);        // api.cu: records msg, retu
 void b200rec_count_launch();                        // api.cu
 
 static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that launches on a second GPU must opt that
+// device in too.  One bit per device ordinal, set once the attribute call succeeded there (thread-safe).
+struct B200recSmemOptIn {
+  std::atomic<unsigned long long> done{0ull};
+};
+template <typename K>
+static inline cudaError_t b200rec_opt_in_smem(B200recSmemOptIn& s, K kernel, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (s.done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) s.done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 // number of SMs of the current device (cached)
 int b200rec_num_sms();

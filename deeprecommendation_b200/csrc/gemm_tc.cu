@@ -562,11 +562,8 @@ static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   constexpr int NSTAGE = (MODE == TC_BF16) ? 4 : 3;
   constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
   const size_t smem = (size_t)NSTAGE * 2 * PLANES * TILE_BYTES + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200REC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static B200recSmemOptIn opted;                     // per template instantiation, one bit per device
+  B200REC_CUDA(b200rec_opt_in_smem(opted, gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK>, (int)smem));
   int nmax = 0;
   for (int q = 0; q < b.n; ++q) nmax = b.prob[q].N > nmax ? b.prob[q].N : nmax;
   const TcParams& p0 = b.prob[0];

@@ -75,12 +75,15 @@ struct NodeGemmParams {
   const unsigned char* Wp;             // b200rec_pack_weights_tc(TF32X3) of W (N, K): [k-block][hi | lo] tiles of 16 KB
   const float* bias; const float* row_scale; int relu;
   void* Y; long long ldy; int y_bf16;   // Y: fp32, or bf16 (GraphNCF's bf16 message mode: K3 gathers half the bytes)
+  // all-gather fused into the epilogue (partitioned propagation): every tile is also stored to Yx[q], q < n_extra — the same
+  // place of the peer ranks' feature tables, mapped over NVLink (csrc/peer.cu)
+  void* Yx[B200REC_PEER_MAX]; int n_extra;
   int dbg;                             // experiments (B200REC_NT_DBG): 1 = no stores, 2 = no MMA, 4 = no TMEM loads
 };
 
 template <int NKB>
 __global__ void __launch_bounds__(NT_THREADS, 1)
-node_gemm_kernel(NodeGemmParams p) {
+node_gemm_kernel(const __grid_constant__ NodeGemmParams p) {
   extern __shared__ unsigned char nt_smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>(((uintptr_t)nt_smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sm_w = sm;                                   // NKB * 32 KB
@@ -224,22 +227,25 @@ node_gemm_kernel(NodeGemmParams p) {
             const int grow = tile * 128 + e * 32 + r, n = cg * 32 + cc;
             if (grow < p.M && n < p.N) {
               const float4 v = *reinterpret_cast<const float4*>(stg + r * NT_STG_LD + cc);
-              if (p.y_bf16) {                                      // 4 rows x 64 bytes per warp instruction
-                __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.Y) + (long long)grow * p.ldy + n;
-                if (n + 3 < p.N && (((uintptr_t)d & 7) == 0)) {
-                  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                  *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
-                } else {
-                  const float o[4] = {v.x, v.y, v.z, v.w};
-                  for (int q = 0; q < 4 && n + q < p.N; ++q) d[q] = __float2bfloat16_rn(o[q]);
+              for (int dq = 0; dq <= p.n_extra; ++dq) {             // dq > 0: the peers' copies of the table (NVLink stores)
+                void* const Yq = dq == 0 ? p.Y : p.Yx[dq - 1];
+                if (p.y_bf16) {                                      // 4 rows x 64 bytes per warp instruction
+                  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Yq) + (long long)grow * p.ldy + n;
+                  if (n + 3 < p.N && (((uintptr_t)d & 7) == 0)) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                    *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+                  } else {
+                    const float o[4] = {v.x, v.y, v.z, v.w};
+                    for (int q = 0; q < 4 && n + q < p.N; ++q) d[q] = __float2bfloat16_rn(o[q]);
+                  }
+                  continue;
                 }
-                continue;
-              }
-              float* d = reinterpret_cast<float*>(p.Y) + (long long)grow * p.ldy + n;
-              if (n + 3 < p.N && (((uintptr_t)d & 15) == 0)) *reinterpret_cast<float4*>(d) = v;
-              else {
-                const float o[4] = {v.x, v.y, v.z, v.w};
-                for (int q = 0; q < 4 && n + q < p.N; ++q) d[q] = o[q];
+                float* d = reinterpret_cast<float*>(Yq) + (long long)grow * p.ldy + n;
+                if (n + 3 < p.N && (((uintptr_t)d & 15) == 0)) *reinterpret_cast<float4*>(d) = v;
+                else {
+                  const float o[4] = {v.x, v.y, v.z, v.w};
+                  for (int q = 0; q < 4 && n + q < p.N; ++q) d[q] = o[q];
+                }
               }
             }
           }
@@ -293,11 +299,8 @@ node_gemm_kernel(NodeGemmParams p) {
 template <int NKB>
 static int nt_launch(const NodeGemmParams& p, cudaStream_t st) {
   const size_t smem = (size_t)NKB * NT_STAGE + NT_NS * NT_STAGE + 512 + 4 * 32 * NT_STG_LD * 4 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200REC_CUDA(cudaFuncSetAttribute(node_gemm_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static B200recSmemOptIn opted;
+  B200REC_CUDA(b200rec_opt_in_smem(opted, node_gemm_kernel<NKB>, (int)smem));
   const int n_tiles = (p.M + 127) / 128;
   const int sms = b200rec_num_sms();
   // persistent grid: every CTA gets the same number of tiles where possible (waves of `sms`)
@@ -312,8 +315,9 @@ static int nt_launch(const NodeGemmParams& p, cudaStream_t st) {
 
 using namespace b200rec;
 
-extern "C" int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
-                                     const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, b200rec_stream_t stream) {
+static int shortk_run(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
+                      const float* row_scale, int relu, void* Y, void* const* extra, int n_extra, int64_t ldy, int y_dtype,
+                      b200rec_stream_t stream) {
   if (M < 0 || !packed_w || !Y || (M > 0 && !X)) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_shortk: null operand");
   if (K <= 0 || K > 128 || (K % 32) || N <= 0 || N > 128) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_shortk: needs K in {32,64,96,128}, N <= 128");
   if (ldx < K || ldy < N || (ldx % 4) || ((uintptr_t)X % 16) || ((uintptr_t)packed_w % 128))
@@ -324,6 +328,8 @@ extern "C" int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64
   NodeGemmParams p;
   p.X = X; p.ldx = ldx; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.Wp = (const unsigned char*)packed_w;
   p.bias = bias; p.row_scale = row_scale; p.relu = relu; p.Y = Y; p.ldy = ldy; p.y_bf16 = y_dtype == B200REC_BF16;
+  p.n_extra = n_extra;
+  for (int q = 0; q < B200REC_PEER_MAX; ++q) p.Yx[q] = q < n_extra ? extra[q] : nullptr;
   {
     const char* e = getenv("B200REC_NT_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -335,4 +341,22 @@ extern "C" int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64
     case 3: return nt_launch<3>(p, st);
     default: return nt_launch<4>(p, st);
   }
+}
+
+extern "C" int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
+                                     const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, b200rec_stream_t stream) {
+  return shortk_run(X, M, K, ldx, packed_w, N, bias, row_scale, relu, Y, nullptr, 0, ldy, y_dtype, stream);
+}
+
+extern "C" int b200rec_linear_shortk_push(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
+                                          const float* row_scale, int relu, void* const* dst, int n_dst, int64_t y_offset, int64_t ldy,
+                                          int y_dtype, b200rec_stream_t stream) {
+  if (!dst || n_dst <= 0 || n_dst > B200REC_PEER_MAX) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_shortk_push: 1..B200REC_PEER_MAX destinations");
+  const int64_t esz = y_dtype == B200REC_BF16 ? 2 : 4;
+  void* d[B200REC_PEER_MAX];
+  for (int q = 0; q < n_dst; ++q) {
+    if (!dst[q]) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_shortk_push: null destination");
+    d[q] = static_cast<unsigned char*>(dst[q]) + y_offset * esz;
+  }
+  return shortk_run(X, M, K, ldx, packed_w, N, bias, row_scale, relu, d[0], d + 1, n_dst - 1, ldy, y_dtype, stream);
 }

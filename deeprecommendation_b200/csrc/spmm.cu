@@ -60,12 +60,24 @@ struct SpmmParams {
   // LightGAT (gnn_ncf.py:97-177): edge weight = w * softmax over the row of att_src[col]; no degree normalisation
   const float* att_src;      // per SOURCE node score A[:, :d]·x[s]; null = LightGCN
   float* partials_ml;        // (n_slots, 2): running max and denominator of multi-chunk rows
+  // partitioned propagation: finished rows go to the receive slot of their owner rank (peer-mapped arenas, csrc/peer.cu)
+  void* push_dst[B200REC_PEER_MAX];
+  int push_parts;
+  int push_rpp;              // rows per owner
+  long long push_off;        // element offset of this rank's slot inside an arena
+  long long push_ld;
 };
 
 // writes 4 consecutive columns [c, c+4) of one finished row
+template <bool PUSH = false>
 __device__ __forceinline__ void row_epilogue4(const SpmmParams& p, int row, int c, float s, float4 v) {
   if (c >= p.d) return;
   v = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+  if constexpr (PUSH) {                 // reduce-scatter fused into the epilogue: one 512-byte remote store per warp and row
+    const int o = row / p.push_rpp;
+    st4(reinterpret_cast<float*>(p.push_dst[o]) + p.push_off + (long long)(row - o * p.push_rpp) * p.push_ld + c, v);
+    return;
+  }
   if (p.x_next) st4(p.x_next + (long long)row * p.ld_x + c, v);
   if (p.acc_out) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -115,9 +127,9 @@ __device__ __forceinline__ uint4 ldg16_keep(const unsigned char* p, uint64_t pol
 // weight 0) and lanes beyond the row width read column 0, so every load is valid and the per-edge cost is
 // 2 SHFL + 1 IMAD.WIDE.U32 + 1 LDG.128 + 4 FFMA (the first version spent ~26 instructions per edge on predicated
 // 64-bit address arithmetic and zero-fill moves — profiles/r01).
-template <int G, int NV, typename T, bool GAT, bool KEEP, int UN = 8>
+template <int G, int NV, typename T, bool GAT, bool KEEP, int UN = 8, bool PUSH = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, (NV == 1 && UN == 8 && !GAT) ? SPMM_MIN_CTAS : 1)
-spmm_chunk_kernel(SpmmParams p) {
+spmm_chunk_kernel(const __grid_constant__ SpmmParams p) {
   constexpr int EPW = 32 / G;                       // edges per warp step
   constexpr int VPL = Lane16<T>::VPL;
   constexpr int STEPS = 32 / EPW;                   // warp steps per 32-edge block (= G)
@@ -236,7 +248,7 @@ spmm_chunk_kernel(SpmmParams p) {
       for (int h = 0; h < VPL / 4; ++h) {
         const int c4 = (sl + nv * G) * VPL + 4 * h;
         const float4 v = make_float4(acc[nv][4 * h], acc[nv][4 * h + 1], acc[nv][4 * h + 2], acc[nv][4 * h + 3]);
-        if (slot < 0) row_epilogue4(p, row, c4, sc, v);
+        if (slot < 0) row_epilogue4<PUSH>(p, row, c4, sc, v);
         else if (c4 < p.d) st4(p.partials + (long long)slot * p.d + c4, v);
       }
     }
@@ -286,9 +298,9 @@ __device__ __forceinline__ void fixup_accumulate(const SpmmParams& p, int first,
   }
 }
 
-template <int NV, bool GAT>
+template <int NV, bool GAT, bool PUSH = false>
 __global__ void __launch_bounds__(FIX_WARPS * 32)
-spmm_fixup_kernel(SpmmParams p) {
+spmm_fixup_kernel(const __grid_constant__ SpmmParams p) {
   __shared__ __align__(16) float s_acc[FIX_WARPS][NV * 128];
   __shared__ float s_red[FIX_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -307,7 +319,7 @@ spmm_fixup_kernel(SpmmParams p) {
       const float sc = GAT ? 1.f / (Lsum + 1e-16f) : (p.dinv ? __ldg(p.dinv + row) : 1.f);
 #pragma unroll
       for (int nv = 0; nv < NV; ++nv)
-        row_epilogue4(p, row, lane * 4 + nv * 128, sc, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
+        row_epilogue4<PUSH>(p, row, lane * 4 + nv * 128, sc, make_float4(acc[nv][0], acc[nv][1], acc[nv][2], acc[nv][3]));
     }
   }
   // ---- phase 2: the CTA's long rows, one after the other, all warps on each (CTA-uniform control flow) ----
@@ -352,7 +364,7 @@ spmm_fixup_kernel(SpmmParams p) {
       }
       const float sc = GAT ? 1.f / (L + 1e-16f) : (p.dinv ? __ldg(p.dinv + row) : 1.f);
 #pragma unroll
-      for (int nv = 0; nv < NV; ++nv) row_epilogue4(p, row, lane * 4 + nv * 128, sc, t[nv]);
+      for (int nv = 0; nv < NV; ++nv) row_epilogue4<PUSH>(p, row, lane * 4 + nv * 128, sc, t[nv]);
     }
     __syncthreads();
   }
@@ -363,7 +375,8 @@ static int launch_chunks(const SpmmParams& p, cudaStream_t st) {
   const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
   static const bool keep = []() { const char* e = getenv("B200REC_SPMM_L2_KEEP"); return e != nullptr && atoi(e) != 0; }();   // off by default: measured 3.21 vs 3.16 ms per config-3 step with the hint
   static const bool unroll16 = []() { const char* e = getenv("B200REC_SPMM_UNROLL"); return e != nullptr && atoi(e) == 16; }();
-  if (p.att_src) spmm_chunk_kernel<G, NV, T, true, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  if (p.push_parts > 0) spmm_chunk_kernel<G, NV, T, false, false, 8, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+  else if (p.att_src) spmm_chunk_kernel<G, NV, T, true, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   else if (keep) spmm_chunk_kernel<G, NV, T, false, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   else if (NV == 1 && G >= 16 && unroll16) spmm_chunk_kernel<G, NV, T, false, false, (NV == 1 && G >= 16) ? 16 : 8><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   else spmm_chunk_kernel<G, NV, T, false, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
@@ -386,7 +399,11 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   }
   if (p.n_multi > 0) {
     const int g2 = ceil_div_i(p.n_multi, FIX_WARPS);
-    if (p.att_src) {
+    if (p.push_parts > 0) {
+      if (p.d <= 128) spmm_fixup_kernel<1, false, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+      else if (p.d <= 256) spmm_fixup_kernel<2, false, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+      else spmm_fixup_kernel<4, false, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+    } else if (p.att_src) {
       if (p.d <= 128) spmm_fixup_kernel<1, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
       else if (p.d <= 256) spmm_fixup_kernel<2, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
       else spmm_fixup_kernel<4, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
@@ -429,6 +446,15 @@ extern "C" int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream) {
   p.multi_row = a->multi_row; p.multi_first_slot = a->multi_first_slot; p.multi_n_slots = a->multi_n_slots;
   p.n_multi = a->n_multi;
   p.att_src = a->att_src; p.partials_ml = a->partials_ml;
+  p.push_parts = a->push_parts; p.push_rpp = a->push_rows_per_part; p.push_off = a->push_offset; p.push_ld = a->push_ld;
+  for (int q = 0; q < B200REC_PEER_MAX; ++q) p.push_dst[q] = a->push_dst[q];
+  if (p.push_parts < 0 || p.push_parts > B200REC_PEER_MAX) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: push_parts out of range");
+  if (p.push_parts > 0) {
+    if (p.att_src || p.push_rpp <= 0 || (p.push_ld % 4) || (p.push_off % 4) || p.push_ld < p.d)
+      return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: bad push arguments (LightGCN only; offsets / leading dimension multiples of 4)");
+    for (int q = 0; q < p.push_parts; ++q)
+      if (!p.push_dst[q] || ((uintptr_t)p.push_dst[q] % 16)) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: null / misaligned push destination");
+  }
   if (p.att_src && p.n_multi > 0 && !p.partials_ml) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: LightGAT needs partials_ml for multi-chunk rows");
   cudaStream_t st = (cudaStream_t)stream;
   if (a->t_dtype == B200REC_F32) return launch_spmm<float>(p, st);

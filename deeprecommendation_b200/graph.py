@@ -33,8 +33,9 @@ class GraphData:
             if torch.is_tensor(v) and v.device != dev:
                 setattr(self, k, v.to(dev, *args, **kwargs))
                 moved = True
-        if moved and '_b200rec_index' in self.__dict__:
-            del self.__dict__['_b200rec_index']
+        if moved:                                   # derived structures live on the old device
+            for k in ('_b200rec_index', '_b200rec_partition'):
+                self.__dict__.pop(k, None)
         return self
 
     def __repr__(self):
@@ -196,6 +197,16 @@ class GraphIndex:
         else:
             self.w_bwd = None
         self._hash = None
+        self._attrs = (attr_u2i, attr_i2u) if has_w else None
+        self._transposed = None
+
+    def transposed(self) -> 'GraphIndex':
+        """Index of the REVERSED edges (CSR by source of this graph): what the backward of a propagation step over a
+        non-symmetric graph multiplies by.  Built on first use."""
+        if self._transposed is None:
+            a = self._attrs or (None, None)
+            self._transposed = GraphIndex(self.u2i.flip(0), self.i2u.flip(0), a[0], a[1], self.num_nodes, self.chunk_size)
+        return self._transposed
 
     def _build_plan(self):
         """SpMM chunk plan (chunk_row / chunk_start / chunk_slot + the multi-chunk row lists) for self.row_ptr."""
@@ -278,13 +289,18 @@ class GraphIndex:
 def get_index(graph) -> GraphIndex:
     """GraphIndex of a graph object (ours or the reference's PyG `Data`), built once and cached on it."""
     idx = getattr(graph, '_b200rec_index', None)
-    u2i = graph.user2item_edge_index
-    if idx is not None and idx.u2i.data_ptr() == u2i.data_ptr() and idx.u2i.device == u2i.device:
-        return idx
+    u2i, i2u = graph.user2item_edge_index, graph.item2user_edge_index
+    au, ai = getattr(graph, 'user2item_edge_attr', None), getattr(graph, 'item2user_edge_attr', None)
     n_nodes = int(graph.item_features.shape[0] + graph.user_features.shape[0])
-    idx = GraphIndex(u2i, graph.item2user_edge_index, getattr(graph, 'user2item_edge_attr', None),
-                     getattr(graph, 'item2user_edge_attr', None), n_nodes)
+    # identity of everything the index was derived from (addresses, in-place versions, sizes): replacing or editing an edge list or
+    # an attr tensor, or changing the node counts, rebuilds it
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) if torch.is_tensor(t) else None for t in (u2i, i2u, au, ai)) + (n_nodes,)
+    if idx is not None and getattr(idx, '_key', None) == key:
+        return idx
+    idx = GraphIndex(u2i, i2u, au, ai, n_nodes)
+    idx._key = key
     try:
+        object.__setattr__(graph, '_b200rec_partition', None)
         object.__setattr__(graph, '_b200rec_index', idx)
     except Exception:
         pass

@@ -562,8 +562,10 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
 # ------------------------------------------------------------------------------------------------------------------
 # K3 SpMM
 # ------------------------------------------------------------------------------------------------------------------
-def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, skip_bits=None, att_src=None):
-    """One propagation step over a `GraphIndex` (graph.py): b200rec_spmm.  Returns nothing; writes x_next / acc_out."""
+def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, skip_bits=None, att_src=None, push=None):
+    """One propagation step over a `GraphIndex` (graph.py): b200rec_spmm.  Returns nothing; writes x_next / acc_out.
+    `push` = (host array of arena addresses, parts, rows per part, element offset, leading dimension): finished rows go to the
+    receive slot of their owner rank instead (peer.py: reduce-scatter fused into the epilogue)."""
     _require_cuda(t)
     if t.stride(1) != 1:
         t = t.contiguous()
@@ -593,6 +595,13 @@ def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, 
         d.multi_row, d.multi_first_slot, d.multi_n_slots = (index.multi_row.data_ptr(), index.multi_first_slot.data_ptr(),
                                                             index.multi_n_slots.data_ptr())
     d.n_multi = index.n_multi
+    if push is not None:
+        dst, parts, rpp, off, ld = push
+        if x_next is not None or acc_out is not None or att_src is not None:
+            raise ValueError('spmm: `push` replaces x_next / acc_out (LightGCN only)')
+        for q in range(parts):
+            d.push_dst[q] = dst[q]
+        d.push_parts, d.push_rows_per_part, d.push_offset, d.push_ld = parts, rpp, off, ld
     ml = None
     if att_src is not None:
         att_src = att_src.contiguous().float().view(-1)
@@ -617,11 +626,18 @@ class _PropagateFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         index = ctx.index
-        if ctx.has_w and ctx.w_bwd is None:
-            raise NotImplementedError('GraphNCF backward needs symmetric edge lists (binary=False)')
         gs = (g * ctx.dinv[:, None]).contiguous() if ctx.dinv is not None else g.contiguous()
         gt = torch.empty_like(gs)
-        spmm_raw(index, gs, w=ctx.w_bwd, dinv=None, x_next=gt, skip_bits=ctx.skip_bits)
+        if getattr(index, 'symmetric', False) and ctx.w_bwd is not None:
+            # both lists hold the same pairs position by position (binary=False): A^T has the sparsity of A, only the weights differ
+            spmm_raw(index, gs, w=ctx.w_bwd, dinv=None, x_next=gt, skip_bits=ctx.skip_bits)
+        else:
+            # binary graphs (graph_providers.py:33,42 filter the two lists by different thresholds) are NOT symmetric: gt = A^T·gs needs
+            # the index of the reversed edges
+            if ctx.skip_bits is not None:
+                raise NotImplementedError('edge masking on a non-symmetric graph (the reference has the same restriction, graph_providers.py:13)')
+            tr = index.transposed()
+            spmm_raw(tr, gs, w=tr.w, dinv=None, x_next=gt)
         return gt, None, None, None, None, None
 
 

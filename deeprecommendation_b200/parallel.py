@@ -186,10 +186,17 @@ class UserPartitionedGraph:
         return (local >= 0) & (local < self.users.rows), local
 
 
-def partition_graph(graph, group=None, scheme: str = 'reduce'):
-    if scheme not in ('reduce', 'gather'):
+def partition_graph(graph, group=None, scheme: str = 'peer', d_max: int = 128, batch_max: int = 8192):
+    """'peer' (default): users partitioned, the exchange written as this library's own kernels over peer-mapped memory (peer.py);
+    'reduce' / 'gather': the same partitions with NCCL collectives issued from Python (kept as the comparison baseline)."""
+    if scheme not in ('peer', 'reduce', 'gather'):
         raise ValueError(scheme)
-    pg = UserPartitionedGraph(graph, group) if scheme == 'reduce' else PartitionedGraph(graph, group)
+    get_index(graph)                                   # (resets a stale partition of an edited graph)
+    if scheme == 'peer':
+        from .peer import partition_graph_peer
+        pg = partition_graph_peer(graph, group, d_max=d_max, batch_max=batch_max)
+    else:
+        pg = UserPartitionedGraph(graph, group) if scheme == 'reduce' else PartitionedGraph(graph, group)
     try:
         object.__setattr__(graph, '_b200rec_partition', pg)
     except Exception:
@@ -334,6 +341,9 @@ def forward_partitioned(model, pg, userIds, itemIds):
     """GraphNCF.forward on a partitioned graph (dispatches on the scheme).  After the propagation only the 2B batch rows are exchanged: every rank
     drops the rows it owns into a zero (2B, d) buffer and one all-reduce (exactly one non-zero contributor per row, so
     the sum is exact) gives every rank the batch embeddings; the MLP on B pairs is then computed on every rank."""
+    from .peer import PeerShard, forward_peer
+    if isinstance(pg, PeerShard):
+        return forward_peer(model, pg, userIds, itemIds)
     if isinstance(pg, UserPartitionedGraph):
         return forward_user_partitioned(model, pg, userIds, itemIds)
     import torch.distributed as dist

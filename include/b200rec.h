@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200REC_VERSION 100
+#define B200REC_VERSION 200
 
 typedef void* b200rec_stream_t; /* cudaStream_t */
 
@@ -32,6 +32,9 @@ enum { B200REC_OK = 0, B200REC_ERR_CUDA = 1, B200REC_ERR_BAD_ARG = 2, B200REC_ER
 enum { B200REC_F32 = 0, B200REC_BF16 = 1 };
 enum { B200REC_ATT_NET = 0, B200REC_ATT_DOT = 1 };
 enum { B200REC_TC_TF32X3 = 0, B200REC_TC_BF16 = 1 };
+#define B200REC_PEER_MAX 16          /* GPUs of one NVSwitch box that one exchange can address */
+#define B200REC_PEER_CHANNELS 16     /* independent flag channels per arena */
+#define B200REC_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 const char* b200rec_last_error(void);
 int b200rec_version(void);
@@ -68,6 +71,14 @@ int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, int64_t ldx, 
  * bf16 mode, rounded once from the fp32 accumulator). */
 int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
                           const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, b200rec_stream_t stream);
+/* The same GEMM with the all-gather of the partitioned GraphNCF propagation fused into its epilogue: every output tile is stored
+ * into the SAME place (element offset `y_offset`, leading dimension ldy) of `n_dst` buffers — `dst` is a HOST array of device
+ * pointers, one per rank of the box (peer-mapped arenas, b200rec_peer_open; the local buffer is one of them) — so the transformed
+ * rows travel over NVLink tile by tile while the next tile is computed.  Replaces the per-layer feature exchange that a
+ * multi-GPU form of models/gnn_ncf.py:336-345 needs. */
+int b200rec_linear_shortk_push(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
+                               const float* row_scale, int relu, void* const* dst, int n_dst, int64_t y_offset, int64_t ldy, int y_dtype,
+                               b200rec_stream_t stream);
 /* Up to four such GEMMs sharing K and mode in ONE launch (candidate + rated-item projections, the two halves of
  * AttentionNet.0 — attention_ncf.py:150-151,176): problem q covers its own rows; fields as in b200rec_linear_tc. */
 typedef struct {
@@ -255,6 +266,14 @@ typedef struct {
   int n_multi;
   const float* att_src; /* LightGAT (gnn_ncf.py:97-177): per-source score; edge weight = w * softmax_row(att_src[col]); NULL = LightGCN */
   float* partials_ml;   /* (n_slots, 2) scratch for the softmax state of multi-chunk rows */
+  /* reduce-scatter fused into the epilogue (partitioned propagation): when push_parts > 0 a finished row r is not written to
+   * x_next / acc_out but into the receive slot of its OWNER rank o = r / push_rows_per_part, i.e. to
+   * (float*)push_dst[o] + push_offset + (r - o * push_rows_per_part) * push_ld — push_dst are the peer-mapped arenas */
+  void* push_dst[B200REC_PEER_MAX];
+  int push_parts;
+  int push_rows_per_part;
+  int64_t push_offset;
+  int64_t push_ld;
 } b200rec_spmm_t;
 int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream);
 
@@ -302,6 +321,33 @@ int b200rec_pairhash_lookup(const int64_t* src, const int64_t* dst, int64_t n, c
 /* training-time target-edge mask (gnn_ncf.py:314-320,369-378): sets skip bits and decrements both endpoints' in-degree */
 int b200rec_mask_targets(const int64_t* positions, int64_t n, int64_t n_edges, const int64_t* u2i, const int64_t* i2u,
                          uint32_t* skip_bits, int* deg, b200rec_stream_t stream);
+
+/* ---- peer-memory exchange of the partitioned GraphNCF propagation (csrc/peer.cu) --------------------------------------
+ * One process per GPU of an NVSwitch box.  Each rank allocates ONE arena, exports it as a CUDA IPC handle (64 opaque bytes,
+ * exchanged by the host code), and maps the arenas of its peers.  The data path then consists of this library's kernels
+ * only: K3 pushes partial rows to their owner (b200rec_spmm_t.push_*), b200rec_peer_reduce adds the receive slots in rank
+ * order, b200rec_linear_shortk_push broadcasts the transformed rows, b200rec_peer_signal / _wait order the ranks (epoch
+ * flags in the arenas; release/acquire at system scope; the wait gives up after timeout_ns and sets *err_flag instead of
+ * hanging the GPU).  Replaces what a multi-GPU form of models/gnn_ncf.py:336-345 would do with all-gather / all-reduce. */
+int b200rec_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle /* host, B200REC_PEER_HANDLE_BYTES */);
+int b200rec_peer_open(const unsigned char* handle /* host */, void** dev_ptr);
+int b200rec_peer_close(void* dev_ptr);
+int b200rec_peer_free(void* dev_ptr);
+/* peer_flags: HOST array of n_peers device pointers to every rank's flag block (uint32 [B200REC_PEER_CHANNELS][B200REC_PEER_MAX]);
+ * counters: LOCAL uint32 [2 * B200REC_PEER_CHANNELS] (signals sent | waits passed), zero-initialised once */
+int b200rec_peer_signal(void* const* peer_flags, int n_peers, int rank, int channel, uint32_t* counters, b200rec_stream_t stream);
+int b200rec_peer_wait(const uint32_t* flags, int n_peers, int channel, uint32_t* counters, int64_t timeout_ns, int* err_flag,
+                      b200rec_stream_t stream);
+/* x_next[r] = sum_{s < n_slots} recv[s * slot_stride + r * ld_recv ..] (slot order);  acc_out = (acc_in + x_next) * acc_scale */
+int b200rec_peer_reduce(const float* recv, int n_slots, int64_t slot_stride, int64_t ld_recv, int64_t rows, int d, float* x_next,
+                        int64_t ld_x, const float* acc_in, float* acc_out, int64_t ld_acc, float acc_scale, b200rec_stream_t stream);
+/* copies src (rows, d) to (float*)dst[q] + dst_offset for every q < n_dst (dst: HOST array of device pointers) */
+int b200rec_peer_push_rows(const float* src, int64_t ld_src, int64_t rows, int d, void* const* dst, int n_dst, int64_t dst_offset,
+                           int64_t ld_dst, b200rec_stream_t stream);
+/* batch rows (models/gnn_ncf.py:354-357 on a partitioned embedding): for every j < n_ids with row0 <= ids[j] < row0 + rows,
+ * row (dst_offset / ld_dst + j) of every destination receives table[ids[j] - row0] * scale */
+int b200rec_peer_gather_rows(const float* table, int64_t ld, int64_t row0, int64_t rows, const int64_t* ids, int64_t n_ids, int d,
+                             float scale, void* const* dst, int n_dst, int64_t dst_offset, int64_t ld_dst, b200rec_stream_t stream);
 
 #ifdef __cplusplus
 }
