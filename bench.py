@@ -175,7 +175,8 @@ def op_breakdown(step_fn, steps, start_index):
 # ----------------------------------------------------------------------------------------------------------------------
 # workload A — AttentionNCF, BASELINE configs[1]
 # ----------------------------------------------------------------------------------------------------------------------
-def build_attention(dev, rank, n_batches=8):
+def build_attention(dev, rank, n_batches=None):
+    n_batches = N_ROTATING if n_batches is None else n_batches
     from deeprecommendation_b200 import synth
     from deeprecommendation_b200.content_providers import ArrayDynamicProvider, ResidentDynamicProvider, ResidentRows
     from deeprecommendation_b200.neural_collaborative_filtering.models import AttentionNCF
@@ -238,24 +239,34 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
         resident = [tuple(t.to(dev) for t in b) for b in host]
 
     def step(i):
-        if graphs is None:
-            return step_eager(i)
-        return graphs[i % nb].replay()
+        # ONE timed step = all `nb` rotating batches (nb x 512 pairs, ~105 MB of inputs each: the working set of a step is far
+        # larger than L2, and K steps make a timed region of tens of milliseconds)
+        out = None
+        for k in range(nb):
+            out = step_eager(k) if graphs is None else graphs[k].replay()
+        return out
 
     ms, launches = timed_steps(step, steps, warmup, dist, dev)
     if graphs is not None:                                   # replays do not pass through the launch counter
         resident = [tuple(g.static_in) for g in graphs]
         l0 = ops.launch_count()
-        step_eager(0)
+        for k in range(nb):
+            step_eager(k)
         launches = (ops.launch_count() - l0) * steps
+    with torch.no_grad():
+        out0 = model(*resident[0]).float().cpu()             # batch 0 through the same call: compared with the oracle's output (`parity`)
 
     # end to end: pinned host buffers in, scores out, every step (H2D straight into the captured input buffers)
     def step_e2e(i):
-        if graphs is not None:
-            return graphs[i % nb](*host[i % nb]).cpu()
-        with torch.no_grad():
-            c, r, um = (t.to(dev, non_blocking=True) for t in host[i % nb])
-            return model(c, r, um).cpu()
+        res = None
+        for k in range(nb):
+            if graphs is not None:
+                res = graphs[k](*host[k]).cpu()
+            else:
+                with torch.no_grad():
+                    c, r, um = (t.to(dev, non_blocking=True) for t in host[k])
+                    res = model(c, r, um).cpu()
+        return res
 
     for i in range(min(warmup, 3)):
         step_e2e(i)
@@ -265,16 +276,19 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
         step_e2e(i)
     torch.cuda.synchronize()
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
-    h2d = int(np.mean([sum(t.numel() * 4 for t in b) for b in host]))
+    h2d = int(np.sum([sum(t.numel() * 4 for t in b) for b in host]))
 
     # the same batches through the device-resident provider: row numbers + CSR cross PCIe, the profile table stays in HBM
     rf = w.get('resident_form') or []
     e2e_res = None
     if rf:
         def step_res(i):
-            c, r, um = rf[i % nb]
-            with torch.no_grad():
-                return model.forward_resident(c, r, um).cpu()
+            res = None
+            for k in range(nb):
+                c, r, um = rf[k]
+                with torch.no_grad():
+                    res = model.forward_resident(c, r, um).cpu()
+            return res
         for i in range(min(warmup, 3)):
             step_res(i)
         _barrier(dist)
@@ -283,10 +297,9 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
             step_res(i)
         torch.cuda.synchronize()
         res_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
-        e2e_res = {'ms': res_ms, 'h2d': int(np.mean([c.pos.numel() * 8 + r.pos.numel() * 8 + um.nbytes() for c, r, um in rf]))}
+        e2e_res = {'ms': res_ms, 'h2d': int(np.sum([c.pos.numel() * 8 + r.pos.numel() * 8 + um.nbytes() for c, r, um in rf]))}
 
-    step = step_eager
-    ops_ms = op_breakdown(step, min(steps, nb), 0)
+    ops_ms = op_breakdown(step_eager, nb, 0)
 
     # training step of the same batches (NCF/train.py:99-105): forward in train mode (dropout 0.2, isclose target mask), sum-MSE loss,
     # backward (K2's own backward kernel, gradient GEMMs on K1a) and Adam; eager launches — the rated-item union differs per batch
@@ -354,29 +367,29 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
             'peak_source': peaks['src'],
             'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
+    roof['traffic_source'] = 'profiles/traffic.json (static: one `ncu --set full` capture of this kernel per round, not measured in this run)'
     if name in ('linear_tc', 'linear_tc_batch'):
-        # roofline_time = max(bytes / HBM_peak, flops / pipe_peak).  In fp32-parity mode every product is issued as three
-        # TF32 MMAs (hi·hi + hi·lo + lo·hi), so the pipe peak of THIS arithmetic is TF32_peak / 3; MEASURED_PEAKS.json has no TF32 figure,
-        # the dense TF32 rate is half the bf16 one (same tcgen05 pipe, 32-bit operands).  The larger of the two times names the bound.
+        # roofline_time = max(bytes / HBM_peak, flops / pipe_peak), frac = roofline_time / measured time, with the
+        # ALGORITHMIC flops 2·M·K·N.  fp32 parity runs on the TF32 pipe (dense rate = half the measured bf16 rate; MEASURED_PEAKS.json has
+        # no TF32 figure).  The 3 MMAs per product of the 3xTF32 split are emulation overhead, not useful work: they only show up in
+        # `issued_frac` (how busy the pipe is), never in `frac`.
         M, K, N = meta
         flops = 2.0 * M * K * N
-        issue = 3.0 if w.get('gemm', 'tf32x3') == 'tf32x3' else 1.0
-        pipe = (peaks['bf16_tflops'] / 2.0 if issue == 3.0 else peaks['bf16_tflops']) / issue
+        tf32 = w.get('gemm', 'tf32x3') == 'tf32x3'
+        issue = 3.0 if tf32 else 1.0
+        pipe = peaks['bf16_tflops'] / 2.0 if tf32 else peaks['bf16_tflops']
         t_hbm, t_pipe = alg_bytes / (peaks['hbm_gbs'] * 1e9), flops / (pipe * 1e12)
-        hbm_view = {'achieved': roof['achieved'], 'peak': roof['peak'], 'unit': 'GB/s', 'frac': roof['frac']}
+        t_roof = max(t_hbm, t_pipe)
+        ach_tf = flops / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+        roof.update({'frac': round(t_roof / (kms * 1e-3), 4) if kms > 0 else 0.0, 'roofline_us': round(t_roof * 1e6, 2),
+                     'hbm_view': {'achieved': roof['achieved'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'roofline_us': round(t_hbm * 1e6, 2)},
+                     'tensor_view': {'achieved': round(ach_tf, 1), 'peak': round(pipe, 1), 'unit': 'TFLOP/s', 'roofline_us': round(t_pipe * 1e6, 2),
+                                     'algorithmic_flops': int(flops),
+                                     'peak_source': peaks['src'] + (': bf16 burst %.0f TFLOP/s / 2 = dense TF32' % peaks['bf16_tflops'] if tf32 else ': bf16 burst')},
+                     'issued_tflops': round(ach_tf * issue, 1), 'issued_frac': round(ach_tf * issue / pipe, 4),
+                     'issued_note': '3 TF32 MMAs per product (hi*hi + hi*lo + lo*hi) for fp32 parity' if tf32 else 'one bf16 MMA per product'})
         if t_pipe > t_hbm:
-            ach = flops / (kms * 1e-3) / 1e12
-            roof.update({'bound': 'tensor', 'achieved': round(ach, 1), 'peak': round(pipe, 1), 'unit': 'TFLOP/s', 'frac': round(ach / pipe, 4),
-                         'algorithmic_flops': int(flops), 'issued_tflops': round(ach * issue, 1),
-                         'peak_source': peaks['src'] + ': bf16 burst %.0f TFLOP/s -> TF32 = half -> / 3 MMAs per product (fp32 parity)' % peaks['bf16_tflops']
-                         if issue == 3.0 else peaks['src'], 'hbm_view': hbm_view})
-            tf = os.path.join(ROOT, 'profiles', 'tf32_peak.json')      # tools/tf32_peak.py: cuBLAS TF32 / bf16 rates measured on this pool's B200
-            if issue == 3.0 and os.path.exists(tf):
-                tfp = json.load(open(tf)).get('tf32_tflops')
-                if tfp:
-                    roof['vs_measured_tf32'] = {'peak': round(tfp / 3.0, 1), 'frac': round(ach / (tfp / 3.0), 4),
-                                                'what': f'cuBLAS TF32 {tfp} TFLOP/s sustained (profiles/tf32_peak.json) / 3 MMAs per product; `frac` above keeps the '
-                                                        'more conservative half-of-bf16-burst denominator'}
+            roof.update({'bound': 'tensor', 'achieved': round(ach_tf, 1), 'peak': round(pipe, 1), 'unit': 'TFLOP/s'})
     # the second roofline kernel of this workload, whichever of K1a / K2 is not the dominant one (same formulas)
     other = []
     for (n2, m2), (k2, _) in ops_ms.items():
@@ -394,7 +407,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
                           'traffic': _traffic('attention')})
     if other:
         roof['other_kernels'] = other
-    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4, roofline=roof, I_mean=I_mean,
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4 * nb, roofline=roof, I_mean=I_mean, out0=out0, nb=nb,
                 nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res, train=train, serving=serving,
                 launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
@@ -406,14 +419,22 @@ def cpu_attention(w, sample_pairs=BATCH, repeats=3):
     cand, rated, um = (t.clone() for t in w['host'][0])
     cand, um = cand[:sample_pairs], um[:sample_pairs]
     with torch.no_grad():
-        R.attention_ncf_forward(w['sd'], cand, rated, um)
+        out = R.attention_ncf_forward(w['sd'], cand, rated, um)
         ts = []
         for _ in range(repeats):
             t0 = time.perf_counter()
             R.attention_ncf_forward(w['sd'], cand, rated, um)
             ts.append(time.perf_counter() - t0)
     return sample_pairs / float(np.median(ts)), torch.get_num_threads(), \
-        f'{sample_pairs} pairs of batch 0 (I={rated.shape[0]} rated items, F={F}), median of {repeats} forwards, oracle/restatement.py'
+        f'{sample_pairs} pairs of batch 0 (I={rated.shape[0]} rated items, F={F}), median of {repeats} forwards, oracle/restatement.py', out
+
+
+def _parity(gpu_out, cpu_out, what, tol=1e-5):
+    """max-norm relative error of the CUDA path against the oracle on the SAME benchmarked inputs (the bar of north_star)"""
+    a, b = gpu_out.detach().double().cpu().reshape(-1), cpu_out.detach().double().cpu().reshape(-1)
+    n = min(a.numel(), b.numel())
+    e = float((a[:n] - b[:n]).abs().max() / b[:n].abs().max())
+    return {'max_rel': e, 'tolerance': tol, 'ok': bool(e <= tol), 'n': int(n), 'vs': what}
 
 
 def cpu_serving(w, repeats=2):
@@ -502,9 +523,9 @@ def build_graph(dev, scale=1.0, world=1, scheme='reduce'):
     model = GraphNCF(**kw).to(dev).eval()
     model.load_state_dict(sd)
     pick = torch.randint(0, E, (64, BATCH), device=dev, generator=g)
-    if world > 1:                       # 1-D nnz-balanced row partition + per-layer all-gather (parallel.py)
+    if world > 1:                       # users 1-D nnz-partitioned; exchange = own kernels over peer memory (peer.py) or NCCL (parallel.py)
         from deeprecommendation_b200.parallel import partition_graph
-        partition_graph(graph, scheme=scheme)
+        partition_graph(graph, scheme=scheme, d_max=d, batch_max=BATCH)
     return dict(model=model, sd=sd, graph=graph, index=index, E=E, nU=nU, nI=nI, d=d, L=L_, pick=pick, build_s=build_s, kw=kw,
                 edges=(users, items, ratings))
 
@@ -559,6 +580,9 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
 
     ops_ms = op_breakdown(step_eager, min(steps, 4), 0)
+    if hasattr(getattr(graph, '_b200rec_partition', None), 'check'):
+        torch.cuda.synchronize()
+        graph._b200rec_partition.check()                     # a peer wait that timed out would have produced garbage: fail loudly
 
     # training step on the same graph (NCF/train.py:99-105 through gnn_ncf.py:298-367): target edges of the batch masked out of the
     # propagation (pair hash + skip bitmap), conv / MLP dropout, sum-MSE backward (K3 on the reverse-edge weights, gradient GEMMs on
@@ -624,7 +648,6 @@ def cpu_graph(w, sample_frac=0.04, repeats=2):
     users, items, ratings = users[:n], items[:n], ratings[:n]
     g = R.create_graph(users, items, ratings, np.arange(w['nU']), np.arange(w['nI']))
     gd = {k: (torch.from_numpy(v) if v is not None else None) for k, v in g.items()}
-    x0 = torch.cat((w['graph'].item_features.cpu(), w['graph'].user_features.cpu()))
     uid = torch.from_numpy(g['user2item_edge_index'][0][:BATCH])
     iid = torch.from_numpy(g['user2item_edge_index'][1][:BATCH])
     gd['item_features'], gd['user_features'] = w['graph'].item_features.cpu(), w['graph'].user_features.cpu()
@@ -632,10 +655,24 @@ def cpu_graph(w, sample_frac=0.04, repeats=2):
     with torch.no_grad():
         for _ in range(repeats + 1):
             t0 = time.perf_counter()
-            R.graph_ncf_forward(w['sd'], gd, uid, iid, w['L'])
+            out = R.graph_ncf_forward(w['sd'], gd, uid, iid, w['L'])
             ts.append(time.perf_counter() - t0)
+    # the CUDA path on the SAME sampled graph (K4 build + K1c + K3 + K1b), for the `parity` figure of the line
+    gpu_out = None
+    try:
+        from deeprecommendation_b200.graph import IdTable, create_graph
+        dev = w['graph'].item_features.device
+        eu, ei, er = (t[:n] for t in w['edges'])
+        g2 = create_graph(eu, ei, er, w['graph'].item_features, w['graph'].user_features, IdTable(torch.arange(w['nU'], device=dev)),
+                          IdTable(torch.arange(w['nI'], device=dev)))
+        with torch.no_grad():
+            gpu_out = w['model'](g2, uid.to(dev), iid.to(dev), dev).float().cpu()
+        del g2
+    except Exception as e:
+        gpu_out = repr(e)[:300]
     return 2 * n * w['L'] / float(np.median(ts[1:])), torch.get_num_threads(), \
-        f'first {n} of {len(w["edges"][0])} interactions ({sample_frac:.0%} edge sample, same node set), median of {repeats} forwards, oracle/restatement.py'
+        f'first {n} of {len(w["edges"][0])} interactions ({sample_frac:.0%} edge sample, same node set), median of {repeats} forwards, oracle/restatement.py', \
+        out, gpu_out
 
 
 def run_k3_hbm_regime(dev, peaks, n_users=8_000_000, n_items=1_000_000, n_edges=100_000_000, d=64, reps=5):
@@ -678,6 +715,12 @@ def run_k3_hbm_regime(dev, peaks, n_users=8_000_000, n_items=1_000_000, n_edges=
     if probe and probe.get(f'gather_{d * 4}B_GBs'):
         roof['random_gather_ceiling'] = {'GB/s': probe[f'gather_{d * 4}B_GBs'], 'frac_of_it': round(achieved / probe[f'gather_{d * 4}B_GBs'], 4),
                                          'what': f'tools/gather_probe.cu: independent random {d * 4}-byte rows of a 4 GiB table, no arithmetic, same GPU, same run'}
+    roof['traffic_source'] = 'profiles/traffic.json (static: one `ncu --set full` capture of this kernel per round, not measured in this run)'
+    if roof.get('traffic'):
+        # `frac` follows SURVEY.md §8d's gather-inclusive formula (every gathered row counted as HBM bytes); the popular rows of the Zipf graph hit
+        # in L2, so the DRAM pins move fewer bytes: dram_frac = measured DRAM bytes per launch / kernel time / HBM peak is the honest HBM figure
+        roof['dram_gbs'] = round(roof['traffic'] / (ms * 1e-3) / 1e9, 1)
+        roof['dram_frac'] = round(roof['traffic'] / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'], 4)
     out = {'metric': 'K3 SpMM directed-edge messages/sec, HBM regime (features >> L2)', 'value': E2 / (ms * 1e-3), 'unit': 'edges/s',
            'ms_per_step': ms, 'dtype': 'f32',
            'config': {'workload': f'one layer of K3 on nU={n_users}, nI={n_items}, E={n_edges} (2E={E2} directed), d={d}: one GPU share of '
@@ -742,6 +785,7 @@ def run_k2_hbm_regime(dev, peaks, n_items=4_000_000, n_rows=8192, H=128, reps=5,
     probe = _gather_probe()
     roof = {'bound': 'hbm', 'kernel': 'att_worklist_kernel + attention_wseg_tma_kernel + attention_merge_kernel (K2, CSR front-end)', 'achieved': round(achieved, 1),
             'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('k2_hbm'),
+            'traffic_source': 'profiles/traffic.json (static: one `ncu --set full` capture of this kernel per round, not measured in this run)',
             'peak_source': peaks['src'], 'kernel_ms': round(ms, 4), 'algorithmic_bytes': int(alg)}
     if probe and probe.get(f'gather_{H * 4}B_GBs'):
         roof['random_gather_ceiling'] = {'GB/s': probe[f'gather_{H * 4}B_GBs'], 'frac_of_it': round(achieved / probe[f'gather_{H * 4}B_GBs'], 4),
@@ -797,23 +841,30 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
         except Exception as e:
             w['graph_capture_error'] = repr(e)[:300]
 
-    def step(i):
-        if graphed is None:
-            return step_eager(i)
-        return graphed(*resident[i % nb])
+    def step(i):                                 # ONE timed step = all `nb` rotating batches (nb x 512 pairs, 275 MB of inputs > L2)
+        out = None
+        for k in range(nb):
+            out = step_eager(k) if graphed is None else graphed(*resident[k])
+        return out
 
     ms, launches = timed_steps(step, steps, warmup, dist, dev)
     if graphed is not None:
         l0 = ops.launch_count()
         step_eager(0)
-        launches = (ops.launch_count() - l0) * steps
+        launches = (ops.launch_count() - l0) * steps * nb
+    with torch.no_grad():
+        out0 = model(*resident[0]).float().cpu()
 
     def step_e2e(i):
-        if graphed is not None:
-            return graphed(*host[i % nb]).cpu()
-        with torch.no_grad():
-            xu, xi = (t.to(dev, non_blocking=True) for t in host[i % nb])
-            return model(xu, xi).cpu()
+        res = None
+        for k in range(nb):
+            if graphed is not None:
+                res = graphed(*host[k]).cpu()
+            else:
+                with torch.no_grad():
+                    xu, xi = (t.to(dev, non_blocking=True) for t in host[k])
+                    res = model(xu, xi).cpu()
+        return res
 
     for i in range(min(warmup, 3)):
         step_e2e(i)
@@ -865,7 +916,8 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
             else:
                 one_step(opt)
 
-        train_ms, _ = timed_steps(train_step, steps, warmup, dist, dev)
+        train_ms, _ = timed_steps(train_step, steps * 4, warmup, dist, dev)
+        train_ms /= 4.0                                                   # (ms of `steps` single-batch train steps)
     finally:
         model.eval()
         model.load_state_dict(w['sd'])
@@ -879,7 +931,7 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
             'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('basic'),
             'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
-    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * F * 4, d2h=BATCH * 4, roofline=roof, train_ms=train_ms, train_mode=train_mode,
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * F * 4 * nb, d2h=BATCH * 4 * nb, roofline=roof, train_ms=train_ms, train_mode=train_mode, out0=out0, nb=nb,
                 launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
@@ -888,13 +940,13 @@ def cpu_basic(w, repeats=10):
     torch.set_num_threads(os.cpu_count() or 1)
     xu, xi = (t.clone() for t in w['host'][0])
     with torch.no_grad():
-        R.basic_ncf_forward(w['sd'], xu, xi)
+        out = R.basic_ncf_forward(w['sd'], xu, xi)
         ts = []
         for _ in range(repeats):
             t0 = time.perf_counter()
             R.basic_ncf_forward(w['sd'], xu, xi)
             ts.append(time.perf_counter() - t0)
-    return BATCH / float(np.median(ts)), torch.get_num_threads(), f'batch 0 ({BATCH} pairs, F={F}), median of {repeats} forwards, oracle/restatement.py'
+    return BATCH / float(np.median(ts)), torch.get_num_threads(), f'batch 0 ({BATCH} pairs, F={F}), median of {repeats} forwards, oracle/restatement.py', out
 
 
 def cpu_basic_train(w, repeats=10):
@@ -991,8 +1043,20 @@ def cpu_allpairs(w, n_users=16, n_items=2000):
         sc = R.basic_ncf_all_pairs(w['sd'], xu, xi)
         R.topk_stable(sc, AP_K)
         dt = time.perf_counter() - t0
+    # the CUDA path on the same sub-grid: scores of the fp32-tolerance mode and of the bf16 mode, top-k against a stable sort of its own scores
+    parity = {}
+    try:
+        dev = w['items'].device
+        for precision, tol in (('fp32', 1e-5), ('bf16', 1e-2)):
+            val, idx, scores = w['model'].recommend(xu.to(dev), w['items'][:n_items], k=AP_K, precision=precision, return_scores=True)
+            pr = _parity(scores, sc, f'oracle/restatement.py::basic_ncf_all_pairs on a {n_users} x {n_items} sub-grid of the benchmarked inputs', tol)
+            sv, si = R.topk_stable(scores.cpu(), AP_K)
+            pr['topk_equals_stable_sort_of_own_scores'] = bool(torch.equal(idx.cpu(), si))
+            parity[precision] = pr
+    except Exception as e:
+        parity = {'error': repr(e)[:300]}
     return n_users * n_items / dt, torch.get_num_threads(), \
-        f'{n_users} users x {n_items} items sub-grid of the same inputs (reference forward per pair + stable top-{AP_K}), oracle/restatement.py'
+        f'{n_users} users x {n_items} items sub-grid of the same inputs (reference forward per pair + stable top-{AP_K}), oracle/restatement.py', parity
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -1030,12 +1094,102 @@ def reference_arm(args):
     line = {'impl': 'reference', 'metric': 'scored user-item pairs/sec (NCF fwd)', 'value': value, 'unit': 'pairs/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': ATT_WORKLOAD, 'batch': BATCH, 'note': (f'each step = one whole batch of {BATCH} pairs' if sample >= BATCH else f'each step = the first {sample} pairs of a batch of {BATCH}') +
-                       ' (the reference materialises two (B*I,128) fp32 tensors, attention_ncf.py:154-155: ~12 GB of host memory per batch)'},
+            'config': attention_config(args.gpus, args.gemm),
+            'run_info': {'note': (f'each reference step = one whole batch of {BATCH} pairs' if sample >= BATCH else f'each reference step = the first {sample} pairs of a batch of {BATCH}') +
+                         f' (a bounded sample of the B200 arm\'s step of {N_ROTATING} batches; the reference materialises two (B*I,128) fp32 tensors, '
+                         'attention_ncf.py:154-155: ~12 GB of host memory per batch)'},
             'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                              'sample': f'{sample} pairs per step x {args.steps} steps, oracle/restatement.py::attention_ncf_forward'},
             'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
+
+
+N_ROTATING = 8
+
+
+def attention_config(world, gemm):
+    """`config` of the headline line — the SAME dict in the B200 arm and in the reference arm (run-specific figures live in `run_info`)"""
+    return {'workload': ATT_WORKLOAD, 'batch': BATCH, 'batches_per_step': N_ROTATING,
+            'parallelism': f'dp{world} (pairs sharded, no collective)',
+            'l2': f'one step = {N_ROTATING} rotating batches (~105 MB of inputs each, resident in HBM): working set of a step >> 126 MB L2',
+            'gemm_engine': gemm}
+
+
+PARALLELISM = {
+    'peer': 'users 1-D nnz-partitioned over {P} GPUs, item rows in {P} equal ranges; no library collective on the data path: K3 pushes partial item rows '
+            'into the owner\'s receive slot over NVLink (reduce-scatter fused into the SpMM epilogue), slots summed in rank order, K1c writes the '
+            'transformed item rows into every rank\'s table (all-gather fused into the GEMM epilogue), epoch flags in peer memory order the '
+            'ranks, batch rows pushed by their owners (deeprecommendation_b200/peer.py, csrc/peer.cu)',
+    'reduce': 'users 1-D nnz-partitioned over {P} GPUs, items replicated; one NCCL all-reduce of the (nI, d) item partials per non-final layer, hidden '
+              'behind the user-row SpMM; batch rows by all-reduce',
+    'gather': 'item and user rows each 1-D nnz-partitioned over {P} GPUs; two NCCL all-gathers per layer, the larger one hidden behind the first '
+              'SpMM; batch rows by all-reduce'}
+
+
+def graph_leg(args, dev, rank, world, dist, peaks):
+    """GraphNCF propagation, BASELINE configs[2] (strong scaling).  Returns (entry, compact scaling summary)."""
+    w = build_graph(dev, args.graph_scale, world, args.graph_scheme)
+    w['eager'] = args.eager
+    w['train_leg'] = world == 1 and not args.no_train_step
+    r = run_graph(w, args.steps, args.warmup, dist, dev, peaks)
+    msgs = 2.0 * w['E'] * w['L'] * args.steps          # the graph is fixed: strong scaling
+    entry = {'metric': 'GNN propagation directed-edge messages/sec (GraphNCF fwd)', 'value': msgs / (r['ms'] * 1e-3),
+             'unit': 'edges/s', 'ms_per_step': r['ms'] / args.steps, 'n_gpus': world,
+             'scaling': 'strong', 'parallelism': PARALLELISM[args.graph_scheme].format(P=world) if world > 1 else 'single GPU',
+             'dtype': 'f32',
+             'config': {'workload': f'configs[2]: GraphNCF L=2 d=128 hetero, synthetic MovieLens-25M shape (nU={w["nU"]}, nI={w["nI"]}, '
+                        f'E={w["E"]}), pre-embedded (N,128) node features, whole-graph propagation + MLP on a batch of 512 per step',
+                        'l2': 'CSR (400 MB) + features (115 MB) > L2', 'index_build_s': round(w['build_s'], 3),
+                        'launch_mode': r['launch_mode'], 'scheme': args.graph_scheme if world > 1 else 'single'},
+             'roofline': r['roofline'],
+             'e2e': {'value': msgs / (r['e2e_ms'] * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
+             'gpu_launches': r['launches']}
+    if r.get('train'):
+        t = r['train']
+        entry['train_step'] = ({'value': 2.0 * w['E'] * w['L'] / (t['ms'] * 1e-3), 'unit': 'edges/s', 'ms_per_step': t['ms'], 'steps': t['steps'],
+                                'launch_mode': 'eager',
+                                'what': 'whole-graph forward in train mode with the 512 target edges masked out (pair hash + skip bitmap), conv and '
+                                        'MLP dropout, sum-MSE backward (K3 on the reverse-edge weights, gradient GEMMs on K1a) and Adam; value counts '
+                                        'the forward messages only (2E*L per step), like the inference line'} if 'ms' in t else t)
+    w['train_leg'] = False
+    bf16_ms = None
+    if world == 1 or args.graph_scheme == 'peer':
+        # bf16 message mode (north_star: rel <= 1e-2): the transform GEMM rounds t once to bf16, K3 gathers 2-byte features
+        w['model'].message_dtype = 'bf16'
+        try:
+            n_steps = max(3, args.steps // 2)
+            rb = run_graph(w, n_steps, 3, dist, dev, peaks)
+            bf16_ms = rb['ms'] / n_steps
+            entry['bf16_mode'] = {'value': 2.0 * w['E'] * w['L'] * n_steps / (rb['ms'] * 1e-3), 'ms_per_step': rb['ms'] / n_steps, 'steps': n_steps,
+                                  'dtype': 'bf16 messages, fp32 accumulate', 'roofline': rb['roofline'],
+                                  'e2e': {'value': 2.0 * w['E'] * w['L'] * n_steps / (rb['e2e_ms'] * 1e-3), 'unit': 'edges/s',
+                                          'h2d_bytes_per_step': rb['h2d'], 'd2h_bytes_per_step': rb['d2h']}}
+        except Exception as e:
+            entry['bf16_mode'] = {'error': repr(e)[:300]}
+        w['model'].message_dtype = 'fp32'
+    # the 1-GPU step of the SAME graph measured in the SAME job (every rank holds the full graph): the denominator of the speed-up
+    single_ms = r['ms'] / args.steps
+    if world > 1:
+        pg = w['graph']._b200rec_partition
+        w['graph']._b200rec_partition = None
+        try:
+            r1 = run_graph(dict(w, eager=args.eager), max(3, args.steps // 2), 3, dist, dev, peaks)
+            single_ms = r1['ms'] / max(3, args.steps // 2)
+        finally:
+            w['graph']._b200rec_partition = pg
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, cpu_out, gpu_out = cpu_graph(w)
+        entry['cpu_baseline'] = {'value': v, 'unit': 'edges/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        entry['parity'] = (_parity(gpu_out, cpu_out, 'oracle/restatement.py::graph_ncf_forward on the 4 % edge sample of the benchmarked graph '
+                                                     '(the CUDA path rebuilt its index for the same sample)') if torch.is_tensor(gpu_out) else {'error': gpu_out})
+    ms = r['ms'] / args.steps
+    scaling = {'metric': entry['metric'], 'config': 'configs[2] MovieLens-25M shape, L=2, d=128, fp32', 'n_gpus': world, 'scheme': entry['config']['scheme'],
+               'value': entry['value'], 'unit': 'edges/s', 'ms_per_step': round(ms, 4),
+               'single_gpu_ms_per_step_same_job': round(single_ms, 4), 'speedup_vs_1gpu': round(single_ms / ms, 3), 'target_at_8': 7.0}
+    if bf16_ms:
+        scaling['bf16_messages'] = {'ms_per_step': round(bf16_ms, 4), 'value': 2.0 * w['E'] * w['L'] / (bf16_ms * 1e-3)}
+    entry['speedup_vs_1gpu'] = scaling['speedup_vs_1gpu']
+    return entry, scaling
 
 
 ATT_WORKLOAD = ('configs[1]: AttentionNCF scoring, synthetic MovieLens-latest-small shape (610 users, 9724 items, 100836 ratings, '
@@ -1056,9 +1210,10 @@ def main():
                     help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
     ap.add_argument('--skip-hbm-regime', action='store_true')
     ap.add_argument('--no-train-step', action='store_true', help='skip the eager train-step legs (AttentionNCF, GraphNCF)')
-    ap.add_argument('--graph-scheme', default='reduce', choices=['reduce', 'gather'],
-                    help="multi-GPU GraphNCF: 'reduce' = users partitioned, items replicated, one all-reduce of the item partials per "
-                         "layer; 'gather' = both sides partitioned, per-layer all-gathers (deeprecommendation_b200/parallel.py)")
+    ap.add_argument('--graph-scheme', default='peer', choices=['peer', 'reduce', 'gather'],
+                    help="multi-GPU GraphNCF: 'peer' = users partitioned, the exchange fused into this library's kernels over peer-mapped "
+                         "memory (deeprecommendation_b200/peer.py); 'reduce' / 'gather' = the same partitions with NCCL collectives issued "
+                         "from Python (deeprecommendation_b200/parallel.py), kept as the comparison baseline")
     ap.add_argument('--eager', action='store_true', help='do not capture the steps into CUDA graphs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -1092,14 +1247,13 @@ def main():
             w['no_train'] = world > 1 or args.no_train_step              # the train-step leg is single-GPU (no gradient all-reduce: out of scope)
             w['eager'] = args.eager
             r = run_attention(w, args.steps, args.warmup, dist, dev, peaks)
-            pairs = BATCH * args.steps * world
+            pairs = BATCH * r['nb'] * args.steps * world
             result = {'metric': 'scored user-item pairs/sec (NCF fwd)', 'value': pairs / (r['ms'] * 1e-3), 'unit': 'pairs/s',
                       'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms'] / args.steps,
                       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                      'config': {'workload': ATT_WORKLOAD, 'batch': BATCH, 'parallelism': f'dp{world} (pairs sharded, no collective)',
-                                 'mean_rated_union_I': r['I_mean'], 'mean_nnz_per_batch': r['nnz_mean'],
-                                 'l2': f'{len(w["host"])} rotating batches (~105 MB each) resident in HBM, > 126 MB L2 between reuses',
-                                 'launch_mode': r['launch_mode']},
+                      'config': attention_config(world, args.gemm),
+                      'run_info': {'mean_rated_union_I': r['I_mean'], 'mean_nnz_per_batch': r['nnz_mean'], 'launch_mode': r['launch_mode'],
+                                   'pairs_per_step_per_gpu': BATCH * r['nb']},
                       'roofline': r['roofline'],
                       'e2e': {'value': pairs / (r['e2e_ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': r['h2d'],
                               'd2h_bytes_per_step': r['d2h'], 'ms_per_step': r['e2e_ms'] / args.steps},
@@ -1120,8 +1274,9 @@ def main():
                                                  'K2 backward = attention_pool_bwd_kernel, forward and gradient GEMMs on K1a, torch elementwise ops '
                                                  'for dropout masks / bias sums / the optimizer'} if 'ms' in t else t)
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
-                v, cores, sample = cpu_attention(w)
+                v, cores, sample, cpu_out = cpu_attention(w)
                 result['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+                result['parity'] = _parity(r['out0'], cpu_out, 'oracle/restatement.py::attention_ncf_forward on batch 0 of the benchmarked config')
                 if r.get('serving') and 'ms_per_request' in r['serving']:
                     try:
                         result['serving']['cpu_ms_per_request'] = cpu_serving(w)
@@ -1140,22 +1295,24 @@ def main():
             w = build_basic(dev, rank)
             w['eager'] = args.eager
             r = run_basic(w, args.steps, args.warmup, dist, dev, peaks)
-            pairs = BATCH * args.steps * world
+            pairs = BATCH * r['nb'] * args.steps * world
             entry = {'metric': 'scored user-item pairs/sec (BasicNCF fwd)', 'value': pairs / (r['ms'] * 1e-3), 'unit': 'pairs/s',
                      'ms_per_step': r['ms'] / args.steps, 'scaling': 'weak', 'dtype': 'f32',
                      'config': {'workload': 'configs[0] shape: BasicNCF(2094, 2094, 128, 128, [256]) forward, batches of 512 (user, item) '
-                                'profile pairs', 'l2': f'{len(w["host"])} rotating batches (275 MB) > L2', 'launch_mode': r.get('launch_mode')},
+                                'profile pairs', 'batches_per_step': r['nb'], 'l2': f'one step = {len(w["host"])} rotating batches (275 MB of inputs) > L2',
+                                'launch_mode': r.get('launch_mode')},
                      'roofline': r['roofline'],
                      'e2e': {'value': pairs / (r['e2e_ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
                      'gpu_launches': r['launches']}
             if r.get('train_ms'):
-                entry['train_step'] = {'value': pairs / (r['train_ms'] * 1e-3), 'unit': 'pairs/s', 'ms_per_step': r['train_ms'] / args.steps,
+                entry['train_step'] = {'value': BATCH * args.steps * world / (r['train_ms'] * 1e-3), 'unit': 'pairs/s', 'ms_per_step': r['train_ms'] / args.steps,
                                        'launch_mode': r.get('train_mode'),
                                        'what': 'forward (dropout 0.2) + sum-MSE backward + Adam on the same batches; forward and gradient GEMMs on K1a, '
                                                'torch elementwise ops for masks / bias sums / the optimizer'}
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
-                v, cores, sample = cpu_basic(w)
+                v, cores, sample, cpu_out = cpu_basic(w)
                 entry['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+                entry['parity'] = _parity(r['out0'], cpu_out, 'oracle/restatement.py::basic_ncf_forward on batch 0 of the benchmarked config')
                 entry['cpu_baseline']['train_step_value'] = cpu_basic_train(w)
             if result is None:
                 result = entry
@@ -1163,51 +1320,6 @@ def main():
                 also.append(entry)
             del w
             torch.cuda.empty_cache()
-        if args.workload in ('all', 'graph'):
-            w = build_graph(dev, args.graph_scale, world, args.graph_scheme)
-            w['eager'] = args.eager
-            w['train_leg'] = world == 1 and not args.no_train_step
-            r = run_graph(w, args.steps, args.warmup, dist, dev, peaks)
-            msgs = 2.0 * w['E'] * w['L'] * args.steps          # the graph is fixed: strong scaling
-            entry = {'metric': 'GNN propagation directed-edge messages/sec (GraphNCF fwd)', 'value': msgs / (r['ms'] * 1e-3),
-                     'unit': 'edges/s', 'ms_per_step': r['ms'] / args.steps,
-                     'scaling': 'strong', 'parallelism': ((f'users 1-D nnz-partitioned over {world} GPUs, items replicated; one NCCL all-reduce of the (nI, d) item partials per non-final layer, hidden behind the user-row SpMM; batch rows by all-reduce' if args.graph_scheme == 'reduce' else f'item and user rows each 1-D nnz-partitioned over {world} GPUs; two NCCL all-gathers per layer, the larger one hidden behind the first SpMM; batch rows by all-reduce') if world > 1 else 'single GPU'),
-                     'dtype': 'f32',
-                     'config': {'workload': f'configs[2]: GraphNCF L=2 d=128 hetero, synthetic MovieLens-25M shape (nU={w["nU"]}, nI={w["nI"]}, '
-                                f'E={w["E"]}), pre-embedded (N,128) node features, whole-graph propagation + MLP on a batch of 512 per step',
-                                'l2': 'CSR (400 MB) + features (115 MB) > L2', 'index_build_s': round(w['build_s'], 3),
-                                'launch_mode': r['launch_mode']},
-                     'roofline': r['roofline'],
-                     'e2e': {'value': msgs / (r['e2e_ms'] * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
-                     'gpu_launches': r['launches']}
-            if r.get('train'):
-                t = r['train']
-                entry['train_step'] = ({'value': 2.0 * w['E'] * w['L'] / (t['ms'] * 1e-3), 'unit': 'edges/s', 'ms_per_step': t['ms'], 'steps': t['steps'],
-                                        'launch_mode': 'eager',
-                                        'what': 'whole-graph forward in train mode with the 512 target edges masked out (pair hash + skip bitmap), conv and '
-                                                'MLP dropout, sum-MSE backward (K3 on the reverse-edge weights, gradient GEMMs on K1a) and Adam; value counts '
-                                                'the forward messages only (2E*L per step), like the inference line'} if 'ms' in t else t)
-            if world == 1:
-                w['train_leg'] = False
-                # bf16 message mode (north_star: rel <= 1e-2): the transform GEMM rounds t once to bf16, K3 gathers 2-byte features
-                w['model'].message_dtype = 'bf16'
-                try:
-                    n_steps = max(3, args.steps // 2)
-                    rb = run_graph(w, n_steps, 3, dist, dev, peaks)
-                    entry['bf16_mode'] = {'value': 2.0 * w['E'] * w['L'] * n_steps / (rb['ms'] * 1e-3), 'ms_per_step': rb['ms'] / n_steps, 'steps': n_steps,
-                                          'dtype': 'bf16 messages, fp32 accumulate', 'roofline': rb['roofline'],
-                                          'e2e': {'value': 2.0 * w['E'] * w['L'] * n_steps / (rb['e2e_ms'] * 1e-3), 'unit': 'edges/s',
-                                                  'h2d_bytes_per_step': rb['h2d'], 'd2h_bytes_per_step': rb['d2h']}}
-                except Exception as e:
-                    entry['bf16_mode'] = {'error': repr(e)[:300]}
-                w['model'].message_dtype = 'fp32'
-            if rank == 0 and world == 1 and not args.no_cpu_baseline:
-                v, cores, sample = cpu_graph(w)
-                entry['cpu_baseline'] = {'value': v, 'unit': 'edges/s', 'cores': cores, 'kind': 'port', 'sample': sample}
-            if result is None:
-                result = entry
-            else:
-                also.append(entry)
         if args.workload in ('all', 'allpairs'):
             w = build_allpairs(dev, rank)
             entry = None
@@ -1230,8 +1342,9 @@ def main():
                 else:
                     entry['bf16_mode'] = {k: e[k] for k in ('value', 'ms_per_step', 'roofline', 'e2e', 'dtype')}
             if rank == 0 and world == 1 and not args.no_cpu_baseline:
-                v, cores, sample = cpu_allpairs(w)
+                v, cores, sample, par = cpu_allpairs(w)
                 entry['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+                entry['parity'] = par
             if result is None:
                 result = entry
             else:
@@ -1248,15 +1361,30 @@ def main():
             also.append(run_k2_hbm_regime(dev, peaks))
         except Exception as e:
             also.append({'metric': 'K2 HBM regime', 'error': repr(e)[:300]})
+    graph_scaling = None
+    if args.workload in ('all', 'graph'):                  # LAST, so that the tail of the line carries the strong-scaling leg
+        with ClockSampler(local) as gclocks:
+            entry, graph_scaling = graph_leg(args, dev, rank, world, dist, peaks)
+        if args.workload == 'graph':
+            clocks = gclocks
+        else:
+            entry['clocks'] = gclocks.summary()
+        also.append(entry)
     if result is None:
         result, also = also[0], also[1:]
-    result.setdefault('config', {})['gemm_engine'] = args.gemm
+    result.setdefault('config', {}).setdefault('gemm_engine', args.gemm)
     for k, v in (('n_gpus', world), ('steps', args.steps), ('warmup', args.warmup), ('higher_is_better', True), ('vs_baseline', None),
                  ('data', 'synthetic')):
         result.setdefault(k, v)
     result['clocks'] = clocks.summary()
+    for e in [result] + also:                               # every roofline object says where its `traffic` figure comes from
+        for ro in (e.get('roofline'), (e.get('bf16_mode') or {}).get('roofline')):
+            if isinstance(ro, dict) and 'traffic' in ro:
+                ro.setdefault('traffic_source', 'profiles/traffic.json (static: one `ncu --set full` capture of this kernel per round, not measured in this run)')
     if also:
         result['also'] = also
+    if graph_scaling is not None:
+        result['graph_scaling'] = graph_scaling            # compact copy of the strong-scaling leg at the very end of the line
     if rank == 0:
         print(json.dumps(result), flush=True)
     if dist is not None:

@@ -67,6 +67,9 @@ SIGNATURES = {
     'b200rec_linear_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),
     'b200rec_linear_shortk': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp]),
     'b200rec_linear_shortk_push': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, C.POINTER(c_vp), c_int, c_i64, c_i64, c_int, c_vp]),
+    'b200rec_linear_sparse': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_vp]),
+    'b200rec_dense_nnz_count': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    'b200rec_dense_nnz_fill': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'b200rec_linear_tc_batch': (c_int, [C.POINTER(LinearProblem), c_int, c_i64, c_int, c_vp]),
     'b200rec_linear_tc_splitk_batch_workspace': (c_sz, [C.POINTER(LinearProblem), c_int, c_i64, c_int]),
     'b200rec_linear_tc_splitk_batch': (c_int, [C.POINTER(LinearProblem), c_int, c_i64, c_int, c_vp, c_sz, c_vp]),

@@ -113,6 +113,137 @@ class ResidentRows:
         return self.table.index_select(0, self.pos.to(self.table.device, non_blocking=True)).to(dev)
 
 
+class OneHotRows:
+    """The `(n, num_classes)` one-hot rows of the collate contract (src/content_providers/one_hot_provider.py:17-21,
+    fixed_profiles_provider.py:49-50: `one_hot_encode(id, all_ids)`) as their column numbers: 8 bytes per row instead of 4·num_classes.
+    Quacks like the tensor the datasets expect (`.float()`, `.to(device)`); models project it with K1s (ops.linear_rows)."""
+    kind = 'onehot'
+
+    def __init__(self, ids, num_classes: int):
+        self.ids = ids if torch.is_tensor(ids) else torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64))
+        self.num_classes = int(num_classes)
+
+    @property
+    def shape(self):
+        return (int(self.ids.numel()), self.num_classes)
+
+    def float(self):
+        return self
+
+    def to(self, device, non_blocking=False):
+        return OneHotRows(self.ids.to(device, non_blocking=non_blocking), self.num_classes)
+
+    def dense(self) -> torch.Tensor:
+        out = torch.zeros(self.shape, dtype=torch.float32, device=self.ids.device)
+        ok = self.ids >= 0
+        out[torch.arange(self.shape[0], device=self.ids.device)[ok], self.ids[ok]] = 1.0
+        return out
+
+
+class MixedRows:
+    """Profile rows whose first `n_sparse` columns are multi-hot / sparse (CSR: row_ptr int32, col int32, val fp32 or None = 1) and whose
+    remaining columns are dense — the item profiles of the reference: 21 genre + 945 personnel multi-hot columns, then 1,128 dense
+    genome-tag relevances.  `dense` may be None (purely multi-hot rows)."""
+    kind = 'mixed'
+
+    def __init__(self, row_ptr, col, val, n_sparse: int, dense=None):
+        as_t = lambda a, dt: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt))
+        self.row_ptr, self.col = as_t(row_ptr, np.int32), as_t(col, np.int32)
+        self.val = None if val is None else as_t(val, np.float32)
+        self.n_sparse = int(n_sparse)
+        self.dense = None if dense is None else (dense if torch.is_tensor(dense) else torch.from_numpy(np.ascontiguousarray(dense, dtype=np.float32)))
+
+    @property
+    def width(self):
+        return self.n_sparse + (0 if self.dense is None else int(self.dense.shape[1]))
+
+    @property
+    def shape(self):
+        return (int(self.row_ptr.numel() - 1), self.width)
+
+    def float(self):
+        return self
+
+    def to(self, device, non_blocking=False):
+        mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
+        return MixedRows(mv(self.row_ptr), mv(self.col), mv(self.val), self.n_sparse, mv(self.dense))
+
+    def dense_rows(self) -> torch.Tensor:
+        """the reference's dense (n, width) tensor, materialised (tests)"""
+        n = self.shape[0]
+        dev = self.row_ptr.device
+        out = torch.zeros((n, self.width), dtype=torch.float32, device=dev)
+        rows = torch.repeat_interleave(torch.arange(n, device=dev), (self.row_ptr[1:] - self.row_ptr[:-1]).long())
+        out[rows, self.col.long()] = 1.0 if self.val is None else self.val
+        if self.dense is not None:
+            out[:, self.n_sparse:] = self.dense
+        return out
+
+    @classmethod
+    def from_dense(cls, rows: np.ndarray, n_sparse: int):
+        """host-side split of dense profile rows (what a provider does once for its whole table)"""
+        rows = np.asarray(rows, dtype=np.float32)
+        sp = rows[:, :n_sparse]
+        r, c = np.nonzero(sp)
+        row_ptr = np.zeros(rows.shape[0] + 1, dtype=np.int32)
+        np.cumsum(np.bincount(r, minlength=rows.shape[0]), out=row_ptr[1:])
+        v = sp[r, c]
+        return cls(row_ptr, c.astype(np.int32), None if np.all(v == 1.0) else v, n_sparse, rows[:, n_sparse:] if n_sparse < rows.shape[1] else None)
+
+    def take(self, idx: np.ndarray):
+        """rows `idx` (host arrays) as a new MixedRows — the per-batch `.loc` lookup of a provider"""
+        rp, col = self.row_ptr.numpy(), self.col.numpy()
+        idx = np.asarray(idx, dtype=np.int64)
+        lens = rp[idx + 1] - rp[idx]
+        nrp = np.zeros(len(idx) + 1, dtype=np.int32)
+        np.cumsum(lens, out=nrp[1:])
+        src = np.repeat(rp[idx], lens) + (np.arange(int(nrp[-1])) - np.repeat(nrp[:-1], lens))
+        return MixedRows(nrp, col[src], None if self.val is None else self.val.numpy()[src], self.n_sparse,
+                         None if self.dense is None else self.dense[torch.from_numpy(idx)])
+
+
+class OneHotArrayProvider(ContentProvider):
+    """One-hot user AND item profiles (src/content_providers/one_hot_provider.py).  sparse=True hands out `OneHotRows` (ids), sparse=False
+    the reference's dense one-hot rows."""
+
+    def __init__(self, item_ids, user_ids, sparse=True):
+        self.item_ids, self.user_ids, self.sparse = np.asarray(item_ids), np.asarray(user_ids), sparse
+
+    def _rows(self, table, ids):
+        pos = np.searchsorted(table, np.atleast_1d(np.asarray(ids)))
+        if self.sparse:
+            return OneHotRows(pos, len(table))
+        out = np.zeros((len(pos), len(table)), dtype=np.float32)
+        out[np.arange(len(pos)), pos] = 1.0
+        return out
+
+    def get_item_profile(self, itemID):
+        return self._rows(self.item_ids, itemID)
+
+    def get_user_profile(self, userID):
+        return self._rows(self.user_ids, userID)
+
+    def get_num_items(self):
+        return len(self.item_ids)
+
+    def get_num_users(self):
+        return len(self.user_ids)
+
+    def get_item_feature_dim(self):
+        return len(self.item_ids)
+
+
+class MixedProfilesProvider(ArrayProfilesProvider):
+    """Fixed profiles whose item rows are handed out as `MixedRows` (multi-hot columns as index lists, dense columns as is)."""
+
+    def __init__(self, item_ids, item_profiles, user_ids, user_profiles, n_sparse):
+        super().__init__(item_ids, item_profiles, user_ids, user_profiles)
+        self._mixed = MixedRows.from_dense(self.item_profiles, n_sparse)
+
+    def get_item_profile(self, itemID):
+        return self._mixed.take(np.searchsorted(self.item_ids, np.atleast_1d(np.asarray(itemID))))
+
+
 class SparseUserMatrix:
     """CSR of the `(B, I)` user_matrix of the collate contract (exact zeros = "unrated" are simply absent)."""
 

@@ -6,9 +6,15 @@ import torch
 from .base import PointwiseDataset, RankingDataset
 
 
+def _tensor(p):
+    """dense rows become the reference's FloatTensor; sparse row containers (content_providers.OneHotRows / MixedRows) pass through — they
+    answer `.float()` / `.to(device)` like a tensor and the models project them with the gather-sum kernel"""
+    return p if getattr(p, 'kind', None) in ('onehot', 'mixed') else torch.FloatTensor(p)
+
+
 def _profiles(cp, users, *item_lists):
-    out = [torch.FloatTensor(cp.get_user_profile(userID=users))]
-    out += [torch.FloatTensor(cp.get_item_profile(itemID=ids)) for ids in item_lists]
+    out = [_tensor(cp.get_user_profile(userID=users))]
+    out += [_tensor(cp.get_item_profile(itemID=ids)) for ids in item_lists]
     return out
 
 

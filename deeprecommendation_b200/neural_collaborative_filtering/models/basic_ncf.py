@@ -25,7 +25,11 @@ class BasicNCF(NCF):
 
     def forward(self, X_user, X_item):
         ue, ie = self.user_embeddings[0], self.item_embeddings[0]
-        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+        if not (torch.is_tensor(X_user) and torch.is_tensor(X_item)):
+            # one-hot / multi-hot rows (content_providers.OneHotRows / MixedRows): gather-sum projection K1s, dense columns on K1a
+            user_emb = ops.linear_rows(X_user, ue.weight, ue.bias)
+            item_emb = ops.linear_rows(X_item, ie.weight, ie.bias)
+        elif not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
             # inference: both projections of the batch in one launch when they are short-M / long-K (split-K over one wave)
             user_emb, item_emb = ops.linear_pair(X_user, ue.weight, ue.bias, X_item, ie.weight, ie.bias)
         else:

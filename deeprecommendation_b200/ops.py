@@ -300,6 +300,140 @@ def linear_pair(xa, wa, ba, xb, wb, bb):
     return outs[0], outs[1]
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# K1s sparse projection (one-hot / multi-hot profile rows)
+# ------------------------------------------------------------------------------------------------------------------
+_wt_cache = {}
+
+
+def _transposed_weight(weight, c0, c1, dtype=torch.float32):
+    """W[:, c0:c1]^T as a contiguous (c1 - c0, N) table (the "embedding table" K1s gathers from), cached per weight version."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), c0, c1, dtype, weight.device.index)
+    hit = _wt_cache.get(key)
+    if hit is not None and hit[0]() is weight:
+        return hit[1]
+    wt = weight.detach()[:, c0:c1].t().to(dtype).contiguous()
+    if len(_wt_cache) > 64:
+        _wt_cache.clear()
+    if not (torch.is_grad_enabled() and weight.requires_grad):
+        _wt_cache[key] = (weakref.ref(weight), wt)
+    return wt
+
+
+def linear_sparse_raw(weight, bias, *, csr=None, ids=None, cols=None, out=None, accumulate=False, table_dtype=torch.float32):
+    """out (+)= bias + sum_k val[k] * weight[:, c0 + col[k]]  — b200rec_linear_sparse.  `csr` = (row_ptr int32 (M+1), col int32, val fp32 | None)
+    or `ids` (M int64: one-hot rows); `cols` = (c0, c1): the weight columns the indices refer to (default: all)."""
+    _require_cuda(weight, bias, out)
+    c0, c1 = (0, weight.shape[1]) if cols is None else cols
+    N = weight.shape[0]
+    if N % 4:
+        raise NotImplementedError('linear_sparse: output width must be a multiple of 4')
+    wt = _transposed_weight(weight, c0, c1, table_dtype)
+    if csr is not None:
+        rp, col, val = csr
+        rp, col = rp.contiguous().int(), col.contiguous().int()
+        val = None if val is None else val.contiguous().float()
+        M = rp.numel() - 1
+        _require_cuda(rp, col, val)
+    else:
+        ids = ids.contiguous().long()
+        _require_cuda(ids)
+        rp = col = val = None
+        M = ids.numel()
+    if out is None:
+        if accumulate:
+            raise ValueError('linear_sparse: accumulate needs `out`')
+        out = torch.empty((M, N), dtype=torch.float32, device=weight.device)
+    elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError('linear_sparse: bad `out`')
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+        bias = bias.detach().contiguous().float()
+    ldy = out.stride(0) if M > 1 else max(N, out.stride(0))
+    nnz = int(col.numel()) if col is not None else M
+    with torch.cuda.device(weight.device), _timed('linear_sparse', (M, nnz, c1 - c0, N)):
+        L.check(L.lib().b200rec_linear_sparse(_ptr(rp), _ptr(col), _ptr(val), _ptr(ids), M, _ptr(wt), c1 - c0, N, N, _dtype_code(table_dtype),
+                                              None if accumulate else _ptr(bias), _ptr(out), ldy, int(accumulate), _stream()), 'linear_sparse')
+    return out
+
+
+def dense_to_csr(x, c0, c1):
+    """(row_ptr int32, col int32, val fp32) of the non-zero entries of x[:, c0:c1] (b200rec_dense_nnz_count / _fill + the library scan)"""
+    _require_cuda(x)
+    x, ldx = _row_major(x)
+    M = x.shape[0]
+    lib = L.lib()
+    cnt = torch.empty(M, dtype=torch.int32, device=x.device)
+    rp = torch.empty(M + 1, dtype=torch.int32, device=x.device)
+    ws = torch.empty(max(int(lib.b200rec_scan_workspace(M)), 16), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(lib.b200rec_dense_nnz_count(_ptr(x), M, ldx, c0, c1, _ptr(cnt), _stream()), 'dense_nnz_count')
+        L.check(lib.b200rec_exclusive_scan_i32(_ptr(cnt), M, _ptr(rp), _ptr(ws), ws.numel(), _stream()), 'scan')
+        nnz = int(rp[-1].item())
+        col = torch.empty(max(nnz, 1), dtype=torch.int32, device=x.device)
+        val = torch.empty(max(nnz, 1), dtype=torch.float32, device=x.device)
+        L.check(lib.b200rec_dense_nnz_fill(_ptr(x), M, ldx, c0, c1, _ptr(rp), _ptr(col), _ptr(val), _stream()), 'dense_nnz_fill')
+    return rp, col[:nnz], val[:nnz]
+
+
+class _SparseLinearFn(torch.autograd.Function):
+    """forward: K1s.  backward: dW^T[col] += val * g[row] (torch index_add_, hardware order like the reference's GEMM-free scatter)."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, rp, col, val, ids, c0, c1):
+        ctx.save_for_backward(weight, rp, col, val, ids)
+        ctx.cols, ctx.has_bias = (c0, c1), bias is not None
+        return linear_sparse_raw(weight, bias, csr=None if rp is None else (rp, col, val), ids=ids, cols=(c0, c1))
+
+    @staticmethod
+    def backward(ctx, g):
+        weight, rp, col, val, ids = ctx.saved_tensors
+        c0, c1 = ctx.cols
+        g = g.contiguous().float()
+        gwt = torch.zeros((c1 - c0, weight.shape[0]), dtype=torch.float32, device=g.device)
+        if ids is not None:
+            ok = ids >= 0
+            gwt.index_add_(0, ids[ok], g[ok])
+        else:
+            rows = torch.repeat_interleave(torch.arange(g.shape[0], device=g.device), (rp[1:] - rp[:-1]).long())
+            contrib = g[rows] if val is None else g[rows] * val[:, None]
+            gwt.index_add_(0, col.long(), contrib)
+        gw = torch.zeros_like(weight, dtype=torch.float32)
+        gw[:, c0:c1] = gwt.t()
+        return gw, (g.sum(0) if ctx.has_bias else None), None, None, None, None, None, None
+
+
+def linear_rows(x, weight, bias=None, out=None):
+    """`nn.Linear` over profile rows in whichever form the provider delivers them (content_providers.py): a dense tensor (K1a), `OneHotRows`
+    (K1s: one table row per output row) or `MixedRows` (K1a over the dense columns, then K1s accumulates the non-zeros of the sparse ones)."""
+    if torch.is_tensor(x):
+        if out is not None:
+            return linear_raw(x, weight, bias, out=out)
+        return linear(x, weight, bias)
+    needs = torch.is_grad_enabled() and (weight.requires_grad or (bias is not None and bias.requires_grad))
+    kind = getattr(x, 'kind', None)
+    if kind == 'onehot':
+        if x.num_classes != weight.shape[1]:
+            raise ValueError(f'one-hot rows over {x.num_classes} classes against a weight with {weight.shape[1]} inputs')
+        if needs:
+            y = _SparseLinearFn.apply(weight, bias, None, None, None, x.ids, 0, weight.shape[1])
+            return y if out is None else out.copy_(y)
+        return linear_sparse_raw(weight, bias, ids=x.ids, out=out)
+    if kind == 'mixed':
+        ns, K = x.n_sparse, weight.shape[1]
+        if x.width != K:
+            raise ValueError(f'mixed rows of width {x.width} against a weight with {K} inputs')
+        if needs:
+            y = _SparseLinearFn.apply(weight, bias if x.dense is None else None, x.row_ptr, x.col, x.val, None, 0, ns)
+            if x.dense is not None:
+                y = y + linear(x.dense, weight[:, ns:], bias)
+            return y if out is None else out.copy_(y)
+        if x.dense is None:
+            return linear_sparse_raw(weight, bias, csr=(x.row_ptr, x.col, x.val), cols=(0, ns), out=out)
+        y = linear_raw(x.dense, weight[:, ns:], bias, out=out)
+        return linear_sparse_raw(weight, None, csr=(x.row_ptr, x.col, x.val), cols=(0, ns), out=y, accumulate=True)
+    raise TypeError(f'cannot project {type(x).__name__}')
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, row_scale, relu):

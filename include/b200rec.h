@@ -79,6 +79,22 @@ int b200rec_linear_shortk(const float* X, int64_t M, int64_t K, int64_t ldx, con
 int b200rec_linear_shortk_push(const float* X, int64_t M, int64_t K, int64_t ldx, const void* packed_w, int64_t N, const float* bias,
                                const float* row_scale, int relu, void* const* dst, int n_dst, int64_t y_offset, int64_t ldy, int y_dtype,
                                b200rec_stream_t stream);
+/* ---- K1s  projection of SPARSE profile rows (csrc/gather_sum.cu) -----------------------------------------------------------
+ * One-hot rows (src/content_providers/one_hot_provider.py:17-21, fixed_profiles_provider.py:49-50) and the ~1 %-dense multi-hot
+ * columns of the item profiles go through the same nn.Linear as dense columns in the reference (models/basic_ncf.py:38-39,
+ * attention_ncf.py:150-151, gnn_ncf.py:300-301).  Here:  Y[m] (+)= bias + sum_{k in row m} val[k] * Wt[col[k]]  with Wt = W^T,
+ * (K, N) row-major fp32 / bf16 — a warp-vectorised gather-sum, 128-bit loads, list order (deterministic).
+ * Rows are given as CSR (row_ptr int32 (M+1), col int32, val fp32 or NULL = 1) or, for one-hot rows, as `ids` (M int64, one
+ * column per row, negative = empty row); exactly one of the two.  accumulate != 0 adds onto the Y a dense-column GEMM has
+ * written (mixed profiles: K1a over the dense slice, then this over the non-zeros); bias is ignored then.  N % 4 == 0. */
+int b200rec_linear_sparse(const int* row_ptr, const int* col, const float* val, const int64_t* ids, int64_t M, const void* Wt, int64_t K,
+                          int64_t N, int64_t ldwt, int wt_dtype, const float* bias, float* Y, int64_t ldy, int accumulate,
+                          b200rec_stream_t stream);
+/* CSR of the non-zero entries of columns [c0, c1) of a dense (M, ldx) matrix, for callers that hold only the dense profile rows:
+ * count -> b200rec_exclusive_scan_i32 -> fill (col relative to c0, column order). */
+int b200rec_dense_nnz_count(const float* X, int64_t M, int64_t ldx, int64_t c0, int64_t c1, int* counts, b200rec_stream_t stream);
+int b200rec_dense_nnz_fill(const float* X, int64_t M, int64_t ldx, int64_t c0, int64_t c1, const int* row_ptr, int* col, float* val,
+                           b200rec_stream_t stream);
 /* Up to four such GEMMs sharing K and mode in ONE launch (candidate + rated-item projections, the two halves of
  * AttentionNet.0 — attention_ncf.py:150-151,176): problem q covers its own rows; fields as in b200rec_linear_tc. */
 typedef struct {

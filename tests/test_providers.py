@@ -116,3 +116,26 @@ def test_resident_provider_collate_equals_dense_collate():
             return torch.zeros(len(cand), 1)
     out, y = DynamicPointwiseDataset.do_forward(Probe(), b, 'cpu')
     assert out.shape == (len(batch), 1) and seen['shapes'] == (len(batch), a[3].shape[0], tuple(a[4].shape))
+
+
+def test_sparse_row_containers_round_trip_and_take():
+    """OneHotRows / MixedRows (the sparse forms of the fixed-profile collate contract) reproduce the dense rows they stand for"""
+    from deeprecommendation_b200.content_providers import MixedProfilesProvider, MixedRows, OneHotArrayProvider, OneHotRows
+    rng = np.random.default_rng(0)
+    rows = np.concatenate([(rng.random((40, 30)) < 0.1).astype(np.float32), rng.random((40, 12)).astype(np.float32)], axis=1)
+    rows[3, :30] = 0.0
+    m = MixedRows.from_dense(rows, 30)
+    assert m.val is None and m.shape == (40, 42) and np.array_equal(m.dense_rows().numpy(), rows)
+    pick = np.array([5, 3, 39, 5])
+    assert np.array_equal(m.take(pick).dense_rows().numpy(), rows[pick])
+    weighted = rows.copy()
+    weighted[:, :30] *= 2.5
+    mw = MixedRows.from_dense(weighted, 30)
+    assert mw.val is not None and np.array_equal(mw.dense_rows().numpy(), weighted)
+    item_ids, user_ids = np.array([3, 8, 20, 41]), np.array([7, 9])
+    sp, de = OneHotArrayProvider(item_ids, user_ids, sparse=True), OneHotArrayProvider(item_ids, user_ids, sparse=False)
+    got = sp.get_item_profile(np.array([20, 3]))
+    assert isinstance(got, OneHotRows) and got.float() is got and np.array_equal(got.dense().numpy(), de.get_item_profile(np.array([20, 3])))
+    assert sp.get_item_feature_dim() == 4 and sp.get_num_users() == 2
+    cp = MixedProfilesProvider(np.arange(40) * 3, rows, np.arange(5), rng.random((5, 42)).astype(np.float32), 30)
+    assert np.array_equal(cp.get_item_profile(np.array([9, 0])).dense_rows().numpy(), rows[[3, 0]])

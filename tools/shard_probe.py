@@ -62,7 +62,7 @@ def main():
         r['reduce_ms'] = timed(lambda: sh.reduce(0, d, x_next=xi, acc_in=acci, acc_out=acci, acc_scale=1.0))
         r['push_transform_ms'] = timed(lambda: sh.push_transform(xi, lin_i, 1, torch.float32))
         r['t_users_ms'] = timed(lambda: ops.linear_raw(xu, lin_u.weight, lin_u.bias, row_scale=sh.dinv_users, out=tu[:nu]))
-        r['signal_wait_ms'] = timed(lambda: (sh.signal(5), sh.wait(5)))
+        r['signal_wait_ms'] = timed(lambda: ([s2.signal(5) for s2 in shards], sh.wait(5)))      # 8 signal kernels + 1 wait kernel
         tb = torch.randn(max(nu, 1), d, device=dev).bfloat16()
         Tb = sh.table(1, d, torch.bfloat16)
         r['A_push_bf16_ms'] = timed(lambda: ops.spmm_raw(sh.index_items, tb, w=sh.index_items.w, dinv=sh.dinv_items_all, push=sh.push_spec(0, d)))
