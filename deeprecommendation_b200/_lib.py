@@ -54,6 +54,14 @@ class SpmmDesc(C.Structure):
                 ('push_dst', c_vp * PEER_MAX), ('push_parts', c_int), ('push_rows_per_part', c_int), ('push_offset', c_i64), ('push_ld', c_i64)]
 
 
+class SpmmStreamDesc(C.Structure):
+    _fields_ = [('colf', c_vp), ('wd', c_vp), ('nnz', c_i64), ('seg', c_int), ('n_segs', c_int), ('seg_first_j', c_vp), ('seg_head_slot', c_vp),
+                ('seg_tail_slot', c_vp), ('rows_ne', c_vp), ('n_ne', c_int), ('rows_empty', c_vp), ('n_empty', c_int), ('t', c_vp), ('t_dtype', c_int),
+                ('ld_t', c_i64), ('d', c_int), ('partials', c_vp), ('multi_row', c_vp), ('multi_first_slot', c_vp), ('multi_n_slots', c_vp),
+                ('n_multi', c_int), ('x_next', c_vp), ('ld_x', c_i64), ('acc_in', c_vp), ('acc_out', c_vp), ('ld_acc', c_i64), ('acc_scale', c_f),
+                ('push_dst', c_vp * PEER_MAX), ('push_parts', c_int), ('push_rows_per_part', c_int), ('push_offset', c_i64), ('push_ld', c_i64)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/b200rec.h
 SIGNATURES = {
     'b200rec_last_error': (C.c_char_p, []),
@@ -90,6 +98,7 @@ SIGNATURES = {
     'b200rec_attention_pool_prepare': (c_int, [C.POINTER(AttentionDesc), c_vp]),
     'b200rec_attention_pool_backward': (c_int, [C.POINTER(AttentionBwdDesc), c_vp]),
     'b200rec_spmm': (c_int, [C.POINTER(SpmmDesc), c_vp]),
+    'b200rec_spmm_stream': (c_int, [C.POINTER(SpmmStreamDesc), c_vp]),
     'b200rec_scan_workspace': (c_sz, [c_i64]),
     'b200rec_exclusive_scan_i32': (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     'b200rec_sort_pairs_workspace': (c_sz, [c_i64]),

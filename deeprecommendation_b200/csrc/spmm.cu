@@ -421,6 +421,24 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
 
 using namespace b200rec;
 
+// the fix-up pass alone, for csrc/spmm_stream.cu (rows cut by segment boundaries; normalisation already folded into the entries)
+int b200rec_spmm_fixup_launch(const float* partials, int d, const int* multi_row, const int* multi_first_slot, const int* multi_n_slots, int n_multi,
+                              float* x_next, long long ld_x, const float* acc_in, float* acc_out, long long ld_acc, float acc_scale,
+                              void* const* push_dst, int push_parts, int push_rpp, long long push_off, long long push_ld, cudaStream_t st) {
+  if (n_multi <= 0) return B200REC_OK;
+  SpmmParams p = {};
+  p.d = d; p.partials = const_cast<float*>(partials); p.dinv = nullptr;
+  p.multi_row = multi_row; p.multi_first_slot = multi_first_slot; p.multi_n_slots = multi_n_slots; p.n_multi = n_multi;
+  p.x_next = x_next; p.ld_x = ld_x; p.acc_in = acc_in; p.acc_out = acc_out; p.ld_acc = ld_acc; p.acc_scale = acc_scale;
+  p.push_parts = push_parts; p.push_rpp = push_rpp; p.push_off = push_off; p.push_ld = push_ld;
+  for (int q = 0; q < B200REC_PEER_MAX; ++q) p.push_dst[q] = push_dst ? push_dst[q] : nullptr;
+  const int g2 = ceil_div_i(n_multi, FIX_WARPS);
+  if (push_parts > 0) spmm_fixup_kernel<1, false, true><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+  else spmm_fixup_kernel<1, false, false><<<g2, FIX_WARPS * 32, 0, st>>>(p);
+  B200REC_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
 extern "C" int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream) {
   if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "spmm: null descriptor");
   if (a->d <= 0 || (a->d % 4) || a->n_chunks < 0 || a->n_multi < 0 || a->chunk_size <= 0 || (a->t_dtype == B200REC_BF16 && (a->d % 8)))

@@ -10,6 +10,7 @@ from the two edge lists once per graph and cached on the graph object.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -284,6 +285,84 @@ class GraphIndex:
         items = self.col[start[rows] + within].long()
         key = torch.sort(rows * self.num_nodes + items).values
         return ptr.int(), (key % self.num_nodes).int()
+
+
+class StreamPlan:
+    """Edge-balanced work plan of the inference SpMM (csrc/spmm_stream.cu) for one CSR + one deg^-1/2 vector: entry stream with the
+    last-entry-of-row flag, destination normalisation folded into the entry values, `seg` entries per warp, the partial slots of rows cut
+    by segment boundaries.  Built once per (index, dinv, seg) with torch ops — index-build time, not on the propagation path."""
+
+    def __init__(self, row_ptr, col, w, dinv, seg: int):
+        dev = row_ptr.device
+        n_rows, nnz = int(row_ptr.numel() - 1), int(col.numel())
+        self.seg, self.nnz, self.n_rows = int(seg), nnz, n_rows
+        rp = row_ptr.long()
+        deg = rp[1:] - rp[:-1]
+        ne = deg > 0
+        self.rows_ne = ne.nonzero().view(-1).int()
+        self.rows_empty = (~ne).nonzero().view(-1).int()
+        self.n_ne, self.n_empty = int(self.rows_ne.numel()), int(self.rows_empty.numel())
+        self.n_segs = (nnz + seg - 1) // seg
+        i32 = lambda n: torch.zeros(max(int(n), 1), dtype=torch.int32, device=dev)
+        if nnz == 0:
+            self.colf, self.wd = i32(1), torch.zeros(1, dtype=torch.float32, device=dev)
+            self.seg_first_j = self.seg_head_slot = self.seg_tail_slot = i32(1)
+            self.multi_row = self.multi_first_slot = self.multi_n_slots = i32(1)
+            self.n_multi = self.n_slots = 0
+            return
+        start, end = rp[:-1][ne], rp[1:][ne]
+        colf = col.int().clone()
+        colf[end - 1] += -2 ** 31                                    # bit 31 = last entry of its row (column numbers are < 2^31)
+        self.colf = colf
+        dst = torch.repeat_interleave(torch.arange(n_rows, device=dev), deg)
+        wd = dinv.float()[dst] if dinv is not None else torch.ones(nnz, dtype=torch.float32, device=dev)
+        self.wd = (wd * w.float()) if w is not None else wd
+        del dst
+        first_seg, last_seg = start // seg, (end - 1) // seg
+        n_pieces = last_seg - first_seg + 1
+        multi = n_pieces > 1
+        self.multi_row = self.rows_ne[multi].contiguous()
+        mn = n_pieces[multi]
+        self.n_multi = int(mn.numel())
+        mfirst = torch.cumsum(mn, 0) - mn
+        self.multi_n_slots, self.multi_first_slot = mn.int(), mfirst.int()
+        self.n_slots = int(mn.sum()) if self.n_multi else 0
+        if self.n_multi == 0:
+            self.multi_row = self.multi_first_slot = self.multi_n_slots = i32(1)
+        slot_base = torch.full((self.n_ne,), -1, dtype=torch.int64, device=dev)
+        slot_base[multi] = mfirst
+        s_idx = torch.arange(self.n_segs, device=dev)
+        s_start = s_idx * seg
+        j0 = torch.searchsorted(start, s_start, right=True) - 1       # row holding the segment's first entry
+        self.seg_first_j = j0.int()
+        head = start[j0] < s_start
+        self.seg_head_slot = torch.where(head, slot_base[j0] + (s_idx - first_seg[j0]), torch.full_like(j0, -1)).int()
+        e_next = torch.clamp(s_start + seg, max=nnz)                  # one past the segment's last entry
+        jl = torch.searchsorted(start, e_next - 1, right=True) - 1
+        still_open = end[jl] > e_next
+        self.seg_tail_slot = torch.where(still_open, slot_base[jl] + (s_idx - first_seg[jl]), torch.full_like(jl, -1)).int()
+
+
+def default_stream_seg(nnz: int) -> int:
+    """entries per warp: long segments amortise the set-up, but a launch should still be >= ~8 warps per resident warp slot of the GPU"""
+    env = os.environ.get('B200REC_SPMM_SEG')
+    if env:
+        return int(env)
+    return 256 if nnz >= 24_000_000 else (128 if nnz >= 2_000_000 else 64)
+
+
+def stream_plan(index, dinv=None, seg=None) -> StreamPlan:
+    """cached StreamPlan of a GraphIndex / local index for its own (or the given) deg^-1/2"""
+    dinv = index.dinv if dinv is None else dinv
+    seg = default_stream_seg(int(index.col.numel())) if seg is None else seg
+    cache = index.__dict__.setdefault('_stream_plans', {})
+    key = (seg, None if dinv is None else (dinv.data_ptr(), dinv._version), None if index.w is None else (index.w.data_ptr(), index.w._version))
+    plan = cache.get(key)
+    if plan is None:
+        if len(cache) > 4:
+            cache.clear()
+        plan = cache[key] = StreamPlan(index.row_ptr, index.col, index.w, dinv, seg)
+    return plan
 
 
 def get_index(graph) -> GraphIndex:

@@ -181,13 +181,13 @@ class GraphNCF(GNN_NCF):
                 last = l == L_ - 1
                 if self.concat:
                     xn = comb[:, d * (l + 1): d * (l + 2)]
-                    ops.spmm_raw(index, t, w=index.w, dinv=None if gat else dinv, x_next=xn, skip_bits=skip, att_src=ps if gat else None)
+                    ops.propagate_step(index, t, dinv=None if gat else dinv, x_next=xn, skip_bits=skip, att_src=ps if gat else None)
                 else:
                     # x is dead once t has been formed (same stream), so one spare buffer serves every layer; it must not
                     # alias x0, which layer 0 still reads as acc_in
                     xn = None if last else spare
-                    ops.spmm_raw(index, t, w=index.w, dinv=None if gat else dinv, x_next=xn, acc_in=x0 if l == 0 else comb, acc_out=comb,
-                                 acc_scale=1.0 / (L_ + 1) if last else 1.0, skip_bits=skip, att_src=ps if gat else None)
+                    ops.propagate_step(index, t, dinv=None if gat else dinv, x_next=xn, acc_in=x0 if l == 0 else comb, acc_out=comb,
+                                       acc_scale=1.0 / (L_ + 1) if last else 1.0, skip_bits=skip, att_src=ps if gat else None)
                 x = xn
             return comb
         if self.convType == 'LightGAT':

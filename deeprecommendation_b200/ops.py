@@ -747,6 +747,61 @@ def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, 
         L.check(L.lib().b200rec_spmm(C.byref(d), _stream()), 'spmm')
 
 
+SPMM_STREAM = os.environ.get('B200REC_SPMM_STREAM', '1') == '1'      # inference SpMM: edge-balanced stream kernel where it applies
+
+
+def stream_applicable(t, *, skip_bits=None, att_src=None):
+    """the stream kernel covers LightGCN inference with 64 < node_emb <= 128 (a lane owns 4 columns); narrower rows keep the row-owner kernel"""
+    return SPMM_STREAM and skip_bits is None and att_src is None and 64 < t.shape[1] <= 128 and t.shape[1] % 4 == 0
+
+
+def spmm_stream_raw(plan, t, *, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, push=None):
+    """One propagation step over a `graph.StreamPlan`: b200rec_spmm_stream (the destination normalisation lives in the plan's entry values)."""
+    _require_cuda(t)
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    d = L.SpmmStreamDesc()
+    d.colf, d.wd, d.nnz, d.seg, d.n_segs = plan.colf.data_ptr(), plan.wd.data_ptr(), plan.nnz, plan.seg, plan.n_segs
+    d.seg_first_j, d.seg_head_slot, d.seg_tail_slot = plan.seg_first_j.data_ptr(), plan.seg_head_slot.data_ptr(), plan.seg_tail_slot.data_ptr()
+    d.rows_ne, d.n_ne = plan.rows_ne.data_ptr() if plan.n_ne else None, plan.n_ne
+    d.rows_empty, d.n_empty = plan.rows_empty.data_ptr() if plan.n_empty else None, plan.n_empty
+    d.t, d.t_dtype, d.ld_t, d.d = t.data_ptr(), _dtype_code(t.dtype), t.stride(0), t.shape[1]
+    partials = None
+    if plan.n_multi > 0:
+        partials = torch.empty((plan.n_slots, t.shape[1]), dtype=torch.float32, device=t.device)
+        d.partials = partials.data_ptr()
+        d.multi_row, d.multi_first_slot, d.multi_n_slots = plan.multi_row.data_ptr(), plan.multi_first_slot.data_ptr(), plan.multi_n_slots.data_ptr()
+    d.n_multi = plan.n_multi
+    if x_next is not None:
+        d.x_next, d.ld_x = x_next.data_ptr(), x_next.stride(0)
+    if acc_out is not None:
+        d.acc_out, d.ld_acc = acc_out.data_ptr(), acc_out.stride(0)
+        if acc_in is not None:
+            if acc_in.stride(0) != acc_out.stride(0):
+                raise ValueError('spmm: acc_in and acc_out must share a leading dimension')
+            d.acc_in = acc_in.data_ptr()
+    d.acc_scale = acc_scale
+    if push is not None:
+        dst, parts, rpp, off, ld = push
+        if x_next is not None or acc_out is not None:
+            raise ValueError('spmm: `push` replaces x_next / acc_out')
+        for q in range(parts):
+            d.push_dst[q] = dst[q]
+        d.push_parts, d.push_rows_per_part, d.push_offset, d.push_ld = parts, rpp, off, ld
+    with torch.cuda.device(t.device), _timed('spmm', (plan.nnz, t.shape[1])):
+        L.check(L.lib().b200rec_spmm_stream(C.byref(d), _stream()), 'spmm_stream')
+
+
+def propagate_step(index, t, *, dinv, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, skip_bits=None, att_src=None, push=None):
+    """x' = dinv ∘ (A_w · t) (+ the fused running mean / the push epilogue) on whichever K3 form applies: the edge-balanced stream kernel for
+    LightGCN inference at 64 < d <= 128, else the row-owner chunk kernel."""
+    if stream_applicable(t, skip_bits=skip_bits, att_src=att_src):
+        from .graph import stream_plan
+        return spmm_stream_raw(stream_plan(index, dinv), t, x_next=x_next, acc_in=acc_in, acc_out=acc_out, acc_scale=acc_scale, push=push)
+    return spmm_raw(index, t, w=index.w, dinv=dinv, x_next=x_next, acc_in=acc_in, acc_out=acc_out, acc_scale=acc_scale, skip_bits=skip_bits,
+                    att_src=att_src, push=push)
+
+
 class _PropagateFn(torch.autograd.Function):
     """x_next = dinv ∘ (A_w · t).  backward = the same kernel on the reverse-direction weights (graph.py: w_bwd)."""
 

@@ -322,13 +322,13 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
             par, last = l & 1, l == L_ - 1
             scale = 1.0 / (L_ + 1) if last else 1.0
             if nu:                                                                   # A_l: partial item rows -> owners' receive slots
-                ops.spmm_raw(sh.index_items, t_users, w=sh.index_items.w, dinv=sh.dinv_items_all, push=sh.push_spec(par, d))
+                ops.propagate_step(sh.index_items, t_users, dinv=sh.dinv_items_all, push=sh.push_spec(par, d))
             sh.signal(CH_A0 + par)
             yield
             sh.wait(CH_T0 + par)
             if nu:                                                                   # B_l: own user rows from the gathered table
-                ops.spmm_raw(sh.index_users, sh.table(par, d, t_dtype), w=sh.index_users.w, dinv=sh.dinv_users, x_next=None if last else spare_u,
-                             acc_in=x0_users if l == 0 else acc_users, acc_out=acc_users, acc_scale=scale)
+                ops.propagate_step(sh.index_users, sh.table(par, d, t_dtype), dinv=sh.dinv_users, x_next=None if last else spare_u,
+                                   acc_in=x0_users if l == 0 else acc_users, acc_out=acc_users, acc_scale=scale)
             yield
             sh.wait(CH_A0 + par)
             sh.reduce(par, d, x_next=None if last else xi_next, acc_in=x0_items if l == 0 else acc_items, acc_out=acc_items, acc_scale=scale)

@@ -293,6 +293,49 @@ typedef struct {
 } b200rec_spmm_t;
 int b200rec_spmm(const b200rec_spmm_t* a, b200rec_stream_t stream);
 
+/* Edge-balanced ("stream") form of the same propagation step for inference (csrc/spmm_stream.cu): a warp owns `seg` consecutive CSR
+ * entries whatever rows they belong to, so short rows (a rank's slice of an item row on a partitioned graph) cost no per-row set-up.
+ *   colf[k]  = source node | (k is the LAST entry of its row) << 31        wd[k] = deg[dst]^-1/2 * w[k]   (gnn_ncf.py:54,91)
+ *   seg_first_j[s]   index into rows_ne of the row holding entry s*seg;   seg_head_slot[s] = partial slot of that row when it began in an
+ *   earlier segment (else -1);   seg_tail_slot[s] = partial slot of the row still open after the segment's last entry (else -1)
+ *   rows_ne / rows_empty = rows with / without entries (ascending);   multi_* = rows cut by a segment boundary and their slot runs,
+ *   added in segment order by the fix-up pass (deterministic).   t (N, d <= 128) fp32 or bf16.   Outputs / push_* as in b200rec_spmm_t. */
+typedef struct {
+  const int* colf;
+  const float* wd;
+  int64_t nnz;
+  int seg;
+  int n_segs;
+  const int* seg_first_j;
+  const int* seg_head_slot;
+  const int* seg_tail_slot;
+  const int* rows_ne;
+  int n_ne;
+  const int* rows_empty;
+  int n_empty;
+  const void* t;
+  int t_dtype;
+  int64_t ld_t;
+  int d;
+  float* partials; /* (n_slots, d) */
+  const int* multi_row;
+  const int* multi_first_slot;
+  const int* multi_n_slots;
+  int n_multi;
+  float* x_next;   /* may be NULL */
+  int64_t ld_x;
+  const float* acc_in; /* may be NULL */
+  float* acc_out;      /* may be NULL */
+  int64_t ld_acc;
+  float acc_scale;
+  void* push_dst[B200REC_PEER_MAX];
+  int push_parts;
+  int push_rows_per_part;
+  int64_t push_offset;
+  int64_t push_ld;
+} b200rec_spmm_stream_t;
+int b200rec_spmm_stream(const b200rec_spmm_stream_t* a, b200rec_stream_t stream);
+
 /* ---- K4  neighbour-index build (bit-exact vs src/content_providers/graph_providers.py:10-66,76-80) ---------------- */
 size_t b200rec_scan_workspace(int64_t n);
 int b200rec_exclusive_scan_i32(const int* in, int64_t n, int* out /* n+1 */, void* ws, size_t ws_bytes, b200rec_stream_t stream);

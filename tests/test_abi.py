@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_field_order():
     from deeprecommendation_b200 import _lib
     src = open(os.path.join(ROOT, 'include', 'b200rec.h')).read()
-    for cname, cls in (('b200rec_attention_t', _lib.AttentionDesc), ('b200rec_attention_bwd_t', _lib.AttentionBwdDesc), ('b200rec_spmm_t', _lib.SpmmDesc), ('b200rec_mlp_t', _lib.MlpDesc)):
+    for cname, cls in (('b200rec_attention_t', _lib.AttentionDesc), ('b200rec_attention_bwd_t', _lib.AttentionBwdDesc), ('b200rec_spmm_t', _lib.SpmmDesc), ('b200rec_spmm_stream_t', _lib.SpmmStreamDesc), ('b200rec_mlp_t', _lib.MlpDesc)):
         body = re.search(r'typedef struct \{([^}]*)\} ' + cname, src).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
         fields = []

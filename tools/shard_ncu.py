@@ -28,7 +28,15 @@ def main():
     tb, Tb = tu.bfloat16(), sh.table(1, d, torch.bfloat16)
     t_full = torch.randn(full.num_nodes, d, device=dev)
     xn = torch.empty(full.num_nodes, d, device=dev)
+    from deeprecommendation_b200.graph import StreamPlan
+    pa = StreamPlan(sh.index_items.row_ptr, sh.index_items.col, sh.index_items.w, sh.dinv_items_all, 128)
+    pb = StreamPlan(sh.index_users.row_ptr, sh.index_users.col, sh.index_users.w, sh.dinv_users, 128)
+    pf = StreamPlan(full.row_ptr, full.col, full.w, full.dinv, 256)
     for _ in range(2):
+        ops.spmm_stream_raw(pa, tu, push=sh.push_spec(0, d))
+        ops.spmm_stream_raw(pb, T, x_next=xu)
+        ops.spmm_stream_raw(pb, Tb, x_next=xu)
+        ops.spmm_stream_raw(pf, t_full, x_next=xn)
         ops.spmm_raw(sh.index_items, tu, w=sh.index_items.w, dinv=sh.dinv_items_all, push=sh.push_spec(0, d))
         ops.spmm_raw(sh.index_users, T, w=sh.index_users.w, dinv=sh.dinv_users, x_next=xu)
         ops.spmm_raw(sh.index_items, tb, w=sh.index_items.w, dinv=sh.dinv_items_all, push=sh.push_spec(0, d))

@@ -43,6 +43,15 @@ def main():
     t_full = torch.randn(full.num_nodes, d, device=dev)
     xn = torch.empty(full.num_nodes, d, device=dev)
     out['full_spmm_ms'] = timed(lambda: ops.spmm_raw(full, t_full, w=full.w, dinv=full.dinv, x_next=xn))
+    from deeprecommendation_b200.graph import StreamPlan
+    tb_full = t_full.bfloat16()
+    for seg in (128, 256, 512):
+        plan = StreamPlan(full.row_ptr, full.col, full.w, full.dinv, seg)
+        out[f'full_stream_seg{seg}_ms'] = timed(lambda: ops.spmm_stream_raw(plan, t_full, x_next=xn))
+        out[f'full_stream_seg{seg}_bf16_ms'] = timed(lambda: ops.spmm_stream_raw(plan, tb_full, x_next=xn))
+        out[f'full_stream_seg{seg}_multi'] = [plan.n_multi, plan.n_slots]
+        del plan
+    out['full_bf16_ms'] = timed(lambda: ops.spmm_raw(full, tb_full, w=full.w, dinv=full.dinv, x_next=xn))
     shards = emulated_shards(graph, world, d_max=d, batch_max=1024)
     lin_u, lin_i, _ = model.gnn_convs[0].typed()
     per_rank = []
@@ -64,6 +73,15 @@ def main():
         r['t_users_ms'] = timed(lambda: ops.linear_raw(xu, lin_u.weight, lin_u.bias, row_scale=sh.dinv_users, out=tu[:nu]))
         r['signal_wait_ms'] = timed(lambda: ([s2.signal(5) for s2 in shards], sh.wait(5)))      # 8 signal kernels + 1 wait kernel
         tb = torch.randn(max(nu, 1), d, device=dev).bfloat16()
+        for seg in (64, 128, 256):
+            pa = StreamPlan(sh.index_items.row_ptr, sh.index_items.col, sh.index_items.w, sh.dinv_items_all, seg)
+            pb = StreamPlan(sh.index_users.row_ptr, sh.index_users.col, sh.index_users.w, sh.dinv_users, seg)
+            r[f'A_stream{seg}_push_ms'] = timed(lambda: ops.spmm_stream_raw(pa, tu, push=sh.push_spec(0, d)))
+            r[f'B_stream{seg}_ms'] = timed(lambda: ops.spmm_stream_raw(pb, T, x_next=xu, acc_in=accu, acc_out=accu, acc_scale=1.0))
+            r[f'A_stream{seg}_push_bf16_ms'] = timed(lambda: ops.spmm_stream_raw(pa, tb, push=sh.push_spec(0, d)))
+            r[f'B_stream{seg}_bf16_ms'] = timed(lambda: ops.spmm_stream_raw(pb, sh.table(1, d, torch.bfloat16), x_next=xu, acc_in=accu, acc_out=accu, acc_scale=1.0))
+            r[f'stream{seg}_multi_A_B'] = [pa.n_multi, pb.n_multi]
+            del pa, pb
         Tb = sh.table(1, d, torch.bfloat16)
         r['A_push_bf16_ms'] = timed(lambda: ops.spmm_raw(sh.index_items, tb, w=sh.index_items.w, dinv=sh.dinv_items_all, push=sh.push_spec(0, d)))
         r['B_bf16_ms'] = timed(lambda: ops.spmm_raw(sh.index_users, Tb, w=sh.index_users.w, dinv=sh.dinv_users, x_next=xu, acc_in=accu, acc_out=accu, acc_scale=1.0))
