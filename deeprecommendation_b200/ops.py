@@ -750,9 +750,14 @@ def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, 
 SPMM_STREAM = os.environ.get('B200REC_SPMM_STREAM', '1') == '1'      # inference SpMM: edge-balanced stream kernel where it applies
 
 
-def stream_applicable(t, *, skip_bits=None, att_src=None):
-    """the stream kernel covers LightGCN inference with 64 < node_emb <= 128 (a lane owns 4 columns); narrower rows keep the row-owner kernel"""
-    return SPMM_STREAM and skip_bits is None and att_src is None and 64 < t.shape[1] <= 128 and t.shape[1] % 4 == 0
+STREAM_MAX_NNZ = int(os.environ.get('B200REC_SPMM_STREAM_MAX_NNZ', str(16_000_000)))
+
+
+def stream_applicable(t, nnz, *, skip_bits=None, att_src=None):
+    """the stream kernel covers LightGCN inference with 64 < node_emb <= 128 (a lane owns 4 columns) on indices of up to STREAM_MAX_NNZ
+    entries — the shards of a partitioned graph, where it is 5-15 % faster (profiles/r02); narrower rows and the whole 50 M-entry graph
+    (1.43 vs 1.42 ms per layer) keep the row-owner kernel"""
+    return (SPMM_STREAM and skip_bits is None and att_src is None and 64 < t.shape[1] <= 128 and t.shape[1] % 4 == 0 and 0 < nnz <= STREAM_MAX_NNZ)
 
 
 def spmm_stream_raw(plan, t, *, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, push=None):
@@ -795,7 +800,7 @@ def spmm_stream_raw(plan, t, *, x_next=None, acc_in=None, acc_out=None, acc_scal
 def propagate_step(index, t, *, dinv, x_next=None, acc_in=None, acc_out=None, acc_scale=1.0, skip_bits=None, att_src=None, push=None):
     """x' = dinv ∘ (A_w · t) (+ the fused running mean / the push epilogue) on whichever K3 form applies: the edge-balanced stream kernel for
     LightGCN inference at 64 < d <= 128, else the row-owner chunk kernel."""
-    if stream_applicable(t, skip_bits=skip_bits, att_src=att_src):
+    if stream_applicable(t, int(index.col.numel()), skip_bits=skip_bits, att_src=att_src):
         from .graph import stream_plan
         return spmm_stream_raw(stream_plan(index, dinv), t, x_next=x_next, acc_in=acc_in, acc_out=acc_out, acc_scale=acc_scale, push=push)
     return spmm_raw(index, t, w=index.w, dinv=dinv, x_next=x_next, acc_in=acc_in, acc_out=acc_out, acc_scale=acc_scale, skip_bits=skip_bits,

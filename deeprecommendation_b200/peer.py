@@ -28,6 +28,7 @@ exchange logic is covered by the single-GPU test-suite; there the ranks advance 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -42,6 +43,8 @@ _CTRL_BYTES = 4096                 # flags uint32[16][16] (1 KB) | counters uint
 _OFF_COUNTERS = L.PEER_CHANNELS * L.PEER_MAX * 4
 _OFF_ERR = _OFF_COUNTERS + 2 * L.PEER_CHANNELS * 4
 WAIT_TIMEOUT_NS = 10_000_000_000
+# the item side of a layer (wait for the partials, slot reduction, transform + broadcast) runs on a second stream under the user-row SpMM
+OVERLAP = os.environ.get('B200REC_PEER_OVERLAP', '1') == '1'
 
 
 class _Raw:
@@ -229,6 +232,11 @@ class PeerShard:
             L.check(L.lib().b200rec_peer_gather_rows(_ptr(table) if rows else None, d, row0, rows, _ptr(ids), ids.numel(), d, float(scale), dst,
                                                     self.world, dst_row * d, d, _stream()), 'peer_gather_rows')
 
+    def side_stream(self):
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def rows_view(self, n, d):
         return self.arena.view(self.off['rows'], (n, d))
 
@@ -318,25 +326,44 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
         sh.signal(CH_T0)
         if nu:
             ops.linear_raw(x0_users, lin_u.weight, lin_u.bias, row_scale=sh.dinv_users, out=t_users[:nu])
+        main = torch.cuda.current_stream(dev)
+        side = sh.side_stream() if OVERLAP else None
+        joined = None
+
+        def item_side(l, par, last, scale):                                          # C_l: needs every rank's A_l, nothing of B_l
+            sh.wait(CH_A0 + par)
+            sh.reduce(par, d, x_next=None if last else xi_next, acc_in=x0_items if l == 0 else acc_items, acc_out=acc_items, acc_scale=scale)
+            if not last:
+                sh.push_transform(xi_next, lin_i, 1 - par, t_dtype)
+                sh.signal(CH_T0 + (1 - par))
+
         for l in range(L_):
             par, last = l & 1, l == L_ - 1
             scale = 1.0 / (L_ + 1) if last else 1.0
             if nu:                                                                   # A_l: partial item rows -> owners' receive slots
                 ops.propagate_step(sh.index_items, t_users, dinv=sh.dinv_items_all, push=sh.push_spec(par, d))
             sh.signal(CH_A0 + par)
+            if side is not None:
+                forked = torch.cuda.Event()
+                forked.record(main)
             yield
+            if side is not None:                                                     # C_l on the side stream, under B_l
+                side.wait_event(forked)
+                with torch.cuda.stream(side):
+                    item_side(l, par, last, scale)
+                    joined = torch.cuda.Event()
+                    joined.record(side)
             sh.wait(CH_T0 + par)
             if nu:                                                                   # B_l: own user rows from the gathered table
                 ops.propagate_step(sh.index_users, sh.table(par, d, t_dtype), dinv=sh.dinv_users, x_next=None if last else spare_u,
                                    acc_in=x0_users if l == 0 else acc_users, acc_out=acc_users, acc_scale=scale)
-            yield
-            sh.wait(CH_A0 + par)
-            sh.reduce(par, d, x_next=None if last else xi_next, acc_in=x0_items if l == 0 else acc_items, acc_out=acc_items, acc_scale=scale)
-            if not last:                                                             # C_l: next layer's tables
-                sh.push_transform(xi_next, lin_i, 1 - par, t_dtype)
-                sh.signal(CH_T0 + (1 - par))
-                if nu:
-                    ops.linear_raw(spare_u, lin_u.weight, lin_u.bias, row_scale=sh.dinv_users, out=t_users[:nu])
+            if side is None:
+                yield
+                item_side(l, par, last, scale)
+            if not last and nu:
+                ops.linear_raw(spare_u, lin_u.weight, lin_u.bias, row_scale=sh.dinv_users, out=t_users[:nu])
+        if joined is not None:
+            main.wait_event(joined)
     if keep is not None:                        # tests: the owned rows of the combined embedding
         keep['items'], keep['users'] = acc_items, acc_users
     sh.gather_rows(acc_items, sh.it_r0, ni, iid, 0, d)
