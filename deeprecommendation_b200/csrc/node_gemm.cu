@@ -81,7 +81,7 @@ struct NodeGemmParams {
   int dbg;                             // experiments (B200REC_NT_DBG): 1 = no stores, 2 = no MMA, 4 = no TMEM loads
 };
 
-template <int NKB>
+template <int NKB, bool PUSH>
 __global__ void __launch_bounds__(NT_THREADS, 1)
 node_gemm_kernel(const __grid_constant__ NodeGemmParams p) {
   extern __shared__ unsigned char nt_smem_raw[];
@@ -227,8 +227,10 @@ node_gemm_kernel(const __grid_constant__ NodeGemmParams p) {
             const int grow = tile * 128 + e * 32 + r, n = cg * 32 + cc;
             if (grow < p.M && n < p.N) {
               const float4 v = *reinterpret_cast<const float4*>(stg + r * NT_STG_LD + cc);
-              for (int dq = 0; dq <= p.n_extra; ++dq) {             // dq > 0: the peers' copies of the table (NVLink stores)
-                void* const Yq = dq == 0 ? p.Y : p.Yx[dq - 1];
+              const int n_dst = PUSH ? p.n_extra + 1 : 1;           // PUSH: the peers' copies of the table (NVLink stores) after the local one
+#pragma unroll 1
+              for (int dq = 0; dq < n_dst; ++dq) {
+                void* const Yq = (!PUSH || dq == 0) ? p.Y : p.Yx[dq - 1];
                 if (p.y_bf16) {                                      // 4 rows x 64 bytes per warp instruction
                   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(Yq) + (long long)grow * p.ldy + n;
                   if (n + 3 < p.N && (((uintptr_t)d & 7) == 0)) {
@@ -296,17 +298,17 @@ node_gemm_kernel(const __grid_constant__ NodeGemmParams p) {
   }
 }
 
-template <int NKB>
+template <int NKB, bool PUSH>
 static int nt_launch(const NodeGemmParams& p, cudaStream_t st) {
   const size_t smem = (size_t)NKB * NT_STAGE + NT_NS * NT_STAGE + 512 + 4 * 32 * NT_STG_LD * 4 + 1024;
   static B200recSmemOptIn opted;
-  B200REC_CUDA(b200rec_opt_in_smem(opted, node_gemm_kernel<NKB>, (int)smem));
+  B200REC_CUDA(b200rec_opt_in_smem(opted, node_gemm_kernel<NKB, PUSH>, (int)smem));
   const int n_tiles = (p.M + 127) / 128;
   const int sms = b200rec_num_sms();
   // persistent grid: every CTA gets the same number of tiles where possible (waves of `sms`)
   const int waves = (n_tiles + sms - 1) / sms;
   const int grid = (n_tiles + waves - 1) / waves;
-  node_gemm_kernel<NKB><<<grid, NT_THREADS, smem, st>>>(p);
+  node_gemm_kernel<NKB, PUSH><<<grid, NT_THREADS, smem, st>>>(p);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -335,11 +337,19 @@ static int shortk_run(const float* X, int64_t M, int64_t K, int64_t ldx, const v
     p.dbg = e ? atoi(e) : 0;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_extra > 0) {
+    switch (K / 32) {
+      case 1: return nt_launch<1, true>(p, st);
+      case 2: return nt_launch<2, true>(p, st);
+      case 3: return nt_launch<3, true>(p, st);
+      default: return nt_launch<4, true>(p, st);
+    }
+  }
   switch (K / 32) {
-    case 1: return nt_launch<1>(p, st);
-    case 2: return nt_launch<2>(p, st);
-    case 3: return nt_launch<3>(p, st);
-    default: return nt_launch<4>(p, st);
+    case 1: return nt_launch<1, false>(p, st);
+    case 2: return nt_launch<2, false>(p, st);
+    case 3: return nt_launch<3, false>(p, st);
+    default: return nt_launch<4, false>(p, st);
   }
 }
 
