@@ -1128,8 +1128,18 @@ PARALLELISM = {
 
 def graph_leg(args, dev, rank, world, dist, peaks):
     """GraphNCF propagation, BASELINE configs[2] (strong scaling).  Returns (entry, compact scaling summary)."""
-    w = build_graph(dev, args.graph_scale, world, args.graph_scheme)
+    w = build_graph(dev, args.graph_scale, 1, args.graph_scheme)
     w['eager'] = args.eager
+    single_ms = None
+    if world > 1:
+        # the 1-GPU step of the SAME graph in the SAME job, BEFORE the graph is partitioned: every rank holds the whole graph and times the
+        # unpartitioned forward on its own GPU (no collective in it); the slowest rank's figure is the denominator of `speedup_vs_1gpu`
+        w['train_leg'] = False
+        n1 = max(3, args.steps // 2)
+        r1 = run_graph(w, n1, 3, None, dev, peaks)
+        single_ms = _max_over_ranks(dist, r1['ms'] / n1, dev)
+        from deeprecommendation_b200.parallel import partition_graph
+        partition_graph(w['graph'], scheme=args.graph_scheme, d_max=w['d'], batch_max=BATCH)
     w['train_leg'] = world == 1 and not args.no_train_step
     r = run_graph(w, args.steps, args.warmup, dist, dev, peaks)
     msgs = 2.0 * w['E'] * w['L'] * args.steps          # the graph is fixed: strong scaling
@@ -1167,16 +1177,8 @@ def graph_leg(args, dev, rank, world, dist, peaks):
         except Exception as e:
             entry['bf16_mode'] = {'error': repr(e)[:300]}
         w['model'].message_dtype = 'fp32'
-    # the 1-GPU step of the SAME graph measured in the SAME job (every rank holds the full graph): the denominator of the speed-up
-    single_ms = r['ms'] / args.steps
-    if world > 1:
-        pg = w['graph']._b200rec_partition
-        w['graph']._b200rec_partition = None
-        try:
-            r1 = run_graph(dict(w, eager=args.eager), max(3, args.steps // 2), 3, dist, dev, peaks)
-            single_ms = r1['ms'] / max(3, args.steps // 2)
-        finally:
-            w['graph']._b200rec_partition = pg
+    if single_ms is None:
+        single_ms = r['ms'] / args.steps
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample, cpu_out, gpu_out = cpu_graph(w)
         entry['cpu_baseline'] = {'value': v, 'unit': 'edges/s', 'cores': cores, 'kind': 'port', 'sample': sample}

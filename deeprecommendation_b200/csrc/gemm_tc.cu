@@ -92,10 +92,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format at [7,10)/[10,13)
 // (BF16 = 1, TF32 = 2), both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-template <int MODE>
+template <int MODE, int BN = TC_BN>
 __device__ __forceinline__ uint32_t make_idesc() {
   const uint32_t fmt = (MODE == TC_BF16) ? 1u : 2u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
 __device__ __forceinline__ float tf32_round(float x) {
@@ -235,24 +235,33 @@ struct TileRegs {
   }
 };
 
-template <int MODE, int NSTAGE, int EPL, bool VEC, bool WPACK>
+// BN = 256 ("wide" form, b200rec_linear_tc_wide): one CTA owns 128 rows x 256 columns, so every X block is loaded, split into TF32
+// hi / lo and written to shared memory ONCE for both halves of W (the BN = 128 grid does that work twice, and the producers — not
+// the tensor pipe — set the pace of a k-block: profiles/r01/gemm_tc_notes.md).  A stage is X (32 KB) + two packed W tiles (64 KB);
+// two stages fit.  TMEM holds two 256-column accumulators (hi·hi | cross terms); the wide form always runs split-K, which keeps the
+// accumulate chains short (see NACC below) and fills the device when M / 128 alone does not.
+template <int MODE, int NSTAGE, int EPL, bool VEC, bool WPACK, int BN = TC_BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
+  static_assert(BN == 128 || (BN == 256 && WPACK), "the wide form needs packed weights");
   int q = 0;
 #pragma unroll
   for (int t = 1; t < TC_MAX_BATCH; ++t)
     if (t < batch.n && (int)blockIdx.y >= batch.tile_start[t]) q = t;
   const TcParams& p = batch.prob[q];
-  if ((int)blockIdx.x * TC_BN >= p.N) return;                   // this problem has fewer n-tiles than the widest of the batch
+  if ((int)blockIdx.x * BN >= p.N) return;                      // this problem has fewer n-tiles than the widest of the batch
   constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
   constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
-  constexpr int STAGE_BYTES = 2 * PLANES * TILE_BYTES;          // A (hi[,lo]) + B (hi[,lo])
+  constexpr int NT = BN / 128;                                  // packed 128-row W tiles per stage
+  constexpr int A_BYTES = PLANES * TILE_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + NT * PLANES * TILE_BYTES;   // A (hi[,lo]) + B (hi[,lo]) x NT
   constexpr int UMMA_K_BYTES = 32;                              // 16 bf16 or 8 tf32 per MMA
   // The tensor core adds into the fp32 accumulator with truncation; over K = 2094 (786 accumulate steps in TF32x3) that
   // alone costs 1.3e-5 (measured).  TF32x3 therefore spreads the work over FOUR TMEM accumulators — hi·hi alternates
-  // between two per k-block, the small cross terms go to two more — and the epilogue adds them in registers.
-  constexpr int NACC = (MODE == TC_BF16) ? 1 : 4;
-  constexpr int TMEM_COLS = 128 * NACC;
+  // between two per k-block, the small cross terms go to two more — and the epilogue adds them in registers.  The wide form has
+  // room for two (512 TMEM columns): hi·hi | cross terms; its k range is split over CTAs, ~130 accumulate steps per chain.
+  constexpr int NACC = (MODE == TC_BF16) ? 1 : (BN == 256 ? 2 : 4);
+  constexpr int TMEM_COLS = BN * NACC;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B needs 1024-byte aligned tiles
   unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -260,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = ((int)blockIdx.y - batch.tile_start[q]) * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int m0 = ((int)blockIdx.y - batch.tile_start[q]) * TC_BM, n0 = blockIdx.x * BN;
   const int num_kb_total = (p.K + KB - 1) / KB;
   const int kb_base = p.kb_per_split ? (int)blockIdx.z * p.kb_per_split : 0;
   const int num_kb = p.kb_per_split ? min(p.kb_per_split, num_kb_total - kb_base) : num_kb_total;
@@ -295,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     aa.init(p.ldx, m0, p.M, warp, lane, p.row_index);
     if constexpr (!WPACK) ab.init(p.ldw, n0, p.N, warp, lane);
     // packed W: tile (n-tile, k-block) = PLANES x 16 KB, already converted and swizzled (pack_weights_kernel)
-    const unsigned char* wp_tiles = WPACK ? p.Wp + ((size_t)blockIdx.x * num_kb_total + kb_base) * (PLANES * TILE_BYTES) : nullptr;
+    const unsigned char* wp_tiles = WPACK ? p.Wp + ((size_t)blockIdx.x * NT * num_kb_total + kb_base) * (PLANES * TILE_BYTES) : nullptr;
     int kstore = kb_shift;                                    // k-block index of the stage being stored
     TileRegs<MODE, EPL> xa[PF + 1], xb[PF + 1];
     int kload = kb_shift;                                     // k-block index of the next load
@@ -324,14 +333,25 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
           mbar_wait(&empty_bar[s], ph ^ 1u);                  // first pass through the ring: returns immediately
           unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
           if constexpr (WPACK) {
-            if (tid == 0) {                                   // W tile: one TMA bulk copy, no thread touches the data
-              mbar_arrive_expect_tx(&full_bar[s], PLANES * TILE_BYTES);
-              tma_bulk_g2s(st + PLANES * TILE_BYTES, wp_tiles + (size_t)kstore * (PLANES * TILE_BYTES), PLANES * TILE_BYTES, &full_bar[s]);
+            if (tid == 0) {                                   // W tile(s): TMA bulk copies, no thread touches the data
+              mbar_arrive_expect_tx(&full_bar[s], NT * PLANES * TILE_BYTES);
+              if constexpr (NT == 1) {
+                tma_bulk_g2s(st + A_BYTES, wp_tiles + (size_t)kstore * (PLANES * TILE_BYTES), PLANES * TILE_BYTES, &full_bar[s]);
+              } else {
+                // two packed tiles [hi | lo] each -> stage layout [hi 0][hi 1][lo 0][lo 1]: the MMA sees one 256-row K-major operand per plane
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                  for (int pl = 0; pl < PLANES; ++pl)
+                    tma_bulk_g2s(st + A_BYTES + (pl * NT + nt) * TILE_BYTES,
+                                 wp_tiles + ((size_t)nt * num_kb_total + kstore) * (PLANES * TILE_BYTES) + (size_t)pl * TILE_BYTES, TILE_BYTES,
+                                 &full_bar[s]);
+              }
             }
             kstore = (kstore + 1 == num_kb) ? 0 : kstore + 1;
           }
           xa[j].store(st, st + TILE_BYTES, aa);
-          if constexpr (!WPACK) xb[j].store(st + PLANES * TILE_BYTES, st + (PLANES + 1) * TILE_BYTES, ab);
+          if constexpr (!WPACK) xb[j].store(st + A_BYTES, st + A_BYTES + TILE_BYTES, ab);
           if (!(p.dbg & 4)) fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core
           mbar_arrive(&full_bar[s]);
         }
@@ -351,13 +371,13 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     const long long e_ldy = split ? e_np : p.ldy;
     const float rs = (!split && p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col0 = chalf * 64 + cc * 32;
+    for (int cc = 0; cc < BN / 64; ++cc) {
+      const int col0 = chalf * (BN / 2) + cc * 32;
       float acc[32];
 #pragma unroll
       for (int a = 0; a < NACC; ++a) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * 128 + col0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * BN + col0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -370,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        const bool written = (a & 1) == 0 || num_kb > 1;      // with a single k-block the odd accumulators stay untouched
+        const bool written = NACC != 4 || (a & 1) == 0 || num_kb > 1;      // (4 accumulators) with a single k-block the odd ones stay untouched
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float x = written ? __uint_as_float(r[j]) : 0.f;
@@ -416,14 +436,14 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
   } else {
     // ===================== MMA issuer (one elected lane) =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc<MODE>();
+      const uint32_t idesc = make_idesc<MODE, BN>();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % NSTAGE;
         const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-        const uint32_t b_hi = a_hi + PLANES * TILE_BYTES;
+        const uint32_t b_hi = a_hi + A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 128 / UMMA_K_BYTES; ++ks) {
           if (p.dbg & 1) break;
@@ -431,10 +451,10 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
           if constexpr (MODE == TC_BF16) {
             umma<MODE>(tmem_base, make_desc(a_hi + off), make_desc(b_hi + off), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
           } else {
-            const uint32_t a_lo = a_hi + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
-            const uint32_t d_main = tmem_base + (uint32_t)((kb & 1) * 128);          // accumulators 0 / 1
-            const uint32_t d_cross = tmem_base + (uint32_t)(256 + (kb & 1) * 128);   // accumulators 2 / 3
-            const uint32_t first = (kb > 1 || ks > 0) ? 1u : 0u;                     // k-blocks 0 and 1 start their accumulators
+            const uint32_t a_lo = a_hi + TILE_BYTES, b_lo = b_hi + NT * TILE_BYTES;
+            const uint32_t d_main = tmem_base + (uint32_t)(NACC == 4 ? (kb & 1) * 128 : 0);            // accumulators 0 / 1
+            const uint32_t d_cross = tmem_base + (uint32_t)(NACC == 4 ? 256 + (kb & 1) * 128 : BN);    // accumulators 2 / 3
+            const uint32_t first = (kb > (NACC == 4 ? 1 : 0) || ks > 0) ? 1u : 0u;   // the first k-block(s) start their accumulators
             umma<MODE>(d_main, make_desc(a_hi + off), make_desc(b_hi + off), idesc, first);    // hi·hi
             umma<MODE>(d_cross, make_desc(a_hi + off), make_desc(b_lo + off), idesc, first);   // hi·lo
             umma<MODE>(d_cross, make_desc(a_lo + off), make_desc(b_hi + off), idesc, 1u);      // lo·hi
@@ -557,19 +577,19 @@ static int tc_splits(long long M, long long N, long long K, int mode, int* kb_pe
   return tc_splits_tiles(((M + 127) / 128) * ((N + 127) / 128), (N % 4) == 0, K, mode, kb_per_split);
 }
 
-template <int MODE, int EPL, bool VEC, bool WPACK>
+template <int MODE, int EPL, bool VEC, bool WPACK, int BN = TC_BN>
 static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
-  constexpr int NSTAGE = (MODE == TC_BF16) ? 4 : 3;
   constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
-  const size_t smem = (size_t)NSTAGE * 2 * PLANES * TILE_BYTES + 1024;
+  constexpr int NSTAGE = BN == 256 ? ((MODE == TC_BF16) ? 4 : 2) : ((MODE == TC_BF16) ? 4 : 3);
+  const size_t smem = (size_t)NSTAGE * (1 + BN / 128) * PLANES * TILE_BYTES + 1024;
   static B200recSmemOptIn opted;                     // per template instantiation, one bit per device
-  B200REC_CUDA(b200rec_opt_in_smem(opted, gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK>, (int)smem));
+  B200REC_CUDA(b200rec_opt_in_smem(opted, gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK, BN>, (int)smem));
   int nmax = 0;
   for (int q = 0; q < b.n; ++q) nmax = b.prob[q].N > nmax ? b.prob[q].N : nmax;
   const TcParams& p0 = b.prob[0];
   const int nsplit = p0.kb_per_split ? ceil_div_i(ceil_div_i(p0.K, (MODE == TC_BF16) ? 64 : 32), p0.kb_per_split) : 1;
-  dim3 grid(ceil_div_i(nmax, TC_BN), b.tile_start[b.n], nsplit);
-  gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK><<<grid, TC_THREADS, smem, st>>>(b);
+  dim3 grid(ceil_div_i(nmax, BN), b.tile_start[b.n], nsplit);
+  gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK, BN><<<grid, TC_THREADS, smem, st>>>(b);
   B200REC_CHECK_LAUNCH();
   if (p0.kb_per_split) {
     for (int q = 0; q < b.n; ++q) {                  // (a batch shares K and kb_per_split: b200rec_linear_tc_splitk_batch)
@@ -583,7 +603,7 @@ static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   return B200REC_OK;
 }
 
-template <int MODE>
+template <int MODE, int BN = TC_BN>
 static int launch_tc(const TcBatch& b, cudaStream_t st) {
   auto aligned = [&](int n) {
     for (int q = 0; q < b.n; ++q) {
@@ -597,15 +617,19 @@ static int launch_tc(const TcBatch& b, cudaStream_t st) {
   bool packed = true;
   for (int q = 0; q < b.n; ++q) packed = packed && b.prob[q].Wp != nullptr;
   if (packed) {
-    if (aligned(4)) return launch_tc_epl<MODE, 4, true, true>(b, st);
-    if (aligned(2)) return launch_tc_epl<MODE, 2, true, true>(b, st);
-    return launch_tc_epl<MODE, 2, false, true>(b, st);
+    if (aligned(4)) return launch_tc_epl<MODE, 4, true, true, BN>(b, st);
+    if (aligned(2)) return launch_tc_epl<MODE, 2, true, true, BN>(b, st);
+    return launch_tc_epl<MODE, 2, false, true, BN>(b, st);
   }
+  if constexpr (BN != TC_BN) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_wide: needs packed weights");
   for (int q = 0; q < b.n; ++q)
     if (b.prob[q].Wp != nullptr && b.prob[q].W == nullptr) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc: a batch mixes packed-only and plain weights");
-  if (aligned(4)) return launch_tc_epl<MODE, 4, true, false>(b, st);        // 128-bit loads (e.g. K = 128 transforms)
-  if (aligned(2)) return launch_tc_epl<MODE, 2, true, false>(b, st);        // 64-bit loads (F = 2094)
-  return launch_tc_epl<MODE, 2, false, false>(b, st);                       // odd K / pitch: scalar loads
+  if constexpr (BN == TC_BN) {
+    if (aligned(4)) return launch_tc_epl<MODE, 4, true, false>(b, st);        // 128-bit loads (e.g. K = 128 transforms)
+    if (aligned(2)) return launch_tc_epl<MODE, 2, true, false>(b, st);        // 64-bit loads (F = 2094)
+    return launch_tc_epl<MODE, 2, false, false>(b, st);                       // odd K / pitch: scalar loads
+  }
+  return B200REC_ERR_BAD_ARG;
 }
 
 }  // namespace b200rec
@@ -696,6 +720,49 @@ extern "C" int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, in
   for (int q = 1; q < TC_MAX_BATCH; ++q) b.tile_start[q + 1] = b.tile_start[1];
   cudaStream_t st = (cudaStream_t)stream;
   return mode == B200REC_TC_TF32X3 ? launch_tc<TC_TF32X3>(b, st) : launch_tc<TC_BF16>(b, st);
+}
+
+// wide form: 128 x 256 tiles, k range split so that (row tiles) x (column pairs) x splits fills the device once
+static int tc_wide_splits(long long M, long long N, long long K, int* kb_per_split) {
+  const long long tiles = ((M + 127) / 128) * ((N + 255) / 256);
+  const int num_kb = (int)((K + 31) / 32);
+  const int sms = b200rec_num_sms();
+  int want = (int)(sms / tiles);
+  if (want < 2) want = 2;                                       // always split: the two TMEM accumulators want short chains
+  if (want > num_kb / 4) want = num_kb / 4;
+  if (want < 1) want = 1;
+  const int kbps = (num_kb + want - 1) / want;
+  *kb_per_split = kbps;
+  return (num_kb + kbps - 1) / kbps;
+}
+
+extern "C" size_t b200rec_linear_tc_wide_workspace(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int kbps = 0;
+  const int splits = tc_wide_splits(M, N, K, &kbps);
+  return (size_t)splits * (size_t)M * (size_t)((N + 3) & ~3LL) * sizeof(float);
+}
+
+extern "C" int b200rec_linear_tc_wide(const float* X, int64_t M, int64_t K, int64_t ldx, int64_t N, const float* bias, const float* row_scale,
+                                      int relu, void* Y, int64_t ldy, int y_dtype, const void* packed_w, const int64_t* row_index,
+                                      int64_t x_rows, void* workspace, size_t workspace_bytes, b200rec_stream_t stream) {
+  TcBatch b;
+  b.n = 1;
+  if (!packed_w) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_wide: needs the packed weights (b200rec_pack_weights_tc, TF32X3)");
+  if (N <= 128 || ((N + 127) / 128) % 2) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc_wide: N must cover an even number of 128-column tiles");
+  const int rc = tc_fill(b.prob[0], X, M, K, ldx, nullptr, N, K, bias, row_scale, relu, Y, ldy, y_dtype, packed_w, row_index, x_rows);
+  if (rc) return rc;
+  if (M == 0) return B200REC_OK;
+  int kbps = 0;
+  const int splits = tc_wide_splits(M, N, K, &kbps);
+  const size_t need = (size_t)splits * (size_t)M * (size_t)((N + 3) & ~3LL) * sizeof(float);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace % 16)) return b200rec_fail(B200REC_ERR_WORKSPACE, "linear_tc_wide: workspace too small");
+  b.prob[0].kb_per_split = kbps;
+  b.prob[0].partial = (float*)workspace;
+  b.tile_start[0] = 0;
+  b.tile_start[1] = ceil_div_i(M, TC_BM);
+  for (int q = 1; q < TC_MAX_BATCH; ++q) b.tile_start[q + 1] = b.tile_start[1];
+  return launch_tc<TC_TF32X3, 256>(b, (cudaStream_t)stream);
 }
 
 extern "C" int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode,

@@ -110,6 +110,7 @@ TC_MIN_ROWS = 2048
 TC_SPLITK_MIN_ROWS = 128      # below TC_MIN_ROWS the tensor-core GEMM runs split-K (if K is long enough to be dealt out)
 SHORTK_MIN_ROWS = 4096  # below this a handful of 64x64 FFMA tiles is as fast as the persistent kernel's set-up
 SPLITK_ANY_N = os.environ.get('B200REC_SPLITK_ANY_N', '1') == '1'   # split-K also when N % 4 != 0 (padded slabs)
+TC_WIDE = os.environ.get('B200REC_TC_WIDE', '1') == '1'      # 128 x 256 tiles + split-K for 128 < N (csrc/gemm_tc.cu, BN = 256)
 TC_MIN_K = 512          # short-K GEMMs (the d x d GraphNCF transforms) are epilogue/latency-bound: FFMA is as fast there
 
 
@@ -187,6 +188,14 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     if engine != 'simt' and ((M >= TC_MIN_ROWS and K >= TC_MIN_K) or engine.endswith('!')) and (x_rows if row_index is not None else M) * ldx < 2 ** 32:
         mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
         packed = _packed_weight(w, ldw, mode) if _pack_weights else None
+        if TC_WIDE and mode == L.TC_TF32X3 and packed is not None and N > 128 and ((N + 127) // 128) % 2 == 0 and K >= 256:
+            # 128 x 256 tiles: every X block converted and staged once for both halves of W, k range split over the CTAs
+            wsb = lib.b200rec_linear_tc_wide_workspace(M, N, K)
+            ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
+            with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
+                L.check(lib.b200rec_linear_tc_wide(_ptr(x), M, K, ldx, N, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy, _dtype_code(out.dtype),
+                                                   _ptr(packed), _ptr(row_index), x_rows, _ptr(ws), wsb, _stream()), 'linear_tc_wide')
+            return out
         with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
             L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                           _dtype_code(out.dtype), mode, _ptr(packed), _ptr(row_index), x_rows, _stream()), 'linear_tc')

@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python bench.py --workload graph --steps 10 --warmup 3 --no-cpu-baseline --no-train-step > gpurun_out/bench_graph_n1.json 2> gpurun_out/bench_graph_n1.err; echo "bench rc=$?"
-tail -c 1200 gpurun_out/bench_graph_n1.json; tail -3 gpurun_out/bench_graph_n1.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_graph_r02_v1.csv python bench.py --workload graph --steps 2 --warmup 3 --no-cpu-baseline --no-train-step --eager > gpurun_out/ncu_graph.log 2>&1; echo "ncu rc=$?"
-python tools/launch_summary.py gpurun_out/launches_graph_r02_v1.csv | tail -25
+timeout 900 python -m pytest tests/test_gemm_tc_gpu.py -x -q -m gpu > gpurun_out/test_gemm.log 2>&1; echo "gemm tests rc=$?"
+tail -8 gpurun_out/test_gemm.log
+timeout 600 python tools/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemm bench rc=$?"
+grep -E "94|96" gpurun_out/gemm_bench.log | head -20

@@ -65,6 +65,14 @@ size_t b200rec_linear_tc_splitk_workspace(int64_t M, int64_t N, int64_t K, int m
 int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, int64_t ldx, const float* W, int64_t N, int64_t ldw, const float* bias,
                              const float* row_scale, int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w,
                              void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
+/* Wide form for 128 < N (an even number of 128-column tiles, e.g. the 256 outputs of AttentionNCF's composite projections,
+ * attention_ncf.py:150-151,176,216): a CTA owns 128 rows x 256 columns, so each X block is read, split and staged once for both
+ * halves of W; the k range is always split (workspace = b200rec_linear_tc_wide_workspace bytes, slabs added in split order by the
+ * same reduction kernel as b200rec_linear_tc_splitk).  fp32 parity (3xTF32); `packed_w` is required. */
+size_t b200rec_linear_tc_wide_workspace(int64_t M, int64_t N, int64_t K);
+int b200rec_linear_tc_wide(const float* X, int64_t M, int64_t K, int64_t ldx, int64_t N, const float* bias, const float* row_scale, int relu,
+                           void* Y, int64_t ldy, int y_dtype, const void* packed_w, const int64_t* row_index, int64_t x_rows, void* workspace,
+                           size_t workspace_bytes, b200rec_stream_t stream);
 /* Persistent short-K variant for the per-node transforms of GraphNCF (K in {32,64,96,128}, N <= 128; csrc/node_gemm.cu):
  * W stays in shared memory (`packed_w` = b200rec_pack_weights_tc(..., B200REC_TC_TF32X3)), row tiles are streamed, fp32 parity
  * by the 3xTF32 split.  X rows 16-byte aligned (ldx % 4 == 0); Y fp32 or bf16 (`y_dtype`; bf16 = the message table of GraphNCF's

@@ -137,3 +137,30 @@ def test_linear_pair_batched_splitk(Ma, Mb, K, Na, Nb):
         ops.set_gemm_engine(prev)
     assert maxnorm_rel(ya, torch.nn.functional.linear(xa.double(), wa.double(), ba.double())) < 1e-5
     assert maxnorm_rel(yb, torch.nn.functional.linear(xb.double(), wb.double(), bb.double())) < 1e-5
+
+
+@pytest.mark.parametrize('M,K,N', [(9461, 2094, 256), (2500, 2094, 256), (4096, 512, 384 + 128), (3000, 1000, 130), (2049, 2094, 200)])
+def test_linear_tc_wide_tiles_fp32_parity(M, K, N):
+    """128 x 256 tiles + split-K (b200rec_linear_tc_wide): the default route of large-M GEMMs with 128 < N.  Same fp32 tolerance as the
+    128 x 128 form, deterministic, agrees with it to fp32 rounding; row_index gather, bias / row scale / ReLU after the slab reduction."""
+    from deeprecommendation_b200 import ops
+    x, w, b, s = _case(M, K, N, M + N)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    xd, wd, bd, sd = x.cuda(), w.cuda(), b.cuda(), s.cuda()
+    assert ops.TC_WIDE
+    y = ops.linear_raw(xd, wd, bd, engine='tf32x3!')
+    assert maxnorm_rel(y, ref) < 1e-5
+    assert torch.equal(y, ops.linear_raw(xd, wd, bd, engine='tf32x3!'))
+    ops.TC_WIDE = False
+    try:
+        y128 = ops.linear_raw(xd, wd, bd, engine='tf32x3!')
+    finally:
+        ops.TC_WIDE = True
+    assert maxnorm_rel(y, y128) < 2e-6
+    out = torch.full((M, N + 8), 3.0, device='cuda')
+    ops.linear_raw(xd, wd, bd, sd, True, out=out[:, 4:4 + N], engine='tf32x3!')
+    assert maxnorm_rel(out[:, 4:4 + N], (ref * s.double()[:, None]).relu()) < 1e-5
+    assert torch.all(out[:, :4] == 3.0) and torch.all(out[:, 4 + N:] == 3.0)
+    idx = torch.randint(0, M, (2300,), generator=torch.Generator().manual_seed(1)).cuda()
+    yg = ops.linear_raw(xd, wd, bd, row_index=idx, engine='tf32x3!')
+    assert maxnorm_rel(yg, ref[idx.cpu()]) < 1e-5
