@@ -580,9 +580,15 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
 
     ops_ms = op_breakdown(step_eager, min(steps, 4), 0)
+    trace = None
     if hasattr(getattr(graph, '_b200rec_partition', None), 'check'):
         torch.cuda.synchronize()
         graph._b200rec_partition.check()                     # a peer wait that timed out would have produced garbage: fail loudly
+        if graphed is not None and os.environ.get('B200REC_PEER_TRACE') == '1':
+            graphed.replay()
+            graphed.replay()
+            torch.cuda.synchronize()
+            trace = graph._b200rec_partition.trace()         # %globaltimer markers of the last replayed step of this rank
 
     # training step on the same graph (NCF/train.py:99-105 through gnn_ncf.py:298-367): target edges of the batch masked out of the
     # propagation (pair hash + skip bitmap), conv / MLP dropout, sum-MSE backward (K3 on the reverse-edge weights, gradient GEMMs on
@@ -635,7 +641,7 @@ def run_graph(w, steps, warmup, dist, dev, peaks):
             roof['fp32_view'] = {'algorithmic_flops': int(flops), 'peak': fp32, 'unit': 'TFLOP/s', 'roofline_ms': round(t_fp32, 4),
                                  'frac': round(t_fp32 / kms, 4), 'what': 'cuBLAS fp32 SIMT rate of this GPU (profiles/tf32_peak.json); the kernel itself '
                                  'is bound by the L1 data path (ncu l1tex 81 %), see DESIGN.md'}
-    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof, train=train,
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * 8, d2h=BATCH * 4, roofline=roof, train=train, trace=trace,
                 launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
@@ -1115,6 +1121,177 @@ def attention_config(world, gemm):
             'gemm_engine': gemm}
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# workload E — GraphNCF 3 layers on 10M users x 1M items x 1B edges, BASELINE configs[4]: built AND run partitioned
+# ----------------------------------------------------------------------------------------------------------------------
+G5_USERS, G5_ITEMS, G5_EDGES, G5_D, G5_LAYERS, G5_VSHARDS = 10_000_000, 1_000_000, 1_000_000_000, 64, 3, 8
+
+
+def g5_shard_edges(v, n_users_v, n_items, n_edges_v, dev, a_user=0.5, a_item=0.9, active_items=0.95):
+    """interactions of VIRTUAL shard v (its own users x all items), unique pairs, Zipf-like degrees on both sides.  The graph is the union of
+    G5_VSHARDS such shards whatever the number of ranks, so every --gpus N runs the SAME graph (a rank owns G5_VSHARDS / N of them)."""
+    g = torch.Generator(device=dev).manual_seed(1000 + v)
+    gi = torch.Generator(device=dev).manual_seed(999)                      # the item popularity order is shared by all shards
+    n_act = max(1, int(round(n_items * active_items)))
+    ip = torch.randperm(n_items, device=dev, generator=gi)[:n_act]
+    cu = torch.cumsum(1.0 / torch.arange(1, n_users_v + 1, device=dev, dtype=torch.float64) ** a_user, 0)
+    ci = torch.cumsum(1.0 / torch.arange(1, n_act + 1, device=dev, dtype=torch.float64) ** a_item, 0)
+    cu, ci = cu / cu[-1], ci / ci[-1]
+    up = torch.randperm(n_users_v, device=dev, generator=g)
+    keys = torch.empty(0, dtype=torch.int64, device=dev)
+    while keys.numel() < n_edges_v:
+        m = int((n_edges_v - keys.numel()) * 1.25) + 1024
+        u = torch.searchsorted(cu, torch.rand(m, device=dev, dtype=torch.float64, generator=g)).clamp_(max=n_users_v - 1)
+        i = torch.searchsorted(ci, torch.rand(m, device=dev, dtype=torch.float64, generator=g)).clamp_(max=n_act - 1)
+        new = up[u] * n_items + ip[i]
+        del u, i
+        keys = torch.unique(torch.cat((keys, new)))
+        del new
+    keys = keys[torch.randperm(keys.numel(), device=dev, generator=g)[:n_edges_v]]
+    ratings = torch.randint(1, 11, (n_edges_v,), device=dev, generator=g).double() * 0.5
+    return keys // n_items, keys % n_items, ratings
+
+
+def run_graph5(args, dev, rank, world, dist, peaks, scale=1.0):
+    """configs[4]: every rank generates and indexes ONLY its own users' interactions (deeprecommendation_b200/sharded.py), the propagation
+    runs over peer memory (peer.py).  Parity at full size: with identity transforms and rank-one features x0[n] = s0[n]·v every layer stays
+    rank-one, x_l[n] = s_l[n]·v with s_{l+1} = D^-1/2 A_w D^-1/2 s_l — a float64 torch SpMV recurrence (+ NCCL sums at check time) that the
+    CUDA path must reproduce on EVERY owned row."""
+    import torch.distributed as tdist
+    from deeprecommendation_b200 import synth
+    from deeprecommendation_b200.neural_collaborative_filtering.models import GraphNCF
+    from deeprecommendation_b200.peer import forward_peer
+    from deeprecommendation_b200.sharded import build_shard
+    V = G5_VSHARDS
+    if world > V or V % world:
+        raise ValueError(f'graph5 runs on 1, 2, 4 or 8 GPUs (the graph is the union of {V} virtual shards)')
+    nU, nI, E, d, L_ = int(G5_USERS * scale), int(G5_ITEMS * scale), int(G5_EDGES * scale), G5_D, G5_LAYERS
+    nU_v, E_v = nU // V, E // V
+    nU, E = nU_v * V, E_v * V
+    mine = list(range(rank * (V // world), (rank + 1) * (V // world)))
+    t0 = time.perf_counter()
+    us, its, rs = [], [], []
+    for k, v in enumerate(mine):
+        u, i, r = g5_shard_edges(v, nU_v, nI, E_v, dev)
+        us.append(u + k * nU_v)
+        its.append(i)
+        rs.append(r)
+    u_local, items, ratings = torch.cat(us), torch.cat(its), torch.cat(rs)
+    del us, its, rs
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    n_local = nU_v * len(mine)
+    users_r0 = mine[0] * nU_v
+    gf = torch.Generator(device=dev).manual_seed(77)
+    item_features = torch.randn(nI, d, device=dev, generator=gf)                        # pre-embedded (N, 64) node features
+    user_features = torch.cat([torch.randn(nU_v, d, device=dev, generator=torch.Generator(device=dev).manual_seed(500 + v)) for v in mine])
+    t0 = time.perf_counter()
+    if dist is None:
+        tdist.init_process_group('gloo', init_method='tcp://127.0.0.1:29597', rank=0, world_size=1) if not tdist.is_initialized() else None
+    sh = build_shard(u_local, items, ratings, nI=nI, nU=nU, users_r0=users_r0, n_local_users=n_local, item_features=item_features,
+                     user_features_local=user_features, d_max=d, batch_max=BATCH, edges_total=2 * E)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    kw = dict(item_dim=d, user_dim=d, num_gnn_layers=L_, hetero=True, node_emb=d, mlp_dense_layers=[128], dropout_rate=0.2)
+    model = GraphNCF(**kw).to(dev).eval()
+    model.load_state_dict(synth.to_torch(synth.graph_ncf_weights(seed=2, **kw)))
+    gb = torch.Generator(device=dev).manual_seed(5)                                    # the same batch on every rank
+    pick = torch.randint(0, E_v, (BATCH,), device=dev, generator=gb)
+    v0 = g5_batch_pairs(nU_v, nI, E_v, pick, dev)
+    uid, iid = (v0[0] + nI).contiguous(), v0[1].contiguous()
+
+    def step(i):
+        with torch.no_grad():
+            return forward_peer(model, sh, uid, iid)
+
+    steps = max(3, min(args.steps, 10))
+    ms, launches = timed_steps(step, steps, 3, dist, dev)
+    torch.cuda.synchronize()
+    sh.check()
+    ops_ms = op_breakdown(step, 2, 0)
+    spmm = sorted([(k, v) for k, v in ops_ms.items() if k[0] == 'spmm'], key=lambda kv: -kv[1][0])
+    # ---- parity at full size: rank-one features through identity transforms vs a float64 SpMV recurrence ----
+    parity = g5_rank_one_check(model, sh, dist, dev, nI, d, L_, uid, iid)
+    sd0 = synth.to_torch(synth.graph_ncf_weights(seed=2, **kw))
+    model.load_state_dict(sd0)
+    msgs = 2.0 * E * L_ * steps
+    kms = float(np.mean([v[0] for _, v in spmm])) if spmm else 0.0
+    e_own = sh.edges_own / 2.0                                                          # directed entries of ONE of this rank's two SpMMs per layer
+    alg = e_own * 8 + e_own * d * 4 + (sh.nI + sh.users_rows) / 2.0 * d * 4             # SURVEY.md §8d K3, features larger than L2
+    roof = {'bound': 'hbm', 'kernel': 'spmm_chunk_kernel + spmm_fixup_kernel (K3; mean of the rank\'s two SpMMs per layer: partial item rows with the push '
+                                      'epilogue, own user rows)', 'achieved': round(alg / (kms * 1e-3) / 1e9, 1) if kms else 0.0, 'peak': peaks['hbm_gbs'],
+            'unit': 'GB/s', 'frac': round(alg / (kms * 1e-3) / 1e9 / peaks['hbm_gbs'], 4) if kms else 0.0, 'traffic': None, 'peak_source': peaks['src'],
+            'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg),
+            'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
+    exch = (world - 1) / world * nI * d * 4
+    return {'metric': 'GNN propagation directed-edge messages/sec (GraphNCF fwd, configs[4])', 'value': msgs / (ms * 1e-3), 'unit': 'edges/s',
+            'ms_per_step': ms / steps, 'steps': steps, 'n_gpus': world, 'scaling': 'strong', 'dtype': 'f32',
+            'parallelism': PARALLELISM['peer'].format(P=world) + '; the graph is generated and indexed per rank (sharded.py): item means / degrees by one all-reduce at build time',
+            'config': {'workload': f'configs[4]: GraphNCF L={L_} d={d} hetero mlp=[128] (train_model.py:166-174), synthetic nU={nU}, nI={nI}, E={E} '
+                                   f'({2 * E} directed), pre-embedded (N,{d}) features, whole-graph propagation + MLP on a batch of {BATCH} per step',
+                       'l2': f'per rank: CSR {sh.edges_own * 8 / 1e9:.1f} GB, features {(n_local + nI) * d * 4 / 1e9:.2f} GB >> L2',
+                       'generate_s': round(gen_s, 2), 'index_build_s': round(build_s, 2), 'launch_mode': 'eager', 'scale': scale},
+            'exchange_bytes_per_layer_per_rank': {'partials_pushed': int(exch), 'transformed_rows_received': int(exch),
+                                                  'note': 'fp32; SURVEY.md §8d counted 2.46 GB for an all-gather of ALL N rows — only the item side crosses NVLink here'},
+            'roofline': roof, 'parity': parity, 'gpu_launches': launches,
+            'e2e': {'value': msgs / (ms * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                    'note': 'the batch ids are resident; configs[2] carries the host-fed leg'}}
+
+
+def g5_batch_pairs(nU_v, nI, E_v, pick, dev):
+    """(user index, item index) of `pick` interactions of virtual shard 0 — regenerated, so that every rank knows the same batch"""
+    u, i, _ = g5_shard_edges(0, nU_v, nI, E_v, dev)
+    return u[pick], i[pick]
+
+
+def g5_rank_one_check(model, sh, dist, dev, nI, d, L_, uid, iid):
+    from deeprecommendation_b200.peer import forward_peer
+    import torch.distributed as tdist
+    eye = torch.eye(d, device=dev)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    for k in sd:
+        if k.startswith(('item_embeddings', 'user_embeddings', 'gnn_convs')):
+            sd[k] = eye.clone() if k.endswith('weight') else torch.zeros_like(sd[k])
+    model.load_state_dict(sd)
+    g = torch.Generator(device=dev).manual_seed(31)
+    v = torch.randn(d, device=dev, generator=g)
+    s_items = torch.rand(nI, device=dev, generator=g, dtype=torch.float64) + 0.5            # same on every rank
+    s_users = torch.rand(sh.users_rows, device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(900 + sh.rank)) + 0.5
+    keep_feat = (sh.item_features_own, sh.user_features_own)
+    sh.item_features_own = (s_items[sh.it_r0: sh.it_r0 + sh.it_rows, None] * v.double()).float()
+    sh.user_features_own = (s_users[:, None] * v.double()).float()
+    keep = {}
+    try:
+        with torch.no_grad():
+            forward_peer(model, sh, uid, iid, keep)
+        torch.cuda.synchronize()
+        sh.check()
+    finally:
+        sh.item_features_own, sh.user_features_own = keep_feat
+    # float64 recurrence with torch ops: s' = dinv ∘ (A_w (dinv ∘ s)) per node type; item rows are sums over ALL ranks' users
+    iu, ii = sh.index_users, sh.index_items
+    rows_u = torch.repeat_interleave(torch.arange(sh.users_rows, device=dev), (iu.row_ptr[1:] - iu.row_ptr[:-1]).long())
+    rows_i = torch.repeat_interleave(torch.arange(nI, device=dev), (ii.row_ptr[1:] - ii.row_ptr[:-1]).long())
+    du, di = sh.dinv_users.double(), sh.dinv_items_all.double()
+    acc_u, acc_i = s_users.clone(), s_items.clone()
+    su, si = s_users, s_items
+    for _ in range(L_):
+        nu = torch.zeros(sh.users_rows, dtype=torch.float64, device=dev).index_add_(0, rows_u, iu.w.double() * (di * si)[iu.col.long()]) * du
+        part = torch.zeros(nI, dtype=torch.float64, device=dev).index_add_(0, rows_i, ii.w.double() * (du * su)[ii.col.long()])
+        if dist is not None:
+            tdist.all_reduce(part)
+        su, si = nu, part * di
+        acc_u, acc_i = acc_u + su, acc_i + si
+    acc_u, acc_i = acc_u / (L_ + 1), acc_i / (L_ + 1)
+    want_u = acc_u[:, None] * v.double()
+    want_i = acc_i[sh.it_r0: sh.it_r0 + sh.it_rows, None] * v.double()
+    den = max(float(want_u.abs().max()), float(want_i.abs().max()))
+    err = max(float((keep['users'].double() - want_u).abs().max()), float((keep['items'].double() - want_i).abs().max()) if sh.it_rows else 0.0) / den
+    err = _max_over_ranks(dist, err, dev)
+    return {'max_rel': err, 'tolerance': 1e-5, 'ok': bool(err <= 1e-5), 'rows_checked': 'every owned user and item row of every rank (max over ranks)',
+            'vs': 'float64 torch SpMV recurrence s_{l+1} = D^-1/2 A_w D^-1/2 s_l on rank-one features with identity transforms (size-independent linearity property)'}
+
+
 PARALLELISM = {
     'peer': 'users 1-D nnz-partitioned over {P} GPUs, item rows in {P} equal ranges; no library collective on the data path: K3 pushes partial item rows '
             'into the owner\'s receive slot over NVLink (reduce-scatter fused into the SpMM epilogue), slots summed in rank order, K1c writes the '
@@ -1154,6 +1331,13 @@ def graph_leg(args, dev, rank, world, dist, peaks):
              'roofline': r['roofline'],
              'e2e': {'value': msgs / (r['e2e_ms'] * 1e-3), 'unit': 'edges/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
              'gpu_launches': r['launches']}
+    if r.get('trace'):
+        traces = [None] * world
+        if dist is not None:
+            dist.all_gather_object(traces, r['trace'])
+        else:
+            traces = [r['trace']]
+        entry['device_trace_us'] = {f'rank{q}': t for q, t in enumerate(traces)}
     if r.get('train'):
         t = r['train']
         entry['train_step'] = ({'value': 2.0 * w['E'] * w['L'] / (t['ms'] * 1e-3), 'unit': 'edges/s', 'ms_per_step': t['ms'], 'steps': t['steps'],
@@ -1205,7 +1389,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs', 'k3hbm', 'k2hbm'])
+    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs', 'k3hbm', 'k2hbm', 'graph5'])
+    ap.add_argument('--graph5-scale', type=float, default=1.0, help='configs[4] at a fraction of its size (users, items and edges scaled together)')
     ap.add_argument('--graph-scale', type=float, default=1.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
@@ -1363,6 +1548,12 @@ def main():
             also.append(run_k2_hbm_regime(dev, peaks))
         except Exception as e:
             also.append({'metric': 'K2 HBM regime', 'error': repr(e)[:300]})
+    if args.workload == 'graph5' or (args.workload == 'all' and world == 8):       # configs[4] names 8 GPUs; other sizes on request
+        try:
+            also.append(run_graph5(args, dev, rank, world, dist, peaks, args.graph5_scale))
+        except Exception as e:
+            also.append({'metric': 'GNN propagation directed-edge messages/sec (GraphNCF fwd, configs[4])', 'error': repr(e)[:400]})
+        torch.cuda.empty_cache()
     graph_scaling = None
     if args.workload in ('all', 'graph'):                  # LAST, so that the tail of the line carries the strong-scaling leg
         with ClockSampler(local) as gclocks:

@@ -136,6 +136,10 @@ __global__ void __launch_bounds__(256) peer_gather_rows_kernel(const float* __re
   }
 }
 
+// device-side tracing: one thread writes %globaltimer (ns) — a marker between the kernels of a captured forward, so that the phases of a
+// rank (and the time it spends waiting for its peers) can be read back after a CUDA-graph replay
+__global__ void device_timestamp_kernel(unsigned long long* slot) { *slot = globaltimer_ns(); }
+
 static int fill_ptrs(PeerPtrs& out, void* const* in, int n, const char* what) {
   if (n <= 0 || n > PEER_MAX || !in) return b200rec_fail(B200REC_ERR_BAD_ARG, what);
   for (int q = 0; q < PEER_MAX; ++q) out.p[q] = q < n ? in[q] : nullptr;
@@ -245,6 +249,13 @@ extern "C" int b200rec_peer_gather_rows(const float* table, int64_t ld, int64_t 
   const int grid = (int)((n_ids * 32 + 255) / 256);
   peer_gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table, ld, row0, rows, reinterpret_cast<const long long*>(ids), (int)n_ids, d / 4,
                                                                   scale, pp, n_dst, dst_offset, ld_dst);
+  B200REC_CHECK_LAUNCH();
+  return B200REC_OK;
+}
+
+extern "C" int b200rec_device_timestamp(uint64_t* slot, b200rec_stream_t stream) {
+  if (!slot) return b200rec_fail(B200REC_ERR_BAD_ARG, "device_timestamp: null slot");
+  device_timestamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(slot));
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }

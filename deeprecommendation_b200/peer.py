@@ -45,6 +45,7 @@ _OFF_ERR = _OFF_COUNTERS + 2 * L.PEER_CHANNELS * 4
 WAIT_TIMEOUT_NS = 10_000_000_000
 # the item side of a layer (wait for the partials, slot reduction, transform + broadcast) runs on a second stream under the user-row SpMM
 OVERLAP = os.environ.get('B200REC_PEER_OVERLAP', '1') == '1'
+TRACE = os.environ.get('B200REC_PEER_TRACE', '0') == '1'
 
 
 class _Raw:
@@ -232,6 +233,31 @@ class PeerShard:
             L.check(L.lib().b200rec_peer_gather_rows(_ptr(table) if rows else None, d, row0, rows, _ptr(ids), ids.numel(), d, float(scale), dst,
                                                     self.world, dst_row * d, d, _stream()), 'peer_gather_rows')
 
+    # ---- device-side trace (B200REC_PEER_TRACE=1): %globaltimer markers between the kernels of a forward, readable after a graph replay
+    def stamp(self, tag):
+        if not TRACE:
+            return
+        if getattr(self, '_trace_buf', None) is None:
+            self._trace_buf = torch.zeros(256, dtype=torch.int64, device=self.device)
+            self._trace_tags = []
+        if self._trace_reset:
+            self._trace_tags, self._trace_reset = [], False
+        k = len(self._trace_tags)
+        if k >= 256:
+            return
+        self._trace_tags.append(tag)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().b200rec_device_timestamp(C.c_void_p(self._trace_buf.data_ptr() + 8 * k), _stream()), 'device_timestamp')
+
+    _trace_reset = True
+
+    def trace(self):
+        """[(tag, microseconds since the first marker)] of the last forward (after a synchronize)"""
+        if getattr(self, '_trace_buf', None) is None:
+            return []
+        t = self._trace_buf[:len(self._trace_tags)].cpu().tolist()
+        return [(tag, round((x - t[0]) / 1e3, 1)) for tag, x in zip(self._trace_tags, t)]
+
     def side_stream(self):
         if getattr(self, '_side', None) is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -310,6 +336,8 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
     nu, ni = sh.users_rows, sh.it_rows
     iid, uid = itemIds.long().contiguous(), userIds.long().contiguous()
     empty = lambda n: torch.empty((n, d), dtype=torch.float32, device=dev)
+    sh._trace_reset = True
+    sh.stamp('start')
     x0_items = ops.linear_raw(sh.item_features_own, ie.weight, ie.bias) if ni else empty(0)
     x0_users = ops.linear_raw(sh.user_features_own, ue.weight, ue.bias) if nu else empty(0)
     acc_items, acc_users = x0_items, x0_users
@@ -331,18 +359,23 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
         joined = None
 
         def item_side(l, par, last, scale):                                          # C_l: needs every rank's A_l, nothing of B_l
+            sh.stamp(f'C{l} begin')
             sh.wait(CH_A0 + par)
+            sh.stamp(f'C{l} partials arrived')
             sh.reduce(par, d, x_next=None if last else xi_next, acc_in=x0_items if l == 0 else acc_items, acc_out=acc_items, acc_scale=scale)
             if not last:
                 sh.push_transform(xi_next, lin_i, 1 - par, t_dtype)
                 sh.signal(CH_T0 + (1 - par))
+            sh.stamp(f'C{l} end')
 
         for l in range(L_):
             par, last = l & 1, l == L_ - 1
             scale = 1.0 / (L_ + 1) if last else 1.0
+            sh.stamp(f'A{l} begin')
             if nu:                                                                   # A_l: partial item rows -> owners' receive slots
                 ops.propagate_step(sh.index_items, t_users, dinv=sh.dinv_items_all, push=sh.push_spec(par, d))
             sh.signal(CH_A0 + par)
+            sh.stamp(f'A{l} end')
             if side is not None:
                 forked = torch.cuda.Event()
                 forked.record(main)
@@ -354,16 +387,19 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
                     joined = torch.cuda.Event()
                     joined.record(side)
             sh.wait(CH_T0 + par)
+            sh.stamp(f'B{l} table arrived')
             if nu:                                                                   # B_l: own user rows from the gathered table
                 ops.propagate_step(sh.index_users, sh.table(par, d, t_dtype), dinv=sh.dinv_users, x_next=None if last else spare_u,
                                    acc_in=x0_users if l == 0 else acc_users, acc_out=acc_users, acc_scale=scale)
             if side is None:
                 yield
                 item_side(l, par, last, scale)
+            sh.stamp(f'B{l} end')
             if not last and nu:
                 ops.linear_raw(spare_u, lin_u.weight, lin_u.bias, row_scale=sh.dinv_users, out=t_users[:nu])
         if joined is not None:
             main.wait_event(joined)
+        sh.stamp('layers joined')
     if keep is not None:                        # tests: the owned rows of the combined embedding
         keep['items'], keep['users'] = acc_items, acc_users
     sh.gather_rows(acc_items, sh.it_r0, ni, iid, 0, d)
@@ -371,11 +407,13 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
     sh.signal(CH_R)
     yield
     sh.wait(CH_R)
+    sh.stamp('batch rows arrived')
     rows = sh.rows_view(2 * B, d)
     if model.MLP is None:
         out = ops.rowdot(rows[B:], rows[:B])
     else:
         out = run_mlp(model.MLP, rows[:B], rows[B:], training=False)               # item first (gnn_ncf.py:361)
+    sh.stamp('end')
     if L_ == 0:                                 # no layer barrier protected `rows` against the next call's writers
         sh.signal(CH_E)
         yield

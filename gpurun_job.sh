@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gemm_tc_gpu.py -x -q -m gpu > gpurun_out/test_gemm.log 2>&1; echo "gemm tests rc=$?"
-tail -8 gpurun_out/test_gemm.log
-timeout 600 python tools/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemm bench rc=$?"
-grep -E "94|96" gpurun_out/gemm_bench.log | head -20
+timeout 600 python -m pytest tests/test_peer_gpu.py -x -q -m gpu > gpurun_out/test_peer.log 2>&1; echo "peer tests rc=$?"
+tail -5 gpurun_out/test_peer.log
+timeout 600 python bench.py --workload graph5 --graph5-scale 0.004 --steps 5 > gpurun_out/bench_graph5_small_n1.json 2> gpurun_out/bench_graph5_small_n1.err; echo "graph5 small rc=$?"
+tail -c 1500 gpurun_out/bench_graph5_small_n1.json; tail -5 gpurun_out/bench_graph5_small_n1.err

@@ -416,6 +416,9 @@ int b200rec_peer_push_rows(const float* src, int64_t ld_src, int64_t rows, int d
 int b200rec_peer_gather_rows(const float* table, int64_t ld, int64_t row0, int64_t rows, const int64_t* ids, int64_t n_ids, int d,
                              float scale, void* const* dst, int n_dst, int64_t dst_offset, int64_t ld_dst, b200rec_stream_t stream);
 
+/* tracing aid: *slot = %globaltimer (ns) when the stream reaches this point (one 1-thread kernel; usable inside a captured graph) */
+int b200rec_device_timestamp(uint64_t* slot, b200rec_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,3 +148,52 @@ def test_peer_two_processes_share_one_gpu_over_cuda_ipc():
     assert r.returncode == 0 and lines, (r.returncode, r.stdout[-2000:], r.stderr[-3000:])
     res = json.loads(lines[-1])
     assert res['ok'] and res['world'] == 2, res
+
+
+def test_sharded_build_equals_shard_cut_from_the_full_index():
+    """sharded.create_graph_local / shard_from_local (a rank sees only ITS users' interactions; item statistics made global by a
+    reduction) against peer.shard_from_full (cut out of the full index): same CSR slices, weights, deg^-1/2 — and the same forward."""
+    from deeprecommendation_b200.graph import IdTable, create_graph, get_index
+    from deeprecommendation_b200.neural_collaborative_filtering.models import GraphNCF
+    from deeprecommendation_b200.parallel import RowPartition, split_rows
+    from deeprecommendation_b200.peer import PeerArena, PeerShard, _rows_per_part, emulated_shards, forward_emulated
+    from deeprecommendation_b200.sharded import create_graph_local, shard_from_local
+    n_users, n_items, n, F, d, P = 2000, 700, 80_000, 64, 64, 4
+    users, items, ratings = synth.interactions_zipf(n_users, n_items, n, seed=17)
+    order = np.argsort(users, kind='stable')                   # interactions grouped by user (a rank's file holds its users' rows)
+    users, items, ratings = users[order], items[order], ratings[order]
+    rng = np.random.default_rng(3)
+    fi, fu = rng.standard_normal((n_items, F)).astype(np.float32), rng.standard_normal((n_users, F)).astype(np.float32)
+    tu, ti, tr = torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), torch.from_numpy(ratings).to(DEV)
+    g = create_graph(tu, ti, tr, torch.from_numpy(fi).to(DEV), torch.from_numpy(fu).to(DEV), IdTable(torch.arange(n_users, device=DEV)),
+                     IdTable(torch.arange(n_items, device=DEV)))
+    full = get_index(g)
+    ref_shards = emulated_shards(g, P, d_max=d, batch_max=512)
+    # the same user ranges, built rank by rank from the rank's own interactions
+    glob = {'cnt': torch.bincount(ti, minlength=n_items).int(), 'sum': torch.zeros(n_items, dtype=torch.float64, device=DEV).index_add_(0, ti, tr.double()),
+            'deg': full.deg[:n_items].clone()}
+    reduce_items = lambda t, what: t.copy_(glob[what])
+    arenas = PeerArena.emulated(PeerShard.layout(P, _rows_per_part(n_items, P), d, 512)['total'], P, DEV)
+    shards = []
+    for q, ref in enumerate(ref_shards):
+        mine = (tu >= ref.users_r0) & (tu < ref.users_r0 + ref.users_rows)
+        gl = create_graph_local(tu[mine] - ref.users_r0, ti[mine], tr[mine], ref.users_rows, n_items, g.item_features,
+                                g.user_features[ref.users_r0: ref.users_r0 + ref.users_rows], reduce_items)
+        sh = shard_from_local(gl, rank=q, world=P, nI=n_items, nU=n_users, users_r0=ref.users_r0, arena=arenas[q], d_max=d, batch_max=512,
+                              reduce_items=reduce_items, edges_total=full.e1 + full.e2)
+        for a, b in ((sh.index_users, ref.index_users), (sh.index_items, ref.index_items)):
+            assert torch.equal(a.row_ptr, b.row_ptr) and torch.equal(a.col, b.col) and torch.equal(a.w, b.w)
+        assert torch.equal(sh.dinv_users, ref.dinv_users) and torch.equal(sh.dinv_items_all, ref.dinv_items_all)
+        shards.append(sh)
+    kw = dict(item_dim=F, user_dim=F, num_gnn_layers=3, hetero=True, node_emb=d, mlp_dense_layers=[128], dropout_rate=0.2)
+    m = GraphNCF(**kw).to(DEV).eval()
+    m.load_state_dict(synth.to_torch(synth.graph_ncf_weights(seed=3, **kw)))
+    pick = rng.permutation(n)[:300]
+    uid, iid = g.user2item_edge_index[0][pick].contiguous(), g.user2item_edge_index[1][pick].contiguous()
+    with torch.no_grad():
+        ref_out = m(g, uid, iid, DEV)
+        outs = forward_emulated(m, shards, uid, iid)
+    torch.cuda.synchronize()
+    for sh, o in zip(shards, outs):
+        sh.check()
+        assert maxnorm_rel(o, ref_out) < 1e-6
