@@ -1292,6 +1292,90 @@ def g5_rank_one_check(model, sh, dist, dev, nI, d, L_, uid, iid):
             'vs': 'float64 torch SpMV recurrence s_{l+1} = D^-1/2 A_w D^-1/2 s_l on rank-one features with identity transforms (size-independent linearity property)'}
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# workload F — configs[3] IN FULL: every (user, item) pair of 10^6 users x 10^5 items scored, top-10 per user, users sharded over the ranks
+# ----------------------------------------------------------------------------------------------------------------------
+APF_USERS, APF_ITEMS = 1_000_000, 100_000
+
+
+def run_allpairs_full(args, dev, rank, world, dist, peaks, n_users_total=APF_USERS):
+    """The serving pattern of src/webapp/backend.py:96-99,113-121 for the whole user base: per rank its share of the users (125 k at 8 GPUs)
+    against the whole catalogue, both MLP variants ([256,128] and [256]), fp32-tolerance and bf16 operands.  Timed per variant, wall clock on the
+    device, max over ranks: user + item projections (K1a), all-pairs MLP + top-k (K5), top-k lists copied to the host.  Nothing is extrapolated."""
+    from deeprecommendation_b200 import synth
+    from deeprecommendation_b200.neural_collaborative_filtering.models import BasicNCF
+    from oracle import restatement as R
+    n_users = n_users_total // world
+    g = torch.Generator(device=dev).manual_seed(4000 + rank)
+
+    def profiles(n, gen):
+        x = torch.rand(n, F, device=dev, generator=gen)
+        x[:, :966] = (x[:, :966] < 0.01).float()
+        return x
+    items = profiles(APF_ITEMS, torch.Generator(device=dev).manual_seed(4999))          # the catalogue is the same on every rank
+    users = (profiles(n_users, g) - 0.3) * 0.1
+    out = {'metric': f'scored user-item pairs/sec (BasicNCF all-pairs + top-{AP_K}, configs[3] in full)', 'unit': 'pairs/s', 'n_gpus': world, 'scaling': 'strong',
+           'config': {'workload': f'configs[3]: {n_users_total} users x {APF_ITEMS} items = {n_users_total * APF_ITEMS:.3g} pairs, top-{AP_K} per user, '
+                                  f'F={F} dense profiles on both sides; {n_users} users per GPU, catalogue replicated, no collective',
+                      'l2': 'user profiles 1 GB, item profiles 0.84 GB, item tables 102 MB per GPU'},
+           'variants': {}}
+    pairs_total = float(n_users) * APF_ITEMS * world
+    for mlp in ([256, 128], [256]):
+        kw = dict(item_dim=F, user_dim=F, item_emb=128, user_emb=128, mlp_dense_layers=mlp, dropout_rate=0.2)
+        sd = synth.to_torch(synth.basic_ncf_weights(seed=1, **kw))
+        model = BasicNCF(**kw).to(dev).eval()
+        model.load_state_dict(sd)
+        for precision, tol in (('fp32', 1e-5), ('bf16', 1e-2)):
+            model.recommend(users[:4736], items, k=AP_K, precision=precision)              # warm-up: packs, caches, lazy inits
+            _barrier(dist)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            val, idx = model.recommend(users, items, k=AP_K, precision=precision)
+            val_h, idx_h = val.cpu(), idx.cpu()                                            # the top-k lists leave the device inside the timed region
+            b.record()
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ms = _max_over_ranks(dist, a.elapsed_time(b), dev)
+            wall_ms = _max_over_ranks(dist, wall_ms, dev)
+            ent = {'ms_total': round(ms, 2), 'wall_ms_total': round(wall_ms, 2), 'value': pairs_total / (ms * 1e-3),
+                   'd2h_bytes': int(val_h.numel() * 4 + idx_h.numel() * 8)}
+            if rank == 0:
+                # sampled users against the oracle on a sub-grid + the selection against a stable sort of the kernel's own scores over ALL items
+                su = torch.arange(0, n_users, max(1, n_users // 16), device=dev)[:16]
+                v2, i2, sc = model.recommend(users[su], items, k=AP_K, precision=precision, return_scores=True)
+                ref = R.basic_ncf_all_pairs(sd, users[su].cpu(), items[:2000].cpu())
+                ent['parity'] = _parity(sc[:, :2000], ref, 'oracle/restatement.py::basic_ncf_all_pairs, 16 sampled users x 2000 items', tol)
+                sv, si = R.topk_stable(sc.cpu(), AP_K)
+                ent['parity']['topk_of_the_full_run_equals_stable_sort'] = bool(torch.equal(idx_h[su.cpu()], si) and torch.equal(val_h[su.cpu()], sv))
+                # full-catalogue error figure of this arithmetic mode: the same 16 users x ALL items in float64 on the device
+                w64 = {k: v.to(dev).double() for k, v in sd.items()}
+                ue = users[su].double() @ w64['user_embeddings.0.weight'].T + w64['user_embeddings.0.bias']
+                ie = items.double() @ w64['item_embeddings.0.weight'].T + w64['item_embeddings.0.bias']
+                keys = sorted({int(k.split('.')[1]) for k in w64 if k.startswith('MLP.')})
+                worst = 0.0
+                for r0 in range(0, su.numel(), 4):                                         # 4 users x 100 k items x 256 doubles = 0.8 GB at a time
+                    h = torch.cat((ue[r0:r0 + 4, None, :].expand(-1, APF_ITEMS, -1), ie[None].expand(min(4, su.numel() - r0), -1, -1)), 2)
+                    for q, kk in enumerate(keys):
+                        h = h @ w64[f'MLP.{kk}.weight'].T + w64[f'MLP.{kk}.bias']
+                        if q < len(keys) - 1:
+                            h = h.relu()
+                    worst = max(worst, float((sc[r0:r0 + 4].double() - h[..., 0]).abs().max() / h.abs().max()))
+                    del h
+                ent['full_catalogue_error'] = {'max_rel': worst, 'tolerance': tol, 'ok': bool(worst <= tol),
+                                               'vs': 'float64 torch evaluation of the same forward on the device, 16 users x all 100k items'}
+                del sc, ue, ie, w64
+            out['variants'][f'mlp{mlp}_{precision}'] = ent
+            del val, idx
+        del model
+    head = out['variants']['mlp[256, 128]_fp32']
+    out.update({'value': head['value'], 'ms_total': head['ms_total'], 'dtype': 'f32',
+                'note': 'headline = MLP [256,128], fp32-tolerance operands; `variants` carries [256] and the bf16 modes; every figure is a full run'})
+    del users, items
+    torch.cuda.empty_cache()
+    return out
+
+
 PARALLELISM = {
     'peer': 'users 1-D nnz-partitioned over {P} GPUs, item rows in {P} equal ranges; no library collective on the data path: K3 pushes partial item rows '
             'into the owner\'s receive slot over NVLink (reduce-scatter fused into the SpMM epilogue), slots summed in rank order, K1c writes the '
@@ -1389,7 +1473,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs', 'k3hbm', 'k2hbm', 'graph5'])
+    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs', 'k3hbm', 'k2hbm', 'graph5', 'allpairs_full'])
+    ap.add_argument('--allpairs-users', type=int, default=APF_USERS, help='total users of the configs[3] full run (default 10^6)')
     ap.add_argument('--graph5-scale', type=float, default=1.0, help='configs[4] at a fraction of its size (users, items and edges scaled together)')
     ap.add_argument('--graph-scale', type=float, default=1.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -1548,6 +1633,12 @@ def main():
             also.append(run_k2_hbm_regime(dev, peaks))
         except Exception as e:
             also.append({'metric': 'K2 HBM regime', 'error': repr(e)[:300]})
+    if args.workload == 'allpairs_full' or (args.workload == 'all' and world == 8):  # configs[3] names 8 GPUs; other sizes on request
+        try:
+            also.append(run_allpairs_full(args, dev, rank, world, dist, peaks, args.allpairs_users))
+        except Exception as e:
+            also.append({'metric': 'scored user-item pairs/sec (BasicNCF all-pairs, configs[3] in full)', 'error': repr(e)[:400]})
+        torch.cuda.empty_cache()
     if args.workload == 'graph5' or (args.workload == 'all' and world == 8):       # configs[4] names 8 GPUs; other sizes on request
         try:
             also.append(run_graph5(args, dev, rank, world, dist, peaks, args.graph5_scale))
