@@ -200,11 +200,12 @@ class PeerShard:
                                                _ptr(acc_in), _ptr(acc_out), d, float(acc_scale), _stream()), 'peer_reduce')
 
     def push_transform(self, x, lin, par, t_dtype):
-        """T[par][it_r0 : it_r0 + rows] = dinv ∘ (W x + b) on EVERY rank — K1c with the all-gather in its epilogue"""
+        """T[par][it_r0 : it_r0 + rows] = dinv ∘ (W x + b) on EVERY rank — K1c with the all-gather in its epilogue.
+        `lin` = a Linear module or a (weight, bias) pair."""
         M, K = x.shape
         if M == 0:
             return
-        w, b = lin.weight, lin.bias
+        w, b = lin if isinstance(lin, tuple) else (lin.weight, lin.bias)
         N = w.shape[0]
         esz = 2 if t_dtype == torch.bfloat16 else 4
         dst = self.arena.ptrs(self.off[f'T{par}'], first=self.rank)
@@ -338,9 +339,17 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
     empty = lambda n: torch.empty((n, d), dtype=torch.float32, device=dev)
     sh._trace_reset = True
     sh.stamp('start')
-    x0_items = ops.linear_raw(sh.item_features_own, ie.weight, ie.bias) if ni else empty(0)
-    x0_users = ops.linear_raw(sh.user_features_own, ue.weight, ue.bias) if nu else empty(0)
+    x0_items, x0_users = empty(ni), empty(nu)
+
+    def embed():                                                                     # x0 = node embeddings of the owned rows (:300-301)
+        if ni:
+            ops.linear_raw(sh.item_features_own, ie.weight, ie.bias, out=x0_items)
+        if nu:
+            ops.linear_raw(sh.user_features_own, ue.weight, ue.bias, out=x0_users)
+
     acc_items, acc_users = x0_items, x0_users
+    if L_ == 0:
+        embed()
     if L_ > 0:
         lin_u, lin_i, _ = model.gnn_convs[0].typed()
         if model.message_dtype not in ('fp32', 'bf16'):
@@ -350,13 +359,32 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
         acc_users, acc_items = empty(nu), empty(ni)
         spare_u = empty(nu) if L_ > 1 else None
         xi_next = empty(ni) if L_ > 1 else None
-        sh.push_transform(x0_items, lin_i, 0, t_dtype)
-        sh.signal(CH_T0)
-        if nu:
-            ops.linear_raw(x0_users, lin_u.weight, lin_u.bias, row_scale=sh.dinv_users, out=t_users[:nu])
         main = torch.cuda.current_stream(dev)
         side = sh.side_stream() if OVERLAP else None
         joined = None
+        # Layer 0's messages straight from the node features: t0 = dinv ∘ (W_t (W_e f + b_e) + b_t) = dinv ∘ ((W_t W_e) f + (W_t b_e + b_t)) — composite
+        # weights formed once per weight version in float64.  So the first SpMM waits for ONE transform only; the embeddings x0 (needed from the
+        # first running-mean update on) and the broadcast of the item messages run on the side stream underneath it.
+        (Wci, bci), (Wcu, bcu) = _layer0_composites(model, ie, ue, lin_i, lin_u)
+        if nu:
+            ops.linear_raw(sh.user_features_own, Wcu, bcu, row_scale=sh.dinv_users, out=t_users[:nu])
+
+        def layer0_side():
+            sh.push_transform(sh.item_features_own, (Wci, bci), 0, t_dtype)
+            sh.signal(CH_T0)
+            embed()
+
+        x0_ready = None
+        if side is not None:
+            start = torch.cuda.Event()
+            start.record(main)
+            side.wait_event(start)
+            with torch.cuda.stream(side):
+                layer0_side()
+                x0_ready = torch.cuda.Event()
+                x0_ready.record(side)
+        else:
+            layer0_side()
 
         def item_side(l, par, last, scale):                                          # C_l: needs every rank's A_l, nothing of B_l
             sh.stamp(f'C{l} begin')
@@ -387,6 +415,8 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
                     joined = torch.cuda.Event()
                     joined.record(side)
             sh.wait(CH_T0 + par)
+            if l == 0 and x0_ready is not None:
+                main.wait_event(x0_ready)                                            # x0_users is B_0's running-mean input
             sh.stamp(f'B{l} table arrived')
             if nu:                                                                   # B_l: own user rows from the gathered table
                 ops.propagate_step(sh.index_users, sh.table(par, d, t_dtype), dinv=sh.dinv_users, x_next=None if last else spare_u,
@@ -418,6 +448,27 @@ def _steps(model, sh: PeerShard, userIds, itemIds, keep=None):
         sh.signal(CH_E)
         yield
         sh.wait(CH_E)
+    return out
+
+
+def _layer0_composites(model, ie, ue, lin_i, lin_u):
+    """((W_i2u·W_item, W_i2u·b_item + b_i2u), (W_u2i·W_user, W_u2i·b_user + b_u2i)) as cached fp32 tensors (float64 products, rounded once)"""
+    ps = (ie.weight, ie.bias, ue.weight, ue.bias, lin_i.weight, lin_i.bias, lin_u.weight, lin_u.bias)
+    key = tuple((p.data_ptr(), p._version) for p in ps if p is not None)
+    hit = getattr(model, '_peer_layer0', None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+
+    def comp(lin, emb):
+        w = (lin.weight.detach().double() @ emb.weight.detach().double()).float().contiguous()
+        eb = emb.bias.detach().double() if emb.bias is not None else torch.zeros(emb.weight.shape[0], dtype=torch.float64, device=w.device)
+        b = lin.weight.detach().double() @ eb
+        if lin.bias is not None:
+            b = b + lin.bias.detach().double()
+        return w, b.float().contiguous()
+
+    out = (comp(lin_i, ie), comp(lin_u, ue))
+    object.__setattr__(model, '_peer_layer0', (key, out))
     return out
 
 
