@@ -222,11 +222,12 @@ class PeerShard:
         local = self.table(par, N, t_dtype)[self.it_r0: self.it_r0 + M]
         ops.linear_raw(x, w, b, row_scale=self.dinv_items_own, out=local)
         if self.world > 1:
-            if esz != 4:
-                raise NotImplementedError('bf16 messages on the peer path need node_emb in {32, 64, 96, 128}')
+            if (N * esz) % 16:
+                raise NotImplementedError('the peer path needs rows of the message table that are multiples of 16 bytes')
+            n32 = N * esz // 4                          # the copy kernel moves 128-bit words: a bf16 row is N/2 32-bit columns
             others = (C.c_void_p * (self.world - 1))(*[self.arena.bases[q] + self.off[f'T{par}'] for q in range(self.world) if q != self.rank])
             with torch.cuda.device(self.device):
-                L.check(L.lib().b200rec_peer_push_rows(_ptr(local), N, M, N, others, self.world - 1, y_off, N, _stream()), 'peer_push_rows')
+                L.check(L.lib().b200rec_peer_push_rows(_ptr(local), n32, M, n32, others, self.world - 1, self.it_r0 * n32, n32, _stream()), 'peer_push_rows')
 
     def gather_rows(self, table, row0, rows, ids, dst_row, d, scale=1.0):
         dst = self.arena.ptrs(self.off['rows'])
