@@ -92,6 +92,8 @@ SIGNATURES = {
     'b200rec_allpairs_splits': (c_int, [c_i64, c_i64, c_int]),
     'b200rec_allpairs_workspace': (c_sz, [c_i64, c_int, c_int]),
     'b200rec_allpairs_topk': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'b200rec_allpairs_relu_dot_splits': (c_int, [c_i64, c_i64]),
+    'b200rec_allpairs_relu_dot_topk': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_f, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'b200rec_topk_rows': (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),
     'b200rec_attention_pool_workspace': (c_sz, [c_i64, c_i64, c_int, c_int]),
     'b200rec_attention_pool_workspace_csr': (c_sz, [c_i64, c_i64, c_int, c_i64, c_i64]),

@@ -541,6 +541,148 @@ allpairs_merge_kernel(const float* __restrict__ part_val, const int* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// One-hidden-layer MLPs ([256] — train_model.py:41, the reference's fixed-profile experiments) in all-pairs mode degenerate to
+//     score(u, i) = b2 + sum_h w2[h] * ReLU(a_u[h] + b_i[h])                     (~3·H1 FP32 operations per pair, NO GEMM)
+// Through the tensor-core kernel above this costs a 2-row MMA per tile and the bf16 hi/lo split of BOTH operands of the only dot
+// product there is (measured 1.1e-5 at F = 2094: over the fp32 budget).  Here it runs where it belongs, on the FP32 pipes, exactly:
+// CTA = 64 users x 128-item tiles, a thread owns 4 users x 8 items = 32 accumulators and walks h through shared memory
+// (user rows resident, item tile transposed to h-major so that a warp's 16 item columns are conflict-free); per h and pair one FADD,
+// one FMNMX, one FFMA.  Same top-k epilogue / split lists / merge kernel as the tensor-core path.
+constexpr int RD_UT = 64, RD_IT = 128, RD_HC = 64, RD_THREADS = 256;
+
+struct ReluDotParams {
+  const float* A; const float* B; const float* w2; float b2;
+  int nU, nI, H1;
+  int k, n_splits, items_per_split;
+  float* part_val; int* part_idx;
+  float* scores; long long lds;
+  const int* seen_ptr; const int* seen_idx;
+};
+
+__global__ void __launch_bounds__(RD_THREADS, 1)
+allpairs_relu_dot_kernel(const ReluDotParams p) {
+  extern __shared__ __align__(16) unsigned char rd_smem[];
+  float* sA = reinterpret_cast<float*>(rd_smem);                       // [RD_UT][H1]
+  float* sW = sA + RD_UT * p.H1;                                        // [H1]
+  float* sB = sW + p.H1;                                                // [2][RD_HC][RD_IT]  (h-major)
+  float* sS = sB + 2 * RD_HC * RD_IT;                                   // [RD_UT][RD_IT] scores of the current tile
+  float* sm_lv = sS + RD_UT * RD_IT;                                    // [RD_UT][AP_KMAX]
+  int* sm_li = reinterpret_cast<int*>(sm_lv + RD_UT * AP_KMAX);
+  float* sm_thr = reinterpret_cast<float*>(sm_li + RD_UT * AP_KMAX);    // [RD_UT]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;                               // users ty + 16 q, items tx + 16 j
+  const int u0 = blockIdx.x * RD_UT;
+  const int users_here = min(RD_UT, p.nU - u0);
+  const int i_begin = blockIdx.y * p.items_per_split, i_end = min(p.nI, i_begin + p.items_per_split);
+  const int H1 = p.H1, n_hc = H1 / RD_HC;
+  for (int i = tid; i < RD_UT * H1 / 4; i += RD_THREADS) {              // user rows (zero rows beyond the last user)
+    const int r = (i * 4) / H1, c = (i * 4) % H1;
+    reinterpret_cast<float4*>(sA)[i] = r < users_here ? __ldg(reinterpret_cast<const float4*>(p.A + (long long)(u0 + r) * H1 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = tid; i < H1; i += RD_THREADS) sW[i] = __ldg(p.w2 + i);
+  for (int i = tid; i < RD_UT * AP_KMAX; i += RD_THREADS) { sm_lv[i] = -INFINITY; sm_li[i] = -1; }
+  if (tid < RD_UT) sm_thr[tid] = -INFINITY;
+  __syncthreads();
+  const int n_it = (i_end - i_begin + RD_IT - 1) / RD_IT;
+  // item-tile chunk (RD_IT items x RD_HC h) global -> registers -> transposed shared memory: thread = (item = tid / 2 [+0], 32 h)
+  const int l_item = tid >> 1, l_h0 = (tid & 1) * 32;
+  float4 pre[8];
+  auto load_chunk = [&](int it, int hc) {
+    const int item = min(i_begin + it * RD_IT + l_item, p.nI - 1);
+    const float* src = p.B + (long long)item * H1 + hc * RD_HC + l_h0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) pre[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
+  };
+  auto store_chunk = [&](int buf) {
+    float* dst = sB + buf * RD_HC * RD_IT;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int h = l_h0 + 4 * q;
+      dst[(h + 0) * RD_IT + l_item] = pre[q].x; dst[(h + 1) * RD_IT + l_item] = pre[q].y;
+      dst[(h + 2) * RD_IT + l_item] = pre[q].z; dst[(h + 3) * RD_IT + l_item] = pre[q].w;
+    }
+  };
+  if (n_it > 0) load_chunk(0, 0);
+  int step = 0;
+  for (int it = 0; it < n_it; ++it) {
+    float acc[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+    for (int hc = 0; hc < n_hc; ++hc, ++step) {
+      const int buf = step & 1;
+      store_chunk(buf);                                                 // (buffer `buf` was last read two chunks ago: a barrier has passed since)
+      __syncthreads();
+      const int nhc = hc + 1 < n_hc ? hc + 1 : 0, nit = hc + 1 < n_hc ? it : it + 1;
+      if (nit < n_it) load_chunk(nit, nhc);                             // next chunk's global loads fly under this chunk's arithmetic
+      const float* bt = sB + buf * RD_HC * RD_IT + tx;
+      const float* at = sA + ty * H1 + hc * RD_HC;
+      const float* wt = sW + hc * RD_HC;
+#pragma unroll 4
+      for (int h = 0; h < RD_HC; ++h) {
+        const float w = wt[h];
+        float a[4], b[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = at[q * 16 * H1 + h];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = bt[h * RD_IT + 16 * j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(w, fmaxf(a[q] + b[j], 0.f), acc[q][j]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sS[(ty + 16 * q) * RD_IT + tx + 16 * j] = acc[q][j] + p.b2;
+    __syncthreads();
+    // ---- tile epilogue: warp w owns users w, w + 8, ... ----
+    for (int ul = warp; ul < users_here; ul += RD_THREADS / 32) {
+      const int u = u0 + ul;
+#pragma unroll 1
+      for (int q = 0; q < RD_IT / 32; ++q) {
+        const int item = i_begin + it * RD_IT + q * 32 + lane;
+        const float sc = sS[ul * RD_IT + q * 32 + lane];
+        const bool valid = item < i_end;
+        if (p.scores != nullptr && valid) p.scores[(long long)u * p.lds + item] = sc;
+        if (p.k > 0) {
+          unsigned mask = __ballot_sync(FULL, valid && sc > sm_thr[ul]);
+          while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float cs = __shfl_sync(FULL, sc, b);
+            const int ci = i_begin + it * RD_IT + q * 32 + b;
+            if (!(cs > sm_thr[ul])) continue;
+            if (p.seen_ptr != nullptr) {
+              int lo = __ldg(p.seen_ptr + u), hi = __ldg(p.seen_ptr + u + 1);
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(p.seen_idx + mid) < ci) lo = mid + 1; else hi = mid;
+              }
+              if (lo < __ldg(p.seen_ptr + u + 1) && __ldg(p.seen_idx + lo) == ci) continue;
+            }
+            ap_insert(sm_lv + ul * AP_KMAX, sm_li + ul * AP_KMAX, sm_thr + ul, p.k, cs, ci, lane);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (p.k > 0) {
+    for (int ul = warp; ul < users_here; ul += RD_THREADS / 32) {
+      const long long o = ((long long)(u0 + ul) * p.n_splits + blockIdx.y) * p.k;
+      for (int j = lane; j < p.k; j += 32) { p.part_val[o + j] = sm_lv[ul * AP_KMAX + j]; p.part_idx[o + j] = sm_li[ul * AP_KMAX + j]; }
+    }
+  }
+}
+
+static size_t rd_smem_bytes(int H1) {
+  return (size_t)(RD_UT * H1 + H1 + 2 * RD_HC * RD_IT + RD_UT * RD_IT + 2 * RD_UT * AP_KMAX + RD_UT) * 4 + 16;
+}
+
 static size_t ap_packed_bytes(int H1, int mode) {
   return (size_t)(H1 / 64) * (mode == AP_BF16 ? 1 : 2) * AP_TILE;
 }
@@ -664,6 +806,60 @@ extern "C" int b200rec_allpairs_topk(const float* A, const float* B, int64_t nU,
   if (nI > 0) {
     const int rc = mode == AP_BF16 ? ap_dispatch<AP_BF16, AP_UQ_BF16>(p, grid, st) : ap_dispatch<AP_BF16X2, AP_UQ_X2>(p, grid, st);
     if (rc) return rc;
+  } else if (k > 0) {
+    B200REC_CUDA(cudaMemsetAsync(p.part_idx, 0xff, (size_t)nU * n_splits * k * sizeof(int), st));
+  }
+  if (k > 0) {
+    allpairs_merge_kernel<<<(unsigned)((nU + 3) / 4), 128, 0, st>>>(p.part_val, p.part_idx, (int)nU, n_splits, k, top_val, top_idx);
+    B200REC_CHECK_LAUNCH();
+  }
+  return B200REC_OK;
+}
+
+static int rd_auto_splits(int64_t nU, int64_t nI) {
+  const int64_t ublocks = (nU + RD_UT - 1) / RD_UT;
+  const int sms = b200rec_num_sms();
+  int64_t splits = ublocks >= sms ? 1 : (2 * sms + ublocks - 1) / ublocks;
+  const int64_t max_splits = (nI + RD_IT - 1) / RD_IT;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 128) splits = 128;
+  return (int)(splits < 1 ? 1 : splits);
+}
+
+extern "C" int b200rec_allpairs_relu_dot_splits(int64_t nU, int64_t nI) { return (nU <= 0 || nI <= 0) ? 1 : rd_auto_splits(nU, nI); }
+
+extern "C" int b200rec_allpairs_relu_dot_topk(const float* A, const float* B, int64_t nU, int64_t nI, int H1, const float* w2, float b2, int k,
+                                              int n_splits, const int* seen_ptr, const int* seen_idx, float* scores, int64_t lds, float* top_val,
+                                              int64_t* top_idx, void* workspace, size_t workspace_bytes, b200rec_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nU < 0 || nI < 0 || !w2 || (nU > 0 && nI > 0 && (!A || !B))) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: null operand");
+  if (H1 <= 0 || H1 > 256 || (H1 % 64)) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "allpairs_relu_dot: H1 must be 64, 128, 192 or 256 (zero-pad)");
+  if (k < 0 || k > AP_KMAX) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: need 0 <= k <= 64");
+  if (k > 0 && (!top_val || !top_idx)) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: top-k outputs missing");
+  if (k == 0 && !scores) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: nothing to compute");
+  if (scores && lds < nI) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: lds too small");
+  if ((seen_ptr == nullptr) != (seen_idx == nullptr)) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: seen CSR needs both arrays");
+  if (nU > INT32_MAX / 2 || nI > INT32_MAX / 2) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "allpairs_relu_dot: dims > 2^30");
+  if ((uintptr_t)A % 16 || (uintptr_t)B % 16) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: A / B must be 16-byte aligned");
+  if (nU == 0) return B200REC_OK;
+  if (n_splits <= 0) n_splits = nI > 0 ? rd_auto_splits(nU, nI) : 1;
+  if (n_splits > 128) return b200rec_fail(B200REC_ERR_BAD_ARG, "allpairs_relu_dot: at most 128 item splits");
+  if (k > 0 && (!workspace || workspace_bytes < b200rec_allpairs_workspace(nU, k, n_splits) || (uintptr_t)workspace % 16))
+    return b200rec_fail(B200REC_ERR_WORKSPACE, "allpairs_relu_dot: workspace too small (b200rec_allpairs_workspace)");
+  ReluDotParams p;
+  p.A = A; p.B = B; p.w2 = w2; p.b2 = b2; p.nU = (int)nU; p.nI = (int)nI; p.H1 = H1; p.k = k; p.n_splits = n_splits;
+  p.items_per_split = (int)(((nI + n_splits - 1) / n_splits + RD_IT - 1) / RD_IT * RD_IT);
+  if (p.items_per_split < RD_IT) p.items_per_split = RD_IT;
+  p.part_val = reinterpret_cast<float*>(workspace);
+  p.part_idx = k > 0 ? reinterpret_cast<int*>(p.part_val + (size_t)nU * n_splits * k) : nullptr;
+  p.scores = scores; p.lds = lds; p.seen_ptr = seen_ptr; p.seen_idx = seen_idx;
+  if (nI > 0) {
+    const size_t smem = rd_smem_bytes(H1);
+    static B200recSmemOptIn opted;
+    B200REC_CUDA(b200rec_opt_in_smem(opted, allpairs_relu_dot_kernel, (int)rd_smem_bytes(256)));
+    dim3 grid((unsigned)((nU + RD_UT - 1) / RD_UT), (unsigned)n_splits);
+    allpairs_relu_dot_kernel<<<grid, RD_THREADS, smem, st>>>(p);
+    B200REC_CHECK_LAUNCH();
   } else if (k > 0) {
     B200REC_CUDA(cudaMemsetAsync(p.part_idx, 0xff, (size_t)nU * n_splits * k * sizeof(int), st));
   }

@@ -128,7 +128,7 @@ __device__ __forceinline__ uint4 ldg16_keep(const unsigned char* p, uint64_t pol
 // 2 SHFL + 1 IMAD.WIDE.U32 + 1 LDG.128 + 4 FFMA (the first version spent ~26 instructions per edge on predicated
 // 64-bit address arithmetic and zero-fill moves — profiles/r01).
 template <int G, int NV, typename T, bool GAT, bool KEEP, int UN = 8, bool PUSH = false>
-__global__ void __launch_bounds__(SPMM_WARPS * 32, (NV == 1 && UN == 8 && !GAT) ? SPMM_MIN_CTAS : 1)
+__global__ void __launch_bounds__(SPMM_WARPS * 32, ((NV == 1 && UN == 8 && !GAT) || (NV * UN == 8 && NV > 1 && !GAT && sizeof(T) == 4)) ? SPMM_MIN_CTAS : 1)
 spmm_chunk_kernel(const __grid_constant__ SpmmParams p) {
   constexpr int EPW = 32 / G;                       // edges per warp step
   constexpr int VPL = Lane16<T>::VPL;
@@ -375,6 +375,13 @@ static int launch_chunks(const SpmmParams& p, cudaStream_t st) {
   const int grid = ceil_div_i(p.n_chunks, SPMM_WARPS);
   static const bool keep = []() { const char* e = getenv("B200REC_SPMM_L2_KEEP"); return e != nullptr && atoi(e) != 0; }();   // off by default: measured 3.21 vs 3.16 ms per config-3 step with the hint
   static const bool unroll16 = []() { const char* e = getenv("B200REC_SPMM_UNROLL"); return e != nullptr && atoi(e) == 16; }();
+  if constexpr (NV > 1 && G < 32) {      // narrow-group layouts (several edges per warp step): plain and push epilogues only
+    constexpr int UNW = 8 / NV;
+    if (p.push_parts > 0) spmm_chunk_kernel<G, NV, T, false, false, UNW, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    else spmm_chunk_kernel<G, NV, T, false, false, UNW, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
+    B200REC_CHECK_LAUNCH();
+    return B200REC_OK;
+  }
   if (p.push_parts > 0) spmm_chunk_kernel<G, NV, T, false, false, 8, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   else if (p.att_src) spmm_chunk_kernel<G, NV, T, true, false><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
   else if (keep) spmm_chunk_kernel<G, NV, T, false, true><<<grid, SPMM_WARPS * 32, 0, st>>>(p);
@@ -391,7 +398,14 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     int rc;
     if (row_bytes <= 128) rc = launch_chunks<8, 1, T>(p, st);
     else if (row_bytes <= 256) rc = launch_chunks<16, 1, T>(p, st);
-    else if (row_bytes <= 512) rc = launch_chunks<32, 1, T>(p, st);
+    else if (row_bytes <= 512) {
+      // 512-byte rows: G lanes per edge x NV 128-bit loads per lane.  Fewer lanes per edge = more edges per SHFL of the (source, weight)
+      // broadcast; the L1 data pipe (register write-back of LDG + SHFL) is this kernel's limiter (profiles/r02/ncu_full_shard_spmm_v1.txt)
+      static const int g512 = []() { const char* e = getenv("B200REC_SPMM_G512"); return e ? atoi(e) : 32; }();
+      if (g512 == 8 && !p.att_src && sizeof(T) == 4) rc = launch_chunks<8, 4, T>(p, st);
+      else if (g512 == 16 && !p.att_src && sizeof(T) == 4) rc = launch_chunks<16, 2, T>(p, st);
+      else rc = launch_chunks<32, 1, T>(p, st);
+    }
     else if (row_bytes <= 1024) rc = launch_chunks<32, 2, T>(p, st);
     else if (row_bytes <= 2048 && sizeof(T) == 4) rc = launch_chunks<32, 4, T>(p, st);
     else return b200rec_fail(B200REC_ERR_UNSUPPORTED, "spmm: node_emb wider than 512");

@@ -1036,6 +1036,34 @@ def allpairs_topk_raw(A, B, packed, mode, k, *, return_scores=False, seen=None, 
     return val, idx, scores
 
 
+def allpairs_relu_dot_raw(A, B, w2, b2, k, *, return_scores=False, seen=None, n_splits=0):
+    """score(u, i) = b2 + w2·ReLU(A[u] + B[i]) for every pair + the k best columns per row — b200rec_allpairs_relu_dot_topk (exact fp32)."""
+    _require_cuda(A, B, w2)
+    nU, H1p = A.shape
+    nI = B.shape[0]
+    lib = L.lib()
+    dev = A.device
+    w2p = torch.zeros(H1p, dtype=torch.float32, device=dev)
+    w2p[:w2.numel()] = w2.float().view(-1)
+    b2v = float(b2.detach().float().view(-1)[0].item()) if b2 is not None else 0.0
+    if n_splits <= 0:
+        n_splits = lib.b200rec_allpairs_relu_dot_splits(nU, nI)
+    val = torch.empty((nU, k), dtype=torch.float32, device=dev) if k > 0 else None
+    idx = torch.empty((nU, k), dtype=torch.int64, device=dev) if k > 0 else None
+    scores = torch.empty((nU, nI), dtype=torch.float32, device=dev) if return_scores else None
+    wsb = lib.b200rec_allpairs_workspace(nU, k, n_splits) if k > 0 else 0
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+    sp = si = None
+    if seen is not None:
+        sp, si = seen[0].contiguous().int(), seen[1].contiguous().int()
+        if sp.numel() != nU + 1:
+            raise ValueError('allpairs: seen_ptr must have nU + 1 entries')
+    with torch.cuda.device(dev), _timed('allpairs_relu_dot', (nU, nI, H1p, k)):
+        L.check(lib.b200rec_allpairs_relu_dot_topk(_ptr(A), _ptr(B), nU, nI, H1p, _ptr(w2p), b2v, k, n_splits, _ptr(sp), _ptr(si), _ptr(scores), nI,
+                                                   _ptr(val), _ptr(idx), _ptr(ws), wsb, _stream()), 'allpairs_relu_dot_topk')
+    return val, idx, scores
+
+
 def mlp_allpairs_topk(row_emb, col_emb, weights, biases, k, *, rows_first=True, precision='fp32', seen=None, return_scores=False,
                       n_splits=0):
     """Scores `MLP(cat(row_emb[u], col_emb[i]))` (rows_first) or `MLP(cat(col_emb[i], row_emb[u]))` for EVERY (u, i) and keeps
@@ -1066,6 +1094,9 @@ def mlp_allpairs_topk(row_emb, col_emb, weights, biases, k, *, rows_first=True, 
         W2, b2, w3, b3 = weights[1], biases[1], weights[2], biases[2]
         if W2.shape[0] > 128:
             raise NotImplementedError(f'all-pairs kernel: second hidden width {W2.shape[0]} > 128')
+    elif precision == 'fp32':
+        # one hidden layer at fp32 parity: score = b2 + w2·ReLU(a_u + b_i) has no GEMM left — exact FP32 kernel (csrc/allpairs.cu, relu_dot)
+        return allpairs_relu_dot_raw(A, Bm, weights[1].detach(), biases[1], k, return_scores=return_scores, seen=seen, n_splits=n_splits)
     else:
         # one hidden layer: score = w2·h1 + b2 = ReLU(w2·h1) - ReLU(-w2·h1) + b2 — two rows of the generic second layer
         w2 = weights[1].detach().view(1, -1)

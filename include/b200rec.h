@@ -144,6 +144,13 @@ int b200rec_rowdot(const float* in0, int64_t ld0, const int64_t* idx0, const flo
 /* ---- row-wise top-k (k <= 64), descending, ties towards the lower column, NaN never selected; rows with fewer than k valid
  * scores are padded with (-inf, -1).  Replaces `sort_values(by='score', ascending=False).iloc[:k]` of src/webapp/backend.py:113-121
  * and the per-user top-K of BASELINE config 4.  scores (rows, cols) ld; out_val (rows, k) fp32; out_idx (rows, k) int64. */
+/* One-hidden-layer MLPs in all-pairs mode: score(u,i) = b2 + sum_h w2[h]·ReLU(A[u,h] + B[i,h]) — ~3·H1 FP32 operations per pair and no GEMM
+ * (SURVEY.md §8d), evaluated exactly on the FP32 pipes with the same top-k / `seen` / split-list semantics as b200rec_allpairs_topk
+ * (whose workspace query it shares).  A (nU, H1), B (nI, H1) contiguous fp32, H1 in {64,128,192,256} (zero-pad), w2 (H1) device. */
+int b200rec_allpairs_relu_dot_splits(int64_t nU, int64_t nI);
+int b200rec_allpairs_relu_dot_topk(const float* A, const float* B, int64_t nU, int64_t nI, int H1, const float* w2, float b2, int k, int n_splits,
+                                   const int* seen_ptr, const int* seen_idx, float* scores, int64_t lds, float* top_val, int64_t* top_idx,
+                                   void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
 int b200rec_topk_rows(const float* scores, int64_t rows, int64_t cols, int64_t ld, int k, float* out_val, int64_t* out_idx,
                       b200rec_stream_t stream);
 

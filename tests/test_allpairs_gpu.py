@@ -180,3 +180,26 @@ def test_attention_recommend_for_user_vs_oracle(dev):
         mask = att[o].numpy() > thr
         assert np.array_equal(out['because'][j].cpu().numpy(), rs[mask])
         assert np.allclose(out['attention'][j].cpu().numpy(), att[o].numpy()[mask], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('nU,nI,H1,k,splits', [(70, 1000, 256, 10, 0), (5, 129, 64, 3, 2), (300, 333, 192, 64, 3), (64, 128, 128, 1, 1)])
+def test_relu_dot_kernel_is_exact_fp32(dev, nU, nI, H1, k, splits):
+    """b200rec_allpairs_relu_dot_topk (one-hidden-layer MLPs in all-pairs mode, FP32 pipes): scores against float64 to fp32 rounding,
+    top-k bit-equal to a stable sort of its own scores, `seen` pairs skipped, split lists merged."""
+    from deeprecommendation_b200 import ops
+    from oracle import restatement as R
+    g = torch.Generator().manual_seed(nU + nI)
+    A, B = torch.randn(nU, H1, generator=g), torch.randn(nI, H1, generator=g)
+    w2, b2 = torch.randn(H1, generator=g) / H1 ** 0.5, torch.randn(1, generator=g)
+    ref = (A.double()[:, None, :] + B.double()[None]).relu() @ w2.double() + b2.double()
+    val, idx, sc = ops.allpairs_relu_dot_raw(A.to(dev), B.to(dev), w2.to(dev), b2.to(dev), k, return_scores=True, n_splits=splits)
+    assert maxnorm_rel(sc, ref) < 2e-6
+    sv, si = R.topk_stable(sc.cpu(), k)
+    assert torch.equal(idx.cpu(), si) and torch.equal(val.cpu(), sv)
+    # seen: user 0 has already interacted with its two best items
+    ptr = torch.zeros(nU + 1, dtype=torch.int32)
+    ptr[1:] = 2
+    seen_items = torch.sort(si[0, :2]).values.int()
+    v2, i2, _ = ops.allpairs_relu_dot_raw(A.to(dev), B.to(dev), w2.to(dev), b2.to(dev), k, seen=(ptr.to(dev), seen_items.to(dev)), n_splits=splits)
+    assert not set(i2[0].cpu().tolist()) & set(seen_items.tolist())
+    assert torch.equal(i2[1:].cpu(), si[1:])
