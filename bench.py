@@ -1403,6 +1403,87 @@ def run_allpairs_full(args, dev, rank, world, dist, peaks, n_users_total=APF_USE
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# workload G — K1s: projection of one-hot / multi-hot profile rows (north_star (1))
+# ----------------------------------------------------------------------------------------------------------------------
+def run_sparse(args, dev, rank, world, dist, peaks):
+    """(a) BasicNCF on the reference's item-profile structure — 966 multi-hot columns (~1 %) as index lists + 1,128 dense columns
+    (content_providers.MixedRows) against the same rows streamed dense; (b) the one-hot variant (one_hot_provider.py:17-21) at a catalogue
+    whose embedding table (4 M x 128 fp32 = 2 GB) does not fit L2: a pure gather, HBM roofline (E_emb*s + 8) bytes per non-zero."""
+    from deeprecommendation_b200 import ops, synth
+    from deeprecommendation_b200.content_providers import MixedRows, OneHotRows
+    from deeprecommendation_b200.neural_collaborative_filtering.models import BasicNCF
+    from oracle import restatement as R
+    kw = dict(item_dim=F, user_dim=F, item_emb=128, user_emb=128, mlp_dense_layers=[256], dropout_rate=0.2)
+    sd = synth.to_torch(synth.basic_ncf_weights(seed=1, **kw))
+    model = BasicNCF(**kw).to(dev).eval()
+    model.load_state_dict(sd)
+    nb = 16
+    xi = [synth.item_profiles(BATCH, seed=50 + b) for b in range(nb)]
+    xu = [((synth.item_profiles(BATCH, seed=90 + b) - 0.3) * 0.1).astype(np.float32) for b in range(nb)]
+    dense = [(torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev)) for u, i in zip(xu, xi)]
+    mixed = [(torch.from_numpy(u).to(dev), MixedRows.from_dense(i, 966).to(dev)) for u, i in zip(xu, xi)]
+    nnz = float(np.mean([m[1].col.numel() for m in mixed]))
+
+    def step_dense(i):
+        with torch.no_grad():
+            out = None
+            for b in range(nb):
+                out = model(*dense[b])
+            return out
+
+    def step_mixed(i):
+        with torch.no_grad():
+            out = None
+            for b in range(nb):
+                out = model(*mixed[b])
+            return out
+
+    ms_d, _ = timed_steps(step_dense, args.steps, 3, dist, dev)
+    ms_m, launches = timed_steps(step_mixed, args.steps, 3, dist, dev)
+    with torch.no_grad():
+        par = _parity(model(*mixed[0]), R.basic_ncf_forward(sd, torch.from_numpy(xu[0]), torch.from_numpy(xi[0])),
+                      'oracle/restatement.py::basic_ncf_forward on the dense form of batch 0')
+    # (b) one-hot lookups out of a table far larger than L2
+    n_classes, E, M = 4_000_000, 128, 1 << 20
+    g = torch.Generator(device=dev).manual_seed(3)
+    wt = torch.randn(n_classes, E, device=dev, generator=g)           # W^T of the (E, n_classes) Linear = the embedding table (ops._transposed_weight caches it)
+    bias = torch.randn(E, device=dev, generator=g)
+    ids = torch.randint(0, n_classes, (M,), device=dev, generator=g)
+    out = torch.empty((M, E), device=dev)
+    from deeprecommendation_b200 import _lib as L
+    import ctypes as C
+
+    def lookup():
+        L.check(L.lib().b200rec_linear_sparse(None, None, None, C.c_void_p(ids.data_ptr()), M, C.c_void_p(wt.data_ptr()), n_classes, E, E, L.F32,
+                                              C.c_void_p(bias.data_ptr()), C.c_void_p(out.data_ptr()), E, 0,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'linear_sparse')
+    ts = []
+    for r in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        lookup()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    kms = float(np.median(ts[2:]))
+    exact = bool(torch.equal(out[:4096], wt[ids[:4096]] + bias))
+    alg = M * (E * 4 + 8) + M * E * 4                                  # table row + id per non-zero, + the output row
+    roof = {'bound': 'hbm', 'kernel': 'gather_sum_kernel (K1s, one-hot ids -> rows of W^T, 4 M x 128 fp32 table = 2 GB)', 'achieved': round(alg / (kms * 1e-3) / 1e9, 1),
+            'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(alg / (kms * 1e-3) / 1e9 / peaks['hbm_gbs'], 4), 'traffic': None,
+            'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg), 'lookup_equals_table_rows_plus_bias': exact}
+    pairs = BATCH * nb * args.steps * world
+    del wt, out, ids
+    torch.cuda.empty_cache()
+    return {'metric': 'scored user-item pairs/sec (BasicNCF fwd, multi-hot item columns as index lists)', 'value': pairs / (ms_m * 1e-3), 'unit': 'pairs/s',
+            'ms_per_step': ms_m / args.steps, 'scaling': 'weak', 'dtype': 'f32',
+            'config': {'workload': f'configs[0] shape with the item profiles handed over as MixedRows: 966 multi-hot columns as index lists (mean {nnz / BATCH:.1f} non-zeros '
+                                   f'per row) + 1,128 dense columns; {nb} batches of {BATCH} per step, eager launches', 'l2': 'inputs 69 MB per step'},
+            'dense_form_same_batches': {'value': pairs / (ms_d * 1e-3), 'ms_per_step': ms_d / args.steps},
+            'roofline': roof, 'parity': par, 'gpu_launches': launches,
+            'e2e': {'value': pairs / (ms_m * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0, 'note': 'inputs resident; configs[0] carries the host-fed leg'}}
+
+
 PARALLELISM = {
     'peer': 'users 1-D nnz-partitioned over {P} GPUs, item rows in {P} equal ranges; no library collective on the data path: K3 pushes partial item rows '
             'into the owner\'s receive slot over NVLink (reduce-scatter fused into the SpMM epilogue), slots summed in rank order, K1c writes the '
@@ -1500,7 +1581,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs', 'k3hbm', 'k2hbm', 'graph5', 'allpairs_full'])
+    ap.add_argument('--workload', default='all', choices=['all', 'attention', 'graph', 'basic', 'allpairs', 'k3hbm', 'k2hbm', 'graph5', 'allpairs_full', 'sparse'])
     ap.add_argument('--allpairs-users', type=int, default=APF_USERS, help='total users of the configs[3] full run (default 10^6)')
     ap.add_argument('--graph5-scale', type=float, default=1.0, help='configs[4] at a fraction of its size (users, items and edges scaled together)')
     ap.add_argument('--graph-scale', type=float, default=1.0)
@@ -1661,6 +1742,12 @@ def main():
             also.append(run_k2_hbm_regime(dev, peaks))
         except Exception as e:
             also.append({'metric': 'K2 HBM regime', 'error': repr(e)[:300]})
+    if args.workload in ('all', 'sparse') and world == 1:
+        try:
+            also.append(run_sparse(args, dev, rank, world, dist, peaks))
+        except Exception as e:
+            also.append({'metric': 'K1s sparse projection', 'error': repr(e)[:400]})
+        torch.cuda.empty_cache()
     if args.workload == 'allpairs_full' or (args.workload == 'all' and world == 8):  # configs[3] names 8 GPUs; other sizes on request
         try:
             also.append(run_allpairs_full(args, dev, rank, world, dist, peaks, args.allpairs_users))

@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_allpairs_gpu.py -x -q -m gpu > gpurun_out/test_allpairs.log 2>&1; echo "allpairs tests rc=$?"
-tail -6 gpurun_out/test_allpairs.log
-timeout 600 python bench.py --workload allpairs_full --allpairs-users 125000 > gpurun_out/bench_allpairs_full_n1.json 2> gpurun_out/bench_allpairs_full_n1.err; echo "allpairs_full 1gpu rc=$?"
-tail -c 3000 gpurun_out/bench_allpairs_full_n1.json; tail -3 gpurun_out/bench_allpairs_full_n1.err
+timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/test_gpu_all.log 2>&1; echo "gpu tests rc=$?"
+tail -6 gpurun_out/test_gpu_all.log
+timeout 900 python bench.py > gpurun_out/bench_r02_n1.json 2> gpurun_out/bench_r02_n1.err; echo "bench rc=$?"
+tail -c 600 gpurun_out/bench_r02_n1.json; tail -3 gpurun_out/bench_r02_n1.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
