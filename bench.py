@@ -367,65 +367,69 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
                                                   'user, top-10, explanations by attention threshold; wall clock per request incl. the D2H of the result'}
         except Exception as e:
             serving = {'error': repr(e)[:300]}
-    (name, meta), (kms, per_step) = max(ops_ms.items(), key=lambda kv: kv[1][0] * kv[1][1])
     I_mean = float(np.mean([b[1].shape[0] for b in host]))
-    if name in ('linear', 'linear_tc', 'linear_tc_batch'):
+    TS = 'profiles/traffic.json (static: one `ncu --set full` capture of this kernel per round, not measured in this run)'
+
+    def k1a_roof(opname, meta, kms):
+        """roofline_time = max(bytes / HBM_peak, flops / pipe_peak), frac = roofline_time / measured time, with the ALGORITHMIC
+        flops 2·M·K·N.  fp32 parity runs on the TF32 pipe (dense rate = half the measured bf16 rate; MEASURED_PEAKS.json has no TF32 figure).
+        The 3 MMAs per product of the 3xTF32 split are emulation overhead, not useful work: they only show in `issued_frac`, never in `frac`."""
         M, K, N = meta
-        alg_bytes = 4.0 * (M * K + N * K + M * N)          # read X and W once, write Y once
-        kname = (f'gemm_tc_kernel (K1a linear {M}x{K}->{N}{" = rated + candidate rows in one launch" if name == "linear_tc_batch" else ""}, tcgen05 {w.get("gemm", "tf32x3")})' if name != 'linear'
-                 else f'gemm_tn_kernel (K1a linear {M}x{K}->{N}, fp32 FFMA)')
-    elif name == 'attention_pool':
-        nnz_mean = float(np.mean(w['nnz']))
-        alg_bytes = nnz_mean * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)
-        kname = 'um_compact_kernel + attention_wseg_kernel + attention_merge_kernel (K2)'
-    else:
-        alg_bytes, kname = 0.0, name
-    achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-    roof = {'bound': 'hbm', 'kernel': kname, 'achieved': round(achieved, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-            'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention' if name.startswith('linear') else 'attention_pool'),
-            'peak_source': peaks['src'],
-            'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
-            'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
-    roof['traffic_source'] = 'profiles/traffic.json (static: one `ncu --set full` capture of this kernel per round, not measured in this run)'
-    if name in ('linear_tc', 'linear_tc_batch'):
-        # roofline_time = max(bytes / HBM_peak, flops / pipe_peak), frac = roofline_time / measured time, with the
-        # ALGORITHMIC flops 2·M·K·N.  fp32 parity runs on the TF32 pipe (dense rate = half the measured bf16 rate; MEASURED_PEAKS.json has
-        # no TF32 figure).  The 3 MMAs per product of the 3xTF32 split are emulation overhead, not useful work: they only show up in
-        # `issued_frac` (how busy the pipe is), never in `frac`.
-        M, K, N = meta
+        ab = 4.0 * (M * K + N * K + M * N)                  # read X and W once, write Y once
+        ach = ab / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        if opname == 'linear':
+            return {'bound': 'hbm', 'kernel': f'gemm_tn_kernel (K1a linear {M}x{K}->{N}, fp32 FFMA)', 'achieved': round(ach, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                    'frac': round(ach / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention'), 'traffic_source': TS, 'peak_source': peaks['src'],
+                    'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(ab)}
         flops = 2.0 * M * K * N
         tf32 = w.get('gemm', 'tf32x3') == 'tf32x3'
         issue = 3.0 if tf32 else 1.0
         pipe = peaks['bf16_tflops'] / 2.0 if tf32 else peaks['bf16_tflops']
-        t_hbm, t_pipe = alg_bytes / (peaks['hbm_gbs'] * 1e9), flops / (pipe * 1e12)
+        t_hbm, t_pipe = ab / (peaks['hbm_gbs'] * 1e9), flops / (pipe * 1e12)
         t_roof = max(t_hbm, t_pipe)
         ach_tf = flops / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
-        roof.update({'frac': round(t_roof / (kms * 1e-3), 4) if kms > 0 else 0.0, 'roofline_us': round(t_roof * 1e6, 2),
-                     'hbm_view': {'achieved': roof['achieved'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'roofline_us': round(t_hbm * 1e6, 2)},
-                     'tensor_view': {'achieved': round(ach_tf, 1), 'peak': round(pipe, 1), 'unit': 'TFLOP/s', 'roofline_us': round(t_pipe * 1e6, 2),
-                                     'algorithmic_flops': int(flops),
-                                     'peak_source': peaks['src'] + (': bf16 burst %.0f TFLOP/s / 2 = dense TF32' % peaks['bf16_tflops'] if tf32 else ': bf16 burst')},
-                     'issued_tflops': round(ach_tf * issue, 1), 'issued_frac': round(ach_tf * issue / pipe, 4),
-                     'issued_note': '3 TF32 MMAs per product (hi*hi + hi*lo + lo*hi) for fp32 parity' if tf32 else 'one bf16 MMA per product'})
-        if t_pipe > t_hbm:
-            roof.update({'bound': 'tensor', 'achieved': round(ach_tf, 1), 'peak': round(pipe, 1), 'unit': 'TFLOP/s'})
-    # the second roofline kernel of this workload, whichever of K1a / K2 is not the dominant one (same formulas)
-    other = []
-    for (n2, m2), (k2, _) in ops_ms.items():
-        if n2 == name:
-            continue
-        if n2 == 'attention_pool':
-            ab = float(np.mean(w['nnz'])) * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)
-            other.append({'kernel': 'um_compact_kernel + attention_wseg_kernel + attention_merge_kernel (K2; tables L2-resident at this size)',
-                          'kernel_ms': round(k2, 4), 'algorithmic_bytes': int(ab), 'achieved': round(ab / (k2 * 1e-3) / 1e9, 1), 'unit': 'GB/s',
-                          'frac': round(ab / (k2 * 1e-3) / 1e9 / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention_pool')})
-        elif n2 in ('linear_tc', 'linear_tc_batch') and m2[1] >= 512:
-            ab = 4.0 * (m2[0] * m2[1] + m2[2] * m2[1] + m2[0] * m2[2])
-            other.append({'kernel': f'gemm_tc_kernel (K1a {m2[0]}x{m2[1]}->{m2[2]})', 'kernel_ms': round(k2, 4), 'algorithmic_bytes': int(ab),
-                          'achieved': round(ab / (k2 * 1e-3) / 1e9, 1), 'unit': 'GB/s', 'frac': round(ab / (k2 * 1e-3) / 1e9 / peaks['hbm_gbs'], 4),
-                          'traffic': _traffic('attention')})
-    if other:
-        roof['other_kernels'] = other
+        tensor = t_pipe > t_hbm
+        return {'bound': 'tensor' if tensor else 'hbm',
+                'kernel': f'gemm_tc_kernel + tc_splitk_reduce_kernel (K1a linear {M}x{K}->{N}, tcgen05 {w.get("gemm", "tf32x3")}, 128x256 tiles + split-K)',
+                'achieved': round(ach_tf, 1) if tensor else round(ach, 1), 'peak': round(pipe, 1) if tensor else peaks['hbm_gbs'],
+                'unit': 'TFLOP/s' if tensor else 'GB/s', 'frac': round(t_roof / (kms * 1e-3), 4) if kms > 0 else 0.0, 'roofline_us': round(t_roof * 1e6, 2),
+                'traffic': _traffic('attention'), 'traffic_source': TS, 'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(ab),
+                'hbm_view': {'achieved': round(ach, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'roofline_us': round(t_hbm * 1e6, 2)},
+                'tensor_view': {'achieved': round(ach_tf, 1), 'peak': round(pipe, 1), 'unit': 'TFLOP/s', 'roofline_us': round(t_pipe * 1e6, 2), 'algorithmic_flops': int(flops),
+                                'peak_source': peaks['src'] + (': bf16 burst %.0f TFLOP/s / 2 = dense TF32' % peaks['bf16_tflops'] if tf32 else ': bf16 burst')},
+                'issued_tflops': round(ach_tf * issue, 1), 'issued_frac': round(ach_tf * issue / pipe, 4),
+                'issued_note': '3 TF32 MMAs per product (hi*hi + hi*lo + lo*hi) for fp32 parity' if tf32 else 'one bf16 MMA per product'}
+
+    def k2_roof(kms):
+        ab = float(np.mean(w['nnz'])) * (2 * 128 * 4 + 8) + BATCH * (128 * 4 + 4)     # SURVEY.md §8d, K2
+        ach = ab / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        tr = _traffic('attention_pool')
+        r = {'bound': 'hbm', 'kernel': 'um_compact_kernel + attention_wseg_kernel + attention_merge_kernel (K2)', 'achieved': round(ach, 1), 'peak': peaks['hbm_gbs'],
+             'unit': 'GB/s', 'frac': round(ach / peaks['hbm_gbs'], 4), 'traffic': tr, 'traffic_source': TS, 'peak_source': peaks['src'], 'kernel_ms': round(kms, 4),
+             'algorithmic_bytes': int(ab),
+             'regime': 'the two gathered tables are 2 x 9.7 MB at this config: L2-resident.  `frac` is SURVEY.md §8d\'s formula (algorithmic gather bytes / time / HBM '
+                       'peak) and measures L2 + latency here, not HBM — the DRAM pins move `traffic` bytes (`dram_frac`); the HBM-regime leg of K2 (`also`, tables 4 GB) is the '
+                       'honest HBM figure'}
+        if tr:
+            r['dram_frac'] = round(tr / (kms * 1e-3) / 1e9 / peaks['hbm_gbs'], 4)
+        return r
+
+    def roof_of(opname, meta, kms):
+        if opname in ('linear', 'linear_tc', 'linear_tc_batch') and meta[1] >= 512:
+            return k1a_roof(opname, meta, kms)
+        if opname == 'attention_pool':
+            return k2_roof(kms)
+        return None
+
+    ranked = sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])
+    roofs = [(n_, roof_of(n_, m_, v_[0])) for (n_, m_), v_ in ranked]
+    roofs = [r_ for _, r_ in roofs if r_ is not None]
+    roof = roofs[0] if roofs else {'bound': 'hbm', 'kernel': ranked[0][0][0], 'achieved': 0.0, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': 0.0, 'traffic': None}
+    roof['op_ms_per_batch'] = {f'{n_}{list(m_)}': round(v_[0] * v_[1], 4) for (n_, m_), v_ in ranked}
+    roof['dominance_note'] = ('K1a (rated-item projection) and K2 (attention pooling) take about the same time per batch at this config; whichever is larger in this run is '
+                              'the object above, the other is `other_kernels[0]` with the same fields')
+    if len(roofs) > 1:
+        roof['other_kernels'] = roofs[1:]
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4 * nb, roofline=roof, I_mean=I_mean, out0=out0, nb=nb,
                 nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res, train=train, serving=serving,
                 launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))

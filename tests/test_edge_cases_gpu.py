@@ -160,3 +160,42 @@ def test_topk_k_larger_than_catalogue():
     assert torch.equal(idx[:, :6].cpu(), ref_idx) and maxnorm_rel(val[:, :6], ref_val) < TOL
     pos2, pos4 = (idx[:, :6] == 2).nonzero()[:, 1], (idx[:, :6] == 4).nonzero()[:, 1]
     assert torch.all(pos2 < pos4)
+
+
+def test_gradients_on_a_binary_graph_vs_oracle_autograd():
+    """binary=True keeps only r >= centre edges per direction (graph_providers.py:33,42): the two edge lists differ, the propagation matrix is
+    NOT symmetric, and the backward must multiply by the index of the reversed edges (GraphIndex.transposed) — round-1 advisor finding: the
+    forward index with swapped weights silently computed A·(D g) instead of Aᵀ·(D g)."""
+    from deeprecommendation_b200.graph import IdTable, create_graph, get_index
+    n_users, n_items, n, F, d = 260, 170, 5000, 16, 32
+    users, items, ratings = synth.interactions_zipf(n_users, n_items, n, seed=91)
+    rng = np.random.default_rng(92)
+    fi, fu = rng.standard_normal((n_items, F)).astype(np.float32), rng.standard_normal((n_users, F)).astype(np.float32)
+    kw = dict(item_dim=F, user_dim=F, num_gnn_layers=2, hetero=True, node_emb=d, mlp_dense_layers=[32], dropout_rate=0.2)
+    sd = synth.to_torch(synth.graph_ncf_weights(seed=93, **kw))
+    ref_g = R.create_graph(users, items, ratings, np.arange(n_users), np.arange(n_items), binary=True)
+    assert ref_g['user2item_edge_index'].shape[1] != ref_g['item2user_edge_index'].shape[1]          # really asymmetric
+    gd = {k: (torch.from_numpy(v) if v is not None else None) for k, v in ref_g.items()}
+    gd['item_features'], gd['user_features'] = torch.from_numpy(fi), torch.from_numpy(fu)
+    e = ref_g['user2item_edge_index']
+    pick = rng.permutation(e.shape[1])[:64]
+    uid, iid = torch.from_numpy(e[0][pick]), torch.from_numpy(e[1][pick])
+    g = create_graph(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), torch.from_numpy(ratings).to(DEV),
+                     torch.from_numpy(fi).to(DEV), torch.from_numpy(fu).to(DEV),
+                     IdTable(torch.arange(n_users, device=DEV)), IdTable(torch.arange(n_items, device=DEV)), binary=True)
+    assert not get_index(g).symmetric
+    m = _models().GraphNCF(**kw).to(DEV).train()
+    m.load_state_dict(sd)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m(g, uid.to(DEV), iid.to(DEV), DEV, mask_targets=False).square().sum().backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    for k in list(ref_sd):
+        if k.startswith('gnn_convs.1.'):
+            ref_sd[k] = ref_sd[k.replace('gnn_convs.1.', 'gnn_convs.0.')]
+    R.graph_ncf_forward(ref_sd, gd, uid, iid, 2).square().sum().backward()
+    got = dict(m.named_parameters())
+    for k in ('item_embeddings.0.weight', 'user_embeddings.0.weight', 'gnn_convs.0.user2item_W.0.weight', 'gnn_convs.0.item2user_W.0.weight',
+              'gnn_convs.0.item2user_W.0.bias', 'MLP.0.weight'):
+        assert maxnorm_rel(got[k].grad, ref_sd[k].grad) < 1e-4, k
