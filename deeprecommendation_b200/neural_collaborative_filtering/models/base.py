@@ -32,6 +32,28 @@ class NCF(nn.Module):
     def important_hypeparams(self) -> str:
         return ''
 
+    # ---- derived copies of the weights (packed MMA tiles, composite / transposed matrices, cached embeddings) -----------------------
+    # They are keyed on (address, tensor `_version`).  Loading a state dict, moving / casting the module, or editing parameters through
+    # `.data` (which does NOT bump `_version`) must drop them: the first two are hooked here, the third is what `invalidate_caches()` is for.
+    _DERIVED = ('_proj_cache', '_comp_cache', '_att_cache', '_cache', '_peer_layer0')
+
+    def invalidate_caches(self):
+        from ... import ops
+        ops.invalidate_caches()
+        for name in self._DERIVED:
+            if name in self.__dict__:
+                object.__setattr__(self, name, None)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_caches()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_caches()
+        return out
+
 
 class GNN_NCF(NCF):
     """forward(graph, userIds, itemIds, device, ...) -> (B, 1); ids are NODE ids (items first)."""

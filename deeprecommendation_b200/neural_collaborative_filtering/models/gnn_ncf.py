@@ -190,11 +190,22 @@ class GraphNCF(GNN_NCF):
                                        acc_scale=1.0 / (L_ + 1) if last else 1.0, skip_bits=skip, att_src=ps if gat else None)
                 x = xn
             return comb
-        if self.convType == 'LightGAT':
-            raise NotImplementedError('LightGAT backward is not implemented: run it under torch.no_grad() (SURVEY.md §8f-1/3)')
         # training path: same kernels through autograd Functions (backward of K3 = K3 on the reverse weights)
         x = torch.cat((ops.linear(graph.item_features, ie.weight, ie.bias), ops.linear(graph.user_features, ue.weight, ue.bias)), 0)
         hs = [x]
+        if self.convType == 'LightGAT':
+            # gnn_ncf.py:128-177 with gradients: W(x_j) per node, the source half of the attention Linear per node, K3 with the edge softmax forward,
+            # closed-form backward (ops._GatPropagateFn).  The destination half of AttNet and its bias cancel inside the row softmax: their gradient is 0.
+            att_u, att_i = self.gnn_convs[0].attention()
+            d_ = x.shape[1]
+            for _ in range(L_):
+                t = torch.cat((ops.linear(x[:nI], lin_i.weight, lin_i.bias), ops.linear(x[nI:], lin_u.weight, lin_u.bias)), 0)
+                if training and p_conv > 0.0:
+                    t = torch.nn.functional.dropout(t, p_conv, training=True)
+                ps = torch.cat((ops.linear(x[:nI], att_i.weight[:, :d_], None), ops.linear(x[nI:], att_u.weight[:, :d_], None)), 0)
+                x = ops.propagate_gat(t, ps, index, skip)
+                hs.append(x)
+            return torch.cat(hs, dim=1) if self.concat else torch.mean(torch.stack(hs, dim=0), dim=0)
         for _ in range(L_):
             t = torch.cat((ops.linear(x[:nI], lin_i.weight, lin_i.bias, row_scale=dinv[:nI]),
                            ops.linear(x[nI:], lin_u.weight, lin_u.bias, row_scale=dinv[nI:])), 0)

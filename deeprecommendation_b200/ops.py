@@ -137,6 +137,15 @@ def _packed_weight(w, ldw, mode):
     return buf
 
 
+def invalidate_caches():
+    """Drops every derived copy of a weight kept by this module (MMA-ready packed weights, transposed tables, all-pairs packs).  The caches are
+    keyed on (address, `_version`): an in-place edit THROUGH `.data` (`p.data.copy_()`, some EMA / weight-averaging utilities) does not bump
+    `_version`, so such code must call this (the model classes do it from `load_state_dict` / `_apply` / `invalidate_caches()`)."""
+    _pack_cache.clear()
+    globals().get('_wt_cache', {}).clear()
+    globals().get('_ap_cache', {}).clear()
+
+
 def set_gemm_engine(name: str):
     global _gemm_engine
     if name not in ('simt', 'tf32x3', 'bf16'):
@@ -846,6 +855,71 @@ class _PropagateFn(torch.autograd.Function):
 
 def propagate(t, index, w, w_bwd, dinv, skip_bits=None):
     return _PropagateFn.apply(t, index, w, w_bwd, dinv, skip_bits)
+
+
+class _GatPropagateFn(torch.autograd.Function):
+    """LightGATConv step (gnn_ncf.py:128-177): x'[r] = Σ_{k in row r} w_k·α_k·t[s_k],  α = softmax over the row of the SOURCE scores ps[s_k] with PyG's
+    `+1e-16` denominator (the destination half of the Linear(2d, 1) and its bias are constant within a row and cancel).
+    forward: K3 with the online edge softmax.  backward (closed form, per edge k of row r):
+        dα_k = w_k·<g[r], t[s_k]>        da_k = α_k·(dα_k − Σ_j α_j dα_j)        dps[s] = Σ_{k: s_k = s} da_k        dt[s] = Σ_{k: s_k = s} w_k α_k g[r_k]
+    dt runs on K3 over the index of the reversed edges with the per-edge weights w·α carried over; the per-edge dot products are formed in chunks of
+    2^20 edges with torch CUDA ops (training-side glue, like the other backward passes of this file)."""
+
+    @staticmethod
+    def forward(ctx, t, ps, index, skip_bits):
+        x_next = torch.empty((index.num_nodes, t.shape[1]), dtype=torch.float32, device=t.device)
+        spmm_raw(index, t, w=index.w, dinv=None, x_next=x_next, skip_bits=skip_bits, att_src=ps)
+        ctx.index, ctx.skip_bits = index, skip_bits
+        ctx.save_for_backward(t, ps)
+        return x_next
+
+    @staticmethod
+    def backward(ctx, g):
+        t, ps = ctx.saved_tensors
+        index, skip = ctx.index, ctx.skip_bits
+        dev = t.device
+        g = g.contiguous().float()
+        rp, col = index.row_ptr.long(), index.col.long()
+        n, nnz = index.num_nodes, col.numel()
+        rows = torch.repeat_interleave(torch.arange(n, device=dev), rp[1:] - rp[:-1])
+        a = ps.detach().float().view(-1)[col]
+        alive = torch.ones(nnz, dtype=torch.bool, device=dev)
+        if skip is not None:                                                    # target edges of the batch take no part in the softmax
+            pos = index.pos.long()
+            alive = ((skip.long()[pos >> 5] >> (pos & 31)) & 1) == 0
+            a = torch.where(alive, a, torch.full_like(a, float('-inf')))
+        amax = torch.full((n,), float('-inf'), device=dev).scatter_reduce(0, rows, a, reduce='amax', include_self=True)
+        e = torch.where(alive, (a - amax[rows]).exp(), torch.zeros_like(a))
+        den = torch.zeros(n, device=dev).index_add_(0, rows, e) + 1e-16
+        alpha = e / den[rows]
+        w = index.w if index.w is not None else torch.ones(nnz, device=dev)
+        d_alpha = torch.empty(nnz, device=dev)
+        for k0 in range(0, nnz, 1 << 20):
+            k1 = min(nnz, k0 + (1 << 20))
+            d_alpha[k0:k1] = (g[rows[k0:k1]] * t.detach().float()[col[k0:k1]]).sum(1)
+        d_alpha = d_alpha * w
+        row_dot = torch.zeros(n, device=dev).index_add_(0, rows, alpha * d_alpha)
+        d_a = alpha * (d_alpha - row_dot[rows])
+        d_ps = torch.zeros(n, device=dev).index_add_(0, col, d_a).view(ps.shape)
+        # dt = A_{w·α}^T g on K3 over the reversed index; its entries find their forward entry through (edge list, position)
+        tr = index.transposed()
+        k_items = index.e1                                                      # item rows come first and hold exactly the u2i list (destination = item)
+        inv_u2i = torch.empty(index.e1, dtype=torch.long, device=dev)
+        inv_i2u = torch.empty(index.e2, dtype=torch.long, device=dev)
+        fpos = index.pos.long()
+        inv_u2i[fpos[:k_items]] = torch.arange(k_items, device=dev)            # forward entries of item rows hold the u2i list (destination = item)
+        inv_i2u[fpos[k_items:]] = torch.arange(k_items, nnz, device=dev)
+        tpos = tr.pos.long()
+        kt = tr.e2                                                              # transposed item rows hold the flipped i2u list (e2 entries), then user rows the flipped u2i list
+        fwd = torch.cat((inv_i2u[tpos[:kt]], inv_u2i[tpos[kt:]]))
+        wt = (w * alpha)[fwd].contiguous()
+        gt = torch.empty_like(g)
+        spmm_raw(tr, g, w=wt, dinv=None, x_next=gt)
+        return gt, d_ps, None, None
+
+
+def propagate_gat(t, ps, index, skip_bits=None):
+    return _GatPropagateFn.apply(t, ps, index, skip_bits)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -551,3 +551,49 @@ def test_attention_overlap_prepare_equals_default():
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(gout, ref_out)
+
+
+@pytest.mark.parametrize('masked', [False, True])
+def test_lightgat_gradients_vs_oracle_autograd(masked):
+    """LightGATConv training step (gnn_ncf.py:97-177 under train.py:99-105): forward on K3's edge-softmax kernel, closed-form backward
+    (ops._GatPropagateFn: dt on K3 over the reversed index, softmax gradient per edge) against torch autograd through the oracle restatement."""
+    from deeprecommendation_b200.graph import IdTable, create_graph
+    n_users, n_items, n, F, d_emb = 300, 120, 6000, 24, 32
+    users, items, ratings = synth.interactions_zipf(n_users, n_items, n, seed=15)
+    rng = np.random.default_rng(13)
+    fi, fu = rng.standard_normal((n_items, F)).astype(np.float32), rng.standard_normal((n_users, F)).astype(np.float32)
+    kw = dict(item_dim=F, user_dim=F, num_gnn_layers=2, hetero=True, node_emb=d_emb, mlp_dense_layers=[32], dropout_rate=0.2, convType='LightGAT')
+    sd = synth.to_torch(synth.graph_ncf_weights(seed=14, **kw))
+    ref_g = R.create_graph(users, items, ratings, np.arange(n_users), np.arange(n_items))
+    gd = {k: (torch.from_numpy(v) if v is not None else None) for k, v in ref_g.items()}
+    gd['item_features'], gd['user_features'] = torch.from_numpy(fi), torch.from_numpy(fu)
+    pick = rng.permutation(n)[:96]
+    uid, iid = torch.from_numpy(ref_g['user2item_edge_index'][0][pick]), torch.from_numpy(ref_g['user2item_edge_index'][1][pick])
+    g = create_graph(torch.from_numpy(users).to(DEV), torch.from_numpy(items).to(DEV), torch.from_numpy(ratings).to(DEV),
+                     torch.from_numpy(fi).to(DEV), torch.from_numpy(fu).to(DEV),
+                     IdTable(torch.arange(n_users, device=DEV)), IdTable(torch.arange(n_items, device=DEV)))
+    m = _models().GraphNCF(**kw).to(DEV).train()
+    m.load_state_dict(sd)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    out = m(g, uid.to(DEV), iid.to(DEV), DEV, mask_targets=masked)
+    out.square().sum().backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    for k in list(ref_sd):
+        if k.startswith('gnn_convs.1.'):
+            ref_sd[k] = ref_sd[k.replace('gnn_convs.1.', 'gnn_convs.0.')]
+    ref = R.graph_ncf_forward(ref_sd, gd, uid, iid, 2, convType='LightGAT', masked_positions=torch.from_numpy(pick) if masked else None)
+    assert maxnorm_rel(out.detach(), ref.detach()) < TOL
+    ref.square().sum().backward()
+    got = dict(m.named_parameters())
+    scale = max(float(v.grad.abs().max()) for v in ref_sd.values() if v.grad is not None)
+    for k in ('item_embeddings.0.weight', 'user_embeddings.0.bias', 'gnn_convs.0.user2item_W.0.weight', 'gnn_convs.0.item2user_W.0.bias',
+              'gnn_convs.0.user2item_AttNet.0.weight', 'gnn_convs.0.item2user_AttNet.0.weight', 'MLP.0.weight'):
+        gk = got[k].grad
+        rk = ref_sd[k].grad
+        if 'AttNet' in k:                       # the destination half cancels in the row softmax: exactly 0 here, ~1e-17·scale in autograd
+            assert float((gk[:, :d_emb].cpu() - rk[:, :d_emb]).abs().max()) < 1e-4 * max(float(rk[:, :d_emb].abs().max()), 1e-6 * scale), k
+            assert float(gk[:, d_emb:].abs().max()) == 0.0 and float(rk[:, d_emb:].abs().max()) < 1e-5 * scale, k
+        else:
+            assert maxnorm_rel(gk, rk) < 1e-4, k

@@ -139,3 +139,22 @@ def test_sparse_row_containers_round_trip_and_take():
     assert sp.get_item_feature_dim() == 4 and sp.get_num_users() == 2
     cp = MixedProfilesProvider(np.arange(40) * 3, rows, np.arange(5), rng.random((5, 42)).astype(np.float32), 30)
     assert np.array_equal(cp.get_item_profile(np.array([9, 0])).dense_rows().numpy(), rows[[3, 0]])
+
+
+def test_model_hooks_drop_derived_weight_copies():
+    """load_state_dict / .to() / invalidate_caches() drop the derived copies of the weights (packed tiles, composites, cached embeddings) that are
+    keyed on (address, _version) — an edit through `.data` bumps neither (round-1 advisor finding)"""
+    from deeprecommendation_b200 import ops
+    from deeprecommendation_b200.neural_collaborative_filtering.models import AttentionNCF, GraphNCF
+    a = AttentionNCF(8, 4, 4, att_dense=4, mlp_dense_layers=[8])
+    a._comp_cache = ('stale', 1)
+    ops._pack_cache['stale'] = 1
+    a.load_state_dict(a.state_dict())
+    assert a._comp_cache is None and 'stale' not in ops._pack_cache
+    g = GraphNCF(8, 8, 2, True, node_emb=4, mlp_dense_layers=[8], cache_eval_embeddings=True)
+    g._cache = ('stale', 1)
+    g.double()
+    assert g._cache is None
+    g._cache = ('stale', 1)
+    g.invalidate_caches()
+    assert g._cache is None
