@@ -140,3 +140,117 @@ def test_user_partitioned_reduce_scheme_matches_single_process(world):
     ret = mp.get_context('spawn').Manager().dict()
     mp.spawn(_worker_reduce, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world and all(ret.values()), dict(ret)
+
+
+# ---- host logic of round 2's partitioned path (pure torch: runs without a GPU) ----------------------------------------------------------
+def _walk_stream_plan(plan, t, d):
+    """CPU model of csrc/spmm_stream.cu + the fix-up pass: every 'warp' walks its segment of the entry stream exactly as the kernel does
+    (flag = last entry of a row, head / tail partial slots, rows_ne numbering, empty rows zero-filled)."""
+    n_rows = plan.n_rows
+    out = torch.full((n_rows, d), float('nan'), dtype=torch.float64)
+    partials = torch.zeros((max(plan.n_slots, 1), d), dtype=torch.float64)
+    colf, wd = plan.colf.tolist(), plan.wd.double()
+    for s in range(plan.n_segs):
+        k0, kend = s * plan.seg, min((s + 1) * plan.seg, plan.nnz)
+        j = int(plan.seg_first_j[s])
+        head = int(plan.seg_head_slot[s])
+        open_is_head = head >= 0
+        acc = torch.zeros(d, dtype=torch.float64)
+        last_flag = True
+        for k in range(k0, kend):
+            c = colf[k]
+            flag = c < 0
+            acc = acc + wd[k] * t[c & 0x7fffffff]
+            last_flag = flag
+            if flag:
+                if open_is_head:
+                    partials[head] = acc
+                    open_is_head = False
+                else:
+                    out[int(plan.rows_ne[j])] = acc
+                acc = torch.zeros(d, dtype=torch.float64)
+                j += 1
+        if not last_flag:
+            partials[head if open_is_head else int(plan.seg_tail_slot[s])] = acc
+    for e in plan.rows_empty.tolist()[:plan.n_empty]:
+        out[e] = 0.0
+    for m in range(plan.n_multi):
+        r, f, n = int(plan.multi_row[m]), int(plan.multi_first_slot[m]), int(plan.multi_n_slots[m])
+        out[r] = partials[f:f + n].sum(0)
+    return out
+
+
+def test_stream_plan_walk_reproduces_the_spmm_on_cpu():
+    from deeprecommendation_b200.graph import StreamPlan
+    g = torch.Generator().manual_seed(0)
+    for seg, deg in ((32, [3, 0, 0, 70, 1, 1, 0, 40, 5, 0]), (32, [32, 32, 64, 0, 128, 1, 31, 0, 0, 200, 32, 5]), (64, [0, 700, 0]), (32, [1] * 100),
+                     (128, torch.randint(0, 90, (60,), generator=g).tolist())):
+        deg_t = torch.tensor(deg)
+        n = len(deg)
+        rp = torch.zeros(n + 1, dtype=torch.int32)
+        rp[1:] = torch.cumsum(deg_t, 0)
+        nnz = int(rp[-1])
+        col = torch.randint(0, 50, (nnz,), generator=g).int()
+        w = torch.randn(nnz, generator=g)
+        dinv = torch.rand(n, generator=g) + 0.1
+        t = torch.randn(50, 8, generator=g).double()
+        plan = StreamPlan(rp, col, w, dinv, seg)
+        assert plan.n_segs * seg >= nnz and int((plan.colf < 0).sum()) == int((deg_t > 0).sum())
+        got = _walk_stream_plan(plan, t, 8)
+        rows = torch.repeat_interleave(torch.arange(n), deg_t)
+        want = torch.zeros(n, 8, dtype=torch.float64).index_add_(0, rows, t[col.long()] * (w.double() * dinv.double()[rows])[:, None])
+        assert not torch.isnan(got).any() and float((got - want).abs().max() / want.abs().max()) < 1e-6, (seg, deg)      # (wd is fp32)
+
+
+def test_peer_arena_layout_is_symmetric_and_ordered():
+    """the arena layout depends only on (world, rows per owner, d_max, batch_max) — identical on every rank — and its regions do not overlap"""
+    from deeprecommendation_b200.peer import PeerShard, _rows_per_part
+    for world, nI, d, bmax in ((8, 62423, 128, 512), (2, 11, 64, 16), (8, 1_000_000, 64, 512)):
+        off = PeerShard.layout(world, _rows_per_part(nI, world), d, bmax)
+        names = ['recv0', 'recv1', 'T0', 'T1', 'rows', 'total']
+        vals = [off[k] for k in names]
+        assert vals == sorted(vals) and vals[0] >= 4096 and all(v % 256 == 0 for v in vals)
+        slab = world * _rows_per_part(nI, world) * d * 4
+        assert all(b - a >= slab for a, b in zip(vals[:4], vals[1:5])) and off['total'] - off['rows'] >= 2 * bmax * d * 4
+        assert world * _rows_per_part(nI, world) >= nI
+
+
+def _peer_partition_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    from deeprecommendation_b200.parallel import RowPartition, column_slice_csr, split_rows
+    g = torch.Generator().manual_seed(5)                      # every rank derives the same CSR, keeps its own user range
+    nI, nU = 40, 90
+    deg = torch.randint(0, 30, (nU,), generator=g)
+    rp = torch.zeros(nU + 1, dtype=torch.int32)
+    rp[1:] = torch.cumsum(deg, 0)
+    users = RowPartition(split_rows(rp, world), rank)
+    edges_own = int(rp[users.r1] - rp[users.r0])
+    tot = torch.tensor([edges_own, users.rows])
+    dist.all_reduce(tot)
+    # item rows restricted to my users' columns: the column slices of all ranks tile the item CSR exactly
+    item_deg = torch.randint(0, 50, (nI,), generator=g)
+    irp = torch.zeros(nI + 1, dtype=torch.int32)
+    irp[1:] = torch.cumsum(item_deg, 0)
+    icol = torch.randint(nI, nI + nU, (int(irp[-1]),), generator=g).int()
+    lrp, lcol = column_slice_csr(irp, icol, nI + users.r0, nI + users.r1)[:2]
+    cnt = torch.tensor([int(lcol.numel())])
+    dist.all_reduce(cnt)
+    q.put((rank, int(tot[0]) == int(rp[-1]), int(tot[1]) == nU, int(cnt[0]) == int(icol.numel()),
+           bool(((lcol >= 0) & (lcol < users.rows)).all()) if lcol.numel() else True))
+    dist.destroy_process_group()
+
+
+def test_peer_user_partition_tiles_the_graph_world2_gloo():
+    """world-size-2 gloo: the users' nnz-balanced ranges and the per-rank column slices of the item rows (the A_l operand of peer.py) tile the graph"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_peer_partition_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(all(r[1:]) for r in res), res
