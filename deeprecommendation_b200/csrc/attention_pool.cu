@@ -30,7 +30,13 @@
 
 #include "common.cuh"
 
+// Compiled twice: as is (the scoring path) and, through csrc/attention_pool_drop.cu, with B200REC_ATT_DROPOUT defined — the training-mode
+// variant that applies AttentionNet's inner Dropout (attention_ncf.py:112-117) to ReLU(Pc + Pr) with a regenerable Philox mask.  The second copy
+// lives in its own namespace and exports ONE entry point (b200rec_attention_pool_dropout), so the scoring kernels stay byte-identical.
 namespace b200rec {
+#ifdef B200REC_ATT_DROPOUT
+namespace attdrop {
+#endif
 
 static int g_att_path = 0;       // b200rec_attention_pool_set_path: 0 auto, 1 register-staged gathers, 2 TMA-staged gathers
 constexpr int ATT_WARPS = 8;      // one CTA per candidate row; the row's non-zeros are split over the warps
@@ -55,6 +61,8 @@ struct AttParams {
   int drop_zero_scores;   // message_dropout is not None: scores == 0.0 -> -inf (:189)
   float score_scale;      // message dropout: kept scores are scaled by 1/(1-p) (:187)
   long long ldPr, ldQ, ldPc;
+  unsigned drop_key, drop_thr16;   // inner dropout (B200REC_ATT_DROPOUT build only): Philox key, keep threshold on 16 bits
+  float drop_scale;
 };
 
 
@@ -189,12 +197,23 @@ struct RowCore {
 #pragma unroll
         for (int jj = 0; jj < LB; ++jj) {
           float s = 0.f;
+#ifdef B200REC_ATT_DROPOUT
+          const int cdrop = __shfl_sync(FULL, my_col, j0 + jj);
+#endif
 #pragma unroll
           for (int hv = 0; hv < HV; ++hv) {
             const float r[4] = {pr[jj][hv].x, pr[jj][hv].y, pr[jj][hv].z, pr[jj][hv].w};
+#ifdef B200REC_ATT_DROPOUT
+            float dm[4] = {1.f, 1.f, 1.f, 1.f};
+            if (MODE == MODE_NET && p.drop_thr16 < 65536u) att_dropout_mult(p.drop_key, p.drop_thr16, p.drop_scale, b, cdrop, lane + 32 * hv, dm);
+#endif
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+#ifdef B200REC_ATT_DROPOUT
+              if (MODE == MODE_NET) s = fmaf(a2[hv][e] * dm[e], fmaxf(pc[hv][e] + r[e], 0.f), s);
+#else
               if (MODE == MODE_NET) s = fmaf(a2[hv][e], fmaxf(pc[hv][e] + r[e], 0.f), s);
+#endif
               else s = fmaf(pc[hv][e], r[e], s);
             }
           }
@@ -248,9 +267,17 @@ struct RowCore {
       if (((valid >> j) & 1u) && h < p.H) {
         const float4 r4 = lds4(sPr + j * 128 + h);
         const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#ifdef B200REC_ATT_DROPOUT
+        float dm[4] = {1.f, 1.f, 1.f, 1.f};
+        if (MODE == MODE_NET && p.drop_thr16 < 65536u) att_dropout_mult(p.drop_key, p.drop_thr16, p.drop_scale, b, __shfl_sync(FULL, my_col, j), lane, dm);
+#endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+#ifdef B200REC_ATT_DROPOUT
+          if (MODE == MODE_NET) s = fmaf(a2[0][e] * dm[e], fmaxf(pc[0][e] + r[e], 0.f), s);
+#else
           if (MODE == MODE_NET) s = fmaf(a2[0][e], fmaxf(pc[0][e] + r[e], 0.f), s);
+#endif
           else s = fmaf(pc[0][e], r[e], s);
         }
       }
@@ -820,9 +847,17 @@ static int dispatch_att(const AttParams& p, const AttInputs& in, cudaStream_t st
   return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: att_dense / user_emb wider than 512");
 }
 
+#ifdef B200REC_ATT_DROPOUT
+}  // namespace attdrop
+#endif
 }  // namespace b200rec
 
 using namespace b200rec;
+#ifdef B200REC_ATT_DROPOUT
+using namespace b200rec::attdrop;
+#define B200REC_ATT_ENTRY b200rec_attention_pool_dropout
+#else
+#define B200REC_ATT_ENTRY b200rec_attention_pool
 
 extern "C" int b200rec_attention_pool_prepare(const b200rec_attention_t* a, b200rec_stream_t stream) {
   if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_prepare: null descriptor");
@@ -851,7 +886,9 @@ extern "C" size_t b200rec_attention_pool_workspace_csr(int64_t B, int64_t I, int
   return (B > 0 && I > 0 && U > 0) ? att_layout(B, I, U, false, max_row_nnz, nnz).total : 0;
 }
 
-extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream) {
+#endif  // !B200REC_ATT_DROPOUT
+
+extern "C" int B200REC_ATT_ENTRY(const b200rec_attention_t* a, b200rec_stream_t stream) {
   if (!a) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: null descriptor");
   if (a->B < 0 || a->I < 0 || a->H <= 0 || a->U <= 0 || (a->H % 4) || (a->U % 4))
     return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: H and U must be positive multiples of 4");
@@ -875,6 +912,21 @@ extern "C" int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stre
   p.ldPr = a->ld_pr ? a->ld_pr : a->H;
   p.ldQ = a->ld_q ? a->ld_q : a->U;
   p.ldPc = a->ld_pc ? a->ld_pc : a->H;
+  p.drop_key = 0u; p.drop_thr16 = 65536u; p.drop_scale = 1.f;
+#ifdef B200REC_ATT_DROPOUT
+  if (!(a->dropout_p >= 0.f && a->dropout_p < 1.f)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_dropout: need 0 <= dropout_p < 1");
+  if (a->B >= (1 << 26)) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool_dropout: more than 2^26 candidate rows");
+  {
+    unsigned thr = (unsigned)((1.0 - (double)a->dropout_p) * 65536.0 + 0.5);
+    if (thr < 1u) thr = 1u;
+    if (thr > 65536u) thr = 65536u;
+    p.drop_thr16 = thr;
+    p.drop_scale = 65536.f / (float)thr;
+    p.drop_key = (unsigned)(a->dropout_seed ^ (a->dropout_seed >> 32));
+  }
+#else
+  if (a->dropout_p != 0.f) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: inner dropout is applied by b200rec_attention_pool_dropout");
+#endif
   if (p.ldPc < a->H || (p.ldPc % 4)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: bad Pc leading dimension");
   if (p.ldPr < a->H || p.ldQ < a->U || (p.ldPr % 4) || (p.ldQ % 4)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: bad table leading dimension");
   if (p.Ec && (!p.Er || p.E <= 0)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: training mask needs both embeddings");

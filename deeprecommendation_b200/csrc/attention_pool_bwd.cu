@@ -34,6 +34,8 @@ struct AttBwdParams {
   int n_slices, slice_cols;  // grid.y and the columns per slice (multiple of 32); a row's non-zeros are dealt out over gridDim.y CTAs
   float score_scale;
   float *dPc, *dPr, *dQ, *da2_rows, *da20_rows;     // dPc (B,H) and the per-row parts are written; dPr (I,H), dQ (I,U) are added to
+  unsigned drop_key, drop_thr16;                    // AttentionNet's inner dropout: the forward's Philox mask is regenerated (65536 = off)
+  float drop_scale;
 };
 
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
@@ -44,11 +46,12 @@ template <int HV, int UV, int MODE>
 struct BwdRow {
   const AttBwdParams& p;
   const int lane;
+  const int brow;
   float pc[HV][4], a2[HV][4], gb[UV][4];
   float dpc[HV][4], da2[HV][4];
   float da20, gdot;
 
-  __device__ BwdRow(const AttBwdParams& p_, int lane_, int b) : p(p_), lane(lane_) {
+  __device__ BwdRow(const AttBwdParams& p_, int lane_, int b) : p(p_), lane(lane_), brow(b) {
     da20 = 0.f;
 #pragma unroll
     for (int hv = 0; hv < HV; ++hv) {
@@ -117,13 +120,15 @@ struct BwdRow {
         const int h = lane * 4 + hv * 128;
         const float r[4] = {pr[k][hv].x, pr[k][hv].y, pr[k][hv].z, pr[k][hv].w};
         float t[4];
+        float dm[4] = {1.f, 1.f, 1.f, 1.f};                         // hidden = ReLU(z) ∘ dm: the forward's dropout multipliers of this pair
+        if (MODE == BWD_NET && p.drop_thr16 < 65536u) att_dropout_mult(p.drop_key, p.drop_thr16, p.drop_scale, brow, ii[k], lane + 32 * hv, dm);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (MODE == BWD_NET) {
             const float z = pc[hv][e] + r[e];
-            t[e] = z > 0.f ? ds * a2[hv][e] : 0.f;
+            t[e] = z > 0.f ? ds * a2[hv][e] * dm[e] : 0.f;
             dpc[hv][e] += t[e];
-            da2[hv][e] = fmaf(ds, fmaxf(z, 0.f), da2[hv][e]);
+            da2[hv][e] = fmaf(ds * dm[e], fmaxf(z, 0.f), da2[hv][e]);
           } else {
             dpc[hv][e] = fmaf(ds, r[e], dpc[hv][e]);
             t[e] = ds * pc[hv][e];
@@ -221,6 +226,16 @@ extern "C" int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a,
   p.ld_um = a->ld_user_matrix ? a->ld_user_matrix : a->I; p.ldo = a->ldo ? a->ldo : a->U; p.ldg = a->ld_grad_out ? a->ld_grad_out : a->U;
   p.B = (int)a->B; p.I = (int)a->I; p.H = a->H; p.U = a->U;
   p.score_scale = a->score_scale == 0.f ? 1.f : a->score_scale;
+  p.drop_key = 0u; p.drop_thr16 = 65536u; p.drop_scale = 1.f;
+  if (a->dropout_p != 0.f) {                        // same derivation as b200rec_attention_pool_dropout
+    if (!(a->dropout_p > 0.f && a->dropout_p < 1.f) || a->B >= (1 << 26)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_backward: bad dropout_p");
+    unsigned thr = (unsigned)((1.0 - (double)a->dropout_p) * 65536.0 + 0.5);
+    if (thr < 1u) thr = 1u;
+    if (thr > 65536u) thr = 65536u;
+    p.drop_thr16 = thr;
+    p.drop_scale = 65536.f / (float)thr;
+    p.drop_key = (unsigned)(a->dropout_seed ^ (a->dropout_seed >> 32));
+  }
   {
     const int n_slices = a->n_slices > 1 ? a->n_slices : 1;
     if (n_slices > 65535) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_backward: too many slices");

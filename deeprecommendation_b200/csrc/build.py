@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(os.path.dirname(HERE), 'libb200rec.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-SOURCES = ['api.cu', 'gemm_f32.cu', 'gemm_tc.cu', 'mlp_tower.cu', 'attention_pool.cu', 'attention_pool_bwd.cu', 'spmm.cu', 'graph_build.cu', 'topk.cu', 'allpairs.cu', 'node_gemm.cu', 'peer.cu', 'gather_sum.cu', 'spmm_stream.cu']
+SOURCES = ['api.cu', 'gemm_f32.cu', 'gemm_tc.cu', 'mlp_tower.cu', 'attention_pool.cu', 'attention_pool_bwd.cu', 'spmm.cu', 'graph_build.cu', 'topk.cu', 'allpairs.cu', 'node_gemm.cu', 'peer.cu', 'gather_sum.cu', 'spmm_stream.cu', 'attention_pool_drop.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr', '-I', os.path.join(ROOT, 'include')]
 
@@ -42,8 +42,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
         srcp = os.path.join(HERE, src)
+        included = [os.path.join(HERE, 'attention_pool.cu')] if src == 'attention_pool_drop.cu' else []     # (that unit #includes the other one)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(p) for p in [srcp] + [d for d in _deps() if not d.endswith('.cu')]):
+                os.path.getmtime(p) for p in [srcp] + included + [d for d in _deps() if not d.endswith('.cu')]):
             return obj, ''
         r = subprocess.run([NVCC] + FLAGS + extra + ['-c', srcp, '-o', obj], capture_output=True, text=True)
         if r.returncode != 0:

@@ -92,4 +92,30 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// ---- counter-based random bits for training-time dropout masks: Philox2x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3";
+// round: (hi, lo) = 0xD256D193 * c0;  c0' = hi ^ key ^ c1;  c1' = lo;  key += 0x9E3779B9).  64 bits per (counter, key); the forward and the
+// backward kernel regenerate the same mask from the same (seed, element index) — nothing is stored.
+__host__ __device__ __forceinline__ uint2 philox2x32_10(unsigned c0, unsigned c1, unsigned key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long prod = 0xD256D193ull * (unsigned long long)c0;
+    const unsigned hi = (unsigned)(prod >> 32), lo = (unsigned)prod;
+    c0 = hi ^ key ^ c1;
+    c1 = lo;
+    key += 0x9E3779B9u;
+  }
+  return make_uint2(c0, c1);
+}
+
+// Dropout multipliers of 4 consecutive hidden units of one (candidate row b, rated item c) pair of AttentionNet (attention_ncf.py:112-117:
+// Linear -> ReLU -> Dropout(p) -> Linear): unit group `g` = (hidden index / 4).  keep iff 16 random bits < thr16 = round((1-p)·65536);
+// the multiplier of a kept unit is 65536 / thr16 (exactly unbiased for the keep probability actually used).
+__device__ __forceinline__ void att_dropout_mult(unsigned key, unsigned thr16, float scale, int b, int c, int g, float (&m)[4]) {
+  const uint2 r = philox2x32_10((unsigned)c, ((unsigned)b << 6) | (unsigned)g, key);
+  m[0] = (r.x & 0xffffu) < thr16 ? scale : 0.f;
+  m[1] = (r.x >> 16) < thr16 ? scale : 0.f;
+  m[2] = (r.y & 0xffffu) < thr16 ? scale : 0.f;
+  m[3] = (r.y >> 16) < thr16 ? scale : 0.f;
+}
+
 }  // namespace b200rec

@@ -218,9 +218,16 @@ class AttentionNCF(NCF):
                     um = um * keep                   # a dropped pair gets -inf, i.e. behaves like "unrated"
                     scale = 1.0 / (1.0 - self.message_dropout)
             train_mask = (Ec, Er, 1e-5, 1e-5)                                           # isclose(atol=1e-5) (:199)
+        inner = None
+        if self.training and mode == L.ATT_NET and len(self.AttentionNet) > 1:
+            p_inner = float(self.AttentionNet[2].p)                                     # Linear -> ReLU -> Dropout(p) -> Linear (:112-117)
+            if p_inner > 0.0:
+                # the mask is a Philox stream keyed by a seed drawn from torch's default generator (reproducible under torch.manual_seed); it
+                # cannot be bit-matched to torch's own dropout stream, like every other dropout of the reference
+                inner = (p_inner, int(torch.randint(0, 2 ** 62, (1,)).item()))
         res = ops.attention_pool(Pc, Pr, Q, mode=mode, a2=a2, a20=a20,
                                  bU=bU, user_matrix=um, return_attention_weights=return_attention_weights,
-                                 train_mask=train_mask, drop_zero_scores=drop_zero, score_scale=scale)
+                                 train_mask=train_mask, drop_zero_scores=drop_zero, score_scale=scale, inner_dropout=inner)
         user_emb, att = res if return_attention_weights else (res, None)
         if user_emb.shape[1] != U:
             user_emb = user_emb[:, :U]

@@ -633,7 +633,7 @@ def attention_prepare(user_matrix, U):
 
 def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None, user_matrix=None, csr=None,
                        return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0, use_workspace=True, max_row_nnz=0,
-                       prepared=None):
+                       prepared=None, inner_dropout=None):
     """out (B,U) [, att (B,I)] — b200rec_attention_pool.  `csr` = (row_ptr int32, col int32, val fp32); `max_row_nnz` (CSR only,
     optional) = a host-known bound of the row lengths, so that the segment grid is not sized by I."""
     _require_cuda(Pc, Pr, Q, user_matrix)
@@ -706,8 +706,15 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
     d.score_scale = float(score_scale)
     if B == 0:
         return (out, att) if return_attention_weights else out
+    entry = L.lib().b200rec_attention_pool
+    if inner_dropout is not None and inner_dropout[0] > 0.0:
+        # training: AttentionNet's Dropout between ReLU and the head Linear (attention_ncf.py:112-117), mask = Philox keyed by `seed`
+        if mode != L.ATT_NET or Pr.dtype != torch.float32:
+            raise ValueError('inner dropout belongs to the AttentionNet variant with fp32 tables')
+        d.dropout_p, d.dropout_seed = float(inner_dropout[0]), int(inner_dropout[1]) & (2 ** 64 - 1)
+        entry = L.lib().b200rec_attention_pool_dropout
     with torch.cuda.device(Pc.device), _timed('attention_pool', (B, I, H, U)):
-        L.check(L.lib().b200rec_attention_pool(C.byref(d), _stream()), 'attention_pool')
+        L.check(entry(C.byref(d), _stream()), 'attention_pool')
     return (out, att) if return_attention_weights else out
 
 
@@ -935,7 +942,7 @@ def _f32_rows(t):
     return t
 
 
-def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode, score_scale=1.0):
+def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode, score_scale=1.0, inner_dropout=None):
     """(dPc, dPr, dQ, da2, da20) — b200rec_attention_pool_backward (csrc/attention_pool_bwd.cu).  `att` / `out` are the forward's
     attention weights and output; da2 / da20 are None in mode DOT."""
     _require_cuda(Pc, Pr, Q, um, att, out, grad_out)
@@ -974,6 +981,8 @@ def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode,
     d.dPc, d.dPr, d.dQ = dPc.data_ptr(), dPr.data_ptr(), dQ.data_ptr()
     if net:
         d.da2_rows, d.da20_rows = da2_rows.data_ptr(), da20_rows.data_ptr()
+    if inner_dropout is not None and inner_dropout[0] > 0.0:
+        d.dropout_p, d.dropout_seed = float(inner_dropout[0]), int(inner_dropout[1]) & (2 ** 64 - 1)
     with torch.cuda.device(dev), _timed('attention_pool_backward', (B, I, H, U)):
         L.check(L.lib().b200rec_attention_pool_backward(C.byref(d), _stream()), 'attention_pool_backward')
     if S > 1:
@@ -986,10 +995,10 @@ class _AttentionPoolFn(torch.autograd.Function):
     only the column sums of the per-row a2 / a20 parts and of grad_out (dbU) are torch reductions."""
 
     @staticmethod
-    def forward(ctx, Pc, Pr, Q, a2, a20, bU, um, mode, want_att, train_mask, drop_zero_scores, score_scale):
+    def forward(ctx, Pc, Pr, Q, a2, a20, bU, um, mode, want_att, train_mask, drop_zero_scores, score_scale, inner_dropout=None):
         out, att = attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, user_matrix=um, return_attention_weights=True,
-                                      train_mask=train_mask, drop_zero_scores=drop_zero_scores, score_scale=score_scale)
-        ctx.mode, ctx.scale = mode, score_scale
+                                      train_mask=train_mask, drop_zero_scores=drop_zero_scores, score_scale=score_scale, inner_dropout=inner_dropout)
+        ctx.mode, ctx.scale, ctx.inner_dropout = mode, score_scale, inner_dropout
         ctx.shapes = (None if a2 is None else a2.shape, None if a20 is None else a20.shape, None if bU is None else bU.shape)
         ctx.save_for_backward(Pc, Pr, Q, a2, bU, um, att, out)
         ctx.mark_non_differentiable(att)
@@ -998,24 +1007,25 @@ class _AttentionPoolFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _g_att=None):
         Pc, Pr, Q, a2, bU, um, att, out = ctx.saved_tensors
-        dPc, dPr, dQ, da2, da20 = attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, g, ctx.mode, ctx.scale)
+        dPc, dPr, dQ, da2, da20 = attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, g, ctx.mode, ctx.scale, ctx.inner_dropout)
         s_a2, s_a20, s_bU = ctx.shapes
         d_a2 = da2.view(s_a2) if (s_a2 is not None and da2 is not None) else None
         d_a20 = da20.view(s_a20) if (s_a20 is not None and da20 is not None) else None
         d_bU = g.sum(0).view(s_bU) if s_bU is not None else None
-        return (dPc, dPr, dQ, d_a2, d_a20, d_bU, None, None, None, None, None, None)
+        return (dPc, dPr, dQ, d_a2, d_a20, d_bU, None, None, None, None, None, None, None)
 
 
 def attention_pool(Pc, Pr, Q, *, mode, a2, a20, bU, user_matrix, return_attention_weights=False, train_mask=None,
-                   drop_zero_scores=False, score_scale=1.0):
+                   drop_zero_scores=False, score_scale=1.0, inner_dropout=None):
+    """`inner_dropout` = (p, seed): AttentionNet's Dropout on ReLU(Pc + Pr) in training mode (fused, regenerated by the backward kernel)."""
     needs = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (Pc, Pr, Q, a2, a20, bU))
     if needs:
         out, att = _AttentionPoolFn.apply(Pc, Pr, Q, a2, a20, bU, user_matrix, mode, return_attention_weights, train_mask,
-                                          drop_zero_scores, score_scale)
+                                          drop_zero_scores, score_scale, inner_dropout)
         return (out, att) if return_attention_weights else out
     return attention_pool_raw(Pc, Pr, Q, mode=mode, a2=a2, a20=a20, bU=bU, user_matrix=user_matrix,
                               return_attention_weights=return_attention_weights, train_mask=train_mask,
-                              drop_zero_scores=drop_zero_scores, score_scale=score_scale)
+                              drop_zero_scores=drop_zero_scores, score_scale=score_scale, inner_dropout=inner_dropout)
 
 
 # ------------------------------------------------------------------------------------------------------------------

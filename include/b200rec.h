@@ -217,10 +217,16 @@ typedef struct {
   int64_t nnz;            /* (0 = unknown).  They only size the work list / partial slots: b200rec_attention_pool_workspace_csr(). */
   int prepared;           /* 1 = b200rec_attention_pool_prepare already ran on this workspace for this user_matrix / CSR */
   int64_t ld_pc;          /* leading dimension of Pc in elements (a column slice of the [Ec | Pc] projection is used in place); 0 = H */
+  float dropout_p;        /* training only, b200rec_attention_pool_dropout: p of the Dropout between AttentionNet's ReLU and its head Linear */
+  uint64_t dropout_seed;  /* (attention_ncf.py:112-117); mask = Philox2x32-10 keyed by the seed, regenerated by the backward kernel */
 } b200rec_attention_t;
 size_t b200rec_attention_pool_workspace(int64_t B, int64_t I, int U, int dense);
 size_t b200rec_attention_pool_workspace_csr(int64_t B, int64_t I, int U, int64_t max_row_nnz, int64_t nnz);
 int b200rec_attention_pool(const b200rec_attention_t* a, b200rec_stream_t stream);
+/* The same op with AttentionNet's inner Dropout applied in training mode: hidden = ReLU(Pc[b] + Pr[i]) ∘ m / keep, m ~ Bernoulli(keep), keep =
+ * round((1 - dropout_p)·65536) / 65536, one Philox2x32-10 call (counter = (i, b·64 + hidden group), key = seed) per 4 hidden units
+ * (csrc/common.cuh).  A separately compiled copy of the kernels (csrc/attention_pool_drop.cu): the scoring build above is untouched. */
+int b200rec_attention_pool_dropout(const b200rec_attention_t* a, b200rec_stream_t stream);
 /* First phase of the segment-parallel path on its own: compaction of the dense matrix / work list into `workspace`.  It reads only
  * user_matrix (or the CSR) — B, I, U, the matrix fields and the workspace of `a` must be set, the tables may be NULL — so a host can
  * launch it on a second stream while the projection GEMMs run, then call b200rec_attention_pool with the same workspace and prepared = 1. */
@@ -260,6 +266,8 @@ typedef struct {
   float* da20_rows;
   int n_slices;             /* 0 / 1 = one CTA per row; n > 1 = the columns are dealt out over n CTAs per row and dPc, da2_rows, da20_rows
                              * hold n parts of B rows each (part-major), which the caller adds */
+  float dropout_p;          /* the forward's inner dropout (b200rec_attention_pool_dropout): same p and seed regenerate the same mask; 0 = none */
+  uint64_t dropout_seed;
 } b200rec_attention_bwd_t;
 int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a, b200rec_stream_t stream);
 
