@@ -382,15 +382,15 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
                     'frac': round(ach / peaks['hbm_gbs'], 4), 'traffic': _traffic('attention'), 'traffic_source': TS, 'peak_source': peaks['src'],
                     'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(ab)}
         flops = 2.0 * M * K * N
-        tf32 = w.get('gemm', 'tf32x3') == 'tf32x3'
-        issue = 3.0 if tf32 else 1.0
+        tf32 = w.get('gemm', 'bf16x3') == 'tf32x3'
+        issue = 1.0 if w.get('gemm') == 'bf16' else 3.0             # hi.hi + hi.lo + lo.hi in both split engines
         pipe = peaks['bf16_tflops'] / 2.0 if tf32 else peaks['bf16_tflops']
         t_hbm, t_pipe = ab / (peaks['hbm_gbs'] * 1e9), flops / (pipe * 1e12)
         t_roof = max(t_hbm, t_pipe)
         ach_tf = flops / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
         tensor = t_pipe > t_hbm
         return {'bound': 'tensor' if tensor else 'hbm',
-                'kernel': f'gemm_tc_kernel + tc_splitk_reduce_kernel (K1a linear {M}x{K}->{N}, tcgen05 {w.get("gemm", "tf32x3")}, 128x256 tiles + split-K)',
+                'kernel': f'gemm_tc_kernel + tc_splitk_reduce_kernel (K1a linear {M}x{K}->{N}, tcgen05 {w.get("gemm", "bf16x3")}, 128x256 tiles + split-K)',
                 'achieved': round(ach_tf, 1) if tensor else round(ach, 1), 'peak': round(pipe, 1) if tensor else peaks['hbm_gbs'],
                 'unit': 'TFLOP/s' if tensor else 'GB/s', 'frac': round(t_roof / (kms * 1e-3), 4) if kms > 0 else 0.0, 'roofline_us': round(t_roof * 1e6, 2),
                 'traffic': _traffic('attention'), 'traffic_source': TS, 'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(ab),
@@ -1590,8 +1590,8 @@ def main():
     ap.add_argument('--graph5-scale', type=float, default=1.0, help='configs[4] at a fraction of its size (users, items and edges scaled together)')
     ap.add_argument('--graph-scale', type=float, default=1.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--gemm', default='tf32x3', choices=['simt', 'tf32x3', 'bf16'],
-                    help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity) or tcgen05 bf16')
+    ap.add_argument('--gemm', default='bf16x3', choices=['simt', 'tf32x3', 'bf16', 'bf16x3'],
+                    help='K1a engine for large-M linears: fp32 FFMA, tcgen05 3xTF32 (fp32 parity), the same with the wide form on a bf16 hi/lo split (fp32 parity, default) or plain tcgen05 bf16')
     ap.add_argument('--skip-hbm-regime', action='store_true')
     ap.add_argument('--no-train-step', action='store_true', help='skip the eager train-step legs (AttentionNCF, GraphNCF)')
     ap.add_argument('--graph-scheme', default='peer', choices=['peer', 'reduce', 'gather'],

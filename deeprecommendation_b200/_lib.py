@@ -6,12 +6,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libb200rec.so')
+LIB_PATH = os.environ.get('B200REC_LIB') or os.path.join(_HERE, 'libb200rec.so')     # (B200REC_LIB: an experimental build of the same ABI, A/B measurements)
 
 OK, ERR_CUDA, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 F32, BF16 = 0, 1
 ATT_NET, ATT_DOT = 0, 1
-TC_TF32X3, TC_BF16 = 0, 1
+TC_TF32X3, TC_BF16, TC_BF16X3 = 0, 1, 2
 AP_BF16, AP_BF16X2 = 0, 1
 MLP_MAX_LAYERS = 8
 PEER_MAX, PEER_CHANNELS, PEER_HANDLE_BYTES = 16, 16, 64
@@ -74,8 +74,8 @@ SIGNATURES = {
     'b200rec_linear_tc_splitk_workspace': (c_sz, [c_i64, c_i64, c_i64, c_int]),
     'b200rec_linear_tc_splitk': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     'b200rec_linear_tc': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),
-    'b200rec_linear_tc_wide_workspace': (c_sz, [c_i64, c_i64, c_i64]),
-    'b200rec_linear_tc_wide': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    'b200rec_linear_tc_wide_workspace': (c_sz, [c_i64, c_i64, c_i64, c_int]),
+    'b200rec_linear_tc_wide': (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     'b200rec_linear_shortk': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_int, c_vp]),
     'b200rec_linear_shortk_push': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, C.POINTER(c_vp), c_int, c_i64, c_i64, c_int, c_vp]),
     'b200rec_linear_sparse': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_vp]),

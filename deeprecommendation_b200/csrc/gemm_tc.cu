@@ -13,6 +13,9 @@
 //             (kind::tf32, fp32 accumulate in TMEM).  The dropped lo·lo term and the truncation of lo are ~2^-21
 //             relative, i.e. inside the reference tolerance rel <= 1e-5.
 //   TC_BF16   (bf16 mode, rel <= 1e-2): one kind::f16 MMA per k-step on bf16-rounded operands.
+//   TC_BF16X3 (wide form only): x = hi + lo with hi = bf16(x), lo = bf16(x - hi); the same three products in kind::f16.  Twice the MMA rate
+//             of TF32 and half the operand bytes per k, at 16 instead of 21 mantissa bits per operand: ~4e-6 relative to the largest
+//             output at K = 2094 (measured), still inside the 1e-5 budget.  Opt-in (`engine='bf16x3'`).
 //
 // CTA = 128 (M) x 128 (N) output tile, accumulator = 128 TMEM columns x 128 lanes (fp32), NSTAGE-deep smem ring.
 // Warp roles: warps 0-7 producers, then epilogue (tcgen05.ld 32x32b: warp w reads TMEM lanes 32*(w%4).., columns
@@ -23,9 +26,20 @@
 
 namespace b200rec {
 
-enum { TC_TF32X3 = 0, TC_BF16 = 1 };
+enum { TC_TF32X3 = 0, TC_BF16 = 1, TC_BF16X3 = 2 };
+// element width and number of operand planes of a mode
+template <int MODE> struct TcMode {
+  static constexpr bool E16 = MODE != TC_TF32X3;            // bf16 elements (64 per 128-byte swizzle row), kind::f16
+  static constexpr int KB = E16 ? 64 : 32;                  // source elements per k-block
+  static constexpr int PLANES = MODE == TC_BF16 ? 1 : 2;    // hi [, lo]
+};
+static inline int tc_kb(int mode) { return mode == TC_TF32X3 ? 32 : 64; }
+static inline int tc_planes(int mode) { return mode == TC_BF16 ? 1 : 2; }
 
 constexpr int TC_BM = 128, TC_BN = 128;
+#ifndef TC_PF16
+#define TC_PF16 1                                   // k-blocks of 64 in flight ahead of the store in the bf16 modes
+#endif
 constexpr int TC_PRODUCERS = 256;                 // 8 warps
 constexpr int TC_THREADS = TC_PRODUCERS + 32;     // + MMA warp
 constexpr int TILE_BYTES = 128 * 128;             // one operand tile: 128 rows x 128 bytes
@@ -66,7 +80,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 template <int MODE>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (MODE == TC_BF16) {
+  if constexpr (TcMode<MODE>::E16) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
@@ -94,7 +108,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // (BF16 = 1, TF32 = 2), both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 template <int MODE, int BN = TC_BN>
 __device__ __forceinline__ uint32_t make_idesc() {
-  const uint32_t fmt = (MODE == TC_BF16) ? 1u : 2u;
+  const uint32_t fmt = TcMode<MODE>::E16 ? 1u : 2u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
@@ -111,7 +125,7 @@ struct TcParams {
   const float* bias; const float* row_scale; int relu;
   const unsigned char* Wp;   // optional: W pre-packed by pack_weights_kernel (swizzled tiles), moved by TMA bulk copies
   const long long* row_index;   // optional: row m of the GEMM is row row_index[m] of X (resident profile table + ids)
-  int dbg;     // experiments only (B200REC_TC_DBG): 1 = no MMA, 2 = no prefetch loads, 4 = no proxy fence
+  int dbg;     // experiments only (B200REC_TC_DBG): 1 = no MMA, 2 = no prefetch loads, 4 = no proxy fence, 8 = no X loads at all, 16 = no W copies
   // split-K (b200rec_linear_tc_splitk): CTA z = blockIdx.z owns k-blocks [z*kb_per_split, ...) and writes its raw fp32 tile to
   // partial[z] (M x N, ld N); bias / scale / activation are applied by tc_splitk_reduce_kernel.  0 = the whole K in one CTA.
   int kb_per_split;
@@ -135,29 +149,53 @@ struct TcBatch {
 // IADD + IMAD.WIDE + LDG and a store LOP/FADD + STS.  History (profiles/r01/gemm_tc_notes.md): half-row-per-thread loads
 // sat on the L1 tag stage; per-load bounds branches made ptxas wrap every LDG in BSSY/BSYNC; recomputing addresses in the
 // loop cost ~1200 instructions per thread and k-block.
+// (x0, x1) -> packed bf16 pairs hi = bf16(x), lo = bf16(x - hi): 2 F2FP + 2 bit ops + 2 FADD (the __nv_bfloat162 helpers cost a re-pack per pair)
+__device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));          // upper half = x1, lower half = x0
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t v0, uint32_t v1) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+}
+
+// Round 2 (profiles/r02/ncu_full_gemm_bf16x3_v1.txt): the producers, not the loads, set the pace — ~35 instructions per (row, lane) and
+// k-block, two warps per scheduler.  Three changes took that to ~12: (1) shared-memory stores are `st.shared` on 32-bit addresses (the generic
+// 64-bit `ST` form kept a pointer pair per row and plane in registers); the swizzled offset of row `it` is a compile-time constant plus one of
+// 8 / RPI run-time XOR terms (`xk`), because row r = 16·warp + it·RPI + sub has r & 7 = ((it·RPI) & 7) | sub with disjoint bits; (2) no row
+// mask: rows past M are clamped at load time and only ever reach accumulator rows that are never written; (3) the k mask runs in the one
+// k-block that crosses K (`store<true>`), every other block stores unmasked.
 template <int MODE, int EPL>
 struct TileAddr {
-  static constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
+  static constexpr int KB = TcMode<MODE>::KB;
   static constexpr int LPR = KB / EPL, RPI = 32 / LPR, ITER = 16 / RPI;
+  static constexpr int NX = (8 / RPI) > 0 ? (8 / RPI) : 1;   // distinct (it·RPI) & 7 values
   unsigned goff[ITER];        // element offset of (clamped row, this lane's first column at k = 0)
-  unsigned soff[ITER];        // byte offset inside a 128x128-byte swizzled tile
-  unsigned row_ok;            // bit it: the row exists
+  unsigned xk[NX];            // tile-relative byte offset of this lane's chunk for every XOR term, + the lane's fixed part
   int kcol;                   // this lane's first column inside a k-block
 
   __device__ __forceinline__ void init(long long ld, int row0, int rows_total, int warp, int lane, const long long* row_index = nullptr) {
     kcol = (lane % LPR) * EPL;
-    row_ok = 0u;
-    const unsigned byte = (unsigned)kcol * ((MODE == TC_BF16) ? 2u : 4u);
+    const unsigned byte = (unsigned)kcol * (TcMode<MODE>::E16 ? 2u : 4u);
+    const unsigned sub = (unsigned)(lane / LPR);
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
-      const int r = warp * 16 + it * RPI + lane / LPR;
-      const int grow = row0 + r;
-      row_ok |= (grow < rows_total ? 1u : 0u) << it;
+      const int grow = row0 + warp * 16 + it * RPI + (int)sub;
       const int crow = min(grow, rows_total - 1);
       const long long srow = row_index ? __ldg(row_index + crow) : (long long)crow;
       goff[it] = (unsigned)(srow * ld) + (unsigned)kcol;
-      soff[it] = (unsigned)(r >> 3) * 1024u + (unsigned)(r & 7) * 128u + (((byte >> 4) ^ (unsigned)(r & 7)) << 4) + (byte & 15u);
     }
+    const unsigned fixed = (unsigned)warp * 2048u + sub * 128u + (byte & 15u);
+#pragma unroll
+    for (int x = 0; x < NX; ++x) xk[x] = fixed + ((((byte >> 4) ^ sub) ^ (unsigned)((x * RPI) & 7)) << 4);
+  }
+  // byte offset of row `it` of this lane inside a 128 x 128-byte swizzled tile (`it` is a compile-time constant after unrolling)
+  __device__ __forceinline__ unsigned soff(int it) const {
+    return xk[it % NX] + (unsigned)(((it * RPI) >> 3) * 1024 + ((it * RPI) & 7) * 128);
   }
 };
 
@@ -174,10 +212,10 @@ struct TileRegs {
     const int k = k0 + a.kcol;
     k_ok = k < K;
     if constexpr (VEC) {
-      const unsigned kc = k_ok ? (unsigned)k0 : 0u;      // out-of-range columns re-read k-block 0 and are zeroed at store time
+      const float* srck = src + (k_ok ? (unsigned)k0 : 0u);   // out-of-range columns re-read k-block 0 and are zeroed at store time
 #pragma unroll
       for (int it = 0; it < ITER; ++it) {
-        const float* p = src + (a.goff[it] + kc);
+        const float* p = srck + a.goff[it];
         if constexpr (EPL == 4) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(p));
           v[it][0] = t.x; v[it][1] = t.y; v[it][2] = t.z; v[it][3] = t.w;
@@ -200,21 +238,33 @@ struct TileRegs {
     }
   }
 
-  __device__ __forceinline__ void store(unsigned char* tile_hi, unsigned char* tile_lo, const Addr& a) const {
+  // MASK: this k-block crosses K — lanes past the end store zeros (uniform per CTA and k-block; false everywhere else)
+  template <bool MASK>
+  __device__ __forceinline__ void store(uint32_t tile_hi, uint32_t tile_lo, const Addr& a) const {
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
-      const bool ok = k_ok && ((a.row_ok >> it) & 1u);
       float x[EPL];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) x[e] = ok ? v[it][e] : 0.f;
+      for (int e = 0; e < EPL; ++e) x[e] = (!MASK || k_ok) ? v[it][e] : 0.f;
+      const uint32_t so = a.soff(it);
       if constexpr (MODE == TC_BF16) {
-        unsigned char* dst = tile_hi + a.soff[it];
         __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]);
         if constexpr (EPL == 4) {
           __nv_bfloat162 b1 = __floats2bfloat162_rn(x[2], x[3]);
-          *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+          sts64(tile_hi + so, *reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
         } else {
-          *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(&b0);
+          sts32(tile_hi + so, *reinterpret_cast<uint32_t*>(&b0));
+        }
+      } else if constexpr (MODE == TC_BF16X3) {
+        uint32_t h[EPL / 2], l[EPL / 2];
+#pragma unroll
+        for (int e = 0; e < EPL; e += 2) bf16_split2(x[e], x[e + 1], h[e / 2], l[e / 2]);
+        if constexpr (EPL == 4) {
+          sts64(tile_hi + so, h[0], h[1]);
+          sts64(tile_lo + so, l[0], l[1]);
+        } else {
+          sts32(tile_hi + so, h[0]);
+          sts32(tile_lo + so, l[0]);
         }
       } else {
         float hi[EPL], lo[EPL];
@@ -224,11 +274,11 @@ struct TileRegs {
           lo[e] = x[e] - hi[e];
         }
         if constexpr (EPL == 4) {
-          *reinterpret_cast<float4*>(tile_hi + a.soff[it]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(tile_lo + a.soff[it]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          sts128(tile_hi + so, __float_as_uint(hi[0]), __float_as_uint(hi[1]), __float_as_uint(hi[2]), __float_as_uint(hi[3]));
+          sts128(tile_lo + so, __float_as_uint(lo[0]), __float_as_uint(lo[1]), __float_as_uint(lo[2]), __float_as_uint(lo[3]));
         } else {
-          *reinterpret_cast<float2*>(tile_hi + a.soff[it]) = make_float2(hi[0], hi[1]);
-          *reinterpret_cast<float2*>(tile_lo + a.soff[it]) = make_float2(lo[0], lo[1]);
+          sts64(tile_hi + so, __float_as_uint(hi[0]), __float_as_uint(hi[1]));
+          sts64(tile_lo + so, __float_as_uint(lo[0]), __float_as_uint(lo[1]));
         }
       }
     }
@@ -240,6 +290,10 @@ struct TileRegs {
 // the tensor pipe — set the pace of a k-block: profiles/r01/gemm_tc_notes.md).  A stage is X (32 KB) + two packed W tiles (64 KB);
 // two stages fit.  TMEM holds two 256-column accumulators (hi·hi | cross terms); the wide form always runs split-K, which keeps the
 // accumulate chains short (see NACC below) and fills the device when M / 128 alone does not.
+// Measured and dropped (round 2, profiles/r02/gemm_pair_ncu_v1.log): launching the two k-splits of a tile as a thread-block cluster so that split 0
+// can wait for split 1's tile and finish the output itself (no second slab, no reduction kernel).  Both ways of handing the tile over lost:
+// through distributed shared memory (~21 B/clk: +7 us), and through L2 with only the cluster barrier as the signal — the cluster launch of
+// these 193 KB CTAs alone takes the kernel from 30 us to 49 us.
 template <int MODE, int NSTAGE, int EPL, bool VEC, bool WPACK, int BN = TC_BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
@@ -250,8 +304,8 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     if (t < batch.n && (int)blockIdx.y >= batch.tile_start[t]) q = t;
   const TcParams& p = batch.prob[q];
   if ((int)blockIdx.x * BN >= p.N) return;                      // this problem has fewer n-tiles than the widest of the batch
-  constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
-  constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
+  constexpr int KB = TcMode<MODE>::KB;
+  constexpr int PLANES = TcMode<MODE>::PLANES;
   constexpr int NT = BN / 128;                                  // packed 128-row W tiles per stage
   constexpr int A_BYTES = PLANES * TILE_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + NT * PLANES * TILE_BYTES;   // A (hi[,lo]) + B (hi[,lo]) x NT
@@ -278,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full_bar[s], TC_PRODUCERS + (WPACK ? 1 : 0));     // + the expect_tx arrive of the W bulk copy
+      mbar_init(&full_bar[s], TC_PRODUCERS / 32 + (WPACK ? 1 : 0));   // one arrive per producer warp + the expect_tx arrive of the W bulk copy
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
@@ -299,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     // SAME W tile at the same moment.  The set of products accumulated is unchanged.
     // k-blocks of global loads in flight ahead of the store.  ncu (profiles/r01/ncu_full_gemm_tc_v3.txt, source page): 27 % of the
     // stall samples sat on the first use of the loaded registers (long scoreboard) with 2 k-blocks ahead.
-    constexpr int PF = (MODE == TC_BF16) ? 1 : 2;    // (3 and 4 were measured: register spills, 5-100 % slower)
+    constexpr int PF = (MODE == TC_TF32X3) ? 2 : TC_PF16;    // (TF32: 3 and 4 were measured: register spills, 5-100 % slower)
     TileAddr<MODE, EPL> aa, ab;
     aa.init(p.ldx, m0, p.M, warp, lane, p.row_index);
     if constexpr (!WPACK) ab.init(p.ldw, n0, p.N, warp, lane);
@@ -308,9 +362,10 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
     int kstore = kb_shift;                                    // k-block index of the stage being stored
     TileRegs<MODE, EPL> xa[PF + 1], xb[PF + 1];
     int kload = kb_shift;                                     // k-block index of the next load
+    int kcur = kb_shift;                                      // k-block index of the register buffer being stored
 #pragma unroll
     for (int d = 0; d < PF; ++d) {
-      if (d < num_kb) {
+      if (d < num_kb && !(p.dbg & 8)) {
         xa[d].template load<VEC>(p.X, aa, (kb_base + kload) * KB, p.K);
         if constexpr (!WPACK) xb[d].template load<VEC>(p.W, ab, (kb_base + kload) * KB, p.K);
         kload = (kload + 1 == num_kb) ? 0 : kload + 1;
@@ -325,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
         if (kb < num_kb) {
           const int s = kb % NSTAGE;
           const uint32_t ph = (uint32_t)(kb / NSTAGE) & 1u;
-          if (kb + PF < num_kb && !(p.dbg & 2)) {              // loads of k-block kb+PF fly while kb is converted
+          if (kb + PF < num_kb && !(p.dbg & 10)) {             // loads of k-block kb+PF fly while kb is converted  (dbg 2 / 8: experiments)
             xa[(j + PF) % (PF + 1)].template load<VEC>(p.X, aa, (kb_base + kload) * KB, p.K);
             if constexpr (!WPACK) xb[(j + PF) % (PF + 1)].template load<VEC>(p.W, ab, (kb_base + kload) * KB, p.K);
             kload = (kload + 1 == num_kb) ? 0 : kload + 1;
@@ -333,7 +388,8 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
           mbar_wait(&empty_bar[s], ph ^ 1u);                  // first pass through the ring: returns immediately
           unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
           if constexpr (WPACK) {
-            if (tid == 0) {                                   // W tile(s): TMA bulk copies, no thread touches the data
+            if (tid == 0 && (p.dbg & 16)) mbar_arrive(&full_bar[s]);          // (experiment: no W copy)
+            if (tid == 0 && !(p.dbg & 16)) {                  // W tile(s): TMA bulk copies, no thread touches the data
               mbar_arrive_expect_tx(&full_bar[s], NT * PLANES * TILE_BYTES);
               if constexpr (NT == 1) {
                 tma_bulk_g2s(st + A_BYTES, wp_tiles + (size_t)kstore * (PLANES * TILE_BYTES), PLANES * TILE_BYTES, &full_bar[s]);
@@ -350,77 +406,116 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
             }
             kstore = (kstore + 1 == num_kb) ? 0 : kstore + 1;
           }
-          xa[j].store(st, st + TILE_BYTES, aa);
-          if constexpr (!WPACK) xb[j].store(st + A_BYTES, st + A_BYTES + TILE_BYTES, ab);
+          const uint32_t st_u = smem_u32(st);
+          if ((kb_base + kcur + 1) * KB > p.K) {              // the one k-block that crosses K: masked stores (uniform branch)
+            xa[j].template store<true>(st_u, st_u + TILE_BYTES, aa);
+            if constexpr (!WPACK) xb[j].template store<true>(st_u + A_BYTES, st_u + A_BYTES + TILE_BYTES, ab);
+          } else {
+            xa[j].template store<false>(st_u, st_u + TILE_BYTES, aa);
+            if constexpr (!WPACK) xb[j].template store<false>(st_u + A_BYTES, st_u + A_BYTES + TILE_BYTES, ab);
+          }
+          kcur = (kcur + 1 == num_kb) ? 0 : kcur + 1;
           if (!(p.dbg & 4)) fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core
-          mbar_arrive(&full_bar[s]);
+          __syncwarp();                                       // one arrive per warp: 256 arrives on one mbarrier serialise in the shared-memory atomic unit
+          if (lane == 0) mbar_arrive(&full_bar[s]);
         }
       }
     }
     // ===================== epilogue =====================
+    // tcgen05.ld hands a thread one accumulator ROW (32 columns at a time).  Stored straight to global memory that is 32 rows x 16 bytes per
+    // instruction — 32 cache lines, 8 K L1 wavefronts per CTA, ~4 us of a 36 us kernel (round 2, ncu).  So the tile goes through the (now idle)
+    // stage memory first: thread = row into a padded [128][BN] fp32 tile (pitch BN*4 + 16: eight 16-byte stores cover all 32 banks), then every
+    // warp walks whole rows, 512 contiguous bytes per instruction, for the slab / the final arithmetic / the partner's partial.
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    const int quad = warp & 3, chalf = warp >> 2;
-    const int row = m0 + quad * 32 + lane;
-    // split-K: the raw tile goes to this split's slab of the workspace; the epilogue arithmetic happens after the reduction
-    const bool split = p.kb_per_split > 0;
-    const float* e_bias = split ? nullptr : p.bias;
-    const int e_relu = split ? 0 : p.relu, e_bf16 = split ? 0 : p.y_bf16;
-    const long long e_np = ((long long)p.N + 3) & ~3LL;          // slab rows are padded to 4 floats: the reduction reads 128-bit vectors for any N
-    void* e_Y = split ? (void*)(p.partial + (size_t)blockIdx.z * (size_t)p.M * (size_t)e_np) : p.Y;
-    const long long e_ldy = split ? e_np : p.ldy;
-    const float rs = (!split && p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
+    constexpr int XPITCH = BN * 4 + 16;
+    const uint32_t xbase = smem_u32(tiles);
+    {
+      const int quad = warp & 3, chalf = warp >> 2;
+      const uint32_t xrow = xbase + (uint32_t)(quad * 32 + lane) * XPITCH;
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 64; ++cc) {
-      const int col0 = chalf * (BN / 2) + cc * 32;
-      float acc[32];
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int col0 = chalf * (BN / 2) + cc * 32;
+        float acc[32];
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * BN + col0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int a = 0; a < NACC; ++a) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * BN + col0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const bool written = NACC != 4 || (a & 1) == 0 || num_kb > 1;      // (4 accumulators) with a single k-block the odd ones stay untouched
 #pragma unroll
-        const bool written = NACC != 4 || (a & 1) == 0 || num_kb > 1;      // (4 accumulators) with a single k-block the odd ones stay untouched
+          for (int j = 0; j < 32; ++j) {
+            const float x = written ? __uint_as_float(r[j]) : 0.f;
+            acc[j] = (a == 0) ? x : acc[j] + x;
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = written ? __uint_as_float(r[j]) : 0.f;
-          acc[j] = (a == 0) ? x : acc[j] + x;
+        for (int j = 0; j < 32; j += 4)
+          sts128(xrow + (uint32_t)(col0 + j) * 4u, __float_as_uint(acc[j]), __float_as_uint(acc[j + 1]), __float_as_uint(acc[j + 2]),
+                 __float_as_uint(acc[j + 3]));
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");       // the eight epilogue warps (a row is written by two of them)
+    // row pass: warp w owns rows w, w + 8, ...; a lane owns 4 consecutive columns of every 128-column group
+    const bool split = p.kb_per_split > 0;                                // raw tile to this split's slab; arithmetic after the reduction
+    const long long e_np = ((long long)p.N + 3) & ~3LL;                   // slab rows are padded to 4 floats
+    if (split) {
+      float* slab = p.partial + (size_t)blockIdx.z * (size_t)p.M * (size_t)e_np;
+#pragma unroll 1
+      for (int r = warp; r < TC_BM; r += TC_PRODUCERS / 32) {
+        const int row = m0 + r;
+        if (row >= p.M) break;
+        const float4* src = reinterpret_cast<const float4*>(tiles + (size_t)r * XPITCH);
+        float* dst = slab + (long long)row * e_np + n0;
+#pragma unroll
+        for (int g = 0; g < BN / 128; ++g) {
+          const int c = g * 128 + lane * 4;
+          if (n0 + c < e_np) *reinterpret_cast<float4*>(dst + c) = src[c / 4];     // (pad columns carry zeros of the zero-padded W)
         }
       }
-      if (row < p.M) {
-        const int gcol0 = n0 + col0;
+    } else {
+#pragma unroll 1
+      for (int r = warp; r < TC_BM; r += TC_PRODUCERS / 32) {
+        const int row = m0 + r;
+        if (row >= p.M) break;
+        const float4* src = reinterpret_cast<const float4*>(tiles + (size_t)r * XPITCH);
+        const float rs = p.row_scale ? __ldg(p.row_scale + row) : 1.f;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
+        for (int g = 0; g < BN / 128; ++g) {
+          const int c = g * 128 + lane * 4, gc = n0 + c;
+          if (gc >= p.N) continue;
+          float4 t = src[c / 4];
+          float o[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int gc = gcol0 + j + e;
-            float x = acc[j + e];
-            if (gc < p.N) {
-              if (e_bias) x += __ldg(e_bias + gc);
-              x *= rs;
-              if (e_relu) x = fmaxf(x, 0.f);
+            if (gc + e < p.N) {
+              if (p.bias) o[e] += __ldg(p.bias + gc + e);
+              o[e] *= rs;
+              if (p.relu) o[e] = fmaxf(o[e], 0.f);
             }
-            o[e] = x;
           }
-          const int gc = gcol0 + j;
-          if (e_bf16) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e_Y) + (long long)row * e_ldy + gc;
+          if (p.y_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.Y) + (long long)row * p.ldy + gc;
+            if (gc + 3 < p.N && ((((uintptr_t)dst) & 7) == 0)) {
+              const __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0], o[1]), b1 = __floats2bfloat162_rn(o[2], o[3]);
+              *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (gc + e < p.N) dst[e] = __float2bfloat16_rn(o[e]);
+              for (int e = 0; e < 4; ++e)
+                if (gc + e < p.N) dst[e] = __float2bfloat16_rn(o[e]);
+            }
           } else {
-            float* dst = reinterpret_cast<float*>(e_Y) + (long long)row * e_ldy + gc;
+            float* dst = reinterpret_cast<float*>(p.Y) + (long long)row * p.ldy + gc;
             if (gc + 3 < p.N && ((((uintptr_t)dst) & 15) == 0)) {
               *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
@@ -478,9 +573,9 @@ gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
 // the MMA wants them (K-major SWIZZLE_128B), zero-padded in N and K.  One thread per (row, 16-byte chunk).
 template <int MODE>
 __global__ void pack_weights_kernel(const float* __restrict__ W, long long ldw, int N, int K, unsigned char* __restrict__ out) {
-  constexpr int KB = (MODE == TC_BF16) ? 64 : 32;
-  constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
-  constexpr int EPC = (MODE == TC_BF16) ? 8 : 4;                  // source elements per 16-byte chunk
+  constexpr int KB = TcMode<MODE>::KB;
+  constexpr int PLANES = TcMode<MODE>::PLANES;
+  constexpr int EPC = TcMode<MODE>::E16 ? 8 : 4;                  // source elements per 16-byte chunk
   const int num_kb = (K + KB - 1) / KB;
   const int n_tiles = (N + 127) / 128;
   const long long total = (long long)n_tiles * num_kb * 128 * 8;  // 8 chunks per 128-byte row
@@ -503,6 +598,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, long long ldw, 
     q.x = *reinterpret_cast<uint32_t*>(&b0); q.y = *reinterpret_cast<uint32_t*>(&b1);
     q.z = *reinterpret_cast<uint32_t*>(&b2); q.w = *reinterpret_cast<uint32_t*>(&b3);
     *reinterpret_cast<uint4*>(base + off) = q;
+  } else if constexpr (MODE == TC_BF16X3) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) bf16_split2(v[e], v[e + 1], h[e / 2], l[e / 2]);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(base + TILE_BYTES + off) = make_uint4(l[0], l[1], l[2], l[3]);
   } else {
     float hi[4], lo[4];
 #pragma unroll
@@ -513,7 +614,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, long long ldw, 
 }
 
 static size_t packed_weight_bytes(long long N, long long K, int mode) {
-  const int KB = (mode == TC_BF16) ? 64 : 32, PL = (mode == TC_BF16) ? 1 : 2;
+  const int KB = tc_kb(mode), PL = tc_planes(mode);
   return (size_t)((N + 127) / 128) * (size_t)((K + KB - 1) / KB) * PL * TILE_BYTES;
 }
 
@@ -560,7 +661,7 @@ tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, in
 
 // number of K splits for a GEMM whose output tiles alone leave most SMs idle (0 = do not split)
 static int tc_splits_tiles(long long tiles, bool n_ok, long long K, int mode, int* kb_per_split) {
-  const int KB = (mode == TC_BF16) ? 64 : 32;
+  const int KB = tc_kb(mode);
   const int num_kb = (int)((K + KB - 1) / KB);
   const int sms = b200rec_num_sms();
   *kb_per_split = 0;
@@ -579,7 +680,7 @@ static int tc_splits(long long M, long long N, long long K, int mode, int* kb_pe
 
 template <int MODE, int EPL, bool VEC, bool WPACK, int BN = TC_BN>
 static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
-  constexpr int PLANES = (MODE == TC_BF16) ? 1 : 2;
+  constexpr int PLANES = TcMode<MODE>::PLANES;
   constexpr int NSTAGE = BN == 256 ? ((MODE == TC_BF16) ? 4 : 2) : ((MODE == TC_BF16) ? 4 : 3);
   const size_t smem = (size_t)NSTAGE * (1 + BN / 128) * PLANES * TILE_BYTES + 1024;
   static B200recSmemOptIn opted;                     // per template instantiation, one bit per device
@@ -587,7 +688,7 @@ static int launch_tc_epl(const TcBatch& b, cudaStream_t st) {
   int nmax = 0;
   for (int q = 0; q < b.n; ++q) nmax = b.prob[q].N > nmax ? b.prob[q].N : nmax;
   const TcParams& p0 = b.prob[0];
-  const int nsplit = p0.kb_per_split ? ceil_div_i(ceil_div_i(p0.K, (MODE == TC_BF16) ? 64 : 32), p0.kb_per_split) : 1;
+  const int nsplit = p0.kb_per_split ? ceil_div_i(ceil_div_i(p0.K, TcMode<MODE>::KB), p0.kb_per_split) : 1;
   dim3 grid(ceil_div_i(nmax, BN), b.tile_start[b.n], nsplit);
   gemm_tc_kernel<MODE, NSTAGE, EPL, VEC, WPACK, BN><<<grid, TC_THREADS, smem, st>>>(b);
   B200REC_CHECK_LAUNCH();
@@ -637,20 +738,21 @@ static int launch_tc(const TcBatch& b, cudaStream_t st) {
 using namespace b200rec;
 
 extern "C" size_t b200rec_packed_weight_bytes(int64_t N, int64_t K, int mode) {
-  return (N > 0 && K > 0) ? packed_weight_bytes(N, K, mode) : 0;
+  return (N > 0 && K > 0 && mode >= 0 && mode <= TC_BF16X3) ? packed_weight_bytes(N, K, mode) : 0;
 }
 
 extern "C" int b200rec_pack_weights_tc(const float* W, int64_t N, int64_t K, int64_t ldw, int mode, void* packed, size_t packed_bytes,
                                        b200rec_stream_t stream) {
   if (!W || !packed || N <= 0 || K <= 0 || ldw < K) return b200rec_fail(B200REC_ERR_BAD_ARG, "pack_weights_tc: bad argument");
+  if (mode < 0 || mode > TC_BF16X3) return b200rec_fail(B200REC_ERR_BAD_ARG, "pack_weights_tc: bad mode");
   if (packed_bytes < packed_weight_bytes(N, K, mode) || ((uintptr_t)packed % 128))
     return b200rec_fail(B200REC_ERR_WORKSPACE, "pack_weights_tc: buffer too small or not 128-byte aligned");
-  const int KB = (mode == TC_BF16) ? 64 : 32;
+  const int KB = tc_kb(mode);
   const long long total = ((N + 127) / 128) * ((K + KB - 1) / KB) * 128LL * 8;
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (mode == TC_BF16) pack_weights_kernel<TC_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)N, (int)K, (unsigned char*)packed);
   else if (mode == TC_TF32X3) pack_weights_kernel<TC_TF32X3><<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)N, (int)K, (unsigned char*)packed);
-  else return b200rec_fail(B200REC_ERR_BAD_ARG, "pack_weights_tc: bad mode");
+  else pack_weights_kernel<TC_BF16X3><<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)N, (int)K, (unsigned char*)packed);
   B200REC_CHECK_LAUNCH();
   return B200REC_OK;
 }
@@ -723,38 +825,40 @@ extern "C" int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, in
 }
 
 // wide form: 128 x 256 tiles, k range split so that (row tiles) x (column pairs) x splits fills the device once
-static int tc_wide_splits(long long M, long long N, long long K, int* kb_per_split) {
+static int tc_wide_splits(long long M, long long N, long long K, int mode, int* kb_per_split) {
   const long long tiles = ((M + 127) / 128) * ((N + 255) / 256);
-  const int num_kb = (int)((K + 31) / 32);
+  const int KB = tc_kb(mode);
+  const int num_kb = (int)((K + KB - 1) / KB);
   const int sms = b200rec_num_sms();
   int want = (int)(sms / tiles);
   if (want < 2) want = 2;                                       // always split: the two TMEM accumulators want short chains
-  if (want > num_kb / 4) want = num_kb / 4;
+  if (want > num_kb * KB / 128) want = num_kb * KB / 128;         // at least 128 columns of k per CTA
   if (want < 1) want = 1;
   const int kbps = (num_kb + want - 1) / want;
   *kb_per_split = kbps;
   return (num_kb + kbps - 1) / kbps;
 }
 
-extern "C" size_t b200rec_linear_tc_wide_workspace(int64_t M, int64_t N, int64_t K) {
-  if (M <= 0 || N <= 0 || K <= 0) return 0;
+extern "C" size_t b200rec_linear_tc_wide_workspace(int64_t M, int64_t N, int64_t K, int mode) {
+  if (M <= 0 || N <= 0 || K <= 0 || (mode != B200REC_TC_TF32X3 && mode != B200REC_TC_BF16X3)) return 0;
   int kbps = 0;
-  const int splits = tc_wide_splits(M, N, K, &kbps);
+  const int splits = tc_wide_splits(M, N, K, mode, &kbps);
   return (size_t)splits * (size_t)M * (size_t)((N + 3) & ~3LL) * sizeof(float);
 }
 
 extern "C" int b200rec_linear_tc_wide(const float* X, int64_t M, int64_t K, int64_t ldx, int64_t N, const float* bias, const float* row_scale,
-                                      int relu, void* Y, int64_t ldy, int y_dtype, const void* packed_w, const int64_t* row_index,
+                                      int relu, void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w, const int64_t* row_index,
                                       int64_t x_rows, void* workspace, size_t workspace_bytes, b200rec_stream_t stream) {
   TcBatch b;
   b.n = 1;
-  if (!packed_w) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_wide: needs the packed weights (b200rec_pack_weights_tc, TF32X3)");
+  if (mode != B200REC_TC_TF32X3 && mode != B200REC_TC_BF16X3) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_wide: mode is TF32X3 or BF16X3");
+  if (!packed_w) return b200rec_fail(B200REC_ERR_BAD_ARG, "linear_tc_wide: needs the packed weights (b200rec_pack_weights_tc, same mode)");
   if (N <= 128 || ((N + 127) / 128) % 2) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "linear_tc_wide: N must cover an even number of 128-column tiles");
   const int rc = tc_fill(b.prob[0], X, M, K, ldx, nullptr, N, K, bias, row_scale, relu, Y, ldy, y_dtype, packed_w, row_index, x_rows);
   if (rc) return rc;
   if (M == 0) return B200REC_OK;
   int kbps = 0;
-  const int splits = tc_wide_splits(M, N, K, &kbps);
+  const int splits = tc_wide_splits(M, N, K, mode, &kbps);
   const size_t need = (size_t)splits * (size_t)M * (size_t)((N + 3) & ~3LL) * sizeof(float);
   if (!workspace || workspace_bytes < need || ((uintptr_t)workspace % 16)) return b200rec_fail(B200REC_ERR_WORKSPACE, "linear_tc_wide: workspace too small");
   b.prob[0].kb_per_split = kbps;
@@ -762,7 +866,7 @@ extern "C" int b200rec_linear_tc_wide(const float* X, int64_t M, int64_t K, int6
   b.tile_start[0] = 0;
   b.tile_start[1] = ceil_div_i(M, TC_BM);
   for (int q = 1; q < TC_MAX_BATCH; ++q) b.tile_start[q + 1] = b.tile_start[1];
-  return launch_tc<TC_TF32X3, 256>(b, (cudaStream_t)stream);
+  return mode == B200REC_TC_TF32X3 ? launch_tc<TC_TF32X3, 256>(b, (cudaStream_t)stream) : launch_tc<TC_BF16X3, 256>(b, (cudaStream_t)stream);
 }
 
 extern "C" int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode,

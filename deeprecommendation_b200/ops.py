@@ -105,7 +105,10 @@ def _dtype_code(dt):
 # ------------------------------------------------------------------------------------------------------------------
 # GEMM engine for K1a: 'simt' = fp32 FFMA everywhere; 'tf32x3' / 'bf16' = tcgen05 tensor-core kernel (csrc/gemm_tc.cu) for
 # large M, FFMA for the small ones (a 128-row tile per CTA cannot fill 148 SMs below ~2k rows).
-_gemm_engine = os.environ.get('B200REC_GEMM_ENGINE', 'tf32x3')   # fp32-parity tensor-core engine by default (the whole GPU suite passes under it)
+# fp32-parity tensor-core engines: 'tf32x3' (3xTF32 everywhere) and 'bf16x3' (default: the same, except that the wide form — large M, 128 < N, long K —
+# runs the three products on a bf16 hi/lo split at twice the MMA rate: ~4e-6 instead of ~6e-7 of the largest output, budget 1e-5; the whole GPU suite
+# passes under either)
+_gemm_engine = os.environ.get('B200REC_GEMM_ENGINE', 'bf16x3')
 TC_MIN_ROWS = 2048
 TC_SPLITK_MIN_ROWS = 128      # below TC_MIN_ROWS the tensor-core GEMM runs split-K (if K is long enough to be dealt out)
 SHORTK_MIN_ROWS = 4096  # below this a handful of 64x64 FFMA tiles is as fast as the persistent kernel's set-up
@@ -146,9 +149,14 @@ def invalidate_caches():
     globals().get('_ap_cache', {}).clear()
 
 
+def _tc_mode(engine):
+    """MMA mode of an engine name: 'bf16' -> bf16 operands; 'tf32x3' and 'bf16x3' -> 3xTF32 (bf16x3 only differs in the wide form)"""
+    return L.TC_BF16 if engine.startswith('bf16') and not engine.startswith('bf16x3') else L.TC_TF32X3
+
+
 def set_gemm_engine(name: str):
     global _gemm_engine
-    if name not in ('simt', 'tf32x3', 'bf16'):
+    if name not in ('simt', 'tf32x3', 'bf16', 'bf16x3'):
         raise ValueError(name)
     prev, _gemm_engine = _gemm_engine, name
     return prev
@@ -184,7 +192,7 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
         return out                                   # empty batch: nothing to launch (nn.Linear returns an empty (0, N) too)
     lib = L.lib()
     engine = engine or _gemm_engine
-    if (engine in ('tf32x3', 'shortk!') and row_index is None and K <= 128 and K % 32 == 0 and N <= 128 and (M >= SHORTK_MIN_ROWS or engine == 'shortk!')
+    if (engine in ('tf32x3', 'bf16x3', 'shortk!') and row_index is None and K <= 128 and K % 32 == 0 and N <= 128 and (M >= SHORTK_MIN_ROWS or engine == 'shortk!')
             and ldx % 4 == 0 and x.data_ptr() % 16 == 0 and out.dtype in (torch.float32, torch.bfloat16)):
         # per-node d x d transforms (GraphNCF): persistent streaming kernel, W resident in shared memory
         packed = _packed_weight(w, ldw, L.TC_TF32X3)
@@ -195,16 +203,19 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     if engine == 'shortk!':
         raise ValueError('linear: shape not supported by the short-K kernel')
     if engine != 'simt' and ((M >= TC_MIN_ROWS and K >= TC_MIN_K) or engine.endswith('!')) and (x_rows if row_index is not None else M) * ldx < 2 ** 32:
-        mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
-        packed = _packed_weight(w, ldw, mode) if _pack_weights else None
-        if TC_WIDE and mode == L.TC_TF32X3 and packed is not None and N > 128 and ((N + 127) // 128) % 2 == 0 and K >= 256:
+        mode = _tc_mode(engine)
+        if TC_WIDE and mode == L.TC_TF32X3 and _pack_weights and N > 128 and ((N + 127) // 128) % 2 == 0 and K >= 256:
             # 128 x 256 tiles: every X block converted and staged once for both halves of W, k range split over the CTAs
-            wsb = lib.b200rec_linear_tc_wide_workspace(M, N, K)
+            if engine.startswith('bf16x3'):              # the same three products on a bf16 hi/lo split (2x MMA rate, ~4e-6)
+                mode = L.TC_BF16X3
+            packed = _packed_weight(w, ldw, mode)
+            wsb = lib.b200rec_linear_tc_wide_workspace(M, N, K, mode)
             ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
             with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
                 L.check(lib.b200rec_linear_tc_wide(_ptr(x), M, K, ldx, N, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy, _dtype_code(out.dtype),
-                                                   _ptr(packed), _ptr(row_index), x_rows, _ptr(ws), wsb, _stream()), 'linear_tc_wide')
+                                                   mode, _ptr(packed), _ptr(row_index), x_rows, _ptr(ws), wsb, _stream()), 'linear_tc_wide')
             return out
+        packed = _packed_weight(w, ldw, mode) if _pack_weights else None
         with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
             L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                           _dtype_code(out.dtype), mode, _ptr(packed), _ptr(row_index), x_rows, _stream()), 'linear_tc')
@@ -212,7 +223,7 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
     if (engine != 'simt' and row_index is None and TC_SPLITK_MIN_ROWS <= M < TC_MIN_ROWS and K >= TC_MIN_K and M * ldx < 2 ** 32
             and (N % 4 == 0 or SPLITK_ANY_N)):
         # short-M, long-K (a batch of pairs against the F-wide profiles): split-K on the tensor cores
-        mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+        mode = _tc_mode(engine)
         ws_bytes = lib.b200rec_linear_tc_splitk_workspace(M, N, K, mode)
         if ws_bytes:
             packed = _packed_weight(w, ldw, mode) if _pack_weights else None
@@ -239,7 +250,7 @@ def linear_tc_batch(problems, engine=None):
     engine = engine or _gemm_engine
     if engine == 'simt':
         raise RuntimeError('linear_tc_batch needs a tensor-core engine (set_gemm_engine)')
-    mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+    mode = _tc_mode(engine)
     arr = (L.LinearProblem * len(problems))()
     keep, outs, K, dev, meta = [], [], None, None, []
     for q, (x, weight, bias, out) in enumerate(problems):
@@ -286,7 +297,7 @@ def linear_pair(xa, wa, ba, xb, wb, bb):
     if not ok:
         return linear_raw(xa, wa, ba), linear_raw(xb, wb, bb)
     _require_cuda(xa, wa, ba, xb, wb, bb)
-    mode = L.TC_BF16 if engine.startswith('bf16') else L.TC_TF32X3
+    mode = _tc_mode(engine)
     arr = (L.LinearProblem * 2)()
     keep, outs = [], []
     for q, (x, weight, bias) in enumerate(((xa, wa, ba), (xb, wb, bb))):

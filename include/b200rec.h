@@ -31,7 +31,7 @@ typedef void* b200rec_stream_t; /* cudaStream_t */
 enum { B200REC_OK = 0, B200REC_ERR_CUDA = 1, B200REC_ERR_BAD_ARG = 2, B200REC_ERR_UNSUPPORTED = 3, B200REC_ERR_WORKSPACE = 4 };
 enum { B200REC_F32 = 0, B200REC_BF16 = 1 };
 enum { B200REC_ATT_NET = 0, B200REC_ATT_DOT = 1 };
-enum { B200REC_TC_TF32X3 = 0, B200REC_TC_BF16 = 1 };
+enum { B200REC_TC_TF32X3 = 0, B200REC_TC_BF16 = 1, B200REC_TC_BF16X3 = 2 /* wide form only */ };
 #define B200REC_PEER_MAX 16          /* GPUs of one NVSwitch box that one exchange can address */
 #define B200REC_PEER_CHANNELS 16     /* independent flag channels per arena */
 #define B200REC_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
@@ -68,11 +68,13 @@ int b200rec_linear_tc_splitk(const float* X, int64_t M, int64_t K, int64_t ldx, 
 /* Wide form for 128 < N (an even number of 128-column tiles, e.g. the 256 outputs of AttentionNCF's composite projections,
  * attention_ncf.py:150-151,176,216): a CTA owns 128 rows x 256 columns, so each X block is read, split and staged once for both
  * halves of W; the k range is always split (workspace = b200rec_linear_tc_wide_workspace bytes, slabs added in split order by the
- * same reduction kernel as b200rec_linear_tc_splitk).  fp32 parity (3xTF32); `packed_w` is required. */
-size_t b200rec_linear_tc_wide_workspace(int64_t M, int64_t N, int64_t K);
+ * same reduction kernel as b200rec_linear_tc_splitk).  `packed_w` (same mode) is required.  mode B200REC_TC_TF32X3: fp32 parity by the
+ * 3xTF32 split (~6e-7 at K = 2094); B200REC_TC_BF16X3: the same three products on a bf16 hi/lo split of both operands — twice the MMA rate, 16
+ * mantissa bits per operand: ~4e-6 of the largest output at K = 2094, inside the 1e-5 budget with less margin (opt-in). */
+size_t b200rec_linear_tc_wide_workspace(int64_t M, int64_t N, int64_t K, int mode);
 int b200rec_linear_tc_wide(const float* X, int64_t M, int64_t K, int64_t ldx, int64_t N, const float* bias, const float* row_scale, int relu,
-                           void* Y, int64_t ldy, int y_dtype, const void* packed_w, const int64_t* row_index, int64_t x_rows, void* workspace,
-                           size_t workspace_bytes, b200rec_stream_t stream);
+                           void* Y, int64_t ldy, int y_dtype, int mode, const void* packed_w, const int64_t* row_index, int64_t x_rows,
+                           void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
 /* Persistent short-K variant for the per-node transforms of GraphNCF (K in {32,64,96,128}, N <= 128; csrc/node_gemm.cu):
  * W stays in shared memory (`packed_w` = b200rec_pack_weights_tc(..., B200REC_TC_TF32X3)), row tiles are streamed, fp32 parity
  * by the 3xTF32 split.  X rows 16-byte aligned (ldx % 4 == 0); Y fp32 or bf16 (`y_dtype`; bf16 = the message table of GraphNCF's
@@ -117,7 +119,7 @@ int b200rec_linear_tc_batch(const b200rec_linear_problem_t* problems, int n_prob
 size_t b200rec_linear_tc_splitk_batch_workspace(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode);
 int b200rec_linear_tc_splitk_batch(const b200rec_linear_problem_t* problems, int n_problems, int64_t K, int mode, void* workspace,
                                    size_t workspace_bytes, b200rec_stream_t stream);
-/* Optional: W converted once into MMA-ready swizzled tiles (bf16 or TF32 hi/lo, zero-padded).  With `packed_w` the GEMM moves
+/* Optional: W converted once into MMA-ready swizzled tiles (bf16, TF32 hi/lo or bf16 hi/lo, zero-padded).  With `packed_w` the GEMM moves
  * the W operand by TMA bulk copies (cp.async.bulk) and only X is converted by the producer warps.  128-byte aligned buffer. */
 size_t b200rec_packed_weight_bytes(int64_t N, int64_t K, int mode);
 int b200rec_pack_weights_tc(const float* W, int64_t N, int64_t K, int64_t ldw, int mode, void* packed, size_t packed_bytes,

@@ -26,7 +26,7 @@ def _attention(kw, seed):
     return m, sd
 
 
-@pytest.mark.parametrize('engine', ['simt', 'tf32x3'])
+@pytest.mark.parametrize('engine', ['simt', 'tf32x3', 'bf16x3'])
 @pytest.mark.parametrize('B,I', [(1, 1), (1, 37), (3, 1), (2, 600)])
 def test_attention_tiny_batches(B, I, engine):
     """a single candidate / a single rated item; both GEMM engines"""

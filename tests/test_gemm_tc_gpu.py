@@ -164,3 +164,29 @@ def test_linear_tc_wide_tiles_fp32_parity(M, K, N):
     idx = torch.randint(0, M, (2300,), generator=torch.Generator().manual_seed(1)).cuda()
     yg = ops.linear_raw(xd, wd, bd, row_index=idx, engine='tf32x3!')
     assert maxnorm_rel(yg, ref[idx.cpu()]) < 1e-5
+
+
+@pytest.mark.parametrize('M,K,N', [(9461, 2094, 256), (2500, 2094, 256), (4096, 512, 384 + 128), (3000, 1000, 130), (2049, 2093, 200), (2100, 2096, 256)])
+def test_linear_tc_wide_bf16x3_split(M, K, N):
+    """The opt-in bf16 hi/lo engine of the wide form (B200REC_TC_BF16X3): the three products of the 3xTF32 scheme on 16-bit-mantissa operands.
+    Budget 1e-5 of the largest output (measured ~4e-6 at K = 2094); deterministic; 64-bit, scalar (odd K) and 128-bit producer loads."""
+    from deeprecommendation_b200 import ops
+    x, w, b, s = _case(M, K, N, M + N + 1)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    xd, wd, bd, sd = x.cuda(), w.cuda(), b.cuda(), s.cuda()
+    y = ops.linear_raw(xd, wd, bd, engine='bf16x3!')
+    err = maxnorm_rel(y, ref)
+    assert err < 1e-5, err
+    assert torch.equal(y, ops.linear_raw(xd, wd, bd, engine='bf16x3!'))
+    y3 = ops.linear_raw(xd, wd, bd, engine='tf32x3!')
+    assert not torch.equal(y, y3)                                   # it really is the other engine
+    out = torch.full((M, N + 8), 3.0, device='cuda')
+    ops.linear_raw(xd, wd, bd, sd, True, out=out[:, 4:4 + N], engine='bf16x3!')
+    assert maxnorm_rel(out[:, 4:4 + N], (ref * s.double()[:, None]).relu()) < 1e-5
+    assert torch.all(out[:, :4] == 3.0) and torch.all(out[:, 4 + N:] == 3.0)
+    idx = torch.randint(0, M, (2300,), generator=torch.Generator().manual_seed(1)).cuda()
+    assert maxnorm_rel(ops.linear_raw(xd, wd, bd, row_index=idx, engine='bf16x3!'), ref[idx.cpu()]) < 1e-5
+    # binary (multi-hot) rows are exact in bf16: only W's split error remains
+    xb = (torch.rand(M, K, generator=torch.Generator().manual_seed(5)) < 0.02).float()
+    eb = maxnorm_rel(ops.linear_raw(xb.cuda(), wd, bd, engine='bf16x3!'), torch.nn.functional.linear(xb.double(), w.double(), b.double()))
+    assert eb < 5e-6, eb

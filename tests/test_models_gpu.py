@@ -519,7 +519,7 @@ def test_attention_forward_resident_equals_dense_forward():
     m.load_state_dict(synth.to_torch(synth.attention_ncf_weights(seed=9, **kw)))
     pick = np.random.default_rng(0).permutation(len(u))[:256]
     batch = [(int(a), int(b), 3.0) for a, b in zip(u[pick], it[pick])]
-    for engine in ('simt', 'tf32x3'):
+    for engine in ('simt', 'tf32x3', 'bf16x3'):
         prev = ops.set_gemm_engine(engine)
         try:
             with torch.no_grad():

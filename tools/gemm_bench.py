@@ -4,12 +4,12 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deeprecommendation_b200 import ops
 
-SHAPES = [(9447, 2094, 256), (9461, 2094, 256), (9600, 2094, 256), (162541, 128, 128), (62423, 128, 128), (512, 2094, 128), (512, 2094, 256), (100000, 2094, 128)]
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or [(9447, 2094, 256), (9461, 2094, 256), (9600, 2094, 256), (162541, 128, 128), (62423, 128, 128), (512, 2094, 128), (512, 2094, 256), (100000, 2094, 128)]
 flush = torch.empty(256 * 1024 * 1024 // 4, device='cuda')
 out = {}
 for M, K, N in SHAPES:
     x = torch.randn(M, K, device='cuda'); w = torch.randn(N, K, device='cuda') / K ** 0.5; b = torch.randn(N, device='cuda')
-    for eng in ('simt', 'tf32x3', 'tf32x3!', 'tf32x3!narrow', 'bf16!') + (('shortk!',) if K <= 128 else ()):
+    for eng in ('simt', 'tf32x3', 'tf32x3!', 'tf32x3!narrow', 'bf16x3!', 'bf16!') + (('shortk!',) if K <= 128 else ()):
         if eng == 'tf32x3!narrow' and N <= 128:
             continue
         ops.TC_WIDE = eng != 'tf32x3!narrow'
