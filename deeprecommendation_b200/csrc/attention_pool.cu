@@ -520,7 +520,8 @@ attention_wseg_tma_kernel(AttParams p, const int* __restrict__ row_ptr, const in
 // One WARP per candidate row: lanes take the segments' (max, denominator) pairs in parallel, then every lane owns 4 output columns
 // and adds the partial vectors in segment order with independent 128-bit loads (v4 used a CTA per row whose threads walked the
 // segments with three dependent scalar loops: 35 us at 8192 rows, 10 % of the K2 call).
-constexpr int MERGE_WARPS = 8;
+constexpr int MERGE_WARPS = 2;      // 512 rows -> 256 CTAs: every SM takes part (8 warps per CTA left 84 of 148 SMs idle at config 2)
+constexpr int MERGE_LD = 16;        // partial vectors in flight per lane: a typical row (~10 segments) is one round of loads
 __global__ void __launch_bounds__(MERGE_WARPS * 32)
 attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* __restrict__ col, const float* __restrict__ val,
                        const int* __restrict__ row_nnz, long long padded_stride, AttWork w) {
@@ -547,11 +548,11 @@ attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* 
   const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;      // no valid rated item -> weights 0 -> user_emb = b_U (:208-209)
   for (int u = lane * 4; u < p.U; u += 128) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < nseg; s0 += 4) {
-      float4 v[4];
-      float f[4];
+    for (int s0 = 0; s0 < nseg; s0 += MERGE_LD) {
+      float4 v[MERGE_LD];
+      float f[MERGE_LD];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < MERGE_LD; ++k) {
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         f[k] = 0.f;
         if (s0 + k < nseg) {
@@ -561,7 +562,7 @@ attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* 
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < MERGE_LD; ++k) {
         a.x = fmaf(v[k].x, f[k], a.x); a.y = fmaf(v[k].y, f[k], a.y); a.z = fmaf(v[k].z, f[k], a.z); a.w = fmaf(v[k].w, f[k], a.w);
       }
     }
@@ -582,7 +583,7 @@ attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* 
 // One CTA per row; pure streaming (four independent coalesced loads per thread and iteration, no dependent work), so
 // the dense scan costs a few microseconds instead of sitting on the critical path of the pooling kernel, and the
 // pooling kernel can split every row's non-zeros EVENLY over its warps.
-// STAGED: the row is first copied to shared memory with 16 independent loads per thread in flight (one memory latency per 4096
+// STAGED: the row is first copied to shared memory with 40 independent loads per thread in flight (one memory latency per 10,240
 // columns instead of one per 128 — the two scans then run out of shared memory); rows wider than the shared memory take the
 // streaming form.
 template <bool STAGED>
@@ -596,15 +597,17 @@ um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __r
   const int b = blockIdx.x;
   const float* __restrict__ grow = um + (long long)b * ld_um;
   if constexpr (STAGED) {
-    for (int i0 = 0; i0 < I; i0 += ATT_WARPS * 32 * 16) {
-      float v[16];
+    // loads are CLAMPED, not predicated: seven predicate registers cap a batch of predicated loads at ~7 in flight (SASS, round 2)
+    constexpr int NLD = 40;                                     // a 10,240-column row in ONE memory latency
+    for (int i0 = 0; i0 < I; i0 += ATT_WARPS * 32 * NLD) {
+      float v[NLD];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < NLD; ++u) {
         const int i = i0 + u * (ATT_WARPS * 32) + (int)threadIdx.x;
-        v[u] = (i < I) ? __ldcs(grow + i) : 0.f;
+        v[u] = __ldcs(grow + min(i, I - 1));
       }
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < NLD; ++u) {
         const int i = i0 + u * (ATT_WARPS * 32) + (int)threadIdx.x;
         if (i < I) um_row_smem[i] = v[u];
       }
@@ -656,6 +659,88 @@ um_compact_kernel(const float* __restrict__ um, long long ld_um, int I, int* __r
       }
       out += __popc(mask);
     }
+  }
+}
+
+// The staged form of the compaction with 128-bit accesses (round 2: the scalar form above issued ~1,700 instructions per warp and row —
+// 60 % issue-slot utilisation, 14 us for the 19 MB matrix of config 2).  A row starts on a 4-byte boundary only, so it is staged into shared
+// memory SHIFTED by its phase (`shift` = words past a 16-byte boundary): padded element e = column e - shift, elements [0, shift) and the tail
+// pad are zeros and drop out of the compaction like any other zero.  Interior vectors move as LDG.128 -> STS.128 (all of a thread's loads in
+// flight at once, clamped rather than predicated), the <= 6 edge elements as scalars.  The scans read one float4 per lane: four ballots per
+// 128 elements give the lane-major (= column) order.
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+um_compact_vec_kernel(const float* __restrict__ um, long long ld_um, int I, int* __restrict__ col, float* __restrict__ val,
+                      int* __restrict__ row_nnz, AttWork w) {
+  extern __shared__ __align__(16) float um_vec_smem[];
+  __shared__ int s_cnt[ATT_WARPS];
+  __shared__ int s_base;
+  constexpr int NT = ATT_WARPS * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float* __restrict__ grow = um + (long long)b * ld_um;
+  const int shift = (int)(((uintptr_t)grow >> 2) & 3);
+  const int n = I + shift, n4 = (n + 3) >> 2;
+  const int q_lo = shift ? 1 : 0, q_hi = n >> 2;                          // vectors entirely inside the row
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(grow - shift);
+  float4* s4 = reinterpret_cast<float4*>(um_vec_smem);
+  constexpr int NLD = 10;                                                 // 256 threads x 10 vectors = 10,240 columns per round
+  for (int q0 = q_lo; q0 < q_hi; q0 += NT * NLD) {
+    float4 v[NLD];
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) v[u] = __ldcs(g4 + min(q0 + u * NT + tid, q_hi - 1));
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int q = q0 + u * NT + tid;
+      if (q < q_hi) s4[q] = v[u];
+    }
+  }
+  if (tid < 8) {                                                          // edges: first vector (tid 0-3), last vector (tid 4-7), pads = 0
+    const int e = (tid < 4) ? tid : 4 * (n4 - 1) + (tid - 4);
+    const bool edge_vec = (tid < 4) ? (q_lo == 1 || q_hi == 0) : (q_hi < n4);
+    if (edge_vec && e < 4 * n4) {
+      const int c = e - shift;
+      um_vec_smem[e] = (c >= 0 && c < I) ? __ldcs(grow + c) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int vpw = (((n4 + ATT_WARPS - 1) / ATT_WARPS) + 31) & ~31;       // vectors per warp, whole iterations of 32
+  const int q_begin = warp * vpw, q_end = min(n4, q_begin + vpw);
+  int cnt = 0;
+  for (int q0 = q_begin; q0 < q_end; q0 += 32) {
+    const int q = q0 + lane;
+    const float4 t = (q < q_end) ? s4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    cnt += (t.x != 0.f) + (t.y != 0.f) + (t.z != 0.f) + (t.w != 0.f);
+  }
+  cnt = __reduce_add_sync(FULL, cnt);
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int x = 0; x < ATT_WARPS; ++x) {
+    if (x < warp) base += s_cnt[x];
+    total += s_cnt[x];
+  }
+  if (tid == 0) row_nnz[b] = total;
+  att_emit_items(w, b, total, tid, NT, &s_base);                          // this row's (row, segment) work items
+  long long out = (long long)b * I + base;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int q0 = q_begin; q0 < q_end; q0 += 32) {
+    const int q = q0 + lane;
+    const float4 t = (q < q_end) ? s4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float x[4] = {t.x, t.y, t.z, t.w};
+    unsigned m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = __ballot_sync(FULL, x[k] != 0.f);
+    long long pos = out + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (x[k] != 0.f) {
+        col[pos] = 4 * q + k - shift;
+        val[pos] = x[k];
+        ++pos;
+      }
+    }
+    out += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
   }
 }
 
@@ -772,10 +857,10 @@ static int att_prepare(int B, int I, int U, const AttInputs& in, cudaStream_t st
     if (launch) {
       const size_t row_bytes = (size_t)I * sizeof(float);
       static const bool streaming = []() { const char* e = getenv("B200REC_ATT_COMPACT_STREAMING"); return e != nullptr && atoi(e) != 0; }();
-      if (row_bytes <= 96 * 1024 && !in.prepare_light && !streaming) {
+      if (row_bytes + 32 <= 96 * 1024 && !in.prepare_light && !streaming) {
         static B200recSmemOptIn opted;
-        B200REC_CUDA(b200rec_opt_in_smem(opted, um_compact_kernel<true>, 96 * 1024));
-        um_compact_kernel<true><<<B, ATT_WARPS * 32, row_bytes, st>>>(in.um, in.ld_um, I, wcol, wval, wnnz, w);
+        B200REC_CUDA(b200rec_opt_in_smem(opted, um_compact_vec_kernel, 96 * 1024));
+        um_compact_vec_kernel<<<B, ATT_WARPS * 32, row_bytes + 32, st>>>(in.um, in.ld_um, I, wcol, wval, wnnz, w);
       } else {
         um_compact_kernel<false><<<B, ATT_WARPS * 32, 0, st>>>(in.um, in.ld_um, I, wcol, wval, wnnz, w);
       }

@@ -199,3 +199,37 @@ def test_gradients_on_a_binary_graph_vs_oracle_autograd():
     for k in ('item_embeddings.0.weight', 'user_embeddings.0.weight', 'gnn_convs.0.user2item_W.0.weight', 'gnn_convs.0.item2user_W.0.weight',
               'gnn_convs.0.item2user_W.0.bias', 'MLP.0.weight'):
         assert maxnorm_rel(got[k].grad, ref_sd[k].grad) < 1e-4, k
+
+
+@pytest.mark.parametrize('I', [1, 2, 3, 5, 37, 1021, 4099, 10241])
+def test_dense_user_matrix_of_every_alignment_phase(I):
+    """The dense front-end stages a row of `user_matrix` with 128-bit accesses, shifted by the row's phase inside a 16-byte granule
+    (um_compact_vec_kernel).  Rows of odd length, column-sliced views (leading dimension != I, base pointer off by 1-3 words), first / last
+    vectors that are only partly inside the row, a row wider than one round of loads: same result as the float64 closed form every time."""
+    from deeprecommendation_b200 import _lib as L
+    from deeprecommendation_b200 import ops
+    B, H, U = 9, 128, 128
+    g = torch.Generator().manual_seed(I)
+    Pc, Pr, Q = torch.randn(B, H, generator=g), torch.randn(I, H, generator=g), torch.randn(I, U, generator=g)
+    a2, a20, bU = torch.randn(H, generator=g) / H ** 0.5, torch.randn(1, generator=g), torch.randn(U, generator=g)
+    full = ((torch.randint(1, 11, (B, I + 3), generator=g).float() * 0.5 - 2.75) * (torch.rand(B, I + 3, generator=g) < 0.4)).float()
+    full[:, :4] = torch.randint(1, 11, (B, 4), generator=g).float() * 0.5 - 2.75        # edges of every view are rated
+    full[:, -4:] = torch.randint(1, 11, (B, 4), generator=g).float() * 0.5 - 2.75
+    full[2] = 0.0                                                                      # a user without ratings
+    fd = full.to(DEV)
+    args = [t.to(DEV) for t in (Pc, Pr, Q)]
+    kw = dict(mode=L.ATT_NET, a2=a2.to(DEV), a20=a20.to(DEV), bU=bU.to(DEV))
+    for off in range(4):
+        um = fd[:, off:off + I]
+        assert um.stride(0) == I + 3
+        out, att = ops.attention_pool(*args, user_matrix=um, return_attention_weights=True, **kw)
+        umd = full[:, off:off + I].double()
+        hidden = (Pc.double()[:, None, :] + Pr.double()[None, :, :]).relu()
+        s = hidden @ a2.double() + a20.double()
+        s = torch.where(umd != 0, s, torch.full_like(s, float('-inf')))
+        alpha = torch.nan_to_num(torch.softmax(s, dim=1), nan=0.0)
+        ref = (alpha * umd) @ Q.double() + bU.double()
+        assert maxnorm_rel(out, ref) < 1e-5, (I, off)
+        assert maxnorm_rel(att, alpha) < 1e-5, (I, off)
+        out_c = ops.attention_pool(*args, user_matrix=um.contiguous(), **kw)
+        assert torch.equal(out, out_c), (I, off)
