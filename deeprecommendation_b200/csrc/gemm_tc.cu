@@ -293,7 +293,9 @@ struct TileRegs {
 // Measured and dropped (round 2, profiles/r02/gemm_pair_ncu_v1.log): launching the two k-splits of a tile as a thread-block cluster so that split 0
 // can wait for split 1's tile and finish the output itself (no second slab, no reduction kernel).  Both ways of handing the tile over lost:
 // through distributed shared memory (~21 B/clk: +7 us), and through L2 with only the cluster barrier as the signal — the cluster launch of
-// these 193 KB CTAs alone takes the kernel from 30 us to 49 us.
+// these 193 KB CTAs takes the kernel from 30 us to 49 us.  A third form without clusters — tickets from a per-tile semaphore, the first split
+// to finish leaves its tile in one slab, the second adds it from L2 and completes the output — measured 46 us: only half of the CTAs take part in
+// that tail, eight warps each, whereas tc_splitk_reduce_kernel streams the two slabs with every SM (8 us).  The separate reduction stays.
 template <int MODE, int NSTAGE, int EPL, bool VEC, bool WPACK, int BN = TC_BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcBatch batch) {
