@@ -1,5 +1,12 @@
 mkdir -p gpurun_out
-python tools/gemm_one.py 9461x2094x256 'bf16x3!' || exit 1
-ncu --set full --import-source on --clock-control none -k regex:"gemm_tc_kernel|tc_splitk_reduce" -s 2 -c 2 -f -o gpurun_out/ncu_gemm_bf16x3_v2 python tools/gemm_one.py 9461x2094x256 'bf16x3!' 4 > gpurun_out/ncu_g1.log 2>&1; tail -1 gpurun_out/ncu_g1.log
-ncu --set full --import-source on --clock-control none -k regex:"gemm_tc_kernel" -s 1 -c 1 -f -o gpurun_out/ncu_gemm_tf32x3_v2 python tools/gemm_one.py 9461x2094x256 'tf32x3!' 4 > gpurun_out/ncu_g2.log 2>&1; tail -1 gpurun_out/ncu_g2.log
-python tools/gemm_bench.py > gpurun_out/gemm_bench_v2.log 2>&1; tail -3 gpurun_out/gemm_bench_v2.log
+export NCCL_DEBUG=WARN
+timeout 1700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 8 > gpurun_out/bench_v2_n8.json 2> gpurun_out/bench_v2_n8.err; echo "rc=$?"
+tail -3 gpurun_out/bench_v2_n8.err
+python - <<'PY'
+import json
+d = json.loads(open('gpurun_out/bench_v2_n8.json').read().strip().splitlines()[-1])
+print({k: d.get(k) for k in ('value', 'ms_per_step', 'n_gpus', 'e2e', 'scaling', 'host_binding')})
+for a in d.get('also', []):
+    print(a.get('metric', a.get('workload')), a.get('value'), a.get('ms_per_step'))
+print(json.dumps(d.get('graph_scaling'))[:700])
+PY
