@@ -30,7 +30,7 @@ class AttentionDesc(C.Structure):
                 ('B', c_i64), ('I', c_i64), ('H', c_int), ('U', c_int), ('out', c_vp), ('ldo', c_i64), ('att_weights', c_vp),
                 ('train_cand_emb', c_vp), ('train_rated_emb', c_vp), ('E', c_int), ('atol', c_f), ('rtol', c_f),
                 ('drop_zero_scores', c_int), ('score_scale', c_f), ('ld_pr', c_i64), ('ld_q', c_i64), ('workspace', c_vp), ('workspace_bytes', c_sz),
-                ('max_row_nnz', c_i64), ('nnz', c_i64), ('prepared', c_int), ('ld_pc', c_i64), ('dropout_p', c_f), ('dropout_seed', C.c_uint64)]
+                ('max_row_nnz', c_i64), ('nnz', c_i64), ('prepared', c_int), ('ld_pc', c_i64), ('dropout_p', c_f), ('dropout_seed', C.c_uint64), ('dropout_seed_dev', c_vp)]
 
 
 class AttentionBwdDesc(C.Structure):
@@ -38,7 +38,7 @@ class AttentionBwdDesc(C.Structure):
                 ('att_weights', c_vp), ('out', c_vp), ('ldo', c_i64), ('grad_out', c_vp), ('ld_grad_out', c_i64), ('B', c_i64), ('I', c_i64),
                 ('H', c_int), ('U', c_int), ('score_scale', c_f), ('ld_pc', c_i64), ('ld_pr', c_i64), ('ld_q', c_i64),
                 ('dPc', c_vp), ('dPr', c_vp), ('dQ', c_vp), ('da2_rows', c_vp), ('da20_rows', c_vp), ('n_slices', c_int), ('dropout_p', c_f),
-                ('dropout_seed', C.c_uint64)]
+                ('dropout_seed', C.c_uint64), ('dropout_seed_dev', c_vp)]
 
 
 class LinearProblem(C.Structure):

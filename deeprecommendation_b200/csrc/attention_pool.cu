@@ -63,6 +63,7 @@ struct AttParams {
   long long ldPr, ldQ, ldPc;
   unsigned drop_key, drop_thr16;   // inner dropout (B200REC_ATT_DROPOUT build only): Philox key, keep threshold on 16 bits
   float drop_scale;
+  const unsigned long long* drop_seed_dev;   // optional: the 64-bit seed lives in device memory (CUDA-graph replays draw a new one each time)
 };
 
 
@@ -104,6 +105,7 @@ struct RowCore {
   float pc[HV][4], a2[HV][4];
   float acc[UV][4];
   float m, l, a20;
+  unsigned dkey;          // Philox key of the inner dropout (dropout build)
 
   __device__ RowCore(const AttParams& p_, int lane_, int b_) : p(p_), lane(lane_), b(b_) {
 #pragma unroll
@@ -124,6 +126,13 @@ struct RowCore {
     m = -INFINITY;
     l = 0.f;
     a20 = (MODE == MODE_NET && p.a20) ? __ldg(p.a20) : 0.f;
+    dkey = p.drop_key;
+#ifdef B200REC_ATT_DROPOUT
+    if (p.drop_seed_dev != nullptr) {
+      const unsigned long long sd = __ldg(p.drop_seed_dev);
+      dkey = (unsigned)(sd ^ (sd >> 32));
+    }
+#endif
   }
 
   // scores of one batch (lane-partial dot products in v[0..31]) -> online-softmax state update; returns this lane's
@@ -205,7 +214,7 @@ struct RowCore {
             const float r[4] = {pr[jj][hv].x, pr[jj][hv].y, pr[jj][hv].z, pr[jj][hv].w};
 #ifdef B200REC_ATT_DROPOUT
             float dm[4] = {1.f, 1.f, 1.f, 1.f};
-            if (MODE == MODE_NET && p.drop_thr16 < 65536u) att_dropout_mult(p.drop_key, p.drop_thr16, p.drop_scale, b, cdrop, lane + 32 * hv, dm);
+            if (MODE == MODE_NET && p.drop_thr16 < 65536u) att_dropout_mult(dkey, p.drop_thr16, p.drop_scale, b, cdrop, lane + 32 * hv, dm);
 #endif
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -269,7 +278,7 @@ struct RowCore {
         const float r[4] = {r4.x, r4.y, r4.z, r4.w};
 #ifdef B200REC_ATT_DROPOUT
         float dm[4] = {1.f, 1.f, 1.f, 1.f};
-        if (MODE == MODE_NET && p.drop_thr16 < 65536u) att_dropout_mult(p.drop_key, p.drop_thr16, p.drop_scale, b, __shfl_sync(FULL, my_col, j), lane, dm);
+        if (MODE == MODE_NET && p.drop_thr16 < 65536u) att_dropout_mult(dkey, p.drop_thr16, p.drop_scale, b, __shfl_sync(FULL, my_col, j), lane, dm);
 #endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -997,7 +1006,7 @@ extern "C" int B200REC_ATT_ENTRY(const b200rec_attention_t* a, b200rec_stream_t 
   p.ldPr = a->ld_pr ? a->ld_pr : a->H;
   p.ldQ = a->ld_q ? a->ld_q : a->U;
   p.ldPc = a->ld_pc ? a->ld_pc : a->H;
-  p.drop_key = 0u; p.drop_thr16 = 65536u; p.drop_scale = 1.f;
+  p.drop_key = 0u; p.drop_thr16 = 65536u; p.drop_scale = 1.f; p.drop_seed_dev = nullptr;
 #ifdef B200REC_ATT_DROPOUT
   if (!(a->dropout_p >= 0.f && a->dropout_p < 1.f)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_dropout: need 0 <= dropout_p < 1");
   if (a->B >= (1 << 26)) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool_dropout: more than 2^26 candidate rows");
@@ -1008,6 +1017,7 @@ extern "C" int B200REC_ATT_ENTRY(const b200rec_attention_t* a, b200rec_stream_t 
     p.drop_thr16 = thr;
     p.drop_scale = 65536.f / (float)thr;
     p.drop_key = (unsigned)(a->dropout_seed ^ (a->dropout_seed >> 32));
+    p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(a->dropout_seed_dev);
   }
 #else
   if (a->dropout_p != 0.f) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: inner dropout is applied by b200rec_attention_pool_dropout");

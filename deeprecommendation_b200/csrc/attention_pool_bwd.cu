@@ -36,6 +36,7 @@ struct AttBwdParams {
   float *dPc, *dPr, *dQ, *da2_rows, *da20_rows;     // dPc (B,H) and the per-row parts are written; dPr (I,H), dQ (I,U) are added to
   unsigned drop_key, drop_thr16;                    // AttentionNet's inner dropout: the forward's Philox mask is regenerated (65536 = off)
   float drop_scale;
+  const unsigned long long* drop_seed_dev;          // the seed in device memory (graph replays), or nullptr
 };
 
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
@@ -121,7 +122,14 @@ struct BwdRow {
         const float r[4] = {pr[k][hv].x, pr[k][hv].y, pr[k][hv].z, pr[k][hv].w};
         float t[4];
         float dm[4] = {1.f, 1.f, 1.f, 1.f};                         // hidden = ReLU(z) ∘ dm: the forward's dropout multipliers of this pair
-        if (MODE == BWD_NET && p.drop_thr16 < 65536u) att_dropout_mult(p.drop_key, p.drop_thr16, p.drop_scale, brow, ii[k], lane + 32 * hv, dm);
+        if (MODE == BWD_NET && p.drop_thr16 < 65536u) {
+          unsigned dkey = p.drop_key;
+          if (p.drop_seed_dev != nullptr) {
+            const unsigned long long sd = __ldg(p.drop_seed_dev);
+            dkey = (unsigned)(sd ^ (sd >> 32));
+          }
+          att_dropout_mult(dkey, p.drop_thr16, p.drop_scale, brow, ii[k], lane + 32 * hv, dm);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (MODE == BWD_NET) {
@@ -226,7 +234,7 @@ extern "C" int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a,
   p.ld_um = a->ld_user_matrix ? a->ld_user_matrix : a->I; p.ldo = a->ldo ? a->ldo : a->U; p.ldg = a->ld_grad_out ? a->ld_grad_out : a->U;
   p.B = (int)a->B; p.I = (int)a->I; p.H = a->H; p.U = a->U;
   p.score_scale = a->score_scale == 0.f ? 1.f : a->score_scale;
-  p.drop_key = 0u; p.drop_thr16 = 65536u; p.drop_scale = 1.f;
+  p.drop_key = 0u; p.drop_thr16 = 65536u; p.drop_scale = 1.f; p.drop_seed_dev = nullptr;
   if (a->dropout_p != 0.f) {                        // same derivation as b200rec_attention_pool_dropout
     if (!(a->dropout_p > 0.f && a->dropout_p < 1.f) || a->B >= (1 << 26)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool_backward: bad dropout_p");
     unsigned thr = (unsigned)((1.0 - (double)a->dropout_p) * 65536.0 + 0.5);
@@ -235,6 +243,7 @@ extern "C" int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a,
     p.drop_thr16 = thr;
     p.drop_scale = 65536.f / (float)thr;
     p.drop_key = (unsigned)(a->dropout_seed ^ (a->dropout_seed >> 32));
+    p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(a->dropout_seed_dev);
   }
   {
     const int n_slices = a->n_slices > 1 ? a->n_slices : 1;

@@ -224,7 +224,8 @@ class AttentionNCF(NCF):
             if p_inner > 0.0:
                 # the mask is a Philox stream keyed by a seed drawn from torch's default generator (reproducible under torch.manual_seed); it
                 # cannot be bit-matched to torch's own dropout stream, like every other dropout of the reference
-                inner = (p_inner, int(torch.randint(0, 2 ** 62, (1,)).item()))
+                # drawn ON the device (no host round trip, and a captured training step gets a new mask on every replay)
+                inner = (p_inner, torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=Pc.device))
         res = ops.attention_pool(Pc, Pr, Q, mode=mode, a2=a2, a20=a20,
                                  bU=bU, user_matrix=um, return_attention_weights=return_attention_weights,
                                  train_mask=train_mask, drop_zero_scores=drop_zero, score_scale=scale, inner_dropout=inner)

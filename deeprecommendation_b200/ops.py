@@ -642,6 +642,17 @@ def attention_prepare(user_matrix, U):
     return AttentionPrepared(ws, um, (B, I), U)
 
 
+def _set_dropout_seed(d, seed, device):
+    """`seed`: a Python int (baked into the launch), or a one-element int64 CUDA tensor the kernels read at run time — what a captured CUDA graph
+    needs, since a replay must draw a new mask (the tensor is produced by torch's graph-safe generator inside the capture)."""
+    if torch.is_tensor(seed):
+        if seed.device != torch.device(device) or seed.dtype != torch.int64 or seed.numel() != 1:
+            raise ValueError('inner dropout: the seed tensor must be one int64 on the device of the tables')
+        d.dropout_seed, d.dropout_seed_dev = 0, seed.data_ptr()
+    else:
+        d.dropout_seed, d.dropout_seed_dev = int(seed) & (2 ** 64 - 1), None
+
+
 def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None, user_matrix=None, csr=None,
                        return_attention_weights=False, train_mask=None, drop_zero_scores=False, score_scale=1.0, use_workspace=True, max_row_nnz=0,
                        prepared=None, inner_dropout=None):
@@ -722,7 +733,8 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
         # training: AttentionNet's Dropout between ReLU and the head Linear (attention_ncf.py:112-117), mask = Philox keyed by `seed`
         if mode != L.ATT_NET or Pr.dtype != torch.float32:
             raise ValueError('inner dropout belongs to the AttentionNet variant with fp32 tables')
-        d.dropout_p, d.dropout_seed = float(inner_dropout[0]), int(inner_dropout[1]) & (2 ** 64 - 1)
+        d.dropout_p = float(inner_dropout[0])
+        _set_dropout_seed(d, inner_dropout[1], Pc.device)
         entry = L.lib().b200rec_attention_pool_dropout
     with torch.cuda.device(Pc.device), _timed('attention_pool', (B, I, H, U)):
         L.check(entry(C.byref(d), _stream()), 'attention_pool')
@@ -993,7 +1005,8 @@ def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode,
     if net:
         d.da2_rows, d.da20_rows = da2_rows.data_ptr(), da20_rows.data_ptr()
     if inner_dropout is not None and inner_dropout[0] > 0.0:
-        d.dropout_p, d.dropout_seed = float(inner_dropout[0]), int(inner_dropout[1]) & (2 ** 64 - 1)
+        d.dropout_p = float(inner_dropout[0])
+        _set_dropout_seed(d, inner_dropout[1], dev)
     with torch.cuda.device(dev), _timed('attention_pool_backward', (B, I, H, U)):
         L.check(L.lib().b200rec_attention_pool_backward(C.byref(d), _stream()), 'attention_pool_backward')
     if S > 1:

@@ -221,6 +221,7 @@ typedef struct {
   int64_t ld_pc;          /* leading dimension of Pc in elements (a column slice of the [Ec | Pc] projection is used in place); 0 = H */
   float dropout_p;        /* training only, b200rec_attention_pool_dropout: p of the Dropout between AttentionNet's ReLU and its head Linear */
   uint64_t dropout_seed;  /* (attention_ncf.py:112-117); mask = Philox2x32-10 keyed by the seed, regenerated by the backward kernel */
+  const uint64_t* dropout_seed_dev;   /* optional: read the seed from DEVICE memory instead (a captured CUDA graph draws a new seed per replay) */
 } b200rec_attention_t;
 size_t b200rec_attention_pool_workspace(int64_t B, int64_t I, int U, int dense);
 size_t b200rec_attention_pool_workspace_csr(int64_t B, int64_t I, int U, int64_t max_row_nnz, int64_t nnz);
@@ -270,6 +271,7 @@ typedef struct {
                              * hold n parts of B rows each (part-major), which the caller adds */
   float dropout_p;          /* the forward's inner dropout (b200rec_attention_pool_dropout): same p and seed regenerate the same mask; 0 = none */
   uint64_t dropout_seed;
+  const uint64_t* dropout_seed_dev;   /* as in b200rec_attention_t: the same device word the forward read */
 } b200rec_attention_bwd_t;
 int b200rec_attention_pool_backward(const b200rec_attention_bwd_t* a, b200rec_stream_t stream);
 
