@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200REC_VERSION 200
+#define B200REC_VERSION 201
 
 typedef void* b200rec_stream_t; /* cudaStream_t */
 

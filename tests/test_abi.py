@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, n), f'{n} declared in include/b200rec.h but not exported'
     assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
     lib = _lib.lib()
-    assert lib.b200rec_version() == 200
+    assert lib.b200rec_version() == 201
 
 
 def test_struct_layouts_match_header_field_order():
