@@ -37,3 +37,39 @@ class GraphedForward:
         """re-run on whatever the captured input buffers (`static_in`) hold"""
         self.graph.replay()
         return self.static_out
+
+
+class PipelinedScoring:
+    """Several captured forwards (one per batch shape) fed from pinned host buffers.  The host -> device copy of batch k + 1 runs on a copy stream
+    while batch k replays (each graph owns its input buffers, so the only hazard is a graph's OWN previous replay: an event per graph), the
+    scores land in pinned host buffers, and the call synchronises once at its end.  At config 2 a batch is 103 MB of inputs for 0.13 ms of
+    kernels: the call is PCIe-bound and the pipeline hides the kernels behind the copies."""
+
+    def __init__(self, graphs):
+        self.graphs = list(graphs)
+        self.copy = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event() for _ in self.graphs]       # inputs of graph k are on the device
+        self.consumed = [torch.cuda.Event() for _ in self.graphs]    # graph k has finished reading them
+        self.out_host = [torch.empty(g.static_out.shape, dtype=g.static_out.dtype).pin_memory() for g in self.graphs]
+        self._first = True
+
+    def __call__(self, host_batches):
+        """host_batches[k]: the (pinned) host tensors of graph k's captured shapes.  Returns the list of pinned host results (overwritten by the
+        next call)."""
+        cur = torch.cuda.current_stream()
+        self.copy.wait_stream(cur)                       # whatever the caller still has queued on the captured input buffers
+        with torch.cuda.stream(self.copy):
+            for k, (g, batch) in enumerate(zip(self.graphs, host_batches)):
+                if not self._first:
+                    self.copy.wait_event(self.consumed[k])
+                for dst, src in zip(g.static_in, batch):
+                    dst.copy_(src, non_blocking=True)
+                self.ready[k].record(self.copy)
+        for k, g in enumerate(self.graphs):
+            cur.wait_event(self.ready[k])
+            g.graph.replay()
+            self.consumed[k].record(cur)
+            self.out_host[k].copy_(g.static_out, non_blocking=True)
+        self._first = False
+        cur.synchronize()
+        return self.out_host

@@ -597,3 +597,31 @@ def test_lightgat_gradients_vs_oracle_autograd(masked):
             assert float(gk[:, d_emb:].abs().max()) == 0.0 and float(rk[:, d_emb:].abs().max()) < 1e-5 * scale, k
         else:
             assert maxnorm_rel(gk, rk) < 1e-4, k
+
+
+def test_pipelined_scoring_equals_sequential_replays():
+    """graphed.PipelinedScoring: H2D copies of batch k + 1 under the kernels of batch k, per-graph events against a graph's own previous replay.
+    Three batch shapes, two calls with different inputs: every result equals the plain captured forward on the same inputs."""
+    from deeprecommendation_b200.graphed import GraphedForward, PipelinedScoring
+    kw = dict(item_dim=96, item_emb=128, user_emb=128, att_dense=128, mlp_dense_layers=[64], dropout_rate=0.2)
+    m = _models().AttentionNCF(**kw).to(DEV).eval()
+    m.load_state_dict(synth.to_torch(synth.attention_ncf_weights(seed=4, **kw)))
+    rng = np.random.default_rng(8)
+
+    def batch(B, I, seed):
+        prof = synth.item_profiles(I + B, seed=seed, f_binary=48, f_dense=48)
+        um = ((rng.integers(1, 11, (B, I)) * 0.5 - 2.75) * (rng.random((B, I)) < 0.3)).astype(np.float32)
+        return tuple(torch.from_numpy(a).pin_memory() for a in (prof[I:], prof[:I], um))
+
+    shapes = [(64, 300), (64, 517), (32, 1200)]
+    first = [batch(B, I, 10 + k) for k, (B, I) in enumerate(shapes)]
+    second = [batch(B, I, 20 + k) for k, (B, I) in enumerate(shapes)]
+    graphs = [GraphedForward(lambda c, r, u: m(c, r, u), *(t.to(DEV) for t in b)) for b in first]
+    pipe = PipelinedScoring(graphs)
+    for batches in (first, second, first):
+        got = [t.clone() for t in pipe(batches)]
+        for k, b in enumerate(batches):
+            want = graphs[k](*b).cpu()
+            assert torch.equal(got[k], want), k
+            with torch.no_grad():
+                assert maxnorm_rel(got[k], m(*(t.to(DEV) for t in b)).cpu()) < 1e-6
