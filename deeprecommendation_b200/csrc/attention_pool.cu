@@ -106,6 +106,8 @@ struct RowCore {
   float acc[UV][4];
   float m, l, a20;
   unsigned dkey;          // Philox key of the inner dropout (dropout build)
+  unsigned hcol[HV], ucol[UV];   // this lane's column vector of a Pr / Q row (float4 units, clamped to the last one in range)
+  int ldPr, ldQ;
 
   __device__ RowCore(const AttParams& p_, int lane_, int b_) : p(p_), lane(lane_), b(b_) {
 #pragma unroll
@@ -126,6 +128,11 @@ struct RowCore {
     m = -INFINITY;
     l = 0.f;
     a20 = (MODE == MODE_NET && p.a20) ? __ldg(p.a20) : 0.f;
+    ldPr = (int)p.ldPr; ldQ = (int)p.ldQ;
+#pragma unroll
+    for (int hv = 0; hv < HV; ++hv) hcol[hv] = (unsigned)min(lane * 4 + hv * 128, p.H - 4) >> 2;
+#pragma unroll
+    for (int uv = 0; uv < UV; ++uv) ucol[uv] = (unsigned)min(lane * 4 + uv * 128, p.U - 4) >> 2;
     dkey = p.drop_key;
 #ifdef B200REC_ATT_DROPOUT
     if (p.drop_seed_dev != nullptr) {
@@ -183,12 +190,23 @@ struct RowCore {
     return pj * my_val;
   }
 
-  // lane j holds non-zero j of this batch (col < 0 beyond `count`)
+  // lane j holds non-zero j of this batch (col < 0 beyond `count`).
+  // Round 2 (ncu source page: 67 instructions per (candidate, rated item) pair and lane, 63 % of them overhead — 64-bit address products per
+  // gathered row, kernel parameters re-read from the constant bank, zero-fill and selects around predicated loads): every lane computes the row
+  // offsets of ITS entry once per batch, in units of one 4-element vector (32 bits: tables below 2^34 elements, checked on the host), and the
+  // inner loops broadcast that one word.  The gathers are unconditional: a lane without an entry (beyond `count`, or an explicit zero of a CSR)
+  // points at the row of the batch's first valid entry — a row this candidate uses anyway, so no new inf / NaN can enter — its score is forced to
+  // -inf and its pooling weight is 0.  Columns past H / U read the last in-range vector: Pc and a2 are zero there, and pooled lanes past U are
+  // never stored.
   __device__ void batch(int my_col, float my_val, int count) {
     const T* __restrict__ Pr = reinterpret_cast<const T*>(p.Pr);
     const T* __restrict__ Q = reinterpret_cast<const T*>(p.Q);
+    const unsigned valid = __ballot_sync(FULL, my_col >= 0);
+    if (valid == 0u) return;                               // nothing rated in this batch: state unchanged
+    const int c_fill = __shfl_sync(FULL, my_col, __ffs(valid) - 1);
+    const unsigned row = (unsigned)(my_col >= 0 ? my_col : c_fill);
+    const unsigned offPr = row * (unsigned)(ldPr >> 2), offQ = row * (unsigned)(ldQ >> 2);     // float4 / 4 x bf16 units
     float v[32];
-#pragma unroll
     constexpr int LB = (HV == 1 && UV == 1) ? 16 : 8;     // row gathers in flight per warp
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += LB) {
@@ -196,12 +214,9 @@ struct RowCore {
         float4 pr[LB][HV];
 #pragma unroll
         for (int jj = 0; jj < LB; ++jj) {
-          const int c = __shfl_sync(FULL, my_col, j0 + jj);
+          const unsigned o = __shfl_sync(FULL, offPr, j0 + jj);
 #pragma unroll
-          for (int hv = 0; hv < HV; ++hv) {
-            const int h = lane * 4 + hv * 128;
-            pr[jj][hv] = (c >= 0 && h < p.H) ? ld4(Pr + (long long)c * p.ldPr + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int hv = 0; hv < HV; ++hv) pr[jj][hv] = ld4(Pr + ((size_t)(o + hcol[hv]) << 2));
         }
 #pragma unroll
         for (int jj = 0; jj < LB; ++jj) {
@@ -235,20 +250,16 @@ struct RowCore {
     }
     const float wgt = softmax_update(v, my_col, my_val, count);
 #pragma unroll
-#pragma unroll
     for (int j0 = 0; j0 < 32; j0 += LB) {
       if (j0 < count) {
         float4 q[LB][UV];
         float w[LB];
 #pragma unroll
         for (int jj = 0; jj < LB; ++jj) {
-          const int c = __shfl_sync(FULL, my_col, j0 + jj);
+          const unsigned o = __shfl_sync(FULL, offQ, j0 + jj);
           w[jj] = __shfl_sync(FULL, wgt, j0 + jj);
 #pragma unroll
-          for (int uv = 0; uv < UV; ++uv) {
-            const int u = lane * 4 + uv * 128;
-            q[jj][uv] = (c >= 0 && u < p.U) ? ld4(Q + (long long)c * p.ldQ + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int uv = 0; uv < UV; ++uv) q[jj][uv] = ld4(Q + ((size_t)(o + ucol[uv]) << 2));
         }
 #pragma unroll
         for (int jj = 0; jj < LB; ++jj)
@@ -391,24 +402,51 @@ attention_pool_csr_kernel(AttParams p, const int* __restrict__ row_ptr, const in
 // combines a row's partials in segment order (bit-reproducible), adds b_U and normalises the attention weights.
 constexpr int ATT_WSEG = 64;
 
+// Round 2 — a two-ended list.  Config 2 has ~4,900 items for 2,368 resident warps: with one list 7 % of the warps took a third full-length item while
+// the rest idled (ncu: issue slots 53 % busy on the active cycles, 23 % of the warp slots).  A row's last segment is SHORT when it holds <= 32 entries
+// (one batch of gathers instead of two); short items are appended from the END of the list (counter[1]), everything else from the front
+// (counter[0]), and the warps walk front-then-back: whatever spills into a last round is a single batch.  A partial lives in the slot of its item's
+// list position; seg_base[b] is the first front slot of row b, tail_pos[b] the slot of its short last segment (or -1).
 struct AttWork {
-  int* counter;        // [0] = number of items
+  int* counter;        // [0] = items at the front of the list, [1] = short items at its end
+  int* tail_pos;       // (B): list position of the row's short last segment, -1 if it has none
   int* seg_base;       // (B): first partial slot of the row
   int2* items;         // (row, segment)
   float* partials;     // (n_items, U + 4): m, l, -, -, acc[U]
   int max_items;       // capacity of items / partials (a max_row_nnz hint that is not a true bound must not overrun them)
 };
 
-__device__ __forceinline__ void att_emit_items(const AttWork& w, int b, int len, int tid, int nthreads, int* s_base) {
-  const int n = (len + ATT_WSEG - 1) / ATT_WSEG;
-  if (tid == 0) {
-    const int base = n > 0 ? atomicAdd(w.counter, n) : 0;
-    w.seg_base[b] = base;
-    *s_base = base;
+// segments of a row of `len` entries, and how many of them go to the front of the list (all but a short last one)
+__device__ __forceinline__ int att_nseg(long long len) { return (int)((len + ATT_WSEG - 1) / ATT_WSEG); }
+__device__ __forceinline__ int att_nfront(long long len) {
+  const int rem = (int)(len % ATT_WSEG);
+  return att_nseg(len) - ((rem >= 1 && rem <= 32) ? 1 : 0);
+}
+// one thread: reserve the row's list positions (front block + short tail), record them, write the tail item; returns the front base
+__device__ __forceinline__ int att_reserve_row(const AttWork& w, int b, long long len) {
+  const int n = att_nseg(len), nf = att_nfront(len);
+  const int base = nf > 0 ? atomicAdd(w.counter, nf) : 0;
+  w.seg_base[b] = base;
+  int tail = -1;
+  if (n > nf) {
+    tail = w.max_items - 1 - atomicAdd(w.counter + 1, 1);
+    if (tail >= 0) w.items[tail] = make_int2(b, n - 1);
   }
+  w.tail_pos[b] = tail;
+  return base;
+}
+// Both ends grow towards each other inside `max_items` slots; with a true bound on the number of items they never meet.  If a caller's hint was
+// too small, front writes stop at the capacity (as before) and the counters are clamped by the readers (att_list_counts).
+__device__ __forceinline__ void att_list_counts(const AttWork& w, int& front, int& back) {
+  front = min(__ldg(w.counter), w.max_items);
+  back = min(__ldg(w.counter + 1), w.max_items - front);
+}
+
+__device__ __forceinline__ void att_emit_items(const AttWork& w, int b, int len, int tid, int nthreads, int* s_base) {
+  if (tid == 0) *s_base = att_reserve_row(w, b, len);
   __syncthreads();
-  const int base = *s_base;
-  for (int j = tid; j < n; j += nthreads)
+  const int base = *s_base, nf = att_nfront(len);
+  for (int j = tid; j < nf; j += nthreads)
     if (base + j < w.max_items) w.items[base + j] = make_int2(b, j);
 }
 
@@ -417,10 +455,8 @@ att_worklist_kernel(const int* __restrict__ row_ptr, int B, AttWork w) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int len = __ldg(row_ptr + b + 1) - __ldg(row_ptr + b);
-  const int n = (len + ATT_WSEG - 1) / ATT_WSEG;
-  const int base = n > 0 ? atomicAdd(w.counter, n) : 0;
-  w.seg_base[b] = base;
-  for (int j = 0; j < n; ++j)
+  const int base = att_reserve_row(w, b, len), nf = att_nfront(len);
+  for (int j = 0; j < nf; ++j)
     if (base + j < w.max_items) w.items[base + j] = make_int2(b, j);
 }
 
@@ -430,8 +466,10 @@ attention_wseg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* _
                       const int* __restrict__ row_nnz, long long padded_stride, AttWork w) {
   const int lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * ATT_WARPS;
-  const int total = min(__ldg(w.counter), w.max_items);
-  for (int it = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5); it < total; it += n_warps) {
+  int front, back;
+  att_list_counts(w, front, back);
+  for (int v = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5); v < front + back; v += n_warps) {
+    const int it = v < front ? v : w.max_items - 1 - (v - front);          // list position = partial slot
     const int2 item = __ldg(w.items + it);
     const int b = item.x, seg = item.y;
     const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
@@ -443,7 +481,7 @@ attention_wseg_kernel(AttParams p, const int* __restrict__ row_ptr, const int* _
     float v0 = 0.f, v1 = 0.f;
     if (seg_start + lane < seg_end) { c0 = __ldg(col + seg_start + lane); v0 = __ldg(val + seg_start + lane); }
     if (seg_start + 32 + lane < seg_end) { c1 = __ldg(col + seg_start + 32 + lane); v1 = __ldg(val + seg_start + 32 + lane); }
-    const int slot_idx = __ldg(w.seg_base + b) + seg;
+    const int slot_idx = it;
     RowCore<HV, UV, MODE, T> core(p, lane, b);
     const int n0 = (int)min(32LL, seg_end - seg_start);
     core.batch(v0 != 0.f ? c0 : -1, v0, n0);                      // an explicit 0.0 is "unrated", like the dense form
@@ -482,8 +520,10 @@ attention_wseg_tma_kernel(AttParams p, const int* __restrict__ row_ptr, const in
   const T* __restrict__ Pr = reinterpret_cast<const T*>(p.Pr);
   const T* __restrict__ Q = reinterpret_cast<const T*>(p.Q);
   const int n_warps = gridDim.x * warps;
-  const int total = min(__ldg(w.counter), w.max_items);
-  for (int it = blockIdx.x * warps + warp; it < total; it += n_warps) {
+  int front, back;
+  att_list_counts(w, front, back);
+  for (int v = blockIdx.x * warps + warp; v < front + back; v += n_warps) {
+    const int it = v < front ? v : w.max_items - 1 - (v - front);          // list position = partial slot
     const int2 item = __ldg(w.items + it);
     const int b = item.x, seg = item.y;
     const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
@@ -499,7 +539,7 @@ attention_wseg_tma_kernel(AttParams p, const int* __restrict__ row_ptr, const in
       if (k < seg_end) { cc[t] = __ldg(col + k); vv[t] = __ldg(val + k); }
       if (vv[t] == 0.f) cc[t] = -1;                               // an explicit 0.0 is "unrated", like the dense form
     }
-    const int slot_idx = __ldg(w.seg_base + b) + seg;
+    const int slot_idx = it;
     RowCore<1, 1, MODE, T> core(p, lane, b);
 #pragma unroll
     for (int t = 0; t < ATT_WSEG / 32; ++t) {
@@ -540,16 +580,18 @@ attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* 
   const long long start = row_nnz ? (long long)b * padded_stride : (long long)__ldg(row_ptr + b);
   const long long end = row_nnz ? start + __ldg(row_nnz + b) : (long long)__ldg(row_ptr + b + 1);
   const int first = __ldg(w.seg_base + b);
-  const int nseg = max(0, min((int)((end - start + ATT_WSEG - 1) / ATT_WSEG), w.max_items - first));
+  const int nf = max(0, min(att_nfront(end - start), w.max_items - first));          // segments at the front of the list: slots first, first + 1, ...
+  const int tail = att_nseg(end - start) > att_nfront(end - start) ? __ldg(w.tail_pos + b) : -1;      // + the short last segment, if any
+  const int nseg = nf + (tail >= 0 ? 1 : 0);
   const long long stride = p.U + 4;
-  const float* base = w.partials + (long long)first * stride;
+  auto slot = [&](int sidx) -> const float* { return w.partials + (long long)(sidx < nf ? first + sidx : tail) * stride; };
   float M = -INFINITY;
-  for (int s0 = 0; s0 < nseg; s0 += 32) M = fmaxf(M, (s0 + lane < nseg) ? base[(long long)(s0 + lane) * stride] : -INFINITY);
+  for (int s0 = 0; s0 < nseg; s0 += 32) M = fmaxf(M, (s0 + lane < nseg) ? *slot(s0 + lane) : -INFINITY);
   M = warp_max(M);
   float Lsum = 0.f;
   for (int s0 = 0; s0 < nseg; s0 += 32) {
     if (s0 + lane < nseg) {
-      const float2 ml = *reinterpret_cast<const float2*>(base + (long long)(s0 + lane) * stride);
+      const float2 ml = *reinterpret_cast<const float2*>(slot(s0 + lane));
       Lsum += ml.y * ((ml.x == -INFINITY) ? 0.f : __expf(ml.x - M));
     }
   }
@@ -565,9 +607,10 @@ attention_merge_kernel(AttParams p, const int* __restrict__ row_ptr, const int* 
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         f[k] = 0.f;
         if (s0 + k < nseg) {
-          const float ms = base[(long long)(s0 + k) * stride];
+          const float* sp = slot(s0 + k);
+          const float ms = sp[0];
           f[k] = (ms == -INFINITY) ? 0.f : __expf(ms - M);
-          v[k] = *reinterpret_cast<const float4*>(base + (long long)(s0 + k) * stride + 4 + u);
+          v[k] = *reinterpret_cast<const float4*>(sp + 4 + u);
         }
       }
 #pragma unroll
@@ -827,13 +870,14 @@ static long long att_max_items(long long B, long long I, long long max_row_nnz, 
   if (max_row_nnz > 0) return std::min(full, B * ((max_row_nnz + ATT_WSEG - 1) / ATT_WSEG));
   return full;
 }
-struct AttLayout { size_t counter, seg_base, items, partials, compact, total; };
-// workspace = counter | seg_base (B) | items | partials | [dense: col, val, row_nnz lists]
+struct AttLayout { size_t counter, tail_pos, seg_base, items, partials, compact, total; };
+// workspace = counters (2) | tail_pos (B) | seg_base (B) | items | partials | [dense: col, val, row_nnz lists]
 static AttLayout att_layout(long long B, long long I, int U, bool dense, long long max_row_nnz, long long nnz) {
   const long long items = att_max_items(B, I, dense ? 0 : max_row_nnz, dense ? 0 : nnz);
   AttLayout l;
   l.counter = 0;
-  l.seg_base = 256;
+  l.tail_pos = 256;
+  l.seg_base = l.tail_pos + align256((size_t)B * sizeof(int));
   l.items = l.seg_base + align256((size_t)B * sizeof(int));
   l.partials = l.items + align256((size_t)items * sizeof(int2));
   l.compact = l.partials + align256((size_t)items * (size_t)(U + 4) * sizeof(float));
@@ -851,13 +895,14 @@ static int att_prepare(int B, int I, int U, const AttInputs& in, cudaStream_t st
   const AttLayout lay = att_layout(B, I, U, dense, in.max_row_nnz, in.nnz);
   unsigned char* ws = reinterpret_cast<unsigned char*>(in.ws);
   w.counter = reinterpret_cast<int*>(ws + lay.counter);
+  w.tail_pos = reinterpret_cast<int*>(ws + lay.tail_pos);
   w.seg_base = reinterpret_cast<int*>(ws + lay.seg_base);
   w.items = reinterpret_cast<int2*>(ws + lay.items);
   w.partials = reinterpret_cast<float*>(ws + lay.partials);
   const long long max_items = att_max_items(B, I, dense ? 0 : in.max_row_nnz, dense ? 0 : in.nnz);
   if (max_items > 0x7fffffffLL) return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: more than 2^31 segments");
   w.max_items = (int)max_items;
-  if (launch) B200REC_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), st));
+  if (launch) B200REC_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(int), st));
   lists.col = in.col; lists.val = in.val; lists.row_nnz = nullptr; lists.row_ptr = in.row_ptr; lists.stride = 0;
   if (dense) {                         // streaming compaction of the dense matrix into row-padded lists (+ the work list)
     int* wcol = reinterpret_cast<int*>(ws + lay.compact);
@@ -1024,6 +1069,9 @@ extern "C" int B200REC_ATT_ENTRY(const b200rec_attention_t* a, b200rec_stream_t 
 #endif
   if (p.ldPc < a->H || (p.ldPc % 4)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: bad Pc leading dimension");
   if (p.ldPr < a->H || p.ldQ < a->U || (p.ldPr % 4) || (p.ldQ % 4)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: bad table leading dimension");
+  // the kernels address a gathered row by a 32-bit count of 4-element vectors
+  if (p.ldPr > 0x7fffffffLL || p.ldQ > 0x7fffffffLL || (double)a->I * (double)(p.ldPr / 4) >= 4294967296.0 || (double)a->I * (double)(p.ldQ / 4) >= 4294967296.0)
+    return b200rec_fail(B200REC_ERR_UNSUPPORTED, "attention_pool: table larger than 2^34 elements");
   if (p.Ec && (!p.Er || p.E <= 0)) return b200rec_fail(B200REC_ERR_BAD_ARG, "attention_pool: training mask needs both embeddings");
   cudaStream_t st = (cudaStream_t)stream;
   const long long ld_um = a->user_matrix ? (a->ld_user_matrix ? a->ld_user_matrix : a->I) : 0;

@@ -1,13 +1,13 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/test_gpu_full.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/test_gpu_full.log
-timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_v3_n1.json 2> gpurun_out/bench_v3_n1.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_v3_n1.err
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_v3.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_v3.log
-timeout 600 python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-260
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_attention_dropout_gpu.py tests/test_edge_cases_gpu.py tests/test_models_gpu.py -x -q -m gpu > gpurun_out/test_k2.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/test_k2.log
+timeout 600 python bench.py --workload attention > gpurun_out/bench_att.json 2> gpurun_out/bench_att.err; echo "rc=$?"
 python - <<'PY'
 import json
-d = json.loads(open('gpurun_out/bench_v3_n1.json').read().strip().splitlines()[-1])
-print({k: d.get(k) for k in ('metric', 'value', 'ms_per_step', 'gpu_launches', 'e2e', 'clocks', 'vs_baseline', 'dtype')})
-print(json.dumps(d.get('train_step'))[:300])
-for a in d.get('also', []):
-    print(a.get('metric', a.get('workload')), a.get('value'), a.get('ms_per_step'), (a.get('parity') or {}).get('max_rel'))
+d = json.loads(open('gpurun_out/bench_att.json').read().strip().splitlines()[-1])
+print({k: d.get(k) for k in ('value', 'ms_per_step', 'gpu_launches')}, d['parity']['max_rel'], d['e2e']['value'])
+print(json.dumps(d['roofline'].get('op_ms_per_batch')))
 PY
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv python bench.py --workload attention --steps 1 --warmup 1 --eager 2>/dev/null | grep gpu__time | awk -F'","' '{print substr($5,1,50), $NF}' | tr -d '"' | grep -i "wseg\|merge\|um_compact" | tail -6
+timeout 600 python bench.py --workload k2hbm 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('k2hbm', d.get('value'), d.get('ms_per_step'), d['roofline'].get('frac'))"
