@@ -161,15 +161,41 @@ struct RowCore {
     if (p.drop_zero_scores && s == 0.f) s = -INFINITY;
     if (p.Ec != nullptr) {     // training: mask rated items whose EMBEDDING is close to the candidate's (:199)
       unsigned masked = 0u;
-      for (int j = 0; j < count; ++j) {
-        const int c = __shfl_sync(FULL, my_col, j);
-        if (c < 0) continue;
-        bool ok = true;
-        for (int e = lane; e < p.E; e += 32) {
-          const float x = __ldg(p.Ec + (long long)b * p.E + e), y = __ldg(p.Er + (long long)c * p.E + e);
-          ok = ok && (fabsf(x - y) <= p.atol + p.rtol * fabsf(y));
+      if (p.E <= 128 && (p.E & 3) == 0 && ((((uintptr_t)p.Ec | (uintptr_t)p.Er) & 15) == 0)) {
+        // the usual shape (item_emb <= 128): a lane owns 4 consecutive embedding columns; the candidate's are read once per batch, the rated
+        // rows as ONE 128-bit gather per pair, eight pairs in flight (the scalar loop below was 4x the cost of the whole pooling in train mode)
+        const int e0 = min(lane * 4, p.E - 4);
+        const bool mine = lane * 4 < p.E;
+        const float4 x = ld4(p.Ec + (long long)b * p.E + e0);
+        const unsigned fill = (unsigned)max(__shfl_sync(FULL, my_col, __ffs(__ballot_sync(FULL, my_col >= 0)) - 1), 0);
+#pragma unroll 1
+        for (int j0 = 0; j0 < count; j0 += 8) {
+          float4 y[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int c = __shfl_sync(FULL, my_col, (j0 + jj) & 31);
+            y[jj] = ld4(p.Er + (long long)(c >= 0 ? (unsigned)c : fill) * p.E + e0);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const bool ok = !mine || (fabsf(x.x - y[jj].x) <= p.atol + p.rtol * fabsf(y[jj].x) && fabsf(x.y - y[jj].y) <= p.atol + p.rtol * fabsf(y[jj].y) &&
+                                      fabsf(x.z - y[jj].z) <= p.atol + p.rtol * fabsf(y[jj].z) && fabsf(x.w - y[jj].w) <= p.atol + p.rtol * fabsf(y[jj].w));
+            const bool close = __all_sync(FULL, ok);
+            const int c = __shfl_sync(FULL, my_col, (j0 + jj) & 31);
+            if (close && j0 + jj < count && c >= 0) masked |= (1u << (j0 + jj));
+          }
         }
-        if (__all_sync(FULL, ok)) masked |= (1u << j);
+      } else {
+        for (int j = 0; j < count; ++j) {
+          const int c = __shfl_sync(FULL, my_col, j);
+          if (c < 0) continue;
+          bool ok = true;
+          for (int e = lane; e < p.E; e += 32) {
+            const float x = __ldg(p.Ec + (long long)b * p.E + e), y = __ldg(p.Er + (long long)c * p.E + e);
+            ok = ok && (fabsf(x - y) <= p.atol + p.rtol * fabsf(y));
+          }
+          if (__all_sync(FULL, ok)) masked |= (1u << j);
+        }
       }
       if ((masked >> lane) & 1u) s = -INFINITY;
     }
