@@ -12,6 +12,7 @@ OK, ERR_CUDA, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 F32, BF16 = 0, 1
 ATT_NET, ATT_DOT = 0, 1
 TC_TF32X3, TC_BF16, TC_BF16X3 = 0, 1, 2
+ABI_VERSION = 201          # B200REC_VERSION of include/b200rec.h these bindings were written against (checked when the library is loaded)
 AP_BF16, AP_BF16X2 = 0, 1
 MLP_MAX_LAYERS = 8
 PEER_MAX, PEER_CHANNELS, PEER_HANDLE_BYTES = 16, 16, 64
@@ -154,6 +155,9 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(h, name)          # AttributeError here = header / library out of sync
             fn.restype, fn.argtypes = res, args
+        if h.b200rec_version() != ABI_VERSION:      # a stale build of an older header: struct layouts / signatures would not match
+            raise ImportError(f'{LIB_PATH} reports ABI version {h.b200rec_version()}, these bindings need {ABI_VERSION}: rebuild it '
+                              f'(python -m deeprecommendation_b200.csrc.build --force)')
         _lib = h
     return _lib
 

@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, n), f'{n} declared in include/b200rec.h but not exported'
     assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
     lib = _lib.lib()
-    assert lib.b200rec_version() == 201
+    header_version = int(re.search(r'#define\s+B200REC_VERSION\s+(\d+)', open(os.path.join(ROOT, 'include', 'b200rec.h')).read()).group(1))
+    assert lib.b200rec_version() == header_version == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header_field_order():
