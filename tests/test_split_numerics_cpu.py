@@ -44,3 +44,15 @@ def test_tf32_hi_lo_split_is_an_order_of_magnitude_tighter():
     wh = _tf32(w); wl = _tf32(w - wh)
     err = _maxnorm_rel(_three_products(xh, xl, wh, wl), x.double() @ w.double().T)
     assert err < 5e-7, err
+
+
+def test_dropout_generator_is_the_published_philox2x32_10():
+    """The numpy restatement that the GPU test holds K2's inner-dropout mask to (tests/test_attention_dropout_gpu.py) against the known-answer
+    vectors of Random123's philox2x32_10 (kat_vectors): the mask generator is the published Philox, not a look-alike."""
+    import numpy as np
+    from tests.test_attention_dropout_gpu import philox2x32_10
+    for c0, c1, key, want in ((0x00000000, 0x00000000, 0x00000000, (0xff1dae59, 0x6cd10df2)),
+                              (0xffffffff, 0xffffffff, 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+                              (0x243f6a88, 0x85a308d3, 0x13198a2e, (0xdd7ce038, 0xf62a4c12))):
+        r0, r1 = philox2x32_10(np.array([c0], dtype=np.uint64), np.array([c1], dtype=np.uint64), key)
+        assert (int(r0[0]), int(r1[0])) == want
