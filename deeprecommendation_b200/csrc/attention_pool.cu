@@ -983,7 +983,7 @@ static int launch_att(const AttParams& p, const AttInputs& in, cudaStream_t st) 
                       (p.ldPr * sizeof(T)) % 16 == 0 && (p.ldQ * sizeof(T)) % 16 == 0 && (uintptr_t)p.Pr % 16 == 0 && (uintptr_t)p.Q % 16 == 0;
   if constexpr (HV == 1 && UV == 1) {
     if (tma_ok) {
-      const int warps = sizeof(T) == 4 ? 6 : 12;
+      const int warps = sizeof(T) == 4 ? 7 : 14;      // 7 x 32 KB (fp32) of rows in flight per SM: 224 KB of the 227
       const size_t smem = (size_t)warps * 64 * 128 * sizeof(T) + (size_t)warps * sizeof(uint64_t);
       static B200recSmemOptIn opted;       // per template instantiation, one bit per device
       B200REC_CUDA(b200rec_opt_in_smem(opted, attention_wseg_tma_kernel<MODE, T>, (int)smem));
