@@ -197,7 +197,7 @@ def op_breakdown(step_fn, steps, start_index):
 def build_attention(dev, rank, n_batches=None):
     n_batches = N_ROTATING if n_batches is None else n_batches
     from deeprecommendation_b200 import synth
-    from deeprecommendation_b200.content_providers import ArrayDynamicProvider, ResidentDynamicProvider, ResidentRows
+    from deeprecommendation_b200.content_providers import ArrayDynamicProvider, DeviceCollateProvider, ResidentRows
     from deeprecommendation_b200.neural_collaborative_filtering.models import AttentionNCF
     users_raw, items_raw, ratings = synth.interactions_small(610, 9724, 100_836, seed=42)
     _, u = synth.dense_ids(users_raw)
@@ -212,15 +212,16 @@ def build_attention(dev, rank, n_batches=None):
     model.load_state_dict(sd)
     rprov = None
     if dev.type == 'cuda':        # device-resident provider: same batches as row numbers + CSR
-        rprov = ResidentDynamicProvider(np.arange(n_items), profiles, np.arange(610), row_ptr, idx, rr, device=dev)
+        rprov = DeviceCollateProvider(np.arange(n_items), profiles, np.arange(610), row_ptr, idx, rr, device=dev)    # (a ResidentDynamicProvider + K6)
     rng = np.random.default_rng(1000 + rank)           # every rank scores its own shard of the pairs (data-parallel)
-    host, nnz, resident_form = [], [], []
+    host, nnz, resident_form, picks = [], [], [], []
     for _ in range(n_batches):
         pick = rng.permutation(len(u))[:BATCH]
         rated_idx, um = prov.collate_indices(u[pick])
         if rprov is not None:
             r_idx, um_csr = rprov.collate_csr(u[pick])
             resident_form.append((ResidentRows(rprov.table, it[pick]), ResidentRows(rprov.table, r_idx), um_csr))
+            picks.append((torch.from_numpy(u[pick].astype(np.int64)).pin_memory(), resident_form[-1][0]))
         cand = torch.from_numpy(profiles[it[pick]]).pin_memory()
         rated = torch.from_numpy(profiles[rated_idx]).pin_memory()
         host.append((cand, rated, torch.from_numpy(um).pin_memory()))
@@ -230,7 +231,7 @@ def build_attention(dev, rank, n_batches=None):
     su = int(np.argsort(counts)[len(counts) // 2])                       # the user with the median number of rated items
     serving = dict(profiles=profiles, positions=idx[row_ptr[su]:row_ptr[su + 1]].astype(np.int64), ratings=rr[row_ptr[su]:row_ptr[su + 1]].astype(np.float64),
                    table=(rprov.table if rprov is not None else None))
-    return dict(model=model, sd=sd, host=host, nnz=nnz, kw=kw, resident_form=resident_form, serving=serving)
+    return dict(model=model, sd=sd, host=host, nnz=nnz, kw=kw, resident_form=resident_form, serving=serving, picks=picks, device_provider=rprov)
 
 
 def run_attention(w, steps, warmup, dist, dev, peaks):
@@ -322,6 +323,41 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
         torch.cuda.synchronize()
         res_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
         e2e_res = {'ms': res_ms, 'h2d': int(np.sum([c.pos.numel() * 8 + r.pos.numel() * 8 + um.nbytes() for c, r, um in rf]))}
+
+    # the same (user, item) samples with the collate itself on the device (K6): per batch 2 x 512 row numbers go up,
+    # the size of the rated-item union (4 B) and the scores come back; sort / unique / multi-hot of the reference's collate are inside the timed region
+    e2e_ids = None
+    dprov, picks = w.get('device_provider'), w.get('picks') or []
+    if dprov is not None and picks:
+        from deeprecommendation_b200.content_providers import ResidentRows
+
+        def step_ids(i):
+            res = None
+            for users, cand in picks:
+                rated_rows, um = dprov.collate_device(users)
+                with torch.no_grad():
+                    res = model.forward_resident(cand, ResidentRows(dprov.table, rated_rows), um).cpu()
+            return res
+        try:
+            for i in range(min(warmup, 3)):
+                step_ids(i)
+            _barrier(dist)
+            t0 = time.perf_counter()
+            for i in range(steps):
+                step_ids(i)
+            torch.cuda.synchronize()
+            ids_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
+            rated0, um0 = dprov.collate_device(picks[0][0])
+            with torch.no_grad():
+                ids_out0 = model.forward_resident(picks[0][1], ResidentRows(dprov.table, rated0), um0).float().cpu()
+            t0 = time.perf_counter()
+            for users, _ in picks:
+                dprov.collate_csr(users.numpy())
+            host_collate_ms = (time.perf_counter() - t0) * 1e3 / len(picks)
+            e2e_ids = {'ms': ids_ms, 'h2d': int(sum(u_.numel() * 8 + c.pos.numel() * 8 for u_, c in picks)), 'd2h_extra': 4 * len(picks),
+                       'bit_equal_to_dense_contract': bool(torch.equal(ids_out0, out0)), 'host_collate_ms_per_batch': host_collate_ms}
+        except Exception as e:
+            e2e_ids = {'error': repr(e)[:300]}
 
     ops_ms = op_breakdown(step_eager, nb, 0)
 
@@ -472,7 +508,7 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     if len(roofs) > 1:
         roof['other_kernels'] = roofs[1:]
     return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=h2d, d2h=BATCH * 4 * nb, roofline=roof, I_mean=I_mean, out0=out0, nb=nb,
-                nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res, train=train, serving=serving,
+                nnz_mean=float(np.mean(w['nnz'])), e2e_res=e2e_res, e2e_ids=e2e_ids, train=train, serving=serving,
                 launch_mode='cuda_graph' if graphs is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
@@ -1690,6 +1726,16 @@ def main():
                                           'note': 'same batches through content_providers.ResidentDynamicProvider + AttentionNCF.forward_resident: '
                                                   'profile table resident in HBM, per step only row numbers + the CSR of user_matrix are copied '
                                                   '(pinned host -> device) and the scores read back; `e2e` above is the dense 6-tuple contract'}
+            if r.get('e2e_ids'):
+                t = r['e2e_ids']
+                result['e2e_device_collate'] = ({'value': pairs / (t['ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': t['h2d'],
+                                                 'd2h_bytes_per_step': r['d2h'] + t['d2h_extra'], 'ms_per_step': t['ms'] / args.steps,
+                                                 'bit_equal_to_dense_contract': t['bit_equal_to_dense_contract'],
+                                                 'host_collate_ms_per_batch': t['host_collate_ms_per_batch'],
+                                                 'note': 'from (user, item) samples: DeviceCollateProvider.collate_device (K6: rated-item union + CSR of user_matrix built '
+                                                         'on the device from the resident rating lists, dynamic_profiles_provider.py:30-73) + AttentionNCF.forward_resident; '
+                                                         'the collate is INSIDE the timed region (`e2e` and `e2e_resident` start from batches collated beforehand on the '
+                                                         'host: `host_collate_ms_per_batch` is what that numpy collate costs per batch)'} if 'ms' in t else t)
             if r.get('serving'):
                 result['serving'] = r['serving']
             if r.get('train'):

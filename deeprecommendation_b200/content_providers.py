@@ -99,8 +99,11 @@ class ResidentRows:
     """Rows of a profile table that lives in HBM: what the dense `(n, F)` tensor of the collate contract becomes when the
     provider is device-resident.  `pos` = int64 row numbers (host, pinned when CUDA is present)."""
 
-    def __init__(self, table: torch.Tensor, pos: np.ndarray):
+    def __init__(self, table: torch.Tensor, pos):
         self.table = table
+        if torch.is_tensor(pos):                 # already a tensor (K6's `rated` lives on the device)
+            self.pos = pos.long()
+            return
         t = torch.from_numpy(np.ascontiguousarray(pos, dtype=np.int64))
         self.pos = t.pin_memory() if torch.cuda.is_available() else t
 
@@ -311,6 +314,100 @@ class ResidentDynamicProvider(ArrayDynamicProvider):
             third = torch.FloatTensor(np.asarray(third, dtype=np.float64))
         rated_idx, um = self.collate_csr(u_idx, ignore_ratings)
         return np.array(cands), self.item_ids[rated_idx], candidate_items, ResidentRows(self.table, rated_idx), um, third
+
+
+class DeviceUserMatrix:
+    """CSR of the `(B, I)` user_matrix in DEVICE memory — what K6 (ops.collate_interacted_raw) leaves behind.  Same duck type as
+    `SparseUserMatrix` for `AttentionNCF.forward_resident` (`row_ptr`, `col`, `val`, `shape`, `max_row_nnz`)."""
+
+    def __init__(self, row_ptr, col, val, shape, max_row_nnz):
+        self.row_ptr, self.col, self.val = row_ptr, col, val
+        self.shape = tuple(shape)
+        self.max_row_nnz = int(max_row_nnz)
+
+    def to_dense(self) -> torch.Tensor:
+        """the reference's dense matrix, on the CSR's device (training path, tests)"""
+        um = torch.zeros(self.shape, dtype=torch.float32, device=self.val.device)
+        rows = torch.repeat_interleave(torch.arange(self.shape[0], device=self.val.device), (self.row_ptr[1:] - self.row_ptr[:-1]).long())
+        um[rows, self.col.long()] = self.val
+        return um
+
+    def nbytes(self) -> int:
+        return 0                                # nothing crosses PCIe
+
+
+class LazyHostIds:
+    """`rated_items_ids` of the 6-tuple (dynamic_profiles_provider.py:59,73) for a batch collated on the device: the ids are
+    downloaded when somebody looks at them (the training / evaluation loops do not; the attention-weight visualisation does)."""
+
+    def __init__(self, item_ids: np.ndarray, rated_rows: torch.Tensor):
+        self._item_ids, self._rows, self._host = item_ids, rated_rows, None
+
+    def _get(self):
+        if self._host is None:
+            self._host = self._item_ids[self._rows.cpu().numpy()]
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._get()
+        return a if dtype is None else a.astype(dtype)
+
+    def __len__(self):
+        return int(self._rows.numel())
+
+    def __getitem__(self, k):
+        return self._get()[k]
+
+
+class DeviceCollateProvider(ResidentDynamicProvider):
+    """`ResidentDynamicProvider` whose collate itself runs on the device (K6, csrc/collate.cu): besides the
+    profile table, every user's rating list lives in HBM (item numbers + the centred rating `rating - (meanRating + 2.5) / 2`, float64
+    arithmetic rounded once to fp32 like dynamic_profiles_provider.py:66).  Per batch the host touches O(B) numbers: the user rows go
+    up (8 B each), the size of the rated-item union comes back (4 B); sort/unique/multi-hot of the reference's collate are three
+    launches of integer work.  Results are bit-identical to `ResidentDynamicProvider.collate_csr` (tests/test_collate_gpu.py)."""
+
+    def __init__(self, item_ids, item_profiles, user_ids, row_ptr, rated_item_idx, rated_rating, device='cuda'):
+        super().__init__(item_ids, item_profiles, user_ids, row_ptr, rated_item_idx, rated_rating, device=device)
+        dev = self.table.device
+        self._list_len = np.diff(self.row_ptr)
+        centred = (self.rated_rating - np.repeat((self.mean_rating + 2.5) / 2, self._list_len)).astype(np.float32)
+        rows_of = np.repeat(np.arange(len(self._list_len)), self._list_len)
+        self._nz_cnt = np.bincount(rows_of[centred != 0.0], minlength=len(self._list_len)).astype(np.int64)
+        self.d_list_ptr = torch.from_numpy(self.row_ptr).to(dev)
+        self.d_list_item = torch.from_numpy(self.rated_item_idx.astype(np.int32)).to(dev)
+        self.d_list_val = torch.from_numpy(centred).to(dev)
+
+    def collate_device(self, user_idx, ignore_ratings=False):
+        """(rated item rows (I,) int64 DEVICE tensor, `DeviceUserMatrix`) for a batch of user INDICES: a host array, or an int64 host
+        tensor (pinned memory makes the upload asynchronous)."""
+        from . import ops
+        dev = self.table.device
+        if torch.is_tensor(user_idx):
+            rows = user_idx.to(dev, non_blocking=True)
+            user_idx = user_idx.numpy()
+        else:
+            user_idx = np.ascontiguousarray(user_idx, dtype=np.int64)
+            rows = torch.from_numpy(user_idx).to(dev)
+        B = len(user_idx)
+        lens = self._list_len[user_idx]
+        cnt = lens if ignore_ratings else self._nz_cnt[user_idx]
+        nnz, total = int(cnt.sum()), int(lens.sum())
+        rated, rp, col, val, counts = ops.collate_interacted_raw(rows, self.d_list_ptr, self.d_list_item, None if ignore_ratings else self.d_list_val,
+                                                                 self.get_num_items(), rated_capacity=min(self.get_num_items(), total),
+                                                                 nnz_capacity=nnz)
+        n_rated = int(counts[0].item())          # the one thing the host has to learn: I sizes the projection GEMM of the rated rows
+        return rated[:n_rated], DeviceUserMatrix(rp, col[:nnz], val[:nnz], (B, n_rated), int(cnt.max()) if B else 0)
+
+    def collate_interacted_items(self, batch, for_ranking: bool, ignore_ratings=False):
+        users, cands, third = zip(*batch)
+        u_idx = np.searchsorted(self.user_ids, np.asarray(users))
+        candidate_items = ResidentRows(self.table, np.searchsorted(self.item_ids, np.asarray(cands)))
+        if for_ranking:
+            third = ResidentRows(self.table, np.searchsorted(self.item_ids, np.asarray(third)))
+        else:
+            third = torch.FloatTensor(np.asarray(third, dtype=np.float64))
+        rated_rows, um = self.collate_device(u_idx, ignore_ratings)
+        return np.array(cands), LazyHostIds(self.item_ids, rated_rows), candidate_items, ResidentRows(self.table, rated_rows), um, third
 
 
 class ArrayGraphProvider(GraphContentProvider):

@@ -1070,6 +1070,34 @@ def topk_rows(scores, k):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# K6 device-side collate (dynamic_profiles_provider.py:30-73)
+# ------------------------------------------------------------------------------------------------------------------
+def collate_interacted_raw(user_rows, list_ptr, list_item, list_val, n_items, *, rated_capacity, nnz_capacity):
+    """(rated int64 (rated_capacity,), um_row_ptr int32 (B+1,), um_col int32, um_val fp32 (nnz_capacity,), counts int32 (2,) = [I, nnz])
+    — b200rec_collate_interacted.  `user_rows` int64 (B,) device; the rating lists (`list_ptr` int64, `list_item` int32, `list_val`
+    fp32 or None) are the provider's resident CSR.  Nothing is read back here: the caller decides when to learn I."""
+    _require_cuda(user_rows, list_ptr, list_item, list_val)
+    if user_rows.dtype != torch.int64 or list_ptr.dtype != torch.int64 or list_item.dtype != torch.int32:
+        raise ValueError('collate_interacted: user_rows / list_ptr must be int64, list_item int32')
+    if list_val is not None and list_val.dtype != torch.float32:
+        raise ValueError('collate_interacted: list_val must be float32')
+    user_rows = user_rows.contiguous()
+    dev = user_rows.device
+    B = int(user_rows.numel())
+    rated = torch.empty(max(int(rated_capacity), 1), dtype=torch.int64, device=dev)
+    rp = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(max(int(nnz_capacity), 1), dtype=torch.int32, device=dev)
+    val = torch.empty(max(int(nnz_capacity), 1), dtype=torch.float32, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    wsb = L.lib().b200rec_collate_workspace(B, int(n_items))
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev), _timed('collate', (B, int(n_items))):
+        L.check(L.lib().b200rec_collate_interacted(_ptr(user_rows), B, _ptr(list_ptr), _ptr(list_item), _ptr(list_val), int(n_items), _ptr(rated),
+                                                   _ptr(rp), _ptr(col), _ptr(val), _ptr(counts), _ptr(ws), wsb, _stream()), 'collate_interacted')
+    return rated, rp, col, val, counts
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # K5 all-pairs scoring + top-k (tcgen05)
 # ------------------------------------------------------------------------------------------------------------------
 _ap_cache = {}

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200REC_VERSION 201
+#define B200REC_VERSION 202
 
 typedef void* b200rec_stream_t; /* cudaStream_t */
 
@@ -407,6 +407,24 @@ int b200rec_pairhash_lookup(const int64_t* src, const int64_t* dst, int64_t n, c
 /* training-time target-edge mask (gnn_ncf.py:314-320,369-378): sets skip bits and decrements both endpoints' in-degree */
 int b200rec_mask_targets(const int64_t* positions, int64_t n, int64_t n_edges, const int64_t* u2i, const int64_t* i2u,
                          uint32_t* skip_bits, int* deg, b200rec_stream_t stream);
+
+/* ---- K6  device-side collate of the dynamic-profile batches (csrc/collate.cu) -----------------------------------------
+ * Replaces DynamicProfilesProvider.collate_interacted_items (src/content_providers/dynamic_profiles_provider.py:30-73; sklearn
+ * MultiLabelBinarizer + pandas `.loc` per batch on the host) for a provider whose rating lists are resident in HBM:
+ *   list_ptr  (n_users + 1) int64   CSR over ALL users of the provider
+ *   list_item int32                 item numbers (rows of the profile table), ascending inside a user (the reference relies on the same order, :64)
+ *   list_val  fp32 or NULL          rating - (meanRating + 2.5) / 2, computed in float64 and rounded once (:66); NULL = ignore_ratings (ones)
+ * For the B users `user_rows` of a batch (repeats allowed):
+ *   rated      (>= I) int64         ascending item numbers of the union of their lists  = rated_items_ids (:59)
+ *   um_row_ptr (B + 1), um_col, um_val   CSR of user_matrix (B, I): col = position of the item in `rated`, list order inside a row; entries
+ *                                   whose value is exactly 0.0 are absent (the dense matrix uses 0.0 for "unrated", attention_ncf.py:158-159)
+ *   counts     int32[2]             { I, nnz }  (device memory)
+ * Capacities are the caller's: `rated` holds min(n_items, total list length of the batch) entries, um_col / um_val the batch's non-zero
+ * count (host-known from per-user counts).  Integer work, bit-exact against the host collate. */
+size_t b200rec_collate_workspace(int64_t B, int64_t n_items);
+int b200rec_collate_interacted(const int64_t* user_rows, int64_t B, const int64_t* list_ptr, const int* list_item, const float* list_val,
+                               int64_t n_items, int64_t* rated, int* um_row_ptr, int* um_col, float* um_val, int* counts,
+                               void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
 
 /* ---- peer-memory exchange of the partitioned GraphNCF propagation (csrc/peer.cu) --------------------------------------
  * One process per GPU of an NVSwitch box.  Each rank allocates ONE arena, exports it as a CUDA IPC handle (64 opaque bytes,
