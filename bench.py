@@ -307,13 +307,15 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     rf = w.get('resident_form') or []
     e2e_res = None
     if rf:
-        def step_res(i):
-            res = None
+        pin_res = torch.empty((nb, BATCH, 1), dtype=torch.float32).pin_memory()
+
+        def step_res(i):                       # scores of every batch land in pinned memory, one synchronize per step
             for k in range(nb):
                 c, r, um = rf[k]
                 with torch.no_grad():
-                    res = model.forward_resident(c, r, um).cpu()
-            return res
+                    pin_res[k].copy_(model.forward_resident(c, r, um), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return pin_res[-1]
         for i in range(min(warmup, 3)):
             step_res(i)
         _barrier(dist)
@@ -331,13 +333,20 @@ def run_attention(w, steps, warmup, dist, dev, peaks):
     if dprov is not None and picks:
         from deeprecommendation_b200.content_providers import ResidentRows
 
+        pin_ids = torch.empty((len(picks), BATCH, 1), dtype=torch.float32).pin_memory()
+
         def step_ids(i):
-            res = None
-            for users, cand in picks:
-                rated_rows, um = dprov.collate_device(users)
+            # K6 of batch k + 1 is enqueued AHEAD of the forward of batch k: its counts are on the host by the time forward k has been launched,
+            # so learning I never drains the stream; scores land in pinned memory, one synchronize per step
+            pend = dprov.collate_launch(picks[0][0])
+            for k, (users, cand) in enumerate(picks):
+                rated_rows, um = dprov.collate_finish(pend)
+                if k + 1 < len(picks):
+                    pend = dprov.collate_launch(picks[k + 1][0])
                 with torch.no_grad():
-                    res = model.forward_resident(cand, ResidentRows(dprov.table, rated_rows), um).cpu()
-            return res
+                    pin_ids[k].copy_(model.forward_resident(cand, ResidentRows(dprov.table, rated_rows), um), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return pin_ids[-1]
         try:
             for i in range(min(warmup, 3)):
                 step_ids(i)
@@ -922,11 +931,17 @@ def build_basic(dev, rank, n_batches=32):
     model = BasicNCF(**kw).to(dev).eval()
     model.load_state_dict(sd)
     rng = np.random.default_rng(2000 + rank)
-    host = []
+    host, resident_form = [], []
+    rprov = None
+    if dev.type == 'cuda':        # both profile tables resident in HBM: the same batches as row numbers
+        from deeprecommendation_b200.content_providers import ResidentProfilesProvider
+        rprov = ResidentProfilesProvider(np.arange(len(item_ids)), profiles, np.arange(610), uprof, device=dev)
     for _ in range(n_batches):
         pick = rng.permutation(len(u))[:BATCH]
         host.append((torch.from_numpy(uprof[u[pick]]).pin_memory(), torch.from_numpy(profiles[it[pick]]).pin_memory()))
-    return dict(model=model, sd=sd, host=host)
+        if rprov is not None:
+            resident_form.append((rprov.get_user_profile(u[pick]), rprov.get_item_profile(it[pick])))
+    return dict(model=model, sd=sd, host=host, resident_form=resident_form)
 
 
 def run_basic(w, steps, warmup, dist, dev, peaks):
@@ -980,6 +995,43 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
         step_e2e(i)
     torch.cuda.synchronize()
     e2e_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
+    # the same batches as row numbers into profile tables resident in HBM (ResidentProfilesProvider): per batch 2 x 512 x 8 B go up.
+    # `e2e_resident`: rows gathered on the device, then the same kernels as the dense contract (identical bits);
+    # `e2e_resident_cached`: every table row projected once per weight version, a batch = the MLP tower over gathered embedding rows
+    res_legs = {}
+    rf = w.get('resident_form') or []
+    if rf:
+        for name, cached in (('e2e_resident', False), ('e2e_resident_cached', True)):
+            try:
+                model.cache_eval_embeddings = cached
+
+                pin_res = torch.empty((len(rf), BATCH, 1), dtype=torch.float32).pin_memory()
+
+                def step_res(i):               # scores of every batch land in pinned memory, one synchronize per step
+                    for k, (xu, xi) in enumerate(rf):
+                        with torch.no_grad():
+                            pin_res[k].copy_(model(xu, xi), non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                    return pin_res[-1]
+                for i in range(min(warmup, 3)):
+                    step_res(i)
+                _barrier(dist)
+                t0 = time.perf_counter()
+                for i in range(steps):
+                    step_res(i)
+                torch.cuda.synchronize()
+                res_ms = _max_over_ranks(dist, (time.perf_counter() - t0) * 1e3, dev)
+                with torch.no_grad():
+                    o = model(*rf[0]).float().cpu()
+                res_legs[name] = {'ms': res_ms, 'h2d': int(sum(a.pos.numel() * 8 + b.pos.numel() * 8 for a, b in rf)),
+                                  'max_rel_vs_dense_contract': float((o - out0).abs().max() / out0.abs().max().clamp_min(1e-30)),
+                                  'bit_equal_to_dense_contract': bool(torch.equal(o, out0))}
+            except Exception as e:
+                res_legs[name] = {'error': repr(e)[:300]}
+            finally:
+                model.cache_eval_embeddings = False
+                model.invalidate_caches()
+
     # configs[0] names a TRAIN step: forward (dropout 0.2 active) + sum-MSE backward + Adam, gradients of every GEMM on K1a
     train_ms, train_mode = None, 'eager'
     try:
@@ -1037,7 +1089,7 @@ def run_basic(w, steps, warmup, dist, dev, peaks):
             'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(achieved / peaks['hbm_gbs'], 4), 'traffic': _traffic('basic'),
             'peak_source': peaks['src'], 'kernel_ms': round(kms, 4), 'algorithmic_bytes': int(alg_bytes),
             'op_ms_per_step': {f'{n}{list(m)}': round(v[0] * v[1], 4) for (n, m), v in sorted(ops_ms.items(), key=lambda kv: -kv[1][0] * kv[1][1])}}
-    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * F * 4 * nb, d2h=BATCH * 4 * nb, roofline=roof, train_ms=train_ms, train_mode=train_mode, out0=out0, nb=nb,
+    return dict(ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=2 * BATCH * F * 4 * nb, d2h=BATCH * 4 * nb, roofline=roof, train_ms=train_ms, train_mode=train_mode, out0=out0, nb=nb, res_legs=res_legs,
                 launch_mode='cuda_graph' if graphed is not None else 'eager: ' + w.get('graph_capture_error', 'requested'))
 
 
@@ -1776,6 +1828,15 @@ def main():
                      'roofline': r['roofline'],
                      'e2e': {'value': pairs / (r['e2e_ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h']},
                      'gpu_launches': r['launches']}
+            for name, t in (r.get('res_legs') or {}).items():
+                entry[name] = ({'value': pairs / (t['ms'] * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': t['h2d'], 'd2h_bytes_per_step': r['d2h'],
+                                'ms_per_step': t['ms'] / args.steps, 'max_rel_vs_dense_contract': t['max_rel_vs_dense_contract'],
+                                'bit_equal_to_dense_contract': t['bit_equal_to_dense_contract'],
+                                'note': ('content_providers.ResidentProfilesProvider + BasicNCF.forward_resident: both profile tables resident in HBM, a batch is '
+                                         '2 x 512 row numbers; ' + ('every table row projected ONCE per weight version (cache_eval_embeddings, inference only), a batch '
+                                                                    'is one MLP-tower launch over gathered embedding rows — not the per-batch projection `value` times'
+                                                                    if name.endswith('cached') else 'rows gathered on the device, then the kernels of the dense contract'))}
+                               if 'ms' in t else t)
             if r.get('train_ms'):
                 entry['train_step'] = {'value': BATCH * args.steps * world / (r['train_ms'] * 1e-3), 'unit': 'pairs/s', 'ms_per_step': r['train_ms'] / args.steps,
                                        'launch_mode': r.get('train_mode'),

@@ -7,9 +7,10 @@ from .base import PointwiseDataset, RankingDataset
 
 
 def _tensor(p):
-    """dense rows become the reference's FloatTensor; sparse row containers (content_providers.OneHotRows / MixedRows) pass through — they
+    """dense rows become the reference's FloatTensor; sparse row containers (content_providers.OneHotRows / MixedRows) and rows of a
+    device-resident table (content_providers.ResidentRows) pass through — they
     answer `.float()` / `.to(device)` like a tensor and the models project them with the gather-sum kernel"""
-    return p if getattr(p, 'kind', None) in ('onehot', 'mixed') else torch.FloatTensor(p)
+    return p if (getattr(p, 'kind', None) in ('onehot', 'mixed') or hasattr(p, 'table')) else torch.FloatTensor(p)
 
 
 def _profiles(cp, users, *item_lists):

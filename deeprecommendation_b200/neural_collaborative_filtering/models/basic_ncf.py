@@ -23,7 +23,33 @@ class BasicNCF(NCF):
         self.user_embeddings = nn.Sequential(nn.Linear(user_dim, user_emb))
         self.MLP = build_MLP_layers(item_emb + user_emb, mlp_dense_layers, dropout_rate=dropout_rate)
 
+    cache_eval_embeddings = False        # forward_resident: project every row of the resident tables once per weight version (inference)
+
+    def forward_resident(self, X_user, X_item):
+        """`forward` fed by `content_providers.ResidentProfilesProvider`: both arguments are `ResidentRows` (row numbers into profile tables
+        that live in HBM).  Default: the rows are gathered on the device and take the same kernels as the dense contract (identical bits).
+        With `cache_eval_embeddings` (inference only) every row of both tables is projected ONCE per weight version and a batch is one
+        launch of the MLP tower over gathered embedding rows — the per-unique-row form SURVEY.md §8d names for config 4, and what the
+        reference's serving loop would want (src/webapp/backend.py:96-99 re-projects every candidate on every request)."""
+        dev = X_user.table.device
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            return self.forward(X_user.dense(), X_item.dense())
+        pu, pi = X_user.pos.to(dev, non_blocking=True), X_item.pos.to(dev, non_blocking=True)
+        if not self.cache_eval_embeddings:
+            return self.forward(X_user.table.index_select(0, pu), X_item.table.index_select(0, pi))
+        ue, ie = self.user_embeddings[0], self.item_embeddings[0]
+        key = (X_user.table.data_ptr(), X_user.table._version, X_item.table.data_ptr(), X_item.table._version,
+               tuple((p.data_ptr(), p._version) for p in (ue.weight, ue.bias, ie.weight, ie.bias)))
+        cached = getattr(self, '_emb_cache', None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                cached = (key, ops.linear_raw(X_user.table, ue.weight, ue.bias), ops.linear_raw(X_item.table, ie.weight, ie.bias))
+            self._emb_cache = cached
+        return run_mlp(self.MLP, cached[1], cached[2], idx0=pu, idx1=pi, training=False)
+
     def forward(self, X_user, X_item):
+        if hasattr(X_user, 'table') and hasattr(X_item, 'table'):
+            return self.forward_resident(X_user, X_item)
         ue, ie = self.user_embeddings[0], self.item_embeddings[0]
         if not (torch.is_tensor(X_user) and torch.is_tensor(X_item)):
             # one-hot / multi-hot rows (content_providers.OneHotRows / MixedRows): gather-sum projection K1s, dense columns on K1a

@@ -125,3 +125,17 @@ def test_attention_scores_from_device_collate_equal_host_collate():
     out = DynamicPointwiseDataset.do_forward(m, dev.collate_interacted_items(batch[:32], False), DEV)[0]
     out.sum().backward()
     assert m.ItemEmbeddings[0].weight.grad is not None and torch.isfinite(m.ItemEmbeddings[0].weight.grad).all()
+
+
+def test_collate_launch_finish_pipelined():
+    """several collates in flight (the loader enqueues batch k + 1 ahead of the forward of batch k): every handle resolves to its own batch"""
+    p = _providers(300, 5000, 80, seed=11)
+    rng = np.random.default_rng(2)
+    batches = [torch.from_numpy(rng.integers(0, 300, 128)).pin_memory() for _ in range(6)]
+    pending = [p.collate_launch(b) for b in batches]
+    for b, h in zip(batches, pending):
+        rated_d, um_d = p.collate_finish(h)
+        rated_h, um_h = p.collate_csr(b.numpy())
+        assert np.array_equal(rated_d.cpu().numpy(), rated_h)
+        assert np.array_equal(um_d.row_ptr.cpu().numpy(), um_h.row_ptr.numpy()) and np.array_equal(um_d.col.cpu().numpy(), um_h.col.numpy())
+        assert np.array_equal(um_d.val.cpu().numpy().view(np.int32), um_h.val.numpy().view(np.int32))

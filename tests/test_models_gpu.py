@@ -66,6 +66,57 @@ def test_basic_cfg1_batches_vs_oracle():
         assert maxnorm_rel(out, ref) < TOL
 
 
+def test_basic_resident_profiles_through_the_dataset_contract():
+    """ResidentProfilesProvider (both profile tables in HBM, batches = row numbers) through FixedPointwiseDataset / FixedRankingDataset:
+    identical bits to the dense contract; with cached per-row embeddings within 1e-5 of the oracle; training falls back to dense rows."""
+    import pandas as pd
+    from deeprecommendation_b200.content_providers import ArrayProfilesProvider, ResidentProfilesProvider
+    from deeprecommendation_b200.neural_collaborative_filtering.datasets.fixed_datasets import FixedPointwiseDataset, FixedRankingDataset
+    kw = dict(item_dim=2094, user_dim=2094, item_emb=128, user_emb=128, mlp_dense_layers=[256, 128], dropout_rate=0.2)
+    sd = synth.to_torch(synth.basic_ncf_weights(seed=3, **kw))
+    m = _models().BasicNCF(**kw).to(DEV).eval()
+    m.load_state_dict(sd)
+    nI, nU, B = 700, 90, 300
+    items = synth.item_profiles(nI, seed=11)
+    users = ((synth.item_profiles(nU, seed=12) - 0.3) * 0.1).astype(np.float32)
+    item_ids, user_ids = np.arange(nI) * 3 + 5, np.arange(nU) * 7 + 1
+    rng = np.random.default_rng(0)
+    pu, pi, pj = rng.integers(0, nU, B), rng.integers(0, nI, B), rng.integers(0, nI, B)
+    frame = pd.DataFrame({'userId': user_ids[pu], 'movieId': item_ids[pi], 'rating': rng.integers(1, 11, B) * 0.5})
+    dense_p, res_p = ArrayProfilesProvider(item_ids, items, user_ids, users), ResidentProfilesProvider(item_ids, items, user_ids, users, device=DEV)
+    outs = {}
+    for name, prov in (('dense', dense_p), ('resident', res_p)):
+        ds = FixedPointwiseDataset(frame, prov)
+        batch = next(iter(torch.utils.data.DataLoader(ds, batch_size=B, collate_fn=ds.use_collate())))
+        with torch.no_grad():
+            outs[name], y = FixedPointwiseDataset.do_forward(m, batch, DEV)
+        assert y.shape == (B,)
+    assert torch.equal(outs['dense'], outs['resident'])
+    ref = R.basic_ncf_forward(sd, torch.from_numpy(users[pu]), torch.from_numpy(items[pi]))
+    assert maxnorm_rel(outs['resident'], ref) < TOL
+    m.cache_eval_embeddings = True
+    ds = FixedPointwiseDataset(frame, res_p)
+    batch = next(iter(torch.utils.data.DataLoader(ds, batch_size=B, collate_fn=ds.use_collate())))
+    with torch.no_grad():
+        cached, _ = FixedPointwiseDataset.do_forward(m, batch, DEV)
+        assert maxnorm_rel(cached, ref) < TOL
+        assert m._emb_cache is not None and m._emb_cache[1].shape == (nU, 128) and m._emb_cache[2].shape == (nI, 128)
+        first = m._emb_cache[1]
+        FixedPointwiseDataset.do_forward(m, batch, DEV)
+        assert m._emb_cache[1] is first                                # reused while the weights are unchanged
+        m.load_state_dict(sd)
+        assert m._emb_cache is None                                    # dropped with the weights
+        # ranking form: (user, positive, negative) rows, two scores per sample
+        trip = (res_p.get_user_profile(user_ids[pu]), res_p.get_item_profile(item_ids[pi]), res_p.get_item_profile(item_ids[pj]))
+        pos, neg = FixedRankingDataset.do_forward(m, trip, DEV)
+        assert maxnorm_rel(pos, ref) < TOL
+        assert maxnorm_rel(neg, R.basic_ncf_forward(sd, torch.from_numpy(users[pu]), torch.from_numpy(items[pj]))) < TOL
+    m.train()
+    out = FixedPointwiseDataset.do_forward(m, batch, DEV)[0]
+    out.sum().backward()
+    assert torch.isfinite(m.user_embeddings[0].weight.grad).all()
+
+
 # ---- AttentionNCF ----------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('name', ['attention_small_net', 'attention_small_lin', 'attention_small_cos'])
 def test_attention_small_vs_reference(name):
