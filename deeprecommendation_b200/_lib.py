@@ -126,6 +126,7 @@ SIGNATURES = {
     'b200rec_mask_targets': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200rec_collate_workspace': (c_sz, [c_i64, c_i64]),
     'b200rec_collate_interacted': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    'b200rec_sample_negatives': (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, C.c_double, C.c_uint64, C.c_uint64, c_vp, c_vp, c_vp, c_vp]),
     'b200rec_peer_alloc': (c_int, [c_sz, C.POINTER(c_vp), C.c_char_p]),
     'b200rec_peer_open': (c_int, [C.c_char_p, C.POINTER(c_vp)]),
     'b200rec_peer_close': (c_int, [c_vp]),

@@ -91,3 +91,42 @@ class RankingDataset(_Hooks, Dataset):
 
     def calculate_loss(self, out_pos, out_neg):
         return self.loss_fn(out_pos, out_neg)
+
+    def device_sampler(self, device='cuda', seed=0):
+        """The negative lists of every sample resident in HBM + one kernel launch per batch (`DeviceNegativeSampler`) instead of one
+        np.random.choice per sample."""
+        return DeviceNegativeSampler(self, device, seed)
+
+
+class DeviceNegativeSampler:
+    """Batched form of `RankingDataset.__getitem__` (datasets/base.py:57-78) on the device (K7, csrc/neg_sample.cu).  The frame's
+    `negative_movieIds` / `negative_ratings` lists become one CSR in HBM (ids must be integers); `sample(rows)` returns the
+    (userId, positive_movieId, negative_movieId) columns of those samples with one negative drawn per sample with probability
+    ∝ rating^w (`dataset.w`, read at every call — the training loop anneals it).  Draws are a Philox stream keyed by `seed`; the position
+    in the stream advances by the batch size, so an epoch never reuses a uniform."""
+
+    def __init__(self, dataset: 'RankingDataset', device='cuda', seed=0):
+        from ... import ops                       # (fails loudly without the CUDA library)
+        self._ops, self.dataset, self.seed, self.offset = ops, dataset, int(seed), 0
+        frame = dataset.samples
+        lens = np.fromiter((len(x) for x in frame['negative_movieIds']), dtype=np.int64, count=len(frame))
+        ptr = np.zeros(len(frame) + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        cat = lambda col, dt: (np.concatenate([np.asarray(x, dtype=dt) for x in frame[col]]) if len(frame) and ptr[-1] else np.zeros(0, dt))
+        self.neg_ptr = torch.from_numpy(ptr).to(device)
+        self.neg_item = torch.from_numpy(cat('negative_movieIds', np.int64)).to(device)
+        self.neg_rating = torch.from_numpy(cat('negative_ratings', np.float32)).to(device)
+        self._users = frame['userId'].to_numpy()
+        self._pos = frame['positive_movieId'].to_numpy()
+
+    def sample(self, rows, return_uniforms=False):
+        """rows: sample numbers of the batch (host array).  -> (userIds ndarray, positive ids ndarray, negative ids int64 DEVICE tensor[, list
+        positions, uniforms])"""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        dev_rows = torch.from_numpy(rows).to(self.neg_ptr.device)
+        res = self._ops.sample_negatives_raw(dev_rows, self.neg_ptr, self.neg_item, self.neg_rating, w=float(self.dataset.w), seed=self.seed,
+                                             offset=self.offset, return_uniforms=return_uniforms)
+        self.offset += len(rows)
+        if return_uniforms:
+            return self._users[rows], self._pos[rows], res[0], res[1], res[2]
+        return self._users[rows], self._pos[rows], res[0]

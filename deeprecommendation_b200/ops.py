@@ -1098,6 +1098,28 @@ def collate_interacted_raw(user_rows, list_ptr, list_item, list_val, n_items, *,
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# K7 negative sampling (datasets/base.py:57-78)
+# ------------------------------------------------------------------------------------------------------------------
+def sample_negatives_raw(sample_rows, neg_ptr, neg_item, neg_rating, *, w, seed, offset, return_uniforms=False):
+    """(negative item ids int64 (B,), position inside the list int32 (B,)[, uniforms float64 (B,)]) — b200rec_sample_negatives."""
+    _require_cuda(sample_rows, neg_ptr, neg_item, neg_rating)
+    if sample_rows.dtype != torch.int64 or neg_ptr.dtype != torch.int64 or neg_item.dtype != torch.int64:
+        raise ValueError('sample_negatives: sample_rows / neg_ptr / neg_item must be int64')
+    if neg_rating is not None and neg_rating.dtype != torch.float32:
+        raise ValueError('sample_negatives: neg_rating must be float32')
+    sample_rows = sample_rows.contiguous()
+    dev, B = sample_rows.device, int(sample_rows.numel())
+    out = torch.empty(B, dtype=torch.int64, device=dev)
+    pos = torch.empty(B, dtype=torch.int32, device=dev)
+    u = torch.empty(B, dtype=torch.float64, device=dev) if return_uniforms else None
+    with torch.cuda.device(dev), _timed('sample_negatives', (B,)):
+        L.check(L.lib().b200rec_sample_negatives(_ptr(sample_rows), B, _ptr(neg_ptr), _ptr(neg_item), _ptr(neg_rating), float(w),
+                                                 int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), _ptr(out), _ptr(pos), _ptr(u), _stream()),
+                'sample_negatives')
+    return (out, pos, u) if return_uniforms else (out, pos)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # K5 all-pairs scoring + top-k (tcgen05)
 # ------------------------------------------------------------------------------------------------------------------
 _ap_cache = {}

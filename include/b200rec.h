@@ -426,6 +426,17 @@ int b200rec_collate_interacted(const int64_t* user_rows, int64_t B, const int64_
                                int64_t n_items, int64_t* rated, int* um_row_ptr, int* um_col, float* um_val, int* counts,
                                void* workspace, size_t workspace_bytes, b200rec_stream_t stream);
 
+/* ---- K7  negative sampling of the ranking datasets (csrc/neg_sample.cu) -----------------------------------------------
+ * Replaces RankingDataset.__getitem__'s per-sample np.random.choice (src/neural_collaborative_filtering/datasets/base.py:57-78,
+ * 'sum_dynamic': p_k = r_k^w / sum_j r_j^w, w = 0 -> uniform) for datasets whose negative lists are resident in HBM as CSR over
+ * samples (neg_ptr int64 (n_samples + 1), neg_item int64, neg_rating fp32 or NULL = uniform).  For every row b of the batch:
+ * u_b = 53-bit uniform from Philox2x32-10 (counter = offset + b, key = seed), out_item[b] = the first list element whose cumulative
+ * weight exceeds u_b * total (np.random.choice's inverse-CDF rule, float64); -1 for an empty list.  out_pos (position inside the
+ * list) and out_u (the uniforms, for parity tests) are optional.  The caller advances `offset` by B per batch. */
+int b200rec_sample_negatives(const int64_t* sample_rows, int64_t B, const int64_t* neg_ptr, const int64_t* neg_item, const float* neg_rating,
+                             double w, uint64_t seed, uint64_t offset, int64_t* out_item, int* out_pos, double* out_u,
+                             b200rec_stream_t stream);
+
 /* ---- peer-memory exchange of the partitioned GraphNCF propagation (csrc/peer.cu) --------------------------------------
  * One process per GPU of an NVSwitch box.  Each rank allocates ONE arena, exports it as a CUDA IPC handle (64 opaque bytes,
  * exchanged by the host code), and maps the arenas of its peers.  The data path then consists of this library's kernels
