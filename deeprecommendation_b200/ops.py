@@ -76,8 +76,39 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_raw_device = getattr(torch._C, '_cuda_getDevice', None)
+
+
 def _stream():
+    """the current stream of the current device as a `cudaStream_t` (the raw getters are ~20x cheaper than building a torch Stream object:
+    an eager forward makes a dozen of these calls — tools/host_profile.py)"""
+    if _raw_stream is not None and _raw_device is not None:
+        return C.c_void_p(_raw_stream(_raw_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _on:
+    """`torch.cuda.device(dev)` that costs nothing when `dev` already is the current device (one process per GPU: always)."""
+    __slots__ = ('idx', 'prev')
+
+    def __init__(self, dev):
+        self.idx = dev.index if isinstance(dev, torch.device) else torch.device(dev).index
+        self.prev = -1
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = _raw_device() if _raw_device is not None else torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+            self.prev = -1
+        return False
 
 
 def _row_major(t: torch.Tensor):
@@ -131,7 +162,7 @@ def _packed_weight(w, ldw, mode):
     N, K = w.shape
     nbytes = lib.b200rec_packed_weight_bytes(N, K, mode)
     buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    with torch.cuda.device(w.device):
+    with _on(w.device):
         L.check(lib.b200rec_pack_weights_tc(_ptr(w), N, K, ldw, mode, _ptr(buf), nbytes, _stream()), 'pack_weights_tc')
     if len(_pack_cache) > 64:
         _pack_cache.clear()
@@ -196,7 +227,7 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
             and ldx % 4 == 0 and x.data_ptr() % 16 == 0 and out.dtype in (torch.float32, torch.bfloat16)):
         # per-node d x d transforms (GraphNCF): persistent streaming kernel, W resident in shared memory
         packed = _packed_weight(w, ldw, L.TC_TF32X3)
-        with torch.cuda.device(x.device), _timed('linear_shortk', (M, K, N)):
+        with _on(x.device), _timed('linear_shortk', (M, K, N)):
             L.check(lib.b200rec_linear_shortk(_ptr(x), M, K, ldx, _ptr(packed), N, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                               _dtype_code(out.dtype), _stream()), 'linear_shortk')
         return out
@@ -211,12 +242,12 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
             packed = _packed_weight(w, ldw, mode)
             wsb = lib.b200rec_linear_tc_wide_workspace(M, N, K, mode)
             ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
-            with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
+            with _on(x.device), _timed('linear_tc', (M, K, N)):
                 L.check(lib.b200rec_linear_tc_wide(_ptr(x), M, K, ldx, N, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy, _dtype_code(out.dtype),
                                                    mode, _ptr(packed), _ptr(row_index), x_rows, _ptr(ws), wsb, _stream()), 'linear_tc_wide')
             return out
         packed = _packed_weight(w, ldw, mode) if _pack_weights else None
-        with torch.cuda.device(x.device), _timed('linear_tc', (M, K, N)):
+        with _on(x.device), _timed('linear_tc', (M, K, N)):
             L.check(lib.b200rec_linear_tc(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                           _dtype_code(out.dtype), mode, _ptr(packed), _ptr(row_index), x_rows, _stream()), 'linear_tc')
         return out
@@ -228,13 +259,13 @@ def linear_raw(x, weight, bias=None, row_scale=None, relu=False, out=None, out_d
         if ws_bytes:
             packed = _packed_weight(w, ldw, mode) if _pack_weights else None
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-            with torch.cuda.device(x.device), _timed('linear_tc_splitk', (M, K, N)):
+            with _on(x.device), _timed('linear_tc_splitk', (M, K, N)):
                 L.check(lib.b200rec_linear_tc_splitk(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                                      _dtype_code(out.dtype), mode, _ptr(packed), _ptr(ws), ws_bytes, _stream()), 'linear_tc_splitk')
             return out
     ws_bytes = lib.b200rec_linear_workspace(M, N, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-    with torch.cuda.device(x.device), _timed('linear', (M, K, N)):
+    with _on(x.device), _timed('linear', (M, K, N)):
         L.check(lib.b200rec_linear(_ptr(x), M, K, ldx, _ptr(w), N, ldw, _ptr(bias), _ptr(row_scale), int(relu), _ptr(out), ldy,
                                    _dtype_code(out.dtype), _ptr(ws), ws_bytes, _stream()), 'linear')
     return out
@@ -281,7 +312,7 @@ def linear_tc_batch(problems, engine=None):
         keep += [x, w, bias, packed, out]
         outs.append(out)
         meta.append((M, N))
-    with torch.cuda.device(dev), _timed('linear_tc_batch', (sum(m for m, _ in meta), K, max(n for _, n in meta))):
+    with _on(dev), _timed('linear_tc_batch', (sum(m for m, _ in meta), K, max(n for _, n in meta))):
         L.check(L.lib().b200rec_linear_tc_batch(arr, len(problems), K, mode, _stream()), 'linear_tc_batch')
     return outs
 
@@ -324,7 +355,7 @@ def linear_pair(xa, wa, ba, xb, wb, bb):
     lib = L.lib()
     ws_bytes = lib.b200rec_linear_tc_splitk_batch_workspace(arr, 2, K, mode)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=outs[0].device)
-    with torch.cuda.device(outs[0].device), _timed('linear_tc_splitk_batch', (Ma + Mb, K, max(wa.shape[0], wb.shape[0]))):
+    with _on(outs[0].device), _timed('linear_tc_splitk_batch', (Ma + Mb, K, max(wa.shape[0], wb.shape[0]))):
         L.check(lib.b200rec_linear_tc_splitk_batch(arr, 2, K, mode, _ptr(ws), ws_bytes, _stream()), 'linear_tc_splitk_batch')
     return outs[0], outs[1]
 
@@ -379,7 +410,7 @@ def linear_sparse_raw(weight, bias, *, csr=None, ids=None, cols=None, out=None, 
         bias = bias.detach().contiguous().float()
     ldy = out.stride(0) if M > 1 else max(N, out.stride(0))
     nnz = int(col.numel()) if col is not None else M
-    with torch.cuda.device(weight.device), _timed('linear_sparse', (M, nnz, c1 - c0, N)):
+    with _on(weight.device), _timed('linear_sparse', (M, nnz, c1 - c0, N)):
         L.check(L.lib().b200rec_linear_sparse(_ptr(rp), _ptr(col), _ptr(val), _ptr(ids), M, _ptr(wt), c1 - c0, N, N, _dtype_code(table_dtype),
                                               None if accumulate else _ptr(bias), _ptr(out), ldy, int(accumulate), _stream()), 'linear_sparse')
     return out
@@ -394,7 +425,7 @@ def dense_to_csr(x, c0, c1):
     cnt = torch.empty(M, dtype=torch.int32, device=x.device)
     rp = torch.empty(M + 1, dtype=torch.int32, device=x.device)
     ws = torch.empty(max(int(lib.b200rec_scan_workspace(M)), 16), dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         L.check(lib.b200rec_dense_nnz_count(_ptr(x), M, ldx, c0, c1, _ptr(cnt), _stream()), 'dense_nnz_count')
         L.check(lib.b200rec_exclusive_scan_i32(_ptr(cnt), M, _ptr(rp), _ptr(ws), ws.numel(), _stream()), 'scan')
         nnz = int(rp[-1].item())
@@ -535,7 +566,7 @@ def mlp_tower_raw(in0, in1, weights, biases, idx0=None, idx1=None):
     out = torch.empty((B, prev), dtype=torch.float32, device=in0.device)
     if B == 0:
         return out
-    with torch.cuda.device(in0.device), _timed('mlp_tower', (B, E0 + E1)):
+    with _on(in0.device), _timed('mlp_tower', (B, E0 + E1)):
         L.check(L.lib().b200rec_mlp_tower(_ptr(in0), ld0, _ptr(idx0), E0, _ptr(in1), ld1, _ptr(idx1), E1, B, C.byref(d), _ptr(out),
                                          prev, _stream()), 'mlp_tower')
     return out
@@ -601,7 +632,7 @@ def rowdot(in0, in1, idx0=None, idx1=None):
     if idx1 is not None:
         idx1 = idx1.contiguous().long()
     out = torch.empty((B, 1), dtype=torch.float32, device=in0.device)
-    with torch.cuda.device(in0.device):
+    with _on(in0.device):
         L.check(L.lib().b200rec_rowdot(_ptr(in0), ld0, _ptr(idx0), _ptr(in1), ld1, _ptr(idx1), in0.shape[1], B, _ptr(out), _stream()),
                 'rowdot')
     return out
@@ -637,7 +668,7 @@ def attention_prepare(user_matrix, U):
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=um.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), wsb
     if B > 0 and I > 0:
-        with torch.cuda.device(um.device), _timed('attention_prepare', (B, I)):
+        with _on(um.device), _timed('attention_prepare', (B, I)):
             L.check(L.lib().b200rec_attention_pool_prepare(C.byref(d), _stream()), 'attention_pool_prepare')
     return AttentionPrepared(ws, um, (B, I), U)
 
@@ -736,7 +767,7 @@ def attention_pool_raw(Pc, Pr, Q, *, mode=L.ATT_NET, a2=None, a20=None, bU=None,
         d.dropout_p = float(inner_dropout[0])
         _set_dropout_seed(d, inner_dropout[1], Pc.device)
         entry = L.lib().b200rec_attention_pool_dropout
-    with torch.cuda.device(Pc.device), _timed('attention_pool', (B, I, H, U)):
+    with _on(Pc.device), _timed('attention_pool', (B, I, H, U)):
         L.check(entry(C.byref(d), _stream()), 'attention_pool')
     return (out, att) if return_attention_weights else out
 
@@ -791,7 +822,7 @@ def spmm_raw(index, t, *, w, dinv=None, x_next=None, acc_in=None, acc_out=None, 
         if index.n_multi > 0:
             ml = torch.empty((index.n_slots, 2), dtype=torch.float32, device=t.device)
             d.partials_ml = ml.data_ptr()
-    with torch.cuda.device(t.device), _timed('spmm', (index.e1 + index.e2, t.shape[1])):
+    with _on(t.device), _timed('spmm', (index.e1 + index.e2, t.shape[1])):
         L.check(L.lib().b200rec_spmm(C.byref(d), _stream()), 'spmm')
 
 
@@ -841,7 +872,7 @@ def spmm_stream_raw(plan, t, *, x_next=None, acc_in=None, acc_out=None, acc_scal
         for q in range(parts):
             d.push_dst[q] = dst[q]
         d.push_parts, d.push_rows_per_part, d.push_offset, d.push_ld = parts, rpp, off, ld
-    with torch.cuda.device(t.device), _timed('spmm', (plan.nnz, t.shape[1])):
+    with _on(t.device), _timed('spmm', (plan.nnz, t.shape[1])):
         L.check(L.lib().b200rec_spmm_stream(C.byref(d), _stream()), 'spmm_stream')
 
 
@@ -1007,7 +1038,7 @@ def attention_pool_backward_raw(Pc, Pr, Q, a2, bU, um, att, out, grad_out, mode,
     if inner_dropout is not None and inner_dropout[0] > 0.0:
         d.dropout_p = float(inner_dropout[0])
         _set_dropout_seed(d, inner_dropout[1], dev)
-    with torch.cuda.device(dev), _timed('attention_pool_backward', (B, I, H, U)):
+    with _on(dev), _timed('attention_pool_backward', (B, I, H, U)):
         L.check(L.lib().b200rec_attention_pool_backward(C.byref(d), _stream()), 'attention_pool_backward')
     if S > 1:
         dPc = dPc.view(S, B, H).sum(0)
@@ -1064,7 +1095,7 @@ def topk_rows(scores, k):
     R, Cc = s2.shape
     val = torch.empty((R, k), dtype=torch.float32, device=s2.device)
     idx = torch.empty((R, k), dtype=torch.int64, device=s2.device)
-    with torch.cuda.device(s2.device), _timed('topk', (R, Cc, k)):
+    with _on(s2.device), _timed('topk', (R, Cc, k)):
         L.check(L.lib().b200rec_topk_rows(_ptr(s2), R, Cc, ld, k, _ptr(val), _ptr(idx), _stream()), 'topk_rows')
     return (val[0], idx[0]) if squeeze else (val, idx)
 
@@ -1091,7 +1122,7 @@ def collate_interacted_raw(user_rows, list_ptr, list_item, list_val, n_items, *,
     counts = torch.empty(2, dtype=torch.int32, device=dev)
     wsb = L.lib().b200rec_collate_workspace(B, int(n_items))
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev), _timed('collate', (B, int(n_items))):
+    with _on(dev), _timed('collate', (B, int(n_items))):
         L.check(L.lib().b200rec_collate_interacted(_ptr(user_rows), B, _ptr(list_ptr), _ptr(list_item), _ptr(list_val), int(n_items), _ptr(rated),
                                                    _ptr(rp), _ptr(col), _ptr(val), _ptr(counts), _ptr(ws), wsb, _stream()), 'collate_interacted')
     return rated, rp, col, val, counts
@@ -1112,7 +1143,7 @@ def sample_negatives_raw(sample_rows, neg_ptr, neg_item, neg_rating, *, w, seed,
     out = torch.empty(B, dtype=torch.int64, device=dev)
     pos = torch.empty(B, dtype=torch.int32, device=dev)
     u = torch.empty(B, dtype=torch.float64, device=dev) if return_uniforms else None
-    with torch.cuda.device(dev), _timed('sample_negatives', (B,)):
+    with _on(dev), _timed('sample_negatives', (B,)):
         L.check(L.lib().b200rec_sample_negatives(_ptr(sample_rows), B, _ptr(neg_ptr), _ptr(neg_item), _ptr(neg_rating), float(w),
                                                  int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), _ptr(out), _ptr(pos), _ptr(u), _stream()),
                 'sample_negatives')
@@ -1154,7 +1185,7 @@ def allpairs_pack(W2, b2, w3, b3, H1p, mode):
     if nbytes == 0:
         raise NotImplementedError(f'all-pairs kernel: first hidden width {H1} > 256')
     buf = torch.empty(nbytes, dtype=torch.uint8, device=W2.device)
-    with torch.cuda.device(W2.device):
+    with _on(W2.device):
         L.check(lib.b200rec_allpairs_pack(_ptr(w2p), H1p, H2, H1p, mode, _ptr(buf), nbytes, _stream()), 'allpairs_pack')
     buf = AllPairsWeights(buf, epi, H2)
     if len(_ap_cache) > 32:
@@ -1188,7 +1219,7 @@ def allpairs_topk_raw(A, B, packed, mode, k, *, return_scores=False, seen=None, 
         sp, si = seen[0].contiguous().int(), seen[1].contiguous().int()
         if sp.numel() != nU + 1:
             raise ValueError('allpairs: seen_ptr must have nU + 1 entries')
-    with torch.cuda.device(dev), _timed('allpairs', (nU, nI, H1p, k, mode)):
+    with _on(dev), _timed('allpairs', (nU, nI, H1p, k, mode)):
         L.check(lib.b200rec_allpairs_topk(_ptr(A), _ptr(B), nU, nI, H1p, _ptr(packed.buf), _ptr(packed.epi), packed.H2, mode, k, n_splits, _ptr(sp), _ptr(si),
                                           _ptr(scores), nI, _ptr(val), _ptr(idx), _ptr(ws), wsb, _stream()), 'allpairs_topk')
     return val, idx, scores
@@ -1219,7 +1250,7 @@ def allpairs_relu_dot_raw(A, B, w2, b2, k, *, return_scores=False, seen=None, n_
         sp, si = seen[0].contiguous().int(), seen[1].contiguous().int()
         if sp.numel() != nU + 1:
             raise ValueError('allpairs: seen_ptr must have nU + 1 entries')
-    with torch.cuda.device(dev), _timed('allpairs_relu_dot', (nU, nI, H1p, k)):
+    with _on(dev), _timed('allpairs_relu_dot', (nU, nI, H1p, k)):
         L.check(lib.b200rec_allpairs_relu_dot_topk(_ptr(A), _ptr(B), nU, nI, H1p, _ptr(w2p), b2v, k, n_splits, _ptr(sp), _ptr(si), _ptr(scores), nI,
                                                    _ptr(val), _ptr(idx), _ptr(ws), wsb, _stream()), 'allpairs_relu_dot_topk')
     return val, idx, scores
