@@ -71,11 +71,12 @@ class RankingDataset(_Hooks, Dataset):
         self.w = 0.0
 
     def _negative_sampling_probs(self, negative_ratings: np.ndarray, type='sum_dynamic'):
+        # (the builtin `sum` — left to right — as in the reference, not numpy's pairwise `.sum()`: the same p to the last bit)
         if type == 'sum':
-            return negative_ratings / negative_ratings.sum()
+            return negative_ratings / sum(negative_ratings)
         if type == 'sum_dynamic':
             boosted = negative_ratings ** self.w
-            return boosted / boosted.sum()
+            return boosted / sum(boosted)
         if type == 'softmax':
             return torch.softmax(torch.as_tensor(negative_ratings, dtype=torch.float32), dim=0).numpy()
         return None

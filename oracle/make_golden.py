@@ -224,14 +224,56 @@ def golden_collate(ref):
           rated_items_idx=rated_idx, candidate_items=cand, rated_items=rated, user_matrix=um)
 
 
+def golden_ranking(ref):
+    """RankingDataset.__getitem__ (datasets/base.py:57-78: np.random.choice with the 'sum_dynamic' weights) and BPR_loss (:97-98) of the
+    unmodified reference on a hand-built frame (its __init__ only reads .h5).  Per access the legacy generator is seeded, the uniform it would
+    produce next is recorded, it is re-seeded and the reference draws: the fixture holds (uniform, drawn negative) pairs."""
+    import importlib
+    base = importlib.import_module('neural_collaborative_filtering.datasets.base')
+    rng = np.random.default_rng(77)
+    n = 40
+    rows = []
+    for k in range(n):
+        m = int(rng.integers(1, 80))
+        ids = rng.choice(50_000, size=m, replace=False)
+        r = rng.integers(0 if k % 6 == 0 else 1, 11, m) * 0.5
+        if not r.any():
+            r[0] = 2.0
+        rows.append({'userId': int(rng.integers(0, 300)), 'positive_movieId': int(rng.integers(0, 50_000)),
+                     'negative_movieIds': ids, 'negative_ratings': r})
+    frame = pd.DataFrame(rows)
+    ds = object.__new__(base.RankingDataset)
+    ds.samples, ds.loss_fn = frame, base.BPR_loss
+    ptr = np.concatenate([[0], np.cumsum([len(x) for x in frame['negative_movieIds']])])
+    access = rng.integers(0, n, 600)
+    out = {}
+    for w in (0.0, 1.0, 2.5):
+        ds.w = w
+        us, negs = [], []
+        for t, item in enumerate(access):
+            np.random.seed(1000 + t)
+            us.append(np.random.random_sample())
+            np.random.seed(1000 + t)
+            user, pos, neg = ds[int(item)]
+            assert user == frame['userId'][int(item)] and pos == frame['positive_movieId'][int(item)]
+            negs.append(int(neg))
+        tag = str(w).replace('.', '_')
+        out[f'uniform_w{tag}'], out[f'negative_w{tag}'] = np.array(us), np.array(negs, dtype=np.int64)
+    a, b = torch.randn(50, 1), torch.randn(50, 1)
+    _save('ranking_sampling', neg_ptr=ptr, neg_item=np.concatenate(list(frame['negative_movieIds'])).astype(np.int64),
+          neg_rating=np.concatenate(list(frame['negative_ratings'])).astype(np.float64), user=frame['userId'].to_numpy(),
+          positive=frame['positive_movieId'].to_numpy(), access=access, bpr_pos=a, bpr_neg=b, bpr_loss=ds.calculate_loss(a, b), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)      # deterministic reduction order for the stored fp32 outputs
     ref = ref_loader.load()
-    golden_basic(ref)
-    golden_attention(ref)
-    golden_graph(ref)
-    golden_collate(ref)
+    only = sys.argv[1:]           # e.g. `python -m oracle.make_golden ranking`: regenerate one family, leave the other fixtures untouched
+    for name, fn in (('basic', golden_basic), ('attention', golden_attention), ('graph', golden_graph), ('collate', golden_collate),
+                     ('ranking', golden_ranking)):
+        if not only or name in only:
+            fn(ref)
 
 
 if __name__ == '__main__':

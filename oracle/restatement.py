@@ -364,3 +364,26 @@ def collate_interacted_items(batch_users: np.ndarray, batch_items: np.ndarray, r
             um[b, cols] = rated_rating[row_ptr[u]:row_ptr[u + 1]] - (mean_rating[u] + 2.5) / 2
     return (rated_ids, profiles[batch_items].astype(np.float32), profiles[rated_ids].astype(np.float32),
             um.astype(np.float32))
+
+
+# --------------------------------------------------------------------------------------------------
+# f-4  RankingDataset negative sampling — neural_collaborative_filtering/datasets/base.py:57-78, BPR loss :97-98
+# --------------------------------------------------------------------------------------------------
+def negative_sampling_probs(negative_ratings: np.ndarray, w: float) -> np.ndarray:
+    """'sum_dynamic' (:62-66): p = r^w / sum(r^w) with the builtin `sum` of the reference (left-to-right float64)."""
+    boosted = np.asarray(negative_ratings, dtype=np.float64) ** w
+    return boosted / sum(boosted)
+
+
+def choice_given_uniform(p: np.ndarray, u: float) -> int:
+    """What `np.random.choice(ids, p=p)` (:76) does with ONE uniform of its stream (numpy/random/mtrand.pyx `choice`, branch `p is not None`,
+    size None): `cdf = p.cumsum(); cdf /= cdf[-1]; idx = cdf.searchsorted(uniform, side='right')`.  tests/test_oracle_sampling.py pins this
+    to the real np.random.choice under a seeded legacy generator."""
+    cdf = np.asarray(p, dtype=np.float64).cumsum()
+    cdf /= cdf[-1]
+    return int(cdf.searchsorted(u, side='right'))
+
+
+def bpr_loss(out_pos: torch.Tensor, out_neg: torch.Tensor) -> torch.Tensor:
+    """:97-98"""
+    return torch.sum(-torch.log(torch.sigmoid(out_pos - out_neg)))
