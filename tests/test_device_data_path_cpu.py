@@ -115,3 +115,32 @@ def test_negative_sampler_uploads_the_lists_as_csr():
         assert 'CUDA' in str(e)
     else:
         raise AssertionError('sampling on CPU tensors must fail loudly')
+
+
+def test_k6_algorithm_equals_host_collate_on_random_ragged_batches():
+    """property check of the three phases against `collate_csr` (itself bit-exact against the reference golden): random catalogues around the
+    32-bit word boundaries of the bitmap, empty lists, exact-zero centred ratings, repeated users"""
+    rng = np.random.default_rng(123)
+    for case in range(60):
+        n_items = int(rng.choice([1, 31, 32, 33, 64, 100, 1000]))
+        n_users = int(rng.integers(1, 12))
+        ptr, items, ratings = [0], [], []
+        for u in range(n_users):
+            k = int(rng.integers(0, min(n_items, 40) + 1))
+            it = np.sort(rng.choice(n_items, size=k, replace=False))
+            r = rng.integers(1, 11, k) * 0.5
+            if u % 3 == 1:
+                r[:] = 2.5                                                   # mean 2.5: centred ratings exactly 0.0
+            items.append(it)
+            ratings.append(r)
+            ptr.append(ptr[-1] + k)
+        items = np.concatenate(items).astype(np.int64) if ptr[-1] else np.zeros(0, np.int64)
+        ratings = np.concatenate(ratings).astype(np.float64) if ptr[-1] else np.zeros(0, np.float64)
+        p = DeviceCollateProvider(np.arange(n_items), np.zeros((n_items, 2), np.float32), np.arange(n_users), np.asarray(ptr, np.int64), items, ratings,
+                                  device='cpu')
+        batch = rng.integers(0, n_users, int(rng.integers(1, 20)))
+        rated, row_ptr, col, val = _k6_numpy(batch, p.d_list_ptr.numpy(), p.d_list_item.numpy(), p.d_list_val.numpy(), n_items)
+        rated_h, um_h = p.collate_csr(batch)
+        assert np.array_equal(rated, rated_h), case
+        assert np.array_equal(row_ptr, um_h.row_ptr.numpy()) and np.array_equal(col, um_h.col.numpy()), case
+        assert np.array_equal(val.view(np.int32), um_h.val.numpy().view(np.int32)), case
