@@ -69,3 +69,15 @@ def test_product_does_not_import_oracle():
             if f.endswith('.py'):
                 txt = open(os.path.join(d, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f'{f} imports the oracle'
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/b200rec.h must compile as C99 with no C++ / CUDA / torch types in any signature."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'b200rec.h')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', header], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
